@@ -1,0 +1,204 @@
+/*
+ * b200splat.h -- C ABI of libb200splat.so, the B200 (sm_100a) Gaussian-splatting rasterizer.
+ *
+ * Drop-in boundary for the hot path of lizhiqi49/threestudio-3dgs.  The reference calls two
+ * un-vendored pip packages (README.md:17-20):
+ *     from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+ *                                   (renderer/diff_gaussian_rasterizer.py:8-11, :83-131)
+ *     from simple_knn._C import distCUDA2        (geometry/gaussian_base.py:25, :434-437)
+ * whose pybind layer binds rasterize_gaussians / rasterize_gaussians_backward / mark_visible /
+ * distCUDA2 [UPSTREAM-RECALL: ext.cpp, rasterize_points.cu of ashawkey/diff-gaussian-rasterization;
+ * ext.cpp of DSaurus/simple-knn].  Each entry point below names the binding it replaces.
+ *
+ * Conventions: plain pointers and sizes only (no torch / C++ types); every pointer marked "device"
+ * is a CUDA device pointer owned by the caller (PyTorch's caching allocator in the shipped Python
+ * host side); every call takes the cudaStream_t to launch on; return value 0 = ok, < 0 = error
+ * (b200splat_last_error() gives the message; no exceptions cross the boundary).  All floating
+ * point is fp32.  Matrices are the reference's transposed (row-vector) 4x4s, 16 floats,
+ * (world_view_transform, full_proj_transform: renderer/gaussian_batch_renderer.py:39-49).
+ */
+#ifndef B200SPLAT_H
+#define B200SPLAT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SPLAT_ABI_VERSION 1
+
+#define B200SPLAT_OK 0
+#define B200SPLAT_ERR_INVALID -1   /* bad argument                                  */
+#define B200SPLAT_ERR_CUDA -2      /* a CUDA runtime call or kernel launch failed   */
+#define B200SPLAT_ERR_NOMEM -3     /* a caller-provided buffer is too small         */
+
+typedef void* b200splat_stream; /* cudaStream_t */
+
+/* Growable-buffer callback: replaces upstream's std::function<char*(size_t)> resizeFunctional
+ * (rasterize_points.cu).  Must return a device pointer to >= bytes bytes, 256-byte aligned,
+ * that stays valid until the matching backward has run; NULL = failure. */
+typedef void* (*b200splat_alloc_fn)(void* user, size_t bytes);
+
+/* GaussianRasterizationSettings (renderer/diff_gaussian_rasterizer.py:83-96). */
+typedef struct b200splat_camera {
+    int32_t image_height;
+    int32_t image_width;
+    float tanfovx;
+    float tanfovy;
+    float scale_modifier;
+    int32_t sh_degree;        /* active degree; clamped to what M coefficients hold */
+    int32_t prefiltered;
+    int32_t debug;            /* !=0: synchronise + check after every kernel        */
+    const float* bg;          /* device, 3  */
+    const float* viewmatrix;  /* device, 16 */
+    const float* projmatrix;  /* device, 16 */
+    const float* campos;      /* device, 3  */
+} b200splat_camera;
+
+/* ---- buffer sizing (bytes) --------------------------------------------------------------- */
+size_t b200splat_geom_bytes(int32_t P);                  /* per-Gaussian state kept for backward */
+size_t b200splat_image_bytes(int32_t H, int32_t W);      /* tile ranges + n_contrib + final T    */
+size_t b200splat_binning_bytes(int64_t num_rendered);    /* key/value ping-pong + sort scratch   */
+size_t b200splat_backward_scratch_bytes(int32_t P);      /* packed 2-D stage gradients           */
+
+/* ---- forward: replaces rasterize_gaussians (RasterizeGaussiansCUDA) ------------------------
+ * Inputs (device): means3D (P,3); shs (P,M,3) or NULL; colors_precomp (P,3) or NULL; opacities
+ * (P,1); scales (P,3) + rotations (P,4) (r,x,y,z) or cov3D_precomp (P,6).  Outputs (device):
+ * out_color (3,H,W), out_depth (1,H,W), out_alpha (1,H,W), radii (P) int32.
+ * geom/image buffers are caller-allocated (sizes above).  The binning buffer depends on
+ * num_rendered = sum(tiles_touched), known only after the scan: either pass binning_buffer with
+ * binning_bytes large enough, or pass binning_alloc and the library calls it once with the exact
+ * size (one stream synchronise, as upstream).  *num_rendered_out (host) receives num_rendered,
+ * *binning_out (host) the binning pointer actually used. */
+typedef struct b200splat_forward_args {
+    b200splat_camera cam;
+    int32_t P;
+    int32_t M; /* SH coefficients per channel present in shs (0 when shs == NULL) */
+    const float* means3D;
+    const float* shs;
+    const float* colors_precomp;
+    const float* opacities;
+    const float* scales;
+    const float* rotations;
+    const float* cov3D_precomp;
+    float* out_color;
+    float* out_depth;
+    float* out_alpha;
+    int32_t* radii;
+    void* geom_buffer;
+    size_t geom_bytes;
+    void* image_buffer;
+    size_t image_bytes;
+    void* binning_buffer;
+    size_t binning_bytes;
+    b200splat_alloc_fn binning_alloc;
+    void* alloc_user;
+    b200splat_stream stream;
+    int64_t* num_rendered_out;
+    void** binning_out;
+} b200splat_forward_args;
+
+int b200splat_forward(const b200splat_forward_args* args);
+
+/* ---- backward: replaces rasterize_gaussians_backward (RasterizeGaussiansBackwardCUDA) -------
+ * Takes the forward's inputs, radii and the three buffers unchanged (they are read
+ * only, so backward may run twice on one forward: system/gaussian_splatting.py:129,137-138),
+ * plus dL/dout_color (3,H,W), dL/dout_depth (1,H,W), dL/dout_alpha (1,H,W) (contiguous; any may
+ * be NULL = zeros).  Writes dense gradients for every Gaussian (zeros where radii == 0):
+ * dL_dmeans3D (P,3), dL_dmeans2D (P,3; NDC units, z = 0; geometry/gaussian_base.py:815-819 reads
+ * it), dL_dopacity (P,1), and, when the matching input was given, dL_dshs (P,M,3),
+ * dL_dcolors (P,3), dL_dscales (P,3), dL_drotations (P,4), dL_dcov3D (P,6).  When accumulate != 0
+ * the results are ADDED to the output tensors instead of overwriting them (multi-view batches).
+ */
+typedef struct b200splat_backward_args {
+    b200splat_camera cam;
+    int32_t P;
+    int32_t M;
+    int64_t num_rendered;
+    const float* means3D;
+    const float* shs;
+    const float* colors_precomp;
+    const float* opacities;
+    const float* scales;
+    const float* rotations;
+    const float* cov3D_precomp;
+    const int32_t* radii;
+    const float* out_alpha; /* accepted for signature parity with upstream, not read: the exact final
+                               transmittance is kept in image_buffer (1 - alpha cancels catastrophically) */
+    const void* geom_buffer;
+    const void* binning_buffer;
+    const void* image_buffer;
+    const float* dL_dout_color;
+    const float* dL_dout_depth;
+    const float* dL_dout_alpha;
+    float* dL_dmeans3D;
+    float* dL_dmeans2D;
+    float* dL_dshs;
+    float* dL_dcolors;
+    float* dL_dopacity;
+    float* dL_dscales;
+    float* dL_drotations;
+    float* dL_dcov3D;
+    void* scratch;
+    size_t scratch_bytes;
+    int32_t accumulate;
+    b200splat_stream stream;
+} b200splat_backward_args;
+
+int b200splat_backward(const b200splat_backward_args* args);
+
+/* ---- mark_visible: replaces markVisible (GaussianRasterizer.markVisible) ------------------- */
+int b200splat_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
+                           const float* projmatrix, uint8_t* present, b200splat_stream stream);
+
+/* ---- distCUDA2: replaces simple_knn._C.distCUDA2 (geometry/gaussian_base.py:434-437) ---------
+ * out[i] = mean squared distance from point i to its 3 nearest other points (exact).
+ * workspace: >= b200splat_dist2_workspace_bytes(P) device bytes. */
+size_t b200splat_dist2_workspace_bytes(int32_t P);
+int b200splat_dist2(int32_t P, const float* points, float* out, void* workspace,
+                    size_t workspace_bytes, b200splat_stream stream);
+
+/* ---- stage-level entry points (parity tests and reuse) ------------------------------------- */
+/* Stable LSD radix sort of (u64 key, u32 value) pairs over key bits [0, end_bit); onesweep.
+ * workspace >= b200splat_sort_workspace_bytes(n).  keys_alt/vals_alt are ping-pong storage;
+ * *result_in_alt (host) is set to 1 when the sorted data ended up in the alt arrays. */
+size_t b200splat_sort_workspace_bytes(int64_t n);
+int b200splat_sort_pairs(int64_t n, int32_t end_bit, uint64_t* keys, uint32_t* vals,
+                         uint64_t* keys_alt, uint32_t* vals_alt, void* workspace,
+                         size_t workspace_bytes, int32_t* result_in_alt, b200splat_stream stream);
+/* Inclusive prefix sum of n uint32 (decoupled look-back). workspace >= ..._scan_workspace_bytes. */
+size_t b200splat_scan_workspace_bytes(int64_t n);
+int b200splat_inclusive_scan_u32(int64_t n, const uint32_t* in, uint32_t* out, void* workspace,
+                                 size_t workspace_bytes, b200splat_stream stream);
+
+/* Views into the buffers of a finished forward (device pointers into the caller's buffers), for
+ * the bit-exact parity checks: tiles_touched (P) u32, point_offsets (P) u32, depths (P) f32,
+ * sorted keys (R) u64, point_list (R) u32, ranges (T,2) u32, n_contrib (H*W) u32. */
+typedef struct b200splat_forward_views {
+    const uint32_t* tiles_touched;
+    const uint32_t* point_offsets;
+    const float* depths;
+    const float* gauss2d; /* (P,12): x, y, conic a, conic b | conic c, opacity, depth, r | g, b, -, - */
+    const float* cov3D;   /* (P,6) */
+    const uint64_t* keys_sorted;
+    const uint32_t* point_list;
+    const uint32_t* ranges;
+    const uint32_t* n_contrib;
+} b200splat_forward_views;
+
+int b200splat_forward_views_get(int32_t P, int32_t H, int32_t W, int64_t num_rendered,
+                                const void* geom_buffer, const void* binning_buffer,
+                                const void* image_buffer, b200splat_forward_views* out);
+
+/* ---- misc ----------------------------------------------------------------------------------- */
+int b200splat_abi_version(void);
+const char* b200splat_last_error(void);
+/* Number of kernels this library launched since process start (all streams). */
+uint64_t b200splat_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SPLAT_H */

@@ -1,0 +1,237 @@
+"""GPU parity: CUDA path (through the drop-in Python surface -> C ABI) vs the CPU oracle.
+
+Bars (BASELINE.json north_star): radii, tiles_touched, sorted keys, tile ranges bit-exact;
+image / depth / alpha max-abs <= 1e-4; parameter gradients <= 1e-3 relative.
+"""
+import pytest
+import torch
+
+from b200splat import scenes
+from oracle import torch_oracle as O
+from oracle.knn import dist2_oracle
+from util import borderline_pixels, cuda_settings, oracle_settings, rel_err
+
+pytestmark = pytest.mark.gpu
+
+IMG_TOL = 1e-4
+GRAD_TOL = 1e-3
+
+
+def _run_cuda(sc, s, *, colors_precomp=None, cov3D=None, shs=None, grads=None, dev="cuda"):
+    from b200splat import ops
+    from diff_gaussian_rasterization import GaussianRasterizer
+    rs = cuda_settings(s, dev)
+    req = lambda t: None if t is None else t.to(dev).clone().requires_grad_(True)
+    m3 = req(sc.means3D)
+    m2 = torch.zeros_like(m3, requires_grad=True)
+    m2n = m2 + 0
+    m2n.retain_grad()
+    op = req(sc.opacities)
+    sh = req(shs if shs is not None else (None if colors_precomp is not None else sc.shs))
+    cp = req(colors_precomp)
+    scl, rot, c3 = (None, None, req(cov3D)) if cov3D is not None else (req(sc.scales), req(sc.rotations), None)
+    color, radii, depth, alpha = GaussianRasterizer(raster_settings=rs)(
+        means3D=m3, means2D=m2n, shs=sh, colors_precomp=cp, opacities=op, scales=scl, rotations=rot,
+        cov3D_precomp=c3)
+    res = dict(color=color, radii=radii, depth=depth, alpha=alpha)
+    if grads is not None:
+        gc, gd, ga = (g.to(dev) for g in grads)
+        loss = (color * gc).sum() + (depth * gd).sum() + (alpha * ga).sum()
+        loss.backward()
+        res["grads"] = dict(means3D=m3.grad, means2D=m2n.grad, opacities=op.grad,
+                            shs=None if sh is None else sh.grad, colors_precomp=None if cp is None else cp.grad,
+                            scales=None if scl is None else scl.grad, rotations=None if rot is None else rot.grad,
+                            cov3D_precomp=None if c3 is None else c3.grad)
+    return res
+
+
+def _run_oracle(sc, s, *, colors_precomp=None, cov3D=None, shs=None, grads=None):
+    shs = shs if shs is not None else (None if colors_precomp is not None else sc.shs)
+    scl, rot = (None, None) if cov3D is not None else (sc.scales, sc.rotations)
+    out, pre, binned = O.rasterize_forward(sc.means3D, None, shs, colors_precomp, sc.opacities, scl, rot, cov3D, s)
+    res = dict(out=out, pre=pre, binned=binned)
+    if grads is not None:
+        res["grads"] = O.rasterize_backward((sc.means3D, None, shs, colors_precomp, sc.opacities, scl, rot, cov3D),
+                                            s, pre, binned, out, *grads)
+    return res
+
+
+def _check_forward(cu, orc, s, allow_borderline=True):
+    out, pre, binned = orc["out"], orc["pre"], orc["binned"]
+    assert torch.equal(cu["radii"].cpu(), pre["radii"]), "radii not bit-exact"
+    bad = borderline_pixels(pre, binned, s, out) if allow_borderline else torch.zeros_like(out["alpha"][0]).bool()
+    frac = float(bad.float().mean())
+    assert frac < 0.01, f"too many borderline pixels excluded: {frac}"
+    keep = ~bad
+    for name, ref in (("color", out["color"]), ("depth", out["depth"]), ("alpha", out["alpha"])):
+        err = ((cu[name].cpu() - ref).abs() * keep[None]).max().item()
+        assert err <= IMG_TOL, f"{name} max-abs {err} > {IMG_TOL}"
+
+
+def _check_grads(cu, orc, tol=GRAD_TOL):
+    for k, ref in orc["grads"].items():
+        if k == "stage" or ref is None:
+            continue
+        got = cu["grads"][k]
+        assert got is not None, f"missing grad {k}"
+        assert got.shape == ref.shape, (k, got.shape, ref.shape)
+        e = rel_err(got, ref)
+        assert e <= tol, f"grad {k}: rel err {e} > {tol}"
+
+
+def _scene(P, deg, H, W, seed, r0=0.8, scale_mul=1.0):
+    sc = scenes.make_scene(P, deg, r0, seed=seed)
+    if scale_mul != 1.0:
+        sc = sc._replace(scales=sc.scales * scale_mul)
+    cam = scenes.sds_cameras(1, H, W, seed=seed + 100)[0]
+    return sc, cam
+
+
+def test_sort_pairs_matches_stable_sort():
+    from b200splat import ops
+    g = torch.Generator().manual_seed(0)
+    for n, bits in ((1, 64), (37, 64), (4096, 43), (4097, 39), (100_003, 45), (1_000_000, 43), (50_000, 8)):
+        keys = torch.randint(0, 2 ** 62, (n,), generator=g, dtype=torch.int64)
+        if bits < 64:
+            keys = keys & ((1 << bits) - 1)
+        # many duplicates in the upper bits (tile ids) and in the depth exponent byte
+        keys = keys & ~(0xF << 28)
+        vals = torch.arange(n, dtype=torch.int32)
+        ks, vs = ops.sort_pairs(keys.cuda(), vals.cuda(), end_bit=bits)
+        rk, perm = torch.sort(keys, stable=True)
+        assert torch.equal(ks.cpu(), rk), (n, bits)
+        assert torch.equal(vs.cpu(), vals[perm]), (n, bits)
+
+
+def test_inclusive_scan():
+    from b200splat import ops
+    g = torch.Generator().manual_seed(1)
+    for n in (1, 7, 2048, 2049, 1_000_003):
+        x = torch.randint(0, 50, (n,), generator=g, dtype=torch.int32)
+        y = ops.inclusive_scan_u32(x.cuda())
+        assert torch.equal(y.cpu(), torch.cumsum(x, 0).to(torch.int32)), n
+
+
+@pytest.mark.parametrize("P,deg,H,W,seed", [
+    (16384, 0, 128, 128, 1235),      # BASELINE configs[0] shape
+    (4000, 3, 96, 80, 7),            # SH degree 3, non-square, W not a multiple of 16
+    (3000, 1, 50, 70, 8),
+    (3000, 2, 64, 64, 9),
+])
+def test_forward_backward_parity(P, deg, H, W, seed):
+    from b200splat import ops
+    sc, cam = _scene(P, deg, H, W, seed)
+    s = oracle_settings(cam, deg)
+    grads = scenes.pixel_grads(H, W, seed + 1)
+    orc = _run_oracle(sc, s, grads=grads)
+    cu = _run_cuda(sc, s, grads=grads)
+    _check_forward(cu, orc, s)
+    _check_grads(cu, orc)
+
+
+def test_intermediates_bit_exact():
+    """tiles_touched, point_offsets, depth bits, sorted keys, point list and tile ranges."""
+    from b200splat import ops
+    sc, cam = _scene(16384, 0, 128, 128, 1235)
+    s = oracle_settings(cam, 0)
+    orc = _run_oracle(sc, s)
+    camc = ops.make_cam(cuda_settings(s), "cuda")
+    d = lambda t: t.cuda().contiguous()
+    color, radii, depth, alpha, st = ops.forward(camc, d(sc.means3D), d(sc.shs), None, d(sc.opacities),
+                                                 d(sc.scales), d(sc.rotations), None)
+    v = {k: t.cpu() for k, t in ops.forward_views(camc, st).items()}
+    pre, binned = orc["pre"], orc["binned"]
+    assert st.num_rendered == binned["num_rendered"]
+    assert torch.equal(radii.cpu(), pre["radii"])
+    assert torch.equal(v["tiles_touched"], pre["tiles_touched"])
+    assert torch.equal(v["point_offsets"], binned["point_offsets"])
+    vis = pre["visible"]
+    assert torch.equal(v["depths"][vis].view(torch.int32), pre["depth"][vis].contiguous().view(torch.int32))
+    assert torch.equal(v["keys_sorted"], binned["keys_sorted"])
+    assert torch.equal(v["point_list"], binned["point_list"])
+    assert torch.equal(v["ranges"], binned["ranges"])
+    nc = orc["out"]["n_contrib"]
+    assert (v["n_contrib"] == nc).float().mean() > 0.999
+
+
+def test_colors_precomp_cov3d_precomp_and_bg():
+    sc, cam = _scene(3000, 0, 64, 64, 21)
+    s = oracle_settings(cam, 0, bg=(0.0, 0.0, 0.0))
+    g = torch.Generator().manual_seed(5)
+    cp = torch.rand(3000, 3, generator=g)
+    c0, c1, c2, c3, c4, c5 = O.cov3d_from_scale_rot(sc.scales, sc.rotations, 1.0)
+    cov = torch.stack([c0, c1, c2, c3, c4, c5], -1).contiguous()
+    grads = scenes.pixel_grads(64, 64, 22)
+    orc = _run_oracle(sc, s, colors_precomp=cp, cov3D=cov, grads=grads)
+    cu = _run_cuda(sc, s, colors_precomp=cp, cov3D=cov, grads=grads)
+    _check_forward(cu, orc, s)
+    _check_grads(cu, orc)
+
+
+def test_degenerate_sh_tensor_with_high_degree():
+    """(P,1,3) 'SH' with sh_degree 3 (renderer/diff_gaussian_rasterizer_shading.py:178-187)."""
+    sc, cam = _scene(2000, 0, 64, 64, 31)
+    s = oracle_settings(cam, 3)
+    grads = scenes.pixel_grads(64, 64, 32)
+    orc = _run_oracle(sc, s, shs=sc.shs[:, :1].contiguous(), grads=grads)
+    cu = _run_cuda(sc, s, shs=sc.shs[:, :1].contiguous(), grads=grads)
+    _check_forward(cu, orc, s)
+    _check_grads(cu, orc)
+
+
+def test_offscreen_and_behind_camera():
+    """FOV clamp gradient convention + near cull + off-screen rectangles."""
+    sc, cam = _scene(3000, 1, 64, 64, 41, r0=3.0, scale_mul=1.0)
+    s = oracle_settings(cam, 1)
+    grads = scenes.pixel_grads(64, 64, 42)
+    orc = _run_oracle(sc, s, grads=grads)
+    assert int((orc["pre"]["radii"] == 0).sum()) > 0
+    cu = _run_cuda(sc, s, grads=grads)
+    _check_forward(cu, orc, s)
+    _check_grads(cu, orc)
+    culled = (orc["pre"]["radii"] == 0)
+    for k, g in cu["grads"].items():
+        if g is not None:
+            assert float(g.cpu()[culled].abs().max()) == 0.0, f"culled Gaussians must get zero {k} grad"
+
+
+def test_empty_and_double_backward():
+    from diff_gaussian_rasterization import GaussianRasterizer
+    sc, cam = _scene(1000, 0, 32, 32, 51)
+    s = oracle_settings(cam, 0)
+    rs = cuda_settings(s)
+    z = lambda *sh: torch.zeros(*sh, device="cuda")
+    color, radii, depth, alpha = GaussianRasterizer(raster_settings=rs)(
+        means3D=z(0, 3), means2D=z(0, 3), shs=z(0, 1, 3), colors_precomp=None, opacities=z(0, 1),
+        scales=z(0, 3), rotations=z(0, 4), cov3D_precomp=None)
+    assert color.shape == (3, 32, 32) and float((color - 1).abs().max()) == 0 and radii.numel() == 0
+    # two backward passes over one forward (system/gaussian_splatting.py:129,137-138)
+    m3 = sc.means3D.cuda().requires_grad_(True)
+    m2 = torch.zeros_like(m3, requires_grad=True)
+    out = GaussianRasterizer(raster_settings=rs)(
+        means3D=m3, means2D=m2, shs=sc.shs.cuda(), colors_precomp=None, opacities=sc.opacities.cuda(),
+        scales=sc.scales.cuda(), rotations=sc.rotations.cuda(), cov3D_precomp=None)
+    out[0].sum().backward(retain_graph=True)
+    g1 = m3.grad.clone()
+    out[0].sum().backward()
+    assert rel_err(m3.grad, 2 * g1) < 1e-5
+    # outputs are independent tensors the caller may write into
+    out[2][out[3] < 0.5] = 0.0
+    with pytest.raises(Exception):
+        GaussianRasterizer(raster_settings=rs)(means3D=m3, means2D=m2, shs=None, colors_precomp=None,
+                                               opacities=sc.opacities.cuda(), scales=sc.scales.cuda(),
+                                               rotations=sc.rotations.cuda(), cov3D_precomp=None)
+
+
+def test_dist2():
+    from simple_knn._C import distCUDA2
+    g = torch.Generator().manual_seed(3)
+    for P in (4096, 5, 20000, 40000):
+        pts = torch.randn(P, 3, generator=g) * torch.tensor([1.0, 0.5, 2.0])
+        got = distCUDA2(pts.cuda()).cpu()
+        ref = dist2_oracle(pts)
+        assert rel_err(got, ref) < 1e-5, P
+    z = distCUDA2(torch.zeros(4096, 3, device="cuda"))     # checkpoint-load path: identical points
+    assert float(z.abs().max()) == 0.0
+    z = distCUDA2(torch.zeros(20000, 3, device="cuda"))
+    assert float(z.abs().max()) == 0.0

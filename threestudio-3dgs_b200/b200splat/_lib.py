@@ -1,0 +1,123 @@
+"""ctypes binding of libb200splat.so (C ABI in include/b200splat.h).
+
+The product path has NO fallback: if the shared library is missing or does not load, importing this
+module raises -- build it with ``python threestudio-3dgs_b200/b200splat/build.py`` (or
+``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = Path(os.environ.get("B200SPLAT_LIB", _HERE / "libb200splat.so"))
+
+ABI_VERSION = 1
+
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
+
+
+class Camera(C.Structure):
+    _fields_ = [
+        ("image_height", C.c_int32), ("image_width", C.c_int32),
+        ("tanfovx", C.c_float), ("tanfovy", C.c_float), ("scale_modifier", C.c_float),
+        ("sh_degree", C.c_int32), ("prefiltered", C.c_int32), ("debug", C.c_int32),
+        ("bg", C.c_void_p), ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("campos", C.c_void_p),
+    ]
+
+
+class ForwardArgs(C.Structure):
+    _fields_ = [
+        ("cam", Camera), ("P", C.c_int32), ("M", C.c_int32),
+        ("means3D", C.c_void_p), ("shs", C.c_void_p), ("colors_precomp", C.c_void_p),
+        ("opacities", C.c_void_p), ("scales", C.c_void_p), ("rotations", C.c_void_p),
+        ("cov3D_precomp", C.c_void_p),
+        ("out_color", C.c_void_p), ("out_depth", C.c_void_p), ("out_alpha", C.c_void_p), ("radii", C.c_void_p),
+        ("geom_buffer", C.c_void_p), ("geom_bytes", C.c_size_t),
+        ("image_buffer", C.c_void_p), ("image_bytes", C.c_size_t),
+        ("binning_buffer", C.c_void_p), ("binning_bytes", C.c_size_t),
+        ("binning_alloc", ALLOC_FN), ("alloc_user", C.c_void_p),
+        ("stream", C.c_void_p),
+        ("num_rendered_out", C.POINTER(C.c_int64)), ("binning_out", C.POINTER(C.c_void_p)),
+    ]
+
+
+class BackwardArgs(C.Structure):
+    _fields_ = [
+        ("cam", Camera), ("P", C.c_int32), ("M", C.c_int32), ("num_rendered", C.c_int64),
+        ("means3D", C.c_void_p), ("shs", C.c_void_p), ("colors_precomp", C.c_void_p),
+        ("opacities", C.c_void_p), ("scales", C.c_void_p), ("rotations", C.c_void_p),
+        ("cov3D_precomp", C.c_void_p), ("radii", C.c_void_p), ("out_alpha", C.c_void_p),
+        ("geom_buffer", C.c_void_p), ("binning_buffer", C.c_void_p), ("image_buffer", C.c_void_p),
+        ("dL_dout_color", C.c_void_p), ("dL_dout_depth", C.c_void_p), ("dL_dout_alpha", C.c_void_p),
+        ("dL_dmeans3D", C.c_void_p), ("dL_dmeans2D", C.c_void_p), ("dL_dshs", C.c_void_p),
+        ("dL_dcolors", C.c_void_p), ("dL_dopacity", C.c_void_p), ("dL_dscales", C.c_void_p),
+        ("dL_drotations", C.c_void_p), ("dL_dcov3D", C.c_void_p),
+        ("scratch", C.c_void_p), ("scratch_bytes", C.c_size_t),
+        ("accumulate", C.c_int32), ("stream", C.c_void_p),
+    ]
+
+
+class ForwardViews(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "tiles_touched", "point_offsets", "depths", "gauss2d", "cov3D", "keys_sorted", "point_list",
+        "ranges", "n_contrib")]
+
+
+# every symbol include/b200splat.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "b200splat_abi_version": (C.c_int, []),
+    "b200splat_last_error": (C.c_char_p, []),
+    "b200splat_launch_count": (C.c_uint64, []),
+    "b200splat_geom_bytes": (C.c_size_t, [C.c_int32]),
+    "b200splat_image_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "b200splat_binning_bytes": (C.c_size_t, [C.c_int64]),
+    "b200splat_backward_scratch_bytes": (C.c_size_t, [C.c_int32]),
+    "b200splat_forward": (C.c_int, [C.POINTER(ForwardArgs)]),
+    "b200splat_backward": (C.c_int, [C.POINTER(BackwardArgs)]),
+    "b200splat_mark_visible": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200splat_dist2_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "b200splat_dist2": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "b200splat_sort_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "b200splat_sort_pairs": (C.c_int, [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_size_t, C.POINTER(C.c_int32), C.c_void_p]),
+    "b200splat_scan_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "b200splat_inclusive_scan_u32": (C.c_int, [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                               C.c_void_p]),
+    "b200splat_forward_views_get": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.POINTER(ForwardViews)]),
+}
+
+
+def _load():
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} not found: the CUDA extension is not built. Run "
+            f"`python {_HERE / 'build.py'}` (needs nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    got = lib.b200splat_abi_version()
+    if got != ABI_VERSION:
+        raise ImportError(f"libb200splat ABI {got} != binding ABI {ABI_VERSION}; rebuild")
+    return lib
+
+
+lib = _load()
+
+
+class B200SplatError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib.b200splat_last_error().decode("utf-8", "replace")
+        raise B200SplatError(f"{what} failed (code {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(lib.b200splat_launch_count())

@@ -1,0 +1,253 @@
+"""Thin torch <-> C-ABI glue: torch owns device memory and streams, libb200splat.so does the work.
+
+Every function here requires CUDA tensors and raises if handed anything else: there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import NamedTuple, Optional
+
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def _f32c(t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
+    if t is None or t.numel() == 0:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError(f"b200splat: {name} must be a CUDA tensor (no CPU fallback); got {t.device}")
+    if t.dtype != torch.float32:
+        t = t.float()
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if t.data_ptr() % 16 != 0:
+        t = t.clone()
+    return t
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Cam(NamedTuple):
+    """Host mirror of GaussianRasterizationSettings with tensors normalised to contiguous fp32 CUDA."""
+    H: int
+    W: int
+    tanfovx: float
+    tanfovy: float
+    scale_modifier: float
+    sh_degree: int
+    prefiltered: bool
+    debug: bool
+    bg: torch.Tensor
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    campos: torch.Tensor
+
+    def c_struct(self) -> _lib.Camera:
+        return _lib.Camera(self.H, self.W, float(self.tanfovx), float(self.tanfovy), float(self.scale_modifier),
+                           int(self.sh_degree), int(bool(self.prefiltered)), int(bool(self.debug)),
+                           self.bg.data_ptr(), self.viewmatrix.data_ptr(), self.projmatrix.data_ptr(),
+                           self.campos.data_ptr())
+
+
+def make_cam(settings, device) -> Cam:
+    t = lambda x, n: _f32c(torch.as_tensor(x, device=device) if not torch.is_tensor(x) else x.to(device), n)
+    return Cam(int(settings.image_height), int(settings.image_width), float(settings.tanfovx),
+               float(settings.tanfovy), float(settings.scale_modifier), int(settings.sh_degree),
+               bool(settings.prefiltered), bool(settings.debug), t(settings.bg, "bg").reshape(-1),
+               t(settings.viewmatrix, "viewmatrix"), t(settings.projmatrix, "projmatrix"),
+               t(settings.campos, "campos").reshape(-1))
+
+
+class ForwardState(NamedTuple):
+    P: int
+    M: int
+    num_rendered: int
+    geom: torch.Tensor
+    binning: Optional[torch.Tensor]
+    image: torch.Tensor
+
+
+def forward(cam: Cam, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp):
+    """Returns color (3,H,W), radii (P,) int32, depth (1,H,W), alpha (1,H,W), ForwardState."""
+    dev = means3D.device
+    if not means3D.is_cuda:
+        raise RuntimeError("b200splat.forward: tensors must be on a CUDA device (no CPU fallback)")
+    P = means3D.shape[0]
+    M = 0 if shs is None else int(shs.shape[1])
+    H, W = cam.H, cam.W
+    color = torch.empty(3, H, W, dtype=torch.float32, device=dev)
+    depth = torch.empty(1, H, W, dtype=torch.float32, device=dev)
+    alpha = torch.empty(1, H, W, dtype=torch.float32, device=dev)
+    radii = torch.empty(P, dtype=torch.int32, device=dev)
+    geom_bytes = lib.b200splat_geom_bytes(P)
+    image_bytes = lib.b200splat_image_bytes(H, W)
+    geom = torch.empty(geom_bytes, dtype=torch.uint8, device=dev)
+    image = torch.empty(image_bytes, dtype=torch.uint8, device=dev)
+    held = []
+
+    def _alloc(_user, nbytes):
+        t = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+        held.append(t)
+        return t.data_ptr()
+
+    cb = _lib.ALLOC_FN(_alloc)
+    nr = C.c_int64(0)
+    bout = C.c_void_p(0)
+    a = _lib.ForwardArgs()
+    a.cam = cam.c_struct()
+    a.P, a.M = P, M
+    a.means3D, a.shs, a.colors_precomp = _ptr(means3D), _ptr(shs), _ptr(colors_precomp)
+    a.opacities, a.scales, a.rotations = _ptr(opacities), _ptr(scales), _ptr(rotations)
+    a.cov3D_precomp = _ptr(cov3D_precomp)
+    a.out_color, a.out_depth, a.out_alpha, a.radii = color.data_ptr(), depth.data_ptr(), alpha.data_ptr(), _ptr(radii)
+    a.geom_buffer, a.geom_bytes = geom.data_ptr(), geom_bytes
+    a.image_buffer, a.image_bytes = image.data_ptr(), image_bytes
+    a.binning_buffer, a.binning_bytes = None, 0
+    a.binning_alloc, a.alloc_user = cb, None
+    a.stream = _stream()
+    a.num_rendered_out = C.pointer(nr)
+    a.binning_out = C.pointer(bout)
+    with torch.cuda.device(dev):
+        check(lib.b200splat_forward(C.byref(a)), "b200splat_forward")
+    binning = held[0] if held else None
+    return color, radii, depth, alpha, ForwardState(P, M, int(nr.value), geom, binning, image)
+
+
+def backward(cam: Cam, st: ForwardState, means3D, shs, colors_precomp, opacities, scales, rotations,
+             cov3D_precomp, radii, out_alpha, g_color, g_depth, g_alpha, out=None, accumulate=False):
+    """Returns dict of dense gradients (tensors allocated here unless ``out`` supplies them)."""
+    dev = means3D.device
+    P, M = st.P, st.M
+    new = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+    out = dict(out or {})
+    out.setdefault("means3D", new(P, 3))
+    out.setdefault("means2D", new(P, 3))
+    out.setdefault("opacities", new(P, 1))
+    if shs is not None:
+        out.setdefault("shs", new(P, M, 3))
+    if colors_precomp is not None:
+        out.setdefault("colors_precomp", new(P, 3))
+    if scales is not None:
+        out.setdefault("scales", new(P, 3))
+        out.setdefault("rotations", new(P, 4))
+    if cov3D_precomp is not None:
+        out.setdefault("cov3D_precomp", new(P, 6))
+    scratch_bytes = lib.b200splat_backward_scratch_bytes(P)
+    scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
+    a = _lib.BackwardArgs()
+    a.cam = cam.c_struct()
+    a.P, a.M, a.num_rendered = P, M, st.num_rendered
+    a.means3D, a.shs, a.colors_precomp = _ptr(means3D), _ptr(shs), _ptr(colors_precomp)
+    a.opacities, a.scales, a.rotations = _ptr(opacities), _ptr(scales), _ptr(rotations)
+    a.cov3D_precomp, a.radii, a.out_alpha = _ptr(cov3D_precomp), _ptr(radii), _ptr(out_alpha)
+    a.geom_buffer, a.binning_buffer, a.image_buffer = _ptr(st.geom), _ptr(st.binning), _ptr(st.image)
+    a.dL_dout_color, a.dL_dout_depth, a.dL_dout_alpha = _ptr(g_color), _ptr(g_depth), _ptr(g_alpha)
+    a.dL_dmeans3D, a.dL_dmeans2D = _ptr(out["means3D"]), _ptr(out["means2D"])
+    a.dL_dshs, a.dL_dcolors = _ptr(out.get("shs")), _ptr(out.get("colors_precomp"))
+    a.dL_dopacity, a.dL_dscales = _ptr(out["opacities"]), _ptr(out.get("scales"))
+    a.dL_drotations, a.dL_dcov3D = _ptr(out.get("rotations")), _ptr(out.get("cov3D_precomp"))
+    a.scratch, a.scratch_bytes = scratch.data_ptr(), scratch_bytes
+    a.accumulate = int(bool(accumulate))
+    a.stream = _stream()
+    with torch.cuda.device(dev):
+        check(lib.b200splat_backward(C.byref(a)), "b200splat_backward")
+    return out
+
+
+def mark_visible(positions: torch.Tensor, viewmatrix: torch.Tensor, projmatrix: torch.Tensor) -> torch.Tensor:
+    positions = _f32c(positions, "positions")
+    P = 0 if positions is None else positions.shape[0]
+    dev = viewmatrix.device
+    present = torch.zeros(P, dtype=torch.uint8, device=dev)
+    if P:
+        v, p = _f32c(viewmatrix, "viewmatrix"), _f32c(projmatrix, "projmatrix")
+        with torch.cuda.device(dev):
+            check(lib.b200splat_mark_visible(P, positions.data_ptr(), v.data_ptr(), p.data_ptr(),
+                                             present.data_ptr(), _stream()), "b200splat_mark_visible")
+    return present.bool()
+
+
+def dist2(points: torch.Tensor) -> torch.Tensor:
+    if not points.is_cuda:
+        raise RuntimeError("distCUDA2: points must be a CUDA tensor (no CPU fallback)")
+    pts = _f32c(points, "points")
+    P = 0 if pts is None else pts.shape[0]
+    out = torch.empty(P, dtype=torch.float32, device=points.device)
+    if P == 0:
+        return out
+    nbytes = lib.b200splat_dist2_workspace_bytes(P)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=points.device)
+    with torch.cuda.device(points.device):
+        check(lib.b200splat_dist2(P, pts.data_ptr(), out.data_ptr(), ws.data_ptr(), nbytes, _stream()),
+              "b200splat_dist2")
+    return out
+
+
+def sort_pairs(keys: torch.Tensor, vals: torch.Tensor, end_bit: int = 64):
+    """Stable ascending sort of (int64 keys viewed as u64, int32 values viewed as u32) on bits [0,end_bit)."""
+    assert keys.is_cuda and keys.dtype == torch.int64 and vals.dtype == torch.int32
+    n = keys.numel()
+    k0, v0 = keys.clone(), vals.clone()
+    k1, v1 = torch.empty_like(k0), torch.empty_like(v0)
+    if n == 0:
+        return k0, v0
+    nbytes = lib.b200splat_sort_workspace_bytes(n)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=keys.device)
+    sel = C.c_int32(0)
+    with torch.cuda.device(keys.device):
+        check(lib.b200splat_sort_pairs(n, end_bit, k0.data_ptr(), v0.data_ptr(), k1.data_ptr(), v1.data_ptr(),
+                                       ws.data_ptr(), nbytes, C.byref(sel), _stream()), "b200splat_sort_pairs")
+    return (k1, v1) if sel.value else (k0, v0)
+
+
+def inclusive_scan_u32(x: torch.Tensor) -> torch.Tensor:
+    assert x.is_cuda and x.dtype == torch.int32
+    n = x.numel()
+    out = torch.empty_like(x)
+    if n == 0:
+        return out
+    nbytes = lib.b200splat_scan_workspace_bytes(n)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.b200splat_inclusive_scan_u32(n, x.data_ptr(), out.data_ptr(), ws.data_ptr(), nbytes, _stream()),
+              "b200splat_inclusive_scan_u32")
+    return out
+
+
+def forward_views(cam: Cam, st: ForwardState):
+    """Copies of the forward's intermediate buffers (for the bit-exact parity tests)."""
+    v = _lib.ForwardViews()
+    check(lib.b200splat_forward_views_get(st.P, cam.H, cam.W, st.num_rendered, _ptr(st.geom), _ptr(st.binning),
+                                          _ptr(st.image), C.byref(v)), "b200splat_forward_views_get")
+    dev = st.geom.device
+    T = ((cam.W + 15) // 16) * ((cam.H + 15) // 16)
+
+    def view(buf, ptr, count, dtype):
+        if not ptr or count == 0:
+            return torch.empty(0, dtype=dtype, device=dev)
+        off = ptr - buf.data_ptr()
+        nb = count * torch.empty(0, dtype=dtype).element_size()
+        return buf[off:off + nb].view(dtype).clone()
+
+    R, P = st.num_rendered, st.P
+    return dict(
+        tiles_touched=view(st.geom, v.tiles_touched, P, torch.int32),
+        point_offsets=view(st.geom, v.point_offsets, P, torch.int32),
+        depths=view(st.geom, v.depths, P, torch.float32),
+        gauss2d=view(st.geom, v.gauss2d, P * 12, torch.float32).reshape(P, 12),
+        cov3D=view(st.geom, v.cov3D, P * 6, torch.float32).reshape(P, 6),
+        keys_sorted=view(st.binning, v.keys_sorted, R, torch.int64) if R else torch.empty(0, dtype=torch.int64),
+        point_list=view(st.binning, v.point_list, R, torch.int32) if R else torch.empty(0, dtype=torch.int32),
+        ranges=view(st.image, v.ranges, T * 2, torch.int32).reshape(T, 2),
+        n_contrib=view(st.image, v.n_contrib, cam.H * cam.W, torch.int32).reshape(cam.H, cam.W),
+    )

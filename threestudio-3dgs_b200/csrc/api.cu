@@ -1,0 +1,360 @@
+// extern "C" surface of libb200splat.so (declared in include/b200splat.h): buffer layouts and the
+// forward / backward pipelines.  Replaces upstream rasterize_points.cu (RasterizeGaussiansCUDA,
+// RasterizeGaussiansBackwardCUDA, markVisible) + cuda_rasterizer/rasterizer_impl.cu
+// (CudaRasterizer::Rasterizer::forward/backward) and simple-knn's distCUDA2 [UPSTREAM-RECALL];
+// reference call sites renderer/diff_gaussian_rasterizer.py:98-131, geometry/gaussian_base.py:434-437.
+#include "../../include/b200splat.h"
+#include "common.cuh"
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+
+namespace b200splat {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(expr)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return fail(B200SPLAT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                        __LINE__);                                                                       \
+    } while (0)
+
+#define DEBUG_SYNC(cam, st, what)                                                                        \
+    do {                                                                                                 \
+        if ((cam).debug) {                                                                               \
+            cudaError_t _e = cudaStreamSynchronize(st);                                                  \
+            if (_e != cudaSuccess)                                                                       \
+                return fail(B200SPLAT_ERR_CUDA, "kernel %s failed: %s", what, cudaGetErrorString(_e));   \
+        }                                                                                                \
+    } while (0)
+
+// ---- layouts --------------------------------------------------------------------------------------
+template <typename T>
+static T* carve(char*& p, size_t count) {
+    T* r = reinterpret_cast<T*>(p);
+    p += align_up(count * sizeof(T), 256);
+    return r;
+}
+
+size_t geom_layout(int P, void* base, GeomViews* v) {
+    char* p = reinterpret_cast<char*>(base);
+    char* p0 = p;
+    GeomViews g;
+    const size_t n = (size_t)(P > 0 ? P : 1);
+    g.rec = carve<float>(p, n * REC_FLOATS);
+    g.depths = carve<float>(p, n);
+    g.cov3D = carve<float>(p, n * 6);
+    g.clamped = carve<uint8_t>(p, n);
+    g.tiles_touched = carve<uint32_t>(p, n);
+    g.point_offsets = carve<uint32_t>(p, n);
+    g.scan_ws_bytes = scan_workspace_bytes((int64_t)n);
+    g.scan_ws = carve<char>(p, g.scan_ws_bytes);
+    if (v) *v = g;
+    return (size_t)(p - p0);
+}
+
+size_t binning_layout(int64_t R, void* base, BinningViews* v) {
+    char* p = reinterpret_cast<char*>(base);
+    char* p0 = p;
+    BinningViews b;
+    const size_t n = (size_t)(R > 0 ? R : 1);
+    b.final_sel = carve<int32_t>(p, 1);
+    b.keys[0] = carve<uint64_t>(p, n);
+    b.keys[1] = carve<uint64_t>(p, n);
+    b.vals[0] = carve<uint32_t>(p, n);
+    b.vals[1] = carve<uint32_t>(p, n);
+    b.sort_ws_bytes = sort_workspace_bytes((int64_t)n);
+    b.sort_ws = carve<char>(p, b.sort_ws_bytes);
+    if (v) *v = b;
+    return (size_t)(p - p0);
+}
+
+size_t image_layout(int H, int W, void* base, ImageViews* v) {
+    char* p = reinterpret_cast<char*>(base);
+    char* p0 = p;
+    ImageViews im;
+    const int gx = (W + BLOCK_X - 1) / BLOCK_X, gy = (H + BLOCK_Y - 1) / BLOCK_Y;
+    im.ranges = carve<uint32_t>(p, (size_t)gx * gy * 2);
+    im.n_contrib = carve<uint32_t>(p, (size_t)H * W);
+    im.final_T = carve<float>(p, (size_t)H * W);
+    if (v) *v = im;
+    return (size_t)(p - p0);
+}
+
+static int higher_msb(uint32_t n) {
+    uint32_t msb = sizeof(n) * 4;
+    uint32_t step = msb;
+    while (step > 1) {
+        step /= 2;
+        if (n >> msb) msb += step; else msb -= step;
+    }
+    if (n >> msb) msb++;
+    return (int)msb;
+}
+
+// parity of the pass count decides which ping-pong half holds the sorted data
+static int sorted_sel_for(int T) {
+    const int end_bit = 32 + higher_msb((uint32_t)T);
+    return ((end_bit + 7) / 8) & 1;
+}
+
+static int make_camera(const b200splat_camera& c, int M, bool has_sh, CameraParams* out) {
+    if (c.image_height <= 0 || c.image_width <= 0) return fail(B200SPLAT_ERR_INVALID, "image size must be positive");
+    if (!c.bg || !c.viewmatrix || !c.projmatrix || !c.campos)
+        return fail(B200SPLAT_ERR_INVALID, "camera device pointers (bg, viewmatrix, projmatrix, campos) must be set");
+    CameraParams p;
+    p.H = c.image_height, p.W = c.image_width;
+    p.grid_x = (p.W + BLOCK_X - 1) / BLOCK_X, p.grid_y = (p.H + BLOCK_Y - 1) / BLOCK_Y;
+    p.tanfovx = c.tanfovx, p.tanfovy = c.tanfovy;
+    p.focal_x = (float)p.W / (2.0f * c.tanfovx);
+    p.focal_y = (float)p.H / (2.0f * c.tanfovy);
+    p.limx = FOV_CLAMP * c.tanfovx;
+    p.limy = FOV_CLAMP * c.tanfovy;
+    p.scale_modifier = c.scale_modifier;
+    p.M = M;
+    int deg = c.sh_degree < 0 ? 0 : c.sh_degree;
+    if (has_sh) {
+        int cap = (int)std::floor(std::sqrt((double)(M > 0 ? M : 1)) + 1e-9) - 1;  // (P,1,3) "SH" with sh_degree > 0
+        if (deg > cap) deg = cap;
+    }
+    if (deg > 3) deg = 3;
+    p.sh_degree = deg;
+    p.bg = c.bg, p.view = c.viewmatrix, p.proj = c.projmatrix, p.campos = c.campos;
+    *out = p;
+    return B200SPLAT_OK;
+}
+
+struct PinnedSlot {
+    int64_t* host = nullptr;
+    uint32_t* host_u32 = nullptr;
+};
+static PinnedSlot& pinned() {
+    static thread_local PinnedSlot s;
+    if (!s.host_u32) {
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, 64, cudaHostAllocDefault) == cudaSuccess) s.host_u32 = reinterpret_cast<uint32_t*>(p);
+    }
+    return s;
+}
+
+}  // namespace b200splat
+
+using namespace b200splat;
+
+extern "C" {
+
+int b200splat_abi_version(void) { return B200SPLAT_ABI_VERSION; }
+const char* b200splat_last_error(void) { return g_err; }
+uint64_t b200splat_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+size_t b200splat_geom_bytes(int32_t P) { return geom_layout(P, nullptr, nullptr); }
+size_t b200splat_image_bytes(int32_t H, int32_t W) { return image_layout(H, W, nullptr, nullptr); }
+size_t b200splat_binning_bytes(int64_t R) { return binning_layout(R, nullptr, nullptr); }
+size_t b200splat_backward_scratch_bytes(int32_t P) {
+    return align_up((size_t)(P > 0 ? P : 1) * GRAD2D_FLOATS * sizeof(float), 256);
+}
+size_t b200splat_sort_workspace_bytes(int64_t n) { return sort_workspace_bytes(n); }
+size_t b200splat_scan_workspace_bytes(int64_t n) { return scan_workspace_bytes(n); }
+size_t b200splat_dist2_workspace_bytes(int32_t P) { return dist2_workspace_bytes(P); }
+
+int b200splat_forward(const b200splat_forward_args* a) {
+    if (!a) return fail(B200SPLAT_ERR_INVALID, "null args");
+    const int P = a->P;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(a->stream);
+    if (P < 0) return fail(B200SPLAT_ERR_INVALID, "P < 0");
+    const bool has_sh = a->shs != nullptr;
+    if (has_sh == (a->colors_precomp != nullptr))
+        return fail(B200SPLAT_ERR_INVALID, "provide exactly one of shs / colors_precomp");
+    const bool has_sr = a->scales != nullptr && a->rotations != nullptr;
+    if (has_sr == (a->cov3D_precomp != nullptr))
+        return fail(B200SPLAT_ERR_INVALID, "provide exactly one of (scales, rotations) / cov3D_precomp");
+    if (has_sh && a->M < 1) return fail(B200SPLAT_ERR_INVALID, "shs given but M < 1");
+    if (!a->out_color || !a->out_depth || !a->out_alpha) return fail(B200SPLAT_ERR_INVALID, "null output image");
+    CameraParams cam;
+    int rc = make_camera(a->cam, a->M, has_sh, &cam);
+    if (rc) return rc;
+    const int T = cam.grid_x * cam.grid_y;
+    ImageViews im;
+    if (!a->image_buffer || a->image_bytes < image_layout(cam.H, cam.W, nullptr, nullptr))
+        return fail(B200SPLAT_ERR_NOMEM, "image_buffer too small");
+    image_layout(cam.H, cam.W, a->image_buffer, &im);
+    if (a->num_rendered_out) *a->num_rendered_out = 0;
+    if (a->binning_out) *a->binning_out = a->binning_buffer;
+
+    int64_t R = 0;
+    GeomViews g{};
+    BinningViews bn{};
+    const uint32_t* point_list = nullptr;
+    if (P > 0) {
+        if (!a->means3D || !a->opacities || !a->radii) return fail(B200SPLAT_ERR_INVALID, "null per-Gaussian input");
+        if (!a->geom_buffer || a->geom_bytes < geom_layout(P, nullptr, nullptr))
+            return fail(B200SPLAT_ERR_NOMEM, "geom_buffer too small");
+        geom_layout(P, a->geom_buffer, &g);
+        CU(launch_preprocess(P, cam, a->means3D, a->scales, a->rotations, a->opacities, a->shs, a->colors_precomp,
+                             a->cov3D_precomp, a->radii, g, st));
+        DEBUG_SYNC(a->cam, st, "preprocess");
+        CU(launch_inclusive_scan(P, g.tiles_touched, g.point_offsets, g.scan_ws, st));
+        DEBUG_SYNC(a->cam, st, "scan");
+        // the one host<->device round trip of the forward: num_rendered sizes the binning buffer
+        PinnedSlot& slot = pinned();
+        if (!slot.host_u32) return fail(B200SPLAT_ERR_CUDA, "cudaHostAlloc failed");
+        CU(cudaMemcpyAsync(slot.host_u32, g.point_offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        R = (int64_t)*slot.host_u32;
+        if (R >= (1ll << 30)) return fail(B200SPLAT_ERR_INVALID, "num_rendered %lld exceeds 2^30", (long long)R);
+    }
+    if (a->num_rendered_out) *a->num_rendered_out = R;
+    if (R > 0) {
+        const size_t need = binning_layout(R, nullptr, nullptr);
+        void* bbuf = a->binning_buffer;
+        if (!bbuf || a->binning_bytes < need) {
+            if (!a->binning_alloc) return fail(B200SPLAT_ERR_NOMEM, "binning_buffer too small and no allocator given");
+            bbuf = a->binning_alloc(a->alloc_user, need);
+            if (!bbuf) return fail(B200SPLAT_ERR_NOMEM, "binning allocator returned NULL for %zu bytes", need);
+        }
+        if (a->binning_out) *a->binning_out = bbuf;
+        binning_layout(R, bbuf, &bn);
+        CU(launch_duplicate(P, cam, a->radii, g, bn.keys[0], bn.vals[0], st));
+        DEBUG_SYNC(a->cam, st, "duplicateWithKeys");
+        int sel = 0;
+        CU(launch_sort_pairs(R, 32 + higher_msb((uint32_t)T), bn.keys, bn.vals, bn.sort_ws, &sel, st));
+        DEBUG_SYNC(a->cam, st, "sort");
+        if (sel != sorted_sel_for(T)) return fail(B200SPLAT_ERR_CUDA, "internal: sort buffer parity mismatch");
+        CU(launch_tile_ranges(R, T, bn.keys[sel], im.ranges, st));
+        DEBUG_SYNC(a->cam, st, "identifyTileRanges");
+        point_list = bn.vals[sel];
+    } else {
+        CU(cudaMemsetAsync(im.ranges, 0, (size_t)T * 8, st));
+    }
+    CU(launch_render_forward(cam, im.ranges, point_list, g.rec, im.n_contrib, im.final_T, a->out_color, a->out_depth,
+                             a->out_alpha, st));
+    DEBUG_SYNC(a->cam, st, "render");
+    return B200SPLAT_OK;
+}
+
+static int sorted_sel(int H, int W) {
+    const int gx = (W + BLOCK_X - 1) / BLOCK_X, gy = (H + BLOCK_Y - 1) / BLOCK_Y;
+    return sorted_sel_for(gx * gy);
+}
+
+int b200splat_backward(const b200splat_backward_args* a) {
+    if (!a) return fail(B200SPLAT_ERR_INVALID, "null args");
+    const int P = a->P;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(a->stream);
+    if (P <= 0) return B200SPLAT_OK;
+    const bool has_sh = a->shs != nullptr;
+    CameraParams cam;
+    int rc = make_camera(a->cam, a->M, has_sh, &cam);
+    if (rc) return rc;
+    if (!a->dL_dmeans3D || !a->dL_dmeans2D || !a->dL_dopacity)
+        return fail(B200SPLAT_ERR_INVALID, "dL_dmeans3D / dL_dmeans2D / dL_dopacity must be given");
+    if (has_sh && !a->dL_dshs) return fail(B200SPLAT_ERR_INVALID, "shs given but dL_dshs is NULL");
+    if (!a->scratch || a->scratch_bytes < b200splat_backward_scratch_bytes(P))
+        return fail(B200SPLAT_ERR_NOMEM, "scratch too small");
+    GeomViews g;
+    ImageViews im;
+    geom_layout(P, const_cast<void*>(a->geom_buffer), &g);
+    image_layout(cam.H, cam.W, const_cast<void*>(a->image_buffer), &im);
+    float* grad2d = reinterpret_cast<float*>(a->scratch);
+    CU(cudaMemsetAsync(grad2d, 0, (size_t)P * GRAD2D_FLOATS * sizeof(float), st));
+    if (a->num_rendered > 0) {
+        BinningViews bn;
+        binning_layout(a->num_rendered, const_cast<void*>(a->binning_buffer), &bn);
+        const uint32_t* point_list = bn.vals[sorted_sel(cam.H, cam.W)];
+        CU(launch_render_backward(cam, im.ranges, point_list, g.rec, im.n_contrib, im.final_T, a->dL_dout_color,
+                                  a->dL_dout_depth, a->dL_dout_alpha, grad2d, st));
+        DEBUG_SYNC(a->cam, st, "render backward");
+    }
+    CU(launch_preprocess_backward(P, cam, a->means3D, a->scales, a->rotations, a->shs, a->cov3D_precomp, a->radii, g,
+                                  grad2d, a->dL_dmeans3D, a->dL_dmeans2D, a->dL_dshs, a->dL_dcolors, a->dL_dopacity,
+                                  a->dL_dscales, a->dL_drotations, a->dL_dcov3D, a->accumulate, st));
+    DEBUG_SYNC(a->cam, st, "preprocess backward");
+    return B200SPLAT_OK;
+}
+
+int b200splat_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                           uint8_t* present, b200splat_stream stream) {
+    if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) return fail(B200SPLAT_ERR_INVALID, "bad argument");
+    CU(launch_mark_visible(P, means3D, viewmatrix, projmatrix, present, reinterpret_cast<cudaStream_t>(stream)));
+    return B200SPLAT_OK;
+}
+
+int b200splat_dist2(int32_t P, const float* points, float* out, void* workspace, size_t workspace_bytes,
+                    b200splat_stream stream) {
+    if (P < 0 || (P > 0 && (!points || !out))) return fail(B200SPLAT_ERR_INVALID, "bad argument");
+    if (P > 0 && (!workspace || workspace_bytes < dist2_workspace_bytes(P)))
+        return fail(B200SPLAT_ERR_NOMEM, "dist2 workspace too small");
+    CU(launch_dist2(P, points, out, workspace, reinterpret_cast<cudaStream_t>(stream)));
+    return B200SPLAT_OK;
+}
+
+int b200splat_sort_pairs(int64_t n, int32_t end_bit, uint64_t* keys, uint32_t* vals, uint64_t* keys_alt,
+                         uint32_t* vals_alt, void* workspace, size_t workspace_bytes, int32_t* result_in_alt,
+                         b200splat_stream stream) {
+    if (n < 0 || n >= (1ll << 30)) return fail(B200SPLAT_ERR_INVALID, "n out of range");
+    if (n > 0 && (!keys || !vals || !keys_alt || !vals_alt || !workspace))
+        return fail(B200SPLAT_ERR_INVALID, "null buffer");
+    if (n > 0 && workspace_bytes < sort_workspace_bytes(n)) return fail(B200SPLAT_ERR_NOMEM, "sort workspace too small");
+    uint64_t* k[2] = {keys, keys_alt};
+    uint32_t* v[2] = {vals, vals_alt};
+    int sel = 0;
+    CU(launch_sort_pairs(n, end_bit, k, v, workspace, &sel, reinterpret_cast<cudaStream_t>(stream)));
+    if (result_in_alt) *result_in_alt = sel;
+    return B200SPLAT_OK;
+}
+
+int b200splat_inclusive_scan_u32(int64_t n, const uint32_t* in, uint32_t* out, void* workspace, size_t workspace_bytes,
+                                 b200splat_stream stream) {
+    if (n < 0) return fail(B200SPLAT_ERR_INVALID, "n < 0");
+    if (n > 0 && (!in || !out || !workspace || workspace_bytes < scan_workspace_bytes(n)))
+        return fail(B200SPLAT_ERR_NOMEM, "scan workspace too small");
+    CU(launch_inclusive_scan(n, in, out, workspace, reinterpret_cast<cudaStream_t>(stream)));
+    return B200SPLAT_OK;
+}
+
+int b200splat_forward_views_get(int32_t P, int32_t H, int32_t W, int64_t num_rendered, const void* geom_buffer,
+                                const void* binning_buffer, const void* image_buffer, b200splat_forward_views* out) {
+    if (!out) return fail(B200SPLAT_ERR_INVALID, "null out");
+    memset(out, 0, sizeof(*out));
+    if (geom_buffer && P > 0) {
+        GeomViews g;
+        geom_layout(P, const_cast<void*>(geom_buffer), &g);
+        out->tiles_touched = g.tiles_touched;
+        out->point_offsets = g.point_offsets;
+        out->depths = g.depths;
+        out->gauss2d = g.rec;
+        out->cov3D = g.cov3D;
+    }
+    if (binning_buffer && num_rendered > 0) {
+        BinningViews b;
+        binning_layout(num_rendered, const_cast<void*>(binning_buffer), &b);
+        const int sel = sorted_sel(H, W);
+        out->keys_sorted = b.keys[sel];
+        out->point_list = b.vals[sel];
+    }
+    if (image_buffer) {
+        ImageViews im;
+        image_layout(H, W, const_cast<void*>(image_buffer), &im);
+        out->ranges = im.ranges;
+        out->n_contrib = im.n_contrib;
+    }
+    return B200SPLAT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,420 @@
+// K2 inclusive scan (decoupled look-back), K4 onesweep LSD radix sort of (u64 key, u32 value) pairs,
+// K5 identifyTileRanges.  Hand-written; no CUB.
+//
+// Replaces cub::DeviceScan::InclusiveSum, cub::DeviceRadixSort::SortPairs and
+// rasterizer_impl.cu identifyTileRanges as called by upstream CudaRasterizer::Rasterizer::forward
+// [UPSTREAM-RECALL]; reference call site renderer/diff_gaussian_rasterizer.py:122-131.
+// All integer work: results are bit-exact by construction (stable sort, exact sums).
+#include "common.cuh"
+
+namespace b200splat {
+
+// ============================================================================================
+// K2: single-pass inclusive scan of uint32 with decoupled look-back
+// ============================================================================================
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+constexpr uint64_t FLAG_AGG = 1ull << 32;
+constexpr uint64_t FLAG_INC = 2ull << 32;
+
+__device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u64(uint64_t* p, uint64_t v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// workspace: [0] ticket counter (u32, padded to 8 B), then one u64 descriptor per tile
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_lookback_kernel(int64_t n, const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t* ticket,
+                     uint64_t* desc) {
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_warp[SCAN_THREADS / 32];
+    __shared__ uint32_t s_excl;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    if (base + SCAN_ITEMS <= n) {
+        const uint4* p = reinterpret_cast<const uint4*>(in + base);
+        uint4 a = __ldg(p), b = __ldg(p + 1);
+        v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) v[i] = (base + i < n) ? in[base + i] : 0u;
+    }
+    uint32_t tsum = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        tsum += v[i];
+        v[i] = tsum;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t warp_off = 0, block_total = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+        uint32_t t = s_warp[w];
+        if (w < warp) warp_off += t;
+        block_total += t;
+    }
+    // look-back by warp 0
+    if (warp == 0) {
+        uint32_t excl = 0;
+        if (tile == 0) {
+            if (lane == 0) st_volatile_u64(desc + 0, FLAG_INC | block_total);
+        } else {
+            if (lane == 0) st_volatile_u64(desc + tile, FLAG_AGG | block_total);
+            int64_t look = (int64_t)tile - 1;
+            while (true) {
+                const int64_t idx = look - lane;
+                uint64_t d = FLAG_INC;  // virtual predecessor of tile 0: inclusive prefix 0
+                if (idx >= 0) {
+                    do {
+                        d = ld_volatile_u64(desc + idx);
+                    } while ((d >> 32) == 0);
+                }
+                const uint32_t inc_mask = __ballot_sync(0xffffffffu, (d >> 32) == 2);
+                uint32_t val = (uint32_t)d;
+                if (inc_mask) {
+                    const int first = __ffs(inc_mask) - 1;
+                    if (lane > first) val = 0;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+                excl += val;
+                if (inc_mask) break;
+                look -= 32;
+            }
+            if (lane == 0) st_volatile_u64(desc + tile, FLAG_INC | (uint64_t)(excl + block_total));
+        }
+        if (lane == 0) s_excl = excl;
+    }
+    __syncthreads();
+    const uint32_t off = s_excl + warp_off + (inc - tsum);
+    if (base + SCAN_ITEMS <= n) {
+        uint4* p = reinterpret_cast<uint4*>(out + base);
+        p[0] = make_uint4(v[0] + off, v[1] + off, v[2] + off, v[3] + off);
+        p[1] = make_uint4(v[4] + off, v[5] + off, v[6] + off, v[7] + off);
+    } else {
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i)
+            if (base + i < n) out[base + i] = v[i] + off;
+    }
+}
+
+size_t scan_workspace_bytes(int64_t n) {
+    int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    return align_up(16 + (size_t)tiles * 8, 256);
+}
+
+cudaError_t launch_inclusive_scan(int64_t n, const uint32_t* in, uint32_t* out, void* ws, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    cudaError_t e = cudaMemsetAsync(ws, 0, scan_workspace_bytes(n), st);
+    if (e != cudaSuccess) return e;
+    uint32_t* ticket = reinterpret_cast<uint32_t*>(ws);
+    uint64_t* desc = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(ws) + 16);
+    scan_lookback_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(n, in, out, ticket, desc);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ============================================================================================
+// K4: onesweep LSD radix sort, 8-bit digits, (u64 key, u32 value)
+// ============================================================================================
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int MAX_PASSES = 8;
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int SORT_ITEMS = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 pairs per CTA
+
+constexpr uint32_t DESC_AGG = 1u << 30;
+constexpr uint32_t DESC_INC = 2u << 30;
+constexpr uint32_t DESC_VAL = (1u << 30) - 1;
+
+// Histogram of every digit place in one read of the keys.  hist: [passes][256] u32 (zeroed).
+__global__ void __launch_bounds__(256)
+radix_histogram_kernel(int64_t n, int passes, int end_bit, const uint64_t* __restrict__ keys,
+                       uint32_t* __restrict__ hist) {
+    __shared__ uint32_t s_hist[MAX_PASSES * RADIX];
+    for (int i = threadIdx.x; i < passes * RADIX; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n_round = (n + 31) / 32 * 32;  // keep warps converged for the votes
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        const bool ok = i < n;
+        const uint64_t k = ok ? __ldg(keys + i) : 0ull;
+        for (int p = 0; p < passes; ++p) {
+            const int shift = p * RADIX_BITS;
+            const int bits = min(RADIX_BITS, end_bit - shift);
+            const uint32_t d = (uint32_t)(k >> shift) & ((1u << bits) - 1u);
+            // warp-uniform digit (typical for the exponent byte of depth): one add for the warp
+            const uint32_t d0 = __shfl_sync(0xffffffffu, d, 0);
+            const uint32_t same = __ballot_sync(0xffffffffu, ok && d == d0);
+            const uint32_t okm = __ballot_sync(0xffffffffu, ok);
+            if (same == okm) {
+                if (lane == 0 && okm) atomicAdd(&s_hist[p * RADIX + d0], (uint32_t)__popc(okm));
+            } else if (ok) {
+                atomicAdd(&s_hist[p * RADIX + d], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * RADIX; i += blockDim.x) {
+        const uint32_t c = s_hist[i];
+        if (c) atomicAdd(&hist[i], c);
+    }
+}
+
+struct SortSmem {
+    uint64_t keys[SORT_TILE];
+    uint32_t vals[SORT_TILE];
+    uint32_t warp_hist[SORT_WARPS][RADIX];
+    uint32_t local_excl[RADIX];   // exclusive offset of digit inside this tile
+    uint32_t bin_offset[RADIX];   // global destination of the tile's first key of digit d, minus local_excl
+    uint32_t warp_tot[SORT_WARPS];
+    uint32_t tile;
+};
+
+// One pass: tile t of the input is ranked locally (stable), its per-digit counts are chained to the
+// previous tiles by decoupled look-back, then keys/values are scattered through shared memory so that
+// the global writes are coalesced per digit run.
+__global__ void __launch_bounds__(SORT_THREADS)
+onesweep_pass_kernel(int64_t n, int shift, int bits, const uint64_t* __restrict__ keys_in,
+                     const uint32_t* __restrict__ vals_in, uint64_t* __restrict__ keys_out,
+                     uint32_t* __restrict__ vals_out, const uint32_t* __restrict__ hist_pass, uint32_t* ticket,
+                     uint32_t* desc /* [tiles][256] */) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SortSmem& S = *reinterpret_cast<SortSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) S.tile = atomicAdd(ticket, 1u);
+    for (int i = tid; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&S.warp_hist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = S.tile;
+    const int64_t tile_base = (int64_t)tile * SORT_TILE;
+    const int valid = (int)min((int64_t)SORT_TILE, n - tile_base);
+    const uint32_t mask = (1u << bits) - 1u;
+
+    // ---- load (warp-striped: item i of lane l in warp w = w*512 + i*32 + l) ------------------
+    uint64_t key[SORT_ITEMS];
+    uint32_t rank[SORT_ITEMS];
+    const int wbase = warp * (32 * SORT_ITEMS) + lane;
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        const int li = wbase + i * 32;
+        key[i] = (li < valid) ? __ldg(keys_in + tile_base + li) : ~0ull;
+    }
+    // ---- warp-level stable ranking -------------------------------------------------------------
+    const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        const uint32_t d = (uint32_t)(key[i] >> shift) & mask;
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t pre = 0;
+        if (lane == leader) {
+            pre = S.warp_hist[warp][d];
+            S.warp_hist[warp][d] = pre + __popc(peers);
+        }
+        pre = __shfl_sync(0xffffffffu, pre, leader);
+        rank[i] = pre + __popc(peers & lt_mask);
+        __syncwarp();
+    }
+    __syncthreads();
+    // ---- per-digit: exclusive prefix over warps, tile total, look-back --------------------------
+    uint32_t bin_total = 0;
+    {
+        const int d = tid;  // SORT_THREADS == RADIX
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; ++w) {
+            const uint32_t t = S.warp_hist[w][d];
+            S.warp_hist[w][d] = bin_total;
+            bin_total += t;
+        }
+        // padding keys (~0) of a partial tile landed in the top digit: not part of the data
+        uint32_t pub = bin_total;
+        if (d == (int)mask) pub -= (uint32_t)(SORT_TILE - valid);
+        uint32_t* my = desc + (size_t)tile * RADIX + d;
+        if (tile == 0) {
+            st_volatile_u32(my, DESC_INC | pub);
+        } else {
+            st_volatile_u32(my, DESC_AGG | pub);
+        }
+        // global digit start = exclusive scan of the global histogram of this digit place
+        // (block-wide scan of 256 values)
+        uint32_t h = (d <= (int)mask) ? hist_pass[d] : 0u;
+        uint32_t hinc = h, linc = bin_total;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t1 = __shfl_up_sync(0xffffffffu, hinc, o);
+            uint32_t t2 = __shfl_up_sync(0xffffffffu, linc, o);
+            if (lane >= o) {
+                hinc += t1;
+                linc += t2;
+            }
+        }
+        __shared__ uint32_t s_h[SORT_WARPS], s_l[SORT_WARPS];
+        if (lane == 31) {
+            s_h[warp] = hinc;
+            s_l[warp] = linc;
+        }
+        __syncthreads();
+        uint32_t hoff = 0, loff = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; ++w) {
+            if (w < warp) {
+                hoff += s_h[w];
+                loff += s_l[w];
+            }
+        }
+        const uint32_t digit_start = hoff + hinc - h;
+        const uint32_t lexcl = loff + linc - bin_total;
+        uint32_t excl = 0;
+        if (tile > 0) {
+            int64_t look = (int64_t)tile - 1;
+            while (true) {
+                uint32_t v;
+                do {
+                    v = ld_volatile_u32(desc + (size_t)look * RADIX + d);
+                } while ((v >> 30) == 0);
+                excl += v & DESC_VAL;
+                if ((v >> 30) == 2) break;
+                --look;
+            }
+            st_volatile_u32(my, DESC_INC | (excl + pub));
+        }
+        S.local_excl[d] = lexcl;
+        S.bin_offset[d] = digit_start + excl - lexcl;
+    }
+    __syncthreads();
+    // ---- scatter to shared memory at the tile-sorted position ------------------------------------
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        const uint32_t d = (uint32_t)(key[i] >> shift) & mask;
+        rank[i] += S.local_excl[d] + S.warp_hist[warp][d];
+        S.keys[rank[i]] = key[i];
+    }
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        const int li = wbase + i * 32;
+        if (li < valid) S.vals[rank[i]] = __ldg(vals_in + tile_base + li);
+    }
+    __syncthreads();
+    // ---- coalesced write-out ------------------------------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        const int p = i * SORT_THREADS + tid;
+        if (p < valid) {
+            const uint64_t k = S.keys[p];
+            const uint32_t d = (uint32_t)(k >> shift) & mask;
+            const uint32_t dst = S.bin_offset[d] + (uint32_t)p;
+            keys_out[dst] = k;
+            vals_out[dst] = S.vals[p];
+        }
+    }
+}
+
+static inline int64_t sort_tiles(int64_t n) { return (n + SORT_TILE - 1) / SORT_TILE; }
+
+// workspace: hist [MAX_PASSES][256] u32 | tickets [MAX_PASSES] u32 (padded) | desc [passes][tiles][256] u32
+size_t sort_workspace_bytes(int64_t n) {
+    const int64_t tiles = sort_tiles(n < 1 ? 1 : n);
+    return align_up((size_t)MAX_PASSES * RADIX * 4 + 256 + (size_t)MAX_PASSES * tiles * RADIX * 4, 256);
+}
+
+cudaError_t launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_t* vals[2], void* ws, int* sel,
+                              cudaStream_t st) {
+    *sel = 0;
+    if (n <= 0) return cudaSuccess;
+    if (end_bit < 1) end_bit = 1;
+    if (end_bit > 64) end_bit = 64;
+    const int passes = (end_bit + RADIX_BITS - 1) / RADIX_BITS;
+    const int64_t tiles = sort_tiles(n);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(onesweep_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(SortSmem));
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const size_t used = (size_t)MAX_PASSES * RADIX * 4 + 256 + (size_t)passes * tiles * RADIX * 4;
+    cudaError_t e = cudaMemsetAsync(ws, 0, used, st);
+    if (e != cudaSuccess) return e;
+    uint32_t* hist = reinterpret_cast<uint32_t*>(ws);
+    uint32_t* tickets = hist + MAX_PASSES * RADIX;
+    uint32_t* desc = tickets + 64;
+    int64_t hg = (n + 255) / 256;
+    int hgrid = (int)(hg < (int64_t)NUM_SMS * 8 ? hg : (int64_t)NUM_SMS * 8);
+    radix_histogram_kernel<<<hgrid, 256, 0, st>>>(n, passes, end_bit, keys[0], hist);
+    count_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    int cur = 0;
+    for (int p = 0; p < passes; ++p) {
+        const int shift = p * RADIX_BITS;
+        const int bits = (end_bit - shift) < RADIX_BITS ? (end_bit - shift) : RADIX_BITS;
+        onesweep_pass_kernel<<<(unsigned)tiles, SORT_THREADS, sizeof(SortSmem), st>>>(
+            n, shift, bits, keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], hist + p * RADIX, tickets + p,
+            desc + (size_t)p * tiles * RADIX);
+        count_launch();
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        cur ^= 1;
+    }
+    *sel = cur;
+    return cudaSuccess;
+}
+
+// ============================================================================================
+// K5: tile ranges from the sorted keys
+// ============================================================================================
+__global__ void __launch_bounds__(256)
+tile_ranges_kernel(int64_t R, const uint64_t* __restrict__ keys, uint32_t* __restrict__ ranges) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    const uint32_t t = (uint32_t)(keys[i] >> 32);
+    if (i == 0) {
+        ranges[2 * t] = 0;
+    } else {
+        const uint32_t tp = (uint32_t)(keys[i - 1] >> 32);
+        if (tp != t) {
+            ranges[2 * tp + 1] = (uint32_t)i;
+            ranges[2 * t] = (uint32_t)i;
+        }
+    }
+    if (i == R - 1) ranges[2 * t + 1] = (uint32_t)R;
+}
+
+cudaError_t launch_tile_ranges(int64_t R, int T, const uint64_t* keys_sorted, uint32_t* ranges, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(ranges, 0, (size_t)T * 8, st);
+    if (e != cudaSuccess || R <= 0) return e;
+    tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, keys_sorted, ranges);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace b200splat
