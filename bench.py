@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""bench.py -- fwd+bwd splat renders/sec on the BASELINE.json headline workload.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # CPU oracle (reference arm)
+
+A *step* is one pass of the hot path over one batch of views on every GPU: for each of the rank's
+views forward + backward (gradients summed into the packed buffer, densification statistics fused),
+then -- for N > 1 -- one SUM all-reduce of the packed buffer and one MAX all-reduce of max_radii.
+Weak scaling: every rank renders ``--views-per-gpu`` views of the same replicated 1M-Gaussian scene.
+Rank 0 prints ONE JSON line.  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "threestudio-3dgs_b200"))
+
+METRIC = "fwd+bwd splat renders/sec"
+UNIT = "renders/s"
+DEFAULT_WORKLOAD = "headline_1m_512_sh3"
+
+
+# ------------------------------------------------------------------------------------------------
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
+    ap.add_argument("--views-per-gpu", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-tiles", type=int, default=64)
+    return ap.parse_args()
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm_gbs=float(d["hbm_gbs"]), sm_max_mhz=float(d.get("sm_max_mhz", 1965.0)), source="measured")
+    return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_render_time(scene, cam, sample_tiles: int, threads: int):
+    """Seconds for ONE fwd+bwd render of the workload on the CPU oracle, measured on a bounded sample:
+    preprocess + key sort run on all P Gaussians; the per-tile blend (fwd + bwd) runs on an evenly spaced
+    subset of ``sample_tiles`` tiles and is scaled by (#tiles / #sampled)."""
+    import torch
+    from oracle import torch_oracle as O
+    from b200splat import scenes
+    torch.set_num_threads(threads)
+    s = O.Settings(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy, torch.ones(3), 1.0,
+                   cam.viewmatrix, cam.projmatrix, scene.sh_degree, cam.campos, False, False)
+    H, W = cam.image_height, cam.image_width
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        pre = O.preprocess(scene.means3D, scene.opacities, scene.scales, scene.rotations, None, scene.shs, None, s)
+        binned = O.bin_and_sort(pre, s)
+    t_front = time.perf_counter() - t0
+    d = O.derived_scalars(s)
+    T = d["grid_x"] * d["grid_y"]
+    n = max(1, min(sample_tiles, T))
+    tiles = [int(i * T / n) for i in range(n)]
+    gc, gd, ga = scenes.pixel_grads(H, W, 7)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        out = O.render_forward(pre, binned, s, tiles=tiles)
+    t_fwd = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    O.rasterize_backward((scene.means3D, None, scene.shs, None, scene.opacities, scene.scales, scene.rotations,
+                          None), s, pre, binned, out, gc, gd, ga, tiles=tiles)
+    t_bwd = time.perf_counter() - t0
+    # backward = per-tile part (scaled) + differentiable preprocess (not scaled); measured together, so
+    # scale only the tile share estimated from the forward ratio -- conservative: scale everything but
+    # t_front, which over-estimates CPU time slightly in the CPU's disfavour? No: keep it honest and
+    # scale only the tile loops; the preprocess-backward share is measured separately below.
+    t0 = time.perf_counter()
+    O.rasterize_backward((scene.means3D, None, scene.shs, None, scene.opacities, scene.scales, scene.rotations,
+                          None), s, pre, binned, out, gc, gd, ga, tiles=[])
+    t_bwd_pre = time.perf_counter() - t0
+    scale = T / n
+    total = t_front + t_fwd * scale + max(t_bwd - t_bwd_pre, 0.0) * scale + t_bwd_pre
+    return total, dict(t_front=t_front, t_fwd_sample=t_fwd, t_bwd_sample=t_bwd, t_bwd_pre=t_bwd_pre, tiles=n,
+                       of_tiles=T, cpu_seconds=t_front + t_fwd + t_bwd + t_bwd_pre)
+
+
+def run_reference(args):
+    """Reference arm: the CPU oracle (kind "port" -- the reference's CUDA rasterizer is un-vendored and
+    cannot be built here) timed on the host cores, same workload/metric/unit."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from b200splat import scenes
+    threads = os.cpu_count() or 1
+    scene, cams = scenes.make_workload(args.workload, views=1)
+    times = []
+    info = {}
+    for i in range(args.warmup + args.steps):
+        t, info = cpu_oracle_render_time(scene, cams[0], args.cpu_sample_tiles, threads)
+        if i >= args.warmup:
+            times.append(t)
+    sec = sum(times) / len(times)
+    val = 1.0 / sec
+    sample = (f"per step: preprocess+sort of all P, blend fwd+bwd on {info['tiles']} of {info['of_tiles']} tiles "
+              f"scaled x{info['of_tiles'] / info['tiles']:.1f}; {info['cpu_seconds']:.1f} s CPU work per step")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "views_per_step": 1, "device": "cpu"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+    from b200splat import _lib, batched, ops, scenes
+    from b200splat import dist as bdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback); "
+                         "use --impl reference for the CPU oracle")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N = world
+    V = args.views_per_gpu
+
+    # ---- workload: replicated scene, per-rank views ------------------------------------------------
+    scene, cams_all = scenes.make_workload(args.workload, views=V * N)
+    cams_host = cams_all[rank * V:(rank + 1) * V]
+    H, W = cams_host[0].image_height, cams_host[0].image_width
+    P = scene.means3D.shape[0]
+    M = scene.shs.shape[1]
+    to = lambda t: t.to(dev).contiguous()
+    means3D, shs, opac, scales, rots = map(to, (scene.means3D, scene.shs, scene.opacities, scene.scales,
+                                                scene.rotations))
+    bg = torch.ones(3, device=dev)
+
+    class S:  # settings-like
+        pass
+
+    def dev_cam(c):
+        s = S()
+        s.image_height, s.image_width, s.tanfovx, s.tanfovy = c.image_height, c.image_width, c.tanfovx, c.tanfovy
+        s.bg, s.scale_modifier, s.viewmatrix, s.projmatrix = bg, 1.0, c.viewmatrix, c.projmatrix
+        s.sh_degree, s.campos, s.prefiltered, s.debug = scene.sh_degree, c.campos, False, False
+        return ops.make_cam(s, dev)
+
+    cams = [dev_cam(c) for c in cams_host]
+    pgrads_host = [scenes.pixel_grads(H, W, 99 + rank * V + v) for v in range(V)]
+    pgrads = [tuple(to(g) for g in pg) for pg in pgrads_host]
+    packed = batched.PackedGrads(P, M, dev)
+
+    def step():
+        batched.render_views_fwd_bwd(cams, means3D, shs, None, opac, scales, rots, pgrads, packed)
+        bdist.allreduce_packed(packed.buffer, packed.max_radii)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = _lib.launch_count() - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    ms_per_step = total_ms / args.steps
+    value = N * V * args.steps / (total_ms / 1e3)
+
+    # ---- e2e: public API (GaussianRasterizer + autograd), host buffers for the step's inputs ----------
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    pin = lambda t: t.contiguous().pin_memory()
+    cam_host_t = [(pin(c.viewmatrix), pin(c.projmatrix), pin(c.campos)) for c in cams_host]
+    bg_host = pin(torch.ones(3))
+    pg_pinned = [tuple(pin(g) for g in pg) for pg in pgrads_host]
+    img_host = torch.empty(V, 3, H, W).pin_memory()
+    loss_host = torch.empty(1).pin_memory()
+    params = [t.clone().requires_grad_(True) for t in (means3D, shs, opac, scales, rots)]
+    h2d = sum(sum(t.numel() * 4 for t in ct) for ct in cam_host_t) + V * 12 + \
+        sum(sum(g.numel() * 4 for g in pg) for pg in pg_pinned)
+    d2h = img_host.numel() * 4 + 4
+
+    def e2e_step():
+        for p in params:
+            p.grad = None
+        loss = None
+        for v in range(V):
+            vm, pm, cp = (t.to(dev, non_blocking=True) for t in cam_host_t[v])
+            bgd = bg_host.to(dev, non_blocking=True)
+            gc, gd, ga = (t.to(dev, non_blocking=True) for t in pg_pinned[v])
+            rs = GaussianRasterizationSettings(H, W, cams_host[v].tanfovx, cams_host[v].tanfovy, bgd, 1.0, vm, pm,
+                                               scene.sh_degree, cp, False, False)
+            m2 = torch.zeros_like(params[0], requires_grad=True)
+            color, radii, depth, alpha = GaussianRasterizer(raster_settings=rs)(
+                means3D=params[0], means2D=m2, shs=params[1], colors_precomp=None, opacities=params[2],
+                scales=params[3], rotations=params[4], cov3D_precomp=None)
+            l = (color * gc).sum() + (depth * gd).sum() + (alpha * ga).sum()
+            loss = l if loss is None else loss + l
+            img_host[v].copy_(color.detach(), non_blocking=True)
+        loss.backward()
+        if world > 1:
+            for p in params:
+                dist.all_reduce(p.grad)
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(loss_host[0])
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = N * V * args.steps / float(e2e_s.item())
+
+    # ---- per-kernel roofline (rank 0): CUDA events on the launch stream, live ----------------------
+    roof, kernels = None, None
+    cpu_base = None
+    if rank == 0:
+        pk = peaks()
+        prof_steps = max(2, min(5, args.steps))
+        torch.cuda.synchronize()
+        _lib.profile_enable(True)
+        for _ in range(prof_steps):
+            batched.render_views_fwd_bwd(cams, means3D, shs, None, opac, scales, rots, pgrads, packed)
+        torch.cuda.synchronize()
+        prof = _lib.profile_read()
+        _lib.profile_enable(False)
+        # work counters of the rank's views (averaged per launch)
+        cnt = dict(V=0, R=0, n_eval_fwd=0, n_eval_bwd=0, staged=0)
+        for cam in cams:
+            color, radii, depth, alpha, st = ops.forward(cam, means3D, shs, None, opac, scales, rots, None)
+            vw = ops.forward_views(cam, st)
+            cnt["V"] += int((radii > 0).sum())
+            cnt["R"] += st.num_rendered
+            cnt["n_eval_fwd"] += int(vw["n_visited"].sum())
+            cnt["n_eval_bwd"] += int(vw["n_contrib"].sum())
+        for k in cnt:
+            cnt[k] /= len(cams)
+        Tn = ((W + 15) // 16) * ((H + 15) // 16)
+        bits = 32 + (Tn - 1).bit_length() + (1 if Tn & (Tn - 1) == 0 else 0)
+        passes = (bits + 7) // 8
+        Mc = M
+        alg = {  # SURVEY.md 8(d) algorithmic bytes / flops per launch
+            "preprocess": ("hbm", P * (44 + 12 * Mc + 48)),
+            "scan": ("hbm", 8 * P),
+            "duplicate": ("hbm", 20 * cnt["V"] + 12 * cnt["R"]),
+            "sort": ("hbm", cnt["R"] * (8 + passes * 24)),
+            "ranges": ("hbm", 8 * cnt["R"] + 8 * Tn),
+            "render_fwd": ("fp32", 30 * cnt["n_eval_fwd"]),
+            "render_bwd": ("fp32", 90 * cnt["n_eval_bwd"]),
+            "preprocess_bwd": ("hbm", P * (84 + 12 * Mc) + P * (40 + 12 * Mc + 4)),
+        }
+        fp32_peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
+        traffic = {}
+        tpath = ROOT / "profiles" / "ncu_traffic.json"
+        if tpath.exists():
+            try:
+                traffic = json.loads(tpath.read_text()).get(args.workload, {})
+            except Exception:
+                traffic = {}
+        kernels = []
+        for name, (bound, work) in alg.items():
+            tot, n = prof.get(name, (0.0, 0))
+            if n == 0:
+                continue
+            avg_ms = tot / n
+            if bound == "hbm":
+                ach, peak, unit = work / (avg_ms * 1e-3) / 1e9, pk["hbm_gbs"], "GB/s"
+            else:
+                ach, peak, unit = work / (avg_ms * 1e-3) / 1e12, fp32_peak, "TFLOP/s"
+            kernels.append({"kernel": name, "bound": bound, "avg_ms": avg_ms, "launches": n, "achieved": ach,
+                            "peak": peak, "unit": unit, "frac": ach / peak, "work_per_launch": work,
+                            "traffic": traffic.get(name)})
+        step_ms = sum(k["avg_ms"] for k in kernels)
+        for k in kernels:
+            k["share_of_step"] = k["avg_ms"] / step_ms if step_ms else None
+        dom = max(kernels, key=lambda k: k["avg_ms"])
+        roof = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"],
+                "unit": dom["unit"], "frac": dom["frac"], "traffic": dom["traffic"], "peak_source": pk["source"] +
+                (" HBM copy" if dom["bound"] == "hbm" else " sm_max_mhz x 148 SM x 128 lanes x 2 (non-tensor FP32)"),
+                "avg_ms": dom["avg_ms"], "counters": cnt}
+        if N == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            sec, info = cpu_oracle_render_time(scene, cams_host[0], args.cpu_sample_tiles, threads)
+            cpu_base = {"value": 1.0 / sec, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": (f"1 view: preprocess+sort of all {P} Gaussians, blend fwd+bwd on {info['tiles']} of "
+                                   f"{info['of_tiles']} tiles scaled x{info['of_tiles'] / info['tiles']:.1f}; "
+                                   f"{info['cpu_seconds']:.1f} s of CPU work")}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "gaussians": P, "sh_degree": scene.sh_degree, "image": [H, W],
+                       "views_per_gpu_per_step": V, "global_views_per_step": V * N,
+                       "parallelism": f"view-dp{N}" if N > 1 else "single",
+                       "allreduce_bytes_per_step": (packed.nbytes + 4 * P) if N > 1 else 0,
+                       "l2": "inputs larger than L2: %.0f MB parameters + per-view key/value buffers > 126 MB"
+                             % ((means3D.numel() + shs.numel() + opac.numel() + scales.numel() + rots.numel()) * 4 / 1e6)},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "diff_gaussian_rasterization.GaussianRasterizer + autograd; cameras, bg and pixel "
+                           "gradients from pinned host memory each step; images + loss read back"},
+            "gpu_launches": launches,
+            "roofline": roof, "kernels": kernels, "cpu_baseline": cpu_base,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

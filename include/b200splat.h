@@ -144,6 +144,12 @@ typedef struct b200splat_backward_args {
     void* scratch;
     size_t scratch_bytes;
     int32_t accumulate;
+    /* Optional fused densification statistics (geometry/gaussian_base.py:815-819, :846-851), each (P) fp32 or
+     * NULL; updated for Gaussians with radii > 0 of THIS view:  stat_grad_accum += ||dL_dmeans2D.xy||,
+     * stat_denom += 1, stat_max_radii = max(stat_max_radii, radii). */
+    float* stat_grad_accum;
+    float* stat_denom;
+    float* stat_max_radii;
     b200splat_stream stream;
 } b200splat_backward_args;
 
@@ -175,7 +181,8 @@ int b200splat_inclusive_scan_u32(int64_t n, const uint32_t* in, uint32_t* out, v
 
 /* Views into the buffers of a finished forward (device pointers into the caller's buffers), for
  * the bit-exact parity checks: tiles_touched (P) u32, point_offsets (P) u32, depths (P) f32,
- * sorted keys (R) u64, point_list (R) u32, ranges (T,2) u32, n_contrib (H*W) u32. */
+ * sorted keys (R) u64, point_list (R) u32, ranges (T,2) u32, n_contrib (H*W) u32 (1-based index of the
+ * last blended list entry), n_visited (H*W) u32 (list entries traversed before the pixel stopped). */
 typedef struct b200splat_forward_views {
     const uint32_t* tiles_touched;
     const uint32_t* point_offsets;
@@ -186,11 +193,21 @@ typedef struct b200splat_forward_views {
     const uint32_t* point_list;
     const uint32_t* ranges;
     const uint32_t* n_contrib;
+    const uint32_t* n_visited;
 } b200splat_forward_views;
 
 int b200splat_forward_views_get(int32_t P, int32_t H, int32_t W, int64_t num_rendered,
                                 const void* geom_buffer, const void* binning_buffer,
                                 const void* image_buffer, b200splat_forward_views* out);
+
+/* ---- per-kernel timing (bench.py roofline): CUDA events recorded on the launch stream around each
+ * kernel family while enabled.  Families: 0 preprocess, 1 scan, 2 duplicateWithKeys, 3 sort,
+ * 4 tile ranges, 5 render fwd, 6 render bwd, 7 preprocess bwd, 8 dist2. */
+#define B200SPLAT_NUM_FAMILIES 9
+int b200splat_profile_enable(int32_t on);
+/* Synchronises the recorded events; fills ms[f] (total) and count[f] (launch groups) per family and
+ * clears the record.  Arrays must hold B200SPLAT_NUM_FAMILIES entries. */
+int b200splat_profile_read(float* ms, int64_t* count);
 
 /* ---- misc ----------------------------------------------------------------------------------- */
 int b200splat_abi_version(void);

@@ -350,7 +350,7 @@ def _blend_tile(pixx, pixy, xy_x, xy_y, con_a, con_b, con_c, opac, rgb, depth, T
     return C, D, A, T_fin, last, any_stop, n_trav
 
 
-def render_forward(pre, binned, s: Settings, chunk: int = 1024):
+def render_forward(pre, binned, s: Settings, chunk: int = 1024, tiles=None):
     """Per-tile blend.  Returns color (3,H,W), depth (1,H,W), alpha (1,H,W), n_contrib (H,W) int32
     and counters n_eval_fwd / n_eval_bwd."""
     d = derived_scalars(s)
@@ -368,8 +368,10 @@ def render_forward(pre, binned, s: Settings, chunk: int = 1024):
     dep = pre["depth"].detach()
     pl = binned["point_list"].to(torch.int64)
     ranges = binned["ranges"]
-    for ty in range(gy):
-        for tx in range(gx):
+    # ``tiles``: optional subset of tile indices (bounded-sample CPU baseline); other tiles stay zero
+    for tile in (range(gx * gy) if tiles is None else tiles):
+        ty, tx = divmod(int(tile), gx)
+        if True:
             r0, r1 = int(ranges[ty * gx + tx, 0]), int(ranges[ty * gx + tx, 1])
             x0, y0 = tx * spec.BLOCK_X, ty * spec.BLOCK_Y
             x1, y1 = min(x0 + spec.BLOCK_X, W), min(y0 + spec.BLOCK_Y, H)
@@ -424,7 +426,7 @@ def rasterize_forward(means3D, means2D, shs, colors_precomp, opacities, scales, 
 # conventions; tile by tile so memory stays bounded.
 # ----------------------------------------------------------------------------------------
 
-def rasterize_backward(inputs, s: Settings, pre, binned, fwd, dL_dcolor, dL_ddepth, dL_dalpha):
+def rasterize_backward(inputs, s: Settings, pre, binned, fwd, dL_dcolor, dL_ddepth, dL_dalpha, tiles=None):
     """Returns dict of gradients for means3D, means2D, shs, colors_precomp, opacities, scales,
     rotations, cov3D_precomp (None where the input was None).  Also returns the per-Gaussian
     2D-stage gradients (dL/dxy_pix, dL/dconic, dL/dopacity, dL/drgb, dL/ddepth) that the CUDA
@@ -454,8 +456,9 @@ def rasterize_backward(inputs, s: Settings, pre, binned, fwd, dL_dcolor, dL_ddep
     ranges = binned["ranges"]
     ncontrib = fwd["n_contrib"]
     det2d = [t.detach() for t in two_d]
-    for ty in range(gy):
-        for tx in range(gx):
+    for tile in (range(gx * gy) if tiles is None else tiles):
+        ty, tx = divmod(int(tile), gx)
+        if True:
             r0 = int(ranges[ty * gx + tx, 0])
             x0, y0 = tx * spec.BLOCK_X, ty * spec.BLOCK_Y
             x1, y1 = min(x0 + spec.BLOCK_X, W), min(y0 + spec.BLOCK_Y, H)

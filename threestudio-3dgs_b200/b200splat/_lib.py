@@ -55,14 +55,16 @@ class BackwardArgs(C.Structure):
         ("dL_dcolors", C.c_void_p), ("dL_dopacity", C.c_void_p), ("dL_dscales", C.c_void_p),
         ("dL_drotations", C.c_void_p), ("dL_dcov3D", C.c_void_p),
         ("scratch", C.c_void_p), ("scratch_bytes", C.c_size_t),
-        ("accumulate", C.c_int32), ("stream", C.c_void_p),
+        ("accumulate", C.c_int32),
+        ("stat_grad_accum", C.c_void_p), ("stat_denom", C.c_void_p), ("stat_max_radii", C.c_void_p),
+        ("stream", C.c_void_p),
     ]
 
 
 class ForwardViews(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "tiles_touched", "point_offsets", "depths", "gauss2d", "cov3D", "keys_sorted", "point_list",
-        "ranges", "n_contrib")]
+        "ranges", "n_contrib", "n_visited")]
 
 
 # every symbol include/b200splat.h declares: name -> (restype, argtypes)
@@ -87,7 +89,12 @@ SYMBOLS = {
                                                C.c_void_p]),
     "b200splat_forward_views_get": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.POINTER(ForwardViews)]),
+    "b200splat_profile_enable": (C.c_int, [C.c_int32]),
+    "b200splat_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
 }
+
+FAMILIES = ("preprocess", "scan", "duplicate", "sort", "ranges", "render_fwd", "render_bwd", "preprocess_bwd",
+            "dist2")
 
 
 def _load():
@@ -117,6 +124,19 @@ def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = lib.b200splat_last_error().decode("utf-8", "replace")
         raise B200SplatError(f"{what} failed (code {rc}): {msg}")
+
+
+def profile_enable(on: bool) -> None:
+    check(lib.b200splat_profile_enable(int(on)), "b200splat_profile_enable")
+
+
+def profile_read():
+    """{family: (total_ms, launch_groups)} since profile_enable(True); clears the record."""
+    n = len(FAMILIES)
+    ms = (C.c_float * n)()
+    cnt = (C.c_int64 * n)()
+    check(lib.b200splat_profile_read(ms, cnt), "b200splat_profile_read")
+    return {FAMILIES[i]: (float(ms[i]), int(cnt[i])) for i in range(n)}
 
 
 def launch_count() -> int:

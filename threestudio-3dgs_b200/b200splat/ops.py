@@ -124,7 +124,7 @@ def forward(cam: Cam, means3D, shs, colors_precomp, opacities, scales, rotations
 
 
 def backward(cam: Cam, st: ForwardState, means3D, shs, colors_precomp, opacities, scales, rotations,
-             cov3D_precomp, radii, out_alpha, g_color, g_depth, g_alpha, out=None, accumulate=False):
+             cov3D_precomp, radii, out_alpha, g_color, g_depth, g_alpha, out=None, accumulate=False, stats=None):
     """Returns dict of dense gradients (tensors allocated here unless ``out`` supplies them)."""
     dev = means3D.device
     P, M = st.P, st.M
@@ -158,6 +158,8 @@ def backward(cam: Cam, st: ForwardState, means3D, shs, colors_precomp, opacities
     a.dL_drotations, a.dL_dcov3D = _ptr(out.get("rotations")), _ptr(out.get("cov3D_precomp"))
     a.scratch, a.scratch_bytes = scratch.data_ptr(), scratch_bytes
     a.accumulate = int(bool(accumulate))
+    if stats is not None:   # (grad_accum, denom, max_radii) each (P,) fp32, updated in place
+        a.stat_grad_accum, a.stat_denom, a.stat_max_radii = (_ptr(t) for t in stats)
     a.stream = _stream()
     with torch.cuda.device(dev):
         check(lib.b200splat_backward(C.byref(a)), "b200splat_backward")
@@ -250,4 +252,5 @@ def forward_views(cam: Cam, st: ForwardState):
         point_list=view(st.binning, v.point_list, R, torch.int32) if R else torch.empty(0, dtype=torch.int32),
         ranges=view(st.image, v.ranges, T * 2, torch.int32).reshape(T, 2),
         n_contrib=view(st.image, v.n_contrib, cam.H * cam.W, torch.int32).reshape(cam.H, cam.W),
+        n_visited=view(st.image, v.n_visited, cam.H * cam.W, torch.int32).reshape(cam.H, cam.W),
     )

@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 namespace b200splat {
 
@@ -93,6 +94,7 @@ size_t image_layout(int H, int W, void* base, ImageViews* v) {
     im.ranges = carve<uint32_t>(p, (size_t)gx * gy * 2);
     im.n_contrib = carve<uint32_t>(p, (size_t)H * W);
     im.final_T = carve<float>(p, (size_t)H * W);
+    im.n_visited = carve<uint32_t>(p, (size_t)H * W);
     if (v) *v = im;
     return (size_t)(p - p0);
 }
@@ -139,6 +141,48 @@ static int make_camera(const b200splat_camera& c, int M, bool has_sh, CameraPara
     *out = p;
     return B200SPLAT_OK;
 }
+
+// ---- per-family CUDA-event timing ---------------------------------------------------------------
+struct ProfRecord {
+    int family;
+    cudaEvent_t a, b;
+};
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRecord> g_prof;
+static std::vector<cudaEvent_t> g_event_pool;
+
+static cudaEvent_t get_event() {
+    if (!g_event_pool.empty()) {
+        cudaEvent_t e = g_event_pool.back();
+        g_event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct ProfScope {
+    bool on = false;
+    ProfRecord r{};
+    cudaStream_t st;
+    ProfScope(int family, cudaStream_t s) : st(s) {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        if (!g_prof_on) return;
+        on = true;
+        r.family = family;
+        r.a = get_event();
+        r.b = get_event();
+        cudaEventRecord(r.a, st);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(r.b, st);
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_prof.push_back(r);
+    }
+};
 
 struct PinnedSlot {
     int64_t* host = nullptr;
@@ -206,10 +250,12 @@ int b200splat_forward(const b200splat_forward_args* a) {
         if (!a->geom_buffer || a->geom_bytes < geom_layout(P, nullptr, nullptr))
             return fail(B200SPLAT_ERR_NOMEM, "geom_buffer too small");
         geom_layout(P, a->geom_buffer, &g);
+        { ProfScope ps(0, st);
         CU(launch_preprocess(P, cam, a->means3D, a->scales, a->rotations, a->opacities, a->shs, a->colors_precomp,
-                             a->cov3D_precomp, a->radii, g, st));
+                             a->cov3D_precomp, a->radii, g, st)); }
         DEBUG_SYNC(a->cam, st, "preprocess");
-        CU(launch_inclusive_scan(P, g.tiles_touched, g.point_offsets, g.scan_ws, st));
+        { ProfScope ps(1, st);
+        CU(launch_inclusive_scan(P, g.tiles_touched, g.point_offsets, g.scan_ws, st)); }
         DEBUG_SYNC(a->cam, st, "scan");
         // the one host<->device round trip of the forward: num_rendered sizes the binning buffer
         PinnedSlot& slot = pinned();
@@ -230,20 +276,24 @@ int b200splat_forward(const b200splat_forward_args* a) {
         }
         if (a->binning_out) *a->binning_out = bbuf;
         binning_layout(R, bbuf, &bn);
-        CU(launch_duplicate(P, cam, a->radii, g, bn.keys[0], bn.vals[0], st));
+        { ProfScope ps(2, st);
+        CU(launch_duplicate(P, cam, a->radii, g, bn.keys[0], bn.vals[0], st)); }
         DEBUG_SYNC(a->cam, st, "duplicateWithKeys");
         int sel = 0;
-        CU(launch_sort_pairs(R, 32 + higher_msb((uint32_t)T), bn.keys, bn.vals, bn.sort_ws, &sel, st));
+        { ProfScope ps(3, st);
+        CU(launch_sort_pairs(R, 32 + higher_msb((uint32_t)T), bn.keys, bn.vals, bn.sort_ws, &sel, st)); }
         DEBUG_SYNC(a->cam, st, "sort");
         if (sel != sorted_sel_for(T)) return fail(B200SPLAT_ERR_CUDA, "internal: sort buffer parity mismatch");
-        CU(launch_tile_ranges(R, T, bn.keys[sel], im.ranges, st));
+        { ProfScope ps(4, st);
+        CU(launch_tile_ranges(R, T, bn.keys[sel], im.ranges, st)); }
         DEBUG_SYNC(a->cam, st, "identifyTileRanges");
         point_list = bn.vals[sel];
     } else {
         CU(cudaMemsetAsync(im.ranges, 0, (size_t)T * 8, st));
     }
-    CU(launch_render_forward(cam, im.ranges, point_list, g.rec, im.n_contrib, im.final_T, a->out_color, a->out_depth,
-                             a->out_alpha, st));
+    { ProfScope ps(5, st);
+    CU(launch_render_forward(cam, im.ranges, point_list, g.rec, im.n_contrib, im.n_visited, im.final_T, a->out_color,
+                             a->out_depth, a->out_alpha, st)); }
     DEBUG_SYNC(a->cam, st, "render");
     return B200SPLAT_OK;
 }
@@ -272,18 +322,24 @@ int b200splat_backward(const b200splat_backward_args* a) {
     geom_layout(P, const_cast<void*>(a->geom_buffer), &g);
     image_layout(cam.H, cam.W, const_cast<void*>(a->image_buffer), &im);
     float* grad2d = reinterpret_cast<float*>(a->scratch);
-    CU(cudaMemsetAsync(grad2d, 0, (size_t)P * GRAD2D_FLOATS * sizeof(float), st));
+    ProfScope* rb = new ProfScope(6, st);
+    cudaError_t me = cudaMemsetAsync(grad2d, 0, (size_t)P * GRAD2D_FLOATS * sizeof(float), st);
+    if (me != cudaSuccess) { delete rb; CU(me); }
     if (a->num_rendered > 0) {
         BinningViews bn;
         binning_layout(a->num_rendered, const_cast<void*>(a->binning_buffer), &bn);
         const uint32_t* point_list = bn.vals[sorted_sel(cam.H, cam.W)];
-        CU(launch_render_backward(cam, im.ranges, point_list, g.rec, im.n_contrib, im.final_T, a->dL_dout_color,
-                                  a->dL_dout_depth, a->dL_dout_alpha, grad2d, st));
-        DEBUG_SYNC(a->cam, st, "render backward");
+        cudaError_t re = launch_render_backward(cam, im.ranges, point_list, g.rec, im.n_contrib, im.final_T,
+                                                a->dL_dout_color, a->dL_dout_depth, a->dL_dout_alpha, grad2d, st);
+        if (re != cudaSuccess) { delete rb; CU(re); }
     }
+    delete rb;
+    DEBUG_SYNC(a->cam, st, "render backward");
+    { ProfScope ps(7, st);
     CU(launch_preprocess_backward(P, cam, a->means3D, a->scales, a->rotations, a->shs, a->cov3D_precomp, a->radii, g,
                                   grad2d, a->dL_dmeans3D, a->dL_dmeans2D, a->dL_dshs, a->dL_dcolors, a->dL_dopacity,
-                                  a->dL_dscales, a->dL_drotations, a->dL_dcov3D, a->accumulate, st));
+                                  a->dL_dscales, a->dL_drotations, a->dL_dcov3D, a->stat_grad_accum, a->stat_denom,
+                                  a->stat_max_radii, a->accumulate, st)); }
     DEBUG_SYNC(a->cam, st, "preprocess backward");
     return B200SPLAT_OK;
 }
@@ -300,7 +356,8 @@ int b200splat_dist2(int32_t P, const float* points, float* out, void* workspace,
     if (P < 0 || (P > 0 && (!points || !out))) return fail(B200SPLAT_ERR_INVALID, "bad argument");
     if (P > 0 && (!workspace || workspace_bytes < dist2_workspace_bytes(P)))
         return fail(B200SPLAT_ERR_NOMEM, "dist2 workspace too small");
-    CU(launch_dist2(P, points, out, workspace, reinterpret_cast<cudaStream_t>(stream)));
+    { ProfScope ps(8, reinterpret_cast<cudaStream_t>(stream));
+    CU(launch_dist2(P, points, out, workspace, reinterpret_cast<cudaStream_t>(stream))); }
     return B200SPLAT_OK;
 }
 
@@ -353,7 +410,31 @@ int b200splat_forward_views_get(int32_t P, int32_t H, int32_t W, int64_t num_ren
         image_layout(H, W, const_cast<void*>(image_buffer), &im);
         out->ranges = im.ranges;
         out->n_contrib = im.n_contrib;
+        out->n_visited = im.n_visited;
     }
+    return B200SPLAT_OK;
+}
+
+int b200splat_profile_enable(int32_t on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on = on != 0;
+    return B200SPLAT_OK;
+}
+
+int b200splat_profile_read(float* ms, int64_t* count) {
+    if (!ms || !count) return fail(B200SPLAT_ERR_INVALID, "null out");
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (int f = 0; f < B200SPLAT_NUM_FAMILIES; ++f) ms[f] = 0.f, count[f] = 0;
+    for (const ProfRecord& r : g_prof) {
+        float t = 0.f;
+        cudaError_t e = cudaEventSynchronize(r.b);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&t, r.a, r.b);
+        if (e != cudaSuccess) return fail(B200SPLAT_ERR_CUDA, "profile event: %s", cudaGetErrorString(e));
+        if (r.family >= 0 && r.family < B200SPLAT_NUM_FAMILIES) ms[r.family] += t, count[r.family] += 1;
+        g_event_pool.push_back(r.a);
+        g_event_pool.push_back(r.b);
+    }
+    g_prof.clear();
     return B200SPLAT_OK;
 }
 

@@ -65,6 +65,7 @@ struct ImageViews {
     uint32_t* ranges;        // T * 2
     uint32_t* n_contrib;     // H * W
     float* final_T;          // H * W  (transmittance after the last blended entry; 1 - alpha loses bits)
+    uint32_t* n_visited;     // H * W  (list entries traversed by the pixel in forward)
 };
 
 size_t geom_layout(int P, void* base, GeomViews* v);
@@ -90,8 +91,8 @@ cudaError_t launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_
 cudaError_t launch_tile_ranges(int64_t R, int T, const uint64_t* keys_sorted, uint32_t* ranges, cudaStream_t st);
 
 cudaError_t launch_render_forward(const CameraParams& cam, const uint32_t* ranges, const uint32_t* point_list,
-                                  const float* rec, uint32_t* n_contrib, float* final_T, float* out_color,
-                                  float* out_depth, float* out_alpha, cudaStream_t st);
+                                  const float* rec, uint32_t* n_contrib, uint32_t* n_visited, float* final_T,
+                                  float* out_color, float* out_depth, float* out_alpha, cudaStream_t st);
 cudaError_t launch_render_backward(const CameraParams& cam, const uint32_t* ranges, const uint32_t* point_list,
                                    const float* rec, const uint32_t* n_contrib, const float* final_T,
                                    const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
@@ -101,6 +102,7 @@ cudaError_t launch_preprocess_backward(int P, const CameraParams& cam, const flo
                                        const int32_t* radii, const GeomViews& g, const float* grad2d,
                                        float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dshs, float* dL_dcolors,
                                        float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dcov3D,
+                                       float* stat_grad_accum, float* stat_denom, float* stat_max_radii,
                                        int accumulate, cudaStream_t st);
 
 size_t dist2_workspace_bytes(int P);

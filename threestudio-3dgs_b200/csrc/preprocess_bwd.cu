@@ -95,7 +95,9 @@ preprocess_backward_kernel(int P, CameraParams cam, const float* __restrict__ me
                            float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dmeans2D,
                            float* __restrict__ dL_dshs, float* __restrict__ dL_dcolors,
                            float* __restrict__ dL_dopacity, float* __restrict__ dL_dscales,
-                           float* __restrict__ dL_drotations, float* __restrict__ dL_dcov3D) {
+                           float* __restrict__ dL_drotations, float* __restrict__ dL_dcov3D,
+                           float* __restrict__ stat_grad_accum, float* __restrict__ stat_denom,
+                           float* __restrict__ stat_max_radii) {
     __shared__ float sV[16], sP[16], sC[3];
     if (threadIdx.x < 16) {
         sV[threadIdx.x] = cam.view[threadIdx.x];
@@ -106,7 +108,8 @@ preprocess_backward_kernel(int P, CameraParams cam, const float* __restrict__ me
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P) return;
     const int M = cam.M;
-    if (radii[idx] <= 0) {
+    const int my_radius = radii[idx];
+    if (my_radius <= 0) {
         if (!ACC) {
             dL_dmeans3D[3 * idx] = dL_dmeans3D[3 * idx + 1] = dL_dmeans3D[3 * idx + 2] = 0.f;
             dL_dmeans2D[3 * idx] = dL_dmeans2D[3 * idx + 1] = dL_dmeans2D[3 * idx + 2] = 0.f;
@@ -285,6 +288,10 @@ preprocess_backward_kernel(int P, CameraParams cam, const float* __restrict__ me
     put<ACC>(dL_dmeans2D + 3 * idx + 1, gny);
     if (!ACC) dL_dmeans2D[3 * idx + 2] = 0.f;
     put<ACC>(dL_dopacity + idx, g_op);
+    // fused densification statistics of this view (geometry/gaussian_base.py:815-819, 846-851)
+    if (stat_grad_accum) stat_grad_accum[idx] += sqrtf(gnx * gnx + gny * gny);
+    if (stat_denom) stat_denom[idx] += 1.0f;
+    if (stat_max_radii) stat_max_radii[idx] = fmaxf(stat_max_radii[idx], (float)my_radius);
 }
 
 cudaError_t launch_preprocess_backward(int P, const CameraParams& cam, const float* means3D, const float* scales,
@@ -292,17 +299,20 @@ cudaError_t launch_preprocess_backward(int P, const CameraParams& cam, const flo
                                        const int32_t* radii, const GeomViews& g, const float* grad2d,
                                        float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dshs, float* dL_dcolors,
                                        float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dcov3D,
+                                       float* stat_grad_accum, float* stat_denom, float* stat_max_radii,
                                        int accumulate, cudaStream_t st) {
     if (P <= 0) return cudaSuccess;
     const int grid = (P + 255) / 256;
     if (accumulate)
         preprocess_backward_kernel<true><<<grid, 256, 0, st>>>(
             P, cam, means3D, scales, rotations, shs, cov3D_precomp, radii, g.cov3D, g.clamped, grad2d, dL_dmeans3D,
-            dL_dmeans2D, dL_dshs, dL_dcolors, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D);
+            dL_dmeans2D, dL_dshs, dL_dcolors, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D, stat_grad_accum,
+            stat_denom, stat_max_radii);
     else
         preprocess_backward_kernel<false><<<grid, 256, 0, st>>>(
             P, cam, means3D, scales, rotations, shs, cov3D_precomp, radii, g.cov3D, g.clamped, grad2d, dL_dmeans3D,
-            dL_dmeans2D, dL_dshs, dL_dcolors, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D);
+            dL_dmeans2D, dL_dshs, dL_dcolors, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D, stat_grad_accum,
+            stat_denom, stat_max_radii);
     count_launch();
     return cudaGetLastError();
 }

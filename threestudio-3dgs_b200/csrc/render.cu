@@ -80,8 +80,8 @@ __device__ __forceinline__ void stage_batch(float4* buf, uint32_t* ids, uint64_t
 __global__ void __launch_bounds__(BLOCK_SIZE)
 render_forward_kernel(int W, int H, int grid_x, const uint32_t* __restrict__ ranges,
                       const uint32_t* __restrict__ point_list, const float* __restrict__ rec,
-                      const float* __restrict__ bg, uint32_t* __restrict__ n_contrib, float* __restrict__ final_T,
-                      float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_alpha) {
+                      const float* __restrict__ bg, uint32_t* __restrict__ n_contrib, uint32_t* __restrict__ n_visited,
+                      float* __restrict__ final_T, float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_alpha) {
     __shared__ __align__(16) float4 s_rec[STAGES][BATCH * 3];
     __shared__ __align__(8) uint64_t s_bar[STAGES];
 
@@ -154,6 +154,7 @@ render_forward_kernel(int W, int H, int grid_x, const uint32_t* __restrict__ ran
         const size_t HW = (size_t)H * W;
         n_contrib[pix] = last_contributor;
         final_T[pix] = T;
+        n_visited[pix] = contributor;
         out_color[pix] = C0 + T * bg[0];
         out_color[HW + pix] = C1 + T * bg[1];
         out_color[2 * HW + pix] = C2 + T * bg[2];
@@ -307,11 +308,11 @@ render_backward_kernel(int W, int H, int grid_x, const uint32_t* __restrict__ ra
 }
 
 cudaError_t launch_render_forward(const CameraParams& cam, const uint32_t* ranges, const uint32_t* point_list,
-                                  const float* rec, uint32_t* n_contrib, float* final_T, float* out_color,
-                                  float* out_depth, float* out_alpha, cudaStream_t st) {
+                                  const float* rec, uint32_t* n_contrib, uint32_t* n_visited, float* final_T,
+                                  float* out_color, float* out_depth, float* out_alpha, cudaStream_t st) {
     dim3 grid(cam.grid_x, cam.grid_y);
     render_forward_kernel<<<grid, BLOCK_SIZE, 0, st>>>(cam.W, cam.H, cam.grid_x, ranges, point_list, rec, cam.bg,
-                                                       n_contrib, final_T, out_color, out_depth, out_alpha);
+                                                       n_contrib, n_visited, final_T, out_color, out_depth, out_alpha);
     count_launch();
     return cudaGetLastError();
 }
