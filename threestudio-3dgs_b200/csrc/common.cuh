@@ -22,7 +22,8 @@ constexpr float T_MIN = 0.0001f;
 constexpr float PW_EPS = 0.0000001f;
 
 // per-Gaussian 2-D record written by preprocess and gathered by the render kernels (48 B, 16 B aligned)
-//   q0 = (x, y, conic_a, conic_b)   q1 = (conic_c, opacity, depth, r)   q2 = (g, b, 0, 0)
+//   q0 = (x, y, conic_a, conic_b)   q1 = (conic_c, opacity, depth, r)   q2 = (g, b, cull_thr, 0)
+//   cull_thr = 2 ln(255 opacity) + margin: the largest value of the conic quadratic at which alpha >= 1/255
 constexpr int REC_FLOATS = 12;
 // packed 2-D stage gradients accumulated by render-backward (48 B per Gaussian)
 //   g0 = (dx, dy, dconic_a, dconic_b)  g1 = (dconic_c, dopacity, dr, dg)  g2 = (db, ddepth, 0, 0)

@@ -214,7 +214,10 @@ preprocess_kernel(int P, CameraParams cam, const float* __restrict__ means3D, co
                 float4* o = reinterpret_cast<float4*>(rec) + 3 * (size_t)idx;
                 o[0] = make_float4(px, py, c * det_inv, -b * det_inv);
                 o[1] = make_float4(a * det_inv, __ldg(opacities + idx), tvz, rgb[0]);
-                o[2] = make_float4(rgb[1], rgb[2], 0.0f, 0.0f);
+                // cull threshold of the render kernels: alpha >= 1/255 needs A dx^2 + 2B dx dy + C dy^2 <= 2 ln(255 o)
+                const float opac = __ldg(opacities + idx);
+                const float thr = opac > 0.0f ? 2.0f * __logf(255.0f * opac) + 0.002f : -1.0f;
+                o[2] = make_float4(rgb[1], rgb[2], thr, 0.0f);
                 depths[idx] = tvz;
                 float2* co = reinterpret_cast<float2*>(cov3D_out) + 3 * (size_t)idx;
                 co[0] = make_float2(c0, c1);

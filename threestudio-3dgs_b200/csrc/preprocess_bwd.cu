@@ -70,17 +70,60 @@ __device__ __forceinline__ void sh_backward(const float* __restrict__ sh, float*
         By[15] = SH_C3_6 * -6.f * x * y, Bz[15] = 0.f;
     }
     float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+    if ((M & 3) == 0 && M <= 16) {
+        // 16-byte path: 4 coefficients (12 floats = 3 float4) per step; per-Gaussian base is 16 B aligned
+        const float4* __restrict__ in4 = reinterpret_cast<const float4*>(sh);
+        float4* __restrict__ out4 = reinterpret_cast<float4*>(dsh);
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const float s0 = __ldg(sh + 3 * k), s1 = __ldg(sh + 3 * k + 1), s2 = __ldg(sh + 3 * k + 2);
-        const float gs = g[0] * s0 + g[1] * s1 + g[2] * s2;
-        ddx += Bx[k] * gs, ddy += By[k] * gs, ddz += Bz[k] * gs;
-        put<ACC>(dsh + 3 * k, B[k] * g[0]);
-        put<ACC>(dsh + 3 * k + 1, B[k] * g[1]);
-        put<ACC>(dsh + 3 * k + 2, B[k] * g[2]);
-    }
-    if (!ACC) {
-        for (int k = 3 * K; k < 3 * M; ++k) dsh[k] = 0.f;
+        for (int k0 = 0; k0 < 16; k0 += 4) {
+            if (k0 >= M) break;
+            float o[12];
+            if (k0 < K) {
+                const float4 a = __ldg(in4 + 3 * (k0 >> 2)), b = __ldg(in4 + 3 * (k0 >> 2) + 1),
+                             c = __ldg(in4 + 3 * (k0 >> 2) + 2);
+                const float sv[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    // K is a compile-time constant: the k < K test folds after unrolling of the caller's DEG
+                    const int kk = (k0 + t < K) ? k0 + t : 0;   // compile-time after unrolling
+                    const bool live = k0 + t < K;
+                    const float Bk = live ? B[kk] : 0.f, Bxk = live ? Bx[kk] : 0.f, Byk = live ? By[kk] : 0.f,
+                                Bzk = live ? Bz[kk] : 0.f;
+                    const float gs = g[0] * sv[3 * t] + g[1] * sv[3 * t + 1] + g[2] * sv[3 * t + 2];
+                    ddx += Bxk * gs, ddy += Byk * gs, ddz += Bzk * gs;
+                    o[3 * t] = Bk * g[0], o[3 * t + 1] = Bk * g[1], o[3 * t + 2] = Bk * g[2];
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < 12; ++t) o[t] = 0.f;
+            }
+            float4* dst = out4 + 3 * (k0 >> 2);
+            if (ACC) {
+                if (k0 < K) {
+                    const float4 p0 = dst[0], p1 = dst[1], p2 = dst[2];
+                    dst[0] = make_float4(p0.x + o[0], p0.y + o[1], p0.z + o[2], p0.w + o[3]);
+                    dst[1] = make_float4(p1.x + o[4], p1.y + o[5], p1.z + o[6], p1.w + o[7]);
+                    dst[2] = make_float4(p2.x + o[8], p2.y + o[9], p2.z + o[10], p2.w + o[11]);
+                }
+            } else {
+                dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+                dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+                dst[2] = make_float4(o[8], o[9], o[10], o[11]);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float s0 = __ldg(sh + 3 * k), s1 = __ldg(sh + 3 * k + 1), s2 = __ldg(sh + 3 * k + 2);
+            const float gs = g[0] * s0 + g[1] * s1 + g[2] * s2;
+            ddx += Bx[k] * gs, ddy += By[k] * gs, ddz += Bz[k] * gs;
+            put<ACC>(dsh + 3 * k, B[k] * g[0]);
+            put<ACC>(dsh + 3 * k + 1, B[k] * g[1]);
+            put<ACC>(dsh + 3 * k + 2, B[k] * g[2]);
+        }
+        if (!ACC) {
+            for (int k = 3 * K; k < 3 * M; ++k) dsh[k] = 0.f;
+        }
     }
     dd[0] = ddx, dd[1] = ddy, dd[2] = ddz;
 }

@@ -5,23 +5,32 @@
 // (_blend_tile); reference consumers renderer/diff_gaussian_rasterizer_advanced.py:122-146.
 //
 // B200 design:
-//  * one CTA per tile, 8 warps, each warp owns an 8x4 pixel block (coherent skip tests);
-//  * the tile's Gaussian list is consumed in batches of 256 entries; each thread stages one
-//    48-byte record (csrc/common.cuh REC layout) with ONE bulk async copy (cp.async.bulk ->
-//    UBLKCP) completing on an mbarrier, double buffered, so the gather of batch k+1 overlaps
-//    the blend of batch k;
+//  * one CTA per tile, 8 warps, each warp owns an 8x4 pixel block;
+//  * the tile's Gaussian list is consumed in batches of 256 entries, double buffered in shared
+//    memory behind mbarriers: each thread gathers one 48-byte record (common.cuh REC layout) either
+//    with one bulk async copy (cp.async.bulk -> UBLKCP, complete_tx on the mbarrier) or with three
+//    16-byte cp.async (LDGSTS) whose completion arrives on the same mbarrier, so the gather of batch
+//    k+1 overlaps the blend of batch k;
+//  * warp-cooperative culling: for every 32 staged entries, lane l bounds entry l's best-case alpha
+//    over the warp's 8x4 pixel rectangle (exact minimum of the conic quadratic over the rectangle
+//    edges); only entries that can reach alpha >= 1/255 somewhere in the rectangle are evaluated by
+//    the 32 pixels.  Culling is conservative, so the set of blended (pixel, Gaussian) pairs -- and
+//    therefore the image, n_contrib and the gradients -- are exactly those of the unculled loop;
 //  * forward terminates a tile as soon as every pixel is saturated (T' < 1e-4);
-//  * backward walks back to front starting at the tile's largest n_contrib, skips entries no
-//    lane of the warp blended, and reduces the 10 per-Gaussian partial gradients across the
-//    warp with shuffles before a single set of global atomics per (warp, Gaussian).
+//  * backward walks back to front starting at the tile's largest n_contrib, and reduces the 10
+//    per-Gaussian partial gradients across the warp with a 12-shuffle transposed butterfly before
+//    one 10-lane global atomic per (warp, Gaussian).
 #include "common.cuh"
+
+#include <cstdlib>
+#include <cstring>
 
 namespace b200splat {
 
 constexpr int BATCH = 256;
 constexpr int STAGES = 2;
 
-// ---- mbarrier / bulk-copy PTX ------------------------------------------------------------------
+// ---- mbarrier / async-copy PTX ----------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -53,6 +62,12 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
 // pixel owned by this thread: warp w -> 8x4 block (w%2, w/2), lane -> (l%8, l/8)
 __device__ __forceinline__ void thread_pixel(int& lx, int& ly) {
@@ -61,36 +76,74 @@ __device__ __forceinline__ void thread_pixel(int& lx, int& ly) {
     ly = (warp >> 1) * 4 + (lane >> 3);
 }
 
-// stage one batch: thread t copies the record of list entry (first + t) into buf[t]
+// stage one batch: thread t gathers the record of list entry `pos` into buf[t]
+template <bool BULK>
 __device__ __forceinline__ void stage_batch(float4* buf, uint32_t* ids, uint64_t* bar, const float* __restrict__ rec,
                                             const uint32_t* __restrict__ point_list, int64_t pos, bool valid) {
     if (valid) {
         const uint32_t id = __ldg(point_list + pos);
         if (ids) ids[threadIdx.x] = id;
-        mbar_arrive_expect_tx(bar, REC_FLOATS * 4);
-        bulk_g2s(buf + 3 * threadIdx.x, rec + (size_t)id * REC_FLOATS, REC_FLOATS * 4, bar);
+        const float* src = rec + (size_t)id * REC_FLOATS;
+        float4* dst = buf + 3 * threadIdx.x;
+        if (BULK) {
+            mbar_arrive_expect_tx(bar, REC_FLOATS * 4);
+            bulk_g2s(dst, src, REC_FLOATS * 4, bar);
+        } else {
+            cp_async16(dst, src);
+            cp_async16(dst + 1, src + 4);
+            cp_async16(dst + 2, src + 8);
+            cp_async_arrive_noinc(bar);
+        }
     } else {
         mbar_arrive(bar);
     }
 }
 
+// Conservative test: can entry (x, y, conic A,B,C, threshold thr = 2 ln(255 o) + margin) reach
+// alpha >= 1/255 at some point of the rectangle [X0,X1] x [Y0,Y1]?  f = A dx^2 + 2 B dx dy + C dy^2 is
+// minimised exactly over the four edges (convex when the conic is positive definite; otherwise keep).
+__device__ __forceinline__ bool cull_keep(const float4 q0, const float C, const float thr, float X0, float X1,
+                                          float Y0, float Y1) {
+    const float A = q0.z, B = q0.w;
+    const float dx0 = q0.x - X0, dx1 = q0.x - X1, dy0 = q0.y - Y0, dy1 = q0.y - Y1;
+    const bool convex = (A > 0.f) && (C > 0.f) && (A * C - B * B > 0.f);
+    const bool inside = (dx0 >= 0.f) && (dx1 <= 0.f) && (dy0 >= 0.f) && (dy1 <= 0.f);
+    const float iC = __fdividef(1.f, C), iA = __fdividef(1.f, A);
+    // lower bound of f at (dx,dy): value minus a 64-ulp bound on the rounding of both this evaluation and
+    // the per-pixel one (terms can cancel for elongated Gaussians)
+    auto lower = [&](float dx, float dy) {
+        const float t1 = A * dx * dx, t2 = 2.f * B * dx * dy, t3 = C * dy * dy;
+        return (t1 + t2 + t3) - 8e-6f * (t1 + fabsf(t2) + t3);
+    };
+    float fmin = lower(dx0, fminf(dy0, fmaxf(dy1, -B * dx0 * iC)));
+    fmin = fminf(fmin, lower(dx1, fminf(dy0, fmaxf(dy1, -B * dx1 * iC))));
+    fmin = fminf(fmin, lower(fminf(dx0, fmaxf(dx1, -B * dy0 * iA)), dy0));
+    fmin = fminf(fmin, lower(fminf(dx0, fmaxf(dx1, -B * dy1 * iA)), dy1));
+    return !convex || inside || !(fmin > thr);
+}
+
 // ============================================================================================
 // K6 forward
 // ============================================================================================
+template <bool BULK>
 __global__ void __launch_bounds__(BLOCK_SIZE)
 render_forward_kernel(int W, int H, int grid_x, const uint32_t* __restrict__ ranges,
                       const uint32_t* __restrict__ point_list, const float* __restrict__ rec,
                       const float* __restrict__ bg, uint32_t* __restrict__ n_contrib, uint32_t* __restrict__ n_visited,
-                      float* __restrict__ final_T, float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_alpha) {
+                      float* __restrict__ final_T, float* __restrict__ out_color, float* __restrict__ out_depth,
+                      float* __restrict__ out_alpha) {
     __shared__ __align__(16) float4 s_rec[STAGES][BATCH * 3];
     __shared__ __align__(8) uint64_t s_bar[STAGES];
 
     const int tile = blockIdx.y * grid_x + blockIdx.x;
     int lx, ly;
     thread_pixel(lx, ly);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int pxi = blockIdx.x * BLOCK_X + lx, pyi = blockIdx.y * BLOCK_Y + ly;
     const bool inside = pxi < W && pyi < H;
     const float pixx = (float)pxi, pixy = (float)pyi;
+    const float X0 = (float)(blockIdx.x * BLOCK_X + (warp & 1) * 8), X1 = X0 + 7.f;
+    const float Y0 = (float)(blockIdx.y * BLOCK_Y + (warp >> 1) * 4), Y1 = Y0 + 3.f;
     const uint32_t r0 = ranges[2 * tile], r1 = ranges[2 * tile + 1];
     const int total = (int)(r1 - r0);
     const int rounds = (total + BATCH - 1) / BATCH;
@@ -104,10 +157,12 @@ render_forward_kernel(int W, int H, int grid_x, const uint32_t* __restrict__ ran
 
     bool done = !inside;
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Wt = 0.f, D = 0.f;
-    uint32_t contributor = 0, last_contributor = 0;
+    uint32_t last_contributor = 0, visited = 0;
+    int traversed = 0;
 
-    if (rounds > 0) stage_batch(s_rec[0], nullptr, &s_bar[0], rec, point_list, (int64_t)r0 + threadIdx.x,
-                                (int)threadIdx.x < total);
+    if (rounds > 0)
+        stage_batch<BULK>(s_rec[0], nullptr, &s_bar[0], rec, point_list, (int64_t)r0 + threadIdx.x,
+                          (int)threadIdx.x < total);
     for (int b = 0; b < rounds; ++b) {
         // also orders "everyone finished reading stage (b+1)&1" before it is refilled
         const int num_done = __syncthreads_count(done);
@@ -119,42 +174,58 @@ render_forward_kernel(int W, int H, int grid_x, const uint32_t* __restrict__ ran
         }
         if (b + 1 < rounds) {
             const int nb = (b + 1) * BATCH + threadIdx.x;
-            stage_batch(s_rec[s ^ 1], nullptr, &s_bar[s ^ 1], rec, point_list, (int64_t)r0 + nb, nb < total);
+            stage_batch<BULK>(s_rec[s ^ 1], nullptr, &s_bar[s ^ 1], rec, point_list, (int64_t)r0 + nb, nb < total);
         }
         mbar_wait(&s_bar[s], (b >> 1) & 1);
         const int count = min(BATCH, total - b * BATCH);
+        traversed = b * BATCH + count;
         const float4* __restrict__ buf = s_rec[s];
-        for (int j = 0; !done && j < count; ++j) {
-            ++contributor;
-            const float4 q0 = buf[3 * j];
-            const float4 q1 = buf[3 * j + 1];
-            const float dx = q0.x - pixx, dy = q0.y - pixy;
-            const float power = -0.5f * (q0.z * dx * dx + q1.x * dy * dy) - q0.w * dx * dy;
-            if (power > 0.0f) continue;
-            const float alpha = fminf(ALPHA_MAX, q1.y * __expf(power));
-            if (alpha < ALPHA_MIN) continue;
-            const float test_T = T * (1.0f - alpha);
-            if (test_T < T_MIN) {
-                done = true;
-                continue;
+        for (int c0 = 0; c0 < count; c0 += 32) {
+            if (__all_sync(0xffffffffu, done)) break;
+            bool keep = false;
+            if (c0 + lane < count) {
+                const float4 q0 = buf[3 * (c0 + lane)];
+                const float4 q1 = buf[3 * (c0 + lane) + 1];
+                const float thr = buf[3 * (c0 + lane) + 2].z;
+                keep = cull_keep(q0, q1.x, thr, X0, X1, Y0, Y1);
             }
-            const float4 q2 = buf[3 * j + 2];
-            const float w = alpha * T;
-            C0 += q1.w * w;
-            C1 += q2.x * w;
-            C2 += q2.y * w;
-            Wt += w;
-            D += q1.z * w;
-            T = test_T;
-            last_contributor = contributor;
+            uint32_t mask = __ballot_sync(0xffffffffu, keep);
+            while (mask) {
+                const int j = c0 + __ffs(mask) - 1;
+                mask &= mask - 1;
+                if (done) continue;
+                const float4 q0 = buf[3 * j];
+                const float4 q1 = buf[3 * j + 1];
+                const float dx = q0.x - pixx, dy = q0.y - pixy;
+                const float power = -0.5f * (q0.z * dx * dx + q1.x * dy * dy) - q0.w * dx * dy;
+                if (power > 0.0f) continue;
+                const float alpha = fminf(ALPHA_MAX, q1.y * __expf(power));
+                if (alpha < ALPHA_MIN) continue;
+                const float test_T = T * (1.0f - alpha);
+                const uint32_t position = (uint32_t)(b * BATCH + j + 1);
+                if (test_T < T_MIN) {
+                    done = true;
+                    visited = position;
+                    continue;
+                }
+                const float4 q2 = buf[3 * j + 2];
+                const float w = alpha * T;
+                C0 += q1.w * w;
+                C1 += q2.x * w;
+                C2 += q2.y * w;
+                Wt += w;
+                D += q1.z * w;
+                T = test_T;
+                last_contributor = position;
+            }
         }
     }
     if (inside) {
         const int pix = pyi * W + pxi;
         const size_t HW = (size_t)H * W;
         n_contrib[pix] = last_contributor;
+        n_visited[pix] = visited ? visited : (uint32_t)traversed;
         final_T[pix] = T;
-        n_visited[pix] = contributor;
         out_color[pix] = C0 + T * bg[0];
         out_color[HW + pix] = C1 + T * bg[1];
         out_color[2 * HW + pix] = C2 + T * bg[2];
@@ -166,12 +237,64 @@ render_forward_kernel(int W, int H, int grid_x, const uint32_t* __restrict__ ran
 // ============================================================================================
 // K7 backward
 // ============================================================================================
-__device__ __forceinline__ float warp_sum(float v) {
+
+// Sum 10 per-lane values over the 32 lanes with 12 shuffles (transposed butterfly): after the call the
+// lane whose slot (see reduce_slot) is k holds the warp total of v[k] in the return value.
+__device__ __forceinline__ float warp_reduce10(const float v[10], int lane) {
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+    float a[5];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+    for (int k = 0; k < 5; ++k) {
+        const float send = b4 ? v[k] : v[k + 5];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+        a[k] = (b4 ? v[k + 5] : v[k]) + recv;
+    }
+    float c[3];
+    {
+        // keep (a0,a1,a2) when b3 == 0, (a3,a4,-) when b3 == 1
+        float send = b3 ? a[0] : a[3];
+        float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+        c[0] = (b3 ? a[3] : a[0]) + recv;
+        send = b3 ? a[1] : a[4];
+        recv = __shfl_xor_sync(0xffffffffu, send, 8);
+        c[1] = (b3 ? a[4] : a[1]) + recv;
+        send = b3 ? a[2] : 0.f;
+        recv = __shfl_xor_sync(0xffffffffu, send, 8);
+        c[2] = (b3 ? 0.f : a[2]) + recv;
+    }
+    float d[2];
+    {
+        // keep (c0,c1) when b2 == 0, (c2,-) when b2 == 1
+        float send = b2 ? c[0] : c[2];
+        float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+        d[0] = (b2 ? c[2] : c[0]) + recv;
+        send = b2 ? c[1] : 0.f;
+        recv = __shfl_xor_sync(0xffffffffu, send, 4);
+        d[1] = (b2 ? 0.f : c[1]) + recv;
+    }
+    float e;
+    {
+        const float send = b1 ? d[0] : d[1];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+        e = (b1 ? d[1] : d[0]) + recv;
+    }
+    e += __shfl_xor_sync(0xffffffffu, e, 1);
+    return e;
+}
+// index k (0..9) of the value a lane ends up holding, or -1
+__device__ __forceinline__ int reduce_slot(int lane) {
+    if (lane & 1) return -1;
+    const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1, b1 = (lane >> 1) & 1;
+    int k;
+    if (!b3) {
+        if (!b2) k = b1; else k = b1 ? -1 : 2;
+    } else {
+        if (!b2) k = 3 + b1; else k = -1;
+    }
+    return k < 0 ? -1 : 5 * b4 + k;
 }
 
+template <bool BULK>
 __global__ void __launch_bounds__(BLOCK_SIZE)
 render_backward_kernel(int W, int H, int grid_x, const uint32_t* __restrict__ ranges,
                        const uint32_t* __restrict__ point_list, const float* __restrict__ rec,
@@ -187,10 +310,12 @@ render_backward_kernel(int W, int H, int grid_x, const uint32_t* __restrict__ ra
     const int tile = blockIdx.y * grid_x + blockIdx.x;
     int lx, ly;
     thread_pixel(lx, ly);
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int pxi = blockIdx.x * BLOCK_X + lx, pyi = blockIdx.y * BLOCK_Y + ly;
     const bool inside = pxi < W && pyi < H;
     const float pixx = (float)pxi, pixy = (float)pyi;
+    const float X0 = (float)(blockIdx.x * BLOCK_X + (warp & 1) * 8), X1 = X0 + 7.f;
+    const float Y0 = (float)(blockIdx.y * BLOCK_Y + (warp >> 1) * 4), Y1 = Y0 + 3.f;
     const int pix = pyi * W + pxi;
     const size_t HW = (size_t)H * W;
     const uint32_t r0 = ranges[2 * tile];
@@ -203,16 +328,15 @@ render_backward_kernel(int W, int H, int grid_x, const uint32_t* __restrict__ ra
     }
     __syncthreads();
     const uint32_t my_last = inside ? n_contrib[pix] : 0u;
-    {
-        uint32_t m = my_last;
+    uint32_t warp_last = my_last;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (lane == 0 && m) atomicMax(&s_max, m);
-    }
+    for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, o));
+    if (lane == 0 && warp_last) atomicMax(&s_max, warp_last);
     __syncthreads();
     const int total = (int)s_max;  // entries [0,total) of the tile's list can have contributed
     if (total == 0) return;
     const int rounds = (total + BATCH - 1) / BATCH;
+    const int slot = reduce_slot(lane);
 
     const float T_final = inside ? final_T[pix] : 0.0f;
     float T = T_final;
@@ -229,90 +353,108 @@ render_backward_kernel(int W, int H, int grid_x, const uint32_t* __restrict__ ra
     // batch b holds list positions total-1-(b*256+t), t = 0..255 (back to front)
     {
         const int p = (int)threadIdx.x;
-        stage_batch(s_rec[0], s_ids[0], &s_bar[0], rec, point_list, (int64_t)r0 + (total - 1 - p), p < total);
+        stage_batch<BULK>(s_rec[0], s_ids[0], &s_bar[0], rec, point_list, (int64_t)r0 + (total - 1 - p), p < total);
     }
     for (int b = 0; b < rounds; ++b) {
         __syncthreads();
         const int s = b & 1;
         if (b + 1 < rounds) {
             const int p = (b + 1) * BATCH + threadIdx.x;
-            stage_batch(s_rec[s ^ 1], s_ids[s ^ 1], &s_bar[s ^ 1], rec, point_list, (int64_t)r0 + (total - 1 - p),
-                        p < total);
+            stage_batch<BULK>(s_rec[s ^ 1], s_ids[s ^ 1], &s_bar[s ^ 1], rec, point_list,
+                              (int64_t)r0 + (total - 1 - p), p < total);
         }
         mbar_wait(&s_bar[s], (b >> 1) & 1);
         const int count = min(BATCH, total - b * BATCH);
         const float4* __restrict__ buf = s_rec[s];
-        for (int j = 0; j < count; ++j) {
-            const uint32_t q = (uint32_t)(total - 1 - (b * BATCH + j));  // 0-based list position
-            const float4 q0 = buf[3 * j];
-            const float4 q1 = buf[3 * j + 1];
-            const float dx = q0.x - pixx, dy = q0.y - pixy;
-            const float power = -0.5f * (q0.z * dx * dx + q1.x * dy * dy) - q0.w * dx * dy;
-            const float G = __expf(power);
-            const float alpha = fminf(ALPHA_MAX, q1.y * G);
-            const bool hit = (q < my_last) && (power <= 0.0f) && (alpha >= ALPHA_MIN);
-            if (!__any_sync(0xffffffffu, hit)) continue;
-            float v_dx = 0.f, v_dy = 0.f, v_ca = 0.f, v_cb = 0.f, v_cc = 0.f, v_op = 0.f, v_r = 0.f, v_g = 0.f,
-                  v_b = 0.f, v_d = 0.f;
-            if (hit) {
-                const float4 q2 = buf[3 * j + 2];
-                T = T / (1.0f - alpha);
-                const float w = alpha * T;
-                float dL_da = 0.f;
-                acc0 = last_alpha * lc0 + (1.0f - last_alpha) * acc0;
-                lc0 = q1.w;
-                dL_da += (q1.w - acc0) * gC0;
-                acc1 = last_alpha * lc1 + (1.0f - last_alpha) * acc1;
-                lc1 = q2.x;
-                dL_da += (q2.x - acc1) * gC1;
-                acc2 = last_alpha * lc2 + (1.0f - last_alpha) * acc2;
-                lc2 = q2.y;
-                dL_da += (q2.y - acc2) * gC2;
-                accD = last_alpha * lD + (1.0f - last_alpha) * accD;
-                lD = q1.z;
-                dL_da += (q1.z - accD) * gD;
-                accA = last_alpha + (1.0f - last_alpha) * accA;
-                dL_da += (1.0f - accA) * gA;
-                dL_da *= T;
-                last_alpha = alpha;
-                dL_da += (-T_final / (1.0f - alpha)) * bg_dot;
-                v_r = w * gC0, v_g = w * gC1, v_b = w * gC2, v_d = w * gD;
-                const float dL_dG = q1.y * dL_da;
-                const float gdx = G * dx, gdy = G * dy;
-                // power = -0.5 (A dx^2 + C dy^2) - B dx dy, d = mean - pixel
-                v_dx = dL_dG * (-gdx * q0.z - gdy * q0.w);
-                v_dy = dL_dG * (-gdy * q1.x - gdx * q0.w);
-                v_ca = -0.5f * gdx * dx * dL_dG;
-                v_cb = -gdx * dy * dL_dG;
-                v_cc = -0.5f * gdy * dy * dL_dG;
-                v_op = G * dL_da;
+        for (int c0 = 0; c0 < count; c0 += 32) {
+            bool keep = false;
+            {
+                const int e = c0 + lane;
+                const uint32_t q = (uint32_t)(total - 1 - (b * BATCH + e));  // 0-based list position
+                if (e < count && q < warp_last) {
+                    const float4 q0 = buf[3 * e];
+                    const float4 q1 = buf[3 * e + 1];
+                    const float thr = buf[3 * e + 2].z;
+                    keep = cull_keep(q0, q1.x, thr, X0, X1, Y0, Y1);
+                }
             }
-            v_dx = warp_sum(v_dx), v_dy = warp_sum(v_dy), v_ca = warp_sum(v_ca), v_cb = warp_sum(v_cb);
-            v_cc = warp_sum(v_cc), v_op = warp_sum(v_op), v_r = warp_sum(v_r), v_g = warp_sum(v_g);
-            v_b = warp_sum(v_b), v_d = warp_sum(v_d);
-            if (lane < 10) {
-                float v = v_dx;
-                v = lane == 1 ? v_dy : v;
-                v = lane == 2 ? v_ca : v;
-                v = lane == 3 ? v_cb : v;
-                v = lane == 4 ? v_cc : v;
-                v = lane == 5 ? v_op : v;
-                v = lane == 6 ? v_r : v;
-                v = lane == 7 ? v_g : v;
-                v = lane == 8 ? v_b : v;
-                v = lane == 9 ? v_d : v;
-                atomicAdd(grad2d + (size_t)s_ids[s][j] * GRAD2D_FLOATS + lane, v);
+            uint32_t mask = __ballot_sync(0xffffffffu, keep);
+            while (mask) {
+                const int j = c0 + __ffs(mask) - 1;
+                mask &= mask - 1;
+                const uint32_t q = (uint32_t)(total - 1 - (b * BATCH + j));
+                const float4 q0 = buf[3 * j];
+                const float4 q1 = buf[3 * j + 1];
+                const float dx = q0.x - pixx, dy = q0.y - pixy;
+                const float power = -0.5f * (q0.z * dx * dx + q1.x * dy * dy) - q0.w * dx * dy;
+                const float G = __expf(power);
+                const float alpha = fminf(ALPHA_MAX, q1.y * G);
+                const bool hit = (q < my_last) && (power <= 0.0f) && (alpha >= ALPHA_MIN);
+                if (!__any_sync(0xffffffffu, hit)) continue;
+                float v[10];
+#pragma unroll
+                for (int k = 0; k < 10; ++k) v[k] = 0.f;
+                if (hit) {
+                    const float4 q2 = buf[3 * j + 2];
+                    T = T / (1.0f - alpha);
+                    const float w = alpha * T;
+                    float dL_da = 0.f;
+                    acc0 = last_alpha * lc0 + (1.0f - last_alpha) * acc0;
+                    lc0 = q1.w;
+                    dL_da += (q1.w - acc0) * gC0;
+                    acc1 = last_alpha * lc1 + (1.0f - last_alpha) * acc1;
+                    lc1 = q2.x;
+                    dL_da += (q2.x - acc1) * gC1;
+                    acc2 = last_alpha * lc2 + (1.0f - last_alpha) * acc2;
+                    lc2 = q2.y;
+                    dL_da += (q2.y - acc2) * gC2;
+                    accD = last_alpha * lD + (1.0f - last_alpha) * accD;
+                    lD = q1.z;
+                    dL_da += (q1.z - accD) * gD;
+                    accA = last_alpha + (1.0f - last_alpha) * accA;
+                    dL_da += (1.0f - accA) * gA;
+                    dL_da *= T;
+                    last_alpha = alpha;
+                    dL_da += (-T_final / (1.0f - alpha)) * bg_dot;
+                    const float dL_dG = q1.y * dL_da;
+                    const float gdx = G * dx, gdy = G * dy;
+                    // power = -0.5 (A dx^2 + C dy^2) - B dx dy, d = mean - pixel
+                    v[0] = dL_dG * (-gdx * q0.z - gdy * q0.w);
+                    v[1] = dL_dG * (-gdy * q1.x - gdx * q0.w);
+                    v[2] = -0.5f * gdx * dx * dL_dG;
+                    v[3] = -gdx * dy * dL_dG;
+                    v[4] = -0.5f * gdy * dy * dL_dG;
+                    v[5] = G * dL_da;
+                    v[6] = w * gC0, v[7] = w * gC1, v[8] = w * gC2, v[9] = w * gD;
+                }
+                const float r = warp_reduce10(v, lane);
+                if (slot >= 0) atomicAdd(grad2d + (size_t)s_ids[s][j] * GRAD2D_FLOATS + slot, r);
             }
         }
     }
+}
+
+static bool use_bulk_staging() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("B200SPLAT_STAGING");
+        mode = (e && strcmp(e, "bulk") == 0) ? 1 : 0;
+    }
+    return mode == 1;
 }
 
 cudaError_t launch_render_forward(const CameraParams& cam, const uint32_t* ranges, const uint32_t* point_list,
                                   const float* rec, uint32_t* n_contrib, uint32_t* n_visited, float* final_T,
                                   float* out_color, float* out_depth, float* out_alpha, cudaStream_t st) {
     dim3 grid(cam.grid_x, cam.grid_y);
-    render_forward_kernel<<<grid, BLOCK_SIZE, 0, st>>>(cam.W, cam.H, cam.grid_x, ranges, point_list, rec, cam.bg,
-                                                       n_contrib, n_visited, final_T, out_color, out_depth, out_alpha);
+    if (use_bulk_staging())
+        render_forward_kernel<true><<<grid, BLOCK_SIZE, 0, st>>>(cam.W, cam.H, cam.grid_x, ranges, point_list, rec,
+                                                                 cam.bg, n_contrib, n_visited, final_T, out_color,
+                                                                 out_depth, out_alpha);
+    else
+        render_forward_kernel<false><<<grid, BLOCK_SIZE, 0, st>>>(cam.W, cam.H, cam.grid_x, ranges, point_list, rec,
+                                                                  cam.bg, n_contrib, n_visited, final_T, out_color,
+                                                                  out_depth, out_alpha);
     count_launch();
     return cudaGetLastError();
 }
@@ -322,9 +464,14 @@ cudaError_t launch_render_backward(const CameraParams& cam, const uint32_t* rang
                                    const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
                                    float* grad2d, cudaStream_t st) {
     dim3 grid(cam.grid_x, cam.grid_y);
-    render_backward_kernel<<<grid, BLOCK_SIZE, 0, st>>>(cam.W, cam.H, cam.grid_x, ranges, point_list, rec, cam.bg,
-                                                        n_contrib, final_T, dL_dcolor, dL_ddepth, dL_dalpha,
-                                                        grad2d);
+    if (use_bulk_staging())
+        render_backward_kernel<true><<<grid, BLOCK_SIZE, 0, st>>>(cam.W, cam.H, cam.grid_x, ranges, point_list, rec,
+                                                                  cam.bg, n_contrib, final_T, dL_dcolor, dL_ddepth,
+                                                                  dL_dalpha, grad2d);
+    else
+        render_backward_kernel<false><<<grid, BLOCK_SIZE, 0, st>>>(cam.W, cam.H, cam.grid_x, ranges, point_list, rec,
+                                                                   cam.bg, n_contrib, final_T, dL_dcolor, dL_ddepth,
+                                                                   dL_dalpha, grad2d);
     count_launch();
     return cudaGetLastError();
 }
