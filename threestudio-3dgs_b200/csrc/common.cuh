@@ -111,6 +111,8 @@ cudaError_t launch_dist2(int P, const float* points, float* out, void* ws, cudaS
 
 void count_launch(int n = 1);
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace b200splat

@@ -113,6 +113,20 @@ preprocess_kernel(int P, CameraParams cam, const float* __restrict__ means3D, co
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P) return;
 
+    // start the long-latency, visibility-dependent loads now: the SH block (2 lines) goes to L2 while the
+    // projection runs, instead of a third serialized DRAM round trip after the cull tests
+    if (shs != nullptr) {
+        const char* shp = reinterpret_cast<const char*>(shs + (size_t)idx * cam.M * 3);
+        prefetch_l2(shp);
+        if (cam.M * 12 > 128) prefetch_l2(shp + 128);
+    }
+    float4 q_early = make_float4(0.f, 0.f, 0.f, 0.f);
+    float s_early[3] = {0.f, 0.f, 0.f};
+    if (cov3D_precomp == nullptr) {
+        q_early = __ldg(reinterpret_cast<const float4*>(rotations) + idx);
+        s_early[0] = __ldg(scales + 3 * idx), s_early[1] = __ldg(scales + 3 * idx + 1), s_early[2] = __ldg(scales + 3 * idx + 2);
+    }
+    const float opac = __ldg(opacities + idx);
     int my_radius = 0;
     uint32_t my_tiles = 0;
     const float x = __ldg(means3D + 3 * idx), y = __ldg(means3D + 3 * idx + 1), z = __ldg(means3D + 3 * idx + 2);
@@ -133,9 +147,8 @@ preprocess_kernel(int P, CameraParams cam, const float* __restrict__ means3D, co
             c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2), c3 = __ldg(c + 3), c4 = __ldg(c + 4), c5 = __ldg(c + 5);
         } else {
             const float mod = cam.scale_modifier;
-            const float sx = mod * __ldg(scales + 3 * idx), sy = mod * __ldg(scales + 3 * idx + 1),
-                        sz = mod * __ldg(scales + 3 * idx + 2);
-            const float4 q = __ldg(reinterpret_cast<const float4*>(rotations) + idx);
+            const float sx = mod * s_early[0], sy = mod * s_early[1], sz = mod * s_early[2];
+            const float4 q = q_early;
             const float r = q.x, qx = q.y, qy = q.z, qz = q.w;
             const float R00 = 1.0f - 2.0f * (qy * qy + qz * qz);
             const float R01 = 2.0f * (qx * qy - r * qz);
@@ -213,9 +226,8 @@ preprocess_kernel(int P, CameraParams cam, const float* __restrict__ means3D, co
                 my_tiles = (uint32_t)area;
                 float4* o = reinterpret_cast<float4*>(rec) + 3 * (size_t)idx;
                 o[0] = make_float4(px, py, c * det_inv, -b * det_inv);
-                o[1] = make_float4(a * det_inv, __ldg(opacities + idx), tvz, rgb[0]);
+                o[1] = make_float4(a * det_inv, opac, tvz, rgb[0]);
                 // cull threshold of the render kernels: alpha >= 1/255 needs A dx^2 + 2B dx dy + C dy^2 <= 2 ln(255 o)
-                const float opac = __ldg(opacities + idx);
                 const float thr = opac > 0.0f ? 2.0f * __logf(255.0f * opac) + 0.002f : -1.0f;
                 o[2] = make_float4(rgb[1], rgb[2], thr, 0.0f);
                 depths[idx] = tvz;

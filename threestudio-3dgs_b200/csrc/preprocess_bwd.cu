@@ -151,6 +151,16 @@ preprocess_backward_kernel(int P, CameraParams cam, const float* __restrict__ me
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P) return;
     const int M = cam.M;
+    if (shs != nullptr) {   // SH block of this Gaussian towards L2 while the covariance chain runs
+        const char* shp = reinterpret_cast<const char*>(shs + (size_t)idx * M * 3);
+        prefetch_l2(shp);
+        if (M * 12 > 128) prefetch_l2(shp + 128);
+        if (ACC) {
+            const char* dp = reinterpret_cast<const char*>(dL_dshs + (size_t)idx * M * 3);
+            prefetch_l2(dp);
+            if (M * 12 > 128) prefetch_l2(dp + 128);
+        }
+    }
     const int my_radius = radii[idx];
     if (my_radius <= 0) {
         if (!ACC) {

@@ -29,6 +29,7 @@ namespace b200splat {
 
 constexpr int BATCH = 256;
 constexpr int STAGES = 2;
+constexpr int ILP = 4;   // survivors whose alpha is evaluated together (hides the LDS/MUFU latency chain)
 
 // ---- mbarrier / async-copy PTX ----------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -180,43 +181,73 @@ render_forward_kernel(int W, int H, int grid_x, const uint32_t* __restrict__ ran
         const int count = min(BATCH, total - b * BATCH);
         traversed = b * BATCH + count;
         const float4* __restrict__ buf = s_rec[s];
-        for (int c0 = 0; c0 < count; c0 += 32) {
-            if (__all_sync(0xffffffffu, done)) break;
+        // batch-level cull: 8 independent tests per lane (entry c*32+lane), mask c parked in lane c
+        uint32_t mymask = 0;
+#pragma unroll
+        for (int c = 0; c < BATCH / 32; ++c) {
+            const int e = c * 32 + lane;
             bool keep = false;
-            if (c0 + lane < count) {
-                const float4 q0 = buf[3 * (c0 + lane)];
-                const float4 q1 = buf[3 * (c0 + lane) + 1];
-                const float thr = buf[3 * (c0 + lane) + 2].z;
+            if (e < count) {
+                const float4 q0 = buf[3 * e];
+                const float4 q1 = buf[3 * e + 1];
+                const float thr = buf[3 * e + 2].z;
                 keep = cull_keep(q0, q1.x, thr, X0, X1, Y0, Y1);
             }
-            uint32_t mask = __ballot_sync(0xffffffffu, keep);
-            while (mask) {
-                const int j = c0 + __ffs(mask) - 1;
-                mask &= mask - 1;
-                if (done) continue;
-                const float4 q0 = buf[3 * j];
-                const float4 q1 = buf[3 * j + 1];
-                const float dx = q0.x - pixx, dy = q0.y - pixy;
-                const float power = -0.5f * (q0.z * dx * dx + q1.x * dy * dy) - q0.w * dx * dy;
-                if (power > 0.0f) continue;
-                const float alpha = fminf(ALPHA_MAX, q1.y * __expf(power));
-                if (alpha < ALPHA_MIN) continue;
-                const float test_T = T * (1.0f - alpha);
-                const uint32_t position = (uint32_t)(b * BATCH + j + 1);
-                if (test_T < T_MIN) {
-                    done = true;
-                    visited = position;
-                    continue;
+            const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+            if (lane == c) mymask = bal;
+        }
+        const int nchunks = (count + 31) >> 5;
+        for (int c = 0; c < nchunks; ++c) {
+            uint32_t m = __shfl_sync(0xffffffffu, mymask, c);
+            if (m == 0) continue;
+            if (__all_sync(0xffffffffu, done)) break;
+            const int base = c * 32;
+            while (m) {
+                // up to ILP survivors: alpha evaluated independently, blended in list order
+                int j[ILP];
+                bool has[ILP];
+#pragma unroll
+                for (int k = 0; k < ILP; ++k) {
+                    has[k] = m != 0;
+                    j[k] = has[k] ? base + __ffs(m) - 1 : (k ? j[0] : base);
+                    m &= m - 1;   // no-op on 0
                 }
-                const float4 q2 = buf[3 * j + 2];
-                const float w = alpha * T;
-                C0 += q1.w * w;
-                C1 += q2.x * w;
-                C2 += q2.y * w;
-                Wt += w;
-                D += q1.z * w;
-                T = test_T;
-                last_contributor = position;
+                float4 q0[ILP], q1[ILP];
+                float alpha[ILP];
+                bool ok[ILP];
+#pragma unroll
+                for (int k = 0; k < ILP; ++k) {
+                    q0[k] = buf[3 * j[k]];
+                    q1[k] = buf[3 * j[k] + 1];
+                }
+#pragma unroll
+                for (int k = 0; k < ILP; ++k) {
+                    const float dx = q0[k].x - pixx, dy = q0[k].y - pixy;
+                    const float power = -0.5f * (q0[k].z * dx * dx + q1[k].x * dy * dy) - q0[k].w * dx * dy;
+                    alpha[k] = fminf(ALPHA_MAX, q1[k].y * __expf(power));
+                    ok[k] = has[k] && (power <= 0.0f) && (alpha[k] >= ALPHA_MIN);
+                }
+#pragma unroll
+                for (int k = 0; k < ILP; ++k) {
+                    if (ok[k] && !done) {
+                        const float test_T = T * (1.0f - alpha[k]);
+                        const uint32_t position = (uint32_t)(b * BATCH + j[k] + 1);
+                        if (test_T < T_MIN) {
+                            done = true;
+                            visited = position;
+                        } else {
+                            const float4 q2 = buf[3 * j[k] + 2];
+                            const float w = alpha[k] * T;
+                            C0 += q1[k].w * w;
+                            C1 += q2.x * w;
+                            C2 += q2.y * w;
+                            Wt += w;
+                            D += q1[k].z * w;
+                            T = test_T;
+                            last_contributor = position;
+                        }
+                    }
+                }
             }
         }
     }
@@ -366,69 +397,96 @@ render_backward_kernel(int W, int H, int grid_x, const uint32_t* __restrict__ ra
         mbar_wait(&s_bar[s], (b >> 1) & 1);
         const int count = min(BATCH, total - b * BATCH);
         const float4* __restrict__ buf = s_rec[s];
-        for (int c0 = 0; c0 < count; c0 += 32) {
-            bool keep = false;
-            {
-                const int e = c0 + lane;
-                const uint32_t q = (uint32_t)(total - 1 - (b * BATCH + e));  // 0-based list position
-                if (e < count && q < warp_last) {
-                    const float4 q0 = buf[3 * e];
-                    const float4 q1 = buf[3 * e + 1];
-                    const float thr = buf[3 * e + 2].z;
-                    keep = cull_keep(q0, q1.x, thr, X0, X1, Y0, Y1);
-                }
-            }
-            uint32_t mask = __ballot_sync(0xffffffffu, keep);
-            while (mask) {
-                const int j = c0 + __ffs(mask) - 1;
-                mask &= mask - 1;
-                const uint32_t q = (uint32_t)(total - 1 - (b * BATCH + j));
-                const float4 q0 = buf[3 * j];
-                const float4 q1 = buf[3 * j + 1];
-                const float dx = q0.x - pixx, dy = q0.y - pixy;
-                const float power = -0.5f * (q0.z * dx * dx + q1.x * dy * dy) - q0.w * dx * dy;
-                const float G = __expf(power);
-                const float alpha = fminf(ALPHA_MAX, q1.y * G);
-                const bool hit = (q < my_last) && (power <= 0.0f) && (alpha >= ALPHA_MIN);
-                if (!__any_sync(0xffffffffu, hit)) continue;
-                float v[10];
+        uint32_t mymask = 0;
 #pragma unroll
-                for (int k = 0; k < 10; ++k) v[k] = 0.f;
-                if (hit) {
-                    const float4 q2 = buf[3 * j + 2];
-                    T = T / (1.0f - alpha);
-                    const float w = alpha * T;
-                    float dL_da = 0.f;
-                    acc0 = last_alpha * lc0 + (1.0f - last_alpha) * acc0;
-                    lc0 = q1.w;
-                    dL_da += (q1.w - acc0) * gC0;
-                    acc1 = last_alpha * lc1 + (1.0f - last_alpha) * acc1;
-                    lc1 = q2.x;
-                    dL_da += (q2.x - acc1) * gC1;
-                    acc2 = last_alpha * lc2 + (1.0f - last_alpha) * acc2;
-                    lc2 = q2.y;
-                    dL_da += (q2.y - acc2) * gC2;
-                    accD = last_alpha * lD + (1.0f - last_alpha) * accD;
-                    lD = q1.z;
-                    dL_da += (q1.z - accD) * gD;
-                    accA = last_alpha + (1.0f - last_alpha) * accA;
-                    dL_da += (1.0f - accA) * gA;
-                    dL_da *= T;
-                    last_alpha = alpha;
-                    dL_da += (-T_final / (1.0f - alpha)) * bg_dot;
-                    const float dL_dG = q1.y * dL_da;
-                    const float gdx = G * dx, gdy = G * dy;
-                    // power = -0.5 (A dx^2 + C dy^2) - B dx dy, d = mean - pixel
-                    v[0] = dL_dG * (-gdx * q0.z - gdy * q0.w);
-                    v[1] = dL_dG * (-gdy * q1.x - gdx * q0.w);
-                    v[2] = -0.5f * gdx * dx * dL_dG;
-                    v[3] = -gdx * dy * dL_dG;
-                    v[4] = -0.5f * gdy * dy * dL_dG;
-                    v[5] = G * dL_da;
-                    v[6] = w * gC0, v[7] = w * gC1, v[8] = w * gC2, v[9] = w * gD;
+        for (int c = 0; c < BATCH / 32; ++c) {
+            const int e = c * 32 + lane;
+            const uint32_t q = (uint32_t)(total - 1 - (b * BATCH + e));  // 0-based list position
+            bool keep = false;
+            if (e < count && q < warp_last) {
+                const float4 q0 = buf[3 * e];
+                const float4 q1 = buf[3 * e + 1];
+                const float thr = buf[3 * e + 2].z;
+                keep = cull_keep(q0, q1.x, thr, X0, X1, Y0, Y1);
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+            if (lane == c) mymask = bal;
+        }
+        const int nchunks = (count + 31) >> 5;
+        for (int c = 0; c < nchunks; ++c) {
+            uint32_t m = __shfl_sync(0xffffffffu, mymask, c);
+            const int base = c * 32;
+            while (m) {
+                int j[ILP];
+                bool has[ILP];
+#pragma unroll
+                for (int k = 0; k < ILP; ++k) {
+                    has[k] = m != 0;
+                    j[k] = has[k] ? base + __ffs(m) - 1 : (k ? j[0] : base);
+                    m &= m - 1;
                 }
-                const float r = warp_reduce10(v, lane);
-                if (slot >= 0) atomicAdd(grad2d + (size_t)s_ids[s][j] * GRAD2D_FLOATS + slot, r);
+                float4 q0[ILP], q1[ILP];
+                float G[ILP], alpha[ILP], inv1m[ILP], ddx[ILP], ddy[ILP];
+                bool hit[ILP];
+#pragma unroll
+                for (int k = 0; k < ILP; ++k) {
+                    q0[k] = buf[3 * j[k]];
+                    q1[k] = buf[3 * j[k] + 1];
+                }
+#pragma unroll
+                for (int k = 0; k < ILP; ++k) {
+                    const uint32_t q = (uint32_t)(total - 1 - (b * BATCH + j[k]));
+                    ddx[k] = q0[k].x - pixx, ddy[k] = q0[k].y - pixy;
+                    const float power =
+                        -0.5f * (q0[k].z * ddx[k] * ddx[k] + q1[k].x * ddy[k] * ddy[k]) - q0[k].w * ddx[k] * ddy[k];
+                    G[k] = __expf(power);
+                    alpha[k] = fminf(ALPHA_MAX, q1[k].y * G[k]);
+                    inv1m[k] = 1.0f / (1.0f - alpha[k]);
+                    hit[k] = has[k] && (q < my_last) && (power <= 0.0f) && (alpha[k] >= ALPHA_MIN);
+                }
+#pragma unroll
+                for (int k = 0; k < ILP; ++k) {
+                    if (!__any_sync(0xffffffffu, hit[k])) continue;
+                    float v[10];
+#pragma unroll
+                    for (int t = 0; t < 10; ++t) v[t] = 0.f;
+                    if (hit[k]) {
+                        const float4 q2 = buf[3 * j[k] + 2];
+                        const float a = alpha[k], dx = ddx[k], dy = ddy[k];
+                        T = T * inv1m[k];
+                        const float w = a * T;
+                        float dL_da = 0.f;
+                        acc0 = last_alpha * lc0 + (1.0f - last_alpha) * acc0;
+                        lc0 = q1[k].w;
+                        dL_da += (q1[k].w - acc0) * gC0;
+                        acc1 = last_alpha * lc1 + (1.0f - last_alpha) * acc1;
+                        lc1 = q2.x;
+                        dL_da += (q2.x - acc1) * gC1;
+                        acc2 = last_alpha * lc2 + (1.0f - last_alpha) * acc2;
+                        lc2 = q2.y;
+                        dL_da += (q2.y - acc2) * gC2;
+                        accD = last_alpha * lD + (1.0f - last_alpha) * accD;
+                        lD = q1[k].z;
+                        dL_da += (q1[k].z - accD) * gD;
+                        accA = last_alpha + (1.0f - last_alpha) * accA;
+                        dL_da += (1.0f - accA) * gA;
+                        dL_da *= T;
+                        last_alpha = a;
+                        dL_da += (-T_final * inv1m[k]) * bg_dot;
+                        const float dL_dG = q1[k].y * dL_da;
+                        const float gdx = G[k] * dx, gdy = G[k] * dy;
+                        // power = -0.5 (A dx^2 + C dy^2) - B dx dy, d = mean - pixel
+                        v[0] = dL_dG * (-gdx * q0[k].z - gdy * q0[k].w);
+                        v[1] = dL_dG * (-gdy * q1[k].x - gdx * q0[k].w);
+                        v[2] = -0.5f * gdx * dx * dL_dG;
+                        v[3] = -gdx * dy * dL_dG;
+                        v[4] = -0.5f * gdy * dy * dL_dG;
+                        v[5] = G[k] * dL_da;
+                        v[6] = w * gC0, v[7] = w * gC1, v[8] = w * gC2, v[9] = w * gD;
+                    }
+                    const float r = warp_reduce10(v, lane);
+                    if (slot >= 0) atomicAdd(grad2d + (size_t)s_ids[s][j[k]] * GRAD2D_FLOATS + slot, r);
+                }
             }
         }
     }
