@@ -95,6 +95,7 @@ size_t image_layout(int H, int W, void* base, ImageViews* v) {
     im.n_contrib = carve<uint32_t>(p, (size_t)H * W);
     im.final_T = carve<float>(p, (size_t)H * W);
     im.n_visited = carve<uint32_t>(p, (size_t)H * W);
+    im.tile_order = carve<uint32_t>(p, (size_t)gx * gy);
     if (v) *v = im;
     return (size_t)(p - p0);
 }
@@ -276,23 +277,27 @@ int b200splat_forward(const b200splat_forward_args* a) {
         }
         if (a->binning_out) *a->binning_out = bbuf;
         binning_layout(R, bbuf, &bn);
+        const int end_bit = 32 + higher_msb((uint32_t)T);
         { ProfScope ps(2, st);
-        CU(launch_duplicate(P, cam, a->radii, g, bn.keys[0], bn.vals[0], st)); }
+        CU(sort_prepare(R, end_bit, bn.sort_ws, st));
+        CU(launch_duplicate(P, cam, a->radii, g, bn.keys[0], bn.vals[0], sort_histogram_ptr(bn.sort_ws), end_bit, st)); }
         DEBUG_SYNC(a->cam, st, "duplicateWithKeys");
         int sel = 0;
         { ProfScope ps(3, st);
-        CU(launch_sort_pairs(R, 32 + higher_msb((uint32_t)T), bn.keys, bn.vals, bn.sort_ws, &sel, st)); }
+        CU(launch_sort_pairs(R, end_bit, bn.keys, bn.vals, bn.sort_ws, &sel, st, /*hist_ready=*/true)); }
         DEBUG_SYNC(a->cam, st, "sort");
         if (sel != sorted_sel_for(T)) return fail(B200SPLAT_ERR_CUDA, "internal: sort buffer parity mismatch");
         { ProfScope ps(4, st);
-        CU(launch_tile_ranges(R, T, bn.keys[sel], im.ranges, st)); }
+        CU(launch_tile_ranges(R, T, bn.keys[sel], im.ranges, st));
+        CU(launch_tile_order(T, im.ranges, im.tile_order, st)); }
         DEBUG_SYNC(a->cam, st, "identifyTileRanges");
         point_list = bn.vals[sel];
     } else {
         CU(cudaMemsetAsync(im.ranges, 0, (size_t)T * 8, st));
+        CU(launch_tile_order(T, im.ranges, im.tile_order, st));
     }
     { ProfScope ps(5, st);
-    CU(launch_render_forward(cam, im.ranges, point_list, g.rec, im.n_contrib, im.n_visited, im.final_T, a->out_color,
+    CU(launch_render_forward(cam, im.ranges, im.tile_order, point_list, g.rec, im.n_contrib, im.n_visited, im.final_T, a->out_color,
                              a->out_depth, a->out_alpha, st)); }
     DEBUG_SYNC(a->cam, st, "render");
     return B200SPLAT_OK;
@@ -329,7 +334,7 @@ int b200splat_backward(const b200splat_backward_args* a) {
         BinningViews bn;
         binning_layout(a->num_rendered, const_cast<void*>(a->binning_buffer), &bn);
         const uint32_t* point_list = bn.vals[sorted_sel(cam.H, cam.W)];
-        cudaError_t re = launch_render_backward(cam, im.ranges, point_list, g.rec, im.n_contrib, im.final_T,
+        cudaError_t re = launch_render_backward(cam, im.ranges, im.tile_order, point_list, g.rec, im.n_contrib, im.final_T,
                                                 a->dL_dout_color, a->dL_dout_depth, a->dL_dout_alpha, grad2d, st);
         if (re != cudaSuccess) { delete rb; CU(re); }
     }

@@ -67,6 +67,7 @@ struct ImageViews {
     uint32_t* n_contrib;     // H * W
     float* final_T;          // H * W  (transmittance after the last blended entry; 1 - alpha loses bits)
     uint32_t* n_visited;     // H * W  (list entries traversed by the pixel in forward)
+    uint32_t* tile_order;    // T      (tiles by decreasing list length: CTA i renders tile_order[i])
 };
 
 size_t geom_layout(int P, void* base, GeomViews* v);
@@ -79,7 +80,7 @@ cudaError_t launch_preprocess(int P, const CameraParams& cam, const float* means
                               const float* colors_precomp, const float* cov3D_precomp, int32_t* radii,
                               const GeomViews& g, cudaStream_t st);
 cudaError_t launch_duplicate(int P, const CameraParams& cam, const int32_t* radii, const GeomViews& g,
-                             uint64_t* keys, uint32_t* vals, cudaStream_t st);
+                             uint64_t* keys, uint32_t* vals, uint32_t* hist, int end_bit, cudaStream_t st);
 cudaError_t launch_mark_visible(int P, const float* means3D, const float* view, const float* proj,
                                 uint8_t* present, cudaStream_t st);
 
@@ -88,13 +89,19 @@ cudaError_t launch_inclusive_scan(int64_t n, const uint32_t* in, uint32_t* out, 
 size_t sort_workspace_bytes(int64_t n);
 // returns index (0/1) of the buffer pair holding the result through *sel
 cudaError_t launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_t* vals[2], void* ws,
-                              int* sel, cudaStream_t st);
+                              int* sel, cudaStream_t st, bool hist_ready = false);
+// zero the sort workspace / where a fused producer (duplicateWithKeys) accumulates the digit histograms
+cudaError_t sort_prepare(int64_t n, int end_bit, void* ws, cudaStream_t st);
+uint32_t* sort_histogram_ptr(void* ws);
 cudaError_t launch_tile_ranges(int64_t R, int T, const uint64_t* keys_sorted, uint32_t* ranges, cudaStream_t st);
+cudaError_t launch_tile_order(int T, const uint32_t* ranges, uint32_t* order, cudaStream_t st);
 
-cudaError_t launch_render_forward(const CameraParams& cam, const uint32_t* ranges, const uint32_t* point_list,
+cudaError_t launch_render_forward(const CameraParams& cam, const uint32_t* ranges, const uint32_t* tile_order,
+                                  const uint32_t* point_list,
                                   const float* rec, uint32_t* n_contrib, uint32_t* n_visited, float* final_T,
                                   float* out_color, float* out_depth, float* out_alpha, cudaStream_t st);
-cudaError_t launch_render_backward(const CameraParams& cam, const uint32_t* ranges, const uint32_t* point_list,
+cudaError_t launch_render_backward(const CameraParams& cam, const uint32_t* ranges, const uint32_t* tile_order,
+                                   const uint32_t* point_list,
                                    const float* rec, const uint32_t* n_contrib, const float* final_T,
                                    const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
                                    float* grad2d, cudaStream_t st);

@@ -244,25 +244,52 @@ preprocess_kernel(int P, CameraParams cam, const float* __restrict__ means3D, co
 }
 
 // key = (tile_id << 32) | float_bits(depth); value = Gaussian index; tiles y-major then x.
+// Fused: the per-digit-place histograms the onesweep sort needs (hist[pass][256]) are accumulated here --
+// all keys of one Gaussian share their low 32 bits, so the four depth digits cost one weighted shared-memory
+// atomic per Gaussian instead of one per key, and the separate histogram read of the key array disappears.
+constexpr int DUP_MAX_PASSES = 8;
 __global__ void __launch_bounds__(256)
 duplicate_kernel(int P, int gx, int gy, const int32_t* __restrict__ radii, const float* __restrict__ rec,
                  const float* __restrict__ depths, const uint32_t* __restrict__ point_offsets,
-                 uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
-    const int rad = radii[idx];
-    if (rad <= 0) return;
-    uint32_t off = (idx == 0) ? 0u : point_offsets[idx - 1];
-    const float2 xy = *reinterpret_cast<const float2*>(rec + (size_t)idx * REC_FLOATS);
-    int x0, y0, x1, y1;
-    get_rect(xy.x, xy.y, (float)rad, gx, gy, x0, y0, x1, y1);
-    const uint64_t dbits = (uint64_t)__float_as_uint(depths[idx]);
-    for (int ty = y0; ty < y1; ++ty) {
-        for (int tx = x0; tx < x1; ++tx) {
-            keys[off] = ((uint64_t)(uint32_t)(ty * gx + tx) << 32) | dbits;
-            vals[off] = (uint32_t)idx;
-            ++off;
+                 uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ hist, int end_bit) {
+    __shared__ uint32_t s_hist[DUP_MAX_PASSES * 256];
+    const int passes = (end_bit + 7) / 8;
+    for (int i = threadIdx.x; i < passes * 256; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < P; idx += gridDim.x * blockDim.x) {
+        const int rad = radii[idx];
+        if (rad <= 0) continue;
+        uint32_t off = (idx == 0) ? 0u : point_offsets[idx - 1];
+        const float2 xy = *reinterpret_cast<const float2*>(rec + (size_t)idx * REC_FLOATS);
+        int x0, y0, x1, y1;
+        get_rect(xy.x, xy.y, (float)rad, gx, gy, x0, y0, x1, y1);
+        const uint32_t d32 = __float_as_uint(depths[idx]);
+        const uint64_t dbits = (uint64_t)d32;
+        const uint32_t ntiles = (uint32_t)((x1 - x0) * (y1 - y0));
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            if (p < passes) {
+                const int bits = min(8, end_bit - 8 * p);
+                atomicAdd(&s_hist[p * 256 + ((d32 >> (8 * p)) & ((1u << bits) - 1u))], ntiles);
+            }
         }
+        for (int ty = y0; ty < y1; ++ty) {
+            for (int tx = x0; tx < x1; ++tx) {
+                const uint32_t tile = (uint32_t)(ty * gx + tx);
+                keys[off] = ((uint64_t)tile << 32) | dbits;
+                vals[off] = (uint32_t)idx;
+                ++off;
+                for (int p = 4; p < passes; ++p) {
+                    const int bits = min(8, end_bit - 8 * p);
+                    atomicAdd(&s_hist[p * 256 + ((tile >> (8 * (p - 4))) & ((1u << bits) - 1u))], 1u);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * 256; i += blockDim.x) {
+        const uint32_t c = s_hist[i];
+        if (c) atomicAdd(&hist[i], c);
     }
 }
 
@@ -288,10 +315,11 @@ cudaError_t launch_preprocess(int P, const CameraParams& cam, const float* means
 }
 
 cudaError_t launch_duplicate(int P, const CameraParams& cam, const int32_t* radii, const GeomViews& g,
-                             uint64_t* keys, uint32_t* vals, cudaStream_t st) {
+                             uint64_t* keys, uint32_t* vals, uint32_t* hist, int end_bit, cudaStream_t st) {
     if (P <= 0) return cudaSuccess;
-    duplicate_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, cam.grid_x, cam.grid_y, radii, g.rec, g.depths,
-                                                       g.point_offsets, keys, vals);
+    const int blocks = min((P + 255) / 256, NUM_SMS * 8);
+    duplicate_kernel<<<blocks, 256, 0, st>>>(P, cam.grid_x, cam.grid_y, radii, g.rec, g.depths,
+                                              g.point_offsets, keys, vals, hist, end_bit);
     count_launch();
     return cudaGetLastError();
 }

@@ -129,22 +129,25 @@ __device__ __forceinline__ bool cull_keep(const float4 q0, const float C, const 
 template <bool BULK>
 __global__ void __launch_bounds__(BLOCK_SIZE)
 render_forward_kernel(int W, int H, int grid_x, const uint32_t* __restrict__ ranges,
-                      const uint32_t* __restrict__ point_list, const float* __restrict__ rec,
+                      const uint32_t* __restrict__ tile_order, const uint32_t* __restrict__ point_list, const float* __restrict__ rec,
                       const float* __restrict__ bg, uint32_t* __restrict__ n_contrib, uint32_t* __restrict__ n_visited,
                       float* __restrict__ final_T, float* __restrict__ out_color, float* __restrict__ out_depth,
                       float* __restrict__ out_alpha) {
     __shared__ __align__(16) float4 s_rec[STAGES][BATCH * 3];
     __shared__ __align__(8) uint64_t s_bar[STAGES];
+    __shared__ __align__(16) uint8_t s_surv[BLOCK_SIZE / 32][BATCH + 16];
 
-    const int tile = blockIdx.y * grid_x + blockIdx.x;
+    const int tile = (int)tile_order[blockIdx.x];   // longest lists first (LPT)
+    const int tile_x = tile % grid_x, tile_y = tile / grid_x;
     int lx, ly;
     thread_pixel(lx, ly);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int pxi = blockIdx.x * BLOCK_X + lx, pyi = blockIdx.y * BLOCK_Y + ly;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const int pxi = tile_x * BLOCK_X + lx, pyi = tile_y * BLOCK_Y + ly;
     const bool inside = pxi < W && pyi < H;
     const float pixx = (float)pxi, pixy = (float)pyi;
-    const float X0 = (float)(blockIdx.x * BLOCK_X + (warp & 1) * 8), X1 = X0 + 7.f;
-    const float Y0 = (float)(blockIdx.y * BLOCK_Y + (warp >> 1) * 4), Y1 = Y0 + 3.f;
+    const float X0 = (float)(tile_x * BLOCK_X + (warp & 1) * 8), X1 = X0 + 7.f;
+    const float Y0 = (float)(tile_y * BLOCK_Y + (warp >> 1) * 4), Y1 = Y0 + 3.f;
     const uint32_t r0 = ranges[2 * tile], r1 = ranges[2 * tile + 1];
     const int total = (int)(r1 - r0);
     const int rounds = (total + BATCH - 1) / BATCH;
@@ -181,8 +184,10 @@ render_forward_kernel(int W, int H, int grid_x, const uint32_t* __restrict__ ran
         const int count = min(BATCH, total - b * BATCH);
         traversed = b * BATCH + count;
         const float4* __restrict__ buf = s_rec[s];
-        // batch-level cull: 8 independent tests per lane (entry c*32+lane), mask c parked in lane c
-        uint32_t mymask = 0;
+        // batch-level cull: 8 independent tests per lane; survivors compacted (in list order) into the
+        // warp's private index list
+        uint8_t* __restrict__ surv = s_surv[warp];
+        int nsurv = 0;
 #pragma unroll
         for (int c = 0; c < BATCH / 32; ++c) {
             const int e = c * 32 + lane;
@@ -194,59 +199,50 @@ render_forward_kernel(int W, int H, int grid_x, const uint32_t* __restrict__ ran
                 keep = cull_keep(q0, q1.x, thr, X0, X1, Y0, Y1);
             }
             const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-            if (lane == c) mymask = bal;
+            if (keep) surv[nsurv + __popc(bal & lt_mask)] = (uint8_t)e;
+            nsurv += __popc(bal);
         }
-        const int nchunks = (count + 31) >> 5;
-        for (int c = 0; c < nchunks; ++c) {
-            uint32_t m = __shfl_sync(0xffffffffu, mymask, c);
-            if (m == 0) continue;
+        __syncwarp();
+        for (int i = 0; i < nsurv; i += ILP) {
             if (__all_sync(0xffffffffu, done)) break;
-            const int base = c * 32;
-            while (m) {
-                // up to ILP survivors: alpha evaluated independently, blended in list order
-                int j[ILP];
-                bool has[ILP];
+            // ILP survivors: alpha evaluated independently, then blended in list order (predicated, branch free)
+            const uint32_t packed = *reinterpret_cast<const uint32_t*>(surv + i);
+            int j[ILP];
+            float alpha[ILP], cr[ILP], cg[ILP], cb[ILP], cd[ILP];
+            bool ok[ILP];
 #pragma unroll
-                for (int k = 0; k < ILP; ++k) {
-                    has[k] = m != 0;
-                    j[k] = has[k] ? base + __ffs(m) - 1 : (k ? j[0] : base);
-                    m &= m - 1;   // no-op on 0
+            for (int k = 0; k < ILP; ++k) {
+                const bool has = i + k < nsurv;
+                j[k] = has ? (int)((packed >> (8 * k)) & 0xffu) : (int)(packed & 0xffu);
+                const float4 q0 = buf[3 * j[k]];
+                const float4 q1 = buf[3 * j[k] + 1];
+                const float2 q2 = *reinterpret_cast<const float2*>(buf + 3 * j[k] + 2);
+                const float dx = q0.x - pixx, dy = q0.y - pixy;
+                const float power = -0.5f * (q0.z * dx * dx + q1.x * dy * dy) - q0.w * dx * dy;
+                alpha[k] = fminf(ALPHA_MAX, q1.y * __expf(power));
+                ok[k] = has && (power <= 0.0f) && (alpha[k] >= ALPHA_MIN);
+                cr[k] = q1.w, cg[k] = q2.x, cb[k] = q2.y, cd[k] = q1.z;
+            }
+#pragma unroll
+            for (int k = 0; k < ILP; ++k) {
+                const bool act = ok[k] && !done;
+                const float test_T = T * (1.0f - alpha[k]);
+                const bool stop = act && (test_T < T_MIN);
+                const bool use = act && !stop;
+                const uint32_t position = (uint32_t)(b * BATCH + j[k] + 1);
+                if (use) {
+                    const float w = alpha[k] * T;
+                    C0 += cr[k] * w;
+                    C1 += cg[k] * w;
+                    C2 += cb[k] * w;
+                    Wt += w;
+                    D += cd[k] * w;
+                    T = test_T;
+                    last_contributor = position;
                 }
-                float4 q0[ILP], q1[ILP];
-                float alpha[ILP];
-                bool ok[ILP];
-#pragma unroll
-                for (int k = 0; k < ILP; ++k) {
-                    q0[k] = buf[3 * j[k]];
-                    q1[k] = buf[3 * j[k] + 1];
-                }
-#pragma unroll
-                for (int k = 0; k < ILP; ++k) {
-                    const float dx = q0[k].x - pixx, dy = q0[k].y - pixy;
-                    const float power = -0.5f * (q0[k].z * dx * dx + q1[k].x * dy * dy) - q0[k].w * dx * dy;
-                    alpha[k] = fminf(ALPHA_MAX, q1[k].y * __expf(power));
-                    ok[k] = has[k] && (power <= 0.0f) && (alpha[k] >= ALPHA_MIN);
-                }
-#pragma unroll
-                for (int k = 0; k < ILP; ++k) {
-                    if (ok[k] && !done) {
-                        const float test_T = T * (1.0f - alpha[k]);
-                        const uint32_t position = (uint32_t)(b * BATCH + j[k] + 1);
-                        if (test_T < T_MIN) {
-                            done = true;
-                            visited = position;
-                        } else {
-                            const float4 q2 = buf[3 * j[k] + 2];
-                            const float w = alpha[k] * T;
-                            C0 += q1[k].w * w;
-                            C1 += q2.x * w;
-                            C2 += q2.y * w;
-                            Wt += w;
-                            D += q1[k].z * w;
-                            T = test_T;
-                            last_contributor = position;
-                        }
-                    }
+                if (stop) {
+                    done = true;
+                    visited = position;
                 }
             }
         }
@@ -328,7 +324,7 @@ __device__ __forceinline__ int reduce_slot(int lane) {
 template <bool BULK>
 __global__ void __launch_bounds__(BLOCK_SIZE)
 render_backward_kernel(int W, int H, int grid_x, const uint32_t* __restrict__ ranges,
-                       const uint32_t* __restrict__ point_list, const float* __restrict__ rec,
+                       const uint32_t* __restrict__ tile_order, const uint32_t* __restrict__ point_list, const float* __restrict__ rec,
                        const float* __restrict__ bg, const uint32_t* __restrict__ n_contrib,
                        const float* __restrict__ final_T, const float* __restrict__ dL_dcolor,
                        const float* __restrict__ dL_ddepth, const float* __restrict__ dL_dalpha,
@@ -336,17 +332,20 @@ render_backward_kernel(int W, int H, int grid_x, const uint32_t* __restrict__ ra
     __shared__ __align__(16) float4 s_rec[STAGES][BATCH * 3];
     __shared__ uint32_t s_ids[STAGES][BATCH];
     __shared__ __align__(8) uint64_t s_bar[STAGES];
+    __shared__ __align__(16) uint8_t s_surv[BLOCK_SIZE / 32][BATCH + 16];
     __shared__ uint32_t s_max;
 
-    const int tile = blockIdx.y * grid_x + blockIdx.x;
+    const int tile = (int)tile_order[blockIdx.x];   // longest lists first (LPT)
+    const int tile_x = tile % grid_x, tile_y = tile / grid_x;
     int lx, ly;
     thread_pixel(lx, ly);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int pxi = blockIdx.x * BLOCK_X + lx, pyi = blockIdx.y * BLOCK_Y + ly;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const int pxi = tile_x * BLOCK_X + lx, pyi = tile_y * BLOCK_Y + ly;
     const bool inside = pxi < W && pyi < H;
     const float pixx = (float)pxi, pixy = (float)pyi;
-    const float X0 = (float)(blockIdx.x * BLOCK_X + (warp & 1) * 8), X1 = X0 + 7.f;
-    const float Y0 = (float)(blockIdx.y * BLOCK_Y + (warp >> 1) * 4), Y1 = Y0 + 3.f;
+    const float X0 = (float)(tile_x * BLOCK_X + (warp & 1) * 8), X1 = X0 + 7.f;
+    const float Y0 = (float)(tile_y * BLOCK_Y + (warp >> 1) * 4), Y1 = Y0 + 3.f;
     const int pix = pyi * W + pxi;
     const size_t HW = (size_t)H * W;
     const uint32_t r0 = ranges[2 * tile];
@@ -397,7 +396,8 @@ render_backward_kernel(int W, int H, int grid_x, const uint32_t* __restrict__ ra
         mbar_wait(&s_bar[s], (b >> 1) & 1);
         const int count = min(BATCH, total - b * BATCH);
         const float4* __restrict__ buf = s_rec[s];
-        uint32_t mymask = 0;
+        uint8_t* __restrict__ surv = s_surv[warp];
+        int nsurv = 0;
 #pragma unroll
         for (int c = 0; c < BATCH / 32; ++c) {
             const int e = c * 32 + lane;
@@ -410,83 +410,86 @@ render_backward_kernel(int W, int H, int grid_x, const uint32_t* __restrict__ ra
                 keep = cull_keep(q0, q1.x, thr, X0, X1, Y0, Y1);
             }
             const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-            if (lane == c) mymask = bal;
+            if (keep) surv[nsurv + __popc(bal & lt_mask)] = (uint8_t)e;
+            nsurv += __popc(bal);
         }
-        const int nchunks = (count + 31) >> 5;
-        for (int c = 0; c < nchunks; ++c) {
-            uint32_t m = __shfl_sync(0xffffffffu, mymask, c);
-            const int base = c * 32;
-            while (m) {
-                int j[ILP];
-                bool has[ILP];
+        __syncwarp();
+        for (int i = 0; i < nsurv; i += ILP) {
+            const uint32_t packed = *reinterpret_cast<const uint32_t*>(surv + i);
+            int j[ILP];
+            float v[ILP][10];
+            bool hit[ILP];
+            float G[ILP], alpha[ILP], inv1m[ILP], ddx[ILP], ddy[ILP], cA[ILP], cB[ILP], cC[ILP], op[ILP];
+            float cr[ILP], cg[ILP], cb[ILP], cd[ILP];
 #pragma unroll
-                for (int k = 0; k < ILP; ++k) {
-                    has[k] = m != 0;
-                    j[k] = has[k] ? base + __ffs(m) - 1 : (k ? j[0] : base);
-                    m &= m - 1;
+            for (int k = 0; k < ILP; ++k) {
+                const bool has = i + k < nsurv;
+                j[k] = has ? (int)((packed >> (8 * k)) & 0xffu) : (int)(packed & 0xffu);
+                const float4 q0 = buf[3 * j[k]];
+                const float4 q1 = buf[3 * j[k] + 1];
+                const float2 q2 = *reinterpret_cast<const float2*>(buf + 3 * j[k] + 2);
+                const uint32_t q = (uint32_t)(total - 1 - (b * BATCH + j[k]));
+                ddx[k] = q0.x - pixx, ddy[k] = q0.y - pixy;
+                cA[k] = q0.z, cB[k] = q0.w, cC[k] = q1.x, op[k] = q1.y;
+                const float power = -0.5f * (cA[k] * ddx[k] * ddx[k] + cC[k] * ddy[k] * ddy[k]) - cB[k] * ddx[k] * ddy[k];
+                G[k] = __expf(power);
+                alpha[k] = fminf(ALPHA_MAX, op[k] * G[k]);
+                inv1m[k] = 1.0f / (1.0f - alpha[k]);
+                hit[k] = has && (q < my_last) && (power <= 0.0f) && (alpha[k] >= ALPHA_MIN);
+                cr[k] = q1.w, cg[k] = q2.x, cb[k] = q2.y, cd[k] = q1.z;
+            }
+            // sequential recurrences, predicated per lane
+#pragma unroll
+            for (int k = 0; k < ILP; ++k) {
+#pragma unroll
+                for (int t = 0; t < 10; ++t) v[k][t] = 0.f;
+                if (hit[k]) {
+                    const float a = alpha[k], dx = ddx[k], dy = ddy[k];
+                    T = T * inv1m[k];
+                    const float w = a * T;
+                    const float om = 1.0f - last_alpha;
+                    float dL_da = 0.f;
+                    acc0 = last_alpha * lc0 + om * acc0;
+                    lc0 = cr[k];
+                    dL_da += (cr[k] - acc0) * gC0;
+                    acc1 = last_alpha * lc1 + om * acc1;
+                    lc1 = cg[k];
+                    dL_da += (cg[k] - acc1) * gC1;
+                    acc2 = last_alpha * lc2 + om * acc2;
+                    lc2 = cb[k];
+                    dL_da += (cb[k] - acc2) * gC2;
+                    accD = last_alpha * lD + om * accD;
+                    lD = cd[k];
+                    dL_da += (cd[k] - accD) * gD;
+                    accA = last_alpha + om * accA;
+                    dL_da += (1.0f - accA) * gA;
+                    dL_da *= T;
+                    last_alpha = a;
+                    dL_da += (-T_final * inv1m[k]) * bg_dot;
+                    const float dL_dG = op[k] * dL_da;
+                    const float gdx = G[k] * dx, gdy = G[k] * dy;
+                    // power = -0.5 (A dx^2 + C dy^2) - B dx dy, d = mean - pixel
+                    v[k][0] = dL_dG * (-gdx * cA[k] - gdy * cB[k]);
+                    v[k][1] = dL_dG * (-gdy * cC[k] - gdx * cB[k]);
+                    v[k][2] = -0.5f * gdx * dx * dL_dG;
+                    v[k][3] = -gdx * dy * dL_dG;
+                    v[k][4] = -0.5f * gdy * dy * dL_dG;
+                    v[k][5] = G[k] * dL_da;
+                    v[k][6] = w * gC0, v[k][7] = w * gC1, v[k][8] = w * gC2, v[k][9] = w * gD;
                 }
-                float4 q0[ILP], q1[ILP];
-                float G[ILP], alpha[ILP], inv1m[ILP], ddx[ILP], ddy[ILP];
-                bool hit[ILP];
+            }
+            // ILP independent warp reductions (interleaved by the scheduler), one 10-lane atomic each
+            uint32_t anyhit = 0;
 #pragma unroll
-                for (int k = 0; k < ILP; ++k) {
-                    q0[k] = buf[3 * j[k]];
-                    q1[k] = buf[3 * j[k] + 1];
-                }
+            for (int k = 0; k < ILP; ++k) anyhit |= (__any_sync(0xffffffffu, hit[k]) ? 1u : 0u) << k;
+            if (anyhit) {
+                float r[ILP];
 #pragma unroll
-                for (int k = 0; k < ILP; ++k) {
-                    const uint32_t q = (uint32_t)(total - 1 - (b * BATCH + j[k]));
-                    ddx[k] = q0[k].x - pixx, ddy[k] = q0[k].y - pixy;
-                    const float power =
-                        -0.5f * (q0[k].z * ddx[k] * ddx[k] + q1[k].x * ddy[k] * ddy[k]) - q0[k].w * ddx[k] * ddy[k];
-                    G[k] = __expf(power);
-                    alpha[k] = fminf(ALPHA_MAX, q1[k].y * G[k]);
-                    inv1m[k] = 1.0f / (1.0f - alpha[k]);
-                    hit[k] = has[k] && (q < my_last) && (power <= 0.0f) && (alpha[k] >= ALPHA_MIN);
-                }
+                for (int k = 0; k < ILP; ++k) r[k] = warp_reduce10(v[k], lane);
 #pragma unroll
-                for (int k = 0; k < ILP; ++k) {
-                    if (!__any_sync(0xffffffffu, hit[k])) continue;
-                    float v[10];
-#pragma unroll
-                    for (int t = 0; t < 10; ++t) v[t] = 0.f;
-                    if (hit[k]) {
-                        const float4 q2 = buf[3 * j[k] + 2];
-                        const float a = alpha[k], dx = ddx[k], dy = ddy[k];
-                        T = T * inv1m[k];
-                        const float w = a * T;
-                        float dL_da = 0.f;
-                        acc0 = last_alpha * lc0 + (1.0f - last_alpha) * acc0;
-                        lc0 = q1[k].w;
-                        dL_da += (q1[k].w - acc0) * gC0;
-                        acc1 = last_alpha * lc1 + (1.0f - last_alpha) * acc1;
-                        lc1 = q2.x;
-                        dL_da += (q2.x - acc1) * gC1;
-                        acc2 = last_alpha * lc2 + (1.0f - last_alpha) * acc2;
-                        lc2 = q2.y;
-                        dL_da += (q2.y - acc2) * gC2;
-                        accD = last_alpha * lD + (1.0f - last_alpha) * accD;
-                        lD = q1[k].z;
-                        dL_da += (q1[k].z - accD) * gD;
-                        accA = last_alpha + (1.0f - last_alpha) * accA;
-                        dL_da += (1.0f - accA) * gA;
-                        dL_da *= T;
-                        last_alpha = a;
-                        dL_da += (-T_final * inv1m[k]) * bg_dot;
-                        const float dL_dG = q1[k].y * dL_da;
-                        const float gdx = G[k] * dx, gdy = G[k] * dy;
-                        // power = -0.5 (A dx^2 + C dy^2) - B dx dy, d = mean - pixel
-                        v[0] = dL_dG * (-gdx * q0[k].z - gdy * q0[k].w);
-                        v[1] = dL_dG * (-gdy * q1[k].x - gdx * q0[k].w);
-                        v[2] = -0.5f * gdx * dx * dL_dG;
-                        v[3] = -gdx * dy * dL_dG;
-                        v[4] = -0.5f * gdy * dy * dL_dG;
-                        v[5] = G[k] * dL_da;
-                        v[6] = w * gC0, v[7] = w * gC1, v[8] = w * gC2, v[9] = w * gD;
-                    }
-                    const float r = warp_reduce10(v, lane);
-                    if (slot >= 0) atomicAdd(grad2d + (size_t)s_ids[s][j[k]] * GRAD2D_FLOATS + slot, r);
-                }
+                for (int k = 0; k < ILP; ++k)
+                    if (slot >= 0 && ((anyhit >> k) & 1u))
+                        atomicAdd(grad2d + (size_t)s_ids[s][j[k]] * GRAD2D_FLOATS + slot, r[k]);
             }
         }
     }
@@ -501,33 +504,35 @@ static bool use_bulk_staging() {
     return mode == 1;
 }
 
-cudaError_t launch_render_forward(const CameraParams& cam, const uint32_t* ranges, const uint32_t* point_list,
+cudaError_t launch_render_forward(const CameraParams& cam, const uint32_t* ranges, const uint32_t* tile_order,
+                                  const uint32_t* point_list,
                                   const float* rec, uint32_t* n_contrib, uint32_t* n_visited, float* final_T,
                                   float* out_color, float* out_depth, float* out_alpha, cudaStream_t st) {
-    dim3 grid(cam.grid_x, cam.grid_y);
+    dim3 grid(cam.grid_x * cam.grid_y);
     if (use_bulk_staging())
-        render_forward_kernel<true><<<grid, BLOCK_SIZE, 0, st>>>(cam.W, cam.H, cam.grid_x, ranges, point_list, rec,
+        render_forward_kernel<true><<<grid, BLOCK_SIZE, 0, st>>>(cam.W, cam.H, cam.grid_x, ranges, tile_order, point_list, rec,
                                                                  cam.bg, n_contrib, n_visited, final_T, out_color,
                                                                  out_depth, out_alpha);
     else
-        render_forward_kernel<false><<<grid, BLOCK_SIZE, 0, st>>>(cam.W, cam.H, cam.grid_x, ranges, point_list, rec,
+        render_forward_kernel<false><<<grid, BLOCK_SIZE, 0, st>>>(cam.W, cam.H, cam.grid_x, ranges, tile_order, point_list, rec,
                                                                   cam.bg, n_contrib, n_visited, final_T, out_color,
                                                                   out_depth, out_alpha);
     count_launch();
     return cudaGetLastError();
 }
 
-cudaError_t launch_render_backward(const CameraParams& cam, const uint32_t* ranges, const uint32_t* point_list,
+cudaError_t launch_render_backward(const CameraParams& cam, const uint32_t* ranges, const uint32_t* tile_order,
+                                   const uint32_t* point_list,
                                    const float* rec, const uint32_t* n_contrib, const float* final_T,
                                    const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
                                    float* grad2d, cudaStream_t st) {
-    dim3 grid(cam.grid_x, cam.grid_y);
+    dim3 grid(cam.grid_x * cam.grid_y);
     if (use_bulk_staging())
-        render_backward_kernel<true><<<grid, BLOCK_SIZE, 0, st>>>(cam.W, cam.H, cam.grid_x, ranges, point_list, rec,
+        render_backward_kernel<true><<<grid, BLOCK_SIZE, 0, st>>>(cam.W, cam.H, cam.grid_x, ranges, tile_order, point_list, rec,
                                                                   cam.bg, n_contrib, final_T, dL_dcolor, dL_ddepth,
                                                                   dL_dalpha, grad2d);
     else
-        render_backward_kernel<false><<<grid, BLOCK_SIZE, 0, st>>>(cam.W, cam.H, cam.grid_x, ranges, point_list, rec,
+        render_backward_kernel<false><<<grid, BLOCK_SIZE, 0, st>>>(cam.W, cam.H, cam.grid_x, ranges, tile_order, point_list, rec,
                                                                    cam.bg, n_contrib, final_T, dL_dcolor, dL_ddepth,
                                                                    dL_dalpha, grad2d);
     count_launch();

@@ -155,6 +155,8 @@ constexpr uint32_t DESC_AGG = 1u << 30;
 constexpr uint32_t DESC_INC = 2u << 30;
 constexpr uint32_t DESC_VAL = (1u << 30) - 1;
 
+static inline int64_t sort_tiles(int64_t n) { return (n + SORT_TILE - 1) / SORT_TILE; }
+
 // Histogram of every digit place in one read of the keys.  hist: [passes][256] u32 (zeroed).
 __global__ void __launch_bounds__(256)
 radix_histogram_kernel(int64_t n, int passes, int end_bit, const uint64_t* __restrict__ keys,
@@ -207,7 +209,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
 onesweep_pass_kernel(int64_t n, int shift, int bits, const uint64_t* __restrict__ keys_in,
                      const uint32_t* __restrict__ vals_in, uint64_t* __restrict__ keys_out,
                      uint32_t* __restrict__ vals_out, const uint32_t* __restrict__ hist_pass, uint32_t* ticket,
-                     uint32_t* desc /* [tiles][256] */) {
+                     uint32_t* desc /* [tiles][256] */, int tiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SortSmem& S = *reinterpret_cast<SortSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -258,7 +260,9 @@ onesweep_pass_kernel(int64_t n, int shift, int bits, const uint64_t* __restrict_
         // padding keys (~0) of a partial tile landed in the top digit: not part of the data
         uint32_t pub = bin_total;
         if (d == (int)mask) pub -= (uint32_t)(SORT_TILE - valid);
-        uint32_t* my = desc + (size_t)tile * RADIX + d;
+        uint32_t* col = desc + d;   // descriptor of tile t for this digit: col[t * RADIX] (coalesced across d)
+        uint32_t* my = col + (size_t)tile * RADIX;
+        (void)tiles;
         if (tile == 0) {
             st_volatile_u32(my, DESC_INC | pub);
         } else {
@@ -295,15 +299,27 @@ onesweep_pass_kernel(int64_t n, int shift, int bits, const uint64_t* __restrict_
         const uint32_t lexcl = loff + linc - bin_total;
         uint32_t excl = 0;
         if (tile > 0) {
-            int64_t look = (int64_t)tile - 1;
-            while (true) {
-                uint32_t v;
-                do {
-                    v = ld_volatile_u32(desc + (size_t)look * RADIX + d);
-                } while ((v >> 30) == 0);
-                excl += v & DESC_VAL;
-                if ((v >> 30) == 2) break;
-                --look;
+            // Decoupled look-back, LOOK predecessor tiles per step: the loads of a
+            // window are independent, so the walk advances LOOK tiles per L2 round trip instead of one
+            // (when a whole wave of CTAs reaches this point together the walk is the pass's critical path).
+            constexpr int LOOK = 8;
+            int look = (int)tile - 1;
+            bool found = false;
+            while (!found) {
+                uint32_t v[LOOK];
+#pragma unroll
+                for (int u = 0; u < LOOK; ++u)
+                    v[u] = (look - u >= 0) ? ld_volatile_u32(col + (size_t)(look - u) * RADIX) : DESC_INC;
+#pragma unroll
+                for (int u = 0; u < LOOK; ++u) {
+                    if (!found) {
+                        uint32_t x = v[u];
+                        while ((x >> 30) == 0) x = ld_volatile_u32(col + (size_t)(look - u) * RADIX);
+                        excl += x & DESC_VAL;
+                        found = (x >> 30) == 2;
+                    }
+                }
+                look -= LOOK;
             }
             st_volatile_u32(my, DESC_INC | (excl + pub));
         }
@@ -338,7 +354,6 @@ onesweep_pass_kernel(int64_t n, int shift, int bits, const uint64_t* __restrict_
     }
 }
 
-static inline int64_t sort_tiles(int64_t n) { return (n + SORT_TILE - 1) / SORT_TILE; }
 
 // workspace: hist [MAX_PASSES][256] u32 | tickets [MAX_PASSES] u32 (padded) | desc [passes][tiles][256] u32
 size_t sort_workspace_bytes(int64_t n) {
@@ -346,8 +361,19 @@ size_t sort_workspace_bytes(int64_t n) {
     return align_up((size_t)MAX_PASSES * RADIX * 4 + 256 + (size_t)MAX_PASSES * tiles * RADIX * 4, 256);
 }
 
+// zero histograms, tickets and descriptors (must precede a fused histogram producer)
+cudaError_t sort_prepare(int64_t n, int end_bit, void* ws, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    if (end_bit < 1) end_bit = 1;
+    if (end_bit > 64) end_bit = 64;
+    const int passes = (end_bit + RADIX_BITS - 1) / RADIX_BITS;
+    const size_t used = (size_t)MAX_PASSES * RADIX * 4 + 256 + (size_t)passes * sort_tiles(n) * RADIX * 4;
+    return cudaMemsetAsync(ws, 0, used, st);
+}
+uint32_t* sort_histogram_ptr(void* ws) { return reinterpret_cast<uint32_t*>(ws); }
+
 cudaError_t launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_t* vals[2], void* ws, int* sel,
-                              cudaStream_t st) {
+                              cudaStream_t st, bool hist_ready) {
     *sel = 0;
     if (n <= 0) return cudaSuccess;
     if (end_bit < 1) end_bit = 1;
@@ -361,25 +387,27 @@ cudaError_t launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    const size_t used = (size_t)MAX_PASSES * RADIX * 4 + 256 + (size_t)passes * tiles * RADIX * 4;
-    cudaError_t e = cudaMemsetAsync(ws, 0, used, st);
-    if (e != cudaSuccess) return e;
+    cudaError_t e = cudaSuccess;
     uint32_t* hist = reinterpret_cast<uint32_t*>(ws);
     uint32_t* tickets = hist + MAX_PASSES * RADIX;
     uint32_t* desc = tickets + 64;
-    int64_t hg = (n + 255) / 256;
-    int hgrid = (int)(hg < (int64_t)NUM_SMS * 8 ? hg : (int64_t)NUM_SMS * 8);
-    radix_histogram_kernel<<<hgrid, 256, 0, st>>>(n, passes, end_bit, keys[0], hist);
-    count_launch();
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    if (!hist_ready) {
+        e = sort_prepare(n, end_bit, ws, st);
+        if (e != cudaSuccess) return e;
+        int64_t hg = (n + 255) / 256;
+        int hgrid = (int)(hg < (int64_t)NUM_SMS * 8 ? hg : (int64_t)NUM_SMS * 8);
+        radix_histogram_kernel<<<hgrid, 256, 0, st>>>(n, passes, end_bit, keys[0], hist);
+        count_launch();
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
     int cur = 0;
     for (int p = 0; p < passes; ++p) {
         const int shift = p * RADIX_BITS;
         const int bits = (end_bit - shift) < RADIX_BITS ? (end_bit - shift) : RADIX_BITS;
         onesweep_pass_kernel<<<(unsigned)tiles, SORT_THREADS, sizeof(SortSmem), st>>>(
             n, shift, bits, keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], hist + p * RADIX, tickets + p,
-            desc + (size_t)p * tiles * RADIX);
+            desc + (size_t)p * tiles * RADIX, (int)tiles);
         count_launch();
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -413,6 +441,65 @@ cudaError_t launch_tile_ranges(int64_t R, int T, const uint64_t* keys_sorted, ui
     cudaError_t e = cudaMemsetAsync(ranges, 0, (size_t)T * 8, st);
     if (e != cudaSuccess || R <= 0) return e;
     tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, keys_sorted, ranges);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ============================================================================================
+// Longest-list-first tile order for the render kernels (LPT scheduling): order[i] = tile with the i-th
+// longest Gaussian list.  One CTA, bitonic sort of (length << 32 | ~tile) in shared memory.
+// ============================================================================================
+__global__ void __launch_bounds__(1024)
+tile_order_kernel(int T, int Tpow2, const uint32_t* __restrict__ ranges, uint32_t* __restrict__ order) {
+    extern __shared__ unsigned long long s_key[];
+    for (int i = threadIdx.x; i < Tpow2; i += blockDim.x) {
+        unsigned long long k = 0ull;   // padding sorts last (descending order)
+        if (i < T) {
+            const uint32_t len = ranges[2 * i + 1] - ranges[2 * i];
+            k = ((unsigned long long)len << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
+        }
+        s_key[i] = k;
+    }
+    __syncthreads();
+    for (int size = 2; size <= Tpow2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < Tpow2 / 2; i += blockDim.x) {
+                const int lo = 2 * i - (i & (stride - 1));   // index with bit `stride` cleared
+                const int hi = lo + stride;
+                const bool desc = (lo & size) == 0;          // descending blocks first -> overall descending
+                const unsigned long long a = s_key[lo], b = s_key[hi];
+                if ((a < b) == desc) {
+                    s_key[lo] = b;
+                    s_key[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < T; i += blockDim.x) order[i] = 0xffffffffu - (uint32_t)(s_key[i] & 0xffffffffull);
+}
+
+__global__ void tile_order_identity_kernel(int T, uint32_t* __restrict__ order) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < T) order[i] = (uint32_t)i;
+}
+
+cudaError_t launch_tile_order(int T, const uint32_t* ranges, uint32_t* order, cudaStream_t st) {
+    int p2 = 1;
+    while (p2 < T) p2 <<= 1;
+    const size_t smem = (size_t)p2 * 8;
+    if (smem > 200 * 1024) {   // > 25600 tiles: keep raster order
+        tile_order_identity_kernel<<<(T + 255) / 256, 256, 0, st>>>(T, order);
+        count_launch();
+        return cudaGetLastError();
+    }
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(tile_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr = smem;
+    }
+    tile_order_kernel<<<1, 1024, smem, st>>>(T, p2, ranges, order);
     count_launch();
     return cudaGetLastError();
 }
