@@ -1,0 +1,208 @@
+"""CPU tests of the oracle: self-pin against the float64 dense renderer, analytic known-answer cases,
+golden vectors (tests/golden/), integer stages.  The reference holds no tests or fixtures for this path
+(SURVEY.md 4), so this file IS the pin of the oracle ("parity unpinned upstream")."""
+import math
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from b200splat import scenes
+from oracle import dense_f64, spec
+from oracle import torch_oracle as O
+from oracle.knn import dist2_oracle
+from util import oracle_settings, rel_err
+
+GOLDEN = Path(__file__).parent / "golden" / "config1_oracle.npz"
+
+
+def _small(P, deg, H, W, seed, scale_mul=0.6):
+    sc = scenes.make_scene(P, deg, 0.8, seed=seed)
+    sc = sc._replace(scales=sc.scales * scale_mul)
+    cam = scenes.sds_cameras(1, H, W, seed=seed + 10)[0]
+    return sc, cam
+
+
+@pytest.mark.parametrize("seed,deg,mode", [(0, 3, "sh"), (1, 1, "sh"), (2, 0, "precomp"), (3, 2, "cov")])
+def test_oracle_matches_float64_dense_renderer(seed, deg, mode):
+    P, H, W = 120, 40, 48
+    sc, cam = _small(P, deg, H, W, seed)
+    s = oracle_settings(cam, deg, bg=(0.3, 0.6, 0.9))
+    g = torch.Generator().manual_seed(seed)
+    shs, cp, cov = sc.shs, None, None
+    scl, rot = sc.scales, sc.rotations
+    if mode == "precomp":
+        shs, cp = None, torch.rand(P, 3, generator=g)
+    if mode == "cov":
+        cov = torch.stack(O.cov3d_from_scale_rot(sc.scales, sc.rotations, 1.0), -1).contiguous()
+        scl = rot = None
+    out, pre, binned = O.rasterize_forward(sc.means3D, None, shs, cp, sc.opacities, scl, rot, cov, s)
+    gc, gd, ga = scenes.pixel_grads(H, W, seed + 5)
+    res = O.rasterize_backward((sc.means3D, None, shs, cp, sc.opacities, scl, rot, cov), s, pre, binned, out,
+                               gc, gd, ga)
+    d = lambda t: None if t is None else t.double().clone().requires_grad_(True)
+    m3, sh64, cp64, op, scl64, rot64, cov64 = map(d, (sc.means3D, shs, cp, sc.opacities, scl, rot, cov))
+    m2 = torch.zeros(P, 3, dtype=torch.float64, requires_grad=True)
+    col, dep, alp, radii = dense_f64.render_dense(m3, m2, sh64, cp64, op, scl64, rot64, cov64, s)
+    assert torch.equal(radii, pre["radii"].long())
+    assert float((col - out["color"]).abs().max()) < 5e-6
+    assert float((dep - out["depth"]).abs().max()) < 2e-5
+    assert float((alp - out["alpha"]).abs().max()) < 5e-6
+    obj = (col * gc.double()).sum() + (dep * gd.double()).sum() + (alp * ga.double()).sum()
+    names = ["means3D", "means2D", "shs", "colors_precomp", "opacities", "scales", "rotations", "cov3D_precomp"]
+    wrt = [(n, t) for n, t in zip(names, (m3, m2, sh64, cp64, op, scl64, rot64, cov64)) if t is not None]
+    grads = torch.autograd.grad(obj, [t for _, t in wrt])
+    for (n, _), g64 in zip(wrt, grads):
+        assert rel_err(res[n], g64) < 2e-5, n
+
+
+def _one_gaussian_settings(H=32, W=32, fov=math.radians(60)):
+    c2w = scenes.look_at_c2w(torch.tensor([3.0, 0.0, 0.0]), torch.zeros(3), torch.tensor([0.0, 0.0, 1.0]))
+    wvt, full, center = scenes.cam_info_gaussian(c2w, fov, fov)
+    t = math.tan(fov / 2)
+    return O.Settings(H, W, t, t, torch.tensor([0.2, 0.4, 0.6]), 1.0, wvt, full, 0, center, False, False)
+
+
+def test_known_answer_single_isotropic_gaussian():
+    s = _one_gaussian_settings()
+    # place the Gaussian so that it projects exactly onto a pixel centre: pixel (16,16) <-> ndc = 1/32
+    H = W = 32
+    z = 3.0
+    ndc = (2 * 16 + 1) / W - 1.0
+    t = math.tan(math.radians(30))
+    # camera looks along -x from (3,0,0); view space x = world -y ... solve by projecting candidates
+    m = torch.zeros(1, 3, requires_grad=False)
+    pre0 = O.preprocess(m, torch.tensor([[0.7]]), torch.full((1, 3), 0.05), torch.tensor([[1.0, 0, 0, 0]]), None,
+                        None, torch.tensor([[0.9, 0.5, 0.1]]), s)
+    # the origin projects to ndc 0 -> pixel 15.5; shift in view space by half a pixel
+    px0 = float(pre0["px"][0])
+    assert abs(px0 - 15.5) < 1e-4
+    fx = W / (2 * t)
+    shift = 0.5 * z / fx
+    # find the world axis that moves +x in the image
+    best = None
+    for axis in range(3):
+        for sign in (1.0, -1.0):
+            mm = torch.zeros(1, 3)
+            mm[0, axis] = sign * shift
+            pp = O.preprocess(mm, torch.tensor([[0.7]]), torch.full((1, 3), 0.05), torch.tensor([[1.0, 0, 0, 0]]),
+                              None, None, torch.tensor([[0.9, 0.5, 0.1]]), s)
+            if abs(float(pp["px"][0]) - 16.0) < 1e-3 and abs(float(pp["py"][0]) - 15.5) < 1e-3:
+                best = mm
+    assert best is not None
+    op, rgb = 0.7, torch.tensor([[0.9, 0.5, 0.1]])
+    out, pre, binned = O.rasterize_forward(best, None, None, rgb, torch.tensor([[op]]), torch.full((1, 3), 0.05),
+                                           torch.tensor([[1.0, 0, 0, 0]]), None, s)
+    # radius formula: isotropic sigma^2 = (fx * 0.05 / z)^2 + 0.3
+    var = (fx * 0.05 / z) ** 2 + 0.3
+    assert int(pre["radii"][0]) == math.ceil(3 * math.sqrt(var))
+    # pixel row 15/16 straddle py = 15.5: the centre column x = 16 has dy = +-0.5
+    G = math.exp(-0.5 * 0.25 / var)
+    a = min(0.99, op * G)
+    for y in (15, 16):
+        assert abs(float(out["alpha"][0, y, 16]) - a) < 1e-6
+        for c in range(3):
+            assert abs(float(out["color"][c, y, 16]) - (float(rgb[0, c]) * a + float(s.bg[c]) * (1 - a))) < 1e-6
+        assert abs(float(out["depth"][0, y, 16]) - float(pre["depth"][0]) * a) < 1e-5
+        assert int(out["n_contrib"][y, 16]) == 1
+    # far corner untouched: background
+    assert torch.allclose(out["color"][:, 0, 0], s.bg)
+
+
+def test_known_answer_near_cull_ordering_and_ties():
+    s = _one_gaussian_settings()
+    sc = torch.full((3, 3), 0.05)
+    rot = torch.tensor([[1.0, 0, 0, 0]]).repeat(3, 1)
+    # camera at x=3 looking at the origin: depth = 3 - x.  Gaussian 0 behind the near plane (depth 0.1)
+    means = torch.tensor([[2.9, 0.0, 0.0], [0.5, 0.0, 0.0], [0.5, 0.0, 0.0]])
+    rgb = torch.tensor([[1.0, 0, 0], [0, 1.0, 0], [0, 0, 1.0]])
+    op = torch.tensor([[0.9], [0.6], [0.6]])
+    out, pre, binned = O.rasterize_forward(means, None, None, rgb, op, sc, rot, None, s)
+    assert int(pre["radii"][0]) == 0 and int(pre["tiles_touched"][0]) == 0
+    assert int(pre["radii"][1]) > 0
+    # identical depth bits -> stable sort keeps index order: 1 before 2 in every tile list
+    pl = binned["point_list"].tolist()
+    rg = binned["ranges"]
+    for t in range(rg.shape[0]):
+        seg = pl[int(rg[t, 0]):int(rg[t, 1])]
+        if seg:
+            assert seg == sorted(seg) and set(seg) <= {1, 2}
+    # green (index 1) is blended first: at the centre pixels green weight > blue weight
+    cy = cx = 15
+    assert float(out["color"][1, cy, cx]) > float(out["color"][2, cy, cx])
+    g = O.rasterize_backward((means, None, None, rgb, op, sc, rot, None), s, pre, binned, out,
+                             *scenes.pixel_grads(32, 32, 1))
+    for k in ("means3D", "means2D", "colors_precomp", "opacities", "scales", "rotations"):
+        assert float(g[k][0].abs().max()) == 0.0          # culled Gaussian: exactly zero gradients
+    # nearer Gaussian first: move Gaussian 2 nearer -> it is listed before Gaussian 1
+    means2 = means.clone()
+    means2[2, 0] = 1.0
+    _, _, b2 = O.rasterize_forward(means2, None, None, rgb, op, sc, rot, None, s)
+    first = int(b2["ranges"][b2["ranges"][:, 1] > 0][0, 0])
+    assert b2["point_list"][first] == 2
+
+
+def test_higher_msb_and_sort_bits():
+    assert [spec.higher_msb(n) for n in (64, 256, 1024, 4096)] == [7, 9, 11, 13]
+    assert spec.higher_msb(1000) == 10 and spec.higher_msb(1) == 1
+
+
+def test_integer_stages_consistent():
+    sc, cam = _small(3000, 0, 64, 80, 5, scale_mul=1.0)
+    s = oracle_settings(cam, 0)
+    with torch.no_grad():
+        pre = O.preprocess(sc.means3D, sc.opacities, sc.scales, sc.rotations, None, sc.shs, None, s)
+        b = O.bin_and_sort(pre, s)
+    assert b["num_rendered"] == int(pre["tiles_touched"].sum())
+    ks = b["keys_sorted"]
+    assert bool((ks[1:] >= ks[:-1]).all())
+    tiles = (ks >> 32)
+    gx = (80 + 15) // 16
+    # every list entry's tile lies inside its Gaussian's rectangle
+    pl = b["point_list"].long()
+    tx, ty = tiles % gx, tiles // gx
+    assert bool(((tx >= pre["rect_min"][pl, 0]) & (tx < pre["rect_max"][pl, 0]) &
+                 (ty >= pre["rect_min"][pl, 1]) & (ty < pre["rect_max"][pl, 1])).all())
+    # ranges partition the list
+    r = b["ranges"].long()
+    assert int((r[:, 1] - r[:, 0]).sum()) == b["num_rendered"]
+    # low word of the key == float bits of the depth
+    assert torch.equal((ks & 0xFFFFFFFF).to(torch.int32), pre["depth"][pl].contiguous().view(torch.int32))
+
+
+def test_golden_vectors_config1():
+    """Oracle output on BASELINE.json configs[0] equals the committed fixture (tests/golden/make_golden.py)."""
+    import importlib.util
+    spec_ = importlib.util.spec_from_file_location("make_golden", GOLDEN.with_name("make_golden.py"))
+    mg = importlib.util.module_from_spec(spec_)
+    spec_.loader.exec_module(mg)
+    new = mg.build()
+    old = np.load(GOLDEN)
+    assert str(old["inputs_sha256"]) == str(new["inputs_sha256"]), "synthetic scene generator changed"
+    for k in ("radii", "tiles_touched", "ranges", "n_contrib"):
+        assert np.array_equal(old[k], new[k]), k
+    assert int(old["num_rendered"]) == int(new["num_rendered"])
+    assert str(old["keys_sorted_sha256"]) == str(new["keys_sorted_sha256"])
+    assert str(old["point_list_sha256"]) == str(new["point_list_sha256"])
+    for k in ("color", "depth", "alpha"):
+        assert float(np.abs(old[k] - new[k]).max()) < 2e-6, k
+    for k in ("g_means3D", "g_means2D", "g_shs", "g_opacities", "g_scales", "g_rotations"):
+        assert float(np.abs(old[k] - new[k]).max()) <= 1e-5 * float(np.abs(old[k]).max()), k
+
+
+def test_dist2_oracle_against_kdtree():
+    g = torch.Generator().manual_seed(0)
+    pts = torch.randn(3000, 3, generator=g)
+    ref = scenes.mean_knn_dist2(pts)
+    got = dist2_oracle(pts)
+    assert rel_err(got, ref) < 1e-5
+    assert float(dist2_oracle(torch.zeros(100, 3)).abs().max()) == 0.0
+    # a duplicate counts as a neighbour at distance 0 (self is excluded by index, not by value):
+    # neighbours of a doubled point are its twin (0) and the doubled nearest other point (d1, d1)
+    base = pts[:10]
+    d = ((base[:, None] - base[None]) ** 2).sum(-1)
+    d.fill_diagonal_(float("inf"))
+    d1 = d.min(dim=1).values
+    dup = dist2_oracle(torch.cat([base, base]))
+    assert torch.allclose(dup[:10], 2 * d1 / 3, rtol=1e-5) and torch.allclose(dup[10:], 2 * d1 / 3, rtol=1e-5)
