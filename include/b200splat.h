@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define B200SPLAT_ABI_VERSION 1
+#define B200SPLAT_ABI_VERSION 2
 
 #define B200SPLAT_OK 0
 #define B200SPLAT_ERR_INVALID -1   /* bad argument                                  */
@@ -155,6 +155,84 @@ typedef struct b200splat_backward_args {
 
 int b200splat_backward(const b200splat_backward_args* args);
 
+/* ---- view-batched forward / backward ------------------------------------------------------------
+ * The reference renders the B views of a step one after the other with the same Gaussians
+ * (renderer/gaussian_batch_renderer.py:21-54).  These entry points take up to B200SPLAT_MAX_VIEWS views at
+ * once: the Gaussian parameters are read once per phase for all views, every phase of the pipeline is ONE
+ * launch for the whole batch (so the long per-tile tails of one view are filled by the others), and
+ * num_rendered never visits the host -- each view's binning buffer has a caller-chosen capacity
+ * (b200splat_binning_capacity(binning_bytes) pairs); if a view needs more, its result is invalid and
+ * overflow_out[v] (sync != 0) / the status word (b200splat_forward_views_get) says so: retry with a larger
+ * buffer.  All views share P, M, the image size, scale_modifier and sh_degree (taken from cams[0]).
+ * Arrays of V device pointers live on the host. */
+#define B200SPLAT_MAX_VIEWS 8
+int64_t b200splat_binning_capacity(size_t binning_bytes);
+
+typedef struct b200splat_batch_forward_args {
+    int32_t V;
+    const b200splat_camera* cams; /* V */
+    int32_t P;
+    int32_t M;
+    const float* means3D;
+    const float* shs;
+    const float* colors_precomp;
+    const float* opacities;
+    const float* scales;
+    const float* rotations;
+    float* const* out_color;      /* V x (3,H,W) */
+    float* const* out_depth;
+    float* const* out_alpha;
+    int32_t* const* radii;        /* V x (P) */
+    void* const* geom_buffer;     /* V, each >= b200splat_geom_bytes(P) */
+    void* const* image_buffer;    /* V, each >= b200splat_image_bytes(H, W) */
+    void* const* binning_buffer;  /* V, each binning_bytes */
+    size_t binning_bytes;
+    b200splat_stream stream;
+    int32_t sync;                 /* != 0: synchronise the stream and fill the two host arrays below */
+    int64_t* num_rendered_out;    /* V */
+    int32_t* overflow_out;        /* V */
+} b200splat_batch_forward_args;
+
+int b200splat_forward_batched(const b200splat_batch_forward_args* args);
+
+/* Gradients of the parameters are summed over the V views (plus the previous contents when
+ * accumulate != 0); dL_dmeans2D (optional) is per view, as are the upstream pixel gradients. */
+typedef struct b200splat_batch_backward_args {
+    int32_t V;
+    const b200splat_camera* cams;
+    int32_t P;
+    int32_t M;
+    const float* means3D;
+    const float* shs;
+    const float* colors_precomp;
+    const float* opacities;
+    const float* scales;
+    const float* rotations;
+    const int32_t* const* radii;
+    const void* const* geom_buffer;
+    const void* const* image_buffer;
+    const void* const* binning_buffer;
+    size_t binning_bytes;
+    const float* const* dL_dout_color; /* V entries, any may be NULL */
+    const float* const* dL_dout_depth;
+    const float* const* dL_dout_alpha;
+    float* const* dL_dmeans2D;         /* NULL or V entries (each NULL or (P,3)) */
+    float* dL_dmeans3D;
+    float* dL_dshs;
+    float* dL_dcolors;
+    float* dL_dopacity;
+    float* dL_dscales;
+    float* dL_drotations;
+    void* const* scratch;              /* V, each >= b200splat_backward_scratch_bytes(P) */
+    int32_t accumulate;
+    float* stat_grad_accum;
+    float* stat_denom;
+    float* stat_max_radii;
+    b200splat_stream stream;
+} b200splat_batch_backward_args;
+
+int b200splat_backward_batched(const b200splat_batch_backward_args* args);
+
 /* ---- mark_visible: replaces markVisible (GaussianRasterizer.markVisible) ------------------- */
 int b200splat_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
                            const float* projmatrix, uint8_t* present, b200splat_stream stream);
@@ -188,12 +266,13 @@ typedef struct b200splat_forward_views {
     const uint32_t* point_offsets;
     const float* depths;
     const float* gauss2d; /* (P,12): x, y, conic a, conic b | conic c, opacity, depth, r | g, b, -, - */
-    const float* cov3D;   /* (P,6) */
+    const float* cov3D;   /* always NULL: Sigma3 is recomputed in backward instead of stored */
     const uint64_t* keys_sorted;
     const uint32_t* point_list;
     const uint32_t* ranges;
     const uint32_t* n_contrib;
     const uint32_t* n_visited;
+    const uint32_t* status; /* [0] != 0: binning capacity overflow */
 } b200splat_forward_views;
 
 int b200splat_forward_views_get(int32_t P, int32_t H, int32_t W, int64_t num_rendered,

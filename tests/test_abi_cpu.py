@@ -32,6 +32,8 @@ def test_struct_layouts_match_header_field_order():
     txt = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
     for cname, cls in (("b200splat_camera", _lib.Camera), ("b200splat_forward_args", _lib.ForwardArgs),
                        ("b200splat_backward_args", _lib.BackwardArgs),
+                       ("b200splat_batch_forward_args", _lib.BatchForwardArgs),
+                       ("b200splat_batch_backward_args", _lib.BatchBackwardArgs),
                        ("b200splat_forward_views", _lib.ForwardViews)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), txt, flags=re.S).group(1)
         fields = [re.split(r"[\s\*]+", d.strip())[-1] for d in body.split(";") if d.strip()]
@@ -41,10 +43,12 @@ def test_struct_layouts_match_header_field_order():
 def test_host_only_entry_points():
     from b200splat import _lib
     lib = _lib.lib
-    assert lib.b200splat_geom_bytes(1000) > 1000 * (48 + 4 + 24 + 1 + 4 + 4)
+    assert lib.b200splat_geom_bytes(1000) > 1000 * (48 + 4 + 1 + 4 + 4)
     assert lib.b200splat_geom_bytes(2000) > lib.b200splat_geom_bytes(1000)
     assert lib.b200splat_image_bytes(512, 512) >= 1024 * 8 + 512 * 512 * 12
     assert lib.b200splat_binning_bytes(1_000_000) >= 1_000_000 * 24
+    cap = lib.b200splat_binning_capacity(lib.b200splat_binning_bytes(1_000_000))
+    assert cap >= 1_000_000 and lib.b200splat_binning_bytes(cap) <= lib.b200splat_binning_bytes(1_000_000)
     assert lib.b200splat_backward_scratch_bytes(1000) >= 48_000
     assert lib.b200splat_sort_workspace_bytes(1 << 20) > 0 and lib.b200splat_scan_workspace_bytes(1 << 20) > 0
     assert lib.b200splat_dist2_workspace_bytes(4096) > 0

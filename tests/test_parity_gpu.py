@@ -299,3 +299,47 @@ def test_fused_densification_stats_and_accumulate():
     assert rel_err(pk.views["grad_accum"], acc) < 1e-5
     for k in ("means3D", "shs", "opacities", "scales", "rotations"):
         assert rel_err(pk.views[k], gsum[k]) < 1e-4, k
+
+
+def test_batched_entry_points_match_per_view_path():
+    """b200splat_forward_batched / _backward_batched (one launch per phase for all views, device-side
+    num_rendered, gradients summed in registers) == the per-view single-view calls, bit-exact on the
+    integer outputs."""
+    from b200splat import batched, ops
+    P, deg, H, W, V = 6000, 3, 80, 96, 3
+    sc, _ = _scene(P, deg, H, W, 71)
+    cams_h = scenes.sds_cameras(V, H, W, seed=72)
+    dev = "cuda"
+    d = lambda t: t.to(dev).contiguous()
+    m3, sh, op, scl, rot = map(d, (sc.means3D, sc.shs, sc.opacities, sc.scales, sc.rotations))
+    cams = [ops.make_cam(cuda_settings(oracle_settings(c, deg)), dev) for c in cams_h]
+    pgs = [tuple(d(g) for g in scenes.pixel_grads(H, W, 80 + i)) for i in range(V)]
+    # per-view path
+    pk_ref = batched.PackedGrads(P, sh.shape[1], dev)
+    ref_imgs = batched.render_views_fwd_bwd(cams, m3, sh, None, op, scl, rot, pgs, pk_ref, keep_images=True)
+    # batched path (tiny initial capacity forces one overflow + regrow in calibrate)
+    br = batched.BatchRenderer(P, sh.shape[1], H, W, dev, views=V)
+    br.ws[0]._alloc_binning(1024)
+    br.step(cams, m3, sh, None, op, scl, rot, pgs)
+    assert not br.overflowed()
+    ws = br.ws[0]
+    for v in range(V):
+        color, depth, alpha, radii = ref_imgs[v]
+        assert torch.equal(ws.radii[v], radii)
+        assert float((ws.color[v] - color).abs().max()) < 1e-6
+        assert float((ws.depth[v] - depth).abs().max()) < 1e-5
+        assert float((ws.alpha[v] - alpha).abs().max()) < 1e-6
+    for k in ("means3D", "shs", "opacities", "scales", "rotations"):
+        assert rel_err(br.packed.views[k], pk_ref.views[k]) < 1e-4, k
+    assert torch.equal(br.packed.max_radii, pk_ref.max_radii)
+    assert torch.equal(br.packed.views["denom"], pk_ref.views["denom"])
+    assert rel_err(br.packed.views["grad_accum"], pk_ref.views["grad_accum"]) < 1e-5
+    # sorted keys / ranges of a batched view are those of the single-view call
+    st_b = ws.states(sh.shape[1])[1]
+    vb = ops.forward_views(cams[1], st_b)
+    _, _, _, _, st_s = ops.forward(cams[1], m3, sh, None, op, scl, rot, None)
+    vs = ops.forward_views(cams[1], st_s)
+    R = st_s.num_rendered
+    assert int(vb["point_offsets"][-1]) == R
+    assert torch.equal(vb["keys_sorted"][:R], vs["keys_sorted"]) and torch.equal(vb["point_list"][:R], vs["point_list"])
+    assert torch.equal(vb["ranges"], vs["ranges"]) and torch.equal(vb["n_contrib"], vs["n_contrib"])

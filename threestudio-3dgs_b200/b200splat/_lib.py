@@ -13,7 +13,8 @@ from pathlib import Path
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("B200SPLAT_LIB", _HERE / "libb200splat.so"))
 
-ABI_VERSION = 1
+ABI_VERSION = 2
+MAX_VIEWS = 8
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 
@@ -64,7 +65,38 @@ class BackwardArgs(C.Structure):
 class ForwardViews(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "tiles_touched", "point_offsets", "depths", "gauss2d", "cov3D", "keys_sorted", "point_list",
-        "ranges", "n_contrib", "n_visited")]
+        "ranges", "n_contrib", "n_visited", "status")]
+
+
+PP = C.POINTER(C.c_void_p)   # host array of device pointers
+
+
+class BatchForwardArgs(C.Structure):
+    _fields_ = [
+        ("V", C.c_int32), ("cams", C.POINTER(Camera)), ("P", C.c_int32), ("M", C.c_int32),
+        ("means3D", C.c_void_p), ("shs", C.c_void_p), ("colors_precomp", C.c_void_p),
+        ("opacities", C.c_void_p), ("scales", C.c_void_p), ("rotations", C.c_void_p),
+        ("out_color", PP), ("out_depth", PP), ("out_alpha", PP), ("radii", PP),
+        ("geom_buffer", PP), ("image_buffer", PP), ("binning_buffer", PP), ("binning_bytes", C.c_size_t),
+        ("stream", C.c_void_p), ("sync", C.c_int32),
+        ("num_rendered_out", C.POINTER(C.c_int64)), ("overflow_out", C.POINTER(C.c_int32)),
+    ]
+
+
+class BatchBackwardArgs(C.Structure):
+    _fields_ = [
+        ("V", C.c_int32), ("cams", C.POINTER(Camera)), ("P", C.c_int32), ("M", C.c_int32),
+        ("means3D", C.c_void_p), ("shs", C.c_void_p), ("colors_precomp", C.c_void_p),
+        ("opacities", C.c_void_p), ("scales", C.c_void_p), ("rotations", C.c_void_p),
+        ("radii", PP), ("geom_buffer", PP), ("image_buffer", PP), ("binning_buffer", PP),
+        ("binning_bytes", C.c_size_t),
+        ("dL_dout_color", PP), ("dL_dout_depth", PP), ("dL_dout_alpha", PP), ("dL_dmeans2D", PP),
+        ("dL_dmeans3D", C.c_void_p), ("dL_dshs", C.c_void_p), ("dL_dcolors", C.c_void_p),
+        ("dL_dopacity", C.c_void_p), ("dL_dscales", C.c_void_p), ("dL_drotations", C.c_void_p),
+        ("scratch", PP), ("accumulate", C.c_int32),
+        ("stat_grad_accum", C.c_void_p), ("stat_denom", C.c_void_p), ("stat_max_radii", C.c_void_p),
+        ("stream", C.c_void_p),
+    ]
 
 
 # every symbol include/b200splat.h declares: name -> (restype, argtypes)
@@ -78,6 +110,9 @@ SYMBOLS = {
     "b200splat_backward_scratch_bytes": (C.c_size_t, [C.c_int32]),
     "b200splat_forward": (C.c_int, [C.POINTER(ForwardArgs)]),
     "b200splat_backward": (C.c_int, [C.POINTER(BackwardArgs)]),
+    "b200splat_binning_capacity": (C.c_int64, [C.c_size_t]),
+    "b200splat_forward_batched": (C.c_int, [C.POINTER(BatchForwardArgs)]),
+    "b200splat_backward_batched": (C.c_int, [C.POINTER(BatchBackwardArgs)]),
     "b200splat_mark_visible": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200splat_dist2_workspace_bytes": (C.c_size_t, [C.c_int32]),
     "b200splat_dist2": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

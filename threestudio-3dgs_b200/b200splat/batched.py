@@ -2,20 +2,27 @@
 single-view rasterizer calls (renderer/gaussian_batch_renderer.py:21-54) followed by per-view
 densification statistics (geometry/gaussian_base.py:815-819, 846-851).
 
-Here the per-view backward writes straight into one packed gradient buffer (first view overwrites,
-later views accumulate) and the statistics are fused into the preprocess-backward kernel, so a
-multi-GPU step is: local views -> ONE sum all-reduce of the packed buffer + ONE max all-reduce of
-max_radii (b200splat/dist.py).  Note the order the reference's statistics impose
-(SURVEY.md 8e): ||means2D.grad|| is taken per view *before* any summation, so it is reduced locally
-per view and only the accumulators are all-reduced, never means2D.grad itself.
+Here the whole batch goes through the C ABI's view-batched entry points (b200splat_forward_batched /
+b200splat_backward_batched): the Gaussian parameters are read once per phase for all views, every
+phase is one launch for the batch, num_rendered stays on the device (persistent binning buffers with a
+capacity), the parameter gradients of all views are summed in registers and written once into one
+packed buffer, and the densification statistics are a fused epilogue.  A multi-GPU step is then:
+local views -> ONE sum all-reduce of the packed buffer + ONE max all-reduce of max_radii
+(b200splat/dist.py).  Note the order the reference's statistics impose:
+||means2D.grad|| is taken per view *before* any summation, so it is reduced per view on the rank and
+only the accumulators are all-reduced, never means2D.grad itself.
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Dict, List, Optional, Sequence
 
 import torch
 
-from . import ops
+from . import _lib, ops
+from ._lib import check, lib
+
+MAX_VIEWS = _lib.MAX_VIEWS
 
 
 class PackedGrads:
@@ -55,12 +62,170 @@ class PackedGrads:
         return {k: v for k, v in self.views.items() if k not in ("grad_accum", "denom")}
 
 
+def _parr(ptrs):
+    return (C.c_void_p * len(ptrs))(*ptrs)
+
+
+class BatchWorkspace:
+    """Persistent device buffers of a view batch (torch owns them): per view the geometry / image /
+    binning buffers, the backward scratch and the output images.  The binning buffers have a capacity in
+    (tile, Gaussian) pairs; ``render`` grows them and re-runs when a view overflowed."""
+
+    def __init__(self, V: int, P: int, H: int, W: int, device, capacity_pairs: Optional[int] = None):
+        assert 1 <= V <= MAX_VIEWS
+        self.V, self.P, self.H, self.W, self.device = V, P, H, W, device
+        u8 = lambda n: torch.empty(int(n), dtype=torch.uint8, device=device)
+        f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=device)
+        self.geom = [u8(lib.b200splat_geom_bytes(P)) for _ in range(V)]
+        self.image = [u8(lib.b200splat_image_bytes(H, W)) for _ in range(V)]
+        self.scratch = [u8(lib.b200splat_backward_scratch_bytes(P)) for _ in range(V)]
+        self.color = [f32(3, H, W) for _ in range(V)]
+        self.depth = [f32(1, H, W) for _ in range(V)]
+        self.alpha = [f32(1, H, W) for _ in range(V)]
+        self.radii = [torch.empty(P, dtype=torch.int32, device=device) for _ in range(V)]
+        self.binning: List[torch.Tensor] = []
+        self.binning_bytes = 0
+        self.num_rendered = [0] * V
+        self._alloc_binning(capacity_pairs or max(4 * P, 1 << 16))
+
+    def _alloc_binning(self, pairs: int):
+        self.binning_bytes = int(lib.b200splat_binning_bytes(int(pairs)))
+        self.binning = [torch.empty(self.binning_bytes, dtype=torch.uint8, device=self.device) for _ in range(self.V)]
+        self.capacity = int(lib.b200splat_binning_capacity(self.binning_bytes))
+
+    def states(self, M: int):
+        """Per-view ops.ForwardState (for ops.forward_views / the single-view backward)."""
+        return [ops.ForwardState(self.P, M, self.capacity, self.geom[v], self.binning[v], self.image[v])
+                for v in range(self.V)]
+
+
+def forward_batched(ws: BatchWorkspace, cams: Sequence[ops.Cam], means3D, shs, colors_precomp, opacities, scales,
+                    rotations, sync: bool = False):
+    """One launch set for all views.  With sync=True returns (num_rendered list, overflow list)."""
+    V = len(cams)
+    assert V == ws.V
+    M = 0 if shs is None else int(shs.shape[1])
+    cam_arr = (_lib.Camera * V)(*[c.c_struct() for c in cams])
+    a = _lib.BatchForwardArgs()
+    a.V, a.cams, a.P, a.M = V, cam_arr, ws.P, M
+    a.means3D, a.shs, a.colors_precomp = ops._ptr(means3D), ops._ptr(shs), ops._ptr(colors_precomp)
+    a.opacities, a.scales, a.rotations = ops._ptr(opacities), ops._ptr(scales), ops._ptr(rotations)
+    keep = [_parr([t.data_ptr() for t in lst]) for lst in (ws.color, ws.depth, ws.alpha, ws.radii, ws.geom,
+                                                            ws.image, ws.binning)]
+    a.out_color, a.out_depth, a.out_alpha, a.radii, a.geom_buffer, a.image_buffer, a.binning_buffer = keep
+    a.binning_bytes = ws.binning_bytes
+    a.stream = ops._stream()
+    a.sync = int(sync)
+    nr = (C.c_int64 * V)()
+    ov = (C.c_int32 * V)()
+    a.num_rendered_out, a.overflow_out = nr, ov
+    with torch.cuda.device(ws.device):
+        check(lib.b200splat_forward_batched(C.byref(a)), "b200splat_forward_batched")
+    if sync:
+        ws.num_rendered = [int(x) for x in nr]
+        return ws.num_rendered, [int(x) for x in ov]
+    return None, None
+
+
+def backward_batched(ws: BatchWorkspace, cams: Sequence[ops.Cam], means3D, shs, colors_precomp, opacities, scales,
+                     rotations, pixel_grads, out: Dict[str, torch.Tensor], accumulate: bool = False,
+                     stats=None, means2D_out: Optional[Sequence[Optional[torch.Tensor]]] = None):
+    V = len(cams)
+    M = 0 if shs is None else int(shs.shape[1])
+    cam_arr = (_lib.Camera * V)(*[c.c_struct() for c in cams])
+    a = _lib.BatchBackwardArgs()
+    a.V, a.cams, a.P, a.M = V, cam_arr, ws.P, M
+    a.means3D, a.shs, a.colors_precomp = ops._ptr(means3D), ops._ptr(shs), ops._ptr(colors_precomp)
+    a.opacities, a.scales, a.rotations = ops._ptr(opacities), ops._ptr(scales), ops._ptr(rotations)
+    gp = lambda i: _parr([ops._ptr(pg[i]) if pg is not None and pg[i] is not None else None for pg in pixel_grads])
+    keep = [_parr([t.data_ptr() for t in lst]) for lst in (ws.radii, ws.geom, ws.image, ws.binning, ws.scratch)]
+    a.radii, a.geom_buffer, a.image_buffer, a.binning_buffer, a.scratch = keep
+    a.binning_bytes = ws.binning_bytes
+    gc, gd, ga = gp(0), gp(1), gp(2)
+    a.dL_dout_color, a.dL_dout_depth, a.dL_dout_alpha = gc, gd, ga
+    m2 = None
+    if means2D_out is not None:
+        m2 = _parr([ops._ptr(t) for t in means2D_out])
+        a.dL_dmeans2D = m2
+    a.dL_dmeans3D, a.dL_dshs, a.dL_dcolors = ops._ptr(out["means3D"]), ops._ptr(out.get("shs")), \
+        ops._ptr(out.get("colors_precomp"))
+    a.dL_dopacity, a.dL_dscales, a.dL_drotations = ops._ptr(out["opacities"]), ops._ptr(out["scales"]), \
+        ops._ptr(out["rotations"])
+    a.accumulate = int(bool(accumulate))
+    if stats is not None:
+        a.stat_grad_accum, a.stat_denom, a.stat_max_radii = (ops._ptr(t) for t in stats)
+    a.stream = ops._stream()
+    with torch.cuda.device(ws.device):
+        check(lib.b200splat_backward_batched(C.byref(a)), "b200splat_backward_batched")
+
+
+class BatchRenderer:
+    """fwd+bwd of a step's views with persistent buffers.  ``step`` returns nothing: gradients and
+    statistics are in ``packed``; rendered images stay in ``ws.color/depth/alpha`` until the next step."""
+
+    def __init__(self, P: int, M: int, H: int, W: int, device, views: int, color_mode: str = "shs"):
+        self.P, self.M, self.H, self.W, self.device = P, M, H, W, device
+        self.chunks = [min(MAX_VIEWS, views - i) for i in range(0, views, MAX_VIEWS)]
+        self.ws = [BatchWorkspace(v, P, H, W, device) for v in self.chunks]
+        self.packed = PackedGrads(P, M, device, color_mode)
+        self.calibrated = False
+
+    def calibrate(self, cams, means3D, shs, colors_precomp, opacities, scales, rotations, headroom: float = 1.25):
+        """Size the binning buffers from one synchronous forward (num_rendered changes slowly between steps)."""
+        i = 0
+        for ws, n in zip(self.ws, self.chunks):
+            while True:
+                nr, ov = forward_batched(ws, cams[i:i + n], means3D, shs, colors_precomp, opacities, scales, rotations,
+                                         sync=True)
+                need = int(max(nr) * headroom) + 4096
+                if any(ov) or ws.capacity < max(nr):
+                    ws._alloc_binning(max(need, 2 * ws.capacity))
+                    continue
+                if ws.capacity > 2 * need or ws.capacity < need:
+                    ws._alloc_binning(need)
+                    continue
+                break
+            i += n
+        self.calibrated = True
+
+    def step(self, cams, means3D, shs, colors_precomp, opacities, scales, rotations, pixel_grads):
+        """pixel_grads[v] = (dL/dcolor, dL/ddepth|None, dL/dalpha|None) or a callable(color, depth, alpha)."""
+        if not self.calibrated:
+            self.calibrate(cams, means3D, shs, colors_precomp, opacities, scales, rotations)
+        pk = self.packed
+        pk.zero_stats_()
+        out = pk.grads()
+        stats = (pk.views["grad_accum"], pk.views["denom"], pk.max_radii)
+        i = 0
+        for ci, (ws, n) in enumerate(zip(self.ws, self.chunks)):
+            cs = cams[i:i + n]
+            forward_batched(ws, cs, means3D, shs, colors_precomp, opacities, scales, rotations, sync=False)
+            pgs = []
+            for v in range(n):
+                pg = pixel_grads[i + v]
+                pgs.append(pg(ws.color[v], ws.depth[v], ws.alpha[v]) if callable(pg) else pg)
+            backward_batched(ws, cs, means3D, shs, colors_precomp, opacities, scales, rotations, pgs, out,
+                             accumulate=ci > 0, stats=stats)
+            i += n
+
+    def overflowed(self) -> bool:
+        """Lazy overflow check (one small D2H): True if any view of the last step exceeded its capacity."""
+        flags = []
+        for ws in self.ws:
+            for v in range(ws.V):
+                st = ops.ForwardState(self.P, self.M, ws.capacity, ws.geom[v], ws.binning[v], ws.image[v])
+                flags.append(ops.status_tensor(self.H, self.W, st))
+        bad = bool(torch.stack(flags)[:, 0].any().item())
+        if bad:
+            self.calibrated = False
+        return bad
+
+
 def render_views_fwd_bwd(cams: Sequence[ops.Cam], means3D, shs, colors_precomp, opacities, scales, rotations,
                          pixel_grads, packed: PackedGrads, keep_images: bool = False):
-    """Forward + backward of every view in ``cams``; parameter gradients summed over the views and the
-    densification statistics of the views land in ``packed``.  ``pixel_grads[v]`` = (dL/dcolor (3,H,W),
-    dL/ddepth (1,H,W) or None, dL/dalpha (1,H,W) or None) or a callable(color, depth, alpha) -> that tuple
-    (the loss).  Returns the list of (color, depth, alpha, radii) when keep_images."""
+    """Per-view reference loop over the single-view entry points (the shape of the reference's own
+    batch_forward): forward + backward of every view, gradients accumulated into ``packed``.  Kept as the
+    baseline the batched path is tested against."""
     packed.zero_stats_()
     out = dict(packed.grads())
     out["means2D"] = packed.means2D_scratch

@@ -226,6 +226,15 @@ def inclusive_scan_u32(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def status_tensor(H: int, W: int, st: ForwardState) -> torch.Tensor:
+    """(4,) int32 device tensor aliasing the view's status words ([0] != 0: binning capacity overflow)."""
+    v = _lib.ForwardViews()
+    check(lib.b200splat_forward_views_get(st.P, H, W, 0, _ptr(st.geom), None, _ptr(st.image), C.byref(v)),
+          "b200splat_forward_views_get")
+    off = v.status - st.image.data_ptr()
+    return st.image[off:off + 16].view(torch.int32)
+
+
 def forward_views(cam: Cam, st: ForwardState):
     """Copies of the forward's intermediate buffers (for the bit-exact parity tests)."""
     v = _lib.ForwardViews()
@@ -247,10 +256,10 @@ def forward_views(cam: Cam, st: ForwardState):
         point_offsets=view(st.geom, v.point_offsets, P, torch.int32),
         depths=view(st.geom, v.depths, P, torch.float32),
         gauss2d=view(st.geom, v.gauss2d, P * 12, torch.float32).reshape(P, 12),
-        cov3D=view(st.geom, v.cov3D, P * 6, torch.float32).reshape(P, 6),
         keys_sorted=view(st.binning, v.keys_sorted, R, torch.int64) if R else torch.empty(0, dtype=torch.int64),
         point_list=view(st.binning, v.point_list, R, torch.int32) if R else torch.empty(0, dtype=torch.int32),
         ranges=view(st.image, v.ranges, T * 2, torch.int32).reshape(T, 2),
         n_contrib=view(st.image, v.n_contrib, cam.H * cam.W, torch.int32).reshape(cam.H, cam.W),
         n_visited=view(st.image, v.n_visited, cam.H * cam.W, torch.int32).reshape(cam.H, cam.W),
+        status=view(st.image, v.status, 4, torch.int32),
     )

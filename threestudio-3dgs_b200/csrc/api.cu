@@ -60,7 +60,6 @@ size_t geom_layout(int P, void* base, GeomViews* v) {
     const size_t n = (size_t)(P > 0 ? P : 1);
     g.rec = carve<float>(p, n * REC_FLOATS);
     g.depths = carve<float>(p, n);
-    g.cov3D = carve<float>(p, n * 6);
     g.clamped = carve<uint8_t>(p, n);
     g.tiles_touched = carve<uint32_t>(p, n);
     g.point_offsets = carve<uint32_t>(p, n);
@@ -70,12 +69,11 @@ size_t geom_layout(int P, void* base, GeomViews* v) {
     return (size_t)(p - p0);
 }
 
-size_t binning_layout(int64_t R, void* base, BinningViews* v) {
+size_t binning_layout(int64_t capacity, void* base, BinningViews* v) {
     char* p = reinterpret_cast<char*>(base);
     char* p0 = p;
     BinningViews b;
-    const size_t n = (size_t)(R > 0 ? R : 1);
-    b.final_sel = carve<int32_t>(p, 1);
+    const size_t n = (size_t)(capacity > 0 ? capacity : 1);
     b.keys[0] = carve<uint64_t>(p, n);
     b.keys[1] = carve<uint64_t>(p, n);
     b.vals[0] = carve<uint32_t>(p, n);
@@ -95,9 +93,21 @@ size_t image_layout(int H, int W, void* base, ImageViews* v) {
     im.n_contrib = carve<uint32_t>(p, (size_t)H * W);
     im.final_T = carve<float>(p, (size_t)H * W);
     im.n_visited = carve<uint32_t>(p, (size_t)H * W);
-    im.tile_order = carve<uint32_t>(p, (size_t)gx * gy);
+    im.tile_order = carve<uint32_t>(p, (size_t)gx * gy * MAX_VIEWS);
+    im.status = carve<uint32_t>(p, STATUS_WORDS);
     if (v) *v = im;
     return (size_t)(p - p0);
+}
+
+// largest capacity (pairs) whose layout fits in `bytes`
+static int64_t capacity_for_bytes(size_t bytes) {
+    int64_t lo = 0, hi = (int64_t)(bytes / 24) + 1;
+    if (hi > (1ll << 30) - 1) hi = (1ll << 30) - 1;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi + 1) / 2;
+        if (binning_layout(mid, nullptr, nullptr) <= bytes) lo = mid; else hi = mid - 1;
+    }
+    return lo;
 }
 
 static int higher_msb(uint32_t n) {
@@ -117,30 +127,63 @@ static int sorted_sel_for(int T) {
     return ((end_bit + 7) / 8) & 1;
 }
 
-static int make_camera(const b200splat_camera& c, int M, bool has_sh, CameraParams* out) {
+// shared (view independent) part of the batch table from the first camera
+static int init_table(const b200splat_camera& c, int P, int M, bool has_sh, BatchTab* tab) {
     if (c.image_height <= 0 || c.image_width <= 0) return fail(B200SPLAT_ERR_INVALID, "image size must be positive");
-    if (!c.bg || !c.viewmatrix || !c.projmatrix || !c.campos)
-        return fail(B200SPLAT_ERR_INVALID, "camera device pointers (bg, viewmatrix, projmatrix, campos) must be set");
-    CameraParams p;
-    p.H = c.image_height, p.W = c.image_width;
-    p.grid_x = (p.W + BLOCK_X - 1) / BLOCK_X, p.grid_y = (p.H + BLOCK_Y - 1) / BLOCK_Y;
-    p.tanfovx = c.tanfovx, p.tanfovy = c.tanfovy;
-    p.focal_x = (float)p.W / (2.0f * c.tanfovx);
-    p.focal_y = (float)p.H / (2.0f * c.tanfovy);
-    p.limx = FOV_CLAMP * c.tanfovx;
-    p.limy = FOV_CLAMP * c.tanfovy;
-    p.scale_modifier = c.scale_modifier;
-    p.M = M;
+    memset(tab, 0, sizeof(*tab));
+    tab->P = P, tab->M = M;
+    tab->H = c.image_height, tab->W = c.image_width;
+    tab->grid_x = (tab->W + BLOCK_X - 1) / BLOCK_X, tab->grid_y = (tab->H + BLOCK_Y - 1) / BLOCK_Y;
+    tab->scale_modifier = c.scale_modifier;
     int deg = c.sh_degree < 0 ? 0 : c.sh_degree;
     if (has_sh) {
         int cap = (int)std::floor(std::sqrt((double)(M > 0 ? M : 1)) + 1e-9) - 1;  // (P,1,3) "SH" with sh_degree > 0
         if (deg > cap) deg = cap;
+        if (deg > 3) deg = 3;
+    } else {
+        deg = -1;
     }
-    if (deg > 3) deg = 3;
-    p.sh_degree = deg;
-    p.bg = c.bg, p.view = c.viewmatrix, p.proj = c.projmatrix, p.campos = c.campos;
-    *out = p;
+    tab->sh_degree = deg;
+    tab->end_bit = 32 + higher_msb((uint32_t)(tab->grid_x * tab->grid_y));
     return B200SPLAT_OK;
+}
+
+static int fill_camera(const b200splat_camera& c, const BatchTab& tab, ViewTab* vt) {
+    if (!c.bg || !c.viewmatrix || !c.projmatrix || !c.campos)
+        return fail(B200SPLAT_ERR_INVALID, "camera device pointers (bg, viewmatrix, projmatrix, campos) must be set");
+    if (c.image_height != tab.H || c.image_width != tab.W)
+        return fail(B200SPLAT_ERR_INVALID, "all views of a batch must share the image size");
+    vt->view = c.viewmatrix, vt->proj = c.projmatrix, vt->campos = c.campos, vt->bg = c.bg;
+    vt->tanfovx = c.tanfovx, vt->tanfovy = c.tanfovy;
+    vt->focal_x = (float)tab.W / (2.0f * c.tanfovx);
+    vt->focal_y = (float)tab.H / (2.0f * c.tanfovy);
+    vt->limx = FOV_CLAMP * c.tanfovx;
+    vt->limy = FOV_CLAMP * c.tanfovy;
+    return B200SPLAT_OK;
+}
+
+static void fill_geom(int P, void* geom, ViewTab* vt) {
+    GeomViews g;
+    geom_layout(P, geom, &g);
+    vt->rec = g.rec, vt->depths = g.depths, vt->clamped = g.clamped;
+    vt->tiles_touched = g.tiles_touched, vt->point_offsets = g.point_offsets;
+    vt->scan_ticket = reinterpret_cast<uint32_t*>(g.scan_ws);
+    vt->scan_desc = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(g.scan_ws) + 16);
+}
+
+static void fill_image(int H, int W, void* image, ViewTab* vt, uint32_t** tile_order) {
+    ImageViews im;
+    image_layout(H, W, image, &im);
+    vt->ranges = im.ranges, vt->n_contrib = im.n_contrib, vt->n_visited = im.n_visited, vt->final_T = im.final_T;
+    vt->status = im.status;
+    if (tile_order) *tile_order = im.tile_order;
+}
+
+static void fill_binning(int64_t capacity, void* binning, ViewTab* vt) {
+    BinningViews b;
+    binning_layout(capacity, binning, &b);
+    vt->keys[0] = b.keys[0], vt->keys[1] = b.keys[1], vt->vals[0] = b.vals[0], vt->vals[1] = b.vals[1];
+    sort_workspace_views(b.sort_ws, &vt->hist, &vt->tickets, &vt->desc);
 }
 
 // ---- per-family CUDA-event timing ---------------------------------------------------------------
@@ -202,6 +245,32 @@ static PinnedSlot& pinned() {
 
 using namespace b200splat;
 
+// binning + render part of the forward, common to the single-view and the batched entry points
+static int forward_tail(BatchTab& tab, int debug, cudaStream_t st) {
+    const int T = tab.grid_x * tab.grid_y;
+    const int sel = sorted_sel_for(T);
+    b200splat_camera dbg{};
+    dbg.debug = debug;
+    if (tab.P > 0 && tab.capacity > 0) {
+        tab.sort_tiles_cap = sort_tiles_for(tab.capacity);
+        { ProfScope ps(2, st);
+        for (int v = 0; v < tab.V; ++v)
+            CU(cudaMemsetAsync(tab.v[v].hist, 0, sort_workspace_zero_bytes(tab.capacity, tab.end_bit), st));
+        CU(launch_duplicate(tab, st)); }
+        DEBUG_SYNC(dbg, st, "duplicateWithKeys");
+        { ProfScope ps(3, st);
+        CU(launch_sort_batch(tab, st)); }
+        DEBUG_SYNC(dbg, st, "sort");
+    }
+    { ProfScope ps(4, st);
+    CU(launch_tile_ranges_batch(tab, sel, st)); }
+    DEBUG_SYNC(dbg, st, "identifyTileRanges");
+    { ProfScope ps(5, st);
+    CU(launch_render_forward(tab, sel, st)); }
+    DEBUG_SYNC(dbg, st, "render");
+    return B200SPLAT_OK;
+}
+
 extern "C" {
 
 int b200splat_abi_version(void) { return B200SPLAT_ABI_VERSION; }
@@ -211,6 +280,7 @@ uint64_t b200splat_launch_count(void) { return g_launches.load(std::memory_order
 size_t b200splat_geom_bytes(int32_t P) { return geom_layout(P, nullptr, nullptr); }
 size_t b200splat_image_bytes(int32_t H, int32_t W) { return image_layout(H, W, nullptr, nullptr); }
 size_t b200splat_binning_bytes(int64_t R) { return binning_layout(R, nullptr, nullptr); }
+int64_t b200splat_binning_capacity(size_t bytes) { return capacity_for_bytes(bytes); }
 size_t b200splat_backward_scratch_bytes(int32_t P) {
     return align_up((size_t)(P > 0 ? P : 1) * GRAD2D_FLOATS * sizeof(float), 256);
 }
@@ -231,37 +301,40 @@ int b200splat_forward(const b200splat_forward_args* a) {
         return fail(B200SPLAT_ERR_INVALID, "provide exactly one of (scales, rotations) / cov3D_precomp");
     if (has_sh && a->M < 1) return fail(B200SPLAT_ERR_INVALID, "shs given but M < 1");
     if (!a->out_color || !a->out_depth || !a->out_alpha) return fail(B200SPLAT_ERR_INVALID, "null output image");
-    CameraParams cam;
-    int rc = make_camera(a->cam, a->M, has_sh, &cam);
+    BatchTab tab;
+    int rc = init_table(a->cam, P, a->M, has_sh, &tab);
     if (rc) return rc;
-    const int T = cam.grid_x * cam.grid_y;
-    ImageViews im;
-    if (!a->image_buffer || a->image_bytes < image_layout(cam.H, cam.W, nullptr, nullptr))
+    tab.V = 1;
+    ViewTab& vt = tab.v[0];
+    rc = fill_camera(a->cam, tab, &vt);
+    if (rc) return rc;
+    if (!a->image_buffer || a->image_bytes < image_layout(tab.H, tab.W, nullptr, nullptr))
         return fail(B200SPLAT_ERR_NOMEM, "image_buffer too small");
-    image_layout(cam.H, cam.W, a->image_buffer, &im);
+    fill_image(tab.H, tab.W, a->image_buffer, &vt, &tab.tile_order);
+    vt.out_color = a->out_color, vt.out_depth = a->out_depth, vt.out_alpha = a->out_alpha;
+    vt.radii = a->radii;
     if (a->num_rendered_out) *a->num_rendered_out = 0;
     if (a->binning_out) *a->binning_out = a->binning_buffer;
+    CU(cudaMemsetAsync(vt.status, 0, STATUS_WORDS * sizeof(uint32_t), st));
 
     int64_t R = 0;
-    GeomViews g{};
-    BinningViews bn{};
-    const uint32_t* point_list = nullptr;
     if (P > 0) {
         if (!a->means3D || !a->opacities || !a->radii) return fail(B200SPLAT_ERR_INVALID, "null per-Gaussian input");
         if (!a->geom_buffer || a->geom_bytes < geom_layout(P, nullptr, nullptr))
             return fail(B200SPLAT_ERR_NOMEM, "geom_buffer too small");
-        geom_layout(P, a->geom_buffer, &g);
+        fill_geom(P, a->geom_buffer, &vt);
         { ProfScope ps(0, st);
-        CU(launch_preprocess(P, cam, a->means3D, a->scales, a->rotations, a->opacities, a->shs, a->colors_precomp,
-                             a->cov3D_precomp, a->radii, g, st)); }
+        CU(launch_preprocess(tab, a->means3D, a->scales, a->rotations, a->opacities, a->shs, a->colors_precomp,
+                             a->cov3D_precomp, st)); }
         DEBUG_SYNC(a->cam, st, "preprocess");
         { ProfScope ps(1, st);
-        CU(launch_inclusive_scan(P, g.tiles_touched, g.point_offsets, g.scan_ws, st)); }
+        CU(launch_scan_batch(tab, st)); }
         DEBUG_SYNC(a->cam, st, "scan");
-        // the one host<->device round trip of the forward: num_rendered sizes the binning buffer
+        // the one host<->device round trip of the single-view forward: num_rendered sizes the binning buffer
+        // (the batched entry point works on a caller-chosen capacity instead and never waits)
         PinnedSlot& slot = pinned();
         if (!slot.host_u32) return fail(B200SPLAT_ERR_CUDA, "cudaHostAlloc failed");
-        CU(cudaMemcpyAsync(slot.host_u32, g.point_offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(slot.host_u32, vt.point_offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         R = (int64_t)*slot.host_u32;
         if (R >= (1ll << 30)) return fail(B200SPLAT_ERR_INVALID, "num_rendered %lld exceeds 2^30", (long long)R);
@@ -276,36 +349,95 @@ int b200splat_forward(const b200splat_forward_args* a) {
             if (!bbuf) return fail(B200SPLAT_ERR_NOMEM, "binning allocator returned NULL for %zu bytes", need);
         }
         if (a->binning_out) *a->binning_out = bbuf;
-        binning_layout(R, bbuf, &bn);
-        const int end_bit = 32 + higher_msb((uint32_t)T);
-        { ProfScope ps(2, st);
-        CU(sort_prepare(R, end_bit, bn.sort_ws, st));
-        CU(launch_duplicate(P, cam, a->radii, g, bn.keys[0], bn.vals[0], sort_histogram_ptr(bn.sort_ws), end_bit, st)); }
-        DEBUG_SYNC(a->cam, st, "duplicateWithKeys");
-        int sel = 0;
-        { ProfScope ps(3, st);
-        CU(launch_sort_pairs(R, end_bit, bn.keys, bn.vals, bn.sort_ws, &sel, st, /*hist_ready=*/true)); }
-        DEBUG_SYNC(a->cam, st, "sort");
-        if (sel != sorted_sel_for(T)) return fail(B200SPLAT_ERR_CUDA, "internal: sort buffer parity mismatch");
-        { ProfScope ps(4, st);
-        CU(launch_tile_ranges(R, T, bn.keys[sel], im.ranges, st));
-        CU(launch_tile_order(T, im.ranges, im.tile_order, st)); }
-        DEBUG_SYNC(a->cam, st, "identifyTileRanges");
-        point_list = bn.vals[sel];
-    } else {
-        CU(cudaMemsetAsync(im.ranges, 0, (size_t)T * 8, st));
-        CU(launch_tile_order(T, im.ranges, im.tile_order, st));
+        fill_binning(R, bbuf, &vt);
+        tab.capacity = (uint32_t)R;
     }
-    { ProfScope ps(5, st);
-    CU(launch_render_forward(cam, im.ranges, im.tile_order, point_list, g.rec, im.n_contrib, im.n_visited, im.final_T, a->out_color,
-                             a->out_depth, a->out_alpha, st)); }
-    DEBUG_SYNC(a->cam, st, "render");
+    return forward_tail(tab, a->cam.debug, st);
+}
+
+int b200splat_forward_batched(const b200splat_batch_forward_args* a) {
+    if (!a) return fail(B200SPLAT_ERR_INVALID, "null args");
+    const int P = a->P, V = a->V;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(a->stream);
+    if (V < 1 || V > MAX_VIEWS) return fail(B200SPLAT_ERR_INVALID, "V must be in [1, %d]", MAX_VIEWS);
+    if (P <= 0) return fail(B200SPLAT_ERR_INVALID, "P must be positive");
+    if (!a->cams || !a->out_color || !a->out_depth || !a->out_alpha || !a->radii || !a->geom_buffer ||
+        !a->image_buffer || !a->binning_buffer)
+        return fail(B200SPLAT_ERR_INVALID, "null per-view array");
+    const bool has_sh = a->shs != nullptr;
+    if (has_sh == (a->colors_precomp != nullptr))
+        return fail(B200SPLAT_ERR_INVALID, "provide exactly one of shs / colors_precomp");
+    if (!a->scales || !a->rotations || !a->means3D || !a->opacities)
+        return fail(B200SPLAT_ERR_INVALID, "means3D, opacities, scales and rotations are required");
+    if (has_sh && a->M < 1) return fail(B200SPLAT_ERR_INVALID, "shs given but M < 1");
+    BatchTab tab;
+    int rc = init_table(a->cams[0], P, a->M, has_sh, &tab);
+    if (rc) return rc;
+    tab.V = V;
+    const int64_t cap = capacity_for_bytes(a->binning_bytes);
+    if (cap < 1) return fail(B200SPLAT_ERR_NOMEM, "binning_bytes too small");
+    tab.capacity = (uint32_t)cap;
+    for (int v = 0; v < V; ++v) {
+        ViewTab& vt = tab.v[v];
+        rc = fill_camera(a->cams[v], tab, &vt);
+        if (rc) return rc;
+        if (!a->geom_buffer[v] || !a->image_buffer[v] || !a->binning_buffer[v] || !a->radii[v] || !a->out_color[v] ||
+            !a->out_depth[v] || !a->out_alpha[v])
+            return fail(B200SPLAT_ERR_INVALID, "null buffer for view %d", v);
+        fill_geom(P, a->geom_buffer[v], &vt);
+        fill_image(tab.H, tab.W, a->image_buffer[v], &vt, v == 0 ? &tab.tile_order : nullptr);
+        fill_binning(cap, a->binning_buffer[v], &vt);
+        vt.out_color = a->out_color[v], vt.out_depth = a->out_depth[v], vt.out_alpha = a->out_alpha[v];
+        vt.radii = a->radii[v];
+        CU(cudaMemsetAsync(vt.status, 0, STATUS_WORDS * sizeof(uint32_t), st));
+    }
+    { ProfScope ps(0, st);
+    CU(launch_preprocess(tab, a->means3D, a->scales, a->rotations, a->opacities, a->shs, a->colors_precomp, nullptr,
+                         st)); }
+    DEBUG_SYNC(a->cams[0], st, "preprocess");
+    { ProfScope ps(1, st);
+    CU(launch_scan_batch(tab, st)); }
+    DEBUG_SYNC(a->cams[0], st, "scan");
+    rc = forward_tail(tab, a->cams[0].debug, st);
+    if (rc) return rc;
+    if (a->sync) {
+        static thread_local uint32_t* host = nullptr;
+        if (!host && cudaHostAlloc(reinterpret_cast<void**>(&host), 2 * MAX_VIEWS * sizeof(uint32_t),
+                                   cudaHostAllocDefault) != cudaSuccess)
+            return fail(B200SPLAT_ERR_CUDA, "cudaHostAlloc failed");
+        for (int v = 0; v < V; ++v) {
+            CU(cudaMemcpyAsync(host + 2 * v, tab.v[v].point_offsets + (P - 1), 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(host + 2 * v + 1, tab.v[v].status + STATUS_OVERFLOW, 4, cudaMemcpyDeviceToHost, st));
+        }
+        CU(cudaStreamSynchronize(st));
+        for (int v = 0; v < V; ++v) {
+            if (a->num_rendered_out) a->num_rendered_out[v] = (int64_t)host[2 * v];
+            if (a->overflow_out) a->overflow_out[v] = (int32_t)(host[2 * v + 1] != 0 || host[2 * v] > tab.capacity);
+        }
+    }
     return B200SPLAT_OK;
 }
 
-static int sorted_sel(int H, int W) {
-    const int gx = (W + BLOCK_X - 1) / BLOCK_X, gy = (H + BLOCK_Y - 1) / BLOCK_Y;
-    return sorted_sel_for(gx * gy);
+static int backward_run(BatchTab& tab, const float* means3D, const float* scales, const float* rotations,
+                        const float* shs, const float* cov3D_precomp, float* dL_dmeans3D, float* dL_dshs,
+                        float* dL_dcolors, float* dL_dopacity, float* dL_dscales, float* dL_drotations,
+                        float* dL_dcov3D, float* sa, float* sd, float* sm, int accumulate, int debug, bool any_pairs,
+                        cudaStream_t st) {
+    b200splat_camera dbg{};
+    dbg.debug = debug;
+    const int sel = sorted_sel_for(tab.grid_x * tab.grid_y);
+    {
+        ProfScope ps(6, st);
+        for (int v = 0; v < tab.V; ++v)
+            CU(cudaMemsetAsync(tab.v[v].grad2d, 0, (size_t)tab.P * GRAD2D_FLOATS * sizeof(float), st));
+        if (any_pairs) CU(launch_render_backward(tab, sel, st));
+    }
+    DEBUG_SYNC(dbg, st, "render backward");
+    { ProfScope ps(7, st);
+    CU(launch_preprocess_backward(tab, means3D, scales, rotations, shs, cov3D_precomp, dL_dmeans3D, dL_dshs, dL_dcolors,
+                                  dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D, sa, sd, sm, accumulate, st)); }
+    DEBUG_SYNC(dbg, st, "preprocess backward");
+    return B200SPLAT_OK;
 }
 
 int b200splat_backward(const b200splat_backward_args* a) {
@@ -314,39 +446,73 @@ int b200splat_backward(const b200splat_backward_args* a) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(a->stream);
     if (P <= 0) return B200SPLAT_OK;
     const bool has_sh = a->shs != nullptr;
-    CameraParams cam;
-    int rc = make_camera(a->cam, a->M, has_sh, &cam);
+    BatchTab tab;
+    int rc = init_table(a->cam, P, a->M, has_sh, &tab);
+    if (rc) return rc;
+    tab.V = 1;
+    ViewTab& vt = tab.v[0];
+    rc = fill_camera(a->cam, tab, &vt);
     if (rc) return rc;
     if (!a->dL_dmeans3D || !a->dL_dmeans2D || !a->dL_dopacity)
         return fail(B200SPLAT_ERR_INVALID, "dL_dmeans3D / dL_dmeans2D / dL_dopacity must be given");
     if (has_sh && !a->dL_dshs) return fail(B200SPLAT_ERR_INVALID, "shs given but dL_dshs is NULL");
     if (!a->scratch || a->scratch_bytes < b200splat_backward_scratch_bytes(P))
         return fail(B200SPLAT_ERR_NOMEM, "scratch too small");
-    GeomViews g;
-    ImageViews im;
-    geom_layout(P, const_cast<void*>(a->geom_buffer), &g);
-    image_layout(cam.H, cam.W, const_cast<void*>(a->image_buffer), &im);
-    float* grad2d = reinterpret_cast<float*>(a->scratch);
-    ProfScope* rb = new ProfScope(6, st);
-    cudaError_t me = cudaMemsetAsync(grad2d, 0, (size_t)P * GRAD2D_FLOATS * sizeof(float), st);
-    if (me != cudaSuccess) { delete rb; CU(me); }
+    if (!a->geom_buffer || !a->image_buffer || !a->radii) return fail(B200SPLAT_ERR_INVALID, "null saved buffer");
+    fill_geom(P, const_cast<void*>(a->geom_buffer), &vt);
+    fill_image(tab.H, tab.W, const_cast<void*>(a->image_buffer), &vt, &tab.tile_order);
+    vt.radii = const_cast<int32_t*>(a->radii);
     if (a->num_rendered > 0) {
-        BinningViews bn;
-        binning_layout(a->num_rendered, const_cast<void*>(a->binning_buffer), &bn);
-        const uint32_t* point_list = bn.vals[sorted_sel(cam.H, cam.W)];
-        cudaError_t re = launch_render_backward(cam, im.ranges, im.tile_order, point_list, g.rec, im.n_contrib, im.final_T,
-                                                a->dL_dout_color, a->dL_dout_depth, a->dL_dout_alpha, grad2d, st);
-        if (re != cudaSuccess) { delete rb; CU(re); }
+        if (!a->binning_buffer) return fail(B200SPLAT_ERR_INVALID, "null binning buffer");
+        fill_binning(a->num_rendered, const_cast<void*>(a->binning_buffer), &vt);
+        tab.capacity = (uint32_t)a->num_rendered;
     }
-    delete rb;
-    DEBUG_SYNC(a->cam, st, "render backward");
-    { ProfScope ps(7, st);
-    CU(launch_preprocess_backward(P, cam, a->means3D, a->scales, a->rotations, a->shs, a->cov3D_precomp, a->radii, g,
-                                  grad2d, a->dL_dmeans3D, a->dL_dmeans2D, a->dL_dshs, a->dL_dcolors, a->dL_dopacity,
-                                  a->dL_dscales, a->dL_drotations, a->dL_dcov3D, a->stat_grad_accum, a->stat_denom,
-                                  a->stat_max_radii, a->accumulate, st)); }
-    DEBUG_SYNC(a->cam, st, "preprocess backward");
-    return B200SPLAT_OK;
+    vt.dL_dcolor = a->dL_dout_color, vt.dL_ddepth = a->dL_dout_depth, vt.dL_dalpha = a->dL_dout_alpha;
+    vt.grad2d = reinterpret_cast<float*>(a->scratch);
+    vt.dL_dmeans2D = a->dL_dmeans2D;
+    return backward_run(tab, a->means3D, a->scales, a->rotations, a->shs, a->cov3D_precomp, a->dL_dmeans3D, a->dL_dshs,
+                        a->dL_dcolors, a->dL_dopacity, a->dL_dscales, a->dL_drotations, a->dL_dcov3D, a->stat_grad_accum,
+                        a->stat_denom, a->stat_max_radii, a->accumulate, a->cam.debug, a->num_rendered > 0, st);
+}
+
+int b200splat_backward_batched(const b200splat_batch_backward_args* a) {
+    if (!a) return fail(B200SPLAT_ERR_INVALID, "null args");
+    const int P = a->P, V = a->V;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(a->stream);
+    if (V < 1 || V > MAX_VIEWS) return fail(B200SPLAT_ERR_INVALID, "V must be in [1, %d]", MAX_VIEWS);
+    if (P <= 0) return fail(B200SPLAT_ERR_INVALID, "P must be positive");
+    if (!a->cams || !a->radii || !a->geom_buffer || !a->image_buffer || !a->binning_buffer || !a->scratch)
+        return fail(B200SPLAT_ERR_INVALID, "null per-view array");
+    const bool has_sh = a->shs != nullptr;
+    if (!a->dL_dmeans3D || !a->dL_dopacity || !a->dL_dscales || !a->dL_drotations)
+        return fail(B200SPLAT_ERR_INVALID, "dL_dmeans3D / dL_dopacity / dL_dscales / dL_drotations must be given");
+    if (has_sh && !a->dL_dshs) return fail(B200SPLAT_ERR_INVALID, "shs given but dL_dshs is NULL");
+    BatchTab tab;
+    int rc = init_table(a->cams[0], P, a->M, has_sh, &tab);
+    if (rc) return rc;
+    tab.V = V;
+    const int64_t cap = capacity_for_bytes(a->binning_bytes);
+    if (cap < 1) return fail(B200SPLAT_ERR_NOMEM, "binning_bytes too small");
+    tab.capacity = (uint32_t)cap;
+    for (int v = 0; v < V; ++v) {
+        ViewTab& vt = tab.v[v];
+        rc = fill_camera(a->cams[v], tab, &vt);
+        if (rc) return rc;
+        if (!a->geom_buffer[v] || !a->image_buffer[v] || !a->binning_buffer[v] || !a->radii[v] || !a->scratch[v])
+            return fail(B200SPLAT_ERR_INVALID, "null buffer for view %d", v);
+        fill_geom(P, const_cast<void*>(a->geom_buffer[v]), &vt);
+        fill_image(tab.H, tab.W, const_cast<void*>(a->image_buffer[v]), &vt, v == 0 ? &tab.tile_order : nullptr);
+        fill_binning(cap, const_cast<void*>(a->binning_buffer[v]), &vt);
+        vt.radii = const_cast<int32_t*>(a->radii[v]);
+        vt.dL_dcolor = a->dL_dout_color ? a->dL_dout_color[v] : nullptr;
+        vt.dL_ddepth = a->dL_dout_depth ? a->dL_dout_depth[v] : nullptr;
+        vt.dL_dalpha = a->dL_dout_alpha ? a->dL_dout_alpha[v] : nullptr;
+        vt.grad2d = reinterpret_cast<float*>(a->scratch[v]);
+        vt.dL_dmeans2D = a->dL_dmeans2D ? a->dL_dmeans2D[v] : nullptr;
+    }
+    return backward_run(tab, a->means3D, a->scales, a->rotations, a->shs, nullptr, a->dL_dmeans3D, a->dL_dshs,
+                        a->dL_dcolors, a->dL_dopacity, a->dL_dscales, a->dL_drotations, nullptr, a->stat_grad_accum,
+                        a->stat_denom, a->stat_max_radii, a->accumulate, a->cams[0].debug, true, st);
 }
 
 int b200splat_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
@@ -401,12 +567,12 @@ int b200splat_forward_views_get(int32_t P, int32_t H, int32_t W, int64_t num_ren
         out->point_offsets = g.point_offsets;
         out->depths = g.depths;
         out->gauss2d = g.rec;
-        out->cov3D = g.cov3D;
     }
-    if (binning_buffer && num_rendered > 0) {
+    if (binning_buffer && num_rendered > 0) {   // num_rendered = the capacity the buffer was laid out for
         BinningViews b;
         binning_layout(num_rendered, const_cast<void*>(binning_buffer), &b);
-        const int sel = sorted_sel(H, W);
+        const int gx = (W + BLOCK_X - 1) / BLOCK_X, gy = (H + BLOCK_Y - 1) / BLOCK_Y;
+        const int sel = sorted_sel_for(gx * gy);
         out->keys_sorted = b.keys[sel];
         out->point_list = b.vals[sel];
     }
@@ -416,6 +582,7 @@ int b200splat_forward_views_get(int32_t P, int32_t H, int32_t W, int64_t num_ren
         out->ranges = im.ranges;
         out->n_contrib = im.n_contrib;
         out->n_visited = im.n_visited;
+        out->status = im.status;
     }
     return B200SPLAT_OK;
 }

@@ -1,5 +1,12 @@
 // Shared definitions of the sm_100a splatting kernels (internal; the public surface is
 // include/b200splat.h).
+//
+// Every kernel of the pipeline takes ONE BatchTab by value (__grid_constant__): the per-view device
+// pointers of up to MAX_VIEWS views that share the Gaussian parameters and the image size.  A phase of
+// the pipeline (preprocess, scan, key duplication, each sort pass, tile ranges, render, ...) is ONE
+// launch for the whole view batch (blockIdx.y or the tile-order entry selects the view); the single-view
+// entry points are the V = 1 case of the same kernels.  num_rendered never has to visit the host: kernels
+// read it from point_offsets[P-1] and are launched over the binning *capacity*.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -11,6 +18,7 @@ constexpr int BLOCK_X = 16;
 constexpr int BLOCK_Y = 16;
 constexpr int BLOCK_SIZE = BLOCK_X * BLOCK_Y;
 constexpr int NUM_SMS = 148;
+constexpr int MAX_VIEWS = 8;
 
 constexpr float NEAR_CULL = 0.2f;
 constexpr float FOV_CLAMP = 1.3f;
@@ -29,26 +37,69 @@ constexpr int REC_FLOATS = 12;
 //   g0 = (dx, dy, dconic_a, dconic_b)  g1 = (dconic_c, dopacity, dr, dg)  g2 = (db, ddepth, 0, 0)
 constexpr int GRAD2D_FLOATS = 12;
 
-struct CameraParams {
-    int H, W;
-    int grid_x, grid_y;
-    float tanfovx, tanfovy;
-    float focal_x, focal_y;
-    float limx, limy;
-    float scale_modifier;
-    int sh_degree;   // effective (clamped) degree
-    int M;           // coefficients per channel in shs
-    const float* bg;
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int MAX_PASSES = 8;
+
+// status words of a view (in its image buffer)
+constexpr int STATUS_OVERFLOW = 0;   // != 0: num_rendered exceeded the binning capacity (results invalid)
+constexpr int STATUS_WORDS = 4;
+
+struct ViewTab {
+    // camera (device pointers to the reference's transposed 4x4s) + host-derived fp32 scalars
     const float* view;
     const float* proj;
     const float* campos;
+    const float* bg;
+    float tanfovx, tanfovy, focal_x, focal_y, limx, limy;
+    // per-Gaussian state of this view (geometry buffer)
+    int32_t* radii;
+    float* rec;
+    float* depths;
+    uint8_t* clamped;
+    uint32_t* tiles_touched;
+    uint32_t* point_offsets;
+    uint32_t* scan_ticket;
+    uint64_t* scan_desc;
+    // binning buffer
+    uint64_t* keys[2];
+    uint32_t* vals[2];
+    uint32_t* hist;      // [MAX_PASSES][256]
+    uint32_t* tickets;   // [MAX_PASSES]
+    uint32_t* desc;      // [passes][tiles_cap][256]
+    // image buffer
+    uint32_t* ranges;
+    uint32_t* n_contrib;
+    uint32_t* n_visited;
+    float* final_T;
+    uint32_t* status;
+    float* out_color;
+    float* out_depth;
+    float* out_alpha;
+    // backward
+    const float* dL_dcolor;
+    const float* dL_ddepth;
+    const float* dL_dalpha;
+    float* grad2d;
+    float* dL_dmeans2D;   // optional per-view output (P,3)
 };
 
-// ---- geometry buffer layout (per Gaussian, SoA) ---------------------------------------------
+struct BatchTab {
+    int V;
+    int P, M, sh_degree;       // sh_degree: effective (clamped) degree; -1 when colours are precomputed
+    int W, H, grid_x, grid_y;
+    float scale_modifier;
+    uint32_t capacity;         // pairs each view's key/value arrays can hold
+    int end_bit;               // sorted key bits [0, end_bit)
+    int sort_tiles_cap;        // ceil(capacity / SORT_TILE)
+    uint32_t* tile_order;      // [V * T] entries (view * T + tile), longest list first
+    ViewTab v[MAX_VIEWS];
+};
+
+// ---- buffer layouts ---------------------------------------------------------------------------
 struct GeomViews {
     float* rec;              // P * 12
     float* depths;           // P
-    float* cov3D;            // P * 6
     uint8_t* clamped;        // P   (bit c set: channel c clamped at 0)
     uint32_t* tiles_touched; // P
     uint32_t* point_offsets; // P
@@ -58,7 +109,6 @@ struct GeomViews {
 struct BinningViews {
     uint64_t* keys[2];
     uint32_t* vals[2];
-    int32_t* final_sel;      // device int: which of the two holds the sorted result (host mirrors)
     void* sort_ws;
     size_t sort_ws_bytes;
 };
@@ -67,49 +117,42 @@ struct ImageViews {
     uint32_t* n_contrib;     // H * W
     float* final_T;          // H * W  (transmittance after the last blended entry; 1 - alpha loses bits)
     uint32_t* n_visited;     // H * W  (list entries traversed by the pixel in forward)
-    uint32_t* tile_order;    // T      (tiles by decreasing list length: CTA i renders tile_order[i])
+    uint32_t* tile_order;    // MAX_VIEWS * T (a batch uses view 0's copy)
+    uint32_t* status;        // STATUS_WORDS
 };
 
 size_t geom_layout(int P, void* base, GeomViews* v);
-size_t binning_layout(int64_t R, void* base, BinningViews* v);
+size_t binning_layout(int64_t capacity, void* base, BinningViews* v);
 size_t image_layout(int H, int W, void* base, ImageViews* v);
 
 // ---- launchers (each returns cudaError_t from the launch) -----------------------------------
-cudaError_t launch_preprocess(int P, const CameraParams& cam, const float* means3D, const float* scales,
-                              const float* rotations, const float* opacities, const float* shs,
-                              const float* colors_precomp, const float* cov3D_precomp, int32_t* radii,
-                              const GeomViews& g, cudaStream_t st);
-cudaError_t launch_duplicate(int P, const CameraParams& cam, const int32_t* radii, const GeomViews& g,
-                             uint64_t* keys, uint32_t* vals, uint32_t* hist, int end_bit, cudaStream_t st);
+cudaError_t launch_preprocess(const BatchTab& tab, const float* means3D, const float* scales, const float* rotations,
+                              const float* opacities, const float* shs, const float* colors_precomp,
+                              const float* cov3D_precomp, cudaStream_t st);
+cudaError_t launch_duplicate(const BatchTab& tab, cudaStream_t st);
 cudaError_t launch_mark_visible(int P, const float* means3D, const float* view, const float* proj,
                                 uint8_t* present, cudaStream_t st);
 
 size_t scan_workspace_bytes(int64_t n);
+cudaError_t launch_scan_batch(const BatchTab& tab, cudaStream_t st);   // tiles_touched -> point_offsets, all views
 cudaError_t launch_inclusive_scan(int64_t n, const uint32_t* in, uint32_t* out, void* ws, cudaStream_t st);
 size_t sort_workspace_bytes(int64_t n);
-// returns index (0/1) of the buffer pair holding the result through *sel
-cudaError_t launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_t* vals[2], void* ws,
-                              int* sel, cudaStream_t st, bool hist_ready = false);
-// zero the sort workspace / where a fused producer (duplicateWithKeys) accumulates the digit histograms
-cudaError_t sort_prepare(int64_t n, int end_bit, void* ws, cudaStream_t st);
-uint32_t* sort_histogram_ptr(void* ws);
-cudaError_t launch_tile_ranges(int64_t R, int T, const uint64_t* keys_sorted, uint32_t* ranges, cudaStream_t st);
-cudaError_t launch_tile_order(int T, const uint32_t* ranges, uint32_t* order, cudaStream_t st);
+void sort_workspace_views(void* ws, uint32_t** hist, uint32_t** tickets, uint32_t** desc);
+size_t sort_workspace_zero_bytes(int64_t capacity, int end_bit);
+int sort_tiles_for(int64_t n);
+// stand-alone sort (stage-level entry point / KNN): histogram kernel + passes; *sel = buffer holding the result
+cudaError_t launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_t* vals[2], void* ws, int* sel,
+                              cudaStream_t st);
+// pipeline sort: histograms already accumulated by duplicateWithKeys, n read from the device per view
+cudaError_t launch_sort_batch(const BatchTab& tab, cudaStream_t st);
+cudaError_t launch_tile_ranges_batch(const BatchTab& tab, int sel, cudaStream_t st);   // + tile order
 
-cudaError_t launch_render_forward(const CameraParams& cam, const uint32_t* ranges, const uint32_t* tile_order,
-                                  const uint32_t* point_list,
-                                  const float* rec, uint32_t* n_contrib, uint32_t* n_visited, float* final_T,
-                                  float* out_color, float* out_depth, float* out_alpha, cudaStream_t st);
-cudaError_t launch_render_backward(const CameraParams& cam, const uint32_t* ranges, const uint32_t* tile_order,
-                                   const uint32_t* point_list,
-                                   const float* rec, const uint32_t* n_contrib, const float* final_T,
-                                   const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
-                                   float* grad2d, cudaStream_t st);
-cudaError_t launch_preprocess_backward(int P, const CameraParams& cam, const float* means3D, const float* scales,
+cudaError_t launch_render_forward(const BatchTab& tab, int sel, cudaStream_t st);
+cudaError_t launch_render_backward(const BatchTab& tab, int sel, cudaStream_t st);
+cudaError_t launch_preprocess_backward(const BatchTab& tab, const float* means3D, const float* scales,
                                        const float* rotations, const float* shs, const float* cov3D_precomp,
-                                       const int32_t* radii, const GeomViews& g, const float* grad2d,
-                                       float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dshs, float* dL_dcolors,
-                                       float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dcov3D,
+                                       float* dL_dmeans3D, float* dL_dshs, float* dL_dcolors, float* dL_dopacity,
+                                       float* dL_dscales, float* dL_drotations, float* dL_dcov3D,
                                        float* stat_grad_accum, float* stat_denom, float* stat_max_radii,
                                        int accumulate, cudaStream_t st);
 

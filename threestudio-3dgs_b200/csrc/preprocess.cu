@@ -9,6 +9,10 @@
 // one IEEE fp32 operation per source operator, in the association order written here, which is
 // the order oracle/torch_oracle.py spells out.  Division and sqrt are nvcc's IEEE defaults.
 // The kernel is HBM-bound (104-284 B/Gaussian), so the lost FMA contraction is free.
+//
+// View batching: the Gaussian parameters (44 + 12 M bytes) are read ONCE and projected into every
+// view of the batch (the reference renders the views of a step one after the other,
+// renderer/gaussian_batch_renderer.py:21-54, re-reading them each time).
 #include "common.cuh"
 
 namespace b200splat {
@@ -61,211 +65,225 @@ __device__ __forceinline__ float sh_channel(const float* s, float x, float y, fl
     return res;
 }
 
+// DEG = -1: colours precomputed; 0..3: SH degree
 template <int DEG>
-__device__ __forceinline__ void sh_to_rgb(const float* __restrict__ sh, float dx, float dy, float dz, float* rgb,
-                                          uint8_t* clamped_bits) {
-    // sh: (M,3) interleaved for this Gaussian; load the (DEG+1)^2 coefficients of each channel
-    constexpr int K = (DEG + 1) * (DEG + 1);
-    float c[3][K];
-    if (K == 16) {
-        const float4* v = reinterpret_cast<const float4*>(sh);
-#pragma unroll
-        for (int i = 0; i < 12; ++i) {
-            float4 q = __ldg(v + i);
-            float e[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                int f = i * 4 + j;
-                c[f % 3][f / 3] = e[j];
-            }
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) c[ch][k] = __ldg(sh + k * 3 + ch);
-        }
-    }
-    uint8_t bits = 0;
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-        float r = sh_channel<DEG>(c[ch], dx, dy, dz) + 0.5f;
-        if (r < 0.0f) bits |= (uint8_t)(1u << ch);
-        rgb[ch] = fmaxf(r, 0.0f);
-    }
-    *clamped_bits = bits;
-}
-
 __global__ void __launch_bounds__(256)
-preprocess_kernel(int P, CameraParams cam, const float* __restrict__ means3D, const float* __restrict__ scales,
-                  const float* __restrict__ rotations, const float* __restrict__ opacities,
-                  const float* __restrict__ shs, const float* __restrict__ colors_precomp,
-                  const float* __restrict__ cov3D_precomp, int32_t* __restrict__ radii, float* __restrict__ rec,
-                  float* __restrict__ depths, float* __restrict__ cov3D_out, uint8_t* __restrict__ clamped,
-                  uint32_t* __restrict__ tiles_touched) {
-    __shared__ float sV[16], sP[16], sC[3];
-    if (threadIdx.x < 16) {
-        sV[threadIdx.x] = cam.view[threadIdx.x];
-        sP[threadIdx.x] = cam.proj[threadIdx.x];
+preprocess_kernel(const __grid_constant__ BatchTab tab, const float* __restrict__ means3D,
+                  const float* __restrict__ scales, const float* __restrict__ rotations,
+                  const float* __restrict__ opacities, const float* __restrict__ shs,
+                  const float* __restrict__ colors_precomp, const float* __restrict__ cov3D_precomp) {
+    __shared__ float sV[MAX_VIEWS][16], sP[MAX_VIEWS][16], sC[MAX_VIEWS][4];
+    const int V = tab.V;
+    for (int i = threadIdx.x; i < V * 16; i += blockDim.x) {
+        sV[i >> 4][i & 15] = tab.v[i >> 4].view[i & 15];
+        sP[i >> 4][i & 15] = tab.v[i >> 4].proj[i & 15];
     }
-    if (threadIdx.x < 3) sC[threadIdx.x] = cam.campos[threadIdx.x];
+    for (int i = threadIdx.x; i < V * 3; i += blockDim.x) sC[i / 3][i % 3] = tab.v[i / 3].campos[i % 3];
     __syncthreads();
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= tab.P) return;
+    constexpr int K = DEG < 0 ? 1 : (DEG + 1) * (DEG + 1);
 
-    // start the long-latency, visibility-dependent loads now: the SH block (2 lines) goes to L2 while the
-    // projection runs, instead of a third serialized DRAM round trip after the cull tests
-    if (shs != nullptr) {
-        const char* shp = reinterpret_cast<const char*>(shs + (size_t)idx * cam.M * 3);
+    const float x = __ldg(means3D + 3 * idx), y = __ldg(means3D + 3 * idx + 1), z = __ldg(means3D + 3 * idx + 2);
+    // the SH block (up to 2 lines) goes to L2 while the cheap near-plane tests run
+    if (DEG >= 0) {
+        const char* shp = reinterpret_cast<const char*>(shs + (size_t)idx * tab.M * 3);
         prefetch_l2(shp);
-        if (cam.M * 12 > 128) prefetch_l2(shp + 128);
+        if (K * 12 > 128) prefetch_l2(shp + 128);
     }
-    float4 q_early = make_float4(0.f, 0.f, 0.f, 0.f);
-    float s_early[3] = {0.f, 0.f, 0.f};
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    float s3[3] = {0.f, 0.f, 0.f};
     if (cov3D_precomp == nullptr) {
-        q_early = __ldg(reinterpret_cast<const float4*>(rotations) + idx);
-        s_early[0] = __ldg(scales + 3 * idx), s_early[1] = __ldg(scales + 3 * idx + 1), s_early[2] = __ldg(scales + 3 * idx + 2);
+        q = __ldg(reinterpret_cast<const float4*>(rotations) + idx);
+        s3[0] = __ldg(scales + 3 * idx), s3[1] = __ldg(scales + 3 * idx + 1), s3[2] = __ldg(scales + 3 * idx + 2);
     }
     const float opac = __ldg(opacities + idx);
-    int my_radius = 0;
-    uint32_t my_tiles = 0;
-    const float x = __ldg(means3D + 3 * idx), y = __ldg(means3D + 3 * idx + 1), z = __ldg(means3D + 3 * idx + 2);
-    // view / projection (transformPoint4x3 / 4x4 on the transposed matrices)
-    const float tvx = sV[0] * x + sV[4] * y + sV[8] * z + sV[12];
-    const float tvy = sV[1] * x + sV[5] * y + sV[9] * z + sV[13];
-    const float tvz = sV[2] * x + sV[6] * y + sV[10] * z + sV[14];
-    if (tvz > NEAR_CULL) {
-        const float hx = sP[0] * x + sP[4] * y + sP[8] * z + sP[12];
-        const float hy = sP[1] * x + sP[5] * y + sP[9] * z + sP[13];
-        const float hw = sP[3] * x + sP[7] * y + sP[11] * z + sP[15];
-        const float pw = 1.0f / (hw + PW_EPS);
-        const float ndcx = hx * pw, ndcy = hy * pw;
-        // Sigma3
-        float c0, c1, c2, c3, c4, c5;
-        if (cov3D_precomp != nullptr) {
-            const float* c = cov3D_precomp + 6 * (size_t)idx;
-            c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2), c3 = __ldg(c + 3), c4 = __ldg(c + 4), c5 = __ldg(c + 5);
-        } else {
-            const float mod = cam.scale_modifier;
-            const float sx = mod * s_early[0], sy = mod * s_early[1], sz = mod * s_early[2];
-            const float4 q = q_early;
-            const float r = q.x, qx = q.y, qy = q.z, qz = q.w;
-            const float R00 = 1.0f - 2.0f * (qy * qy + qz * qz);
-            const float R01 = 2.0f * (qx * qy - r * qz);
-            const float R02 = 2.0f * (qx * qz + r * qy);
-            const float R10 = 2.0f * (qx * qy + r * qz);
-            const float R11 = 1.0f - 2.0f * (qx * qx + qz * qz);
-            const float R12 = 2.0f * (qy * qz - r * qx);
-            const float R20 = 2.0f * (qx * qz - r * qy);
-            const float R21 = 2.0f * (qy * qz + r * qx);
-            const float R22 = 1.0f - 2.0f * (qx * qx + qy * qy);
-            const float L00 = R00 * sx, L01 = R01 * sy, L02 = R02 * sz;
-            const float L10 = R10 * sx, L11 = R11 * sy, L12 = R12 * sz;
-            const float L20 = R20 * sx, L21 = R21 * sy, L22 = R22 * sz;
-            c0 = L00 * L00 + L01 * L01 + L02 * L02;
-            c1 = L00 * L10 + L01 * L11 + L02 * L12;
-            c2 = L00 * L20 + L01 * L21 + L02 * L22;
-            c3 = L10 * L10 + L11 * L11 + L12 * L12;
-            c4 = L10 * L20 + L11 * L21 + L12 * L22;
-            c5 = L20 * L20 + L21 * L21 + L22 * L22;
+
+    uint32_t front = 0;
+    for (int v = 0; v < V; ++v) {
+        const float tvz = sV[v][2] * x + sV[v][6] * y + sV[v][10] * z + sV[v][14];
+        if (tvz > NEAR_CULL) front |= 1u << v;
+    }
+    if (front == 0) {
+        for (int v = 0; v < V; ++v) {
+            tab.v[v].radii[idx] = 0;
+            tab.v[v].tiles_touched[idx] = 0;
         }
-        // EWA projection
-        const float txtz = tvx / tvz, tytz = tvy / tvz;
-        const float tx = fminf(cam.limx, fmaxf(-cam.limx, txtz)) * tvz;
-        const float ty = fminf(cam.limy, fmaxf(-cam.limy, tytz)) * tvz;
-        const float J00 = cam.focal_x / tvz;
-        const float J02 = -(cam.focal_x * tx) / (tvz * tvz);
-        const float J11 = cam.focal_y / tvz;
-        const float J12 = -(cam.focal_y * ty) / (tvz * tvz);
-        const float M00 = J00 * sV[0] + J02 * sV[2];
-        const float M01 = J00 * sV[4] + J02 * sV[6];
-        const float M02 = J00 * sV[8] + J02 * sV[10];
-        const float M10 = J11 * sV[1] + J12 * sV[2];
-        const float M11 = J11 * sV[5] + J12 * sV[6];
-        const float M12 = J11 * sV[9] + J12 * sV[10];
-        const float N00 = M00 * c0 + M01 * c1 + M02 * c2;
-        const float N01 = M00 * c1 + M01 * c3 + M02 * c4;
-        const float N02 = M00 * c2 + M01 * c4 + M02 * c5;
-        const float N10 = M10 * c0 + M11 * c1 + M12 * c2;
-        const float N11 = M10 * c1 + M11 * c3 + M12 * c4;
-        const float N12 = M10 * c2 + M11 * c4 + M12 * c5;
-        const float a = N00 * M00 + N01 * M01 + N02 * M02 + DILATION;
-        const float b = N00 * M10 + N01 * M11 + N02 * M12;
-        const float c = N10 * M10 + N11 * M11 + N12 * M12 + DILATION;
-        const float det = a * c - b * b;
-        if (det != 0.0f) {
-            const float det_inv = 1.0f / det;
-            const float mid = 0.5f * (a + c);
-            const float disc = sqrtf(fmaxf(mid * mid - det, LAMBDA_FLOOR));
-            const float lam = fmaxf(mid + disc, mid - disc);
-            const float radius_f = ceilf(3.0f * sqrtf(lam));
-            const float px = ndc2pix(ndcx, cam.W), py = ndc2pix(ndcy, cam.H);
-            int x0, y0, x1, y1;
-            get_rect(px, py, radius_f, cam.grid_x, cam.grid_y, x0, y0, x1, y1);
-            const int area = (x1 - x0) * (y1 - y0);
-            if (area > 0) {
-                float rgb[3];
-                uint8_t bits = 0;
-                if (colors_precomp != nullptr) {
-                    rgb[0] = __ldg(colors_precomp + 3 * idx);
-                    rgb[1] = __ldg(colors_precomp + 3 * idx + 1);
-                    rgb[2] = __ldg(colors_precomp + 3 * idx + 2);
-                } else {
-                    float dx = x - sC[0], dy = y - sC[1], dz = z - sC[2];
-                    const float n = sqrtf(dx * dx + dy * dy + dz * dz);
-                    dx = dx / n, dy = dy / n, dz = dz / n;
-                    const float* sh = shs + (size_t)idx * cam.M * 3;
-                    switch (cam.sh_degree) {
-                        case 0: sh_to_rgb<0>(sh, dx, dy, dz, rgb, &bits); break;
-                        case 1: sh_to_rgb<1>(sh, dx, dy, dz, rgb, &bits); break;
-                        case 2: sh_to_rgb<2>(sh, dx, dy, dz, rgb, &bits); break;
-                        default: sh_to_rgb<3>(sh, dx, dy, dz, rgb, &bits); break;
-                    }
+        return;
+    }
+    // Sigma3 (view independent)
+    float c0, c1, c2, c3, c4, c5;
+    if (cov3D_precomp != nullptr) {
+        const float* c = cov3D_precomp + 6 * (size_t)idx;
+        c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2), c3 = __ldg(c + 3), c4 = __ldg(c + 4), c5 = __ldg(c + 5);
+    } else {
+        const float mod = tab.scale_modifier;
+        const float sx = mod * s3[0], sy = mod * s3[1], sz = mod * s3[2];
+        const float r = q.x, qx = q.y, qy = q.z, qz = q.w;
+        const float R00 = 1.0f - 2.0f * (qy * qy + qz * qz);
+        const float R01 = 2.0f * (qx * qy - r * qz);
+        const float R02 = 2.0f * (qx * qz + r * qy);
+        const float R10 = 2.0f * (qx * qy + r * qz);
+        const float R11 = 1.0f - 2.0f * (qx * qx + qz * qz);
+        const float R12 = 2.0f * (qy * qz - r * qx);
+        const float R20 = 2.0f * (qx * qz - r * qy);
+        const float R21 = 2.0f * (qy * qz + r * qx);
+        const float R22 = 1.0f - 2.0f * (qx * qx + qy * qy);
+        const float L00 = R00 * sx, L01 = R01 * sy, L02 = R02 * sz;
+        const float L10 = R10 * sx, L11 = R11 * sy, L12 = R12 * sz;
+        const float L20 = R20 * sx, L21 = R21 * sy, L22 = R22 * sz;
+        c0 = L00 * L00 + L01 * L01 + L02 * L02;
+        c1 = L00 * L10 + L01 * L11 + L02 * L12;
+        c2 = L00 * L20 + L01 * L21 + L02 * L22;
+        c3 = L10 * L10 + L11 * L11 + L12 * L12;
+        c4 = L10 * L20 + L11 * L21 + L12 * L22;
+        c5 = L20 * L20 + L21 * L21 + L22 * L22;
+    }
+    // colour inputs (view independent): SH coefficients per channel, or the precomputed colour
+    float coef[3][K];
+    if (DEG < 0) {
+        coef[0][0] = __ldg(colors_precomp + 3 * idx);
+        coef[1][0] = __ldg(colors_precomp + 3 * idx + 1);
+        coef[2][0] = __ldg(colors_precomp + 3 * idx + 2);
+    } else {
+        const float* sh = shs + (size_t)idx * tab.M * 3;
+        if (K == 16) {
+            const float4* v4 = reinterpret_cast<const float4*>(sh);
+#pragma unroll
+            for (int i = 0; i < 12; ++i) {
+                const float4 t = __ldg(v4 + i);
+                const float e[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int f = i * 4 + j;
+                    coef[f % 3][f / 3] = e[j];
                 }
-                my_radius = (int)radius_f;
-                my_tiles = (uint32_t)area;
-                float4* o = reinterpret_cast<float4*>(rec) + 3 * (size_t)idx;
-                o[0] = make_float4(px, py, c * det_inv, -b * det_inv);
-                o[1] = make_float4(a * det_inv, opac, tvz, rgb[0]);
-                // cull threshold of the render kernels: alpha >= 1/255 needs A dx^2 + 2B dx dy + C dy^2 <= 2 ln(255 o)
-                const float thr = opac > 0.0f ? 2.0f * __logf(255.0f * opac) + 0.002f : -1.0f;
-                o[2] = make_float4(rgb[1], rgb[2], thr, 0.0f);
-                depths[idx] = tvz;
-                float2* co = reinterpret_cast<float2*>(cov3D_out) + 3 * (size_t)idx;
-                co[0] = make_float2(c0, c1);
-                co[1] = make_float2(c2, c3);
-                co[2] = make_float2(c4, c5);
-                clamped[idx] = bits;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) coef[ch][k] = __ldg(sh + k * 3 + ch);
             }
         }
     }
-    radii[idx] = my_radius;
-    tiles_touched[idx] = my_tiles;
+    // cull threshold of the render kernels: alpha >= 1/255 needs A dx^2 + 2B dx dy + C dy^2 <= 2 ln(255 o)
+    const float thr = opac > 0.0f ? 2.0f * __logf(255.0f * opac) + 0.002f : -1.0f;
+
+    for (int v = 0; v < V; ++v) {
+        const ViewTab& vt = tab.v[v];
+        int my_radius = 0;
+        uint32_t my_tiles = 0;
+        if ((front >> v) & 1u) {
+            const float* mV = sV[v];
+            const float* mP = sP[v];
+            // view / projection (transformPoint4x3 / 4x4 on the transposed matrices)
+            const float tvx = mV[0] * x + mV[4] * y + mV[8] * z + mV[12];
+            const float tvy = mV[1] * x + mV[5] * y + mV[9] * z + mV[13];
+            const float tvz = mV[2] * x + mV[6] * y + mV[10] * z + mV[14];
+            const float hx = mP[0] * x + mP[4] * y + mP[8] * z + mP[12];
+            const float hy = mP[1] * x + mP[5] * y + mP[9] * z + mP[13];
+            const float hw = mP[3] * x + mP[7] * y + mP[11] * z + mP[15];
+            const float pw = 1.0f / (hw + PW_EPS);
+            const float ndcx = hx * pw, ndcy = hy * pw;
+            // EWA projection
+            const float txtz = tvx / tvz, tytz = tvy / tvz;
+            const float tx = fminf(vt.limx, fmaxf(-vt.limx, txtz)) * tvz;
+            const float ty = fminf(vt.limy, fmaxf(-vt.limy, tytz)) * tvz;
+            const float J00 = vt.focal_x / tvz;
+            const float J02 = -(vt.focal_x * tx) / (tvz * tvz);
+            const float J11 = vt.focal_y / tvz;
+            const float J12 = -(vt.focal_y * ty) / (tvz * tvz);
+            const float M00 = J00 * mV[0] + J02 * mV[2];
+            const float M01 = J00 * mV[4] + J02 * mV[6];
+            const float M02 = J00 * mV[8] + J02 * mV[10];
+            const float M10 = J11 * mV[1] + J12 * mV[2];
+            const float M11 = J11 * mV[5] + J12 * mV[6];
+            const float M12 = J11 * mV[9] + J12 * mV[10];
+            const float N00 = M00 * c0 + M01 * c1 + M02 * c2;
+            const float N01 = M00 * c1 + M01 * c3 + M02 * c4;
+            const float N02 = M00 * c2 + M01 * c4 + M02 * c5;
+            const float N10 = M10 * c0 + M11 * c1 + M12 * c2;
+            const float N11 = M10 * c1 + M11 * c3 + M12 * c4;
+            const float N12 = M10 * c2 + M11 * c4 + M12 * c5;
+            const float a = N00 * M00 + N01 * M01 + N02 * M02 + DILATION;
+            const float b = N00 * M10 + N01 * M11 + N02 * M12;
+            const float c = N10 * M10 + N11 * M11 + N12 * M12 + DILATION;
+            const float det = a * c - b * b;
+            if (det != 0.0f) {
+                const float det_inv = 1.0f / det;
+                const float mid = 0.5f * (a + c);
+                const float disc = sqrtf(fmaxf(mid * mid - det, LAMBDA_FLOOR));
+                const float lam = fmaxf(mid + disc, mid - disc);
+                const float radius_f = ceilf(3.0f * sqrtf(lam));
+                const float px = ndc2pix(ndcx, tab.W), py = ndc2pix(ndcy, tab.H);
+                int x0, y0, x1, y1;
+                get_rect(px, py, radius_f, tab.grid_x, tab.grid_y, x0, y0, x1, y1);
+                const int area = (x1 - x0) * (y1 - y0);
+                if (area > 0) {
+                    float rgb[3];
+                    uint8_t bits = 0;
+                    if (DEG < 0) {
+                        rgb[0] = coef[0][0], rgb[1] = coef[1][0], rgb[2] = coef[2][0];
+                    } else {
+                        float dx = x - sC[v][0], dy = y - sC[v][1], dz = z - sC[v][2];
+                        const float n = sqrtf(dx * dx + dy * dy + dz * dz);
+                        dx = dx / n, dy = dy / n, dz = dz / n;
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) {
+                            const float rr = sh_channel<(DEG < 0 ? 0 : DEG)>(coef[ch], dx, dy, dz) + 0.5f;
+                            if (rr < 0.0f) bits |= (uint8_t)(1u << ch);
+                            rgb[ch] = fmaxf(rr, 0.0f);
+                        }
+                    }
+                    my_radius = (int)radius_f;
+                    my_tiles = (uint32_t)area;
+                    float4* o = reinterpret_cast<float4*>(vt.rec) + 3 * (size_t)idx;
+                    o[0] = make_float4(px, py, c * det_inv, -b * det_inv);
+                    o[1] = make_float4(a * det_inv, opac, tvz, rgb[0]);
+                    o[2] = make_float4(rgb[1], rgb[2], thr, 0.0f);
+                    vt.depths[idx] = tvz;
+                    vt.clamped[idx] = bits;
+                }
+            }
+        }
+        vt.radii[idx] = my_radius;
+        vt.tiles_touched[idx] = my_tiles;
+    }
 }
 
 // key = (tile_id << 32) | float_bits(depth); value = Gaussian index; tiles y-major then x.
 // Fused: the per-digit-place histograms the onesweep sort needs (hist[pass][256]) are accumulated here --
 // all keys of one Gaussian share their low 32 bits, so the four depth digits cost one weighted shared-memory
 // atomic per Gaussian instead of one per key, and the separate histogram read of the key array disappears.
-constexpr int DUP_MAX_PASSES = 8;
+// blockIdx.y = view.  Pairs beyond the binning capacity are dropped and flagged (STATUS_OVERFLOW).
 __global__ void __launch_bounds__(256)
-duplicate_kernel(int P, int gx, int gy, const int32_t* __restrict__ radii, const float* __restrict__ rec,
-                 const float* __restrict__ depths, const uint32_t* __restrict__ point_offsets,
-                 uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ hist, int end_bit) {
-    __shared__ uint32_t s_hist[DUP_MAX_PASSES * 256];
+duplicate_kernel(const __grid_constant__ BatchTab tab) {
+    __shared__ uint32_t s_hist[MAX_PASSES * 256];
+    const ViewTab& vt = tab.v[blockIdx.y];
+    const int end_bit = tab.end_bit;
     const int passes = (end_bit + 7) / 8;
+    const int gx = tab.grid_x, gy = tab.grid_y;
     for (int i = threadIdx.x; i < passes * 256; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < P; idx += gridDim.x * blockDim.x) {
+    const int32_t* __restrict__ radii = vt.radii;
+    const uint32_t* __restrict__ point_offsets = vt.point_offsets;
+    uint64_t* __restrict__ keys = vt.keys[0];
+    uint32_t* __restrict__ vals = vt.vals[0];
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < tab.P; idx += gridDim.x * blockDim.x) {
         const int rad = radii[idx];
         if (rad <= 0) continue;
         uint32_t off = (idx == 0) ? 0u : point_offsets[idx - 1];
-        const float2 xy = *reinterpret_cast<const float2*>(rec + (size_t)idx * REC_FLOATS);
+        const float2 xy = *reinterpret_cast<const float2*>(vt.rec + (size_t)idx * REC_FLOATS);
         int x0, y0, x1, y1;
         get_rect(xy.x, xy.y, (float)rad, gx, gy, x0, y0, x1, y1);
-        const uint32_t d32 = __float_as_uint(depths[idx]);
+        const uint32_t d32 = __float_as_uint(vt.depths[idx]);
         const uint64_t dbits = (uint64_t)d32;
         const uint32_t ntiles = (uint32_t)((x1 - x0) * (y1 - y0));
+        if (off + ntiles > tab.capacity) {
+            atomicOr(vt.status + STATUS_OVERFLOW, 1u);
+            continue;
+        }
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
             if (p < passes) {
@@ -289,7 +307,7 @@ duplicate_kernel(int P, int gx, int gy, const int32_t* __restrict__ radii, const
     __syncthreads();
     for (int i = threadIdx.x; i < passes * 256; i += blockDim.x) {
         const uint32_t c = s_hist[i];
-        if (c) atomicAdd(&hist[i], c);
+        if (c) atomicAdd(&vt.hist[i], c);
     }
 }
 
@@ -302,24 +320,30 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, co
     present[idx] = tvz > NEAR_CULL ? 1 : 0;
 }
 
-cudaError_t launch_preprocess(int P, const CameraParams& cam, const float* means3D, const float* scales,
-                              const float* rotations, const float* opacities, const float* shs,
-                              const float* colors_precomp, const float* cov3D_precomp, int32_t* radii,
-                              const GeomViews& g, cudaStream_t st) {
-    if (P <= 0) return cudaSuccess;
-    preprocess_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, cam, means3D, scales, rotations, opacities, shs,
-                                                        colors_precomp, cov3D_precomp, radii, g.rec, g.depths,
-                                                        g.cov3D, g.clamped, g.tiles_touched);
+cudaError_t launch_preprocess(const BatchTab& tab, const float* means3D, const float* scales, const float* rotations,
+                              const float* opacities, const float* shs, const float* colors_precomp,
+                              const float* cov3D_precomp, cudaStream_t st) {
+    if (tab.P <= 0) return cudaSuccess;
+    const int grid = (tab.P + 255) / 256;
+#define LAUNCH_PRE(D)                                                                                             \
+    preprocess_kernel<D><<<grid, 256, 0, st>>>(tab, means3D, scales, rotations, opacities, shs, colors_precomp, \
+                                                cov3D_precomp)
+    switch (tab.sh_degree) {
+        case -1: LAUNCH_PRE(-1); break;
+        case 0: LAUNCH_PRE(0); break;
+        case 1: LAUNCH_PRE(1); break;
+        case 2: LAUNCH_PRE(2); break;
+        default: LAUNCH_PRE(3); break;
+    }
+#undef LAUNCH_PRE
     count_launch();
     return cudaGetLastError();
 }
 
-cudaError_t launch_duplicate(int P, const CameraParams& cam, const int32_t* radii, const GeomViews& g,
-                             uint64_t* keys, uint32_t* vals, uint32_t* hist, int end_bit, cudaStream_t st) {
-    if (P <= 0) return cudaSuccess;
-    const int blocks = min((P + 255) / 256, NUM_SMS * 8);
-    duplicate_kernel<<<blocks, 256, 0, st>>>(P, cam.grid_x, cam.grid_y, radii, g.rec, g.depths,
-                                              g.point_offsets, keys, vals, hist, end_bit);
+cudaError_t launch_duplicate(const BatchTab& tab, cudaStream_t st) {
+    if (tab.P <= 0) return cudaSuccess;
+    const int bx = min((tab.P + 255) / 256, max(1, NUM_SMS * 8 / tab.V));
+    duplicate_kernel<<<dim3(bx, tab.V), 256, 0, st>>>(tab);
     count_launch();
     return cudaGetLastError();
 }

@@ -1,4 +1,5 @@
-// K8 preprocess backward: 2-D stage gradients -> parameter gradients, one fused kernel.
+// K8 preprocess backward: 2-D stage gradients -> parameter gradients, one fused kernel for a whole
+// view batch.
 //
 // Replaces upstream backward.cu computeCov2DCUDA + preprocessCUDA (+ computeColorFromSH and
 // computeCov3D backward) [UPSTREAM-RECALL; SURVEY.md Appendix A]; the gradients it produces are
@@ -7,6 +8,12 @@
 // the FOV clamp zeroes dL/dt.x|y and treats the clamped t.x|y as constant w.r.t. t.z; the conic
 // gradient uses 1/(det^2 + 1e-7); culled Gaussians (radii == 0) get exactly-zero gradients;
 // dL/dmeans2D is the gradient w.r.t. the NDC position (pixel gradient x W/2, H/2), z = 0.
+//
+// View batching: one thread owns one Gaussian and loops over the V views of the step, so the parameters
+// (and the SH block) are read once, the gradients of all views are summed in registers and written once
+// -- instead of V read-modify-write passes -- and Sigma3's backward runs once on the summed dL/dSigma.
+// The reference's per-view densification statistics (geometry/gaussian_base.py:815-819, 846-851) are an
+// optional fused epilogue.
 #include "common.cuh"
 
 namespace b200splat {
@@ -26,276 +33,336 @@ constexpr float SH_C3_4 = -0.4570457994644658f;
 constexpr float SH_C3_5 = 1.445305721320277f;
 constexpr float SH_C3_6 = -0.5900435899266435f;
 
+// SH basis values and their gradients w.r.t. the unit direction for coefficients 4C .. 4C+3
+template <int C>
+__device__ __forceinline__ void sh_basis_chunk(float x, float y, float z, float B[4], float Bx[4], float By[4],
+                                               float Bz[4]) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) B[t] = Bx[t] = By[t] = Bz[t] = 0.f;
+    const float xx = x * x, yy = y * y, zz = z * z;
+    if (C == 0) {
+        B[0] = SH_C0;
+        B[1] = -SH_C1 * y, By[1] = -SH_C1;
+        B[2] = SH_C1 * z, Bz[2] = SH_C1;
+        B[3] = -SH_C1 * x, Bx[3] = -SH_C1;
+    } else if (C == 1) {
+        B[0] = SH_C2_0 * x * y, Bx[0] = SH_C2_0 * y, By[0] = SH_C2_0 * x;
+        B[1] = SH_C2_1 * y * z, By[1] = SH_C2_1 * z, Bz[1] = SH_C2_1 * y;
+        B[2] = SH_C2_2 * (2.f * zz - xx - yy), Bx[2] = SH_C2_2 * -2.f * x, By[2] = SH_C2_2 * -2.f * y,
+        Bz[2] = SH_C2_2 * 4.f * z;
+        B[3] = SH_C2_3 * x * z, Bx[3] = SH_C2_3 * z, Bz[3] = SH_C2_3 * x;
+    } else if (C == 2) {
+        B[0] = SH_C2_4 * (xx - yy), Bx[0] = SH_C2_4 * 2.f * x, By[0] = SH_C2_4 * -2.f * y;
+        B[1] = SH_C3_0 * y * (3.f * xx - yy), Bx[1] = SH_C3_0 * 6.f * x * y, By[1] = SH_C3_0 * (3.f * xx - 3.f * yy);
+        B[2] = SH_C3_1 * x * y * z, Bx[2] = SH_C3_1 * y * z, By[2] = SH_C3_1 * x * z, Bz[2] = SH_C3_1 * x * y;
+        B[3] = SH_C3_2 * y * (4.f * zz - xx - yy), Bx[3] = SH_C3_2 * -2.f * x * y,
+        By[3] = SH_C3_2 * (4.f * zz - xx - 3.f * yy), Bz[3] = SH_C3_2 * 8.f * y * z;
+    } else {
+        B[0] = SH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy), Bx[0] = SH_C3_3 * -6.f * x * z,
+        By[0] = SH_C3_3 * -6.f * y * z, Bz[0] = SH_C3_3 * (6.f * zz - 3.f * xx - 3.f * yy);
+        B[1] = SH_C3_4 * x * (4.f * zz - xx - yy), Bx[1] = SH_C3_4 * (4.f * zz - 3.f * xx - yy),
+        By[1] = SH_C3_4 * -2.f * x * y, Bz[1] = SH_C3_4 * 8.f * x * z;
+        B[2] = SH_C3_5 * z * (xx - yy), Bx[2] = SH_C3_5 * 2.f * x * z, By[2] = SH_C3_5 * -2.f * y * z,
+        Bz[2] = SH_C3_5 * (xx - yy);
+        B[3] = SH_C3_6 * x * (xx - 3.f * yy), Bx[3] = SH_C3_6 * (3.f * xx - 3.f * yy), By[3] = SH_C3_6 * -6.f * x * y;
+    }
+}
+
+// one chunk of 4 coefficients of one view: accumulate dL/dsh (registers) and dL/ddir
+template <int C, int K, bool VEC>
+__device__ __forceinline__ void sh_chunk_backward(const float* __restrict__ sh, float x, float y, float z,
+                                                  const float g[3], float* dsh /* [12] of this chunk */,
+                                                  float& ddx, float& ddy, float& ddz) {
+    if (4 * C >= K) return;
+    float B[4], Bx[4], By[4], Bz[4];
+    sh_basis_chunk<C>(x, y, z, B, Bx, By, Bz);
+    float sv[12];
+    if (VEC) {
+        const float4* in4 = reinterpret_cast<const float4*>(sh) + 3 * C;
+        const float4 a = __ldg(in4), b = __ldg(in4 + 1), c = __ldg(in4 + 2);
+        sv[0] = a.x, sv[1] = a.y, sv[2] = a.z, sv[3] = a.w, sv[4] = b.x, sv[5] = b.y, sv[6] = b.z, sv[7] = b.w;
+        sv[8] = c.x, sv[9] = c.y, sv[10] = c.z, sv[11] = c.w;
+    } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) sv[3 * t + ch] = (4 * C + t < K) ? __ldg(sh + 3 * (4 * C + t) + ch) : 0.f;
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        if (4 * C + t < K) {
+            const float gs = g[0] * sv[3 * t] + g[1] * sv[3 * t + 1] + g[2] * sv[3 * t + 2];
+            ddx += Bx[t] * gs, ddy += By[t] * gs, ddz += Bz[t] * gs;
+            dsh[3 * t] += B[t] * g[0];
+            dsh[3 * t + 1] += B[t] * g[1];
+            dsh[3 * t + 2] += B[t] * g[2];
+        }
+    }
+}
+
 template <bool ACC>
 __device__ __forceinline__ void put(float* p, float v) {
     if (ACC) *p += v; else *p = v;
 }
 
-// SH backward for one Gaussian.  g[c] = dL/drgb_c already masked by the clamp flags.
-// Writes dL/dsh (all M coefficients; zeros above the active degree) and returns dL/ddir.
-template <int DEG, bool ACC>
-__device__ __forceinline__ void sh_backward(const float* __restrict__ sh, float* __restrict__ dsh, int M,
-                                            float x, float y, float z, const float g[3], float dd[3]) {
-    constexpr int K = (DEG + 1) * (DEG + 1);
-    float B[K], Bx[K], By[K], Bz[K];
-    B[0] = SH_C0, Bx[0] = By[0] = Bz[0] = 0.f;
-    if (DEG > 0) {
-        B[1] = -SH_C1 * y, Bx[1] = 0.f, By[1] = -SH_C1, Bz[1] = 0.f;
-        B[2] = SH_C1 * z, Bx[2] = 0.f, By[2] = 0.f, Bz[2] = SH_C1;
-        B[3] = -SH_C1 * x, Bx[3] = -SH_C1, By[3] = 0.f, Bz[3] = 0.f;
-    }
-    if (DEG > 1) {
-        const float xx = x * x, yy = y * y, zz = z * z;
-        B[4] = SH_C2_0 * x * y, Bx[4] = SH_C2_0 * y, By[4] = SH_C2_0 * x, Bz[4] = 0.f;
-        B[5] = SH_C2_1 * y * z, Bx[5] = 0.f, By[5] = SH_C2_1 * z, Bz[5] = SH_C2_1 * y;
-        B[6] = SH_C2_2 * (2.f * zz - xx - yy), Bx[6] = SH_C2_2 * -2.f * x, By[6] = SH_C2_2 * -2.f * y,
-        Bz[6] = SH_C2_2 * 4.f * z;
-        B[7] = SH_C2_3 * x * z, Bx[7] = SH_C2_3 * z, By[7] = 0.f, Bz[7] = SH_C2_3 * x;
-        B[8] = SH_C2_4 * (xx - yy), Bx[8] = SH_C2_4 * 2.f * x, By[8] = SH_C2_4 * -2.f * y, Bz[8] = 0.f;
-    }
-    if (DEG > 2) {
-        const float xx = x * x, yy = y * y, zz = z * z;
-        B[9] = SH_C3_0 * y * (3.f * xx - yy), Bx[9] = SH_C3_0 * 6.f * x * y, By[9] = SH_C3_0 * (3.f * xx - 3.f * yy),
-        Bz[9] = 0.f;
-        B[10] = SH_C3_1 * x * y * z, Bx[10] = SH_C3_1 * y * z, By[10] = SH_C3_1 * x * z, Bz[10] = SH_C3_1 * x * y;
-        B[11] = SH_C3_2 * y * (4.f * zz - xx - yy), Bx[11] = SH_C3_2 * -2.f * x * y,
-        By[11] = SH_C3_2 * (4.f * zz - xx - 3.f * yy), Bz[11] = SH_C3_2 * 8.f * y * z;
-        B[12] = SH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy), Bx[12] = SH_C3_3 * -6.f * x * z,
-        By[12] = SH_C3_3 * -6.f * y * z, Bz[12] = SH_C3_3 * (6.f * zz - 3.f * xx - 3.f * yy);
-        B[13] = SH_C3_4 * x * (4.f * zz - xx - yy), Bx[13] = SH_C3_4 * (4.f * zz - 3.f * xx - yy),
-        By[13] = SH_C3_4 * -2.f * x * y, Bz[13] = SH_C3_4 * 8.f * x * z;
-        B[14] = SH_C3_5 * z * (xx - yy), Bx[14] = SH_C3_5 * 2.f * x * z, By[14] = SH_C3_5 * -2.f * y * z,
-        Bz[14] = SH_C3_5 * (xx - yy);
-        B[15] = SH_C3_6 * x * (xx - 3.f * yy), Bx[15] = SH_C3_6 * (3.f * xx - 3.f * yy),
-        By[15] = SH_C3_6 * -6.f * x * y, Bz[15] = 0.f;
-    }
-    float ddx = 0.f, ddy = 0.f, ddz = 0.f;
-    if ((M & 3) == 0 && M <= 16) {
-        // 16-byte path: 4 coefficients (12 floats = 3 float4) per step; per-Gaussian base is 16 B aligned
-        const float4* __restrict__ in4 = reinterpret_cast<const float4*>(sh);
-        float4* __restrict__ out4 = reinterpret_cast<float4*>(dsh);
-#pragma unroll
-        for (int k0 = 0; k0 < 16; k0 += 4) {
-            if (k0 >= M) break;
-            float o[12];
-            if (k0 < K) {
-                const float4 a = __ldg(in4 + 3 * (k0 >> 2)), b = __ldg(in4 + 3 * (k0 >> 2) + 1),
-                             c = __ldg(in4 + 3 * (k0 >> 2) + 2);
-                const float sv[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    // K is a compile-time constant: the k < K test folds after unrolling of the caller's DEG
-                    const int kk = (k0 + t < K) ? k0 + t : 0;   // compile-time after unrolling
-                    const bool live = k0 + t < K;
-                    const float Bk = live ? B[kk] : 0.f, Bxk = live ? Bx[kk] : 0.f, Byk = live ? By[kk] : 0.f,
-                                Bzk = live ? Bz[kk] : 0.f;
-                    const float gs = g[0] * sv[3 * t] + g[1] * sv[3 * t + 1] + g[2] * sv[3 * t + 2];
-                    ddx += Bxk * gs, ddy += Byk * gs, ddz += Bzk * gs;
-                    o[3 * t] = Bk * g[0], o[3 * t + 1] = Bk * g[1], o[3 * t + 2] = Bk * g[2];
-                }
-            } else {
-#pragma unroll
-                for (int t = 0; t < 12; ++t) o[t] = 0.f;
-            }
-            float4* dst = out4 + 3 * (k0 >> 2);
-            if (ACC) {
-                if (k0 < K) {
-                    const float4 p0 = dst[0], p1 = dst[1], p2 = dst[2];
-                    dst[0] = make_float4(p0.x + o[0], p0.y + o[1], p0.z + o[2], p0.w + o[3]);
-                    dst[1] = make_float4(p1.x + o[4], p1.y + o[5], p1.z + o[6], p1.w + o[7]);
-                    dst[2] = make_float4(p2.x + o[8], p2.y + o[9], p2.z + o[10], p2.w + o[11]);
-                }
-            } else {
-                dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-                dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-                dst[2] = make_float4(o[8], o[9], o[10], o[11]);
-            }
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const float s0 = __ldg(sh + 3 * k), s1 = __ldg(sh + 3 * k + 1), s2 = __ldg(sh + 3 * k + 2);
-            const float gs = g[0] * s0 + g[1] * s1 + g[2] * s2;
-            ddx += Bx[k] * gs, ddy += By[k] * gs, ddz += Bz[k] * gs;
-            put<ACC>(dsh + 3 * k, B[k] * g[0]);
-            put<ACC>(dsh + 3 * k + 1, B[k] * g[1]);
-            put<ACC>(dsh + 3 * k + 2, B[k] * g[2]);
-        }
-        if (!ACC) {
-            for (int k = 3 * K; k < 3 * M; ++k) dsh[k] = 0.f;
-        }
-    }
-    dd[0] = ddx, dd[1] = ddy, dd[2] = ddz;
-}
-
-template <bool ACC>
-__global__ void __launch_bounds__(256)
-preprocess_backward_kernel(int P, CameraParams cam, const float* __restrict__ means3D,
+// DEG = -1: colours precomputed
+template <int DEG, bool ACC, bool VEC>
+__global__ void __launch_bounds__(128)
+preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __restrict__ means3D,
                            const float* __restrict__ scales, const float* __restrict__ rotations,
                            const float* __restrict__ shs, const float* __restrict__ cov3D_precomp,
-                           const int32_t* __restrict__ radii, const float* __restrict__ cov3D_saved,
-                           const uint8_t* __restrict__ clamped, const float* __restrict__ grad2d,
-                           float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dmeans2D,
-                           float* __restrict__ dL_dshs, float* __restrict__ dL_dcolors,
-                           float* __restrict__ dL_dopacity, float* __restrict__ dL_dscales,
-                           float* __restrict__ dL_drotations, float* __restrict__ dL_dcov3D,
-                           float* __restrict__ stat_grad_accum, float* __restrict__ stat_denom,
-                           float* __restrict__ stat_max_radii) {
-    __shared__ float sV[16], sP[16], sC[3];
-    if (threadIdx.x < 16) {
-        sV[threadIdx.x] = cam.view[threadIdx.x];
-        sP[threadIdx.x] = cam.proj[threadIdx.x];
+                           float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dshs,
+                           float* __restrict__ dL_dcolors, float* __restrict__ dL_dopacity,
+                           float* __restrict__ dL_dscales, float* __restrict__ dL_drotations,
+                           float* __restrict__ dL_dcov3D, float* __restrict__ stat_grad_accum,
+                           float* __restrict__ stat_denom, float* __restrict__ stat_max_radii) {
+    __shared__ float sV[MAX_VIEWS][16], sP[MAX_VIEWS][16], sC[MAX_VIEWS][4];
+    const int V = tab.V;
+    for (int i = threadIdx.x; i < V * 16; i += blockDim.x) {
+        sV[i >> 4][i & 15] = tab.v[i >> 4].view[i & 15];
+        sP[i >> 4][i & 15] = tab.v[i >> 4].proj[i & 15];
     }
-    if (threadIdx.x < 3) sC[threadIdx.x] = cam.campos[threadIdx.x];
+    for (int i = threadIdx.x; i < V * 3; i += blockDim.x) sC[i / 3][i % 3] = tab.v[i / 3].campos[i % 3];
     __syncthreads();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
-    const int M = cam.M;
-    if (shs != nullptr) {   // SH block of this Gaussian towards L2 while the covariance chain runs
-        const char* shp = reinterpret_cast<const char*>(shs + (size_t)idx * M * 3);
-        prefetch_l2(shp);
-        if (M * 12 > 128) prefetch_l2(shp + 128);
-        if (ACC) {
-            const char* dp = reinterpret_cast<const char*>(dL_dshs + (size_t)idx * M * 3);
-            prefetch_l2(dp);
-            if (M * 12 > 128) prefetch_l2(dp + 128);
-        }
+    if (idx >= tab.P) return;
+    const int M = tab.M;
+    constexpr int K = DEG < 0 ? 0 : (DEG + 1) * (DEG + 1);
+    constexpr int NCH = (K + 3) / 4;          // live chunks of 4 coefficients
+    constexpr int NSH = NCH > 0 ? NCH * 12 : 1;
+
+    uint32_t vis = 0;
+    int max_radius = 0;
+    for (int v = 0; v < V; ++v) {
+        const int r = tab.v[v].radii[idx];
+        if (r > 0) vis |= 1u << v;
+        max_radius = max(max_radius, r);
     }
-    const int my_radius = radii[idx];
-    if (my_radius <= 0) {
+    if (vis == 0) {
         if (!ACC) {
             dL_dmeans3D[3 * idx] = dL_dmeans3D[3 * idx + 1] = dL_dmeans3D[3 * idx + 2] = 0.f;
-            dL_dmeans2D[3 * idx] = dL_dmeans2D[3 * idx + 1] = dL_dmeans2D[3 * idx + 2] = 0.f;
             dL_dopacity[idx] = 0.f;
             if (dL_dshs) for (int k = 0; k < 3 * M; ++k) dL_dshs[(size_t)idx * 3 * M + k] = 0.f;
             if (dL_dcolors) dL_dcolors[3 * idx] = dL_dcolors[3 * idx + 1] = dL_dcolors[3 * idx + 2] = 0.f;
             if (dL_dscales) dL_dscales[3 * idx] = dL_dscales[3 * idx + 1] = dL_dscales[3 * idx + 2] = 0.f;
-            if (dL_drotations)
-                reinterpret_cast<float4*>(dL_drotations)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (dL_drotations) reinterpret_cast<float4*>(dL_drotations)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (dL_dcov3D) for (int k = 0; k < 6; ++k) dL_dcov3D[(size_t)idx * 6 + k] = 0.f;
+            for (int v = 0; v < V; ++v) {
+                float* m2 = tab.v[v].dL_dmeans2D;
+                if (m2) m2[3 * idx] = m2[3 * idx + 1] = m2[3 * idx + 2] = 0.f;
+            }
         }
         return;
     }
-    const float4* gp = reinterpret_cast<const float4*>(grad2d) + 3 * (size_t)idx;
-    const float4 g0 = gp[0], g1 = gp[1], g2 = gp[2];
-    const float g_px = g0.x, g_py = g0.y, g_ca = g0.z, g_cb = g0.w, g_cc = g1.x, g_op = g1.y;
-    float g_rgb[3] = {g1.z, g1.w, g2.x};
-    const float g_depth = g2.y;
-
+    const float* sh = DEG >= 0 ? shs + (size_t)idx * M * 3 : nullptr;
+    if (DEG >= 0) {   // SH block of this Gaussian towards L2 while the covariance chain runs
+        prefetch_l2(sh);
+        if (K * 12 > 128) prefetch_l2(reinterpret_cast<const char*>(sh) + 128);
+    }
     const float x = means3D[3 * idx], y = means3D[3 * idx + 1], z = means3D[3 * idx + 2];
-    float dmx = 0.f, dmy = 0.f, dmz = 0.f;
 
-    // ---- conic -> cov2D -> (Sigma3, t) ----------------------------------------------------------
-    const float tvx = sV[0] * x + sV[4] * y + sV[8] * z + sV[12];
-    const float tvy = sV[1] * x + sV[5] * y + sV[9] * z + sV[13];
-    const float tvz = sV[2] * x + sV[6] * y + sV[10] * z + sV[14];
-    const float txtz = tvx / tvz, tytz = tvy / tvz;
-    const float tx = fminf(cam.limx, fmaxf(-cam.limx, txtz)) * tvz;
-    const float ty = fminf(cam.limy, fmaxf(-cam.limy, tytz)) * tvz;
-    const float xmul = (txtz < -cam.limx || txtz > cam.limx) ? 0.f : 1.f;
-    const float ymul = (tytz < -cam.limy || tytz > cam.limy) ? 0.f : 1.f;
-    const float itz = 1.0f / tvz, itz2 = itz * itz, itz3 = itz2 * itz;
-    const float J00 = cam.focal_x * itz, J02 = -cam.focal_x * tx * itz2;
-    const float J11 = cam.focal_y * itz, J12 = -cam.focal_y * ty * itz2;
-    const float M0[3] = {J00 * sV[0] + J02 * sV[2], J00 * sV[4] + J02 * sV[6], J00 * sV[8] + J02 * sV[10]};
-    const float M1[3] = {J11 * sV[1] + J12 * sV[2], J11 * sV[5] + J12 * sV[6], J11 * sV[9] + J12 * sV[10]};
+    // Sigma3 (view independent); R and s kept for its backward
     float c0, c1, c2, c3, c4, c5;
-    {
-        const float* cs = (cov3D_precomp ? cov3D_precomp : cov3D_saved) + 6 * (size_t)idx;
+    float R[3][3], s[3];
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool has_sr = (scales != nullptr) && (cov3D_precomp == nullptr);
+    if (!has_sr) {
+        const float* cs = cov3D_precomp + 6 * (size_t)idx;
         c0 = cs[0], c1 = cs[1], c2 = cs[2], c3 = cs[3], c4 = cs[4], c5 = cs[5];
-    }
-    const float S0[3] = {c0 * M0[0] + c1 * M0[1] + c2 * M0[2], c1 * M0[0] + c3 * M0[1] + c4 * M0[2],
-                         c2 * M0[0] + c4 * M0[1] + c5 * M0[2]};  // Sigma M0
-    const float S1[3] = {c0 * M1[0] + c1 * M1[1] + c2 * M1[2], c1 * M1[0] + c3 * M1[1] + c4 * M1[2],
-                         c2 * M1[0] + c4 * M1[1] + c5 * M1[2]};  // Sigma M1
-    const float a = M0[0] * S0[0] + M0[1] * S0[1] + M0[2] * S0[2] + DILATION;
-    const float b = M0[0] * S1[0] + M0[1] * S1[1] + M0[2] * S1[2];
-    const float c = M1[0] * S1[0] + M1[1] * S1[1] + M1[2] * S1[2] + DILATION;
-    const float det = a * c - b * b;
-    const float d2i = 1.0f / (det * det + 0.0000001f);
-    const float dLa = d2i * (-c * c * g_ca + b * c * g_cb + (det - a * c) * g_cc);
-    const float dLc = d2i * (-a * a * g_cc + a * b * g_cb + (det - a * c) * g_ca);
-    const float dLb = d2i * (2.f * b * c * g_ca - (det + 2.f * b * b) * g_cb + 2.f * a * b * g_cc);
-    float dS[6];
-    dS[0] = M0[0] * M0[0] * dLa + M0[0] * M1[0] * dLb + M1[0] * M1[0] * dLc;
-    dS[3] = M0[1] * M0[1] * dLa + M0[1] * M1[1] * dLb + M1[1] * M1[1] * dLc;
-    dS[5] = M0[2] * M0[2] * dLa + M0[2] * M1[2] * dLb + M1[2] * M1[2] * dLc;
-    dS[1] = 2.f * M0[0] * M0[1] * dLa + (M0[0] * M1[1] + M0[1] * M1[0]) * dLb + 2.f * M1[0] * M1[1] * dLc;
-    dS[2] = 2.f * M0[0] * M0[2] * dLa + (M0[0] * M1[2] + M0[2] * M1[0]) * dLb + 2.f * M1[0] * M1[2] * dLc;
-    dS[4] = 2.f * M0[1] * M0[2] * dLa + (M0[1] * M1[2] + M0[2] * M1[1]) * dLb + 2.f * M1[1] * M1[2] * dLc;
-    {
-        float dM0[3], dM1[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            dM0[k] = 2.f * dLa * S0[k] + dLb * S1[k];
-            dM1[k] = 2.f * dLc * S1[k] + dLb * S0[k];
-        }
-        const float dJ00 = dM0[0] * sV[0] + dM0[1] * sV[4] + dM0[2] * sV[8];
-        const float dJ02 = dM0[0] * sV[2] + dM0[1] * sV[6] + dM0[2] * sV[10];
-        const float dJ11 = dM1[0] * sV[1] + dM1[1] * sV[5] + dM1[2] * sV[9];
-        const float dJ12 = dM1[0] * sV[2] + dM1[1] * sV[6] + dM1[2] * sV[10];
-        const float dtx = xmul * -cam.focal_x * itz2 * dJ02;
-        const float dty = ymul * -cam.focal_y * itz2 * dJ12;
-        const float dtz = -cam.focal_x * itz2 * dJ00 - cam.focal_y * itz2 * dJ11 +
-                          2.f * cam.focal_x * tx * itz3 * dJ02 + 2.f * cam.focal_y * ty * itz3 * dJ12;
-        dmx += sV[0] * dtx + sV[1] * dty + sV[2] * dtz;
-        dmy += sV[4] * dtx + sV[5] * dty + sV[6] * dtz;
-        dmz += sV[8] * dtx + sV[9] * dty + sV[10] * dtz;
-    }
-    // ---- mean2D (NDC) and depth -----------------------------------------------------------------
-    const float gnx = g_px * 0.5f * (float)cam.W, gny = g_py * 0.5f * (float)cam.H;
-    {
-        const float hx = sP[0] * x + sP[4] * y + sP[8] * z + sP[12];
-        const float hy = sP[1] * x + sP[5] * y + sP[9] * z + sP[13];
-        const float hw = sP[3] * x + sP[7] * y + sP[11] * z + sP[15];
-        const float pw = 1.0f / (hw + PW_EPS);
-        const float mul1 = hx * pw * pw, mul2 = hy * pw * pw;
-        dmx += (sP[0] * pw - sP[3] * mul1) * gnx + (sP[1] * pw - sP[3] * mul2) * gny;
-        dmy += (sP[4] * pw - sP[7] * mul1) * gnx + (sP[5] * pw - sP[7] * mul2) * gny;
-        dmz += (sP[8] * pw - sP[11] * mul1) * gnx + (sP[9] * pw - sP[11] * mul2) * gny;
-        dmx += sV[2] * g_depth;
-        dmy += sV[6] * g_depth;
-        dmz += sV[10] * g_depth;
-    }
-    // ---- colour ---------------------------------------------------------------------------------
-    if (shs != nullptr) {
-        const uint8_t bits = clamped[idx];
+        for (int i = 0; i < 3; ++i) {
+            s[i] = 0.f;
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch)
-            if (bits & (1u << ch)) g_rgb[ch] = 0.f;
-        float dx = x - sC[0], dy = y - sC[1], dz = z - sC[2];
-        const float n = sqrtf(dx * dx + dy * dy + dz * dz);
-        const float in = 1.0f / n;
-        dx *= in, dy *= in, dz *= in;
-        float dd[3];
-        const float* sh = shs + (size_t)idx * M * 3;
-        float* dsh = dL_dshs + (size_t)idx * M * 3;
-        switch (cam.sh_degree) {
-            case 0: sh_backward<0, ACC>(sh, dsh, M, dx, dy, dz, g_rgb, dd); break;
-            case 1: sh_backward<1, ACC>(sh, dsh, M, dx, dy, dz, g_rgb, dd); break;
-            case 2: sh_backward<2, ACC>(sh, dsh, M, dx, dy, dz, g_rgb, dd); break;
-            default: sh_backward<3, ACC>(sh, dsh, M, dx, dy, dz, g_rgb, dd); break;
+            for (int j = 0; j < 3; ++j) R[i][j] = 0.f;
         }
-        // through dir = d / |d|
-        const float dot = dx * dd[0] + dy * dd[1] + dz * dd[2];
-        dmx += (dd[0] - dx * dot) * in;
-        dmy += (dd[1] - dy * dot) * in;
-        dmz += (dd[2] - dz * dot) * in;
-    } else if (dL_dcolors) {
-        put<ACC>(dL_dcolors + 3 * idx, g_rgb[0]);
-        put<ACC>(dL_dcolors + 3 * idx + 1, g_rgb[1]);
-        put<ACC>(dL_dcolors + 3 * idx + 2, g_rgb[2]);
-    }
-    // ---- Sigma3 -> scale / rotation -------------------------------------------------------------
-    if (scales != nullptr && dL_dscales != nullptr) {
-        const float mod = cam.scale_modifier;
-        const float sx = mod * scales[3 * idx], sy = mod * scales[3 * idx + 1], sz = mod * scales[3 * idx + 2];
-        const float4 q = reinterpret_cast<const float4*>(rotations)[idx];
+    } else {
+        const float mod = tab.scale_modifier;
+        s[0] = mod * scales[3 * idx], s[1] = mod * scales[3 * idx + 1], s[2] = mod * scales[3 * idx + 2];
+        q = reinterpret_cast<const float4*>(rotations)[idx];
         const float r = q.x, qx = q.y, qy = q.z, qz = q.w;
-        const float R[3][3] = {{1.f - 2.f * (qy * qy + qz * qz), 2.f * (qx * qy - r * qz), 2.f * (qx * qz + r * qy)},
-                               {2.f * (qx * qy + r * qz), 1.f - 2.f * (qx * qx + qz * qz), 2.f * (qy * qz - r * qx)},
-                               {2.f * (qx * qz - r * qy), 2.f * (qy * qz + r * qx), 1.f - 2.f * (qx * qx + qy * qy)}};
-        const float s[3] = {sx, sy, sz};
+        R[0][0] = 1.f - 2.f * (qy * qy + qz * qz), R[0][1] = 2.f * (qx * qy - r * qz), R[0][2] = 2.f * (qx * qz + r * qy);
+        R[1][0] = 2.f * (qx * qy + r * qz), R[1][1] = 1.f - 2.f * (qx * qx + qz * qz), R[1][2] = 2.f * (qy * qz - r * qx);
+        R[2][0] = 2.f * (qx * qz - r * qy), R[2][1] = 2.f * (qy * qz + r * qx), R[2][2] = 1.f - 2.f * (qx * qx + qy * qy);
+        float L[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) L[i][j] = R[i][j] * s[j];
+        // same association as the forward kernel (preprocess.cu); FMA contraction differs by <= 1 ulp
+        c0 = L[0][0] * L[0][0] + L[0][1] * L[0][1] + L[0][2] * L[0][2];
+        c1 = L[0][0] * L[1][0] + L[0][1] * L[1][1] + L[0][2] * L[1][2];
+        c2 = L[0][0] * L[2][0] + L[0][1] * L[2][1] + L[0][2] * L[2][2];
+        c3 = L[1][0] * L[1][0] + L[1][1] * L[1][1] + L[1][2] * L[1][2];
+        c4 = L[1][0] * L[2][0] + L[1][1] * L[2][1] + L[1][2] * L[2][2];
+        c5 = L[2][0] * L[2][0] + L[2][1] * L[2][1] + L[2][2] * L[2][2];
+    }
+
+    float dmx = 0.f, dmy = 0.f, dmz = 0.f, dop = 0.f;
+    float dS[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float dcol[3] = {0.f, 0.f, 0.f};
+    float dsh[NSH];
+#pragma unroll
+    for (int i = 0; i < NSH; ++i) dsh[i] = 0.f;
+    float st_norm = 0.f, st_cnt = 0.f;
+
+    for (int v = 0; v < V; ++v) {
+        const ViewTab& vt = tab.v[v];
+        if (!((vis >> v) & 1u)) {
+            if (!ACC && vt.dL_dmeans2D) {
+                vt.dL_dmeans2D[3 * idx] = vt.dL_dmeans2D[3 * idx + 1] = vt.dL_dmeans2D[3 * idx + 2] = 0.f;
+            }
+            continue;
+        }
+        const float* mV = sV[v];
+        const float* mP = sP[v];
+        const float4* gp = reinterpret_cast<const float4*>(vt.grad2d) + 3 * (size_t)idx;
+        const float4 g0 = gp[0], g1 = gp[1], g2 = gp[2];
+        const float g_px = g0.x, g_py = g0.y, g_ca = g0.z, g_cb = g0.w, g_cc = g1.x, g_op = g1.y;
+        float g_rgb[3] = {g1.z, g1.w, g2.x};
+        const float g_depth = g2.y;
+
+        // ---- conic -> cov2D -> (Sigma3, t) ------------------------------------------------------
+        const float tvx = mV[0] * x + mV[4] * y + mV[8] * z + mV[12];
+        const float tvy = mV[1] * x + mV[5] * y + mV[9] * z + mV[13];
+        const float tvz = mV[2] * x + mV[6] * y + mV[10] * z + mV[14];
+        const float txtz = tvx / tvz, tytz = tvy / tvz;
+        const float tx = fminf(vt.limx, fmaxf(-vt.limx, txtz)) * tvz;
+        const float ty = fminf(vt.limy, fmaxf(-vt.limy, tytz)) * tvz;
+        const float xmul = (txtz < -vt.limx || txtz > vt.limx) ? 0.f : 1.f;
+        const float ymul = (tytz < -vt.limy || tytz > vt.limy) ? 0.f : 1.f;
+        const float itz = 1.0f / tvz, itz2 = itz * itz, itz3 = itz2 * itz;
+        const float J00 = vt.focal_x * itz, J02 = -vt.focal_x * tx * itz2;
+        const float J11 = vt.focal_y * itz, J12 = -vt.focal_y * ty * itz2;
+        const float M0[3] = {J00 * mV[0] + J02 * mV[2], J00 * mV[4] + J02 * mV[6], J00 * mV[8] + J02 * mV[10]};
+        const float M1[3] = {J11 * mV[1] + J12 * mV[2], J11 * mV[5] + J12 * mV[6], J11 * mV[9] + J12 * mV[10]};
+        const float S0[3] = {c0 * M0[0] + c1 * M0[1] + c2 * M0[2], c1 * M0[0] + c3 * M0[1] + c4 * M0[2],
+                             c2 * M0[0] + c4 * M0[1] + c5 * M0[2]};  // Sigma M0
+        const float S1[3] = {c0 * M1[0] + c1 * M1[1] + c2 * M1[2], c1 * M1[0] + c3 * M1[1] + c4 * M1[2],
+                             c2 * M1[0] + c4 * M1[1] + c5 * M1[2]};  // Sigma M1
+        const float a = M0[0] * S0[0] + M0[1] * S0[1] + M0[2] * S0[2] + DILATION;
+        const float b = M0[0] * S1[0] + M0[1] * S1[1] + M0[2] * S1[2];
+        const float c = M1[0] * S1[0] + M1[1] * S1[1] + M1[2] * S1[2] + DILATION;
+        const float det = a * c - b * b;
+        const float d2i = 1.0f / (det * det + 0.0000001f);
+        const float dLa = d2i * (-c * c * g_ca + b * c * g_cb + (det - a * c) * g_cc);
+        const float dLc = d2i * (-a * a * g_cc + a * b * g_cb + (det - a * c) * g_ca);
+        const float dLb = d2i * (2.f * b * c * g_ca - (det + 2.f * b * b) * g_cb + 2.f * a * b * g_cc);
+        dS[0] += M0[0] * M0[0] * dLa + M0[0] * M1[0] * dLb + M1[0] * M1[0] * dLc;
+        dS[3] += M0[1] * M0[1] * dLa + M0[1] * M1[1] * dLb + M1[1] * M1[1] * dLc;
+        dS[5] += M0[2] * M0[2] * dLa + M0[2] * M1[2] * dLb + M1[2] * M1[2] * dLc;
+        dS[1] += 2.f * M0[0] * M0[1] * dLa + (M0[0] * M1[1] + M0[1] * M1[0]) * dLb + 2.f * M1[0] * M1[1] * dLc;
+        dS[2] += 2.f * M0[0] * M0[2] * dLa + (M0[0] * M1[2] + M0[2] * M1[0]) * dLb + 2.f * M1[0] * M1[2] * dLc;
+        dS[4] += 2.f * M0[1] * M0[2] * dLa + (M0[1] * M1[2] + M0[2] * M1[1]) * dLb + 2.f * M1[1] * M1[2] * dLc;
+        {
+            float dM0[3], dM1[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                dM0[k] = 2.f * dLa * S0[k] + dLb * S1[k];
+                dM1[k] = 2.f * dLc * S1[k] + dLb * S0[k];
+            }
+            const float dJ00 = dM0[0] * mV[0] + dM0[1] * mV[4] + dM0[2] * mV[8];
+            const float dJ02 = dM0[0] * mV[2] + dM0[1] * mV[6] + dM0[2] * mV[10];
+            const float dJ11 = dM1[0] * mV[1] + dM1[1] * mV[5] + dM1[2] * mV[9];
+            const float dJ12 = dM1[0] * mV[2] + dM1[1] * mV[6] + dM1[2] * mV[10];
+            const float dtx = xmul * -vt.focal_x * itz2 * dJ02;
+            const float dty = ymul * -vt.focal_y * itz2 * dJ12;
+            const float dtz = -vt.focal_x * itz2 * dJ00 - vt.focal_y * itz2 * dJ11 +
+                              2.f * vt.focal_x * tx * itz3 * dJ02 + 2.f * vt.focal_y * ty * itz3 * dJ12;
+            dmx += mV[0] * dtx + mV[1] * dty + mV[2] * dtz;
+            dmy += mV[4] * dtx + mV[5] * dty + mV[6] * dtz;
+            dmz += mV[8] * dtx + mV[9] * dty + mV[10] * dtz;
+        }
+        // ---- mean2D (NDC) and depth -------------------------------------------------------------
+        const float gnx = g_px * 0.5f * (float)tab.W, gny = g_py * 0.5f * (float)tab.H;
+        {
+            const float hx = mP[0] * x + mP[4] * y + mP[8] * z + mP[12];
+            const float hy = mP[1] * x + mP[5] * y + mP[9] * z + mP[13];
+            const float hw = mP[3] * x + mP[7] * y + mP[11] * z + mP[15];
+            const float pw = 1.0f / (hw + PW_EPS);
+            const float mul1 = hx * pw * pw, mul2 = hy * pw * pw;
+            dmx += (mP[0] * pw - mP[3] * mul1) * gnx + (mP[1] * pw - mP[3] * mul2) * gny;
+            dmy += (mP[4] * pw - mP[7] * mul1) * gnx + (mP[5] * pw - mP[7] * mul2) * gny;
+            dmz += (mP[8] * pw - mP[11] * mul1) * gnx + (mP[9] * pw - mP[11] * mul2) * gny;
+            dmx += mV[2] * g_depth;
+            dmy += mV[6] * g_depth;
+            dmz += mV[10] * g_depth;
+        }
+        if (vt.dL_dmeans2D) {
+            put<ACC>(vt.dL_dmeans2D + 3 * idx, gnx);
+            put<ACC>(vt.dL_dmeans2D + 3 * idx + 1, gny);
+            if (!ACC) vt.dL_dmeans2D[3 * idx + 2] = 0.f;
+        }
+        // densification statistics of this view (geometry/gaussian_base.py:815-819)
+        st_norm += sqrtf(gnx * gnx + gny * gny);
+        st_cnt += 1.0f;
+        dop += g_op;
+        // ---- colour -----------------------------------------------------------------------------
+        if (DEG >= 0) {
+            const uint8_t bits = vt.clamped[idx];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch)
+                if (bits & (1u << ch)) g_rgb[ch] = 0.f;
+            float dx = x - sC[v][0], dy = y - sC[v][1], dz = z - sC[v][2];
+            const float n = sqrtf(dx * dx + dy * dy + dz * dz);
+            const float in = 1.0f / n;
+            dx *= in, dy *= in, dz *= in;
+            float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+            sh_chunk_backward<0, K, VEC>(sh, dx, dy, dz, g_rgb, dsh, ddx, ddy, ddz);
+            if (NCH > 1) sh_chunk_backward<1, K, VEC>(sh, dx, dy, dz, g_rgb, dsh + (NCH > 1 ? 12 : 0), ddx, ddy, ddz);
+            if (NCH > 2) sh_chunk_backward<2, K, VEC>(sh, dx, dy, dz, g_rgb, dsh + (NCH > 2 ? 24 : 0), ddx, ddy, ddz);
+            if (NCH > 3) sh_chunk_backward<3, K, VEC>(sh, dx, dy, dz, g_rgb, dsh + (NCH > 3 ? 36 : 0), ddx, ddy, ddz);
+            // through dir = d / |d|
+            const float dot = dx * ddx + dy * ddy + dz * ddz;
+            dmx += (ddx - dx * dot) * in;
+            dmy += (ddy - dy * dot) * in;
+            dmz += (ddz - dz * dot) * in;
+        } else {
+            dcol[0] += g_rgb[0], dcol[1] += g_rgb[1], dcol[2] += g_rgb[2];
+        }
+    }
+
+    // ---- write-out ---------------------------------------------------------------------------------
+    if (DEG >= 0) {
+        float* dst = dL_dshs + (size_t)idx * M * 3;
+        if (VEC) {
+            float4* out4 = reinterpret_cast<float4*>(dst);
+            const int nch_mem = M >> 2;
+#pragma unroll
+            for (int C = 0; C < 4; ++C) {
+                if (C < nch_mem) {
+                    float o[12];
+#pragma unroll
+                    for (int t = 0; t < 12; ++t) o[t] = (C < NCH) ? dsh[(C < NCH ? C : 0) * 12 + t] : 0.f;
+                    float4* d4 = out4 + 3 * C;
+                    if (ACC) {
+                        if (C < NCH) {
+                            const float4 p0 = d4[0], p1 = d4[1], p2 = d4[2];
+                            d4[0] = make_float4(p0.x + o[0], p0.y + o[1], p0.z + o[2], p0.w + o[3]);
+                            d4[1] = make_float4(p1.x + o[4], p1.y + o[5], p1.z + o[6], p1.w + o[7]);
+                            d4[2] = make_float4(p2.x + o[8], p2.y + o[9], p2.z + o[10], p2.w + o[11]);
+                        }
+                    } else {
+                        d4[0] = make_float4(o[0], o[1], o[2], o[3]);
+                        d4[1] = make_float4(o[4], o[5], o[6], o[7]);
+                        d4[2] = make_float4(o[8], o[9], o[10], o[11]);
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3 * K; ++k) put<ACC>(dst + k, dsh[k]);
+            if (!ACC) for (int k = 3 * K; k < 3 * M; ++k) dst[k] = 0.f;
+        }
+    } else if (dL_dcolors) {
+        put<ACC>(dL_dcolors + 3 * idx, dcol[0]);
+        put<ACC>(dL_dcolors + 3 * idx + 1, dcol[1]);
+        put<ACC>(dL_dcolors + 3 * idx + 2, dcol[2]);
+    }
+    // ---- Sigma3 -> scale / rotation (once, on the dL/dSigma summed over the views) ------------------
+    if (has_sr && dL_dscales != nullptr) {
+        const float mod = tab.scale_modifier;
+        const float r = q.x, qx = q.y, qy = q.z, qz = q.w;
         // G = dL/dSigma as a full symmetric matrix; dL/dL = 2 G L, L = R diag(s)
         const float Gm[3][3] = {{dS[0], 0.5f * dS[1], 0.5f * dS[2]},
                                 {0.5f * dS[1], dS[3], 0.5f * dS[4]},
@@ -337,35 +404,42 @@ preprocess_backward_kernel(int P, CameraParams cam, const float* __restrict__ me
     put<ACC>(dL_dmeans3D + 3 * idx, dmx);
     put<ACC>(dL_dmeans3D + 3 * idx + 1, dmy);
     put<ACC>(dL_dmeans3D + 3 * idx + 2, dmz);
-    put<ACC>(dL_dmeans2D + 3 * idx, gnx);
-    put<ACC>(dL_dmeans2D + 3 * idx + 1, gny);
-    if (!ACC) dL_dmeans2D[3 * idx + 2] = 0.f;
-    put<ACC>(dL_dopacity + idx, g_op);
-    // fused densification statistics of this view (geometry/gaussian_base.py:815-819, 846-851)
-    if (stat_grad_accum) stat_grad_accum[idx] += sqrtf(gnx * gnx + gny * gny);
-    if (stat_denom) stat_denom[idx] += 1.0f;
-    if (stat_max_radii) stat_max_radii[idx] = fmaxf(stat_max_radii[idx], (float)my_radius);
+    put<ACC>(dL_dopacity + idx, dop);
+    // fused densification statistics (geometry/gaussian_base.py:815-819, 846-851)
+    if (stat_grad_accum) stat_grad_accum[idx] += st_norm;
+    if (stat_denom) stat_denom[idx] += st_cnt;
+    if (stat_max_radii) stat_max_radii[idx] = fmaxf(stat_max_radii[idx], (float)max_radius);
 }
 
-cudaError_t launch_preprocess_backward(int P, const CameraParams& cam, const float* means3D, const float* scales,
+cudaError_t launch_preprocess_backward(const BatchTab& tab, const float* means3D, const float* scales,
                                        const float* rotations, const float* shs, const float* cov3D_precomp,
-                                       const int32_t* radii, const GeomViews& g, const float* grad2d,
-                                       float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dshs, float* dL_dcolors,
-                                       float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dcov3D,
+                                       float* dL_dmeans3D, float* dL_dshs, float* dL_dcolors, float* dL_dopacity,
+                                       float* dL_dscales, float* dL_drotations, float* dL_dcov3D,
                                        float* stat_grad_accum, float* stat_denom, float* stat_max_radii,
                                        int accumulate, cudaStream_t st) {
-    if (P <= 0) return cudaSuccess;
-    const int grid = (P + 255) / 256;
-    if (accumulate)
-        preprocess_backward_kernel<true><<<grid, 256, 0, st>>>(
-            P, cam, means3D, scales, rotations, shs, cov3D_precomp, radii, g.cov3D, g.clamped, grad2d, dL_dmeans3D,
-            dL_dmeans2D, dL_dshs, dL_dcolors, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D, stat_grad_accum,
-            stat_denom, stat_max_radii);
-    else
-        preprocess_backward_kernel<false><<<grid, 256, 0, st>>>(
-            P, cam, means3D, scales, rotations, shs, cov3D_precomp, radii, g.cov3D, g.clamped, grad2d, dL_dmeans3D,
-            dL_dmeans2D, dL_dshs, dL_dcolors, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D, stat_grad_accum,
-            stat_denom, stat_max_radii);
+    if (tab.P <= 0) return cudaSuccess;
+    const int grid = (tab.P + 127) / 128;
+    const bool vec = tab.sh_degree >= 0 && (tab.M & 3) == 0 && tab.M <= 16 &&
+                     ((reinterpret_cast<uintptr_t>(shs) | reinterpret_cast<uintptr_t>(dL_dshs)) & 15) == 0;
+#define LAUNCH_PB(D, A, VC)                                                                                        \
+    preprocess_backward_kernel<D, A, VC><<<grid, 128, 0, st>>>(                                                    \
+        tab, means3D, scales, rotations, shs, cov3D_precomp, dL_dmeans3D, dL_dshs, dL_dcolors, dL_dopacity,        \
+        dL_dscales, dL_drotations, dL_dcov3D, stat_grad_accum, stat_denom, stat_max_radii)
+#define DISPATCH_DEG(A, VC)                                                                                        \
+    switch (tab.sh_degree) {                                                                                       \
+        case -1: LAUNCH_PB(-1, A, false); break;                                                                   \
+        case 0: LAUNCH_PB(0, A, VC); break;                                                                        \
+        case 1: LAUNCH_PB(1, A, VC); break;                                                                        \
+        case 2: LAUNCH_PB(2, A, VC); break;                                                                        \
+        default: LAUNCH_PB(3, A, VC); break;                                                                       \
+    }
+    if (accumulate) {
+        if (vec) { DISPATCH_DEG(true, true) } else { DISPATCH_DEG(true, false) }
+    } else {
+        if (vec) { DISPATCH_DEG(false, true) } else { DISPATCH_DEG(false, false) }
+    }
+#undef DISPATCH_DEG
+#undef LAUNCH_PB
     count_launch();
     return cudaGetLastError();
 }

@@ -128,17 +128,27 @@ __device__ __forceinline__ bool cull_keep(const float4 q0, const float C, const 
 // ============================================================================================
 template <bool BULK>
 __global__ void __launch_bounds__(BLOCK_SIZE)
-render_forward_kernel(int W, int H, int grid_x, const uint32_t* __restrict__ ranges,
-                      const uint32_t* __restrict__ tile_order, const uint32_t* __restrict__ point_list, const float* __restrict__ rec,
-                      const float* __restrict__ bg, uint32_t* __restrict__ n_contrib, uint32_t* __restrict__ n_visited,
-                      float* __restrict__ final_T, float* __restrict__ out_color, float* __restrict__ out_depth,
-                      float* __restrict__ out_alpha) {
+render_forward_kernel(const __grid_constant__ BatchTab tab, int sel) {
     __shared__ __align__(16) float4 s_rec[STAGES][BATCH * 3];
     __shared__ __align__(8) uint64_t s_bar[STAGES];
     __shared__ __align__(16) uint8_t s_surv[BLOCK_SIZE / 32][BATCH + 16];
 
-    const int tile = (int)tile_order[blockIdx.x];   // longest lists first (LPT)
+    const int W = tab.W, H = tab.H, grid_x = tab.grid_x;
+    const int n_tiles = grid_x * tab.grid_y;
+    const uint32_t entry = tab.tile_order[blockIdx.x];   // longest lists of the whole view batch first (LPT)
+    const ViewTab& vt = tab.v[entry / n_tiles];
+    const int tile = (int)(entry % n_tiles);
     const int tile_x = tile % grid_x, tile_y = tile / grid_x;
+    const uint32_t* __restrict__ ranges = vt.ranges;
+    const uint32_t* __restrict__ point_list = vt.vals[sel];
+    const float* __restrict__ rec = vt.rec;
+    const float* __restrict__ bg = vt.bg;
+    uint32_t* __restrict__ n_contrib = vt.n_contrib;
+    uint32_t* __restrict__ n_visited = vt.n_visited;
+    float* __restrict__ final_T = vt.final_T;
+    float* __restrict__ out_color = vt.out_color;
+    float* __restrict__ out_depth = vt.out_depth;
+    float* __restrict__ out_alpha = vt.out_alpha;
     int lx, ly;
     thread_pixel(lx, ly);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -323,20 +333,29 @@ __device__ __forceinline__ int reduce_slot(int lane) {
 
 template <bool BULK>
 __global__ void __launch_bounds__(BLOCK_SIZE)
-render_backward_kernel(int W, int H, int grid_x, const uint32_t* __restrict__ ranges,
-                       const uint32_t* __restrict__ tile_order, const uint32_t* __restrict__ point_list, const float* __restrict__ rec,
-                       const float* __restrict__ bg, const uint32_t* __restrict__ n_contrib,
-                       const float* __restrict__ final_T, const float* __restrict__ dL_dcolor,
-                       const float* __restrict__ dL_ddepth, const float* __restrict__ dL_dalpha,
-                       float* __restrict__ grad2d) {
+render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
     __shared__ __align__(16) float4 s_rec[STAGES][BATCH * 3];
     __shared__ uint32_t s_ids[STAGES][BATCH];
     __shared__ __align__(8) uint64_t s_bar[STAGES];
     __shared__ __align__(16) uint8_t s_surv[BLOCK_SIZE / 32][BATCH + 16];
     __shared__ uint32_t s_max;
 
-    const int tile = (int)tile_order[blockIdx.x];   // longest lists first (LPT)
+    const int W = tab.W, H = tab.H, grid_x = tab.grid_x;
+    const int n_tiles = grid_x * tab.grid_y;
+    const uint32_t entry = tab.tile_order[blockIdx.x];   // longest lists of the whole view batch first (LPT)
+    const ViewTab& vt = tab.v[entry / n_tiles];
+    const int tile = (int)(entry % n_tiles);
     const int tile_x = tile % grid_x, tile_y = tile / grid_x;
+    const uint32_t* __restrict__ ranges = vt.ranges;
+    const uint32_t* __restrict__ point_list = vt.vals[sel];
+    const float* __restrict__ rec = vt.rec;
+    const float* __restrict__ bg = vt.bg;
+    const uint32_t* __restrict__ n_contrib = vt.n_contrib;
+    const float* __restrict__ final_T = vt.final_T;
+    const float* __restrict__ dL_dcolor = vt.dL_dcolor;
+    const float* __restrict__ dL_ddepth = vt.dL_ddepth;
+    const float* __restrict__ dL_dalpha = vt.dL_dalpha;
+    float* __restrict__ grad2d = vt.grad2d;
     int lx, ly;
     thread_pixel(lx, ly);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -504,37 +523,22 @@ static bool use_bulk_staging() {
     return mode == 1;
 }
 
-cudaError_t launch_render_forward(const CameraParams& cam, const uint32_t* ranges, const uint32_t* tile_order,
-                                  const uint32_t* point_list,
-                                  const float* rec, uint32_t* n_contrib, uint32_t* n_visited, float* final_T,
-                                  float* out_color, float* out_depth, float* out_alpha, cudaStream_t st) {
-    dim3 grid(cam.grid_x * cam.grid_y);
+cudaError_t launch_render_forward(const BatchTab& tab, int sel, cudaStream_t st) {
+    const unsigned grid = (unsigned)(tab.V * tab.grid_x * tab.grid_y);
     if (use_bulk_staging())
-        render_forward_kernel<true><<<grid, BLOCK_SIZE, 0, st>>>(cam.W, cam.H, cam.grid_x, ranges, tile_order, point_list, rec,
-                                                                 cam.bg, n_contrib, n_visited, final_T, out_color,
-                                                                 out_depth, out_alpha);
+        render_forward_kernel<true><<<grid, BLOCK_SIZE, 0, st>>>(tab, sel);
     else
-        render_forward_kernel<false><<<grid, BLOCK_SIZE, 0, st>>>(cam.W, cam.H, cam.grid_x, ranges, tile_order, point_list, rec,
-                                                                  cam.bg, n_contrib, n_visited, final_T, out_color,
-                                                                  out_depth, out_alpha);
+        render_forward_kernel<false><<<grid, BLOCK_SIZE, 0, st>>>(tab, sel);
     count_launch();
     return cudaGetLastError();
 }
 
-cudaError_t launch_render_backward(const CameraParams& cam, const uint32_t* ranges, const uint32_t* tile_order,
-                                   const uint32_t* point_list,
-                                   const float* rec, const uint32_t* n_contrib, const float* final_T,
-                                   const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
-                                   float* grad2d, cudaStream_t st) {
-    dim3 grid(cam.grid_x * cam.grid_y);
+cudaError_t launch_render_backward(const BatchTab& tab, int sel, cudaStream_t st) {
+    const unsigned grid = (unsigned)(tab.V * tab.grid_x * tab.grid_y);
     if (use_bulk_staging())
-        render_backward_kernel<true><<<grid, BLOCK_SIZE, 0, st>>>(cam.W, cam.H, cam.grid_x, ranges, tile_order, point_list, rec,
-                                                                  cam.bg, n_contrib, final_T, dL_dcolor, dL_ddepth,
-                                                                  dL_dalpha, grad2d);
+        render_backward_kernel<true><<<grid, BLOCK_SIZE, 0, st>>>(tab, sel);
     else
-        render_backward_kernel<false><<<grid, BLOCK_SIZE, 0, st>>>(cam.W, cam.H, cam.grid_x, ranges, tile_order, point_list, rec,
-                                                                   cam.bg, n_contrib, final_T, dL_dcolor, dL_ddepth,
-                                                                   dL_dalpha, grad2d);
+        render_backward_kernel<false><<<grid, BLOCK_SIZE, 0, st>>>(tab, sel);
     count_launch();
     return cudaGetLastError();
 }

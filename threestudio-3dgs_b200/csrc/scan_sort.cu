@@ -1,23 +1,15 @@
 // K2 inclusive scan (decoupled look-back), K4 onesweep LSD radix sort of (u64 key, u32 value) pairs,
-// K5 identifyTileRanges.  Hand-written; no CUB.
+// K5 identifyTileRanges + longest-list-first tile order.  Hand-written; no CUB.
 //
 // Replaces cub::DeviceScan::InclusiveSum, cub::DeviceRadixSort::SortPairs and
 // rasterizer_impl.cu identifyTileRanges as called by upstream CudaRasterizer::Rasterizer::forward
 // [UPSTREAM-RECALL]; reference call site renderer/diff_gaussian_rasterizer.py:122-131.
 // All integer work: results are bit-exact by construction (stable sort, exact sums).
+// Every kernel handles a whole view batch (blockIdx.y = view) and reads the pair count of a view from
+// device memory (point_offsets[P-1]), so the host never has to wait for it.
 #include "common.cuh"
 
 namespace b200splat {
-
-// ============================================================================================
-// K2: single-pass inclusive scan of uint32 with decoupled look-back
-// ============================================================================================
-constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 8;
-constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
-
-constexpr uint64_t FLAG_AGG = 1ull << 32;
-constexpr uint64_t FLAG_INC = 2ull << 32;
 
 __device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p) {
     uint64_t v;
@@ -36,14 +28,34 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
     asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// workspace: [0] ticket counter (u32, padded to 8 B), then one u64 descriptor per tile
+// ============================================================================================
+// K2: single-pass inclusive scan of uint32 with decoupled look-back
+// ============================================================================================
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+constexpr uint64_t FLAG_AGG = 1ull << 32;
+constexpr uint64_t FLAG_INC = 2ull << 32;
+
+struct ScanTab {
+    int V;
+    const uint32_t* in[MAX_VIEWS];
+    uint32_t* out[MAX_VIEWS];
+    uint32_t* ticket[MAX_VIEWS];
+    uint64_t* desc[MAX_VIEWS];
+};
+
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_lookback_kernel(int64_t n, const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t* ticket,
-                     uint64_t* desc) {
+scan_lookback_kernel(int64_t n, const __grid_constant__ ScanTab tab) {
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_warp[SCAN_THREADS / 32];
     __shared__ uint32_t s_excl;
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    const int view = blockIdx.y;
+    const uint32_t* __restrict__ in = tab.in[view];
+    uint32_t* __restrict__ out = tab.out[view];
+    uint64_t* desc = tab.desc[view];
+    if (threadIdx.x == 0) s_tile = atomicAdd(tab.ticket[view], 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
     const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
@@ -128,14 +140,37 @@ size_t scan_workspace_bytes(int64_t n) {
     return align_up(16 + (size_t)tiles * 8, 256);
 }
 
+cudaError_t launch_scan_batch(const BatchTab& tab, cudaStream_t st) {
+    const int64_t n = tab.P;
+    if (n <= 0) return cudaSuccess;
+    const int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    ScanTab s;
+    s.V = tab.V;
+    for (int v = 0; v < tab.V; ++v) {
+        s.in[v] = tab.v[v].tiles_touched;
+        s.out[v] = tab.v[v].point_offsets;
+        s.ticket[v] = tab.v[v].scan_ticket;
+        s.desc[v] = tab.v[v].scan_desc;
+        cudaError_t e = cudaMemsetAsync(tab.v[v].scan_ticket, 0, scan_workspace_bytes(n), st);
+        if (e != cudaSuccess) return e;
+    }
+    scan_lookback_kernel<<<dim3((unsigned)tiles, tab.V), SCAN_THREADS, 0, st>>>(n, s);
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t launch_inclusive_scan(int64_t n, const uint32_t* in, uint32_t* out, void* ws, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
-    int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    const int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     cudaError_t e = cudaMemsetAsync(ws, 0, scan_workspace_bytes(n), st);
     if (e != cudaSuccess) return e;
-    uint32_t* ticket = reinterpret_cast<uint32_t*>(ws);
-    uint64_t* desc = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(ws) + 16);
-    scan_lookback_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(n, in, out, ticket, desc);
+    ScanTab s;
+    s.V = 1;
+    s.in[0] = in;
+    s.out[0] = out;
+    s.ticket[0] = reinterpret_cast<uint32_t*>(ws);
+    s.desc[0] = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(ws) + 16);
+    scan_lookback_kernel<<<dim3((unsigned)tiles, 1), SCAN_THREADS, 0, st>>>(n, s);
     count_launch();
     return cudaGetLastError();
 }
@@ -143,9 +178,6 @@ cudaError_t launch_inclusive_scan(int64_t n, const uint32_t* in, uint32_t* out, 
 // ============================================================================================
 // K4: onesweep LSD radix sort, 8-bit digits, (u64 key, u32 value)
 // ============================================================================================
-constexpr int RADIX_BITS = 8;
-constexpr int RADIX = 1 << RADIX_BITS;
-constexpr int MAX_PASSES = 8;
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_ITEMS = 16;
@@ -155,9 +187,10 @@ constexpr uint32_t DESC_AGG = 1u << 30;
 constexpr uint32_t DESC_INC = 2u << 30;
 constexpr uint32_t DESC_VAL = (1u << 30) - 1;
 
-static inline int64_t sort_tiles(int64_t n) { return (n + SORT_TILE - 1) / SORT_TILE; }
+int sort_tiles_for(int64_t n) { return (int)((n + SORT_TILE - 1) / SORT_TILE); }
 
-// Histogram of every digit place in one read of the keys.  hist: [passes][256] u32 (zeroed).
+// Histogram of every digit place in one read of the keys (stand-alone sort only; the pipeline gets its
+// histograms from duplicateWithKeys).  hist: [passes][256] u32 (zeroed).
 __global__ void __launch_bounds__(256)
 radix_histogram_kernel(int64_t n, int passes, int end_bit, const uint64_t* __restrict__ keys,
                        uint32_t* __restrict__ hist) {
@@ -192,13 +225,30 @@ radix_histogram_kernel(int64_t n, int passes, int end_bit, const uint64_t* __res
     }
 }
 
+struct SortView {
+    const uint32_t* n_ptr;       // device pair count (nullptr: use n_fixed)
+    uint32_t n_fixed;
+    const uint32_t* overflow;    // != nullptr and *overflow != 0: skip (histograms do not describe the data)
+    const uint64_t* keys_in;
+    const uint32_t* vals_in;
+    uint64_t* keys_out;
+    uint32_t* vals_out;
+    const uint32_t* hist_pass;
+    uint32_t* ticket;
+    uint32_t* desc;              // [tiles][256]
+};
+struct SortTab {
+    uint32_t capacity;
+    SortView v[MAX_VIEWS];
+};
+
 struct SortSmem {
     uint64_t keys[SORT_TILE];
     uint32_t vals[SORT_TILE];
     uint32_t warp_hist[SORT_WARPS][RADIX];
     uint32_t local_excl[RADIX];   // exclusive offset of digit inside this tile
     uint32_t bin_offset[RADIX];   // global destination of the tile's first key of digit d, minus local_excl
-    uint32_t warp_tot[SORT_WARPS];
+    uint32_t s_h[SORT_WARPS], s_l[SORT_WARPS];
     uint32_t tile;
 };
 
@@ -206,20 +256,23 @@ struct SortSmem {
 // previous tiles by decoupled look-back, then keys/values are scattered through shared memory so that
 // the global writes are coalesced per digit run.
 __global__ void __launch_bounds__(SORT_THREADS)
-onesweep_pass_kernel(int64_t n, int shift, int bits, const uint64_t* __restrict__ keys_in,
-                     const uint32_t* __restrict__ vals_in, uint64_t* __restrict__ keys_out,
-                     uint32_t* __restrict__ vals_out, const uint32_t* __restrict__ hist_pass, uint32_t* ticket,
-                     uint32_t* desc /* [tiles][256] */, int tiles) {
+onesweep_pass_kernel(int shift, int bits, const __grid_constant__ SortTab tab) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SortSmem& S = *reinterpret_cast<SortSmem*>(smem_raw);
+    const SortView& sv = tab.v[blockIdx.y];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) S.tile = atomicAdd(ticket, 1u);
+    if (sv.overflow != nullptr && *sv.overflow != 0u) return;
+    const int64_t n = sv.n_ptr ? (int64_t)min(*sv.n_ptr, tab.capacity) : (int64_t)sv.n_fixed;
+    if ((int64_t)blockIdx.x * SORT_TILE >= n) return;   // launched over the capacity; tickets only order live CTAs
+    if (tid == 0) S.tile = atomicAdd(sv.ticket, 1u);
     for (int i = tid; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&S.warp_hist[0][0])[i] = 0;
     __syncthreads();
     const uint32_t tile = S.tile;
     const int64_t tile_base = (int64_t)tile * SORT_TILE;
     const int valid = (int)min((int64_t)SORT_TILE, n - tile_base);
     const uint32_t mask = (1u << bits) - 1u;
+    const uint64_t* __restrict__ keys_in = sv.keys_in;
+    const uint32_t* __restrict__ vals_in = sv.vals_in;
 
     // ---- load (warp-striped: item i of lane l in warp w = w*512 + i*32 + l) ------------------
     uint64_t key[SORT_ITEMS];
@@ -260,9 +313,8 @@ onesweep_pass_kernel(int64_t n, int shift, int bits, const uint64_t* __restrict_
         // padding keys (~0) of a partial tile landed in the top digit: not part of the data
         uint32_t pub = bin_total;
         if (d == (int)mask) pub -= (uint32_t)(SORT_TILE - valid);
-        uint32_t* col = desc + d;   // descriptor of tile t for this digit: col[t * RADIX] (coalesced across d)
+        uint32_t* col = sv.desc + d;   // descriptor of tile t for this digit: col[t * RADIX] (coalesced across d)
         uint32_t* my = col + (size_t)tile * RADIX;
-        (void)tiles;
         if (tile == 0) {
             st_volatile_u32(my, DESC_INC | pub);
         } else {
@@ -270,7 +322,7 @@ onesweep_pass_kernel(int64_t n, int shift, int bits, const uint64_t* __restrict_
         }
         // global digit start = exclusive scan of the global histogram of this digit place
         // (block-wide scan of 256 values)
-        uint32_t h = (d <= (int)mask) ? hist_pass[d] : 0u;
+        uint32_t h = (d <= (int)mask) ? sv.hist_pass[d] : 0u;
         uint32_t hinc = h, linc = bin_total;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -281,27 +333,25 @@ onesweep_pass_kernel(int64_t n, int shift, int bits, const uint64_t* __restrict_
                 linc += t2;
             }
         }
-        __shared__ uint32_t s_h[SORT_WARPS], s_l[SORT_WARPS];
         if (lane == 31) {
-            s_h[warp] = hinc;
-            s_l[warp] = linc;
+            S.s_h[warp] = hinc;
+            S.s_l[warp] = linc;
         }
         __syncthreads();
         uint32_t hoff = 0, loff = 0;
 #pragma unroll
         for (int w = 0; w < SORT_WARPS; ++w) {
             if (w < warp) {
-                hoff += s_h[w];
-                loff += s_l[w];
+                hoff += S.s_h[w];
+                loff += S.s_l[w];
             }
         }
         const uint32_t digit_start = hoff + hinc - h;
         const uint32_t lexcl = loff + linc - bin_total;
         uint32_t excl = 0;
         if (tile > 0) {
-            // Decoupled look-back, LOOK predecessor tiles per step: the loads of a
-            // window are independent, so the walk advances LOOK tiles per L2 round trip instead of one
-            // (when a whole wave of CTAs reaches this point together the walk is the pass's critical path).
+            // Decoupled look-back, LOOK predecessor tiles per step: the loads of a window are independent,
+            // so the walk advances LOOK tiles per L2 round trip instead of one.
             constexpr int LOOK = 8;
             int look = (int)tile - 1;
             bool found = false;
@@ -341,6 +391,8 @@ onesweep_pass_kernel(int64_t n, int shift, int bits, const uint64_t* __restrict_
     }
     __syncthreads();
     // ---- coalesced write-out ------------------------------------------------------------------------
+    uint64_t* __restrict__ keys_out = sv.keys_out;
+    uint32_t* __restrict__ vals_out = sv.vals_out;
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; ++i) {
         const int p = i * SORT_THREADS + tid;
@@ -354,32 +406,23 @@ onesweep_pass_kernel(int64_t n, int shift, int bits, const uint64_t* __restrict_
     }
 }
 
-
-// workspace: hist [MAX_PASSES][256] u32 | tickets [MAX_PASSES] u32 (padded) | desc [passes][tiles][256] u32
+// workspace: hist [MAX_PASSES][256] u32 | tickets [64] u32 | desc [passes][tiles][256] u32
 size_t sort_workspace_bytes(int64_t n) {
-    const int64_t tiles = sort_tiles(n < 1 ? 1 : n);
+    const int64_t tiles = sort_tiles_for(n < 1 ? 1 : n);
     return align_up((size_t)MAX_PASSES * RADIX * 4 + 256 + (size_t)MAX_PASSES * tiles * RADIX * 4, 256);
 }
-
-// zero histograms, tickets and descriptors (must precede a fused histogram producer)
-cudaError_t sort_prepare(int64_t n, int end_bit, void* ws, cudaStream_t st) {
-    if (n <= 0) return cudaSuccess;
-    if (end_bit < 1) end_bit = 1;
-    if (end_bit > 64) end_bit = 64;
+size_t sort_workspace_zero_bytes(int64_t capacity, int end_bit) {
     const int passes = (end_bit + RADIX_BITS - 1) / RADIX_BITS;
-    const size_t used = (size_t)MAX_PASSES * RADIX * 4 + 256 + (size_t)passes * sort_tiles(n) * RADIX * 4;
-    return cudaMemsetAsync(ws, 0, used, st);
+    return (size_t)MAX_PASSES * RADIX * 4 + 256 + (size_t)passes * sort_tiles_for(capacity < 1 ? 1 : capacity) * RADIX * 4;
 }
-uint32_t* sort_histogram_ptr(void* ws) { return reinterpret_cast<uint32_t*>(ws); }
+void sort_workspace_views(void* ws, uint32_t** hist, uint32_t** tickets, uint32_t** desc) {
+    uint32_t* h = reinterpret_cast<uint32_t*>(ws);
+    *hist = h;
+    *tickets = h + MAX_PASSES * RADIX;
+    *desc = h + MAX_PASSES * RADIX + 64;
+}
 
-cudaError_t launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_t* vals[2], void* ws, int* sel,
-                              cudaStream_t st, bool hist_ready) {
-    *sel = 0;
-    if (n <= 0) return cudaSuccess;
-    if (end_bit < 1) end_bit = 1;
-    if (end_bit > 64) end_bit = 64;
-    const int passes = (end_bit + RADIX_BITS - 1) / RADIX_BITS;
-    const int64_t tiles = sort_tiles(n);
+static cudaError_t ensure_sort_attr() {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(onesweep_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -387,27 +430,38 @@ cudaError_t launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    cudaError_t e = cudaSuccess;
-    uint32_t* hist = reinterpret_cast<uint32_t*>(ws);
-    uint32_t* tickets = hist + MAX_PASSES * RADIX;
-    uint32_t* desc = tickets + 64;
-    if (!hist_ready) {
-        e = sort_prepare(n, end_bit, ws, st);
-        if (e != cudaSuccess) return e;
-        int64_t hg = (n + 255) / 256;
-        int hgrid = (int)(hg < (int64_t)NUM_SMS * 8 ? hg : (int64_t)NUM_SMS * 8);
-        radix_histogram_kernel<<<hgrid, 256, 0, st>>>(n, passes, end_bit, keys[0], hist);
-        count_launch();
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-    }
+    return cudaSuccess;
+}
+
+cudaError_t launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_t* vals[2], void* ws, int* sel,
+                              cudaStream_t st) {
+    *sel = 0;
+    if (n <= 0) return cudaSuccess;
+    if (end_bit < 1) end_bit = 1;
+    if (end_bit > 64) end_bit = 64;
+    const int passes = (end_bit + RADIX_BITS - 1) / RADIX_BITS;
+    const int tiles = sort_tiles_for(n);
+    cudaError_t e = ensure_sort_attr();
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(ws, 0, sort_workspace_zero_bytes(n, end_bit), st);
+    if (e != cudaSuccess) return e;
+    uint32_t *hist, *tickets, *desc;
+    sort_workspace_views(ws, &hist, &tickets, &desc);
+    int64_t hg = (n + 255) / 256;
+    int hgrid = (int)(hg < (int64_t)NUM_SMS * 8 ? hg : (int64_t)NUM_SMS * 8);
+    radix_histogram_kernel<<<hgrid, 256, 0, st>>>(n, passes, end_bit, keys[0], hist);
+    count_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
     int cur = 0;
     for (int p = 0; p < passes; ++p) {
         const int shift = p * RADIX_BITS;
         const int bits = (end_bit - shift) < RADIX_BITS ? (end_bit - shift) : RADIX_BITS;
-        onesweep_pass_kernel<<<(unsigned)tiles, SORT_THREADS, sizeof(SortSmem), st>>>(
-            n, shift, bits, keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], hist + p * RADIX, tickets + p,
-            desc + (size_t)p * tiles * RADIX, (int)tiles);
+        SortTab t;
+        t.capacity = (uint32_t)n;
+        t.v[0] = SortView{nullptr, (uint32_t)n, nullptr, keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1],
+                          hist + p * RADIX, tickets + p, desc + (size_t)p * tiles * RADIX};
+        onesweep_pass_kernel<<<dim3(tiles, 1), SORT_THREADS, sizeof(SortSmem), st>>>(shift, bits, t);
         count_launch();
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -417,13 +471,46 @@ cudaError_t launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_
     return cudaSuccess;
 }
 
+cudaError_t launch_sort_batch(const BatchTab& tab, cudaStream_t st) {
+    if (tab.P <= 0 || tab.capacity == 0) return cudaSuccess;
+    const int end_bit = tab.end_bit;
+    const int passes = (end_bit + RADIX_BITS - 1) / RADIX_BITS;
+    const int tiles = tab.sort_tiles_cap;
+    cudaError_t e = ensure_sort_attr();
+    if (e != cudaSuccess) return e;
+    int cur = 0;
+    for (int p = 0; p < passes; ++p) {
+        const int shift = p * RADIX_BITS;
+        const int bits = (end_bit - shift) < RADIX_BITS ? (end_bit - shift) : RADIX_BITS;
+        SortTab t;
+        t.capacity = tab.capacity;
+        for (int v = 0; v < tab.V; ++v) {
+            const ViewTab& vt = tab.v[v];
+            t.v[v] = SortView{vt.point_offsets + (tab.P - 1), 0u, vt.status + STATUS_OVERFLOW, vt.keys[cur],
+                              vt.vals[cur], vt.keys[cur ^ 1], vt.vals[cur ^ 1], vt.hist + p * RADIX, vt.tickets + p,
+                              vt.desc + (size_t)p * tiles * RADIX};
+        }
+        onesweep_pass_kernel<<<dim3(tiles, tab.V), SORT_THREADS, sizeof(SortSmem), st>>>(shift, bits, t);
+        count_launch();
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        cur ^= 1;
+    }
+    return cudaSuccess;
+}
+
 // ============================================================================================
-// K5: tile ranges from the sorted keys
+// K5: tile ranges from the sorted keys, and the longest-list-first tile order of the batch
 // ============================================================================================
 __global__ void __launch_bounds__(256)
-tile_ranges_kernel(int64_t R, const uint64_t* __restrict__ keys, uint32_t* __restrict__ ranges) {
+tile_ranges_kernel(const __grid_constant__ BatchTab tab, int sel) {
+    const ViewTab& vt = tab.v[blockIdx.y];
+    if (vt.status[STATUS_OVERFLOW] != 0u) return;
+    const int64_t R = (int64_t)min(vt.point_offsets[tab.P - 1], tab.capacity);
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= R) return;
+    const uint64_t* __restrict__ keys = vt.keys[sel];
+    uint32_t* __restrict__ ranges = vt.ranges;
     const uint32_t t = (uint32_t)(keys[i] >> 32);
     if (i == 0) {
         ranges[2 * t] = 0;
@@ -437,33 +524,25 @@ tile_ranges_kernel(int64_t R, const uint64_t* __restrict__ keys, uint32_t* __res
     if (i == R - 1) ranges[2 * t + 1] = (uint32_t)R;
 }
 
-cudaError_t launch_tile_ranges(int64_t R, int T, const uint64_t* keys_sorted, uint32_t* ranges, cudaStream_t st) {
-    cudaError_t e = cudaMemsetAsync(ranges, 0, (size_t)T * 8, st);
-    if (e != cudaSuccess || R <= 0) return e;
-    tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, keys_sorted, ranges);
-    count_launch();
-    return cudaGetLastError();
-}
-
-// ============================================================================================
-// Longest-list-first tile order for the render kernels (LPT scheduling): order[i] = tile with the i-th
-// longest Gaussian list.  One CTA, bitonic sort of (length << 32 | ~tile) in shared memory.
-// ============================================================================================
+// order[i] = (view * T + tile) with the i-th longest Gaussian list of the batch (LPT scheduling of the
+// render CTAs).  One CTA, bitonic sort of (length << 32 | ~entry) in shared memory.
 __global__ void __launch_bounds__(1024)
-tile_order_kernel(int T, int Tpow2, const uint32_t* __restrict__ ranges, uint32_t* __restrict__ order) {
+tile_order_kernel(const __grid_constant__ BatchTab tab, int n, int npow2) {
     extern __shared__ unsigned long long s_key[];
-    for (int i = threadIdx.x; i < Tpow2; i += blockDim.x) {
+    const int T = tab.grid_x * tab.grid_y;
+    for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
         unsigned long long k = 0ull;   // padding sorts last (descending order)
-        if (i < T) {
-            const uint32_t len = ranges[2 * i + 1] - ranges[2 * i];
+        if (i < n) {
+            const uint32_t* r = tab.v[i / T].ranges + 2 * (i % T);
+            const uint32_t len = r[1] - r[0];
             k = ((unsigned long long)len << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
         }
         s_key[i] = k;
     }
     __syncthreads();
-    for (int size = 2; size <= Tpow2; size <<= 1) {
+    for (int size = 2; size <= npow2; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int i = threadIdx.x; i < Tpow2 / 2; i += blockDim.x) {
+            for (int i = threadIdx.x; i < npow2 / 2; i += blockDim.x) {
                 const int lo = 2 * i - (i & (stride - 1));   // index with bit `stride` cleared
                 const int hi = lo + stride;
                 const bool desc = (lo & size) == 0;          // descending blocks first -> overall descending
@@ -476,20 +555,34 @@ tile_order_kernel(int T, int Tpow2, const uint32_t* __restrict__ ranges, uint32_
             __syncthreads();
         }
     }
-    for (int i = threadIdx.x; i < T; i += blockDim.x) order[i] = 0xffffffffu - (uint32_t)(s_key[i] & 0xffffffffull);
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        tab.tile_order[i] = 0xffffffffu - (uint32_t)(s_key[i] & 0xffffffffull);
 }
 
-__global__ void tile_order_identity_kernel(int T, uint32_t* __restrict__ order) {
+__global__ void tile_order_identity_kernel(int n, uint32_t* __restrict__ order) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < T) order[i] = (uint32_t)i;
+    if (i < n) order[i] = (uint32_t)i;
 }
 
-cudaError_t launch_tile_order(int T, const uint32_t* ranges, uint32_t* order, cudaStream_t st) {
+cudaError_t launch_tile_ranges_batch(const BatchTab& tab, int sel, cudaStream_t st) {
+    const int T = tab.grid_x * tab.grid_y;
+    for (int v = 0; v < tab.V; ++v) {
+        cudaError_t e = cudaMemsetAsync(tab.v[v].ranges, 0, (size_t)T * 8, st);
+        if (e != cudaSuccess) return e;
+    }
+    if (tab.P > 0 && tab.capacity > 0) {
+        const unsigned gx = (unsigned)(((int64_t)tab.capacity + 255) / 256);
+        tile_ranges_kernel<<<dim3(gx, tab.V), 256, 0, st>>>(tab, sel);
+        count_launch();
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    const int n = tab.V * T;
     int p2 = 1;
-    while (p2 < T) p2 <<= 1;
+    while (p2 < n) p2 <<= 1;
     const size_t smem = (size_t)p2 * 8;
-    if (smem > 200 * 1024) {   // > 25600 tiles: keep raster order
-        tile_order_identity_kernel<<<(T + 255) / 256, 256, 0, st>>>(T, order);
+    if (smem > 200 * 1024) {   // > 25600 tiles in the batch: keep raster order
+        tile_order_identity_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, tab.tile_order);
         count_launch();
         return cudaGetLastError();
     }
@@ -499,7 +592,7 @@ cudaError_t launch_tile_order(int T, const uint32_t* ranges, uint32_t* order, cu
         if (e != cudaSuccess) return e;
         attr = smem;
     }
-    tile_order_kernel<<<1, 1024, smem, st>>>(T, p2, ranges, order);
+    tile_order_kernel<<<1, 1024, smem, st>>>(tab, n, p2);
     count_launch();
     return cudaGetLastError();
 }
