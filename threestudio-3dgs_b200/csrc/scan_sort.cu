@@ -255,7 +255,7 @@ struct SortSmem {
 // One pass: tile t of the input is ranked locally (stable), its per-digit counts are chained to the
 // previous tiles by decoupled look-back, then keys/values are scattered through shared memory so that
 // the global writes are coalesced per digit run.
-__global__ void __launch_bounds__(SORT_THREADS)
+__global__ void __launch_bounds__(SORT_THREADS, 3)
 onesweep_pass_kernel(int shift, int bits, const __grid_constant__ SortTab tab) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SortSmem& S = *reinterpret_cast<SortSmem*>(smem_raw);
@@ -284,21 +284,26 @@ onesweep_pass_kernel(int shift, int bits, const __grid_constant__ SortTab tab) {
         key[i] = (li < valid) ? __ldg(keys_in + tile_base + li) : ~0ull;
     }
     // ---- warp-level stable ranking -------------------------------------------------------------
+    // All 16 match.any are independent; the per-digit running count of the warp is advanced with one
+    // shared-memory atomic per (item, digit group) issued by the group's first lane.  Items are issued in
+    // order (the __syncwarp keeps the atomics of successive items ordered), but nothing waits for an
+    // atomic's return value until all have been issued, so the latencies overlap.
     const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t info[SORT_ITEMS];   // leader lane | rank inside the digit group << 8
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; ++i) {
         const uint32_t d = (uint32_t)(key[i] >> shift) & mask;
         const uint32_t peers = __match_any_sync(0xffffffffu, d);
         const int leader = __ffs(peers) - 1;
         uint32_t pre = 0;
-        if (lane == leader) {
-            pre = S.warp_hist[warp][d];
-            S.warp_hist[warp][d] = pre + __popc(peers);
-        }
-        pre = __shfl_sync(0xffffffffu, pre, leader);
-        rank[i] = pre + __popc(peers & lt_mask);
+        if (lane == leader) pre = atomicAdd(&S.warp_hist[warp][d], (uint32_t)__popc(peers));
+        rank[i] = pre;
+        info[i] = (uint32_t)leader | ((uint32_t)__popc(peers & lt_mask) << 8);
         __syncwarp();
     }
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i)
+        rank[i] = __shfl_sync(0xffffffffu, rank[i], (int)(info[i] & 31u)) + (info[i] >> 8);
     __syncthreads();
     // ---- per-digit: exclusive prefix over warps, tile total, look-back --------------------------
     uint32_t bin_total = 0;
