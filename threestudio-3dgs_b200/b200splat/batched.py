@@ -242,3 +242,113 @@ def render_views_fwd_bwd(cams: Sequence[ops.Cam], means3D, shs, colors_precomp, 
         if keep_images:
             images.append((color, depth, alpha, radii))
     return images
+
+
+# ------------------------------------------------------------------------------------------------------
+# autograd surface of the batched path: the operator a GaussianBatchRenderer-style caller uses instead of
+# a Python loop over single-view GaussianRasterizer calls (renderer/gaussian_batch_renderer.py:21-54)
+# ------------------------------------------------------------------------------------------------------
+class _RasterizeViews(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, owner, cams, means3D, means2D, shs, colors_precomp, opacities, scales, rotations):
+        ws = owner.ws
+        V, P, H, W = ws.V, ws.P, ws.H, ws.W
+        dev = means3D.device
+        f = ops._f32c
+        m3, sh_, cp_, op_ = f(means3D, "means3D"), f(shs, "shs"), f(colors_precomp, "colors_precomp"), \
+            f(opacities, "opacities")
+        sc_, ro_ = f(scales, "scales"), f(rotations, "rotations")
+        # fresh outputs every call (callers write into them in place); the workspace only lends scratch
+        color = torch.empty(V, 3, H, W, dtype=torch.float32, device=dev)
+        depth = torch.empty(V, 1, H, W, dtype=torch.float32, device=dev)
+        alpha = torch.empty(V, 1, H, W, dtype=torch.float32, device=dev)
+        radii = torch.empty(V, P, dtype=torch.int32, device=dev)
+        ws.color, ws.depth, ws.alpha = list(color.unbind(0)), list(depth.unbind(0)), list(alpha.unbind(0))
+        ws.radii = list(radii.unbind(0))
+        if not owner.calibrated:
+            owner.calibrate(cams, m3, sh_, cp_, op_, sc_, ro_)
+        else:
+            forward_batched(ws, cams, m3, sh_, cp_, op_, sc_, ro_, sync=False)
+        owner.generation += 1
+        ctx.owner, ctx.cams, ctx.generation = owner, cams, owner.generation
+        ctx.has = (sh_ is not None, cp_ is not None)
+        e = lambda t: t if t is not None else torch.empty(0, device=dev)
+        ctx.save_for_backward(m3, e(sh_), e(cp_), op_, sc_, ro_)
+        ctx.mark_non_differentiable(radii)
+        return color, radii, depth, alpha
+
+    @staticmethod
+    def backward(ctx, g_color, g_radii, g_depth, g_alpha):
+        owner = ctx.owner
+        if ctx.generation != owner.generation:
+            raise RuntimeError("ViewBatchRasterizer: the workspace was reused by a later forward before this "
+                               "backward ran; use one ViewBatchRasterizer per live graph")
+        ws = owner.ws
+        m3, sh_, cp_, op_, sc_, ro_ = ctx.saved_tensors
+        has_sh, has_cp = ctx.has
+        sh_ = sh_ if has_sh else None
+        cp_ = cp_ if has_cp else None
+        V, P = ws.V, ws.P
+        dev = m3.device
+        new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        out = {"means3D": new(P, 3), "opacities": new(P, 1), "scales": new(P, 3), "rotations": new(P, 4)}
+        if has_sh:
+            out["shs"] = new(P, sh_.shape[1], 3)
+        if has_cp:
+            out["colors_precomp"] = new(P, 3)
+        m2 = new(V, P, 3)
+        g = lambda t: None if t is None else ops._f32c(t, "grad")
+        gc, gd, ga = g(g_color), g(g_depth), g(g_alpha)
+        pgs = [(None if gc is None else gc[v], None if gd is None else gd[v], None if ga is None else ga[v])
+               for v in range(V)]
+        backward_batched(ws, ctx.cams, m3, sh_, cp_, op_, sc_, ro_, pgs, out, accumulate=False,
+                         means2D_out=list(m2.unbind(0)))
+        return (None, None, out["means3D"], m2, out.get("shs"), out.get("colors_precomp"), out["opacities"],
+                out["scales"], out["rotations"])
+
+
+class ViewBatchRasterizer(torch.nn.Module):
+    """Batched counterpart of ``GaussianRasterizer``: ``forward(raster_settings_list, means3D, means2D (V,P,3),
+    opacities, shs=None, colors_precomp=None, scales=, rotations=)`` -> ``(color (V,3,H,W), radii (V,P) int32,
+    depth (V,1,H,W), alpha (V,1,H,W))`` with autograd; ``means2D.grad[v]`` is view v's NDC gradient, exactly what
+    the per-view call would have produced (geometry/gaussian_base.py:815-819 reads it per view).  Holds the
+    persistent device workspace of the batch; one instance per concurrently live autograd graph."""
+
+    def __init__(self, views: int, P: int, H: int, W: int, device="cuda"):
+        super().__init__()
+        assert views <= MAX_VIEWS, f"at most {MAX_VIEWS} views per batch call"
+        self.ws = BatchWorkspace(views, P, H, W, torch.device(device))
+        self.calibrated = False
+        self.generation = 0
+
+    def calibrate(self, cams, means3D, shs, colors_precomp, opacities, scales, rotations, headroom: float = 1.25):
+        ws = self.ws
+        while True:
+            nr, ov = forward_batched(ws, cams, means3D, shs, colors_precomp, opacities, scales, rotations, sync=True)
+            need = int(max(nr) * headroom) + 4096
+            if any(ov) or ws.capacity < need:
+                ws._alloc_binning(max(need, 2 * ws.capacity) if any(ov) else need)
+                continue
+            break
+        self.calibrated = True
+
+    def check_overflow(self) -> bool:
+        """One small device read; True (and re-calibration scheduled) if a view outgrew its binning capacity."""
+        ws = self.ws
+        flags = [ops.status_tensor(ws.H, ws.W, st) for st in ws.states(0)]
+        bad = bool(torch.stack(flags)[:, 0].any().item())
+        if bad:
+            self.calibrated = False
+        return bad
+
+    def forward(self, raster_settings, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None,
+                rotations=None):
+        if (shs is None) == (colors_precomp is None):
+            raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+        if scales is None or rotations is None:
+            raise Exception("The batched rasterizer needs the scale/rotation pair")
+        ws = self.ws
+        if means3D.shape[0] != ws.P:
+            raise RuntimeError("number of Gaussians changed (densify/prune): build a new ViewBatchRasterizer")
+        cams = [ops.make_cam(rs, means3D.device) for rs in raster_settings]
+        return _RasterizeViews.apply(self, cams, means3D, means2D, shs, colors_precomp, opacities, scales, rotations)
