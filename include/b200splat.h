@@ -273,6 +273,9 @@ typedef struct b200splat_forward_views {
     const uint32_t* n_contrib;
     const uint32_t* n_visited;
     const uint32_t* status; /* [0] != 0: binning capacity overflow */
+    /* > 0: the sort ran on packed words -- keys_sorted[i] holds (key << packed_idx_bits) | gaussian_index and
+     * point_list is unused; 0: keys_sorted / point_list are the plain sorted pair arrays */
+    int64_t packed_idx_bits;
 } b200splat_forward_views;
 
 int b200splat_forward_views_get(int32_t P, int32_t H, int32_t W, int64_t num_rendered,

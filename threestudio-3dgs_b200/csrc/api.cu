@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -95,6 +96,7 @@ size_t image_layout(int H, int W, void* base, ImageViews* v) {
     im.n_visited = carve<uint32_t>(p, (size_t)H * W);
     im.tile_order = carve<uint32_t>(p, (size_t)gx * gy * MAX_VIEWS);
     im.status = carve<uint32_t>(p, STATUS_WORDS);
+    im.tile_count = carve<uint32_t>(p, (size_t)gx * gy);
     if (v) *v = im;
     return (size_t)(p - p0);
 }
@@ -145,6 +147,11 @@ static int init_table(const b200splat_camera& c, int P, int M, bool has_sh, Batc
     }
     tab->sh_degree = deg;
     tab->end_bit = 32 + higher_msb((uint32_t)(tab->grid_x * tab->grid_y));
+    // pack the Gaussian index into the key word when both fit in 64 bits (B200SPLAT_SORT=pairs disables)
+    int ib = 1;
+    while (ib < 32 && (1ll << ib) < (long long)(P > 1 ? P : 2)) ++ib;
+    static const bool pairs_only = [] { const char* e = getenv("B200SPLAT_SORT"); return e && strcmp(e, "pairs") == 0; }();
+    tab->idx_bits = (!pairs_only && tab->end_bit + ib <= 64) ? ib : 0;
     return B200SPLAT_OK;
 }
 
@@ -176,6 +183,7 @@ static void fill_image(int H, int W, void* image, ViewTab* vt, uint32_t** tile_o
     image_layout(H, W, image, &im);
     vt->ranges = im.ranges, vt->n_contrib = im.n_contrib, vt->n_visited = im.n_visited, vt->final_T = im.final_T;
     vt->status = im.status;
+    vt->tile_count = im.tile_count;
     if (tile_order) *tile_order = im.tile_order;
 }
 
@@ -254,8 +262,10 @@ static int forward_tail(BatchTab& tab, int debug, cudaStream_t st) {
     if (tab.P > 0 && tab.capacity > 0) {
         tab.sort_tiles_cap = sort_tiles_for(tab.capacity);
         { ProfScope ps(2, st);
-        for (int v = 0; v < tab.V; ++v)
+        for (int v = 0; v < tab.V; ++v) {
             CU(cudaMemsetAsync(tab.v[v].hist, 0, sort_workspace_zero_bytes(tab.capacity, tab.end_bit), st));
+            CU(cudaMemsetAsync(tab.v[v].tile_count, 0, (size_t)T * sizeof(uint32_t), st));
+        }
         CU(launch_duplicate(tab, st)); }
         DEBUG_SYNC(dbg, st, "duplicateWithKeys");
         { ProfScope ps(3, st);
@@ -575,6 +585,10 @@ int b200splat_forward_views_get(int32_t P, int32_t H, int32_t W, int64_t num_ren
         const int sel = sorted_sel_for(gx * gy);
         out->keys_sorted = b.keys[sel];
         out->point_list = b.vals[sel];
+        BatchTab t;
+        b200splat_camera c{};
+        c.image_height = H, c.image_width = W;
+        if (init_table(c, P, 0, false, &t) == B200SPLAT_OK) out->packed_idx_bits = t.idx_bits;
     }
     if (image_buffer) {
         ImageViews im;

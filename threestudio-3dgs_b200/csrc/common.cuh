@@ -73,6 +73,7 @@ struct ViewTab {
     uint32_t* n_visited;
     float* final_T;
     uint32_t* status;
+    uint32_t* tile_count;  // [T] pairs per tile, accumulated by duplicateWithKeys (ranges = its exclusive scan)
     float* out_color;
     float* out_depth;
     float* out_alpha;
@@ -92,6 +93,7 @@ struct BatchTab {
     uint32_t capacity;         // pairs each view's key/value arrays can hold
     int end_bit;               // sorted key bits [0, end_bit)
     int sort_tiles_cap;        // ceil(capacity / SORT_TILE)
+    int idx_bits;              // > 0: key and Gaussian index packed in ONE u64 (key << idx_bits | idx), no value arrays
     uint32_t* tile_order;      // [V * T] entries (view * T + tile), longest list first
     ViewTab v[MAX_VIEWS];
 };
@@ -119,6 +121,7 @@ struct ImageViews {
     uint32_t* n_visited;     // H * W  (list entries traversed by the pixel in forward)
     uint32_t* tile_order;    // MAX_VIEWS * T (a batch uses view 0's copy)
     uint32_t* status;        // STATUS_WORDS
+    uint32_t* tile_count;    // T
 };
 
 size_t geom_layout(int P, void* base, GeomViews* v);

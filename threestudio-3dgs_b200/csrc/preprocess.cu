@@ -257,54 +257,98 @@ preprocess_kernel(const __grid_constant__ BatchTab tab, const float* __restrict_
 // all keys of one Gaussian share their low 32 bits, so the four depth digits cost one weighted shared-memory
 // atomic per Gaussian instead of one per key, and the separate histogram read of the key array disappears.
 // blockIdx.y = view.  Pairs beyond the binning capacity are dropped and flagged (STATUS_OVERFLOW).
+// When tab.idx_bits > 0 the Gaussian index rides in the low bits of the same 64-bit word (no value array):
+// one third less sort traffic; the sort then works on bits [idx_bits, idx_bits + end_bit).
+constexpr int DUP_MAX_TILES = 8192;   // tile histogram kept in shared memory up to this many tiles
 __global__ void __launch_bounds__(256)
 duplicate_kernel(const __grid_constant__ BatchTab tab) {
-    __shared__ uint32_t s_hist[MAX_PASSES * 256];
+    extern __shared__ uint32_t s_dyn[];   // [passes*256] digit histograms | [T] tile histogram (if it fits)
     const ViewTab& vt = tab.v[blockIdx.y];
     const int end_bit = tab.end_bit;
     const int passes = (end_bit + 7) / 8;
     const int gx = tab.grid_x, gy = tab.grid_y;
-    for (int i = threadIdx.x; i < passes * 256; i += blockDim.x) s_hist[i] = 0;
+    const int T = gx * gy;
+    const bool tile_hist = T <= DUP_MAX_TILES;
+    const int idx_bits = tab.idx_bits;
+    uint32_t* s_hist = s_dyn;
+    uint32_t* s_tile = s_dyn + passes * 256;
+    for (int i = threadIdx.x; i < passes * 256 + (tile_hist ? T : 0); i += blockDim.x) s_dyn[i] = 0;
     __syncthreads();
     const int32_t* __restrict__ radii = vt.radii;
     const uint32_t* __restrict__ point_offsets = vt.point_offsets;
     uint64_t* __restrict__ keys = vt.keys[0];
     uint32_t* __restrict__ vals = vt.vals[0];
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < tab.P; idx += gridDim.x * blockDim.x) {
-        const int rad = radii[idx];
-        if (rad <= 0) continue;
-        uint32_t off = (idx == 0) ? 0u : point_offsets[idx - 1];
-        const float2 xy = *reinterpret_cast<const float2*>(vt.rec + (size_t)idx * REC_FLOATS);
-        int x0, y0, x1, y1;
-        get_rect(xy.x, xy.y, (float)rad, gx, gy, x0, y0, x1, y1);
-        const uint32_t d32 = __float_as_uint(vt.depths[idx]);
-        const uint64_t dbits = (uint64_t)d32;
-        const uint32_t ntiles = (uint32_t)((x1 - x0) * (y1 - y0));
-        if (off + ntiles > tab.capacity) {
-            atomicOr(vt.status + STATUS_OVERFLOW, 1u);
-            continue;
+    const int lane = threadIdx.x & 31;
+    const int P_round = (tab.P + 31) / 32 * 32;   // warps stay converged for the votes below
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < P_round; idx += gridDim.x * blockDim.x) {
+        const int rad = idx < tab.P ? radii[idx] : 0;
+        bool live = rad > 0;
+        uint32_t off = 0, d32 = 0, ntiles = 0;
+        int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+        if (live) {
+            off = (idx == 0) ? 0u : point_offsets[idx - 1];
+            const float2 xy = *reinterpret_cast<const float2*>(vt.rec + (size_t)idx * REC_FLOATS);
+            get_rect(xy.x, xy.y, (float)rad, gx, gy, x0, y0, x1, y1);
+            d32 = __float_as_uint(vt.depths[idx]);
+            ntiles = (uint32_t)((x1 - x0) * (y1 - y0));
+            if (off + ntiles > tab.capacity) {
+                atomicOr(vt.status + STATUS_OVERFLOW, 1u);
+                live = false;
+            }
         }
+        const uint64_t dbits = (uint64_t)d32;
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
             if (p < passes) {
                 const int bits = min(8, end_bit - 8 * p);
-                atomicAdd(&s_hist[p * 256 + ((d32 >> (8 * p)) & ((1u << bits) - 1u))], ntiles);
+                const uint32_t dig = (d32 >> (8 * p)) & ((1u << bits) - 1u);
+                if (p < 3) {
+                    if (live) atomicAdd(&s_hist[p * 256 + dig], ntiles);   // mantissa bytes: spread addresses
+                } else {
+                    // the exponent byte takes a handful of values: aggregate the warp's lanes per digit first
+                    const uint32_t peers = __match_any_sync(0xffffffffu, live ? dig : 0xffffffffu);
+                    const uint32_t total = __reduce_add_sync(peers, live ? ntiles : 0u);
+                    if (live && lane == __ffs(peers) - 1) atomicAdd(&s_hist[p * 256 + dig], total);
+                }
             }
         }
+        if (!live) continue;
         for (int ty = y0; ty < y1; ++ty) {
             for (int tx = x0; tx < x1; ++tx) {
                 const uint32_t tile = (uint32_t)(ty * gx + tx);
-                keys[off] = ((uint64_t)tile << 32) | dbits;
-                vals[off] = (uint32_t)idx;
+                const uint64_t key = ((uint64_t)tile << 32) | dbits;
+                if (idx_bits) {
+                    keys[off] = (key << idx_bits) | (uint64_t)(uint32_t)idx;
+                } else {
+                    keys[off] = key;
+                    vals[off] = (uint32_t)idx;
+                }
                 ++off;
-                for (int p = 4; p < passes; ++p) {
-                    const int bits = min(8, end_bit - 8 * p);
-                    atomicAdd(&s_hist[p * 256 + ((tile >> (8 * (p - 4))) & ((1u << bits) - 1u))], 1u);
+                if (tile_hist) {
+                    atomicAdd(&s_tile[tile], 1u);   // digit histograms of the tile bytes are derived at flush time
+                } else {
+                    for (int p = 4; p < passes; ++p) {
+                        const int bits = min(8, end_bit - 8 * p);
+                        atomicAdd(&s_hist[p * 256 + ((tile >> (8 * (p - 4))) & ((1u << bits) - 1u))], 1u);
+                    }
                 }
             }
         }
     }
     __syncthreads();
+    if (tile_hist) {
+        for (int t = threadIdx.x; t < T; t += blockDim.x) {
+            const uint32_t c = s_tile[t];
+            if (c) {
+                atomicAdd(&vt.tile_count[t], c);
+                for (int p = 4; p < passes; ++p) {
+                    const int bits = min(8, end_bit - 8 * p);
+                    atomicAdd(&s_hist[p * 256 + (((uint32_t)t >> (8 * (p - 4))) & ((1u << bits) - 1u))], c);
+                }
+            }
+        }
+        __syncthreads();
+    }
     for (int i = threadIdx.x; i < passes * 256; i += blockDim.x) {
         const uint32_t c = s_hist[i];
         if (c) atomicAdd(&vt.hist[i], c);
@@ -342,8 +386,18 @@ cudaError_t launch_preprocess(const BatchTab& tab, const float* means3D, const f
 
 cudaError_t launch_duplicate(const BatchTab& tab, cudaStream_t st) {
     if (tab.P <= 0) return cudaSuccess;
+    const int T = tab.grid_x * tab.grid_y;
+    const int passes = (tab.end_bit + 7) / 8;
+    const size_t smem = ((size_t)passes * 256 + (T <= DUP_MAX_TILES ? T : 0)) * sizeof(uint32_t);
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(duplicate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr = smem;
+    }
+    // few, fat CTAs: every CTA flushes its histograms with global atomics
     const int bx = min((tab.P + 255) / 256, max(1, NUM_SMS * 8 / tab.V));
-    duplicate_kernel<<<dim3(bx, tab.V), 256, 0, st>>>(tab);
+    duplicate_kernel<<<dim3(bx, tab.V), 256, smem, st>>>(tab);
     count_launch();
     return cudaGetLastError();
 }

@@ -77,12 +77,21 @@ __device__ __forceinline__ void thread_pixel(int& lx, int& ly) {
     ly = (warp >> 1) * 4 + (lane >> 3);
 }
 
+struct PointList {   // sorted list: packed words (key << idx_bits | idx) or a plain index array
+    const uint64_t* words;
+    const uint32_t* vals;
+    uint32_t mask;
+    __device__ __forceinline__ uint32_t at(int64_t pos) const {
+        return words ? (uint32_t)(__ldg(words + pos)) & mask : __ldg(vals + pos);
+    }
+};
+
 // stage one batch: thread t gathers the record of list entry `pos` into buf[t]
 template <bool BULK>
 __device__ __forceinline__ void stage_batch(float4* buf, uint32_t* ids, uint64_t* bar, const float* __restrict__ rec,
-                                            const uint32_t* __restrict__ point_list, int64_t pos, bool valid) {
+                                            const PointList point_list, int64_t pos, bool valid) {
     if (valid) {
-        const uint32_t id = __ldg(point_list + pos);
+        const uint32_t id = point_list.at(pos);
         if (ids) ids[threadIdx.x] = id;
         const float* src = rec + (size_t)id * REC_FLOATS;
         float4* dst = buf + 3 * threadIdx.x;
@@ -140,7 +149,8 @@ render_forward_kernel(const __grid_constant__ BatchTab tab, int sel) {
     const int tile = (int)(entry % n_tiles);
     const int tile_x = tile % grid_x, tile_y = tile / grid_x;
     const uint32_t* __restrict__ ranges = vt.ranges;
-    const uint32_t* __restrict__ point_list = vt.vals[sel];
+    const PointList point_list{tab.idx_bits ? vt.keys[sel] : nullptr, vt.vals[sel],
+                               tab.idx_bits ? (uint32_t)((1ull << tab.idx_bits) - 1ull) : 0xffffffffu};
     const float* __restrict__ rec = vt.rec;
     const float* __restrict__ bg = vt.bg;
     uint32_t* __restrict__ n_contrib = vt.n_contrib;
@@ -347,7 +357,8 @@ render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
     const int tile = (int)(entry % n_tiles);
     const int tile_x = tile % grid_x, tile_y = tile / grid_x;
     const uint32_t* __restrict__ ranges = vt.ranges;
-    const uint32_t* __restrict__ point_list = vt.vals[sel];
+    const PointList point_list{tab.idx_bits ? vt.keys[sel] : nullptr, vt.vals[sel],
+                               tab.idx_bits ? (uint32_t)((1ull << tab.idx_bits) - 1ull) : 0xffffffffu};
     const float* __restrict__ rec = vt.rec;
     const float* __restrict__ bg = vt.bg;
     const uint32_t* __restrict__ n_contrib = vt.n_contrib;

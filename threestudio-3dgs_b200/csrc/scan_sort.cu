@@ -9,6 +9,9 @@
 // device memory (point_offsets[P-1]), so the host never has to wait for it.
 #include "common.cuh"
 
+#include <cstddef>
+#include <cstdlib>
+
 namespace b200splat {
 
 __device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p) {
@@ -244,18 +247,20 @@ struct SortTab {
 
 struct SortSmem {
     uint64_t keys[SORT_TILE];
-    uint32_t vals[SORT_TILE];
     uint32_t warp_hist[SORT_WARPS][RADIX];
     uint32_t local_excl[RADIX];   // exclusive offset of digit inside this tile
     uint32_t bin_offset[RADIX];   // global destination of the tile's first key of digit d, minus local_excl
     uint32_t s_h[SORT_WARPS], s_l[SORT_WARPS];
     uint32_t tile;
+    uint32_t pad[3];
+    uint32_t vals[SORT_TILE];     // last: keys-only passes do not allocate it
 };
 
 // One pass: tile t of the input is ranked locally (stable), its per-digit counts are chained to the
 // previous tiles by decoupled look-back, then keys/values are scattered through shared memory so that
 // the global writes are coalesced per digit run.
-__global__ void __launch_bounds__(SORT_THREADS, 3)
+template <bool HAS_VALS, int MINB>
+__global__ void __launch_bounds__(SORT_THREADS, MINB)
 onesweep_pass_kernel(int shift, int bits, const __grid_constant__ SortTab tab) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SortSmem& S = *reinterpret_cast<SortSmem*>(smem_raw);
@@ -389,10 +394,12 @@ onesweep_pass_kernel(int shift, int bits, const __grid_constant__ SortTab tab) {
         rank[i] += S.local_excl[d] + S.warp_hist[warp][d];
         S.keys[rank[i]] = key[i];
     }
+    if (HAS_VALS) {
 #pragma unroll
-    for (int i = 0; i < SORT_ITEMS; ++i) {
-        const int li = wbase + i * 32;
-        if (li < valid) S.vals[rank[i]] = __ldg(vals_in + tile_base + li);
+        for (int i = 0; i < SORT_ITEMS; ++i) {
+            const int li = wbase + i * 32;
+            if (li < valid) S.vals[rank[i]] = __ldg(vals_in + tile_base + li);
+        }
     }
     __syncthreads();
     // ---- coalesced write-out ------------------------------------------------------------------------
@@ -406,7 +413,7 @@ onesweep_pass_kernel(int shift, int bits, const __grid_constant__ SortTab tab) {
             const uint32_t d = (uint32_t)(k >> shift) & mask;
             const uint32_t dst = S.bin_offset[d] + (uint32_t)p;
             keys_out[dst] = k;
-            vals_out[dst] = S.vals[p];
+            if (HAS_VALS) vals_out[dst] = S.vals[p];
         }
     }
 }
@@ -427,11 +434,20 @@ void sort_workspace_views(void* ws, uint32_t** hist, uint32_t** tickets, uint32_
     *desc = h + MAX_PASSES * RADIX + 64;
 }
 
+// keys-only passes do not touch SortSmem::vals: leave it out of the dynamic allocation (more CTAs per SM)
+constexpr size_t SORT_SMEM_KEYS_ONLY = offsetof(SortSmem, vals);
+
 static cudaError_t ensure_sort_attr() {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(onesweep_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(onesweep_pass_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)sizeof(SortSmem));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(onesweep_pass_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(SortSmem));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(onesweep_pass_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(SortSmem));
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -466,7 +482,7 @@ cudaError_t launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_
         t.capacity = (uint32_t)n;
         t.v[0] = SortView{nullptr, (uint32_t)n, nullptr, keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1],
                           hist + p * RADIX, tickets + p, desc + (size_t)p * tiles * RADIX};
-        onesweep_pass_kernel<<<dim3(tiles, 1), SORT_THREADS, sizeof(SortSmem), st>>>(shift, bits, t);
+        onesweep_pass_kernel<true, 3><<<dim3(tiles, 1), SORT_THREADS, sizeof(SortSmem), st>>>(shift, bits, t);
         count_launch();
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -495,7 +511,15 @@ cudaError_t launch_sort_batch(const BatchTab& tab, cudaStream_t st) {
                               vt.vals[cur], vt.keys[cur ^ 1], vt.vals[cur ^ 1], vt.hist + p * RADIX, vt.tickets + p,
                               vt.desc + (size_t)p * tiles * RADIX};
         }
-        onesweep_pass_kernel<<<dim3(tiles, tab.V), SORT_THREADS, sizeof(SortSmem), st>>>(shift, bits, t);
+        static const int occ = [] { const char* e = getenv("B200SPLAT_SORT_OCC"); return e ? atoi(e) : 3; }();
+        if (tab.idx_bits > 0 && occ == 4)
+            onesweep_pass_kernel<false, 4><<<dim3(tiles, tab.V), SORT_THREADS, SORT_SMEM_KEYS_ONLY, st>>>(
+                shift + tab.idx_bits, bits, t);
+        else if (tab.idx_bits > 0)
+            onesweep_pass_kernel<false, 3><<<dim3(tiles, tab.V), SORT_THREADS, SORT_SMEM_KEYS_ONLY, st>>>(
+                shift + tab.idx_bits, bits, t);
+        else
+            onesweep_pass_kernel<true, 3><<<dim3(tiles, tab.V), SORT_THREADS, sizeof(SortSmem), st>>>(shift, bits, t);
         count_launch();
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -516,11 +540,12 @@ tile_ranges_kernel(const __grid_constant__ BatchTab tab, int sel) {
     if (i >= R) return;
     const uint64_t* __restrict__ keys = vt.keys[sel];
     uint32_t* __restrict__ ranges = vt.ranges;
-    const uint32_t t = (uint32_t)(keys[i] >> 32);
+    const int tshift = 32 + tab.idx_bits;
+    const uint32_t t = (uint32_t)(keys[i] >> tshift);
     if (i == 0) {
         ranges[2 * t] = 0;
     } else {
-        const uint32_t tp = (uint32_t)(keys[i - 1] >> 32);
+        const uint32_t tp = (uint32_t)(keys[i - 1] >> tshift);
         if (tp != t) {
             ranges[2 * tp + 1] = (uint32_t)i;
             ranges[2 * t] = (uint32_t)i;
@@ -529,75 +554,119 @@ tile_ranges_kernel(const __grid_constant__ BatchTab tab, int sel) {
     if (i == R - 1) ranges[2 * t + 1] = (uint32_t)R;
 }
 
-// order[i] = (view * T + tile) with the i-th longest Gaussian list of the batch (LPT scheduling of the
-// render CTAs).  One CTA, bitonic sort of (length << 32 | ~entry) in shared memory.
+// order[] = the batch's (view * T + tile) entries by decreasing Gaussian-list length (LPT scheduling of the
+// render CTAs).  One CTA, counting sort on a monotone 11-bit key of the length (float exponent + 3 mantissa
+// bits: 8 buckets per octave) -- the order inside a bucket is irrelevant for load balance.
+constexpr int ORDER_BUCKETS = 2048;
 __global__ void __launch_bounds__(1024)
-tile_order_kernel(const __grid_constant__ BatchTab tab, int n, int npow2) {
-    extern __shared__ unsigned long long s_key[];
+tile_order_kernel(const __grid_constant__ BatchTab tab, int n) {
+    __shared__ uint32_t s_cnt[ORDER_BUCKETS];
     const int T = tab.grid_x * tab.grid_y;
-    for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
-        unsigned long long k = 0ull;   // padding sorts last (descending order)
-        if (i < n) {
-            const uint32_t* r = tab.v[i / T].ranges + 2 * (i % T);
-            const uint32_t len = r[1] - r[0];
-            k = ((unsigned long long)len << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
-        }
-        s_key[i] = k;
+    for (int i = threadIdx.x; i < ORDER_BUCKETS; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+    auto bucket_of = [&](int i) {
+        const uint32_t* r = tab.v[i / T].ranges + 2 * (i % T);
+        const uint32_t len = r[1] - r[0];
+        // descending: longest lists get the smallest bucket index
+        const uint32_t k = len ? min((uint32_t)(ORDER_BUCKETS - 1), __float_as_uint((float)len) >> 20) : 0u;
+        return (ORDER_BUCKETS - 1) - k;
+    };
+    // warp-aggregated shared atomics: most tiles of a sparse image are empty and share one bucket
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_round = (n + 31) / 32 * 32;
+    for (int i = threadIdx.x; i < n_round; i += blockDim.x) {
+        const uint32_t b = i < n ? bucket_of(i) : 0xffffffffu;
+        const uint32_t peers = __match_any_sync(0xffffffffu, b);
+        if (i < n && lane == __ffs(peers) - 1) atomicAdd(&s_cnt[b], (uint32_t)__popc(peers));
     }
     __syncthreads();
-    for (int size = 2; size <= npow2; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int i = threadIdx.x; i < npow2 / 2; i += blockDim.x) {
-                const int lo = 2 * i - (i & (stride - 1));   // index with bit `stride` cleared
-                const int hi = lo + stride;
-                const bool desc = (lo & size) == 0;          // descending blocks first -> overall descending
-                const unsigned long long a = s_key[lo], b = s_key[hi];
-                if ((a < b) == desc) {
-                    s_key[lo] = b;
-                    s_key[hi] = a;
-                }
-            }
-            __syncthreads();
-        }
+    // exclusive scan of the bucket counts (2 buckets per thread)
+    __shared__ uint32_t s_warp[32];
+    const uint32_t c0 = s_cnt[2 * threadIdx.x], c1 = s_cnt[2 * threadIdx.x + 1];
+    uint32_t inc = c0 + c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
     }
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
-        tab.tile_order[i] = 0xffffffffu - (uint32_t)(s_key[i] & 0xffffffffull);
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w = 0; w < warp; ++w) woff += s_warp[w];
+    const uint32_t excl = woff + inc - (c0 + c1);
+    __syncthreads();
+    s_cnt[2 * threadIdx.x] = excl;
+    s_cnt[2 * threadIdx.x + 1] = excl + c0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_round; i += blockDim.x) {
+        const uint32_t b = i < n ? bucket_of(i) : 0xffffffffu;
+        const uint32_t peers = __match_any_sync(0xffffffffu, b);
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (i < n && lane == leader) base = atomicAdd(&s_cnt[b], (uint32_t)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (i < n) tab.tile_order[base + __popc(peers & ((1u << lane) - 1u))] = (uint32_t)i;
+    }
 }
 
-__global__ void tile_order_identity_kernel(int n, uint32_t* __restrict__ order) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) order[i] = (uint32_t)i;
+// ranges[t] = exclusive scan of the per-tile pair counts accumulated by duplicateWithKeys (== positions of the
+// tile's run in the sorted array); untouched tiles stay (0,0).  One CTA per view.
+__global__ void __launch_bounds__(1024)
+tile_ranges_from_counts_kernel(const __grid_constant__ BatchTab tab) {
+    const ViewTab& vt = tab.v[blockIdx.x];
+    const int T = tab.grid_x * tab.grid_y;
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const bool overflow = vt.status[STATUS_OVERFLOW] != 0u;
+    for (int base = 0; base < T; base += 1024) {
+        const int t = base + threadIdx.x;
+        const uint32_t c = (t < T && !overflow) ? vt.tile_count[t] : 0u;
+        uint32_t inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += x;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        uint32_t woff = s_carry;
+        for (int w = 0; w < warp; ++w) woff += s_warp[w];
+        const uint32_t start = woff + inc - c;
+        if (t < T) {
+            vt.ranges[2 * t] = c ? start : 0u;
+            vt.ranges[2 * t + 1] = c ? start + c : 0u;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = start + c;
+        __syncthreads();
+    }
 }
 
 cudaError_t launch_tile_ranges_batch(const BatchTab& tab, int sel, cudaStream_t st) {
     const int T = tab.grid_x * tab.grid_y;
-    for (int v = 0; v < tab.V; ++v) {
-        cudaError_t e = cudaMemsetAsync(tab.v[v].ranges, 0, (size_t)T * 8, st);
-        if (e != cudaSuccess) return e;
-    }
-    if (tab.P > 0 && tab.capacity > 0) {
-        const unsigned gx = (unsigned)(((int64_t)tab.capacity + 255) / 256);
-        tile_ranges_kernel<<<dim3(gx, tab.V), 256, 0, st>>>(tab, sel);
+    if (tab.P > 0 && tab.capacity > 0 && T <= 8192) {
+        tile_ranges_from_counts_kernel<<<tab.V, 1024, 0, st>>>(tab);
         count_launch();
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
+    } else {
+        for (int v = 0; v < tab.V; ++v) {
+            cudaError_t e = cudaMemsetAsync(tab.v[v].ranges, 0, (size_t)T * 8, st);
+            if (e != cudaSuccess) return e;
+        }
+        if (tab.P > 0 && tab.capacity > 0) {
+            const unsigned gx = (unsigned)(((int64_t)tab.capacity + 255) / 256);
+            tile_ranges_kernel<<<dim3(gx, tab.V), 256, 0, st>>>(tab, sel);
+            count_launch();
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+        }
     }
     const int n = tab.V * T;
-    int p2 = 1;
-    while (p2 < n) p2 <<= 1;
-    const size_t smem = (size_t)p2 * 8;
-    if (smem > 200 * 1024) {   // > 25600 tiles in the batch: keep raster order
-        tile_order_identity_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, tab.tile_order);
-        count_launch();
-        return cudaGetLastError();
-    }
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(tile_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr = smem;
-    }
-    tile_order_kernel<<<1, 1024, smem, st>>>(tab, n, p2);
+    tile_order_kernel<<<1, 1024, 0, st>>>(tab, n);
     count_launch();
     return cudaGetLastError();
 }
