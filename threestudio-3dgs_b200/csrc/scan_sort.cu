@@ -183,14 +183,27 @@ cudaError_t launch_inclusive_scan(int64_t n, const uint32_t* in, uint32_t* out, 
 // ============================================================================================
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int SORT_ITEMS = 16;
-constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 pairs per CTA
+constexpr int SORT_ITEMS_MAX = 24;
+constexpr int SORT_TILE = SORT_THREADS * 16;  // default 4096 pairs per CTA (workspace sizing assumes >= 2048)
 
 constexpr uint32_t DESC_AGG = 1u << 30;
 constexpr uint32_t DESC_INC = 2u << 30;
 constexpr uint32_t DESC_VAL = (1u << 30) - 1;
 
-int sort_tiles_for(int64_t n) { return (int)((n + SORT_TILE - 1) / SORT_TILE); }
+// items per thread of the keys-only passes (tile = 256 * items); B200SPLAT_SORT_ITEMS = 8 | 16 | 24
+static int sort_items() {
+    static const int it = [] {
+        const char* e = getenv("B200SPLAT_SORT_ITEMS");
+        const int v = e ? atoi(e) : 24;   // measured on B200 (1M Gaussians, 4 views): 8 -> 202, 16 -> 171, 24 -> 163 us/view
+        return (v == 8 || v == 16) ? v : 24;
+    }();
+    return it;
+}
+int sort_tiles_for(int64_t n) {   // tiles of the pipeline's (keys-only or pair) passes
+    const int64_t tile = (int64_t)SORT_THREADS * sort_items();
+    return (int)((n + tile - 1) / tile);
+}
+static int sort_tiles_pairs(int64_t n) { return (int)((n + SORT_TILE - 1) / SORT_TILE); }
 
 // Histogram of every digit place in one read of the keys (stand-alone sort only; the pipeline gets its
 // histograms from duplicateWithKeys).  hist: [passes][256] u32 (zeroed).
@@ -245,25 +258,28 @@ struct SortTab {
     SortView v[MAX_VIEWS];
 };
 
-struct SortSmem {
-    uint64_t keys[SORT_TILE];
+template <int ITEMS>
+struct SortSmemT {
+    uint64_t keys[SORT_THREADS * ITEMS];
     uint32_t warp_hist[SORT_WARPS][RADIX];
     uint32_t local_excl[RADIX];   // exclusive offset of digit inside this tile
     uint32_t bin_offset[RADIX];   // global destination of the tile's first key of digit d, minus local_excl
     uint32_t s_h[SORT_WARPS], s_l[SORT_WARPS];
     uint32_t tile;
     uint32_t pad[3];
-    uint32_t vals[SORT_TILE];     // last: keys-only passes do not allocate it
+    uint32_t vals[SORT_THREADS * ITEMS];     // last: keys-only passes do not allocate it
 };
+using SortSmem = SortSmemT<16>;
 
 // One pass: tile t of the input is ranked locally (stable), its per-digit counts are chained to the
 // previous tiles by decoupled look-back, then keys/values are scattered through shared memory so that
 // the global writes are coalesced per digit run.
-template <bool HAS_VALS, int MINB>
+template <bool HAS_VALS, int MINB, int SORT_ITEMS>
 __global__ void __launch_bounds__(SORT_THREADS, MINB)
 onesweep_pass_kernel(int shift, int bits, const __grid_constant__ SortTab tab) {
+    constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SortSmem& S = *reinterpret_cast<SortSmem*>(smem_raw);
+    SortSmemT<SORT_ITEMS>& S = *reinterpret_cast<SortSmemT<SORT_ITEMS>*>(smem_raw);
     const SortView& sv = tab.v[blockIdx.y];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (sv.overflow != nullptr && *sv.overflow != 0u) return;
@@ -419,13 +435,14 @@ onesweep_pass_kernel(int shift, int bits, const __grid_constant__ SortTab tab) {
 }
 
 // workspace: hist [MAX_PASSES][256] u32 | tickets [64] u32 | desc [passes][tiles][256] u32
+static int64_t sort_tiles_max(int64_t n) { return (n + 2047) / 2048; }
 size_t sort_workspace_bytes(int64_t n) {
-    const int64_t tiles = sort_tiles_for(n < 1 ? 1 : n);
+    const int64_t tiles = sort_tiles_max(n < 1 ? 1 : n);
     return align_up((size_t)MAX_PASSES * RADIX * 4 + 256 + (size_t)MAX_PASSES * tiles * RADIX * 4, 256);
 }
 size_t sort_workspace_zero_bytes(int64_t capacity, int end_bit) {
     const int passes = (end_bit + RADIX_BITS - 1) / RADIX_BITS;
-    return (size_t)MAX_PASSES * RADIX * 4 + 256 + (size_t)passes * sort_tiles_for(capacity < 1 ? 1 : capacity) * RADIX * 4;
+    return (size_t)MAX_PASSES * RADIX * 4 + 256 + (size_t)passes * sort_tiles_max(capacity < 1 ? 1 : capacity) * RADIX * 4;
 }
 void sort_workspace_views(void* ws, uint32_t** hist, uint32_t** tickets, uint32_t** desc) {
     uint32_t* h = reinterpret_cast<uint32_t*>(ws);
@@ -435,19 +452,21 @@ void sort_workspace_views(void* ws, uint32_t** hist, uint32_t** tickets, uint32_
 }
 
 // keys-only passes do not touch SortSmem::vals: leave it out of the dynamic allocation (more CTAs per SM)
-constexpr size_t SORT_SMEM_KEYS_ONLY = offsetof(SortSmem, vals);
 
 static cudaError_t ensure_sort_attr() {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(onesweep_pass_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(SortSmem));
+        cudaError_t e = cudaFuncSetAttribute(onesweep_pass_kernel<true, 3, 16>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(onesweep_pass_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sizeof(SortSmem));
+        e = cudaFuncSetAttribute(onesweep_pass_kernel<false, 3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(SortSmemT<16>));
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(onesweep_pass_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sizeof(SortSmem));
+        e = cudaFuncSetAttribute(onesweep_pass_kernel<false, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(SortSmemT<8>));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(onesweep_pass_kernel<false, 2, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(SortSmemT<24>));
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -461,7 +480,7 @@ cudaError_t launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_
     if (end_bit < 1) end_bit = 1;
     if (end_bit > 64) end_bit = 64;
     const int passes = (end_bit + RADIX_BITS - 1) / RADIX_BITS;
-    const int tiles = sort_tiles_for(n);
+    const int tiles = sort_tiles_pairs(n);
     cudaError_t e = ensure_sort_attr();
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(ws, 0, sort_workspace_zero_bytes(n, end_bit), st);
@@ -482,7 +501,7 @@ cudaError_t launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_
         t.capacity = (uint32_t)n;
         t.v[0] = SortView{nullptr, (uint32_t)n, nullptr, keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1],
                           hist + p * RADIX, tickets + p, desc + (size_t)p * tiles * RADIX};
-        onesweep_pass_kernel<true, 3><<<dim3(tiles, 1), SORT_THREADS, sizeof(SortSmem), st>>>(shift, bits, t);
+        onesweep_pass_kernel<true, 3, 16><<<dim3(tiles, 1), SORT_THREADS, sizeof(SortSmem), st>>>(shift, bits, t);
         count_launch();
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -496,7 +515,7 @@ cudaError_t launch_sort_batch(const BatchTab& tab, cudaStream_t st) {
     if (tab.P <= 0 || tab.capacity == 0) return cudaSuccess;
     const int end_bit = tab.end_bit;
     const int passes = (end_bit + RADIX_BITS - 1) / RADIX_BITS;
-    const int tiles = tab.sort_tiles_cap;
+    const int tiles = tab.idx_bits > 0 ? sort_tiles_for(tab.capacity) : sort_tiles_pairs(tab.capacity);
     cudaError_t e = ensure_sort_attr();
     if (e != cudaSuccess) return e;
     int cur = 0;
@@ -511,15 +530,22 @@ cudaError_t launch_sort_batch(const BatchTab& tab, cudaStream_t st) {
                               vt.vals[cur], vt.keys[cur ^ 1], vt.vals[cur ^ 1], vt.hist + p * RADIX, vt.tickets + p,
                               vt.desc + (size_t)p * tiles * RADIX};
         }
-        static const int occ = [] { const char* e = getenv("B200SPLAT_SORT_OCC"); return e ? atoi(e) : 3; }();
-        if (tab.idx_bits > 0 && occ == 4)
-            onesweep_pass_kernel<false, 4><<<dim3(tiles, tab.V), SORT_THREADS, SORT_SMEM_KEYS_ONLY, st>>>(
-                shift + tab.idx_bits, bits, t);
-        else if (tab.idx_bits > 0)
-            onesweep_pass_kernel<false, 3><<<dim3(tiles, tab.V), SORT_THREADS, SORT_SMEM_KEYS_ONLY, st>>>(
-                shift + tab.idx_bits, bits, t);
-        else
-            onesweep_pass_kernel<true, 3><<<dim3(tiles, tab.V), SORT_THREADS, sizeof(SortSmem), st>>>(shift, bits, t);
+        if (tab.idx_bits > 0) {
+            const int sh = shift + tab.idx_bits;
+            const dim3 grid(tiles, tab.V);
+            switch (sort_items()) {
+                case 8:
+                    onesweep_pass_kernel<false, 4, 8><<<grid, SORT_THREADS, offsetof(SortSmemT<8>, vals), st>>>(sh, bits, t);
+                    break;
+                case 24:
+                    onesweep_pass_kernel<false, 2, 24><<<grid, SORT_THREADS, offsetof(SortSmemT<24>, vals), st>>>(sh, bits, t);
+                    break;
+                default:
+                    onesweep_pass_kernel<false, 3, 16><<<grid, SORT_THREADS, offsetof(SortSmemT<16>, vals), st>>>(sh, bits, t);
+            }
+        } else {
+            onesweep_pass_kernel<true, 3, 16><<<dim3(tiles, tab.V), SORT_THREADS, sizeof(SortSmem), st>>>(shift, bits, t);
+        }
         count_launch();
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
