@@ -5,12 +5,18 @@
 // (_blend_tile); reference consumers renderer/diff_gaussian_rasterizer_advanced.py:122-146.
 //
 // B200 design:
-//  * one CTA per tile, 8 warps, each warp owns an 8x4 pixel block;
-//  * the tile's Gaussian list is consumed in batches of 256 entries, double buffered in shared
-//    memory behind mbarriers: each thread gathers one 48-byte record (common.cuh REC layout) either
-//    with one bulk async copy (cp.async.bulk -> UBLKCP, complete_tx on the mbarrier) or with three
-//    16-byte cp.async (LDGSTS) whose completion arrives on the same mbarrier, so the gather of batch
-//    k+1 overlaps the blend of batch k;
+//  * forward: one CTA (8 warps, one 8x4 pixel block each) per tile shares batches of 256 staged entries,
+//    double buffered (measured faster than warp-private staging for the forward: 64 vs 75 us/view);
+//  * backward: the unit of work is ONE WARP = one 8x4 pixel block of a tile, launched as its own 32-thread CTA:
+//    the eight warps of a tile used to wait for each other at a barrier per batch (40 % of the stall
+//    samples: an edge-of-object block walks ten times more survivors than its neighbours), and a finished
+//    warp kept its registers until the slowest one was done.  Independent warps stop as soon as their own
+//    32 pixels are saturated (forward) / start at their own last contributor (backward), and the SM back-
+//    fills with the next work item;
+//  * a warp consumes its tile's Gaussian list in batches of 64 entries through a 3-stage shared-memory
+//    ring behind mbarriers: each lane gathers two 48-byte records per batch (common.cuh REC layout) either
+//    with bulk async copies (cp.async.bulk -> UBLKCP, complete_tx on the mbarrier) or with 16-byte
+//    cp.async (LDGSTS) whose completion arrives on the same mbarrier, two batches ahead of the blend;
 //  * warp-cooperative culling: for every 32 staged entries, lane l bounds entry l's best-case alpha
 //    over the warp's 8x4 pixel rectangle (exact minimum of the conic quadratic over the rectangle
 //    edges); only entries that can reach alpha >= 1/255 somewhere in the rectangle are evaluated by
@@ -27,8 +33,9 @@
 
 namespace b200splat {
 
-constexpr int BATCH = 256;
-constexpr int STAGES = 2;
+constexpr int BATCH = 64;    // list entries per warp batch (2 per lane)
+constexpr int STAGES = 3;    // ring depth: two batches in flight while one is blended
+constexpr int WARPS_PER_TILE = BLOCK_SIZE / 32;
 constexpr int ILP = 4;   // survivors whose alpha is evaluated together (hides the LDS/MUFU latency chain)
 
 // ---- mbarrier / async-copy PTX ----------------------------------------------------------------
@@ -70,11 +77,11 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// pixel owned by this thread: warp w -> 8x4 block (w%2, w/2), lane -> (l%8, l/8)
-__device__ __forceinline__ void thread_pixel(int& lx, int& ly) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    lx = (warp & 1) * 8 + (lane & 7);
-    ly = (warp >> 1) * 4 + (lane >> 3);
+// pixel owned by this lane: block w of the tile -> 8x4 pixels at (w%2, w/2), lane -> (l%8, l/8)
+__device__ __forceinline__ void thread_pixel(int wblock, int& lx, int& ly) {
+    const int lane = threadIdx.x & 31;
+    lx = (wblock & 1) * 8 + (lane & 7);
+    ly = (wblock >> 1) * 4 + (lane >> 3);
 }
 
 struct PointList {   // sorted list: packed words (key << idx_bits | idx) or a plain index array
@@ -86,15 +93,15 @@ struct PointList {   // sorted list: packed words (key << idx_bits | idx) or a p
     }
 };
 
-// stage one batch: thread t gathers the record of list entry `pos` into buf[t]
+// gather the record of list entry `pos` into buf[slot]; completion arrives on `bar`
 template <bool BULK>
-__device__ __forceinline__ void stage_batch(float4* buf, uint32_t* ids, uint64_t* bar, const float* __restrict__ rec,
-                                            const PointList point_list, int64_t pos, bool valid) {
+__device__ __forceinline__ void stage_entry(float4* buf, uint32_t* ids, uint64_t* bar, const float* __restrict__ rec,
+                                            const PointList point_list, int slot, int64_t pos, bool valid) {
     if (valid) {
         const uint32_t id = point_list.at(pos);
-        if (ids) ids[threadIdx.x] = id;
+        if (ids) ids[slot] = id;
         const float* src = rec + (size_t)id * REC_FLOATS;
-        float4* dst = buf + 3 * threadIdx.x;
+        float4* dst = buf + 3 * slot;
         if (BULK) {
             mbar_arrive_expect_tx(bar, REC_FLOATS * 4);
             bulk_g2s(dst, src, REC_FLOATS * 4, bar);
@@ -132,15 +139,29 @@ __device__ __forceinline__ bool cull_keep(const float4 q0, const float C, const 
     return !convex || inside || !(fmin > thr);
 }
 
+// ---- CTA-per-tile helpers of the forward kernel (8 warps share one staged batch of 256 entries) --------
+constexpr int FWD_BATCH = 256;
+constexpr int FWD_STAGES = 2;
+__device__ __forceinline__ void thread_pixel_cta(int& lx, int& ly) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    lx = (warp & 1) * 8 + (lane & 7);
+    ly = (warp >> 1) * 4 + (lane >> 3);
+}
+template <bool BULK>
+__device__ __forceinline__ void stage_batch_cta(float4* buf, uint32_t* ids, uint64_t* bar, const float* __restrict__ rec,
+                                                const PointList point_list, int64_t pos, bool valid) {
+    stage_entry<BULK>(buf, ids, bar, rec, point_list, (int)threadIdx.x, pos, valid);
+}
+
 // ============================================================================================
 // K6 forward
 // ============================================================================================
 template <bool BULK>
 __global__ void __launch_bounds__(BLOCK_SIZE)
 render_forward_kernel(const __grid_constant__ BatchTab tab, int sel) {
-    __shared__ __align__(16) float4 s_rec[STAGES][BATCH * 3];
-    __shared__ __align__(8) uint64_t s_bar[STAGES];
-    __shared__ __align__(16) uint8_t s_surv[BLOCK_SIZE / 32][BATCH + 16];
+    __shared__ __align__(16) float4 s_rec[FWD_STAGES][FWD_BATCH * 3];
+    __shared__ __align__(8) uint64_t s_bar[FWD_STAGES];
+    __shared__ __align__(16) uint8_t s_surv[BLOCK_SIZE / 32][FWD_BATCH + 16];
 
     const int W = tab.W, H = tab.H, grid_x = tab.grid_x;
     const int n_tiles = grid_x * tab.grid_y;
@@ -160,7 +181,7 @@ render_forward_kernel(const __grid_constant__ BatchTab tab, int sel) {
     float* __restrict__ out_depth = vt.out_depth;
     float* __restrict__ out_alpha = vt.out_alpha;
     int lx, ly;
-    thread_pixel(lx, ly);
+    thread_pixel_cta(lx, ly);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const int pxi = tile_x * BLOCK_X + lx, pyi = tile_y * BLOCK_Y + ly;
@@ -170,7 +191,7 @@ render_forward_kernel(const __grid_constant__ BatchTab tab, int sel) {
     const float Y0 = (float)(tile_y * BLOCK_Y + (warp >> 1) * 4), Y1 = Y0 + 3.f;
     const uint32_t r0 = ranges[2 * tile], r1 = ranges[2 * tile + 1];
     const int total = (int)(r1 - r0);
-    const int rounds = (total + BATCH - 1) / BATCH;
+    const int rounds = (total + FWD_BATCH - 1) / FWD_BATCH;
 
     if (threadIdx.x == 0) {
         mbar_init(&s_bar[0], BLOCK_SIZE);
@@ -185,7 +206,7 @@ render_forward_kernel(const __grid_constant__ BatchTab tab, int sel) {
     int traversed = 0;
 
     if (rounds > 0)
-        stage_batch<BULK>(s_rec[0], nullptr, &s_bar[0], rec, point_list, (int64_t)r0 + threadIdx.x,
+        stage_batch_cta<BULK>(s_rec[0], nullptr, &s_bar[0], rec, point_list, (int64_t)r0 + threadIdx.x,
                           (int)threadIdx.x < total);
     for (int b = 0; b < rounds; ++b) {
         // also orders "everyone finished reading stage (b+1)&1" before it is refilled
@@ -197,19 +218,19 @@ render_forward_kernel(const __grid_constant__ BatchTab tab, int sel) {
             break;
         }
         if (b + 1 < rounds) {
-            const int nb = (b + 1) * BATCH + threadIdx.x;
-            stage_batch<BULK>(s_rec[s ^ 1], nullptr, &s_bar[s ^ 1], rec, point_list, (int64_t)r0 + nb, nb < total);
+            const int nb = (b + 1) * FWD_BATCH + threadIdx.x;
+            stage_batch_cta<BULK>(s_rec[s ^ 1], nullptr, &s_bar[s ^ 1], rec, point_list, (int64_t)r0 + nb, nb < total);
         }
         mbar_wait(&s_bar[s], (b >> 1) & 1);
-        const int count = min(BATCH, total - b * BATCH);
-        traversed = b * BATCH + count;
+        const int count = min(FWD_BATCH, total - b * FWD_BATCH);
+        traversed = b * FWD_BATCH + count;
         const float4* __restrict__ buf = s_rec[s];
         // batch-level cull: 8 independent tests per lane; survivors compacted (in list order) into the
         // warp's private index list
         uint8_t* __restrict__ surv = s_surv[warp];
         int nsurv = 0;
 #pragma unroll
-        for (int c = 0; c < BATCH / 32; ++c) {
+        for (int c = 0; c < FWD_BATCH / 32; ++c) {
             const int e = c * 32 + lane;
             bool keep = false;
             if (e < count) {
@@ -249,7 +270,7 @@ render_forward_kernel(const __grid_constant__ BatchTab tab, int sel) {
                 const float test_T = T * (1.0f - alpha[k]);
                 const bool stop = act && (test_T < T_MIN);
                 const bool use = act && !stop;
-                const uint32_t position = (uint32_t)(b * BATCH + j[k] + 1);
+                const uint32_t position = (uint32_t)(b * FWD_BATCH + j[k] + 1);
                 if (use) {
                     const float w = alpha[k] * T;
                     C0 += cr[k] * w;
@@ -342,110 +363,103 @@ __device__ __forceinline__ int reduce_slot(int lane) {
 }
 
 template <bool BULK>
-__global__ void __launch_bounds__(BLOCK_SIZE)
+__global__ void __launch_bounds__(32)
 render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
     __shared__ __align__(16) float4 s_rec[STAGES][BATCH * 3];
     __shared__ uint32_t s_ids[STAGES][BATCH];
     __shared__ __align__(8) uint64_t s_bar[STAGES];
-    __shared__ __align__(16) uint8_t s_surv[BLOCK_SIZE / 32][BATCH + 16];
-    __shared__ uint32_t s_max;
+    __shared__ __align__(16) uint8_t s_surv[BATCH + 16];
 
     const int W = tab.W, H = tab.H, grid_x = tab.grid_x;
     const int n_tiles = grid_x * tab.grid_y;
-    const uint32_t entry = tab.tile_order[blockIdx.x];   // longest lists of the whole view batch first (LPT)
+    const uint32_t entry = tab.tile_order[blockIdx.x / WARPS_PER_TILE];   // longest lists of the batch first (LPT)
+    const int wblock = blockIdx.x % WARPS_PER_TILE;
     const ViewTab& vt = tab.v[entry / n_tiles];
     const int tile = (int)(entry % n_tiles);
     const int tile_x = tile % grid_x, tile_y = tile / grid_x;
-    const uint32_t* __restrict__ ranges = vt.ranges;
     const PointList point_list{tab.idx_bits ? vt.keys[sel] : nullptr, vt.vals[sel],
                                tab.idx_bits ? (uint32_t)((1ull << tab.idx_bits) - 1ull) : 0xffffffffu};
     const float* __restrict__ rec = vt.rec;
     const float* __restrict__ bg = vt.bg;
-    const uint32_t* __restrict__ n_contrib = vt.n_contrib;
-    const float* __restrict__ final_T = vt.final_T;
-    const float* __restrict__ dL_dcolor = vt.dL_dcolor;
-    const float* __restrict__ dL_ddepth = vt.dL_ddepth;
-    const float* __restrict__ dL_dalpha = vt.dL_dalpha;
     float* __restrict__ grad2d = vt.grad2d;
     int lx, ly;
-    thread_pixel(lx, ly);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    thread_pixel(wblock, lx, ly);
+    const int lane = threadIdx.x;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const int pxi = tile_x * BLOCK_X + lx, pyi = tile_y * BLOCK_Y + ly;
     const bool inside = pxi < W && pyi < H;
     const float pixx = (float)pxi, pixy = (float)pyi;
-    const float X0 = (float)(tile_x * BLOCK_X + (warp & 1) * 8), X1 = X0 + 7.f;
-    const float Y0 = (float)(tile_y * BLOCK_Y + (warp >> 1) * 4), Y1 = Y0 + 3.f;
+    const float X0 = (float)(tile_x * BLOCK_X + (wblock & 1) * 8), X1 = X0 + 7.f;
+    const float Y0 = (float)(tile_y * BLOCK_Y + (wblock >> 1) * 4), Y1 = Y0 + 3.f;
     const int pix = pyi * W + pxi;
     const size_t HW = (size_t)H * W;
-    const uint32_t r0 = ranges[2 * tile];
+    const uint32_t r0 = vt.ranges[2 * tile];
 
-    if (threadIdx.x == 0) {
-        mbar_init(&s_bar[0], BLOCK_SIZE);
-        mbar_init(&s_bar[1], BLOCK_SIZE);
-        mbar_fence_init();
-        s_max = 0;
-    }
-    __syncthreads();
-    const uint32_t my_last = inside ? n_contrib[pix] : 0u;
+    const uint32_t my_last = inside ? vt.n_contrib[pix] : 0u;
     uint32_t warp_last = my_last;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, o));
-    if (lane == 0 && warp_last) atomicMax(&s_max, warp_last);
-    __syncthreads();
-    const int total = (int)s_max;  // entries [0,total) of the tile's list can have contributed
+    const int total = (int)warp_last;  // entries [0,total) of the tile's list can have contributed to this block
     if (total == 0) return;
     const int rounds = (total + BATCH - 1) / BATCH;
     const int slot = reduce_slot(lane);
 
-    const float T_final = inside ? final_T[pix] : 0.0f;
+    const float T_final = inside ? vt.final_T[pix] : 0.0f;
     float T = T_final;
     float gC0 = 0.f, gC1 = 0.f, gC2 = 0.f, gD = 0.f, gA = 0.f;
     if (inside) {
-        if (dL_dcolor) gC0 = dL_dcolor[pix], gC1 = dL_dcolor[HW + pix], gC2 = dL_dcolor[2 * HW + pix];
-        if (dL_ddepth) gD = dL_ddepth[pix];
-        if (dL_dalpha) gA = dL_dalpha[pix];
+        if (vt.dL_dcolor) gC0 = vt.dL_dcolor[pix], gC1 = vt.dL_dcolor[HW + pix], gC2 = vt.dL_dcolor[2 * HW + pix];
+        if (vt.dL_ddepth) gD = vt.dL_ddepth[pix];
+        if (vt.dL_dalpha) gA = vt.dL_dalpha[pix];
     }
     const float bg_dot = bg[0] * gC0 + bg[1] * gC1 + bg[2] * gC2;
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accD = 0.f, accA = 0.f;
     float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, lD = 0.f;
 
-    // batch b holds list positions total-1-(b*256+t), t = 0..255 (back to front)
-    {
-        const int p = (int)threadIdx.x;
-        stage_batch<BULK>(s_rec[0], s_ids[0], &s_bar[0], rec, point_list, (int64_t)r0 + (total - 1 - p), p < total);
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(&s_bar[s], BATCH);
+        mbar_fence_init();
     }
-    for (int b = 0; b < rounds; ++b) {
-        __syncthreads();
-        const int s = b & 1;
-        if (b + 1 < rounds) {
-            const int p = (b + 1) * BATCH + threadIdx.x;
-            stage_batch<BULK>(s_rec[s ^ 1], s_ids[s ^ 1], &s_bar[s ^ 1], rec, point_list,
-                              (int64_t)r0 + (total - 1 - p), p < total);
+    __syncwarp();
+    // batch b holds list positions total-1-(b*64+t), t = 0..63 (back to front)
+    auto stage = [&](int b) {
+        const int s = b % STAGES;
+#pragma unroll
+        for (int u = 0; u < BATCH / 32; ++u) {
+            const int sl = lane + 32 * u;
+            const int p = b * BATCH + sl;
+            stage_entry<BULK>(s_rec[s], s_ids[s], &s_bar[s], rec, point_list, sl, (int64_t)r0 + (total - 1 - p),
+                              p < total);
         }
-        mbar_wait(&s_bar[s], (b >> 1) & 1);
+    };
+    stage(0);
+    if (rounds > 1) stage(1);
+    for (int b = 0; b < rounds; ++b) {
+        __syncwarp();   // every lane finished with the slot refilled below (batch b-1's)
+        if (b + 2 < rounds) stage(b + 2);
+        const int s = b % STAGES;
+        mbar_wait(&s_bar[s], (b / STAGES) & 1);
         const int count = min(BATCH, total - b * BATCH);
         const float4* __restrict__ buf = s_rec[s];
-        uint8_t* __restrict__ surv = s_surv[warp];
         int nsurv = 0;
 #pragma unroll
         for (int c = 0; c < BATCH / 32; ++c) {
             const int e = c * 32 + lane;
-            const uint32_t q = (uint32_t)(total - 1 - (b * BATCH + e));  // 0-based list position
             bool keep = false;
-            if (e < count && q < warp_last) {
+            if (e < count) {
                 const float4 q0 = buf[3 * e];
                 const float4 q1 = buf[3 * e + 1];
                 const float thr = buf[3 * e + 2].z;
                 keep = cull_keep(q0, q1.x, thr, X0, X1, Y0, Y1);
             }
             const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-            if (keep) surv[nsurv + __popc(bal & lt_mask)] = (uint8_t)e;
+            if (keep) s_surv[nsurv + __popc(bal & lt_mask)] = (uint8_t)e;
             nsurv += __popc(bal);
         }
         __syncwarp();
         for (int i = 0; i < nsurv; i += ILP) {
-            const uint32_t packed = *reinterpret_cast<const uint32_t*>(surv + i);
+            const uint32_t packed = *reinterpret_cast<const uint32_t*>(s_surv + i);
             int j[ILP];
             float v[ILP][10];
             bool hit[ILP];
@@ -545,11 +559,11 @@ cudaError_t launch_render_forward(const BatchTab& tab, int sel, cudaStream_t st)
 }
 
 cudaError_t launch_render_backward(const BatchTab& tab, int sel, cudaStream_t st) {
-    const unsigned grid = (unsigned)(tab.V * tab.grid_x * tab.grid_y);
+    const unsigned grid = (unsigned)(tab.V * tab.grid_x * tab.grid_y * WARPS_PER_TILE);
     if (use_bulk_staging())
-        render_backward_kernel<true><<<grid, BLOCK_SIZE, 0, st>>>(tab, sel);
+        render_backward_kernel<true><<<grid, 32, 0, st>>>(tab, sel);
     else
-        render_backward_kernel<false><<<grid, BLOCK_SIZE, 0, st>>>(tab, sel);
+        render_backward_kernel<false><<<grid, 32, 0, st>>>(tab, sel);
     count_launch();
     return cudaGetLastError();
 }
