@@ -68,14 +68,31 @@ __device__ __forceinline__ void sh_basis_chunk(float x, float y, float z, float 
     }
 }
 
-// one chunk of 4 coefficients of one view: accumulate dL/dsh (registers) and dL/ddir
-template <int C, int K, bool VEC>
-__device__ __forceinline__ void sh_chunk_backward(const float* __restrict__ sh, float x, float y, float z,
-                                                  const float g[3], float* dsh /* [12] of this chunk */,
-                                                  float& ddx, float& ddy, float& ddz) {
-    if (4 * C >= K) return;
+// one chunk of 4 coefficients, one view: acc[12] += basis * g, and the chunk's part of dL/ddir
+template <int C, int K>
+__device__ __forceinline__ void sh_chunk_view(const float sv[12], float x, float y, float z, const float g[3],
+                                              float acc[12], float& ddx, float& ddy, float& ddz) {
     float B[4], Bx[4], By[4], Bz[4];
     sh_basis_chunk<C>(x, y, z, B, Bx, By, Bz);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        if (4 * C + t < K) {
+            const float gs = g[0] * sv[3 * t] + g[1] * sv[3 * t + 1] + g[2] * sv[3 * t + 2];
+            ddx += Bx[t] * gs, ddy += By[t] * gs, ddz += Bz[t] * gs;
+            acc[3 * t] += B[t] * g[0];
+            acc[3 * t + 1] += B[t] * g[1];
+            acc[3 * t + 2] += B[t] * g[2];
+        }
+    }
+}
+
+// Phase B of the kernel for chunk C: load the chunk's 12 SH floats once, loop over the views (their masked
+// colour gradient and unit direction come from shared memory), store the chunk's dL/dsh, accumulate each
+// view's dL/ddir in shared memory.
+template <int C, int K, bool ACC, bool VEC>
+__device__ __forceinline__ void sh_chunk_all_views(const float* __restrict__ sh, float* __restrict__ dst, int M, int V,
+                                                   uint32_t vis, const float* __restrict__ s_view /* [V][10][128] */) {
+    if (4 * C >= K) return;
     float sv[12];
     if (VEC) {
         const float4* in4 = reinterpret_cast<const float4*>(sh) + 3 * C;
@@ -89,14 +106,38 @@ __device__ __forceinline__ void sh_chunk_backward(const float* __restrict__ sh, 
             for (int ch = 0; ch < 3; ++ch) sv[3 * t + ch] = (4 * C + t < K) ? __ldg(sh + 3 * (4 * C + t) + ch) : 0.f;
         }
     }
+    float acc[12];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        if (4 * C + t < K) {
-            const float gs = g[0] * sv[3 * t] + g[1] * sv[3 * t + 1] + g[2] * sv[3 * t + 2];
-            ddx += Bx[t] * gs, ddy += By[t] * gs, ddz += Bz[t] * gs;
-            dsh[3 * t] += B[t] * g[0];
-            dsh[3 * t + 1] += B[t] * g[1];
-            dsh[3 * t + 2] += B[t] * g[2];
+    for (int t = 0; t < 12; ++t) acc[t] = 0.f;
+    float* sw = const_cast<float*>(s_view);
+    for (int v = 0; v < V; ++v) {
+        if (!((vis >> v) & 1u)) continue;
+        float* r = sw + (size_t)v * 10 * 128 + threadIdx.x;
+        const float g[3] = {r[0 * 128], r[1 * 128], r[2 * 128]};
+        const float dx = r[3 * 128], dy = r[4 * 128], dz = r[5 * 128];
+        float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+        sh_chunk_view<C, K>(sv, dx, dy, dz, g, acc, ddx, ddy, ddz);
+        r[7 * 128] += ddx, r[8 * 128] += ddy, r[9 * 128] += ddz;
+    }
+    if (VEC) {
+        float4* d4 = reinterpret_cast<float4*>(dst) + 3 * C;
+        if (ACC) {
+            const float4 p0 = d4[0], p1 = d4[1], p2 = d4[2];
+            d4[0] = make_float4(p0.x + acc[0], p0.y + acc[1], p0.z + acc[2], p0.w + acc[3]);
+            d4[1] = make_float4(p1.x + acc[4], p1.y + acc[5], p1.z + acc[6], p1.w + acc[7]);
+            d4[2] = make_float4(p2.x + acc[8], p2.y + acc[9], p2.z + acc[10], p2.w + acc[11]);
+        } else {
+            d4[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            d4[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            d4[2] = make_float4(acc[8], acc[9], acc[10], acc[11]);
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < 12; ++t) {
+            if (4 * C + t / 3 < K) {
+                float* p = dst + 12 * C + t;
+                if (ACC) *p += acc[t]; else *p = acc[t];
+            }
         }
     }
 }
@@ -118,6 +159,8 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
                            float* __restrict__ dL_dcov3D, float* __restrict__ stat_grad_accum,
                            float* __restrict__ stat_denom, float* __restrict__ stat_max_radii) {
     __shared__ float sV[MAX_VIEWS][16], sP[MAX_VIEWS][16], sC[MAX_VIEWS][4];
+    // per (view, thread): masked colour gradient (3), unit view direction (3), 1/|d| (1), dL/ddir (3)
+    extern __shared__ float s_view[];   // [V][10][128]
     const int V = tab.V;
     for (int i = threadIdx.x; i < V * 16; i += blockDim.x) {
         sV[i >> 4][i & 15] = tab.v[i >> 4].view[i & 15];
@@ -130,7 +173,6 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
     const int M = tab.M;
     constexpr int K = DEG < 0 ? 0 : (DEG + 1) * (DEG + 1);
     constexpr int NCH = (K + 3) / 4;          // live chunks of 4 coefficients
-    constexpr int NSH = NCH > 0 ? NCH * 12 : 1;
 
     uint32_t vis = 0;
     int max_radius = 0;
@@ -159,6 +201,14 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
     if (DEG >= 0) {   // SH block of this Gaussian towards L2 while the covariance chain runs
         prefetch_l2(sh);
         if (K * 12 > 128) prefetch_l2(reinterpret_cast<const char*>(sh) + 128);
+    }
+    // every view's 48-byte gradient record too: the per-view chain below then hits L2 instead of DRAM
+    for (int v = 0; v < V; ++v) {
+        if ((vis >> v) & 1u) {
+            const char* gp = reinterpret_cast<const char*>(tab.v[v].grad2d + (size_t)idx * GRAD2D_FLOATS);
+            prefetch_l2(gp);
+            prefetch_l2(gp + 44);
+        }
     }
     const float x = means3D[3 * idx], y = means3D[3 * idx + 1], z = means3D[3 * idx + 2];
 
@@ -201,9 +251,6 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
     float dmx = 0.f, dmy = 0.f, dmz = 0.f, dop = 0.f;
     float dS[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float dcol[3] = {0.f, 0.f, 0.f};
-    float dsh[NSH];
-#pragma unroll
-    for (int i = 0; i < NSH; ++i) dsh[i] = 0.f;
     float st_norm = 0.f, st_cnt = 0.f;
 
     for (int v = 0; v < V; ++v) {
@@ -306,53 +353,41 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
             float dx = x - sC[v][0], dy = y - sC[v][1], dz = z - sC[v][2];
             const float n = sqrtf(dx * dx + dy * dy + dz * dz);
             const float in = 1.0f / n;
-            dx *= in, dy *= in, dz *= in;
-            float ddx = 0.f, ddy = 0.f, ddz = 0.f;
-            sh_chunk_backward<0, K, VEC>(sh, dx, dy, dz, g_rgb, dsh, ddx, ddy, ddz);
-            if (NCH > 1) sh_chunk_backward<1, K, VEC>(sh, dx, dy, dz, g_rgb, dsh + (NCH > 1 ? 12 : 0), ddx, ddy, ddz);
-            if (NCH > 2) sh_chunk_backward<2, K, VEC>(sh, dx, dy, dz, g_rgb, dsh + (NCH > 2 ? 24 : 0), ddx, ddy, ddz);
-            if (NCH > 3) sh_chunk_backward<3, K, VEC>(sh, dx, dy, dz, g_rgb, dsh + (NCH > 3 ? 36 : 0), ddx, ddy, ddz);
-            // through dir = d / |d|
-            const float dot = dx * ddx + dy * ddy + dz * ddz;
-            dmx += (ddx - dx * dot) * in;
-            dmy += (ddy - dy * dot) * in;
-            dmz += (ddz - dz * dot) * in;
+            float* r = s_view + (size_t)v * 10 * 128 + threadIdx.x;
+            r[0 * 128] = g_rgb[0], r[1 * 128] = g_rgb[1], r[2 * 128] = g_rgb[2];
+            r[3 * 128] = dx * in, r[4 * 128] = dy * in, r[5 * 128] = dz * in, r[6 * 128] = in;
+            r[7 * 128] = 0.f, r[8 * 128] = 0.f, r[9 * 128] = 0.f;
         } else {
             dcol[0] += g_rgb[0], dcol[1] += g_rgb[1], dcol[2] += g_rgb[2];
         }
     }
 
-    // ---- write-out ---------------------------------------------------------------------------------
+    // ---- SH: chunk-outer / view-inner (each 48-byte chunk of the SH block is loaded once) ---------------
     if (DEG >= 0) {
         float* dst = dL_dshs + (size_t)idx * M * 3;
-        if (VEC) {
-            float4* out4 = reinterpret_cast<float4*>(dst);
-            const int nch_mem = M >> 2;
-#pragma unroll
-            for (int C = 0; C < 4; ++C) {
-                if (C < nch_mem) {
-                    float o[12];
-#pragma unroll
-                    for (int t = 0; t < 12; ++t) o[t] = (C < NCH) ? dsh[(C < NCH ? C : 0) * 12 + t] : 0.f;
-                    float4* d4 = out4 + 3 * C;
-                    if (ACC) {
-                        if (C < NCH) {
-                            const float4 p0 = d4[0], p1 = d4[1], p2 = d4[2];
-                            d4[0] = make_float4(p0.x + o[0], p0.y + o[1], p0.z + o[2], p0.w + o[3]);
-                            d4[1] = make_float4(p1.x + o[4], p1.y + o[5], p1.z + o[6], p1.w + o[7]);
-                            d4[2] = make_float4(p2.x + o[8], p2.y + o[9], p2.z + o[10], p2.w + o[11]);
-                        }
-                    } else {
-                        d4[0] = make_float4(o[0], o[1], o[2], o[3]);
-                        d4[1] = make_float4(o[4], o[5], o[6], o[7]);
-                        d4[2] = make_float4(o[8], o[9], o[10], o[11]);
-                    }
-                }
+        sh_chunk_all_views<0, K, ACC, VEC>(sh, dst, M, V, vis, s_view);
+        sh_chunk_all_views<1, K, ACC, VEC>(sh, dst, M, V, vis, s_view);
+        sh_chunk_all_views<2, K, ACC, VEC>(sh, dst, M, V, vis, s_view);
+        sh_chunk_all_views<3, K, ACC, VEC>(sh, dst, M, V, vis, s_view);
+        if (!ACC) {   // coefficients above the active degree get zero gradients
+            if (VEC) {
+                float4* d4 = reinterpret_cast<float4*>(dst);
+                for (int i = 3 * NCH; i < 3 * (M >> 2); ++i) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                // dead coefficients inside the last live chunk were written as zeros by the chunk store
+            } else {
+                for (int k = 3 * K; k < 3 * M; ++k) dst[k] = 0.f;
             }
-        } else {
-#pragma unroll
-            for (int k = 0; k < 3 * K; ++k) put<ACC>(dst + k, dsh[k]);
-            if (!ACC) for (int k = 3 * K; k < 3 * M; ++k) dst[k] = 0.f;
+        }
+        // through dir = d / |d|, per view
+        for (int v = 0; v < V; ++v) {
+            if (!((vis >> v) & 1u)) continue;
+            const float* r = s_view + (size_t)v * 10 * 128 + threadIdx.x;
+            const float dx = r[3 * 128], dy = r[4 * 128], dz = r[5 * 128], in = r[6 * 128];
+            const float ddx = r[7 * 128], ddy = r[8 * 128], ddz = r[9 * 128];
+            const float dot = dx * ddx + dy * ddy + dz * ddz;
+            dmx += (ddx - dx * dot) * in;
+            dmy += (ddy - dy * dot) * in;
+            dmz += (ddz - dz * dot) * in;
         }
     } else if (dL_dcolors) {
         put<ACC>(dL_dcolors + 3 * idx, dcol[0]);
@@ -419,10 +454,11 @@ cudaError_t launch_preprocess_backward(const BatchTab& tab, const float* means3D
                                        int accumulate, cudaStream_t st) {
     if (tab.P <= 0) return cudaSuccess;
     const int grid = (tab.P + 127) / 128;
+    const size_t smem = tab.sh_degree >= 0 ? (size_t)tab.V * 10 * 128 * sizeof(float) : 0;
     const bool vec = tab.sh_degree >= 0 && (tab.M & 3) == 0 && tab.M <= 16 &&
                      ((reinterpret_cast<uintptr_t>(shs) | reinterpret_cast<uintptr_t>(dL_dshs)) & 15) == 0;
 #define LAUNCH_PB(D, A, VC)                                                                                        \
-    preprocess_backward_kernel<D, A, VC><<<grid, 128, 0, st>>>(                                                    \
+    preprocess_backward_kernel<D, A, VC><<<grid, 128, smem, st>>>(                                                    \
         tab, means3D, scales, rotations, shs, cov3D_precomp, dL_dmeans3D, dL_dshs, dL_dcolors, dL_dopacity,        \
         dL_dscales, dL_drotations, dL_dcov3D, stat_grad_accum, stat_denom, stat_max_radii)
 #define DISPATCH_DEG(A, VC)                                                                                        \
