@@ -195,12 +195,12 @@ static int sort_items() {
     static const int it = [] {
         const char* e = getenv("B200SPLAT_SORT_ITEMS");
         const int v = e ? atoi(e) : 24;   // measured on B200 (1M Gaussians, 4 views): 8 -> 202, 16 -> 171, 24 -> 163 us/view
-        return (v == 8 || v == 16) ? v : 24;
+        return (v == 8 || v == 16 || v == 512) ? v : 24;   // 512 = 512 threads x 12 items
     }();
     return it;
 }
 int sort_tiles_for(int64_t n) {   // tiles of the pipeline's (keys-only or pair) passes
-    const int64_t tile = (int64_t)SORT_THREADS * sort_items();
+    const int64_t tile = sort_items() == 512 ? 6144 : (int64_t)SORT_THREADS * sort_items();
     return (int)((n + tile - 1) / tile);
 }
 static int sort_tiles_pairs(int64_t n) { return (int)((n + SORT_TILE - 1) / SORT_TILE); }
@@ -258,35 +258,37 @@ struct SortTab {
     SortView v[MAX_VIEWS];
 };
 
-template <int ITEMS>
+template <int ITEMS, int NT = SORT_THREADS>
 struct SortSmemT {
-    uint64_t keys[SORT_THREADS * ITEMS];
-    uint32_t warp_hist[SORT_WARPS][RADIX];
+    uint64_t keys[NT * ITEMS];
+    uint32_t warp_hist[NT / 32][RADIX + 1];   // +1: the same digit of different warps falls in different banks
     uint32_t local_excl[RADIX];   // exclusive offset of digit inside this tile
     uint32_t bin_offset[RADIX];   // global destination of the tile's first key of digit d, minus local_excl
-    uint32_t s_h[SORT_WARPS], s_l[SORT_WARPS];
+    uint32_t s_h[RADIX / 32], s_l[RADIX / 32];
     uint32_t tile;
     uint32_t pad[3];
-    uint32_t vals[SORT_THREADS * ITEMS];     // last: keys-only passes do not allocate it
+    uint32_t vals[NT * ITEMS];     // last: keys-only passes do not allocate it
 };
 using SortSmem = SortSmemT<16>;
 
 // One pass: tile t of the input is ranked locally (stable), its per-digit counts are chained to the
 // previous tiles by decoupled look-back, then keys/values are scattered through shared memory so that
 // the global writes are coalesced per digit run.
-template <bool HAS_VALS, int MINB, int SORT_ITEMS>
-__global__ void __launch_bounds__(SORT_THREADS, MINB)
+template <bool HAS_VALS, int MINB, int SORT_ITEMS, int NT = 256>
+__global__ void __launch_bounds__(NT, MINB)
 onesweep_pass_kernel(int shift, int bits, const __grid_constant__ SortTab tab) {
+    constexpr int SORT_THREADS = NT;
+    constexpr int SORT_WARPS = NT / 32;
     constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SortSmemT<SORT_ITEMS>& S = *reinterpret_cast<SortSmemT<SORT_ITEMS>*>(smem_raw);
+    SortSmemT<SORT_ITEMS, NT>& S = *reinterpret_cast<SortSmemT<SORT_ITEMS, NT>*>(smem_raw);
     const SortView& sv = tab.v[blockIdx.y];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (sv.overflow != nullptr && *sv.overflow != 0u) return;
     const int64_t n = sv.n_ptr ? (int64_t)min(*sv.n_ptr, tab.capacity) : (int64_t)sv.n_fixed;
     if ((int64_t)blockIdx.x * SORT_TILE >= n) return;   // launched over the capacity; tickets only order live CTAs
     if (tid == 0) S.tile = atomicAdd(sv.ticket, 1u);
-    for (int i = tid; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&S.warp_hist[0][0])[i] = 0;
+    for (int i = tid; i < SORT_WARPS * (RADIX + 1); i += SORT_THREADS) (&S.warp_hist[0][0])[i] = 0;
     __syncthreads();
     const uint32_t tile = S.tile;
     const int64_t tile_base = (int64_t)tile * SORT_TILE;
@@ -310,26 +312,54 @@ onesweep_pass_kernel(int shift, int bits, const __grid_constant__ SortTab tab) {
     // order (the __syncwarp keeps the atomics of successive items ordered), but nothing waits for an
     // atomic's return value until all have been issued, so the latencies overlap.
     const uint32_t lt_mask = (1u << lane) - 1u;
-    uint32_t info[SORT_ITEMS];   // leader lane | rank inside the digit group << 8
+    // fast path: the warp's digits span at most 4 consecutive values (the exponent byte of depth, the top tile
+    // bits): one ballot per (value, item) gives the stable ranks with full ILP -- the generic path below would
+    // chain ITEMS shared-memory atomics on the same one or two addresses
+    uint32_t dmin = 0xffffffffu, dmax = 0u;
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; ++i) {
         const uint32_t d = (uint32_t)(key[i] >> shift) & mask;
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
-        const int leader = __ffs(peers) - 1;
-        uint32_t pre = 0;
-        if (lane == leader) pre = atomicAdd(&S.warp_hist[warp][d], (uint32_t)__popc(peers));
-        rank[i] = pre;
-        info[i] = (uint32_t)leader | ((uint32_t)__popc(peers & lt_mask) << 8);
-        __syncwarp();
+        dmin = min(dmin, d);
+        dmax = max(dmax, d);
     }
+    dmin = __reduce_min_sync(0xffffffffu, dmin);
+    dmax = __reduce_max_sync(0xffffffffu, dmax);
+    if (dmax - dmin < 4u) {
+        for (uint32_t dv = dmin; dv <= dmax; ++dv) {
+            uint32_t run = 0;
 #pragma unroll
-    for (int i = 0; i < SORT_ITEMS; ++i)
-        rank[i] = __shfl_sync(0xffffffffu, rank[i], (int)(info[i] & 31u)) + (info[i] >> 8);
+            for (int i = 0; i < SORT_ITEMS; ++i) {
+                const bool mine = ((uint32_t)(key[i] >> shift) & mask) == dv;
+                const uint32_t bal = __ballot_sync(0xffffffffu, mine);
+                if (mine) rank[i] = run + __popc(bal & lt_mask);
+                run += __popc(bal);
+            }
+            if (lane == 0) S.warp_hist[warp][dv] = run;
+        }
+    } else {
+        uint32_t info[SORT_ITEMS];   // leader lane | rank inside the digit group << 8
+#pragma unroll
+        for (int i = 0; i < SORT_ITEMS; ++i) {
+            const uint32_t d = (uint32_t)(key[i] >> shift) & mask;
+            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            const int leader = __ffs(peers) - 1;
+            uint32_t pre = 0;
+            if (lane == leader) pre = atomicAdd(&S.warp_hist[warp][d], (uint32_t)__popc(peers));
+            rank[i] = pre;
+            info[i] = (uint32_t)leader | ((uint32_t)__popc(peers & lt_mask) << 8);
+            __syncwarp();
+        }
+#pragma unroll
+        for (int i = 0; i < SORT_ITEMS; ++i)
+            rank[i] = __shfl_sync(0xffffffffu, rank[i], (int)(info[i] & 31u)) + (info[i] >> 8);
+    }
     __syncthreads();
-    // ---- per-digit: exclusive prefix over warps, tile total, look-back --------------------------
-    uint32_t bin_total = 0;
-    {
-        const int d = tid;  // SORT_THREADS == RADIX
+    // ---- per-digit (threads 0..255): exclusive prefix over warps, tile total, look-back --------------
+    uint32_t bin_total = 0, pub = 0, h = 0, hinc = 0, linc = 0;
+    uint32_t* col = nullptr;
+    uint32_t* my = nullptr;
+    if (tid < RADIX) {
+        const int d = tid;
 #pragma unroll
         for (int w = 0; w < SORT_WARPS; ++w) {
             const uint32_t t = S.warp_hist[w][d];
@@ -337,19 +367,18 @@ onesweep_pass_kernel(int shift, int bits, const __grid_constant__ SortTab tab) {
             bin_total += t;
         }
         // padding keys (~0) of a partial tile landed in the top digit: not part of the data
-        uint32_t pub = bin_total;
+        pub = bin_total;
         if (d == (int)mask) pub -= (uint32_t)(SORT_TILE - valid);
-        uint32_t* col = sv.desc + d;   // descriptor of tile t for this digit: col[t * RADIX] (coalesced across d)
-        uint32_t* my = col + (size_t)tile * RADIX;
+        col = sv.desc + d;   // descriptor of tile t for this digit: col[t * RADIX] (coalesced across d)
+        my = col + (size_t)tile * RADIX;
         if (tile == 0) {
             st_volatile_u32(my, DESC_INC | pub);
         } else {
             st_volatile_u32(my, DESC_AGG | pub);
         }
         // global digit start = exclusive scan of the global histogram of this digit place
-        // (block-wide scan of 256 values)
-        uint32_t h = (d <= (int)mask) ? sv.hist_pass[d] : 0u;
-        uint32_t hinc = h, linc = bin_total;
+        h = (d <= (int)mask) ? sv.hist_pass[d] : 0u;
+        hinc = h, linc = bin_total;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             uint32_t t1 = __shfl_up_sync(0xffffffffu, hinc, o);
@@ -363,10 +392,13 @@ onesweep_pass_kernel(int shift, int bits, const __grid_constant__ SortTab tab) {
             S.s_h[warp] = hinc;
             S.s_l[warp] = linc;
         }
-        __syncthreads();
+    }
+    __syncthreads();
+    if (tid < RADIX) {
+        const int d = tid;
         uint32_t hoff = 0, loff = 0;
 #pragma unroll
-        for (int w = 0; w < SORT_WARPS; ++w) {
+        for (int w = 0; w < RADIX / 32; ++w) {
             if (w < warp) {
                 hoff += S.s_h[w];
                 loff += S.s_l[w];
@@ -468,6 +500,9 @@ static cudaError_t ensure_sort_attr() {
         e = cudaFuncSetAttribute(onesweep_pass_kernel<false, 2, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)sizeof(SortSmemT<24>));
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(onesweep_pass_kernel<false, 2, 12, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(SortSmemT<12, 512>));
+        if (e != cudaSuccess) return e;
         attr_set = true;
     }
     return cudaSuccess;
@@ -540,6 +575,11 @@ cudaError_t launch_sort_batch(const BatchTab& tab, cudaStream_t st) {
                 case 24:
                     onesweep_pass_kernel<false, 2, 24><<<grid, SORT_THREADS, offsetof(SortSmemT<24>, vals), st>>>(sh, bits, t);
                     break;
+                case 512: {
+                    using SM = SortSmemT<12, 512>;
+                    onesweep_pass_kernel<false, 2, 12, 512><<<grid, 512, offsetof(SM, vals), st>>>(sh, bits, t);
+                    break;
+                }
                 default:
                     onesweep_pass_kernel<false, 3, 16><<<grid, SORT_THREADS, offsetof(SortSmemT<16>, vals), st>>>(sh, bits, t);
             }
