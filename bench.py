@@ -65,7 +65,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -252,7 +252,6 @@ def main():
         step()
     e1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     launches = _lib.launch_count() - l0
     if renderer.overflowed():
         raise SystemExit("bench: a view exceeded its binning capacity during the timed region (invalid run)")
@@ -359,6 +358,8 @@ def main():
 
     e2e_dropin = time_e2e(e2e_step)
     e2e_value = time_e2e(e2e_step_batched)
+    # clocks / throttle reasons were sampled (20 ms period) from the start of the resident timed region to here
+    clocks = sampler.stop() if rank == 0 else None
     if vbr.check_overflow():
         raise SystemExit("bench: binning capacity overflow in the e2e region (invalid run)")
 
