@@ -41,7 +41,8 @@ def parse_args():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--views-per-gpu", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-tiles", type=int, default=64)
+    ap.add_argument("--cpu-sample-tiles", type=int, default=0,
+                    help="tiles of the CPU-oracle sample (0: 512 for the cpu_baseline leg, 256 per reference-arm step)")
     return ap.parse_args()
 
 
@@ -159,7 +160,7 @@ def run_reference(args):
     times = []
     info = {}
     for i in range(args.warmup + args.steps):
-        t, info = cpu_oracle_render_time(scene, cams[0], args.cpu_sample_tiles, threads)
+        t, info = cpu_oracle_render_time(scene, cams[0], args.cpu_sample_tiles or 256, threads)
         if i >= args.warmup:
             times.append(t)
     sec = sum(times) / len(times)
@@ -434,7 +435,7 @@ def main():
                 "avg_ms": dom["avg_ms"], "counters": cnt}
         if N == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            sec, info = cpu_oracle_render_time(scene, cams_host[0], args.cpu_sample_tiles, threads)
+            sec, info = cpu_oracle_render_time(scene, cams_host[0], args.cpu_sample_tiles or 512, threads)
             cpu_base = {"value": 1.0 / sec, "unit": UNIT, "cores": threads, "kind": "port",
                         "sample": (f"1 view: preprocess+sort of all {P} Gaussians, blend fwd+bwd on {info['tiles']} of "
                                    f"{info['of_tiles']} tiles scaled x{info['of_tiles'] / info['tiles']:.1f}; "

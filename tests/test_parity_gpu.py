@@ -390,3 +390,102 @@ def test_view_batch_rasterizer_autograd_matches_per_view_operator():
     m2c = torch.zeros(V, P, 3, device=dev, requires_grad=True)
     C2, _, _, _ = rast(rss, means3D=m3b, means2D=m2c, opacities=opb, shs=shb, scales=sclb, rotations=rotb)
     assert float((C2 - C).abs().max()) == 0.0
+
+
+@pytest.mark.timeout(600)
+def test_config2_shape_single_view_parity():
+    """BASELINE.json configs[1] shape (100K Gaussians, 512x512, SH degree 0), one of its views, against the oracle."""
+    scene, cams = scenes.make_workload("config2_100k_512_sh0_b4", views=1)
+    cam = cams[0]
+    s = oracle_settings(cam, 0)
+    grads = scenes.pixel_grads(512, 512, 5)
+    orc = _run_oracle(scene, s, grads=grads)
+    cu = _run_cuda(scene, s, grads=grads)
+    _check_forward(cu, orc, s)
+    _check_grads(cu, orc)
+
+
+@pytest.mark.timeout(600)
+def test_full_size_properties_headline_workload():
+    """BASELINE headline size (1M Gaussians, SH3, 512x512): size-independent properties of the CUDA path --
+    sortedness, range partition, bounds, determinism of the integer outputs, linearity of backward in the
+    upstream gradient, batched == single-view."""
+    from b200splat import batched, ops
+    scene, cams_h = scenes.make_workload("headline_1m_512_sh3", views=2)
+    dev = "cuda"
+    d = lambda t: t.to(dev).contiguous()
+    m3, sh, op, scl, rot = map(d, (scene.means3D, scene.shs, scene.opacities, scene.scales, scene.rotations))
+    P, H, W = m3.shape[0], 512, 512
+    cams = [ops.make_cam(cuda_settings(oracle_settings(c, 3)), dev) for c in cams_h]
+    color, radii, depth, alpha, st = ops.forward(cams[0], m3, sh, None, op, scl, rot, None)
+    v = ops.forward_views(cams[0], st)
+    R = st.num_rendered
+    assert R == int(v["tiles_touched"].long().sum()) == int(v["point_offsets"][-1])
+    ks = v["keys_sorted"]
+    assert bool((ks[1:] >= ks[:-1]).all()), "keys not sorted"
+    assert bool((torch.sort(v["point_list"].long()).values == torch.sort(
+        torch.repeat_interleave(torch.arange(P, device=dev), v["tiles_touched"].long())).values).all()), \
+        "point list is not a permutation of the duplicated indices"
+    rg = v["ranges"].long()
+    lens = rg[:, 1] - rg[:, 0]
+    assert int(lens.sum()) == R and bool((lens >= 0).all())
+    tiles_of = (ks >> 32)
+    nz = lens > 0
+    assert bool((tiles_of[rg[nz, 0]] == torch.nonzero(nz).reshape(-1)).all())
+    # depth bits of the key == float bits of the Gaussian's depth
+    assert torch.equal((ks & 0xFFFFFFFF).to(torch.int32), v["depths"][v["point_list"].long()].view(torch.int32))
+    nc = v["n_contrib"].long().reshape(H // 16, 16, W // 16, 16).permute(0, 2, 1, 3).reshape(-1, 256)
+    assert bool((nc.max(1).values <= lens).all())
+    assert torch.isfinite(color).all() and float(alpha.min()) >= 0 and float(alpha.max()) <= 1 + 1e-5
+    assert bool(((radii > 0) == (v["tiles_touched"] > 0)).all())
+    # second forward: integer outputs identical (deterministic), images identical
+    color2, radii2, _, alpha2, st2 = ops.forward(cams[0], m3, sh, None, op, scl, rot, None)
+    v2 = ops.forward_views(cams[0], st2)
+    assert torch.equal(radii, radii2) and torch.equal(v["keys_sorted"], v2["keys_sorted"])
+    assert torch.equal(v["point_list"], v2["point_list"]) and torch.equal(color, color2)
+    # backward is linear in the upstream gradient
+    g1 = tuple(d(g) for g in scenes.pixel_grads(H, W, 3))
+    ga = ops.backward(cams[0], st, m3, sh, None, op, scl, rot, None, radii, alpha, *g1)
+    gb = ops.backward(cams[0], st, m3, sh, None, op, scl, rot, None, radii, alpha, *(2.5 * g for g in g1))
+    for k in ("means3D", "means2D", "shs", "opacities", "scales", "rotations"):
+        assert rel_err(gb[k], 2.5 * ga[k]) < 1e-4, k
+        culled = radii == 0
+        assert float(ga[k][culled].abs().max()) == 0.0 if bool(culled.any()) else True
+    # batched path == single-view path at full size
+    br = batched.BatchRenderer(P, sh.shape[1], H, W, dev, views=2)
+    pgs = [g1, tuple(d(g) for g in scenes.pixel_grads(H, W, 4))]
+    br.step(cams, m3, sh, None, op, scl, rot, pgs)
+    assert not br.overflowed()
+    assert torch.equal(br.ws[0].radii[0], radii) and float((br.ws[0].color[0] - color).abs().max()) < 1e-6
+    _, radii_b, _, alpha_b, st_b = ops.forward(cams[1], m3, sh, None, op, scl, rot, None)
+    gsum = {k: ga[k] + ops.backward(cams[1], st_b, m3, sh, None, op, scl, rot, None, radii_b, alpha_b, *pgs[1])[k]
+            for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+    for k, t in gsum.items():
+        assert rel_err(br.packed.views[k], t) < 1e-4, k
+
+
+def test_stress_shape_pair_mode_and_large_tile_count():
+    """Pair-sort fallback (index does not fit beside the key): 600K Gaussians at 1024x1024 (T = 4096, 45 key bits)
+    -- the stress config's tile count -- batched == per-view, sortedness."""
+    from b200splat import batched, ops
+    P, H, W = 600_000, 1024, 1024
+    sc = scenes.make_scene(P, 0, 0.5, seed=5)
+    cams_h = scenes.mvdream_cameras(2, H, W, seed=6)
+    dev = "cuda"
+    d = lambda t: t.to(dev).contiguous()
+    m3, sh, op, scl, rot = map(d, (sc.means3D, sc.shs, sc.opacities, sc.scales, sc.rotations))
+    cams = [ops.make_cam(cuda_settings(oracle_settings(c, 0)), dev) for c in cams_h]
+    color, radii, depth, alpha, st = ops.forward(cams[0], m3, sh, None, op, scl, rot, None)
+    v = ops.forward_views(cams[0], st)
+    ks = v["keys_sorted"]
+    assert bool((ks[1:] >= ks[:-1]).all())
+    assert int((v["ranges"][:, 1] - v["ranges"][:, 0]).sum()) == st.num_rendered
+    pgs = [tuple(d(g) for g in scenes.pixel_grads(H, W, 7 + i)) for i in range(2)]
+    pk = batched.PackedGrads(P, 1, dev)
+    batched.render_views_fwd_bwd(cams, m3, sh, None, op, scl, rot, pgs, pk)
+    br = batched.BatchRenderer(P, 1, H, W, dev, views=2)
+    br.step(cams, m3, sh, None, op, scl, rot, pgs)
+    assert not br.overflowed()
+    assert torch.equal(br.ws[0].radii[0], radii) and float((br.ws[0].color[0] - color).abs().max()) < 1e-6
+    for k in ("means3D", "shs", "opacities", "scales", "rotations"):
+        assert rel_err(br.packed.views[k], pk.views[k]) < 1e-4, k
