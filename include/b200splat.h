@@ -259,7 +259,7 @@ int b200splat_inclusive_scan_u32(int64_t n, const uint32_t* in, uint32_t* out, v
 
 /* Views into the buffers of a finished forward (device pointers into the caller's buffers), for
  * the bit-exact parity checks: tiles_touched (P) u32, point_offsets (P) u32, depths (P) f32,
- * sorted keys (R) u64, point_list (R) u32, ranges (T,2) u32, n_contrib (H*W) u32 (1-based index of the
+ * sorted pair words (R) u64, ranges (T,2) u32, n_contrib (H*W) u32 (1-based index of the
  * last blended list entry), n_visited (H*W) u32 (list entries traversed before the pixel stopped). */
 typedef struct b200splat_forward_views {
     const uint32_t* tiles_touched;
@@ -273,9 +273,10 @@ typedef struct b200splat_forward_views {
     const uint32_t* n_contrib;
     const uint32_t* n_visited;
     const uint32_t* status; /* [0] != 0: binning capacity overflow */
-    /* > 0: the sort ran on packed words -- keys_sorted[i] holds (key << packed_idx_bits) | gaussian_index and
-     * point_list is unused; 0: keys_sorted / point_list are the plain sorted pair arrays */
+    /* keys_sorted[i] holds the sorted pair WORD (tile_id << packed_idx_bits) | gaussian_index (packed_idx_bits = 32);
+     * upstream's 64-bit key of entry i is (tile_id << 32) | float_bits(depths[gaussian_index]); point_list is unused */
     int64_t packed_idx_bits;
+    const uint64_t* gaussian_order; /* (P) words (depth_bits << 32 | index) sorted by depth: the per-view depth order */
 } b200splat_forward_views;
 
 int b200splat_forward_views_get(int32_t P, int32_t H, int32_t W, int64_t num_rendered,

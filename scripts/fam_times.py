@@ -1,0 +1,6 @@
+import json,sys
+for line in sys.stdin:
+    line=line.strip()
+    if line.startswith('{"metric"'):
+        d=json.loads(line)
+        print(round(d["value"],1), {k["kernel"]: round(k["avg_ms"]*1000,1) for k in d["kernels"]})

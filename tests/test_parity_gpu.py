@@ -144,8 +144,14 @@ def test_intermediates_bit_exact():
     assert st.num_rendered == binned["num_rendered"]
     assert torch.equal(radii.cpu(), pre["radii"])
     assert torch.equal(v["tiles_touched"], pre["tiles_touched"])
-    assert torch.equal(v["point_offsets"], binned["point_offsets"])
     vis = pre["visible"]
+    # the Gaussians are depth-sorted first (stable; culled ones last) and the offsets are the scan in THAT order
+    dbits = pre["depth"].contiguous().view(torch.int32).long() & 0xFFFFFFFF
+    dbits = torch.where(vis, dbits, torch.full_like(dbits, 0xFFFFFFFF))
+    order = torch.sort(dbits, stable=True).indices
+    assert torch.equal(v["gaussian_order"] & 0xFFFFFFFF, order)
+    assert torch.equal(v["point_offsets"].long(), torch.cumsum(pre["tiles_touched"].long()[order], 0))
+    assert int(v["point_offsets"][-1]) == int(binned["point_offsets"][-1])
     assert torch.equal(v["depths"][vis].view(torch.int32), pre["depth"][vis].contiguous().view(torch.int32))
     assert torch.equal(v["keys_sorted"], binned["keys_sorted"])
     assert torch.equal(v["point_list"], binned["point_list"])

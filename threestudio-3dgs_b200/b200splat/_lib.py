@@ -65,7 +65,8 @@ class BackwardArgs(C.Structure):
 class ForwardViews(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "tiles_touched", "point_offsets", "depths", "gauss2d", "cov3D", "keys_sorted", "point_list",
-        "ranges", "n_contrib", "n_visited", "status")] + [("packed_idx_bits", C.c_int64)]
+        "ranges", "n_contrib", "n_visited", "status")] + [("packed_idx_bits", C.c_int64),
+                                                            ("gaussian_order", C.c_void_p)]
 
 
 PP = C.POINTER(C.c_void_p)   # host array of device pointers

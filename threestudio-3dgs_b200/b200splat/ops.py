@@ -251,13 +251,12 @@ def forward_views(cam: Cam, st: ForwardState):
         return buf[off:off + nb].view(dtype).clone()
 
     R, P = st.num_rendered, st.P
-    keys = view(st.binning, v.keys_sorted, R, torch.int64) if R else torch.empty(0, dtype=torch.int64, device=dev)
-    if v.packed_idx_bits > 0:      # unpack (key << bits | idx) words
-        b = int(v.packed_idx_bits)
-        plist = (keys & ((1 << b) - 1)).to(torch.int32)
-        keys = (keys >> b) & ((1 << (64 - b)) - 1)
-    else:
-        plist = view(st.binning, v.point_list, R, torch.int32) if R else torch.empty(0, dtype=torch.int32, device=dev)
+    words = view(st.binning, v.keys_sorted, R, torch.int64) if R else torch.empty(0, dtype=torch.int64, device=dev)
+    depths = view(st.geom, v.depths, P, torch.float32)
+    # sorted pair words are (tile << 32 | gaussian); upstream's key = (tile << 32) | float_bits(depth[gaussian])
+    plist = (words & 0xFFFFFFFF).to(torch.int32)
+    dbits = depths.view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    keys = ((words >> 32) << 32) | (dbits[plist.long()] if R else words)
     return dict(
         tiles_touched=view(st.geom, v.tiles_touched, P, torch.int32),
         point_offsets=view(st.geom, v.point_offsets, P, torch.int32),
@@ -265,6 +264,7 @@ def forward_views(cam: Cam, st: ForwardState):
         gauss2d=view(st.geom, v.gauss2d, P * 12, torch.float32).reshape(P, 12),
         keys_sorted=keys,
         point_list=plist,
+        gaussian_order=view(st.geom, v.gaussian_order, P, torch.int64),
         ranges=view(st.image, v.ranges, T * 2, torch.int32).reshape(T, 2),
         n_contrib=view(st.image, v.n_contrib, cam.H * cam.W, torch.int32).reshape(cam.H, cam.W),
         n_visited=view(st.image, v.n_visited, cam.H * cam.W, torch.int32).reshape(cam.H, cam.W),

@@ -60,6 +60,9 @@ size_t geom_layout(int P, void* base, GeomViews* v) {
     GeomViews g;
     const size_t n = (size_t)(P > 0 ? P : 1);
     g.rec = carve<float>(p, n * REC_FLOATS);
+    g.gwords[0] = carve<uint64_t>(p, n);
+    g.gwords[1] = carve<uint64_t>(p, n);
+    g.gsort_ws = carve<char>(p, sort_workspace_bytes((int64_t)n));
     g.depths = carve<float>(p, n);
     g.clamped = carve<uint8_t>(p, n);
     g.tiles_touched = carve<uint32_t>(p, n);
@@ -125,8 +128,8 @@ static int higher_msb(uint32_t n) {
 
 // parity of the pass count decides which ping-pong half holds the sorted data
 static int sorted_sel_for(int T) {
-    const int end_bit = 32 + higher_msb((uint32_t)T);
-    return ((end_bit + 7) / 8) & 1;
+    const int tile_bits = higher_msb((uint32_t)T);
+    return ((tile_bits + 7) / 8) & 1;
 }
 
 // shared (view independent) part of the batch table from the first camera
@@ -146,12 +149,10 @@ static int init_table(const b200splat_camera& c, int P, int M, bool has_sh, Batc
         deg = -1;
     }
     tab->sh_degree = deg;
-    tab->end_bit = 32 + higher_msb((uint32_t)(tab->grid_x * tab->grid_y));
-    // pack the Gaussian index into the key word when both fit in 64 bits (B200SPLAT_SORT=pairs disables)
-    int ib = 1;
-    while (ib < 32 && (1ll << ib) < (long long)(P > 1 ? P : 2)) ++ib;
-    static const bool pairs_only = [] { const char* e = getenv("B200SPLAT_SORT"); return e && strcmp(e, "pairs") == 0; }();
-    tab->idx_bits = (!pairs_only && tab->end_bit + ib <= 64) ? ib : 0;
+    // pair words are (tile << 32 | gaussian index): only the tile bits are sorted (the Gaussians are emitted in
+    // depth order), upstream's bit count 32 + getHigherMsb(T) minus the 32 depth bits
+    tab->end_bit = higher_msb((uint32_t)(tab->grid_x * tab->grid_y));
+    tab->idx_bits = 32;
     return B200SPLAT_OK;
 }
 
@@ -174,6 +175,8 @@ static void fill_geom(int P, void* geom, ViewTab* vt) {
     geom_layout(P, geom, &g);
     vt->rec = g.rec, vt->depths = g.depths, vt->clamped = g.clamped;
     vt->tiles_touched = g.tiles_touched, vt->point_offsets = g.point_offsets;
+    vt->gwords[0] = g.gwords[0], vt->gwords[1] = g.gwords[1];
+    sort_workspace_views(g.gsort_ws, &vt->ghist, &vt->gtickets, &vt->gdesc);
     vt->scan_ticket = reinterpret_cast<uint32_t*>(g.scan_ws);
     vt->scan_desc = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(g.scan_ws) + 16);
 }
@@ -197,6 +200,7 @@ static void fill_binning(int64_t capacity, void* binning, ViewTab* vt) {
 // ---- per-family CUDA-event timing ---------------------------------------------------------------
 struct ProfRecord {
     int family;
+    bool counted;   // false: time is added to the family but it is not a separate launch group
     cudaEvent_t a, b;
 };
 static std::mutex g_prof_mu;
@@ -219,11 +223,12 @@ struct ProfScope {
     bool on = false;
     ProfRecord r{};
     cudaStream_t st;
-    ProfScope(int family, cudaStream_t s) : st(s) {
+    ProfScope(int family, cudaStream_t s, bool counted = true) : st(s) {
         std::lock_guard<std::mutex> lk(g_prof_mu);
         if (!g_prof_on) return;
         on = true;
         r.family = family;
+        r.counted = counted;
         r.a = get_event();
         r.b = get_event();
         cudaEventRecord(r.a, st);
@@ -337,6 +342,9 @@ int b200splat_forward(const b200splat_forward_args* a) {
         CU(launch_preprocess(tab, a->means3D, a->scales, a->rotations, a->opacities, a->shs, a->colors_precomp,
                              a->cov3D_precomp, st)); }
         DEBUG_SYNC(a->cam, st, "preprocess");
+        { ProfScope ps(3, st, /*counted=*/false);
+        CU(launch_gaussian_sort(tab, st)); }
+        DEBUG_SYNC(a->cam, st, "depth sort");
         { ProfScope ps(1, st);
         CU(launch_scan_batch(tab, st)); }
         DEBUG_SYNC(a->cam, st, "scan");
@@ -405,6 +413,9 @@ int b200splat_forward_batched(const b200splat_batch_forward_args* a) {
     CU(launch_preprocess(tab, a->means3D, a->scales, a->rotations, a->opacities, a->shs, a->colors_precomp, nullptr,
                          st)); }
     DEBUG_SYNC(a->cams[0], st, "preprocess");
+    { ProfScope ps(3, st, /*counted=*/false);
+    CU(launch_gaussian_sort(tab, st)); }
+    DEBUG_SYNC(a->cams[0], st, "depth sort");
     { ProfScope ps(1, st);
     CU(launch_scan_batch(tab, st)); }
     DEBUG_SYNC(a->cams[0], st, "scan");
@@ -577,6 +588,7 @@ int b200splat_forward_views_get(int32_t P, int32_t H, int32_t W, int64_t num_ren
         out->point_offsets = g.point_offsets;
         out->depths = g.depths;
         out->gauss2d = g.rec;
+        out->gaussian_order = g.gwords[0];
     }
     if (binning_buffer && num_rendered > 0) {   // num_rendered = the capacity the buffer was laid out for
         BinningViews b;
@@ -585,10 +597,7 @@ int b200splat_forward_views_get(int32_t P, int32_t H, int32_t W, int64_t num_ren
         const int sel = sorted_sel_for(gx * gy);
         out->keys_sorted = b.keys[sel];
         out->point_list = b.vals[sel];
-        BatchTab t;
-        b200splat_camera c{};
-        c.image_height = H, c.image_width = W;
-        if (init_table(c, P, 0, false, &t) == B200SPLAT_OK) out->packed_idx_bits = t.idx_bits;
+        out->packed_idx_bits = 32;
     }
     if (image_buffer) {
         ImageViews im;
@@ -616,7 +625,7 @@ int b200splat_profile_read(float* ms, int64_t* count) {
         cudaError_t e = cudaEventSynchronize(r.b);
         if (e == cudaSuccess) e = cudaEventElapsedTime(&t, r.a, r.b);
         if (e != cudaSuccess) return fail(B200SPLAT_ERR_CUDA, "profile event: %s", cudaGetErrorString(e));
-        if (r.family >= 0 && r.family < B200SPLAT_NUM_FAMILIES) ms[r.family] += t, count[r.family] += 1;
+        if (r.family >= 0 && r.family < B200SPLAT_NUM_FAMILIES) ms[r.family] += t, count[r.family] += r.counted ? 1 : 0;
         g_event_pool.push_back(r.a);
         g_event_pool.push_back(r.b);
     }

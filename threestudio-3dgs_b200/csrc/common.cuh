@@ -61,6 +61,11 @@ struct ViewTab {
     uint32_t* point_offsets;
     uint32_t* scan_ticket;
     uint64_t* scan_desc;
+    // depth order of the Gaussians: words (depth_bits << 32 | index), ping-pong, + its sort workspace
+    uint64_t* gwords[2];
+    uint32_t* ghist;
+    uint32_t* gtickets;
+    uint32_t* gdesc;
     // binning buffer
     uint64_t* keys[2];
     uint32_t* vals[2];
@@ -91,9 +96,9 @@ struct BatchTab {
     int W, H, grid_x, grid_y;
     float scale_modifier;
     uint32_t capacity;         // pairs each view's key/value arrays can hold
-    int end_bit;               // sorted key bits [0, end_bit)
+    int end_bit;               // tile-id bits: pair words (tile << 32 | index) are sorted on bits [32, 32 + end_bit)
     int sort_tiles_cap;        // ceil(capacity / SORT_TILE)
-    int idx_bits;              // > 0: key and Gaussian index packed in ONE u64 (key << idx_bits | idx), no value arrays
+    int idx_bits;              // index bits of a pair word (32)
     uint32_t* tile_order;      // [V * T] entries (view * T + tile), longest list first
     ViewTab v[MAX_VIEWS];
 };
@@ -101,6 +106,8 @@ struct BatchTab {
 // ---- buffer layouts ---------------------------------------------------------------------------
 struct GeomViews {
     float* rec;              // P * 12
+    uint64_t* gwords[2];     // P each
+    void* gsort_ws;
     float* depths;           // P
     uint8_t* clamped;        // P   (bit c set: channel c clamped at 0)
     uint32_t* tiles_touched; // P
@@ -137,7 +144,8 @@ cudaError_t launch_mark_visible(int P, const float* means3D, const float* view, 
                                 uint8_t* present, cudaStream_t st);
 
 size_t scan_workspace_bytes(int64_t n);
-cudaError_t launch_scan_batch(const BatchTab& tab, cudaStream_t st);   // tiles_touched -> point_offsets, all views
+cudaError_t launch_scan_batch(const BatchTab& tab, cudaStream_t st);   // tiles_touched (in depth order) -> point_offsets
+cudaError_t launch_gaussian_sort(const BatchTab& tab, cudaStream_t st);   // gwords[0] sorted by depth bits (stable)
 cudaError_t launch_inclusive_scan(int64_t n, const uint32_t* in, uint32_t* out, void* ws, cudaStream_t st);
 size_t sort_workspace_bytes(int64_t n);
 void sort_workspace_views(void* ws, uint32_t** hist, uint32_t** tickets, uint32_t** desc);

@@ -108,6 +108,7 @@ preprocess_kernel(const __grid_constant__ BatchTab tab, const float* __restrict_
         for (int v = 0; v < V; ++v) {
             tab.v[v].radii[idx] = 0;
             tab.v[v].tiles_touched[idx] = 0;
+            tab.v[v].gwords[0][idx] = 0xFFFFFFFF00000000ull | (uint64_t)(uint32_t)idx;   // culled: sorts last
         }
         return;
     }
@@ -174,6 +175,7 @@ preprocess_kernel(const __grid_constant__ BatchTab tab, const float* __restrict_
         const ViewTab& vt = tab.v[v];
         int my_radius = 0;
         uint32_t my_tiles = 0;
+        float my_depth = 0.f;
         if ((front >> v) & 1u) {
             const float* mV = sV[v];
             const float* mP = sP[v];
@@ -243,22 +245,26 @@ preprocess_kernel(const __grid_constant__ BatchTab tab, const float* __restrict_
                     o[1] = make_float4(a * det_inv, opac, tvz, rgb[0]);
                     o[2] = make_float4(rgb[1], rgb[2], thr, 0.0f);
                     vt.depths[idx] = tvz;
+                    my_depth = tvz;
                     vt.clamped[idx] = bits;
                 }
             }
         }
         vt.radii[idx] = my_radius;
         vt.tiles_touched[idx] = my_tiles;
+        // word of the per-view depth sort of the Gaussians (culled ones sort last and emit nothing)
+        vt.gwords[0][idx] = ((uint64_t)(my_radius > 0 ? __float_as_uint(my_depth) : 0xFFFFFFFFu) << 32) |
+                            (uint64_t)(uint32_t)idx;
     }
 }
 
-// key = (tile_id << 32) | float_bits(depth); value = Gaussian index; tiles y-major then x.
-// Fused: the per-digit-place histograms the onesweep sort needs (hist[pass][256]) are accumulated here --
-// all keys of one Gaussian share their low 32 bits, so the four depth digits cost one weighted shared-memory
-// atomic per Gaussian instead of one per key, and the separate histogram read of the key array disappears.
-// blockIdx.y = view.  Pairs beyond the binning capacity are dropped and flagged (STATUS_OVERFLOW).
-// When tab.idx_bits > 0 the Gaussian index rides in the low bits of the same 64-bit word (no value array):
-// one third less sort traffic; the sort then works on bits [idx_bits, idx_bits + end_bit).
+// duplicateWithKeys over the Gaussians IN DEPTH ORDER: position i of the depth-sorted list emits one word
+// (tile_id << 32 | gaussian) per tile of its rectangle (tiles y-major then x) at point_offsets[i-1].  The words
+// of one tile are therefore already in (depth, index) order; a STABLE sort on the tile bits alone (2 passes for
+// 1024 tiles instead of 6 passes over 43 key bits) finishes the job and yields exactly the order upstream's sort
+// of (tile << 32 | depth) keys gives.  Fused: per-tile pair counts (-> tile ranges by an exclusive scan, and the
+// digit histograms of the tile-bit sort).  blockIdx.y = view.  Pairs beyond the binning capacity are dropped and
+// flagged (STATUS_OVERFLOW).
 constexpr int DUP_MAX_TILES = 8192;   // tile histogram kept in shared memory up to this many tiles
 __global__ void __launch_bounds__(256)
 duplicate_kernel(const __grid_constant__ BatchTab tab) {
@@ -269,67 +275,38 @@ duplicate_kernel(const __grid_constant__ BatchTab tab) {
     const int gx = tab.grid_x, gy = tab.grid_y;
     const int T = gx * gy;
     const bool tile_hist = T <= DUP_MAX_TILES;
-    const int idx_bits = tab.idx_bits;
     uint32_t* s_hist = s_dyn;
     uint32_t* s_tile = s_dyn + passes * 256;
     for (int i = threadIdx.x; i < passes * 256 + (tile_hist ? T : 0); i += blockDim.x) s_dyn[i] = 0;
     __syncthreads();
     const int32_t* __restrict__ radii = vt.radii;
     const uint32_t* __restrict__ point_offsets = vt.point_offsets;
-    uint64_t* __restrict__ keys = vt.keys[0];
-    uint32_t* __restrict__ vals = vt.vals[0];
-    const int lane = threadIdx.x & 31;
-    const int P_round = (tab.P + 31) / 32 * 32;   // warps stay converged for the votes below
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < P_round; idx += gridDim.x * blockDim.x) {
-        const int rad = idx < tab.P ? radii[idx] : 0;
-        bool live = rad > 0;
-        uint32_t off = 0, d32 = 0, ntiles = 0;
-        int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-        if (live) {
-            off = (idx == 0) ? 0u : point_offsets[idx - 1];
-            const float2 xy = *reinterpret_cast<const float2*>(vt.rec + (size_t)idx * REC_FLOATS);
-            get_rect(xy.x, xy.y, (float)rad, gx, gy, x0, y0, x1, y1);
-            d32 = __float_as_uint(vt.depths[idx]);
-            ntiles = (uint32_t)((x1 - x0) * (y1 - y0));
-            if (off + ntiles > tab.capacity) {
-                atomicOr(vt.status + STATUS_OVERFLOW, 1u);
-                live = false;
-            }
+    const uint64_t* __restrict__ order = vt.gwords[0];
+    uint64_t* __restrict__ words = vt.keys[0];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < tab.P; i += gridDim.x * blockDim.x) {
+        const uint32_t g = (uint32_t)__ldg(order + i);
+        const int rad = radii[g];
+        if (rad <= 0) continue;
+        uint32_t off = (i == 0) ? 0u : point_offsets[i - 1];
+        const float2 xy = *reinterpret_cast<const float2*>(vt.rec + (size_t)g * REC_FLOATS);
+        int x0, y0, x1, y1;
+        get_rect(xy.x, xy.y, (float)rad, gx, gy, x0, y0, x1, y1);
+        const uint32_t ntiles = (uint32_t)((x1 - x0) * (y1 - y0));
+        if (off + ntiles > tab.capacity) {
+            atomicOr(vt.status + STATUS_OVERFLOW, 1u);
+            continue;
         }
-        const uint64_t dbits = (uint64_t)d32;
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            if (p < passes) {
-                const int bits = min(8, end_bit - 8 * p);
-                const uint32_t dig = (d32 >> (8 * p)) & ((1u << bits) - 1u);
-                if (p < 3) {
-                    if (live) atomicAdd(&s_hist[p * 256 + dig], ntiles);   // mantissa bytes: spread addresses
-                } else {
-                    // the exponent byte takes a handful of values: aggregate the warp's lanes per digit first
-                    const uint32_t peers = __match_any_sync(0xffffffffu, live ? dig : 0xffffffffu);
-                    const uint32_t total = __reduce_add_sync(peers, live ? ntiles : 0u);
-                    if (live && lane == __ffs(peers) - 1) atomicAdd(&s_hist[p * 256 + dig], total);
-                }
-            }
-        }
-        if (!live) continue;
         for (int ty = y0; ty < y1; ++ty) {
             for (int tx = x0; tx < x1; ++tx) {
                 const uint32_t tile = (uint32_t)(ty * gx + tx);
-                const uint64_t key = ((uint64_t)tile << 32) | dbits;
-                if (idx_bits) {
-                    keys[off] = (key << idx_bits) | (uint64_t)(uint32_t)idx;
-                } else {
-                    keys[off] = key;
-                    vals[off] = (uint32_t)idx;
-                }
+                words[off] = ((uint64_t)tile << 32) | (uint64_t)g;
                 ++off;
                 if (tile_hist) {
                     atomicAdd(&s_tile[tile], 1u);   // digit histograms of the tile bytes are derived at flush time
                 } else {
-                    for (int p = 4; p < passes; ++p) {
+                    for (int p = 0; p < passes; ++p) {
                         const int bits = min(8, end_bit - 8 * p);
-                        atomicAdd(&s_hist[p * 256 + ((tile >> (8 * (p - 4))) & ((1u << bits) - 1u))], 1u);
+                        atomicAdd(&s_hist[p * 256 + ((tile >> (8 * p)) & ((1u << bits) - 1u))], 1u);
                     }
                 }
             }
@@ -341,9 +318,9 @@ duplicate_kernel(const __grid_constant__ BatchTab tab) {
             const uint32_t c = s_tile[t];
             if (c) {
                 atomicAdd(&vt.tile_count[t], c);
-                for (int p = 4; p < passes; ++p) {
+                for (int p = 0; p < passes; ++p) {
                     const int bits = min(8, end_bit - 8 * p);
-                    atomicAdd(&s_hist[p * 256 + (((uint32_t)t >> (8 * (p - 4))) & ((1u << bits) - 1u))], c);
+                    atomicAdd(&s_hist[p * 256 + (((uint32_t)t >> (8 * p)) & ((1u << bits) - 1u))], c);
                 }
             }
         }

@@ -43,6 +43,7 @@ constexpr uint64_t FLAG_INC = 2ull << 32;
 
 struct ScanTab {
     int V;
+    const uint64_t* perm[MAX_VIEWS];   // optional: element i of the scan is in[(uint32)perm[i]] (depth order)
     const uint32_t* in[MAX_VIEWS];
     uint32_t* out[MAX_VIEWS];
     uint32_t* ticket[MAX_VIEWS];
@@ -63,7 +64,11 @@ scan_lookback_kernel(int64_t n, const __grid_constant__ ScanTab tab) {
     const uint32_t tile = s_tile;
     const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
     uint32_t v[SCAN_ITEMS];
-    if (base + SCAN_ITEMS <= n) {
+    const uint64_t* __restrict__ perm = tab.perm[view];
+    if (perm != nullptr) {
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) v[i] = (base + i < n) ? __ldg(in + (uint32_t)__ldg(perm + base + i)) : 0u;
+    } else if (base + SCAN_ITEMS <= n) {
         const uint4* p = reinterpret_cast<const uint4*>(in + base);
         uint4 a = __ldg(p), b = __ldg(p + 1);
         v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
@@ -150,6 +155,7 @@ cudaError_t launch_scan_batch(const BatchTab& tab, cudaStream_t st) {
     ScanTab s;
     s.V = tab.V;
     for (int v = 0; v < tab.V; ++v) {
+        s.perm[v] = tab.v[v].gwords[0];
         s.in[v] = tab.v[v].tiles_touched;
         s.out[v] = tab.v[v].point_offsets;
         s.ticket[v] = tab.v[v].scan_ticket;
@@ -169,6 +175,7 @@ cudaError_t launch_inclusive_scan(int64_t n, const uint32_t* in, uint32_t* out, 
     if (e != cudaSuccess) return e;
     ScanTab s;
     s.V = 1;
+    s.perm[0] = nullptr;
     s.in[0] = in;
     s.out[0] = out;
     s.ticket[0] = reinterpret_cast<uint32_t*>(ws);
@@ -199,6 +206,14 @@ static int sort_items() {
     }();
     return it;
 }
+static int gsort_items() {   // tile size of the Gaussian (depth) sort: P keys only, so smaller tiles spread better
+    static const int it = [] {
+        const char* e = getenv("B200SPLAT_GSORT_ITEMS");
+        const int v = e ? atoi(e) : 24;
+        return (v == 8 || v == 16) ? v : 24;
+    }();
+    return it;
+}
 int sort_tiles_for(int64_t n) {   // tiles of the pipeline's (keys-only or pair) passes
     const int64_t tile = sort_items() == 512 ? 6144 : (int64_t)SORT_THREADS * sort_items();
     return (int)((n + tile - 1) / tile);
@@ -207,10 +222,15 @@ static int sort_tiles_pairs(int64_t n) { return (int)((n + SORT_TILE - 1) / SORT
 
 // Histogram of every digit place in one read of the keys (stand-alone sort only; the pipeline gets its
 // histograms from duplicateWithKeys).  hist: [passes][256] u32 (zeroed).
+struct HistTab {
+    const uint64_t* keys[MAX_VIEWS];
+    uint32_t* hist[MAX_VIEWS];
+};
 __global__ void __launch_bounds__(256)
-radix_histogram_kernel(int64_t n, int passes, int end_bit, const uint64_t* __restrict__ keys,
-                       uint32_t* __restrict__ hist) {
+radix_histogram_kernel(int64_t n, int passes, int end_bit, int shift_base, const __grid_constant__ HistTab tab) {
     __shared__ uint32_t s_hist[MAX_PASSES * RADIX];
+    const uint64_t* __restrict__ keys = tab.keys[blockIdx.y];
+    uint32_t* __restrict__ hist = tab.hist[blockIdx.y];
     for (int i = threadIdx.x; i < passes * RADIX; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -222,7 +242,7 @@ radix_histogram_kernel(int64_t n, int passes, int end_bit, const uint64_t* __res
         for (int p = 0; p < passes; ++p) {
             const int shift = p * RADIX_BITS;
             const int bits = min(RADIX_BITS, end_bit - shift);
-            const uint32_t d = (uint32_t)(k >> shift) & ((1u << bits) - 1u);
+            const uint32_t d = (uint32_t)(k >> (shift + shift_base)) & ((1u << bits) - 1u);
             // warp-uniform digit (typical for the exponent byte of depth): one add for the warp
             const uint32_t d0 = __shfl_sync(0xffffffffu, d, 0);
             const uint32_t same = __ballot_sync(0xffffffffu, ok && d == d0);
@@ -524,7 +544,10 @@ cudaError_t launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_
     sort_workspace_views(ws, &hist, &tickets, &desc);
     int64_t hg = (n + 255) / 256;
     int hgrid = (int)(hg < (int64_t)NUM_SMS * 8 ? hg : (int64_t)NUM_SMS * 8);
-    radix_histogram_kernel<<<hgrid, 256, 0, st>>>(n, passes, end_bit, keys[0], hist);
+    HistTab ht;
+    ht.keys[0] = keys[0];
+    ht.hist[0] = hist;
+    radix_histogram_kernel<<<dim3(hgrid, 1), 256, 0, st>>>(n, passes, end_bit, 0, ht);
     count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -546,11 +569,74 @@ cudaError_t launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_
     return cudaSuccess;
 }
 
+// keys-only pass over all views of the batch with the configured tile size
+static cudaError_t launch_keys_pass(int shift, int bits, const SortTab& t, int tiles, int V, cudaStream_t st,
+                                    int items = 0) {
+    const dim3 grid(tiles, V);
+    switch (items ? items : sort_items()) {
+        case 8:
+            onesweep_pass_kernel<false, 4, 8><<<grid, SORT_THREADS, offsetof(SortSmemT<8>, vals), st>>>(shift, bits, t);
+            break;
+        case 16:
+            onesweep_pass_kernel<false, 3, 16><<<grid, SORT_THREADS, offsetof(SortSmemT<16>, vals), st>>>(shift, bits, t);
+            break;
+        case 512: {
+            using SM = SortSmemT<12, 512>;
+            onesweep_pass_kernel<false, 2, 12, 512><<<grid, 512, offsetof(SM, vals), st>>>(shift, bits, t);
+            break;
+        }
+        default:
+            onesweep_pass_kernel<false, 2, 24><<<grid, SORT_THREADS, offsetof(SortSmemT<24>, vals), st>>>(shift, bits, t);
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
+// Stable sort of every view's P Gaussian words (depth_bits << 32 | index) on the depth bits: 4 passes over P
+// elements (instead of 6 passes over ~3.6 P pair keys).  Result in gwords[0].
+cudaError_t launch_gaussian_sort(const BatchTab& tab, cudaStream_t st) {
+    if (tab.P <= 0) return cudaSuccess;
+    cudaError_t e = ensure_sort_attr();
+    if (e != cudaSuccess) return e;
+    const int64_t n = tab.P;
+    const int items = gsort_items();
+    const int tiles = (int)((n + (int64_t)SORT_THREADS * items - 1) / ((int64_t)SORT_THREADS * items));
+    HistTab ht;
+    for (int v = 0; v < tab.V; ++v) {
+        e = cudaMemsetAsync(tab.v[v].ghist, 0, sort_workspace_zero_bytes(n, 32), st);
+        if (e != cudaSuccess) return e;
+        ht.keys[v] = tab.v[v].gwords[0];
+        ht.hist[v] = tab.v[v].ghist;
+    }
+    int64_t hg = (n + 255) / 256;
+    const int hgrid = (int)(hg < (int64_t)NUM_SMS * 8 / tab.V ? hg : (int64_t)NUM_SMS * 8 / tab.V);
+    radix_histogram_kernel<<<dim3(hgrid > 0 ? hgrid : 1, tab.V), 256, 0, st>>>(n, 4, 32, 32, ht);
+    count_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    int cur = 0;
+    for (int p = 0; p < 4; ++p) {
+        SortTab t;
+        t.capacity = (uint32_t)n;
+        for (int v = 0; v < tab.V; ++v) {
+            const ViewTab& vt = tab.v[v];
+            t.v[v] = SortView{nullptr, (uint32_t)n, nullptr, vt.gwords[cur], nullptr, vt.gwords[cur ^ 1], nullptr,
+                              vt.ghist + p * RADIX, vt.gtickets + p, vt.gdesc + (size_t)p * tiles * RADIX};
+        }
+        e = launch_keys_pass(32 + 8 * p, 8, t, tiles, tab.V, st, items);
+        if (e != cudaSuccess) return e;
+        cur ^= 1;
+    }
+    return cudaSuccess;   // 4 passes: back in gwords[0]
+}
+
+// Stable sort of every view's pair words (tile << 32 | index) on the tile bits [32, 32 + end_bit); histograms
+// come from duplicateWithKeys, the pair count from the device.  Result in keys[passes & 1].
 cudaError_t launch_sort_batch(const BatchTab& tab, cudaStream_t st) {
     if (tab.P <= 0 || tab.capacity == 0) return cudaSuccess;
     const int end_bit = tab.end_bit;
     const int passes = (end_bit + RADIX_BITS - 1) / RADIX_BITS;
-    const int tiles = tab.idx_bits > 0 ? sort_tiles_for(tab.capacity) : sort_tiles_pairs(tab.capacity);
+    const int tiles = sort_tiles_for(tab.capacity);
     cudaError_t e = ensure_sort_attr();
     if (e != cudaSuccess) return e;
     int cur = 0;
@@ -562,32 +648,10 @@ cudaError_t launch_sort_batch(const BatchTab& tab, cudaStream_t st) {
         for (int v = 0; v < tab.V; ++v) {
             const ViewTab& vt = tab.v[v];
             t.v[v] = SortView{vt.point_offsets + (tab.P - 1), 0u, vt.status + STATUS_OVERFLOW, vt.keys[cur],
-                              vt.vals[cur], vt.keys[cur ^ 1], vt.vals[cur ^ 1], vt.hist + p * RADIX, vt.tickets + p,
+                              nullptr, vt.keys[cur ^ 1], nullptr, vt.hist + p * RADIX, vt.tickets + p,
                               vt.desc + (size_t)p * tiles * RADIX};
         }
-        if (tab.idx_bits > 0) {
-            const int sh = shift + tab.idx_bits;
-            const dim3 grid(tiles, tab.V);
-            switch (sort_items()) {
-                case 8:
-                    onesweep_pass_kernel<false, 4, 8><<<grid, SORT_THREADS, offsetof(SortSmemT<8>, vals), st>>>(sh, bits, t);
-                    break;
-                case 24:
-                    onesweep_pass_kernel<false, 2, 24><<<grid, SORT_THREADS, offsetof(SortSmemT<24>, vals), st>>>(sh, bits, t);
-                    break;
-                case 512: {
-                    using SM = SortSmemT<12, 512>;
-                    onesweep_pass_kernel<false, 2, 12, 512><<<grid, 512, offsetof(SM, vals), st>>>(sh, bits, t);
-                    break;
-                }
-                default:
-                    onesweep_pass_kernel<false, 3, 16><<<grid, SORT_THREADS, offsetof(SortSmemT<16>, vals), st>>>(sh, bits, t);
-            }
-        } else {
-            onesweep_pass_kernel<true, 3, 16><<<dim3(tiles, tab.V), SORT_THREADS, sizeof(SortSmem), st>>>(shift, bits, t);
-        }
-        count_launch();
-        e = cudaGetLastError();
+        e = launch_keys_pass(32 + shift, bits, t, tiles, tab.V, st);
         if (e != cudaSuccess) return e;
         cur ^= 1;
     }
@@ -606,7 +670,7 @@ tile_ranges_kernel(const __grid_constant__ BatchTab tab, int sel) {
     if (i >= R) return;
     const uint64_t* __restrict__ keys = vt.keys[sel];
     uint32_t* __restrict__ ranges = vt.ranges;
-    const int tshift = 32 + tab.idx_bits;
+    const int tshift = 32;
     const uint32_t t = (uint32_t)(keys[i] >> tshift);
     if (i == 0) {
         ranges[2 * t] = 0;
