@@ -357,14 +357,36 @@ onesweep_pass_kernel(int shift, int bits, const __grid_constant__ SortTab tab) {
             if (lane == 0) S.warp_hist[warp][dv] = run;
         }
     } else {
-        uint32_t info[SORT_ITEMS];   // leader lane | rank inside the digit group << 8
+        // phase 1: all match.any back to back (their latency overlaps; nothing consumes a result yet)
+        uint32_t info[SORT_ITEMS];   // peers mask, then leader lane | rank inside the digit group << 8
+#pragma unroll
+        for (int i = 0; i < SORT_ITEMS; ++i) {
+            // match.any by 8 ballots: MATCH.ANY issues at ~1 per 60 cycles per SM (it was 58% of the pass),
+            // a vote at ~1 per cycle
+            const uint32_t d = (uint32_t)(key[i] >> shift) & mask;
+            uint32_t peers = 0xffffffffu;
+#pragma unroll
+            for (int b = 0; b < RADIX_BITS; ++b) {
+                const bool bit = (d >> b) & 1u;
+                const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+                peers &= bit ? bal : ~bal;
+            }
+            info[i] = peers;
+        }
+        // phase 2: one running-count update per (item, digit group), in item order
 #pragma unroll
         for (int i = 0; i < SORT_ITEMS; ++i) {
             const uint32_t d = (uint32_t)(key[i] >> shift) & mask;
-            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            const uint32_t peers = info[i];
             const int leader = __ffs(peers) - 1;
             uint32_t pre = 0;
-            if (lane == leader) pre = atomicAdd(&S.warp_hist[warp][d], (uint32_t)__popc(peers));
+            // plain read-modify-write: the leaders of one item hold distinct digits and the table is private to
+            // the warp (shared-memory atomics with a return value cost ~2 cycles per lane SM-wide: they were the
+            // limiter of the pass); __syncwarp orders the store before the next item's load
+            if (lane == leader) {
+                pre = S.warp_hist[warp][d];
+                S.warp_hist[warp][d] = pre + (uint32_t)__popc(peers);
+            }
             rank[i] = pre;
             info[i] = (uint32_t)leader | ((uint32_t)__popc(peers & lt_mask) << 8);
             __syncwarp();
