@@ -66,6 +66,7 @@ size_t geom_layout(int P, void* base, GeomViews* v) {
     g.depths = carve<float>(p, n);
     g.clamped = carve<uint8_t>(p, n);
     g.tiles_touched = carve<uint32_t>(p, n);
+    g.rect = carve<ushort4>(p, n);
     g.point_offsets = carve<uint32_t>(p, n);
     g.scan_ws_bytes = scan_workspace_bytes((int64_t)n);
     g.scan_ws = carve<char>(p, g.scan_ws_bytes);
@@ -175,6 +176,7 @@ static void fill_geom(int P, void* geom, ViewTab* vt) {
     geom_layout(P, geom, &g);
     vt->rec = g.rec, vt->depths = g.depths, vt->clamped = g.clamped;
     vt->tiles_touched = g.tiles_touched, vt->point_offsets = g.point_offsets;
+    vt->rect = g.rect;
     vt->gwords[0] = g.gwords[0], vt->gwords[1] = g.gwords[1];
     sort_workspace_views(g.gsort_ws, &vt->ghist, &vt->gtickets, &vt->gdesc);
     vt->scan_ticket = reinterpret_cast<uint32_t*>(g.scan_ws);

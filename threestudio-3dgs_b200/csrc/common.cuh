@@ -58,6 +58,7 @@ struct ViewTab {
     float* depths;
     uint8_t* clamped;
     uint32_t* tiles_touched;
+    ushort4* rect;             // tile rectangle (x0, y0, x1, y1) of the Gaussian; empty when culled
     uint32_t* point_offsets;
     uint32_t* scan_ticket;
     uint64_t* scan_desc;
@@ -111,6 +112,7 @@ struct GeomViews {
     float* depths;           // P
     uint8_t* clamped;        // P   (bit c set: channel c clamped at 0)
     uint32_t* tiles_touched; // P
+    ushort4* rect;           // P
     uint32_t* point_offsets; // P
     void* scan_ws;
     size_t scan_ws_bytes;

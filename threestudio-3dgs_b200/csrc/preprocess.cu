@@ -108,6 +108,7 @@ preprocess_kernel(const __grid_constant__ BatchTab tab, const float* __restrict_
         for (int v = 0; v < V; ++v) {
             tab.v[v].radii[idx] = 0;
             tab.v[v].tiles_touched[idx] = 0;
+            tab.v[v].rect[idx] = make_ushort4(0, 0, 0, 0);
             tab.v[v].gwords[0][idx] = 0xFFFFFFFF00000000ull | (uint64_t)(uint32_t)idx;   // culled: sorts last
         }
         return;
@@ -175,6 +176,7 @@ preprocess_kernel(const __grid_constant__ BatchTab tab, const float* __restrict_
         const ViewTab& vt = tab.v[v];
         int my_radius = 0;
         uint32_t my_tiles = 0;
+        ushort4 my_rect = make_ushort4(0, 0, 0, 0);
         float my_depth = 0.f;
         if ((front >> v) & 1u) {
             const float* mV = sV[v];
@@ -240,6 +242,7 @@ preprocess_kernel(const __grid_constant__ BatchTab tab, const float* __restrict_
                     }
                     my_radius = (int)radius_f;
                     my_tiles = (uint32_t)area;
+                    my_rect = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
                     float4* o = reinterpret_cast<float4*>(vt.rec) + 3 * (size_t)idx;
                     o[0] = make_float4(px, py, c * det_inv, -b * det_inv);
                     o[1] = make_float4(a * det_inv, opac, tvz, rgb[0]);
@@ -252,6 +255,7 @@ preprocess_kernel(const __grid_constant__ BatchTab tab, const float* __restrict_
         }
         vt.radii[idx] = my_radius;
         vt.tiles_touched[idx] = my_tiles;
+        vt.rect[idx] = my_rect;
         // word of the per-view depth sort of the Gaussians (culled ones sort last and emit nothing)
         vt.gwords[0][idx] = ((uint64_t)(my_radius > 0 ? __float_as_uint(my_depth) : 0xFFFFFFFFu) << 32) |
                             (uint64_t)(uint32_t)idx;
@@ -279,19 +283,17 @@ duplicate_kernel(const __grid_constant__ BatchTab tab) {
     uint32_t* s_tile = s_dyn + passes * 256;
     for (int i = threadIdx.x; i < passes * 256 + (tile_hist ? T : 0); i += blockDim.x) s_dyn[i] = 0;
     __syncthreads();
-    const int32_t* __restrict__ radii = vt.radii;
+    const ushort4* __restrict__ rect = vt.rect;
     const uint32_t* __restrict__ point_offsets = vt.point_offsets;
     const uint64_t* __restrict__ order = vt.gwords[0];
     uint64_t* __restrict__ words = vt.keys[0];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < tab.P; i += gridDim.x * blockDim.x) {
         const uint32_t g = (uint32_t)__ldg(order + i);
-        const int rad = radii[g];
-        if (rad <= 0) continue;
-        uint32_t off = (i == 0) ? 0u : point_offsets[i - 1];
-        const float2 xy = *reinterpret_cast<const float2*>(vt.rec + (size_t)g * REC_FLOATS);
-        int x0, y0, x1, y1;
-        get_rect(xy.x, xy.y, (float)rad, gx, gy, x0, y0, x1, y1);
+        const ushort4 rc = __ldg(rect + g);   // 8-byte gather from an L2-resident array (not the 48-byte record)
+        const int x0 = rc.x, y0 = rc.y, x1 = rc.z, y1 = rc.w;
         const uint32_t ntiles = (uint32_t)((x1 - x0) * (y1 - y0));
+        if (ntiles == 0) continue;
+        uint32_t off = (i == 0) ? 0u : point_offsets[i - 1];
         if (off + ntiles > tab.capacity) {
             atomicOr(vt.status + STATUS_OVERFLOW, 1u);
             continue;
