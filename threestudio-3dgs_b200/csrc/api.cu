@@ -128,9 +128,13 @@ static int higher_msb(uint32_t n) {
 }
 
 // parity of the pass count decides which ping-pong half holds the sorted data
+static int tile_id_bits(int T) {
+    int b = 1;
+    while (b < 31 && (1 << b) < T) ++b;
+    return b;
+}
 static int sorted_sel_for(int T) {
-    const int tile_bits = higher_msb((uint32_t)T);
-    return ((tile_bits + 7) / 8) & 1;
+    return pair_sort_result_sel(tile_id_bits(T));
 }
 
 // shared (view independent) part of the batch table from the first camera
@@ -152,8 +156,10 @@ static int init_table(const b200splat_camera& c, int P, int M, bool has_sh, Batc
     tab->sh_degree = deg;
     // pair words are (tile << 32 | gaussian index): only the tile bits are sorted (the Gaussians are emitted in
     // depth order), upstream's bit count 32 + getHigherMsb(T) minus the 32 depth bits
-    tab->end_bit = higher_msb((uint32_t)(tab->grid_x * tab->grid_y));
+    // (upstream sorts 32 + getHigherMsb(T) bits; the tile ids are < T, so the bits of T - 1 give the same order)
+    tab->end_bit = tile_id_bits(tab->grid_x * tab->grid_y);
     tab->idx_bits = 32;
+    tab->digit_passes = pair_sort_digit_passes(tab->end_bit);
     return B200SPLAT_OK;
 }
 
@@ -270,7 +276,7 @@ static int forward_tail(BatchTab& tab, int debug, cudaStream_t st) {
         tab.sort_tiles_cap = sort_tiles_for(tab.capacity);
         { ProfScope ps(2, st);
         for (int v = 0; v < tab.V; ++v) {
-            CU(cudaMemsetAsync(tab.v[v].hist, 0, sort_workspace_zero_bytes(tab.capacity, tab.end_bit), st));
+            CU(cudaMemsetAsync(tab.v[v].hist, 0, pair_sort_zero_bytes(tab.capacity, tab.end_bit), st));
             CU(cudaMemsetAsync(tab.v[v].tile_count, 0, (size_t)T * sizeof(uint32_t), st));
         }
         CU(launch_duplicate(tab, st)); }

@@ -99,6 +99,7 @@ struct BatchTab {
     uint32_t capacity;         // pairs each view's key/value arrays can hold
     int end_bit;               // tile-id bits: pair words (tile << 32 | index) are sorted on bits [32, 32 + end_bit)
     int sort_tiles_cap;        // ceil(capacity / SORT_TILE)
+    int digit_passes;          // 8-bit passes of the pair sort; 0 = one wide pass binned by the per-tile counts
     int idx_bits;              // index bits of a pair word (32)
     uint32_t* tile_order;      // [V * T] entries (view * T + tile), longest list first
     ViewTab v[MAX_VIEWS];
@@ -152,6 +153,9 @@ cudaError_t launch_inclusive_scan(int64_t n, const uint32_t* in, uint32_t* out, 
 size_t sort_workspace_bytes(int64_t n);
 void sort_workspace_views(void* ws, uint32_t** hist, uint32_t** tickets, uint32_t** desc);
 size_t sort_workspace_zero_bytes(int64_t capacity, int end_bit);
+size_t pair_sort_zero_bytes(int64_t capacity, int end_bit);   // same for the pipeline's pair sort (wide or 8-bit)
+int pair_sort_digit_passes(int end_bit);   // 0: single wide pass (tile ids of <= 10 bits)
+int pair_sort_result_sel(int end_bit);     // which of keys[0/1] holds the sorted words
 int sort_tiles_for(int64_t n);
 // stand-alone sort (stage-level entry point / KNN): histogram kernel + passes; *sel = buffer holding the result
 cudaError_t launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_t* vals[2], void* ws, int* sel,

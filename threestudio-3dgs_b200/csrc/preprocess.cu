@@ -275,7 +275,7 @@ duplicate_kernel(const __grid_constant__ BatchTab tab) {
     extern __shared__ uint32_t s_dyn[];   // [passes*256] digit histograms | [T] tile histogram (if it fits)
     const ViewTab& vt = tab.v[blockIdx.y];
     const int end_bit = tab.end_bit;
-    const int passes = (end_bit + 7) / 8;
+    const int passes = tab.digit_passes;   // 0: the sort bins by the per-tile counts directly
     const int gx = tab.grid_x, gy = tab.grid_y;
     const int T = gx * gy;
     const bool tile_hist = T <= DUP_MAX_TILES;
@@ -366,7 +366,7 @@ cudaError_t launch_preprocess(const BatchTab& tab, const float* means3D, const f
 cudaError_t launch_duplicate(const BatchTab& tab, cudaStream_t st) {
     if (tab.P <= 0) return cudaSuccess;
     const int T = tab.grid_x * tab.grid_y;
-    const int passes = (tab.end_bit + 7) / 8;
+    const int passes = tab.digit_passes;
     const size_t smem = ((size_t)passes * 256 + (T <= DUP_MAX_TILES ? T : 0)) * sizeof(uint32_t);
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {

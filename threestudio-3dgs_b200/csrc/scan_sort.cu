@@ -508,6 +508,195 @@ onesweep_pass_kernel(int shift, int bits, const __grid_constant__ SortTab tab) {
     }
 }
 
+// --------------------------------------------------------------------------------------------
+// K4w: stable partition of the pair words by tile id in ONE pass (tile ids of at most WIDE_BITS bits, i.e.
+// up to 1024 tiles: 512 x 512 images).  Same structure as onesweep_pass_kernel with a 1024-bin digit; every
+// thread owns WIDE_DPT bins (bin = tid + k * 256, so descriptor rows are read coalesced), whose look-backs run
+// interleaved.  The global histogram of the digit is duplicateWithKeys' per-tile count.
+// --------------------------------------------------------------------------------------------
+constexpr int WIDE_BITS = 10;
+constexpr int WIDE_BINS = 1 << WIDE_BITS;
+constexpr int WIDE_DPT = WIDE_BINS / SORT_THREADS;
+template <int ITEMS>
+struct WideSmemT {
+    uint64_t keys[SORT_THREADS * ITEMS];
+    uint32_t warp_hist[SORT_WARPS][WIDE_BINS + 1];
+    uint32_t a[WIDE_BINS];   // bin total of this tile -> exclusive offset of the bin inside the tile
+    uint32_t b[WIDE_BINS];   // global bin count -> global bin start -> destination of the tile's first key of the bin
+    uint32_t s_h[SORT_WARPS], s_l[SORT_WARPS];
+    uint32_t tile;
+    uint32_t pad[3];
+};
+
+template <int ITEMS>
+__global__ void __launch_bounds__(SORT_THREADS, 2)
+tile_partition_kernel(int n_bins, const __grid_constant__ SortTab tab) {
+    constexpr int TILE = SORT_THREADS * ITEMS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WideSmemT<ITEMS>& S = *reinterpret_cast<WideSmemT<ITEMS>*>(smem_raw);
+    const SortView& sv = tab.v[blockIdx.y];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (sv.overflow != nullptr && *sv.overflow != 0u) return;
+    const int64_t n = sv.n_ptr ? (int64_t)min(*sv.n_ptr, tab.capacity) : (int64_t)sv.n_fixed;
+    if ((int64_t)blockIdx.x * TILE >= n) return;
+    if (tid == 0) S.tile = atomicAdd(sv.ticket, 1u);
+    for (int i = tid; i < SORT_WARPS * (WIDE_BINS + 1); i += SORT_THREADS) (&S.warp_hist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = S.tile;
+    const int64_t tile_base = (int64_t)tile * TILE;
+    const int valid = (int)min((int64_t)TILE, n - tile_base);
+    constexpr uint32_t mask = WIDE_BINS - 1;
+    const uint64_t* __restrict__ keys_in = sv.keys_in;
+
+    uint64_t key[ITEMS];
+    uint32_t rank[ITEMS];
+    const int wbase = warp * (32 * ITEMS) + lane;
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const int li = wbase + i * 32;
+        key[i] = (li < valid) ? __ldg(keys_in + tile_base + li) : ~0ull;
+    }
+    // ---- warp-level stable ranking (ballot match, running counts by plain read-modify-write) --------
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    {
+        uint32_t info[ITEMS];
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const uint32_t d = (uint32_t)(key[i] >> 32) & mask;
+            uint32_t peers = 0xffffffffu;
+#pragma unroll
+            for (int b = 0; b < WIDE_BITS; ++b) {
+                const bool bit = (d >> b) & 1u;
+                const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+                peers &= bit ? bal : ~bal;
+            }
+            info[i] = peers;
+        }
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const uint32_t d = (uint32_t)(key[i] >> 32) & mask;
+            const uint32_t peers = info[i];
+            const int leader = __ffs(peers) - 1;
+            uint32_t pre = 0;
+            if (lane == leader) {
+                pre = S.warp_hist[warp][d];
+                S.warp_hist[warp][d] = pre + (uint32_t)__popc(peers);
+            }
+            rank[i] = pre;
+            info[i] = (uint32_t)leader | ((uint32_t)__popc(peers & lt_mask) << 8);
+            __syncwarp();
+        }
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i)
+            rank[i] = __shfl_sync(0xffffffffu, rank[i], (int)(info[i] & 31u)) + (info[i] >> 8);
+    }
+    __syncthreads();
+    // ---- P1: per bin, exclusive prefix over the warps, tile total, publish the descriptor -----------
+    uint32_t pub[WIDE_DPT];
+#pragma unroll
+    for (int k = 0; k < WIDE_DPT; ++k) {
+        const int d = tid + k * SORT_THREADS;
+        uint32_t bin_total = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; ++w) {
+            const uint32_t t = S.warp_hist[w][d];
+            S.warp_hist[w][d] = bin_total;
+            bin_total += t;
+        }
+        pub[k] = bin_total;
+        if (d == (int)mask) pub[k] -= (uint32_t)(TILE - valid);   // padding keys (~0) of a partial tile
+        st_volatile_u32(sv.desc + (size_t)tile * WIDE_BINS + d, (tile == 0 ? DESC_INC : DESC_AGG) | pub[k]);
+        S.a[d] = bin_total;
+        S.b[d] = d < n_bins ? sv.hist_pass[d] : 0u;
+    }
+    __syncthreads();
+    // ---- P2: exclusive scans over the bins (thread t scans bins 4t..4t+3) ---------------------------
+    {
+        uint32_t la[WIDE_DPT], lb[WIDE_DPT], sa = 0, sb = 0;
+#pragma unroll
+        for (int k = 0; k < WIDE_DPT; ++k) {
+            la[k] = sa, lb[k] = sb;
+            sa += S.a[tid * WIDE_DPT + k];
+            sb += S.b[tid * WIDE_DPT + k];
+        }
+        uint32_t ia = sa, ib = sb;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t1 = __shfl_up_sync(0xffffffffu, ia, o);
+            const uint32_t t2 = __shfl_up_sync(0xffffffffu, ib, o);
+            if (lane >= o) ia += t1, ib += t2;
+        }
+        if (lane == 31) S.s_l[warp] = ia, S.s_h[warp] = ib;
+        __syncthreads();
+        uint32_t oa = ia - sa, ob = ib - sb;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; ++w)
+            if (w < warp) oa += S.s_l[w], ob += S.s_h[w];
+#pragma unroll
+        for (int k = 0; k < WIDE_DPT; ++k) {
+            S.a[tid * WIDE_DPT + k] = oa + la[k];
+            S.b[tid * WIDE_DPT + k] = ob + lb[k];
+        }
+    }
+    __syncthreads();
+    // ---- P3: decoupled look-back of the thread's bins, interleaved ----------------------------------
+    {
+        uint32_t excl[WIDE_DPT];
+        bool found[WIDE_DPT];
+#pragma unroll
+        for (int k = 0; k < WIDE_DPT; ++k) excl[k] = 0, found[k] = (tile == 0);
+        constexpr int LOOK = 4;
+        int look = (int)tile - 1;
+        const uint32_t* col = sv.desc + tid;
+        while (!(found[0] && found[1] && found[2] && found[3])) {
+            uint32_t v[WIDE_DPT][LOOK];
+#pragma unroll
+            for (int k = 0; k < WIDE_DPT; ++k)
+#pragma unroll
+                for (int u = 0; u < LOOK; ++u)
+                    v[k][u] = (!found[k] && look - u >= 0)
+                                  ? ld_volatile_u32(col + (size_t)(look - u) * WIDE_BINS + k * SORT_THREADS)
+                                  : DESC_INC;
+#pragma unroll
+            for (int k = 0; k < WIDE_DPT; ++k)
+#pragma unroll
+                for (int u = 0; u < LOOK; ++u) {
+                    if (!found[k]) {
+                        uint32_t x = v[k][u];
+                        while ((x >> 30) == 0)
+                            x = ld_volatile_u32(col + (size_t)(look - u) * WIDE_BINS + k * SORT_THREADS);
+                        excl[k] += x & DESC_VAL;
+                        found[k] = (x >> 30) == 2;
+                    }
+                }
+            look -= LOOK;
+        }
+#pragma unroll
+        for (int k = 0; k < WIDE_DPT; ++k) {
+            const int d = tid + k * SORT_THREADS;
+            if (tile > 0) st_volatile_u32(sv.desc + (size_t)tile * WIDE_BINS + d, DESC_INC | (excl[k] + pub[k]));
+            S.b[d] = S.b[d] + excl[k] - S.a[d];
+        }
+    }
+    __syncthreads();
+    // ---- scatter through shared memory, coalesced write-out -----------------------------------------
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const uint32_t d = (uint32_t)(key[i] >> 32) & mask;
+        S.keys[rank[i] + S.a[d] + S.warp_hist[warp][d]] = key[i];
+    }
+    __syncthreads();
+    uint64_t* __restrict__ keys_out = sv.keys_out;
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const int p = i * SORT_THREADS + tid;
+        if (p < valid) {
+            const uint64_t k = S.keys[p];
+            keys_out[S.b[(uint32_t)(k >> 32) & mask] + (uint32_t)p] = k;
+        }
+    }
+}
+
 // workspace: hist [MAX_PASSES][256] u32 | tickets [64] u32 | desc [passes][tiles][256] u32
 static int64_t sort_tiles_max(int64_t n) { return (n + 2047) / 2048; }
 size_t sort_workspace_bytes(int64_t n) {
@@ -517,6 +706,24 @@ size_t sort_workspace_bytes(int64_t n) {
 size_t sort_workspace_zero_bytes(int64_t capacity, int end_bit) {
     const int passes = (end_bit + RADIX_BITS - 1) / RADIX_BITS;
     return (size_t)MAX_PASSES * RADIX * 4 + 256 + (size_t)passes * sort_tiles_max(capacity < 1 ? 1 : capacity) * RADIX * 4;
+}
+static bool wide_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("B200SPLAT_WIDE_PARTITION");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+int pair_sort_digit_passes(int end_bit) {
+    return (end_bit <= WIDE_BITS && wide_enabled()) ? 0 : (end_bit + RADIX_BITS - 1) / RADIX_BITS;
+}
+int pair_sort_result_sel(int end_bit) {
+    const int p = pair_sort_digit_passes(end_bit);
+    return p == 0 ? 1 : (p & 1);
+}
+size_t pair_sort_zero_bytes(int64_t capacity, int end_bit) {
+    if (pair_sort_digit_passes(end_bit) != 0) return sort_workspace_zero_bytes(capacity, end_bit);
+    return (size_t)MAX_PASSES * RADIX * 4 + 256 + (size_t)sort_tiles_for(capacity < 1 ? 1 : capacity) * WIDE_BINS * 4;
 }
 void sort_workspace_views(void* ws, uint32_t** hist, uint32_t** tickets, uint32_t** desc) {
     uint32_t* h = reinterpret_cast<uint32_t*>(ws);
@@ -544,6 +751,15 @@ static cudaError_t ensure_sort_attr() {
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(onesweep_pass_kernel<false, 2, 12, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)sizeof(SortSmemT<12, 512>));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(tile_partition_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(WideSmemT<8>));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(tile_partition_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(WideSmemT<16>));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(tile_partition_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(WideSmemT<24>));
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -657,10 +873,33 @@ cudaError_t launch_gaussian_sort(const BatchTab& tab, cudaStream_t st) {
 cudaError_t launch_sort_batch(const BatchTab& tab, cudaStream_t st) {
     if (tab.P <= 0 || tab.capacity == 0) return cudaSuccess;
     const int end_bit = tab.end_bit;
-    const int passes = (end_bit + RADIX_BITS - 1) / RADIX_BITS;
+    const int passes = tab.digit_passes;
     const int tiles = sort_tiles_for(tab.capacity);
     cudaError_t e = ensure_sort_attr();
     if (e != cudaSuccess) return e;
+    if (passes == 0) {   // one wide pass: bins = tiles, global histogram = the per-tile counts
+        SortTab t;
+        t.capacity = tab.capacity;
+        for (int v = 0; v < tab.V; ++v) {
+            const ViewTab& vt = tab.v[v];
+            t.v[v] = SortView{vt.point_offsets + (tab.P - 1), 0u, vt.status + STATUS_OVERFLOW, vt.keys[0], nullptr,
+                              vt.keys[1], nullptr, vt.tile_count, vt.tickets, vt.desc};
+        }
+        const dim3 grid(tiles, tab.V);
+        const int n_bins = tab.grid_x * tab.grid_y;
+        switch (sort_items()) {
+            case 8:
+                tile_partition_kernel<8><<<grid, SORT_THREADS, sizeof(WideSmemT<8>), st>>>(n_bins, t);
+                break;
+            case 16:
+                tile_partition_kernel<16><<<grid, SORT_THREADS, sizeof(WideSmemT<16>), st>>>(n_bins, t);
+                break;
+            default:
+                tile_partition_kernel<24><<<grid, SORT_THREADS, sizeof(WideSmemT<24>), st>>>(n_bins, t);
+        }
+        count_launch();
+        return cudaGetLastError();
+    }
     int cur = 0;
     for (int p = 0; p < passes; ++p) {
         const int shift = p * RADIX_BITS;
