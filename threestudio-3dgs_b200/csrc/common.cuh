@@ -179,6 +179,15 @@ cudaError_t launch_dist2(int P, const float* points, float* out, void* ws, cudaS
 void count_launch(int n = 1);
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// per-thread asynchronous 16-byte copies global -> shared (LDGSTS), groups committed / awaited by the same thread
+__device__ __forceinline__ void cpa16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cpa_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

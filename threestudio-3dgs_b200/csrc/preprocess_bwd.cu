@@ -18,6 +18,8 @@
 
 namespace b200splat {
 
+constexpr int SH_ROW_F4 = 13;   // staged SH row: 12 float4 + 1 of padding
+
 constexpr float SH_C0 = 0.28209479177387814f;
 constexpr float SH_C1 = 0.4886025119029199f;
 constexpr float SH_C2_0 = 1.0925484305920792f;
@@ -86,17 +88,24 @@ __device__ __forceinline__ void sh_chunk_view(const float sv[12], float x, float
     }
 }
 
-// Phase B of the kernel for chunk C: load the chunk's 12 SH floats once, loop over the views (their masked
-// colour gradient and unit direction come from shared memory), store the chunk's dL/dsh, accumulate each
-// view's dL/ddir in shared memory.
+// Phase B of the kernel for chunk C: take the chunk's 12 SH floats once (from the thread's staged row in shared
+// memory, or from global), loop over the views (their masked colour gradient and unit direction sit in the
+// thread's shared-memory slot), store the chunk's dL/dsh, accumulate each view's dL/ddir in the slot.
+// Slot of (view, thread): 3 float4 = (g.r, g.g, g.b, dir.x) (dir.y, dir.z, 1/|d|, -) (ddir.x, ddir.y, ddir.z, -).
 template <int C, int K, bool ACC, bool VEC>
-__device__ __forceinline__ void sh_chunk_all_views(const float* __restrict__ sh, float* __restrict__ dst, int M, int V,
-                                                   uint32_t vis, const float* __restrict__ s_view /* [V][10][128] */) {
+__device__ __forceinline__ void sh_chunk_all_views(const float* __restrict__ sh, const float4* sh_row,
+                                                   float* __restrict__ dst, int M, int V, uint32_t vis,
+                                                   float4* s_slots /* [V][128][3] */) {
     if (4 * C >= K) return;
     float sv[12];
     if (VEC) {
-        const float4* in4 = reinterpret_cast<const float4*>(sh) + 3 * C;
-        const float4 a = __ldg(in4), b = __ldg(in4 + 1), c = __ldg(in4 + 2);
+        float4 a, b, c;
+        if (sh_row != nullptr) {
+            a = sh_row[3 * C], b = sh_row[3 * C + 1], c = sh_row[3 * C + 2];
+        } else {
+            const float4* in4 = reinterpret_cast<const float4*>(sh) + 3 * C;
+            a = __ldg(in4), b = __ldg(in4 + 1), c = __ldg(in4 + 2);
+        }
         sv[0] = a.x, sv[1] = a.y, sv[2] = a.z, sv[3] = a.w, sv[4] = b.x, sv[5] = b.y, sv[6] = b.z, sv[7] = b.w;
         sv[8] = c.x, sv[9] = c.y, sv[10] = c.z, sv[11] = c.w;
     } else {
@@ -109,15 +118,14 @@ __device__ __forceinline__ void sh_chunk_all_views(const float* __restrict__ sh,
     float acc[12];
 #pragma unroll
     for (int t = 0; t < 12; ++t) acc[t] = 0.f;
-    float* sw = const_cast<float*>(s_view);
     for (int v = 0; v < V; ++v) {
         if (!((vis >> v) & 1u)) continue;
-        float* r = sw + (size_t)v * 10 * 128 + threadIdx.x;
-        const float g[3] = {r[0 * 128], r[1 * 128], r[2 * 128]};
-        const float dx = r[3 * 128], dy = r[4 * 128], dz = r[5 * 128];
-        float ddx = 0.f, ddy = 0.f, ddz = 0.f;
-        sh_chunk_view<C, K>(sv, dx, dy, dz, g, acc, ddx, ddy, ddz);
-        r[7 * 128] += ddx, r[8 * 128] += ddy, r[9 * 128] += ddz;
+        float4* r = s_slots + ((size_t)v * 128 + threadIdx.x) * 3;
+        const float4 ra = r[0], rb = r[1];
+        float4 rc = r[2];
+        const float g[3] = {ra.x, ra.y, ra.z};
+        sh_chunk_view<C, K>(sv, ra.w, rb.x, rb.y, g, acc, rc.x, rc.y, rc.z);
+        r[2] = rc;
     }
     if (VEC) {
         float4* d4 = reinterpret_cast<float4*>(dst) + 3 * C;
@@ -159,9 +167,13 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
                            float* __restrict__ dL_dcov3D, float* __restrict__ stat_grad_accum,
                            float* __restrict__ stat_denom, float* __restrict__ stat_max_radii) {
     __shared__ float sV[MAX_VIEWS][16], sP[MAX_VIEWS][16], sC[MAX_VIEWS][4];
-    // per (view, thread): masked colour gradient (3), unit view direction (3), 1/|d| (1), dL/ddir (3)
-    extern __shared__ float s_view[];   // [V][10][128]
+    // dynamic shared memory: one 48-byte slot per (view, thread) -- first the landing zone of the view's gradient
+    // record (cp.async), then the SH phase's per-view state -- and, on the vector path, the thread's SH row
+    // (row stride 13 float4: LDS.128 of neighbouring threads fall in different bank groups)
+    extern __shared__ float4 s_dyn4[];
+    float4* s_slots = s_dyn4;   // [V][128][3]
     const int V = tab.V;
+    float4* sh_row = (VEC && DEG >= 0) ? s_dyn4 + (size_t)V * 128 * 3 + threadIdx.x * SH_ROW_F4 : nullptr;
     for (int i = threadIdx.x; i < V * 16; i += blockDim.x) {
         sV[i >> 4][i & 15] = tab.v[i >> 4].view[i & 15];
         sP[i >> 4][i & 15] = tab.v[i >> 4].proj[i & 15];
@@ -174,12 +186,22 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
     constexpr int K = DEG < 0 ? 0 : (DEG + 1) * (DEG + 1);
     constexpr int NCH = (K + 3) / 4;          // live chunks of 4 coefficients
 
-    uint32_t vis = 0;
+    // every load whose address is known goes out first: radii, clamp bits and the parameters of the Gaussian
+    uint32_t vis = 0, clampbits = 0;
     int max_radius = 0;
     for (int v = 0; v < V; ++v) {
         const int r = tab.v[v].radii[idx];
+        if (DEG >= 0) clampbits |= (uint32_t)tab.v[v].clamped[idx] << (4 * v);
         if (r > 0) vis |= 1u << v;
         max_radius = max(max_radius, r);
+    }
+    const float x = means3D[3 * idx], y = means3D[3 * idx + 1], z = means3D[3 * idx + 2];
+    const bool has_sr = (scales != nullptr) && (cov3D_precomp == nullptr);
+    float sc_in[3] = {0.f, 0.f, 0.f};
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has_sr) {
+        sc_in[0] = scales[3 * idx], sc_in[1] = scales[3 * idx + 1], sc_in[2] = scales[3 * idx + 2];
+        q = reinterpret_cast<const float4*>(rotations)[idx];
     }
     if (vis == 0) {
         if (!ACC) {
@@ -197,26 +219,31 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
         }
         return;
     }
-    const float* sh = DEG >= 0 ? shs + (size_t)idx * M * 3 : nullptr;
-    if (DEG >= 0) {   // SH block of this Gaussian towards L2 while the covariance chain runs
-        prefetch_l2(sh);
-        if (K * 12 > 128) prefetch_l2(reinterpret_cast<const char*>(sh) + 128);
-    }
-    // every view's 48-byte gradient record too: the per-view chain below then hits L2 instead of DRAM
+    // asynchronous copies into the thread's own shared-memory slots: group 0 = the visible views' 48-byte
+    // gradient records, group 1 = the SH row.  They land while Sigma3 / the per-view chains run.
     for (int v = 0; v < V; ++v) {
         if ((vis >> v) & 1u) {
-            const char* gp = reinterpret_cast<const char*>(tab.v[v].grad2d + (size_t)idx * GRAD2D_FLOATS);
-            prefetch_l2(gp);
-            prefetch_l2(gp + 44);
+            const float4* gp = reinterpret_cast<const float4*>(tab.v[v].grad2d) + 3 * (size_t)idx;
+            float4* slot = s_slots + ((size_t)v * 128 + threadIdx.x) * 3;
+            cpa16(slot, gp), cpa16(slot + 1, gp + 1), cpa16(slot + 2, gp + 2);
         }
     }
-    const float x = means3D[3 * idx], y = means3D[3 * idx + 1], z = means3D[3 * idx + 2];
-
+    cpa_commit();
+    const float* sh = DEG >= 0 ? shs + (size_t)idx * M * 3 : nullptr;
+    if (DEG >= 0) {
+        if (VEC) {
+            const float4* s4 = reinterpret_cast<const float4*>(sh);
+#pragma unroll
+            for (int j = 0; j < 3 * NCH; ++j) cpa16(sh_row + j, s4 + j);
+        } else {
+            prefetch_l2(sh);
+            if (K * 12 > 128) prefetch_l2(reinterpret_cast<const char*>(sh) + 128);
+        }
+    }
+    cpa_commit();
     // Sigma3 (view independent); R and s kept for its backward
     float c0, c1, c2, c3, c4, c5;
     float R[3][3], s[3];
-    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool has_sr = (scales != nullptr) && (cov3D_precomp == nullptr);
     if (!has_sr) {
         const float* cs = cov3D_precomp + 6 * (size_t)idx;
         c0 = cs[0], c1 = cs[1], c2 = cs[2], c3 = cs[3], c4 = cs[4], c5 = cs[5];
@@ -228,8 +255,7 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
         }
     } else {
         const float mod = tab.scale_modifier;
-        s[0] = mod * scales[3 * idx], s[1] = mod * scales[3 * idx + 1], s[2] = mod * scales[3 * idx + 2];
-        q = reinterpret_cast<const float4*>(rotations)[idx];
+        s[0] = mod * sc_in[0], s[1] = mod * sc_in[1], s[2] = mod * sc_in[2];
         const float r = q.x, qx = q.y, qy = q.z, qz = q.w;
         R[0][0] = 1.f - 2.f * (qy * qy + qz * qz), R[0][1] = 2.f * (qx * qy - r * qz), R[0][2] = 2.f * (qx * qz + r * qy);
         R[1][0] = 2.f * (qx * qy + r * qz), R[1][1] = 1.f - 2.f * (qx * qx + qz * qz), R[1][2] = 2.f * (qy * qz - r * qx);
@@ -253,6 +279,7 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
     float dcol[3] = {0.f, 0.f, 0.f};
     float st_norm = 0.f, st_cnt = 0.f;
 
+    cpa_wait<1>();   // the gradient records have landed (each thread reads only what it copied itself)
     for (int v = 0; v < V; ++v) {
         const ViewTab& vt = tab.v[v];
         if (!((vis >> v) & 1u)) {
@@ -263,8 +290,8 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
         }
         const float* mV = sV[v];
         const float* mP = sP[v];
-        const float4* gp = reinterpret_cast<const float4*>(vt.grad2d) + 3 * (size_t)idx;
-        const float4 g0 = gp[0], g1 = gp[1], g2 = gp[2];
+        float4* slot = s_slots + ((size_t)v * 128 + threadIdx.x) * 3;
+        const float4 g0 = slot[0], g1 = slot[1], g2 = slot[2];
         const float g_px = g0.x, g_py = g0.y, g_ca = g0.z, g_cb = g0.w, g_cc = g1.x, g_op = g1.y;
         float g_rgb[3] = {g1.z, g1.w, g2.x};
         const float g_depth = g2.y;
@@ -346,17 +373,16 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
         dop += g_op;
         // ---- colour -----------------------------------------------------------------------------
         if (DEG >= 0) {
-            const uint8_t bits = vt.clamped[idx];
+            const uint32_t bits = (clampbits >> (4 * v)) & 7u;
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch)
                 if (bits & (1u << ch)) g_rgb[ch] = 0.f;
             float dx = x - sC[v][0], dy = y - sC[v][1], dz = z - sC[v][2];
             const float n = sqrtf(dx * dx + dy * dy + dz * dz);
             const float in = 1.0f / n;
-            float* r = s_view + (size_t)v * 10 * 128 + threadIdx.x;
-            r[0 * 128] = g_rgb[0], r[1 * 128] = g_rgb[1], r[2 * 128] = g_rgb[2];
-            r[3 * 128] = dx * in, r[4 * 128] = dy * in, r[5 * 128] = dz * in, r[6 * 128] = in;
-            r[7 * 128] = 0.f, r[8 * 128] = 0.f, r[9 * 128] = 0.f;
+            slot[0] = make_float4(g_rgb[0], g_rgb[1], g_rgb[2], dx * in);
+            slot[1] = make_float4(dy * in, dz * in, in, 0.f);
+            slot[2] = make_float4(0.f, 0.f, 0.f, 0.f);
         } else {
             dcol[0] += g_rgb[0], dcol[1] += g_rgb[1], dcol[2] += g_rgb[2];
         }
@@ -365,10 +391,11 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
     // ---- SH: chunk-outer / view-inner (each 48-byte chunk of the SH block is loaded once) ---------------
     if (DEG >= 0) {
         float* dst = dL_dshs + (size_t)idx * M * 3;
-        sh_chunk_all_views<0, K, ACC, VEC>(sh, dst, M, V, vis, s_view);
-        sh_chunk_all_views<1, K, ACC, VEC>(sh, dst, M, V, vis, s_view);
-        sh_chunk_all_views<2, K, ACC, VEC>(sh, dst, M, V, vis, s_view);
-        sh_chunk_all_views<3, K, ACC, VEC>(sh, dst, M, V, vis, s_view);
+        cpa_wait<0>();   // the SH row has landed
+        sh_chunk_all_views<0, K, ACC, VEC>(sh, sh_row, dst, M, V, vis, s_slots);
+        sh_chunk_all_views<1, K, ACC, VEC>(sh, sh_row, dst, M, V, vis, s_slots);
+        sh_chunk_all_views<2, K, ACC, VEC>(sh, sh_row, dst, M, V, vis, s_slots);
+        sh_chunk_all_views<3, K, ACC, VEC>(sh, sh_row, dst, M, V, vis, s_slots);
         if (!ACC) {   // coefficients above the active degree get zero gradients
             if (VEC) {
                 float4* d4 = reinterpret_cast<float4*>(dst);
@@ -381,9 +408,10 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
         // through dir = d / |d|, per view
         for (int v = 0; v < V; ++v) {
             if (!((vis >> v) & 1u)) continue;
-            const float* r = s_view + (size_t)v * 10 * 128 + threadIdx.x;
-            const float dx = r[3 * 128], dy = r[4 * 128], dz = r[5 * 128], in = r[6 * 128];
-            const float ddx = r[7 * 128], ddy = r[8 * 128], ddz = r[9 * 128];
+            const float4* r = s_slots + ((size_t)v * 128 + threadIdx.x) * 3;
+            const float4 ra = r[0], rb = r[1], rc = r[2];
+            const float dx = ra.w, dy = rb.x, dz = rb.y, in = rb.z;
+            const float ddx = rc.x, ddy = rc.y, ddz = rc.z;
             const float dot = dx * ddx + dy * ddy + dz * ddz;
             dmx += (ddx - dx * dot) * in;
             dmy += (ddy - dy * dot) * in;
@@ -454,13 +482,22 @@ cudaError_t launch_preprocess_backward(const BatchTab& tab, const float* means3D
                                        int accumulate, cudaStream_t st) {
     if (tab.P <= 0) return cudaSuccess;
     const int grid = (tab.P + 127) / 128;
-    const size_t smem = tab.sh_degree >= 0 ? (size_t)tab.V * 10 * 128 * sizeof(float) : 0;
     const bool vec = tab.sh_degree >= 0 && (tab.M & 3) == 0 && tab.M <= 16 &&
                      ((reinterpret_cast<uintptr_t>(shs) | reinterpret_cast<uintptr_t>(dL_dshs)) & 15) == 0;
+    const size_t smem = ((size_t)tab.V * 128 * 3 + (vec ? 128 * SH_ROW_F4 : 0)) * sizeof(float4);
 #define LAUNCH_PB(D, A, VC)                                                                                        \
-    preprocess_backward_kernel<D, A, VC><<<grid, 128, smem, st>>>(                                                    \
-        tab, means3D, scales, rotations, shs, cov3D_precomp, dL_dmeans3D, dL_dshs, dL_dcolors, dL_dopacity,        \
-        dL_dscales, dL_drotations, dL_dcov3D, stat_grad_accum, stat_denom, stat_max_radii)
+    {                                                                                                              \
+        auto kfn = preprocess_backward_kernel<D, A, VC>;                                                           \
+        static size_t attr = 48 * 1024;                                                                            \
+        if (smem > attr) {                                                                                         \
+            cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+            if (e != cudaSuccess) return e;                                                                        \
+            attr = smem;                                                                                           \
+        }                                                                                                          \
+        kfn<<<grid, 128, smem, st>>>(tab, means3D, scales, rotations, shs, cov3D_precomp, dL_dmeans3D, dL_dshs,     \
+                                     dL_dcolors, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D,                \
+                                     stat_grad_accum, stat_denom, stat_max_radii);                                 \
+    }
 #define DISPATCH_DEG(A, VC)                                                                                        \
     switch (tab.sh_degree) {                                                                                       \
         case -1: LAUNCH_PB(-1, A, false); break;                                                                   \
