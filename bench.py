@@ -400,9 +400,8 @@ def main():
         torch.cuda.synchronize()
         prof = _lib.profile_read()
         _lib.profile_enable(False)
-        # one launch group covers the whole view batch: per-view averages = group time / views
-        prof = {k: (t, n * V) for k, (t, n) in prof.items()}
-        # work counters of the rank's views (averaged per launch)
+        # one launch group covers the whole view batch: times and work below are PER LAUNCH (V views)
+        # work counters of the rank's views (summed over the batch)
         cnt = dict(V=0, R=0, n_eval_fwd=0, n_eval_bwd=0, staged=0)
         for cam in cams:
             color, radii, depth, alpha, st = ops.forward(cam, means3D, shs, None, opac, scales, rots, None)
@@ -411,21 +410,25 @@ def main():
             cnt["R"] += st.num_rendered
             cnt["n_eval_fwd"] += int(vw["n_visited"].sum())
             cnt["n_eval_bwd"] += int(vw["n_contrib"].sum())
-        for k in cnt:
-            cnt[k] /= len(cams)
         Tn = ((W + 15) // 16) * ((H + 15) // 16)
-        bits = 32 + (Tn - 1).bit_length() + (1 if Tn & (Tn - 1) == 0 else 0)
-        passes = (bits + 7) // 8
-        Mc = M
-        alg = {  # SURVEY.md 8(d) algorithmic bytes / flops per launch
-            "preprocess": ("hbm", P * (44 + 12 * Mc + 48)),
-            "scan": ("hbm", 8 * P),
-            "duplicate": ("hbm", 20 * cnt["V"] + 12 * cnt["R"]),
-            "sort": ("hbm", cnt["R"] * (8 + passes * 24)),
-            "ranges": ("hbm", 8 * cnt["R"] + 8 * Tn),
+        tile_bits = max(1, (Tn - 1).bit_length())
+        pair_passes = 1 if tile_bits <= 10 else (tile_bits + 7) // 8
+        Mc, Rs = M, cnt["R"]
+        alg = {  # algorithmic bytes / flops per launch of the view batch
+            # parameters read once for the batch; per view: record 48 + depth 4 + radius 4 + tiles 4 + rect 8 +
+            # depth-sort word 8 + clamp bits 1
+            "preprocess": ("hbm", P * (44 + 12 * Mc) + V * P * 77),
+            # per view: depth-order word 8 + gathered tile count 4 + offset 4
+            "scan": ("hbm", V * 16 * P),
+            # per view: order word 8 + rect 8 + offset 4 per Gaussian, one 8-byte pair word per pair
+            "duplicate": ("hbm", V * 20 * P + 8 * Rs),
+            # Gaussian depth sort: histogram read 8 P + 4 passes x 16 P; pair partition: passes x 16 R
+            "sort": ("hbm", V * 72 * P + pair_passes * 16 * Rs),
+            "ranges": ("hbm", V * 16 * Tn),
             "render_fwd": ("fp32", 30 * cnt["n_eval_fwd"]),
             "render_bwd": ("fp32", 90 * cnt["n_eval_bwd"]),
-            "preprocess_bwd": ("hbm", P * (84 + 12 * Mc) + P * (40 + 12 * Mc + 4)),
+            # parameters read once, gradients written once; per view: 48-byte gradient record + radius 4 + clamp 1
+            "preprocess_bwd": ("hbm", P * (44 + 12 * Mc) + P * (44 + 12 * Mc) + V * P * 53),
         }
         fp32_peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
         traffic = {}
@@ -447,7 +450,7 @@ def main():
                 ach, peak, unit = work / (avg_ms * 1e-3) / 1e12, fp32_peak, "TFLOP/s"
             kernels.append({"kernel": name, "bound": bound, "avg_ms": avg_ms, "launches": n, "achieved": ach,
                             "peak": peak, "unit": unit, "frac": ach / peak, "work_per_launch": work,
-                            "traffic": traffic.get(name)})
+                            "views_per_launch": V, "us_per_view": 1e3 * avg_ms / V, "traffic": traffic.get(name)})
         step_ms = sum(k["avg_ms"] for k in kernels)
         for k in kernels:
             k["share_of_step"] = k["avg_ms"] / step_ms if step_ms else None

@@ -67,17 +67,19 @@ with open(f"{out_dir}/{tag}_ncu_full_summary.md", "w") as f:
                 f"{g('sm__warps_active.avg.pct_of_peak_sustained_active'):.1f} | {int(g('launch__registers_per_thread'))} | "
                 f"{g('smsp__inst_executed.sum') / 1e6:.1f} M | {', '.join(f'{a} {b:.1f}' for a, b in st[:3])} |\n")
         traffic.setdefault(name, []).append(rd + wr)
-fam = {"preprocess_kernel<3>": "preprocess", "duplicate_kernel": "duplicate", "onesweep_pass_kernel<0, 2, 24>": "sort",
-       "render_forward_kernel<0>": "render_fwd", "render_backward_kernel<0>": "render_bwd",
-       "preprocess_backward_kernel<3, 0, 1>": "preprocess_bwd"}
-V = 4
+# family traffic per launch group (one step of the view batch): all kernels of the family summed
+fam_of = [("preprocess_backward_kernel", "preprocess_bwd"), ("preprocess_kernel", "preprocess"),
+          ("scan_lookback_kernel", "scan"), ("duplicate_kernel", "duplicate"), ("radix_histogram_kernel", "sort"),
+          ("onesweep_pass_kernel", "sort"), ("tile_partition_kernel", "sort"), ("tile_ranges", "ranges"),
+          ("tile_order_kernel", "ranges"), ("render_forward_kernel", "render_fwd"),
+          ("render_backward_kernel", "render_bwd")]
+steps_captured = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 tj = {}
 for k, v in traffic.items():
-    f_ = fam.get(k)
-    if not f_: continue
-    per_launch = sum(v) / len(v)
-    # per-view bytes of the family: sort = 6 passes per view
-    tj[f_] = per_launch / V * (6 if f_ == "sort" else 1)
-json.dump({"headline_1m_512_sh3": tj, "_note": "dram__bytes_read.sum + dram__bytes_write.sum per VIEW (batched launch / 4 views; "
-           "sort = 6 passes), from profiles/%s_ncu_full_summary.md" % tag}, open(f"{out_dir}/ncu_traffic.json", "w"), indent=1)
+    f_ = next((f for pre, f in fam_of if k.startswith(pre)), None)
+    if f_:
+        tj[f_] = tj.get(f_, 0.0) + sum(v) / steps_captured
+json.dump({"headline_1m_512_sh3": tj, "_note": "dram__bytes_read.sum + dram__bytes_write.sum per LAUNCH GROUP (one step of "
+           "the 4-view batch; all kernels of the family summed), from profiles/%s_ncu_full_summary.md" % tag},
+          open(f"{out_dir}/ncu_traffic.json", "w"), indent=1)
 print(tj)
