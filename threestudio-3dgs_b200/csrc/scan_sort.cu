@@ -34,8 +34,10 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
 // ============================================================================================
 // K2: single-pass inclusive scan of uint32 with decoupled look-back
 // ============================================================================================
-constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 8;
+// 8192 elements per CTA: the look-back chain of a 1M-element scan is 123 tiles (4 warp-wide windows) deep;
+// with 2048-element tiles it was 489 tiles / 15 windows and the launch took 38 us for 4 views
+constexpr int SCAN_THREADS = 512;
+constexpr int SCAN_ITEMS = 16;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 constexpr uint64_t FLAG_AGG = 1ull << 32;
@@ -70,8 +72,11 @@ scan_lookback_kernel(int64_t n, const __grid_constant__ ScanTab tab) {
         for (int i = 0; i < SCAN_ITEMS; ++i) v[i] = (base + i < n) ? __ldg(in + (uint32_t)__ldg(perm + base + i)) : 0u;
     } else if (base + SCAN_ITEMS <= n) {
         const uint4* p = reinterpret_cast<const uint4*>(in + base);
-        uint4 a = __ldg(p), b = __ldg(p + 1);
-        v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS / 4; ++i) {
+            const uint4 a = __ldg(p + i);
+            v[4 * i] = a.x, v[4 * i + 1] = a.y, v[4 * i + 2] = a.z, v[4 * i + 3] = a.w;
+        }
     } else {
 #pragma unroll
         for (int i = 0; i < SCAN_ITEMS; ++i) v[i] = (base + i < n) ? in[base + i] : 0u;
@@ -134,8 +139,9 @@ scan_lookback_kernel(int64_t n, const __grid_constant__ ScanTab tab) {
     const uint32_t off = s_excl + warp_off + (inc - tsum);
     if (base + SCAN_ITEMS <= n) {
         uint4* p = reinterpret_cast<uint4*>(out + base);
-        p[0] = make_uint4(v[0] + off, v[1] + off, v[2] + off, v[3] + off);
-        p[1] = make_uint4(v[4] + off, v[5] + off, v[6] + off, v[7] + off);
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS / 4; ++i)
+            p[i] = make_uint4(v[4 * i] + off, v[4 * i + 1] + off, v[4 * i + 2] + off, v[4 * i + 3] + off);
     } else {
 #pragma unroll
         for (int i = 0; i < SCAN_ITEMS; ++i)
@@ -243,7 +249,11 @@ radix_histogram_kernel(int64_t n, int passes, int end_bit, int shift_base, const
             const int shift = p * RADIX_BITS;
             const int bits = min(RADIX_BITS, end_bit - shift);
             const uint32_t d = (uint32_t)(k >> (shift + shift_base)) & ((1u << bits) - 1u);
-            // warp-uniform digit (typical for the exponent byte of depth): one add for the warp
+            if (p + 1 < passes) {   // low digits are spread: one plain shared-memory atomic per key
+                if (ok) atomicAdd(&s_hist[p * RADIX + d], 1u);
+                continue;
+            }
+            // top digit: often warp-uniform (the exponent byte of depth) -- one add for the warp
             const uint32_t d0 = __shfl_sync(0xffffffffu, d, 0);
             const uint32_t same = __ballot_sync(0xffffffffu, ok && d == d0);
             const uint32_t okm = __ballot_sync(0xffffffffu, ok);
@@ -277,6 +287,27 @@ struct SortTab {
     uint32_t capacity;
     SortView v[MAX_VIEWS];
 };
+
+// match.any by ballots: lanes holding the same BITS-bit digit.  MATCH.ANY issues at ~1 per 60 cycles per SM (it was
+// 58 % of a pass's stall samples); this is 4 instructions per bit (bit test, vote, select, and-xor), spelled in
+// PTX because the C++ form compiles to 6-8 (second predicate, shifts, 64-bit tests folded back into the key).
+template <int BITS>
+__device__ __forceinline__ uint32_t ballot_match(uint32_t d) {
+    uint32_t peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < BITS; ++b) {
+        asm("{\n\t.reg .pred p;\n\t.reg .b32 t, bal;\n\t"
+            "and.b32 t, %1, %2;\n\t"
+            "setp.ne.u32 p, t, 0;\n\t"
+            "vote.sync.ballot.b32 bal, p, 0xffffffff;\n\t"
+            "selp.b32 t, 0, 0xffffffff, p;\n\t"
+            "xor.b32 bal, bal, t;\n\t"
+            "and.b32 %0, %0, bal;\n\t}"
+            : "+r"(peers)
+            : "r"(d), "r"(1u << b));
+    }
+    return peers;
+}
 
 template <int ITEMS, int NT = SORT_THREADS>
 struct SortSmemT {
@@ -361,17 +392,7 @@ onesweep_pass_kernel(int shift, int bits, const __grid_constant__ SortTab tab) {
         uint32_t info[SORT_ITEMS];   // peers mask, then leader lane | rank inside the digit group << 8
 #pragma unroll
         for (int i = 0; i < SORT_ITEMS; ++i) {
-            // match.any by 8 ballots: MATCH.ANY issues at ~1 per 60 cycles per SM (it was 58% of the pass),
-            // a vote at ~1 per cycle
-            const uint32_t d = (uint32_t)(key[i] >> shift) & mask;
-            uint32_t peers = 0xffffffffu;
-#pragma unroll
-            for (int b = 0; b < RADIX_BITS; ++b) {
-                const bool bit = (d >> b) & 1u;
-                const uint32_t bal = __ballot_sync(0xffffffffu, bit);
-                peers &= bit ? bal : ~bal;
-            }
-            info[i] = peers;
+            info[i] = ballot_match<RADIX_BITS>((uint32_t)(key[i] >> shift) & mask);
         }
         // phase 2: one running-count update per (item, digit group), in item order
 #pragma unroll
@@ -562,15 +583,7 @@ tile_partition_kernel(int n_bins, const __grid_constant__ SortTab tab) {
         uint32_t info[ITEMS];
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
-            const uint32_t d = (uint32_t)(key[i] >> 32) & mask;
-            uint32_t peers = 0xffffffffu;
-#pragma unroll
-            for (int b = 0; b < WIDE_BITS; ++b) {
-                const bool bit = (d >> b) & 1u;
-                const uint32_t bal = __ballot_sync(0xffffffffu, bit);
-                peers &= bit ? bal : ~bal;
-            }
-            info[i] = peers;
+            info[i] = ballot_match<WIDE_BITS>((uint32_t)(key[i] >> 32) & mask);
         }
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
