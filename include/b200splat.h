@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define B200SPLAT_ABI_VERSION 2
+#define B200SPLAT_ABI_VERSION 3
 
 #define B200SPLAT_OK 0
 #define B200SPLAT_ERR_INVALID -1   /* bad argument                                  */
@@ -225,6 +225,10 @@ typedef struct b200splat_batch_backward_args {
     float* dL_drotations;
     void* const* scratch;              /* V, each >= b200splat_backward_scratch_bytes(P) */
     int32_t accumulate;
+    /* != 0: the caller guarantees every scratch buffer is all-zero on entry (e.g. a persistent workspace
+     * allocated zeroed); the library then skips its own clear and leaves the buffers all-zero on return
+     * (the consumer kernel zeroes each record it has read), so the next call can pass 1 again */
+    int32_t scratch_clean;
     float* stat_grad_accum;
     float* stat_denom;
     float* stat_max_radii;

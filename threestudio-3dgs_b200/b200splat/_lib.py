@@ -13,7 +13,7 @@ from pathlib import Path
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("B200SPLAT_LIB", _HERE / "libb200splat.so"))
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_VIEWS = 8
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
@@ -94,7 +94,7 @@ class BatchBackwardArgs(C.Structure):
         ("dL_dout_color", PP), ("dL_dout_depth", PP), ("dL_dout_alpha", PP), ("dL_dmeans2D", PP),
         ("dL_dmeans3D", C.c_void_p), ("dL_dshs", C.c_void_p), ("dL_dcolors", C.c_void_p),
         ("dL_dopacity", C.c_void_p), ("dL_dscales", C.c_void_p), ("dL_drotations", C.c_void_p),
-        ("scratch", PP), ("accumulate", C.c_int32),
+        ("scratch", PP), ("accumulate", C.c_int32), ("scratch_clean", C.c_int32),
         ("stat_grad_accum", C.c_void_p), ("stat_denom", C.c_void_p), ("stat_max_radii", C.c_void_p),
         ("stream", C.c_void_p),
     ]

@@ -78,7 +78,9 @@ class BatchWorkspace:
         f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=device)
         self.geom = [u8(lib.b200splat_geom_bytes(P)) for _ in range(V)]
         self.image = [u8(lib.b200splat_image_bytes(H, W)) for _ in range(V)]
-        self.scratch = [u8(lib.b200splat_backward_scratch_bytes(P)) for _ in range(V)]
+        # all-zero on entry to every backward and left all-zero by it (b200splat_batch_backward_args.scratch_clean)
+        self.scratch = [torch.zeros(int(lib.b200splat_backward_scratch_bytes(P)), dtype=torch.uint8, device=device)
+                        for _ in range(V)]
         self.color = [f32(3, H, W) for _ in range(V)]
         self.depth = [f32(1, H, W) for _ in range(V)]
         self.alpha = [f32(1, H, W) for _ in range(V)]
@@ -155,8 +157,14 @@ def backward_batched(ws: BatchWorkspace, cams: Sequence[ops.Cam], means3D, shs, 
     if stats is not None:
         a.stat_grad_accum, a.stat_denom, a.stat_max_radii = (ops._ptr(t) for t in stats)
     a.stream = ops._stream()
-    with torch.cuda.device(ws.device):
-        check(lib.b200splat_backward_batched(C.byref(a)), "b200splat_backward_batched")
+    a.scratch_clean = 1   # ws.scratch is zero on entry; the library leaves it zero (it re-zeroes what it consumed)
+    try:
+        with torch.cuda.device(ws.device):
+            check(lib.b200splat_backward_batched(C.byref(a)), "b200splat_backward_batched")
+    except Exception:
+        for t in ws.scratch:   # a failed launch may leave partial sums behind: restore the invariant
+            t.zero_()
+        raise
 
 
 class BatchRenderer:

@@ -159,6 +159,7 @@ static int init_table(const b200splat_camera& c, int P, int M, bool has_sh, Batc
     // (upstream sorts 32 + getHigherMsb(T) bits; the tile ids are < T, so the bits of T - 1 give the same order)
     tab->end_bit = tile_id_bits(tab->grid_x * tab->grid_y);
     tab->idx_bits = 32;
+    tab->clean_scratch = 0;
     tab->digit_passes = pair_sort_digit_passes(tab->end_bit);
     return B200SPLAT_OK;
 }
@@ -267,7 +268,7 @@ static PinnedSlot& pinned() {
 using namespace b200splat;
 
 // binning + render part of the forward, common to the single-view and the batched entry points
-static int forward_tail(BatchTab& tab, int debug, cudaStream_t st) {
+static int forward_tail(BatchTab& tab, int debug, cudaStream_t st, bool binning_cleared = false) {
     const int T = tab.grid_x * tab.grid_y;
     const int sel = sorted_sel_for(T);
     b200splat_camera dbg{};
@@ -275,7 +276,7 @@ static int forward_tail(BatchTab& tab, int debug, cudaStream_t st) {
     if (tab.P > 0 && tab.capacity > 0) {
         tab.sort_tiles_cap = sort_tiles_for(tab.capacity);
         { ProfScope ps(2, st);
-        for (int v = 0; v < tab.V; ++v) {
+        for (int v = 0; v < tab.V && !binning_cleared; ++v) {
             CU(cudaMemsetAsync(tab.v[v].hist, 0, pair_sort_zero_bytes(tab.capacity, tab.end_bit), st));
             CU(cudaMemsetAsync(tab.v[v].tile_count, 0, (size_t)T * sizeof(uint32_t), st));
         }
@@ -338,7 +339,7 @@ int b200splat_forward(const b200splat_forward_args* a) {
     vt.radii = a->radii;
     if (a->num_rendered_out) *a->num_rendered_out = 0;
     if (a->binning_out) *a->binning_out = a->binning_buffer;
-    CU(cudaMemsetAsync(vt.status, 0, STATUS_WORDS * sizeof(uint32_t), st));
+    if (P <= 0) CU(cudaMemsetAsync(vt.status, 0, STATUS_WORDS * sizeof(uint32_t), st));
 
     int64_t R = 0;
     if (P > 0) {
@@ -347,14 +348,15 @@ int b200splat_forward(const b200splat_forward_args* a) {
             return fail(B200SPLAT_ERR_NOMEM, "geom_buffer too small");
         fill_geom(P, a->geom_buffer, &vt);
         { ProfScope ps(0, st);
+        CU(launch_clear_batch(tab, /*with_binning=*/false, st));   // binning buffer: sized after the scan
         CU(launch_preprocess(tab, a->means3D, a->scales, a->rotations, a->opacities, a->shs, a->colors_precomp,
                              a->cov3D_precomp, st)); }
         DEBUG_SYNC(a->cam, st, "preprocess");
         { ProfScope ps(3, st, /*counted=*/false);
-        CU(launch_gaussian_sort(tab, st)); }
+        CU(launch_gaussian_sort(tab, st, /*cleared=*/true)); }
         DEBUG_SYNC(a->cam, st, "depth sort");
         { ProfScope ps(1, st);
-        CU(launch_scan_batch(tab, st)); }
+        CU(launch_scan_batch(tab, st, /*cleared=*/true)); }
         DEBUG_SYNC(a->cam, st, "scan");
         // the one host<->device round trip of the single-view forward: num_rendered sizes the binning buffer
         // (the batched entry point works on a caller-chosen capacity instead and never waits)
@@ -415,19 +417,19 @@ int b200splat_forward_batched(const b200splat_batch_forward_args* a) {
         fill_binning(cap, a->binning_buffer[v], &vt);
         vt.out_color = a->out_color[v], vt.out_depth = a->out_depth[v], vt.out_alpha = a->out_alpha[v];
         vt.radii = a->radii[v];
-        CU(cudaMemsetAsync(vt.status, 0, STATUS_WORDS * sizeof(uint32_t), st));
     }
     { ProfScope ps(0, st);
+    CU(launch_clear_batch(tab, /*with_binning=*/true, st));
     CU(launch_preprocess(tab, a->means3D, a->scales, a->rotations, a->opacities, a->shs, a->colors_precomp, nullptr,
                          st)); }
     DEBUG_SYNC(a->cams[0], st, "preprocess");
     { ProfScope ps(3, st, /*counted=*/false);
-    CU(launch_gaussian_sort(tab, st)); }
+    CU(launch_gaussian_sort(tab, st, /*cleared=*/true)); }
     DEBUG_SYNC(a->cams[0], st, "depth sort");
     { ProfScope ps(1, st);
-    CU(launch_scan_batch(tab, st)); }
+    CU(launch_scan_batch(tab, st, /*cleared=*/true)); }
     DEBUG_SYNC(a->cams[0], st, "scan");
-    rc = forward_tail(tab, a->cams[0].debug, st);
+    rc = forward_tail(tab, a->cams[0].debug, st, /*binning_cleared=*/true);
     if (rc) return rc;
     if (a->sync) {
         static thread_local uint32_t* host = nullptr;
@@ -451,14 +453,16 @@ static int backward_run(BatchTab& tab, const float* means3D, const float* scales
                         const float* shs, const float* cov3D_precomp, float* dL_dmeans3D, float* dL_dshs,
                         float* dL_dcolors, float* dL_dopacity, float* dL_dscales, float* dL_drotations,
                         float* dL_dcov3D, float* sa, float* sd, float* sm, int accumulate, int debug, bool any_pairs,
-                        cudaStream_t st) {
+                        cudaStream_t st, bool scratch_clean = false) {
     b200splat_camera dbg{};
     dbg.debug = debug;
     const int sel = sorted_sel_for(tab.grid_x * tab.grid_y);
     {
         ProfScope ps(6, st);
-        for (int v = 0; v < tab.V; ++v)
-            CU(cudaMemsetAsync(tab.v[v].grad2d, 0, (size_t)tab.P * GRAD2D_FLOATS * sizeof(float), st));
+        tab.clean_scratch = scratch_clean ? 1 : 0;
+        if (!scratch_clean)
+            for (int v = 0; v < tab.V; ++v)
+                CU(cudaMemsetAsync(tab.v[v].grad2d, 0, (size_t)tab.P * GRAD2D_FLOATS * sizeof(float), st));
         if (any_pairs) CU(launch_render_backward(tab, sel, st));
     }
     DEBUG_SYNC(dbg, st, "render backward");
@@ -541,7 +545,7 @@ int b200splat_backward_batched(const b200splat_batch_backward_args* a) {
     }
     return backward_run(tab, a->means3D, a->scales, a->rotations, a->shs, nullptr, a->dL_dmeans3D, a->dL_dshs,
                         a->dL_dcolors, a->dL_dopacity, a->dL_dscales, a->dL_drotations, nullptr, a->stat_grad_accum,
-                        a->stat_denom, a->stat_max_radii, a->accumulate, a->cams[0].debug, true, st);
+                        a->stat_denom, a->stat_max_radii, a->accumulate, a->cams[0].debug, true, st, a->scratch_clean != 0);
 }
 
 int b200splat_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,

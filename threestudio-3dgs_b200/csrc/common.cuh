@@ -101,6 +101,7 @@ struct BatchTab {
     int sort_tiles_cap;        // ceil(capacity / SORT_TILE)
     int digit_passes;          // 8-bit passes of the pair sort; 0 = one wide pass binned by the per-tile counts
     int idx_bits;              // index bits of a pair word (32)
+    int clean_scratch;         // preprocess backward zeroes every grad2d record it has read (self-cleaning scratch)
     uint32_t* tile_order;      // [V * T] entries (view * T + tile), longest list first
     ViewTab v[MAX_VIEWS];
 };
@@ -147,8 +148,10 @@ cudaError_t launch_mark_visible(int P, const float* means3D, const float* view, 
                                 uint8_t* present, cudaStream_t st);
 
 size_t scan_workspace_bytes(int64_t n);
-cudaError_t launch_scan_batch(const BatchTab& tab, cudaStream_t st);   // tiles_touched (in depth order) -> point_offsets
-cudaError_t launch_gaussian_sort(const BatchTab& tab, cudaStream_t st);   // gwords[0] sorted by depth bits (stable)
+cudaError_t launch_scan_batch(const BatchTab& tab, cudaStream_t st, bool cleared = false);
+// zero the small per-view work areas of a forward in one launch (with_binning: also the pair sort's and the tile counts)
+cudaError_t launch_clear_batch(const BatchTab& tab, bool with_binning, cudaStream_t st);   // tiles_touched (in depth order) -> point_offsets
+cudaError_t launch_gaussian_sort(const BatchTab& tab, cudaStream_t st, bool cleared = false);   // gwords[0] sorted by depth bits (stable)
 cudaError_t launch_inclusive_scan(int64_t n, const uint32_t* in, uint32_t* out, void* ws, cudaStream_t st);
 size_t sort_workspace_bytes(int64_t n);
 void sort_workspace_views(void* ws, uint32_t** hist, uint32_t** tickets, uint32_t** desc);

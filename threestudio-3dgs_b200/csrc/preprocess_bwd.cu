@@ -280,6 +280,14 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
     float st_norm = 0.f, st_cnt = 0.f;
 
     cpa_wait<1>();   // the gradient records have landed (each thread reads only what it copied itself)
+    if (tab.clean_scratch) {   // self-cleaning scratch: the record is consumed, leave zeros for the next backward
+        for (int v = 0; v < V; ++v) {
+            if ((vis >> v) & 1u) {
+                float4* gp = reinterpret_cast<float4*>(tab.v[v].grad2d) + 3 * (size_t)idx;
+                gp[0] = gp[1] = gp[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
     for (int v = 0; v < V; ++v) {
         const ViewTab& vt = tab.v[v];
         if (!((vis >> v) & 1u)) {

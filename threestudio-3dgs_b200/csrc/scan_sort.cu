@@ -154,7 +154,49 @@ size_t scan_workspace_bytes(int64_t n) {
     return align_up(16 + (size_t)tiles * 8, 256);
 }
 
-cudaError_t launch_scan_batch(const BatchTab& tab, cudaStream_t st) {
+// One launch zeroes every small per-view work area of a forward (status words, scan descriptors, the depth
+// sort's and the pair sort's histograms / tickets / look-back descriptors, per-tile counts) for all views --
+// instead of 5 memset nodes per view in the stream.
+constexpr int CLEAR_REGIONS = 5;
+struct ClearTab {
+    uint32_t* p[MAX_VIEWS][CLEAR_REGIONS];
+    uint32_t words[CLEAR_REGIONS];
+};
+__global__ void __launch_bounds__(256)
+clear_regions_kernel(const __grid_constant__ ClearTab tab) {
+    uint32_t* __restrict__ p = tab.p[blockIdx.z][blockIdx.y];
+    const uint32_t n = tab.words[blockIdx.y];
+    if (p == nullptr) return;
+    const uint32_t n4 = ((reinterpret_cast<uintptr_t>(p) & 15) == 0) ? n / 4 : 0;
+    uint4* p4 = reinterpret_cast<uint4*>(p);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x)
+        p4[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (uint32_t i = 4 * n4 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0u;
+}
+size_t pair_sort_zero_bytes(int64_t capacity, int end_bit);
+cudaError_t launch_clear_batch(const BatchTab& tab, bool with_binning, cudaStream_t st) {
+    if (tab.P <= 0) return cudaSuccess;
+    ClearTab c;
+    const int T = tab.grid_x * tab.grid_y;
+    c.words[0] = STATUS_WORDS;
+    c.words[1] = (uint32_t)(scan_workspace_bytes(tab.P) / 4);
+    c.words[2] = (uint32_t)(sort_workspace_zero_bytes(tab.P, 32) / 4);
+    c.words[3] = with_binning ? (uint32_t)(pair_sort_zero_bytes(tab.capacity, tab.end_bit) / 4) : 0u;
+    c.words[4] = with_binning ? (uint32_t)T : 0u;
+    for (int v = 0; v < MAX_VIEWS; ++v) {
+        const bool live = v < tab.V;
+        c.p[v][0] = live ? tab.v[v].status : nullptr;
+        c.p[v][1] = live ? tab.v[v].scan_ticket : nullptr;
+        c.p[v][2] = live ? tab.v[v].ghist : nullptr;
+        c.p[v][3] = live && with_binning ? tab.v[v].hist : nullptr;
+        c.p[v][4] = live && with_binning ? tab.v[v].tile_count : nullptr;
+    }
+    clear_regions_kernel<<<dim3(48, CLEAR_REGIONS, tab.V), 256, 0, st>>>(c);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scan_batch(const BatchTab& tab, cudaStream_t st, bool cleared) {
     const int64_t n = tab.P;
     if (n <= 0) return cudaSuccess;
     const int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
@@ -166,8 +208,10 @@ cudaError_t launch_scan_batch(const BatchTab& tab, cudaStream_t st) {
         s.out[v] = tab.v[v].point_offsets;
         s.ticket[v] = tab.v[v].scan_ticket;
         s.desc[v] = tab.v[v].scan_desc;
-        cudaError_t e = cudaMemsetAsync(tab.v[v].scan_ticket, 0, scan_workspace_bytes(n), st);
-        if (e != cudaSuccess) return e;
+        if (!cleared) {
+            cudaError_t e = cudaMemsetAsync(tab.v[v].scan_ticket, 0, scan_workspace_bytes(n), st);
+            if (e != cudaSuccess) return e;
+        }
     }
     scan_lookback_kernel<<<dim3((unsigned)tiles, tab.V), SCAN_THREADS, 0, st>>>(n, s);
     count_launch();
@@ -845,7 +889,7 @@ static cudaError_t launch_keys_pass(int shift, int bits, const SortTab& t, int t
 
 // Stable sort of every view's P Gaussian words (depth_bits << 32 | index) on the depth bits: 4 passes over P
 // elements (instead of 6 passes over ~3.6 P pair keys).  Result in gwords[0].
-cudaError_t launch_gaussian_sort(const BatchTab& tab, cudaStream_t st) {
+cudaError_t launch_gaussian_sort(const BatchTab& tab, cudaStream_t st, bool cleared) {
     if (tab.P <= 0) return cudaSuccess;
     cudaError_t e = ensure_sort_attr();
     if (e != cudaSuccess) return e;
@@ -854,8 +898,10 @@ cudaError_t launch_gaussian_sort(const BatchTab& tab, cudaStream_t st) {
     const int tiles = (int)((n + (int64_t)SORT_THREADS * items - 1) / ((int64_t)SORT_THREADS * items));
     HistTab ht;
     for (int v = 0; v < tab.V; ++v) {
-        e = cudaMemsetAsync(tab.v[v].ghist, 0, sort_workspace_zero_bytes(n, 32), st);
-        if (e != cudaSuccess) return e;
+        if (!cleared) {
+            e = cudaMemsetAsync(tab.v[v].ghist, 0, sort_workspace_zero_bytes(n, 32), st);
+            if (e != cudaSuccess) return e;
+        }
         ht.keys[v] = tab.v[v].gwords[0];
         ht.hist[v] = tab.v[v].ghist;
     }
