@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--views-per-gpu", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="launch the step from Python every time (no CUDA graph)")
     ap.add_argument("--cpu-sample-tiles", type=int, default=0,
                     help="tiles of the CPU-oracle sample (0: 512 for the cpu_baseline leg, 256 per reference-arm step)")
     return ap.parse_args()
@@ -230,8 +231,25 @@ def main():
     packed = renderer.packed
     renderer.calibrate(cams, means3D, shs, None, opac, scales, rots)
 
+    # the step's launches are recorded once into a CUDA graph (the C ABI never synchronises in the batched path);
+    # --eager launches them from Python every step instead
+    graph, launch_mode = None, "eager"
+    l_a = _lib.launch_count()
+    renderer.step(cams, means3D, shs, None, opac, scales, rots, pgrads)
+    launches_per_step = _lib.launch_count() - l_a
+    if not args.eager:
+        try:
+            graph = renderer.capture_step(cams, means3D, shs, None, opac, scales, rots, pgrads)
+            launch_mode = "cuda_graph"
+        except Exception as exc:   # report, do not hide: the run continues on the eager path
+            print(f"bench: CUDA graph capture failed ({exc!r}); eager launches", file=sys.stderr)
+            graph = None
+
     def step():
-        renderer.step(cams, means3D, shs, None, opac, scales, rots, pgrads)
+        if graph is not None:
+            graph.replay()
+        else:
+            renderer.step(cams, means3D, shs, None, opac, scales, rots, pgrads)
         bdist.allreduce_packed(packed.buffer, packed.max_radii)
 
     def barrier():
@@ -253,7 +271,7 @@ def main():
         step()
     e1.record()
     barrier()
-    launches = _lib.launch_count() - l0
+    launches = (_lib.launch_count() - l0) if graph is None else launches_per_step * args.steps
     if renderer.overflowed():
         raise SystemExit("bench: a view exceeded its binning capacity during the timed region (invalid run)")
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -475,6 +493,7 @@ def main():
             "config": {"workload": args.workload, "gaussians": P, "sh_degree": scene.sh_degree, "image": [H, W],
                        "views_per_gpu_per_step": V, "global_views_per_step": V * N,
                        "path": "b200splat_forward_batched/_backward_batched: one launch per phase for the V views",
+                       "launch": launch_mode,
                        "parallelism": f"view-dp{N}" if N > 1 else "single",
                        "allreduce_bytes_per_step": (packed.nbytes + 4 * P) if N > 1 else 0,
                        "l2": "inputs larger than L2: %.0f MB parameters + per-view key/value buffers > 126 MB"

@@ -340,6 +340,19 @@ def test_batched_entry_points_match_per_view_path():
     assert torch.equal(br.packed.max_radii, pk_ref.max_radii)
     assert torch.equal(br.packed.views["denom"], pk_ref.views["denom"])
     assert rel_err(br.packed.views["grad_accum"], pk_ref.views["grad_accum"]) < 1e-5
+    # the backward scratch cleans itself (scratch_clean): a second and a third step give the same gradients,
+    # and so does the CUDA-graph replay of the step
+    first = br.packed.buffer.clone()
+    for _ in range(2):
+        br.step(cams, m3, sh, None, op, scl, rot, pgs)
+        assert rel_err(br.packed.buffer, first) < 1e-5
+    for t in ws.scratch:
+        assert int(t.view(torch.int32).ne(0).sum()) == 0, "scratch must be all-zero between steps"
+    graph = br.capture_step(cams, m3, sh, None, op, scl, rot, pgs)
+    br.packed.buffer.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert rel_err(br.packed.buffer, first) < 1e-5
     # sorted keys / ranges of a batched view are those of the single-view call
     st_b = ws.states(sh.shape[1])[1]
     vb = ops.forward_views(cams[1], st_b)

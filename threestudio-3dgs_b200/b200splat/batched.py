@@ -216,6 +216,24 @@ class BatchRenderer:
                              accumulate=ci > 0, stats=stats)
             i += n
 
+    def capture_step(self, cams, means3D, shs, colors_precomp, opacities, scales, rotations, pixel_grads):
+        """Record one step (every launch of the view batch's forward + backward) into a CUDA graph and return it;
+        ``graph.replay()`` then re-runs the step on the same buffers without per-launch host work.  The inputs
+        must keep their addresses (parameters updated in place, cameras / pixel gradients written into the same
+        tensors); pixel_grads must be tensors, not callables."""
+        assert self.calibrated, "calibrate() first: the binning capacity is baked into the graph"
+        assert not any(callable(pg) for pg in pixel_grads)
+        args = (cams, means3D, shs, colors_precomp, opacities, scales, rotations, pixel_grads)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            self.step(*args)   # eager once on the side stream: one-time attribute / allocation work happens here
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.step(*args)
+        return graph
+
     def overflowed(self) -> bool:
         """Lazy overflow check (one small D2H): True if any view of the last step exceeded its capacity."""
         flags = []
