@@ -287,28 +287,45 @@ duplicate_kernel(const __grid_constant__ BatchTab tab) {
     const uint32_t* __restrict__ point_offsets = vt.point_offsets;
     const uint64_t* __restrict__ order = vt.gwords[0];
     uint64_t* __restrict__ words = vt.keys[0];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < tab.P; i += gridDim.x * blockDim.x) {
-        const uint32_t g = (uint32_t)__ldg(order + i);
-        const ushort4 rc = __ldg(rect + g);   // 8-byte gather from an L2-resident array (not the 48-byte record)
-        const int x0 = rc.x, y0 = rc.y, x1 = rc.z, y1 = rc.w;
-        const uint32_t ntiles = (uint32_t)((x1 - x0) * (y1 - y0));
-        if (ntiles == 0) continue;
-        uint32_t off = (i == 0) ? 0u : point_offsets[i - 1];
-        if (off + ntiles > tab.capacity) {
-            atomicOr(vt.status + STATUS_OVERFLOW, 1u);
-            continue;
+    // 4 Gaussians per thread and iteration: the order words / offsets of all four, then the four dependent rectangle
+    // gathers, are in flight together (the kernel was bound by the order -> rect load chain)
+    constexpr int DUP_ILP = 4;
+    const int stride = gridDim.x * blockDim.x;
+    for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < tab.P; i0 += DUP_ILP * stride) {
+        uint32_t g[DUP_ILP], off[DUP_ILP];
+        ushort4 rc[DUP_ILP];
+#pragma unroll
+        for (int u = 0; u < DUP_ILP; ++u) {
+            const int i = i0 + u * stride;
+            const bool live = i < tab.P;
+            g[u] = live ? (uint32_t)__ldg(order + i) : 0u;
+            off[u] = (live && i > 0) ? __ldg(point_offsets + i - 1) : 0u;
         }
-        for (int ty = y0; ty < y1; ++ty) {
-            for (int tx = x0; tx < x1; ++tx) {
-                const uint32_t tile = (uint32_t)(ty * gx + tx);
-                words[off] = ((uint64_t)tile << 32) | (uint64_t)g;
-                ++off;
-                if (tile_hist) {
-                    atomicAdd(&s_tile[tile], 1u);   // digit histograms of the tile bytes are derived at flush time
-                } else {
-                    for (int p = 0; p < passes; ++p) {
-                        const int bits = min(8, end_bit - 8 * p);
-                        atomicAdd(&s_hist[p * 256 + ((tile >> (8 * p)) & ((1u << bits) - 1u))], 1u);
+#pragma unroll
+        for (int u = 0; u < DUP_ILP; ++u)
+            rc[u] = (i0 + u * stride < tab.P) ? __ldg(rect + g[u]) : make_ushort4(0, 0, 0, 0);
+#pragma unroll
+        for (int u = 0; u < DUP_ILP; ++u) {
+            const int x0 = rc[u].x, y0 = rc[u].y, x1 = rc[u].z, y1 = rc[u].w;
+            const uint32_t ntiles = (uint32_t)((x1 - x0) * (y1 - y0));
+            if (ntiles == 0) continue;
+            uint32_t o = off[u];
+            if (o + ntiles > tab.capacity) {
+                atomicOr(vt.status + STATUS_OVERFLOW, 1u);
+                continue;
+            }
+            for (int ty = y0; ty < y1; ++ty) {
+                for (int tx = x0; tx < x1; ++tx) {
+                    const uint32_t tile = (uint32_t)(ty * gx + tx);
+                    words[o] = ((uint64_t)tile << 32) | (uint64_t)g[u];
+                    ++o;
+                    if (tile_hist) {
+                        atomicAdd(&s_tile[tile], 1u);   // digit histograms of the tile bytes are derived at flush time
+                    } else {
+                        for (int p = 0; p < passes; ++p) {
+                            const int bits = min(8, end_bit - 8 * p);
+                            atomicAdd(&s_hist[p * 256 + ((tile >> (8 * p)) & ((1u << bits) - 1u))], 1u);
+                        }
                     }
                 }
             }
