@@ -41,6 +41,8 @@ def parse_args():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--views-per-gpu", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--allreduce", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU gradient exchange: own NVLink peer-memory kernel (default) or NCCL")
     ap.add_argument("--eager", action="store_true", help="launch the step from Python every time (no CUDA graph)")
     ap.add_argument("--cpu-sample-tiles", type=int, default=0,
                     help="tiles of the CPU-oracle sample (0: 512 for the cpu_baseline leg, 256 per reference-arm step)")
@@ -227,7 +229,17 @@ def main():
     cams = [dev_cam(c) for c in cams_host]
     pgrads_host = [scenes.pixel_grads(H, W, 99 + rank * V + v) for v in range(V)]
     pgrads = [tuple(to(g) for g in pg) for pg in pgrads_host]
-    renderer = batched.BatchRenderer(P, M, H, W, dev, views=V)
+    # multi-GPU: the packed gradient buffer lives in CUDA-IPC memory mapped by all ranks and is all-reduced in
+    # place by one kernel per rank over NVLink peer memory (csrc/p2p.cu); --allreduce nccl uses NCCL instead
+    p2p, allreduce_mode = None, ("none" if world == 1 else "nccl")
+    if world > 1 and args.allreduce == "p2p" and P % 4 == 0:
+        try:
+            p2p = bdist.P2PAllReduce(batched.PackedGrads.floats(P, M), P, dev)
+            allreduce_mode = "p2p_nvlink_kernel"
+        except Exception as exc:
+            print(f"bench: P2P all-reduce unavailable ({exc!r}); using NCCL", file=sys.stderr)
+            p2p = None
+    renderer = batched.BatchRenderer(P, M, H, W, dev, views=V, packed_storage=None if p2p is None else p2p.buffer)
     packed = renderer.packed
     renderer.calibrate(cams, means3D, shs, None, opac, scales, rots)
 
@@ -250,7 +262,10 @@ def main():
             graph.replay()
         else:
             renderer.step(cams, means3D, shs, None, opac, scales, rots, pgrads)
-        bdist.allreduce_packed(packed.buffer, packed.max_radii)
+        if p2p is not None:
+            p2p()
+        else:
+            bdist.allreduce_packed(packed.buffer, packed.max_radii)
 
     def barrier():
         if world > 1:
@@ -274,6 +289,8 @@ def main():
     launches = (_lib.launch_count() - l0) if graph is None else launches_per_step * args.steps
     if renderer.overflowed():
         raise SystemExit("bench: a view exceeded its binning capacity during the timed region (invalid run)")
+    if p2p is not None and p2p.failed():
+        raise SystemExit("bench: the P2P all-reduce timed out waiting for a peer (invalid run)")
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -493,7 +510,7 @@ def main():
             "config": {"workload": args.workload, "gaussians": P, "sh_degree": scene.sh_degree, "image": [H, W],
                        "views_per_gpu_per_step": V, "global_views_per_step": V * N,
                        "path": "b200splat_forward_batched/_backward_batched: one launch per phase for the V views",
-                       "launch": launch_mode,
+                       "launch": launch_mode, "allreduce": allreduce_mode,
                        "parallelism": f"view-dp{N}" if N > 1 else "single",
                        "allreduce_bytes_per_step": (packed.nbytes + 4 * P) if N > 1 else 0,
                        "l2": "inputs larger than L2: %.0f MB parameters + per-view key/value buffers > 126 MB"

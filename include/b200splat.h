@@ -296,6 +296,33 @@ int b200splat_profile_enable(int32_t on);
  * clears the record.  Arrays must hold B200SPLAT_NUM_FAMILIES entries. */
 int b200splat_profile_read(float* ms, int64_t* count);
 
+/* ---- all-reduce over NVLink peer memory (new capability: the reference is single-GPU) ----------
+ * One process per GPU.  Each rank allocates its exchange buffer and its signal words with
+ * b200splat_p2p_alloc (cudaMalloc + CUDA IPC export, zero-filled), sends the 64-byte handles to its peers
+ * (any host channel: torch.distributed all_gather_object), maps the peers' with b200splat_p2p_open, and then
+ * calls b200splat_p2p_allreduce once per step on its own stream: floats [0, n_sum) of every rank's buffer
+ * become their sum over the ranks, floats [n_sum, n_sum + n_max) their maximum, in place, bit-identical on
+ * all ranks.  n_sum and n_max must be multiples of 4; epoch must increase by 1 per call, equally on all ranks.
+ * Returns B200SPLAT_OK immediately (stream-ordered); b200splat_p2p_error reads the rank's error flag
+ * (peer timeout) -- it synchronises nothing itself, call it after the stream is known to be idle. */
+#define B200SPLAT_P2P_MAX_RANKS 8
+#define B200SPLAT_P2P_HANDLE_BYTES 64
+#define B200SPLAT_P2P_SIGNAL_BYTES 256
+typedef struct b200splat_p2p_args {
+    int32_t rank, world;
+    void* bufs[B200SPLAT_P2P_MAX_RANKS];    /* device pointers valid on THIS rank: own buffer + mapped peers */
+    void* signals[B200SPLAT_P2P_MAX_RANKS]; /* same for the B200SPLAT_P2P_SIGNAL_BYTES signal areas */
+    int64_t n_sum, n_max;
+    uint32_t epoch;
+    b200splat_stream stream;
+} b200splat_p2p_args;
+int b200splat_p2p_alloc(size_t bytes, void** ptr, void* handle_out);
+int b200splat_p2p_open(const void* handle, void** ptr);
+int b200splat_p2p_close(void* mapped_ptr);
+int b200splat_p2p_free(void* ptr);
+int b200splat_p2p_allreduce(const b200splat_p2p_args* args);
+int b200splat_p2p_error(const void* own_signals, int32_t* flag_out);
+
 /* ---- misc ----------------------------------------------------------------------------------- */
 int b200splat_abi_version(void);
 const char* b200splat_last_error(void);

@@ -1,0 +1,62 @@
+"""All-reduce over NVLink peer memory (csrc/p2p.cu) against torch sums; needs >= 2 GPUs on the box
+(`gpurun --gpus 2 -- python -m pytest tests/test_p2p_gpu.py -m gpu`); skipped on a single GPU."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_sum, n_max, rounds, out):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "threestudio-3dgs_b200"))
+    import torch.distributed as dist
+    from b200splat import dist as bdist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dev = torch.device("cuda", rank)
+    ar = bdist.P2PAllReduce(n_sum, n_max, dev)
+    ok = True
+    for r in range(rounds):
+        gens = [torch.Generator().manual_seed(1000 * r + k) for k in range(world)]
+        parts = [torch.randn(n_sum + n_max, generator=g) for g in gens]
+        want_sum = parts[0][:n_sum].clone()
+        for k in range(1, world):            # the kernel sums in rank order: bit-exact expectation
+            want_sum += parts[k][:n_sum]
+        want_max = torch.stack([p[n_sum:] for p in parts]).max(0).values
+        ar.buffer.copy_(parts[rank].to(dev))
+        ar()
+        torch.cuda.synchronize(dev)
+        got = ar.buffer.cpu()
+        ok = ok and torch.equal(got[:n_sum], want_sum) and torch.equal(got[n_sum:], want_max)
+    ok = ok and not ar.failed()
+    ar.close()
+    res = torch.tensor([1 if ok else 0])
+    dist.all_reduce(res, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        out.put(int(res.item()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_sum,n_max", [(61 * 4096, 4096), (1 << 20, 0), (4, 4)])
+def test_p2p_allreduce_matches_rank_ordered_sum(n_sum, n_max):
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    mp.spawn(_worker, args=(world, _free_port(), n_sum, n_max, 3, q), nprocs=world, join=True)
+    assert q.get() == 1

@@ -100,11 +100,24 @@ class BatchBackwardArgs(C.Structure):
     ]
 
 
+class P2PArgs(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("bufs", C.c_void_p * 8), ("signals", C.c_void_p * 8),
+                ("n_sum", C.c_int64), ("n_max", C.c_int64), ("epoch", C.c_uint32), ("stream", C.c_void_p)]
+
+
+P2P_HANDLE_BYTES, P2P_SIGNAL_BYTES = 64, 256
+
 # every symbol include/b200splat.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "b200splat_abi_version": (C.c_int, []),
     "b200splat_last_error": (C.c_char_p, []),
     "b200splat_launch_count": (C.c_uint64, []),
+    "b200splat_p2p_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
+    "b200splat_p2p_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "b200splat_p2p_close": (C.c_int, [C.c_void_p]),
+    "b200splat_p2p_free": (C.c_int, [C.c_void_p]),
+    "b200splat_p2p_allreduce": (C.c_int, [C.POINTER(P2PArgs)]),
+    "b200splat_p2p_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "b200splat_geom_bytes": (C.c_size_t, [C.c_int32]),
     "b200splat_image_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "b200splat_binning_bytes": (C.c_size_t, [C.c_int64]),

@@ -30,14 +30,24 @@ class PackedGrads:
     grad_accum 1 | denom 1] x P floats in ONE contiguous fp32 buffer (the all-reduce payload,
     4*P*(13+3M) bytes), plus max_radii (P) reduced with MAX."""
 
-    def __init__(self, P: int, M: int, device, color_mode: str = "shs"):
+    @staticmethod
+    def floats(P: int, M: int, color_mode: str = "shs") -> int:
+        """Floats of the SUM segment (the MAX segment, max_radii, is P more)."""
+        return (13 + (3 * M if color_mode == "shs" else 3)) * P
+
+    def __init__(self, P: int, M: int, device, color_mode: str = "shs", storage: Optional[torch.Tensor] = None):
+        """``storage``: optional flat fp32 tensor of at least floats() + P elements that backs the buffer and
+        max_radii -- e.g. the exchange buffer of ``dist.P2PAllReduce``, so the all-reduce runs in place."""
         self.P, self.M, self.color_mode = P, M, color_mode
         ncol = 3 * M if color_mode == "shs" else 3
         widths = [("means3D", 3), ("scales", 3), ("rotations", 4), ("opacities", 1),
                   (color_mode if color_mode == "shs" else "colors_precomp", ncol),
                   ("grad_accum", 1), ("denom", 1)]
         total = sum(w for _, w in widths) * P
-        self.buffer = torch.zeros(total, dtype=torch.float32, device=device)
+        if storage is not None:
+            assert storage.dtype == torch.float32 and storage.is_contiguous() and storage.numel() >= total + P
+            storage[:total + P].zero_()
+        self.buffer = storage[:total] if storage is not None else torch.zeros(total, dtype=torch.float32, device=device)
         self.views: Dict[str, torch.Tensor] = {}
         off = 0
         for name, w in widths:
@@ -46,7 +56,8 @@ class PackedGrads:
         self.views["opacities"] = self.views["opacities"].view(P, 1)
         if color_mode == "shs":
             self.views["shs"] = self.views["shs"].view(P, M, 3)
-        self.max_radii = torch.zeros(P, dtype=torch.float32, device=device)
+        self.max_radii = storage[total:total + P] if storage is not None else \
+            torch.zeros(P, dtype=torch.float32, device=device)
         self.means2D_scratch = torch.empty(P, 3, dtype=torch.float32, device=device)
 
     @property
@@ -171,11 +182,12 @@ class BatchRenderer:
     """fwd+bwd of a step's views with persistent buffers.  ``step`` returns nothing: gradients and
     statistics are in ``packed``; rendered images stay in ``ws.color/depth/alpha`` until the next step."""
 
-    def __init__(self, P: int, M: int, H: int, W: int, device, views: int, color_mode: str = "shs"):
+    def __init__(self, P: int, M: int, H: int, W: int, device, views: int, color_mode: str = "shs",
+                 packed_storage: Optional[torch.Tensor] = None):
         self.P, self.M, self.H, self.W, self.device = P, M, H, W, device
         self.chunks = [min(MAX_VIEWS, views - i) for i in range(0, views, MAX_VIEWS)]
         self.ws = [BatchWorkspace(v, P, H, W, device) for v in self.chunks]
-        self.packed = PackedGrads(P, M, device, color_mode)
+        self.packed = PackedGrads(P, M, device, color_mode, storage=packed_storage)
         self.calibrated = False
 
     def calibrate(self, cams, means3D, shs, colors_precomp, opacities, scales, rotations, headroom: float = 1.25):

@@ -27,6 +27,7 @@ SOURCES = {
     "render.cu": [],
     "preprocess_bwd.cu": [],
     "knn.cu": [],
+    "p2p.cu": [],
     "api.cu": [],
 }
 

@@ -26,6 +26,106 @@ def allreduce_packed(buffer: torch.Tensor, max_radii: torch.Tensor, group=None):
     dist.all_reduce(max_radii, op=dist.ReduceOp.MAX, group=group)
 
 
+class _RawCudaArray:
+    """Zero-copy view of raw device memory for torch.as_tensor (CUDA array interface)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class P2PAllReduce:
+    """In-place SUM (+ MAX tail) all-reduce of one fp32 buffer per rank over NVLink peer memory
+    (include/b200splat.h b200splat_p2p_*, csrc/p2p.cu): every rank's buffer is cudaMalloc memory exported with
+    CUDA IPC and mapped by all peers; one kernel per rank reduces its slice from all ranks and stores the result to
+    all ranks.  ``buffer`` is the rank's exchange tensor (n_sum + n_max floats): build the step's PackedGrads on
+    it (``PackedGrads(..., storage=ar.buffer)``) and call ``ar()`` after the backward.  One process per GPU of
+    ONE box; the handles travel through ``torch.distributed`` (any backend)."""
+
+    def __init__(self, n_sum: int, n_max: int, device, group=None):
+        import ctypes as C
+        from . import _lib
+        self._lib, self._C = _lib, C
+        assert n_sum % 4 == 0 and n_max % 4 == 0, "segment lengths must be multiples of 4 floats"
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        assert self.world <= 8, "one NVSwitch box: at most 8 ranks"
+        self.n_sum, self.n_max, self.device, self.epoch = n_sum, n_max, torch.device(device), 0
+        lib = _lib.lib
+        # every step below is collective-safe: a rank that fails still takes part in the exchange of the status, so
+        # all ranks raise together instead of some waiting in a collective for a peer that already gave up
+        self._own, self._mapped = None, []
+        self._bufs, self._sigs = [0] * self.world, [0] * self.world
+        err = None
+        with torch.cuda.device(self.device):
+            buf, sig = C.c_void_p(), C.c_void_p()
+            hb, hs = C.create_string_buffer(_lib.P2P_HANDLE_BYTES), C.create_string_buffer(_lib.P2P_HANDLE_BYTES)
+            try:
+                _lib.check(lib.b200splat_p2p_alloc((n_sum + n_max) * 4, C.byref(buf), hb), "b200splat_p2p_alloc")
+                _lib.check(lib.b200splat_p2p_alloc(_lib.P2P_SIGNAL_BYTES, C.byref(sig), hs), "b200splat_p2p_alloc")
+                self._own = (buf.value, sig.value)
+            except Exception as exc:
+                err = repr(exc)
+            handles: list = [None] * self.world
+            dist.all_gather_object(handles, (err, hb.raw, hs.raw), group=group)
+            if not any(h[0] for h in handles):
+                try:
+                    for k, (_, b_h, s_h) in enumerate(handles):
+                        if k == self.rank:
+                            self._bufs[k], self._sigs[k] = self._own
+                            continue
+                        pb, ps = C.c_void_p(), C.c_void_p()
+                        _lib.check(lib.b200splat_p2p_open(b_h, C.byref(pb)), "b200splat_p2p_open")
+                        self._mapped.append(pb.value)
+                        _lib.check(lib.b200splat_p2p_open(s_h, C.byref(ps)), "b200splat_p2p_open")
+                        self._mapped.append(ps.value)
+                        self._bufs[k], self._sigs[k] = pb.value, ps.value
+                except Exception as exc:
+                    err = repr(exc)
+            status: list = [None] * self.world
+            dist.all_gather_object(status, err or next((h[0] for h in handles if h[0]), None), group=group)
+        bad = [f"rank {k}: {e}" for k, e in enumerate(status) if e]
+        if bad:
+            self.buffer = None
+            self._release()
+            raise RuntimeError("P2PAllReduce setup failed (" + "; ".join(bad) + ")")
+        self.buffer = torch.as_tensor(_RawCudaArray(self._own[0], n_sum + n_max, "<f4"), device=self.device)
+        dist.barrier(group=group)   # every rank has mapped every peer before the first exchange
+
+    def __call__(self):
+        """Stream-ordered on the current stream: on return of the kernel the buffer holds the reduced values."""
+        C, _lib = self._C, self._lib
+        self.epoch += 1
+        a = _lib.P2PArgs()
+        a.rank, a.world, a.n_sum, a.n_max, a.epoch = self.rank, self.world, self.n_sum, self.n_max, self.epoch
+        for k in range(self.world):
+            a.bufs[k], a.signals[k] = self._bufs[k], self._sigs[k]
+        a.stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib.b200splat_p2p_allreduce(C.byref(a)), "b200splat_p2p_allreduce")
+
+    def failed(self) -> bool:
+        """True if a peer never showed up within the kernel's spin bound (synchronises the device)."""
+        C = self._C
+        torch.cuda.synchronize(self.device)
+        flag = C.c_int32(0)
+        self._lib.check(self._lib.lib.b200splat_p2p_error(self._own[1], C.byref(flag)), "b200splat_p2p_error")
+        return flag.value != 0
+
+    def _release(self):
+        lib = self._lib.lib
+        for p in self._mapped:
+            lib.b200splat_p2p_close(p)
+        self._mapped = []
+        if self._own:
+            lib.b200splat_p2p_free(self._own[0])
+            lib.b200splat_p2p_free(self._own[1])
+            self._own = None
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        self.buffer = None
+        self._release()
+
+
 def reference_update_states(xyz_gradient_accum, denom, max_radii2D, grad_accum_step, denom_step, max_radii_step):
     """Apply one step's (all-reduced) statistics to the persistent accumulators exactly as the
     reference's per-view loop does (geometry/gaussian_base.py:815-819, 846-851)."""

@@ -298,6 +298,66 @@ static int forward_tail(BatchTab& tab, int debug, cudaStream_t st, bool binning_
 extern "C" {
 
 int b200splat_abi_version(void) { return B200SPLAT_ABI_VERSION; }
+
+// ---- all-reduce over NVLink peer memory ----------------------------------------------------------
+int b200splat_p2p_alloc(size_t bytes, void** ptr, void* handle_out) {
+    if (!ptr || !handle_out || bytes == 0) return fail(B200SPLAT_ERR_INVALID, "bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == B200SPLAT_P2P_HANDLE_BYTES, "IPC handle size");
+    void* p = nullptr;
+    CU(cudaMalloc(&p, bytes));
+    CU(cudaMemset(p, 0, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return fail(B200SPLAT_ERR_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle_out, &h, sizeof(h));
+    *ptr = p;
+    return B200SPLAT_OK;
+}
+int b200splat_p2p_open(const void* handle, void** ptr) {
+    if (!handle || !ptr) return fail(B200SPLAT_ERR_INVALID, "bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    CU(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return B200SPLAT_OK;
+}
+int b200splat_p2p_close(void* mapped_ptr) {
+    if (mapped_ptr) CU(cudaIpcCloseMemHandle(mapped_ptr));
+    return B200SPLAT_OK;
+}
+int b200splat_p2p_free(void* ptr) {
+    if (ptr) CU(cudaFree(ptr));
+    return B200SPLAT_OK;
+}
+int b200splat_p2p_allreduce(const b200splat_p2p_args* a) {
+    if (!a) return fail(B200SPLAT_ERR_INVALID, "null args");
+    if (a->world < 1 || a->world > P2P_MAX_RANKS || a->rank < 0 || a->rank >= a->world)
+        return fail(B200SPLAT_ERR_INVALID, "rank %d / world %d out of range (max %d)", a->rank, a->world, P2P_MAX_RANKS);
+    if (a->n_sum < 0 || a->n_max < 0 || (a->n_sum & 3) || (a->n_max & 3))
+        return fail(B200SPLAT_ERR_INVALID, "n_sum and n_max must be non-negative multiples of 4");
+    static_assert(P2P_SIGNAL_WORDS * 4 == B200SPLAT_P2P_SIGNAL_BYTES, "signal area size");
+    P2PTab t;
+    t.rank = a->rank, t.world = a->world, t.epoch = a->epoch;
+    t.n_sum4 = a->n_sum / 4, t.n_max4 = a->n_max / 4;
+    for (int k = 0; k < P2P_MAX_RANKS; ++k) {
+        t.bufs[k] = k < a->world ? reinterpret_cast<float*>(a->bufs[k]) : nullptr;
+        t.signals[k] = k < a->world ? reinterpret_cast<uint32_t*>(a->signals[k]) : nullptr;
+        if (k < a->world && (!t.bufs[k] || !t.signals[k] || (reinterpret_cast<uintptr_t>(t.bufs[k]) & 15)))
+            return fail(B200SPLAT_ERR_INVALID, "buffer / signal pointer of rank %d missing or misaligned", k);
+    }
+    if (a->world == 1) return B200SPLAT_OK;
+    CU(launch_p2p_allreduce(t, reinterpret_cast<cudaStream_t>(a->stream)));
+    return B200SPLAT_OK;
+}
+int b200splat_p2p_error(const void* own_signals, int32_t* flag_out) {
+    if (!own_signals || !flag_out) return fail(B200SPLAT_ERR_INVALID, "bad argument");
+    uint32_t w = 0;
+    CU(cudaMemcpy(&w, reinterpret_cast<const uint32_t*>(own_signals) + P2P_ERROR_WORD, 4, cudaMemcpyDeviceToHost));
+    *flag_out = (int32_t)w;
+    return B200SPLAT_OK;
+}
 const char* b200splat_last_error(void) { return g_err; }
 uint64_t b200splat_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 

@@ -181,6 +181,20 @@ cudaError_t launch_dist2(int P, const float* points, float* out, void* ws, cudaS
 
 void count_launch(int n = 1);
 
+// ---- all-reduce over NVLink peer memory (p2p.cu) -------------------------------------------------
+constexpr int P2P_MAX_RANKS = 8;
+constexpr int P2P_ERROR_WORD = 2 * P2P_MAX_RANKS;       // signal row layout: [ready x 8][done x 8][error][counter]
+constexpr int P2P_COUNTER_WORD = 2 * P2P_MAX_RANKS + 1;
+constexpr int P2P_SIGNAL_WORDS = 64;
+struct P2PTab {
+    int rank, world;
+    uint32_t epoch;
+    int64_t n_sum4, n_max4;            // float4 counts: [0, n_sum4) summed, [n_sum4, n_sum4 + n_max4) max-reduced
+    float* bufs[P2P_MAX_RANKS];        // every rank's buffer (own + IPC-mapped peers)
+    uint32_t* signals[P2P_MAX_RANKS];  // every rank's signal words
+};
+cudaError_t launch_p2p_allreduce(const P2PTab& t, cudaStream_t st);
+
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // per-thread asynchronous 16-byte copies global -> shared (LDGSTS), groups committed / awaited by the same thread
 __device__ __forceinline__ void cpa16(void* smem_dst, const void* gmem_src) {

@@ -1,0 +1,209 @@
+// All-reduce of a rank's packed gradient buffer over NVLink peer memory, one kernel per rank.
+//
+// The view-data-parallel step (one process per GPU, Gaussians replicated) ends with SUM(packed gradients +
+// densification accumulators) and MAX(max_radii) over the ranks (b200splat/dist.py).  Every rank's buffer lives
+// in cudaMalloc memory exported with CUDA IPC and mapped by all peers, so one kernel per rank does the whole
+// exchange with plain loads / stores through NVSwitch:
+//
+//   phase 0  rank r tells every peer "my buffer is complete" (release store of the epoch into the peer's signal
+//            row) and waits for the same from every peer;
+//   reduce   r owns the r-th slice of the float4 index space: it loads that slice from ALL ranks (its own
+//            included) in rank order 0..N-1 -- so every rank ends up with bit-identical sums -- and stores the
+//            result into ALL ranks' buffers.  Only r ever touches slice r, anywhere, so the exchange is in place;
+//            inbound (peer loads) and outbound (peer stores) traffic run in opposite NVLink directions at once:
+//            (N-1)/N of the buffer each way, against 2 (N-1)/N each way for a ring all-reduce;
+//   phase 1  the last CTA to finish tells every peer "my stores have landed" (after a system fence) and waits for
+//            every peer's: when the kernel completes the local buffer is fully reduced and no peer reads it any more.
+//
+// Spins are bounded (about 4 s of SM clock): a dead peer turns into an error flag, not a hung GPU.
+#include "common.cuh"
+#include <cstdlib>
+
+namespace b200splat {
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_cg4(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_cg4(float4* p, float4 v) {
+    asm volatile("st.global.cg.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+struct float8 {
+    float v[8];
+};
+// 256-bit global accesses (LDG/STG.E.ENL2.256, sm_100): half as many NVLink requests as 128-bit ones
+__device__ __forceinline__ float8 ld_cg8(const float* p) {
+    float8 r;
+    asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]),
+                   "=f"(r.v[7])
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_cg8(float* p, const float8& r) {
+    asm volatile("st.global.cg.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]),
+                 "f"(r.v[3]), "f"(r.v[4]), "f"(r.v[5]), "f"(r.v[6]), "f"(r.v[7])
+                 : "memory");
+}
+
+constexpr long long P2P_SPIN_LIMIT = 8000000000ll;   // SM clocks
+
+// wait until every peer's word in my signal row `row` reached `epoch`; returns false on timeout
+__device__ __forceinline__ bool wait_row(const P2PTab& t, int row, int tid) {
+    bool ok = true;
+    if (tid < t.world) {
+        const uint32_t* flag = t.signals[t.rank] + row * P2P_MAX_RANKS + tid;
+        const long long t0 = clock64();
+        while ((int32_t)(ld_acquire_sys(flag) - t.epoch) < 0) {
+            if (clock64() - t0 > P2P_SPIN_LIMIT) {
+                ok = false;
+                break;
+            }
+        }
+        if (!ok) atomicExch(t.signals[t.rank] + P2P_ERROR_WORD, 1u);
+    }
+    return ok;
+}
+
+template <bool IS_MAX, int U>
+__device__ __forceinline__ void reduce_slice(const P2PTab& t, int64_t first4, int64_t n4, int mode) {
+    // float4 elements [first4, first4 + n4) of every rank's buffer; this rank's share of them
+    const int64_t lo = first4 + n4 * t.rank / t.world, hi = first4 + n4 * (t.rank + 1) / t.world;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += U * stride) {
+        float4 acc[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + u * stride;
+            acc[u] = i < hi ? ld_cg4(reinterpret_cast<const float4*>(t.bufs[0]) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int k = 1; k < t.world && mode != 2; ++k) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = i0 + u * stride;
+                v[u] = i < hi ? ld_cg4(reinterpret_cast<const float4*>(t.bufs[k]) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (IS_MAX) {
+                    acc[u].x = fmaxf(acc[u].x, v[u].x), acc[u].y = fmaxf(acc[u].y, v[u].y);
+                    acc[u].z = fmaxf(acc[u].z, v[u].z), acc[u].w = fmaxf(acc[u].w, v[u].w);
+                } else {
+                    acc[u].x += v[u].x, acc[u].y += v[u].y, acc[u].z += v[u].z, acc[u].w += v[u].w;
+                }
+            }
+        }
+        for (int k = 0; k < (mode == 1 ? 1 : t.world); ++k) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = i0 + u * stride;
+                if (i < hi) st_cg4(reinterpret_cast<float4*>(t.bufs[k]) + i, acc[u]);
+            }
+        }
+    }
+}
+
+// the same over 32-byte elements (first8 / n8 in units of 8 floats)
+template <bool IS_MAX, int U>
+__device__ __forceinline__ void reduce_slice8(const P2PTab& t, int64_t first8, int64_t n8) {
+    const int64_t lo = first8 + n8 * t.rank / t.world, hi = first8 + n8 * (t.rank + 1) / t.world;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += U * stride) {
+        float8 acc[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < hi) acc[u] = ld_cg8(t.bufs[0] + 8 * i);
+        }
+        for (int k = 1; k < t.world; ++k) {
+            float8 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = i0 + u * stride;
+                if (i < hi) v[u] = ld_cg8(t.bufs[k] + 8 * i);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (i0 + u * stride < hi) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        acc[u].v[c] = IS_MAX ? fmaxf(acc[u].v[c], v[u].v[c]) : acc[u].v[c] + v[u].v[c];
+                }
+            }
+        }
+        for (int k = 0; k < t.world; ++k) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = i0 + u * stride;
+                if (i < hi) st_cg8(t.bufs[k] + 8 * i, acc[u]);
+            }
+        }
+    }
+}
+
+template <int U>
+__global__ void __launch_bounds__(256)
+p2p_allreduce_kernel(const __grid_constant__ P2PTab t, int mode) {
+    __shared__ int s_flag;
+    const int tid = threadIdx.x;
+    // phase 0
+    if (blockIdx.x == 0 && tid < t.world) st_release_sys(t.signals[tid] + 0 * P2P_MAX_RANKS + t.rank, t.epoch);
+    if (tid == 0) s_flag = 1;
+    __syncthreads();
+    if (!wait_row(t, 0, tid)) s_flag = 0;
+    __syncthreads();
+    if (s_flag) {
+        const bool wide = mode == 0 && ((t.n_sum4 | t.n_max4) & 1) == 0 &&
+                          (reinterpret_cast<uintptr_t>(t.bufs[t.rank]) & 31) == 0;
+        if (wide) {
+            reduce_slice8<false, (U > 2 ? U / 2 : 1)>(t, 0, t.n_sum4 / 2);
+            reduce_slice8<true, (U > 2 ? U / 2 : 1)>(t, t.n_sum4 / 2, t.n_max4 / 2);
+        } else {
+            reduce_slice<false, U>(t, 0, t.n_sum4, mode);
+            reduce_slice<true, U>(t, t.n_sum4, t.n_max4, mode);
+        }
+    }
+    // phase 1.  One system fence per CTA, by the thread that then counts the CTA as finished (the barrier makes
+    // the other threads' stores part of what the fence orders); a fence per thread cost ~0.3 ms per call: every
+    // warp waited for its own NVLink round trip
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence_system();
+        uint32_t* counter = t.signals[t.rank] + P2P_COUNTER_WORD;
+        const uint32_t prev = atomicAdd(counter, 1u);
+        s_flag = (prev == gridDim.x - 1) ? 2 : 0;
+        if (s_flag == 2) {
+            *counter = 0u;
+            __threadfence_system();   // acquire side: every other CTA's fenced stores precede the signal below
+        }
+    }
+    __syncthreads();
+    if (s_flag == 2) {
+        if (tid < t.world) st_release_sys(t.signals[tid] + 1 * P2P_MAX_RANKS + t.rank, t.epoch);
+        wait_row(t, 1, tid);
+    }
+}
+
+cudaError_t launch_p2p_allreduce(const P2PTab& t, cudaStream_t st) {
+    static const int blocks = getenv("B200SPLAT_P2P_BLOCKS") ? atoi(getenv("B200SPLAT_P2P_BLOCKS")) : NUM_SMS * 4;
+    static const int unroll = getenv("B200SPLAT_P2P_UNROLL") ? atoi(getenv("B200SPLAT_P2P_UNROLL")) : 4;
+    static const int mode = getenv("B200SPLAT_P2P_MODE") ? atoi(getenv("B200SPLAT_P2P_MODE")) : 0;   // 1/2: timing experiments
+    if (unroll == 8) p2p_allreduce_kernel<8><<<blocks, 256, 0, st>>>(t, mode);
+    else if (unroll == 2) p2p_allreduce_kernel<2><<<blocks, 256, 0, st>>>(t, mode);
+    else p2p_allreduce_kernel<4><<<blocks, 256, 0, st>>>(t, mode);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace b200splat
