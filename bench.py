@@ -41,8 +41,9 @@ def parse_args():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--views-per-gpu", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--allreduce", default="p2p", choices=["p2p", "nccl"],
-                    help="multi-GPU gradient exchange: own NVLink peer-memory kernel (default) or NCCL")
+    ap.add_argument("--allreduce", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="multi-GPU gradient exchange: own NVLink peer-memory kernel, NCCL, or auto = the faster one "
+                         "measured on this pool (p2p up to 4 GPUs, NCCL/NVLS at 8)")
     ap.add_argument("--eager", action="store_true", help="launch the step from Python every time (no CUDA graph)")
     ap.add_argument("--cpu-sample-tiles", type=int, default=0,
                     help="tiles of the CPU-oracle sample (0: 512 for the cpu_baseline leg, 256 per reference-arm step)")
@@ -232,7 +233,8 @@ def main():
     # multi-GPU: the packed gradient buffer lives in CUDA-IPC memory mapped by all ranks and is all-reduced in
     # place by one kernel per rank over NVLink peer memory (csrc/p2p.cu); --allreduce nccl uses NCCL instead
     p2p, allreduce_mode = None, ("none" if world == 1 else "nccl")
-    if world > 1 and args.allreduce == "p2p" and P % 4 == 0:
+    use_p2p = args.allreduce == "p2p" or (args.allreduce == "auto" and world <= 4)
+    if world > 1 and use_p2p and P % 4 == 0:
         try:
             p2p = bdist.P2PAllReduce(batched.PackedGrads.floats(P, M), P, dev)
             allreduce_mode = "p2p_nvlink_kernel"
