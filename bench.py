@@ -44,6 +44,11 @@ def parse_args():
     ap.add_argument("--allreduce", default="auto", choices=["auto", "p2p", "nccl"],
                     help="multi-GPU gradient exchange: own NVLink peer-memory kernel, NCCL, or auto = the faster one "
                          "measured on this pool (p2p up to 4 GPUs, NCCL/NVLS at 8)")
+    ap.add_argument("--exchange-chunks", type=int, default=1,
+                    help="multi-GPU: Gaussian ranges of the preprocess backward whose exchange overlaps the next range "
+                         "(1 = one exchange after the step, the default: measured at 2 GPUs 1/2/4/8 ranges -> "
+                         "3976/3927/3815/3640 renders/s -- the per-range handshakes and the SM slots the exchange "
+                         "kernel takes from the compute cost more than the overlap returns)")
     ap.add_argument("--eager", action="store_true", help="launch the step from Python every time (no CUDA graph)")
     ap.add_argument("--cpu-sample-tiles", type=int, default=0,
                     help="tiles of the CPU-oracle sample (0: 512 for the cpu_baseline leg, 256 per reference-arm step)")
@@ -248,18 +253,34 @@ def main():
     # the step's launches are recorded once into a CUDA graph (the C ABI never synchronises in the batched path);
     # --eager launches them from Python every step instead
     graph, launch_mode = None, "eager"
+    chunks = args.exchange_chunks if world > 1 else 1
     l_a = _lib.launch_count()
     renderer.step(cams, means3D, shs, None, opac, scales, rots, pgrads)
     launches_per_step = _lib.launch_count() - l_a
     if not args.eager:
         try:
-            graph = renderer.capture_step(cams, means3D, shs, None, opac, scales, rots, pgrads)
+            graph = renderer.capture_step(cams, means3D, shs, None, opac, scales, rots, pgrads, head_only=chunks > 1)
             launch_mode = "cuda_graph"
         except Exception as exc:   # report, do not hide: the run continues on the eager path
             print(f"bench: CUDA graph capture failed ({exc!r}); eager launches", file=sys.stderr)
             graph = None
 
+    def exchange(g0, g1):
+        if p2p is not None:
+            p2p(packed.segments(g0, g1))
+        else:
+            bdist.allreduce_packed_range(packed, g0, g1)
+
     def step():
+        if chunks > 1:
+            # multi-GPU: forward + render backward, then preprocess backward in Gaussian ranges whose gradients are
+            # exchanged on a side stream while the next range is computed
+            if graph is not None:
+                graph.replay()
+            else:
+                renderer.step_head(cams, means3D, shs, None, opac, scales, rots, pgrads)
+            renderer.step_tail(cams, means3D, shs, None, opac, scales, rots, exchange, chunks=chunks)
+            return
         if graph is not None:
             graph.replay()
         else:
@@ -288,7 +309,9 @@ def main():
         step()
     e1.record()
     barrier()
-    launches = (_lib.launch_count() - l0) if graph is None else launches_per_step * args.steps
+    launches = _lib.launch_count() - l0          # launched from the host inside the timed region (incl. p2p kernels)
+    if graph is not None:                        # + the graph's nodes: the whole step, or the step minus the
+        launches += (launches_per_step - (1 if chunks > 1 else 0)) * args.steps   # chunked preprocess backward
     if renderer.overflowed():
         raise SystemExit("bench: a view exceeded its binning capacity during the timed region (invalid run)")
     if p2p is not None and p2p.failed():
@@ -512,7 +535,7 @@ def main():
             "config": {"workload": args.workload, "gaussians": P, "sh_degree": scene.sh_degree, "image": [H, W],
                        "views_per_gpu_per_step": V, "global_views_per_step": V * N,
                        "path": "b200splat_forward_batched/_backward_batched: one launch per phase for the V views",
-                       "launch": launch_mode, "allreduce": allreduce_mode,
+                       "launch": launch_mode, "allreduce": allreduce_mode, "exchange_chunks": chunks,
                        "parallelism": f"view-dp{N}" if N > 1 else "single",
                        "allreduce_bytes_per_step": (packed.nbytes + 4 * P) if N > 1 else 0,
                        "l2": "inputs larger than L2: %.0f MB parameters + per-view key/value buffers > 126 MB"

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define B200SPLAT_ABI_VERSION 3
+#define B200SPLAT_ABI_VERSION 4
 
 #define B200SPLAT_OK 0
 #define B200SPLAT_ERR_INVALID -1   /* bad argument                                  */
@@ -229,6 +229,12 @@ typedef struct b200splat_batch_backward_args {
      * allocated zeroed); the library then skips its own clear and leaves the buffers all-zero on return
      * (the consumer kernel zeroes each record it has read), so the next call can pass 1 again */
     int32_t scratch_clean;
+    /* phase: 0 = whole backward; 1 = render backward only (pixel gradients -> per-view 2-D gradient records);
+     * 2 = preprocess backward only, for the Gaussians [g_begin, g_end) (g_end <= 0: P) -- lets the caller exchange
+     * the finished gradients of one Gaussian range with its peers while the next range is computed */
+    int32_t phase;
+    int32_t g_begin;
+    int32_t g_end;
     float* stat_grad_accum;
     float* stat_denom;
     float* stat_max_radii;
@@ -300,19 +306,25 @@ int b200splat_profile_read(float* ms, int64_t* count);
  * One process per GPU.  Each rank allocates its exchange buffer and its signal words with
  * b200splat_p2p_alloc (cudaMalloc + CUDA IPC export, zero-filled), sends the 64-byte handles to its peers
  * (any host channel: torch.distributed all_gather_object), maps the peers' with b200splat_p2p_open, and then
- * calls b200splat_p2p_allreduce once per step on its own stream: floats [0, n_sum) of every rank's buffer
- * become their sum over the ranks, floats [n_sum, n_sum + n_max) their maximum, in place, bit-identical on
- * all ranks.  n_sum and n_max must be multiples of 4; epoch must increase by 1 per call, equally on all ranks.
+ * calls b200splat_p2p_allreduce on its own stream: every listed segment of every rank's buffer becomes its sum (or
+ * maximum) over the ranks, in place, bit-identical on all ranks.  Segment offsets / counts are multiples of 4 floats;
+ * epoch must increase by 1 per call, equally on all ranks (calls of one group are stream-ordered on each rank).
  * Returns B200SPLAT_OK immediately (stream-ordered); b200splat_p2p_error reads the rank's error flag
  * (peer timeout) -- it synchronises nothing itself, call it after the stream is known to be idle. */
 #define B200SPLAT_P2P_MAX_RANKS 8
 #define B200SPLAT_P2P_HANDLE_BYTES 64
 #define B200SPLAT_P2P_SIGNAL_BYTES 256
+#define B200SPLAT_P2P_MAX_SEGMENTS 16
+#define B200SPLAT_P2P_SUM 0
+#define B200SPLAT_P2P_MAX 1
 typedef struct b200splat_p2p_args {
     int32_t rank, world;
     void* bufs[B200SPLAT_P2P_MAX_RANKS];    /* device pointers valid on THIS rank: own buffer + mapped peers */
     void* signals[B200SPLAT_P2P_MAX_RANKS]; /* same for the B200SPLAT_P2P_SIGNAL_BYTES signal areas */
-    int64_t n_sum, n_max;
+    int32_t n_segments;                     /* 1..16 disjoint float ranges of the buffer, reduced in one kernel */
+    int64_t seg_offset[B200SPLAT_P2P_MAX_SEGMENTS]; /* in floats, multiple of 4 */
+    int64_t seg_count[B200SPLAT_P2P_MAX_SEGMENTS];  /* in floats, multiple of 4 */
+    int32_t seg_op[B200SPLAT_P2P_MAX_SEGMENTS];     /* B200SPLAT_P2P_SUM | B200SPLAT_P2P_MAX */
     uint32_t epoch;
     b200splat_stream stream;
 } b200splat_p2p_args;

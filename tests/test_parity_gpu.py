@@ -353,6 +353,17 @@ def test_batched_entry_points_match_per_view_path():
     graph.replay()
     torch.cuda.synchronize()
     assert rel_err(br.packed.buffer, first) < 1e-5
+    # the multi-GPU split of the step (forward + render backward | preprocess backward in Gaussian ranges, each
+    # followed by its exchange on a side stream) computes the same gradients
+    ranges = []
+    br.packed.buffer.zero_()
+    br.step_head(cams, m3, sh, None, op, scl, rot, pgs)
+    br.step_tail(cams, m3, sh, None, op, scl, rot, lambda g0, g1: ranges.append((g0, g1)), chunks=3)
+    torch.cuda.synchronize()
+    assert ranges[0][0] == 0 and ranges[-1][1] == P and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+    assert rel_err(br.packed.buffer, first) < 1e-5
+    segs = br.packed.segments(ranges[1][0], ranges[1][1])
+    assert len(segs) == len(br.packed.fields) + 1 and all(o % 4 == 0 and c % 4 == 0 for o, c, _ in segs)
     # sorted keys / ranges of a batched view are those of the single-view call
     st_b = ws.states(sh.shape[1])[1]
     vb = ops.forward_views(cams[1], st_b)

@@ -13,7 +13,7 @@ from pathlib import Path
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("B200SPLAT_LIB", _HERE / "libb200splat.so"))
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_VIEWS = 8
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
@@ -95,6 +95,7 @@ class BatchBackwardArgs(C.Structure):
         ("dL_dmeans3D", C.c_void_p), ("dL_dshs", C.c_void_p), ("dL_dcolors", C.c_void_p),
         ("dL_dopacity", C.c_void_p), ("dL_dscales", C.c_void_p), ("dL_drotations", C.c_void_p),
         ("scratch", PP), ("accumulate", C.c_int32), ("scratch_clean", C.c_int32),
+        ("phase", C.c_int32), ("g_begin", C.c_int32), ("g_end", C.c_int32),
         ("stat_grad_accum", C.c_void_p), ("stat_denom", C.c_void_p), ("stat_max_radii", C.c_void_p),
         ("stream", C.c_void_p),
     ]
@@ -102,7 +103,8 @@ class BatchBackwardArgs(C.Structure):
 
 class P2PArgs(C.Structure):
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("bufs", C.c_void_p * 8), ("signals", C.c_void_p * 8),
-                ("n_sum", C.c_int64), ("n_max", C.c_int64), ("epoch", C.c_uint32), ("stream", C.c_void_p)]
+                ("n_segments", C.c_int32), ("seg_offset", C.c_int64 * 16), ("seg_count", C.c_int64 * 16),
+                ("seg_op", C.c_int32 * 16), ("epoch", C.c_uint32), ("stream", C.c_void_p)]
 
 
 P2P_HANDLE_BYTES, P2P_SIGNAL_BYTES = 64, 256

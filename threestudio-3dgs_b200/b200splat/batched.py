@@ -49,8 +49,10 @@ class PackedGrads:
             storage[:total + P].zero_()
         self.buffer = storage[:total] if storage is not None else torch.zeros(total, dtype=torch.float32, device=device)
         self.views: Dict[str, torch.Tensor] = {}
+        self.fields: List[tuple] = []   # (name, offset in floats, floats per Gaussian)
         off = 0
         for name, w in widths:
+            self.fields.append((name, off, w))
             self.views[name] = self.buffer[off:off + w * P].view(P, w) if w > 1 else self.buffer[off:off + P]
             off += w * P
         self.views["opacities"] = self.views["opacities"].view(P, 1)
@@ -63,6 +65,15 @@ class PackedGrads:
     @property
     def nbytes(self) -> int:
         return self.buffer.numel() * 4
+
+    def segments(self, g0: int = 0, g1: Optional[int] = None):
+        """(offset, count, op) float ranges of the exchange storage that hold Gaussians [g0, g1): one SUM range per
+        field of the packed buffer plus the MAX range of max_radii (which sits right behind the buffer when the
+        storage is shared).  op: 0 = sum, 1 = max."""
+        g1 = self.P if g1 is None else g1
+        segs = [(off + w * g0, w * (g1 - g0), 0) for _, off, w in self.fields]
+        segs.append((self.buffer.numel() + g0, g1 - g0, 1))
+        return segs
 
     def zero_stats_(self):
         self.views["grad_accum"].zero_()
@@ -142,7 +153,9 @@ def forward_batched(ws: BatchWorkspace, cams: Sequence[ops.Cam], means3D, shs, c
 
 def backward_batched(ws: BatchWorkspace, cams: Sequence[ops.Cam], means3D, shs, colors_precomp, opacities, scales,
                      rotations, pixel_grads, out: Dict[str, torch.Tensor], accumulate: bool = False,
-                     stats=None, means2D_out: Optional[Sequence[Optional[torch.Tensor]]] = None):
+                     stats=None, means2D_out: Optional[Sequence[Optional[torch.Tensor]]] = None,
+                     phase: int = 0, g_range: Optional[tuple] = None):
+    """phase 0: whole backward; 1: render backward only; 2: preprocess backward only, Gaussians g_range=(g0, g1)."""
     V = len(cams)
     M = 0 if shs is None else int(shs.shape[1])
     cam_arr = (_lib.Camera * V)(*[c.c_struct() for c in cams])
@@ -168,6 +181,9 @@ def backward_batched(ws: BatchWorkspace, cams: Sequence[ops.Cam], means3D, shs, 
     if stats is not None:
         a.stat_grad_accum, a.stat_denom, a.stat_max_radii = (ops._ptr(t) for t in stats)
     a.stream = ops._stream()
+    a.phase = int(phase)
+    if g_range is not None:
+        a.g_begin, a.g_end = int(g_range[0]), int(g_range[1])
     a.scratch_clean = 1   # ws.scratch is zero on entry; the library leaves it zero (it re-zeroes what it consumed)
     try:
         with torch.cuda.device(ws.device):
@@ -228,22 +244,67 @@ class BatchRenderer:
                              accumulate=ci > 0, stats=stats)
             i += n
 
-    def capture_step(self, cams, means3D, shs, colors_precomp, opacities, scales, rotations, pixel_grads):
+    def step_head(self, cams, means3D, shs, colors_precomp, opacities, scales, rotations, pixel_grads):
+        """First part of a step whose gradients are exchanged chunk by chunk (multi-GPU): forward + render
+        backward of the view batch.  ``step_tail`` finishes it.  One view chunk (<= MAX_VIEWS views) only."""
+        assert len(self.ws) == 1, "chunked exchange needs the step's views in one batch"
+        if not self.calibrated:
+            self.calibrate(cams, means3D, shs, colors_precomp, opacities, scales, rotations)
+        pk, ws = self.packed, self.ws[0]
+        pk.zero_stats_()
+        forward_batched(ws, cams, means3D, shs, colors_precomp, opacities, scales, rotations, sync=False)
+        pgs = [pg(ws.color[v], ws.depth[v], ws.alpha[v]) if callable(pg) else pg for v, pg in enumerate(pixel_grads)]
+        backward_batched(ws, cams, means3D, shs, colors_precomp, opacities, scales, rotations, pgs, pk.grads(),
+                         stats=(pk.views["grad_accum"], pk.views["denom"], pk.max_radii), phase=1)
+
+    def step_tail(self, cams, means3D, shs, colors_precomp, opacities, scales, rotations, exchange, chunks: int = 4):
+        """Preprocess backward in ``chunks`` Gaussian ranges; after each range ``exchange(g0, g1)`` runs on a side
+        stream (all-reduce of that range of the packed buffer across the ranks), so the exchange of range c is
+        under way while range c+1 is computed.  Returns with the side stream joined."""
+        pk, ws, P = self.packed, self.ws[0], self.P
+        main = torch.cuda.current_stream(self.device)
+        if not hasattr(self, "_side"):
+            # high priority: the exchange kernel's CTAs take SM slots as the running compute CTAs retire, instead of
+            # queueing behind the whole next preprocess-backward range (which fills every SM's registers)
+            self._side = torch.cuda.Stream(device=self.device, priority=-1)
+            self._events = [torch.cuda.Event() for _ in range(16)]
+        side = self._side
+        step = ((P + chunks - 1) // chunks + 127) // 128 * 128   # whole CTAs of the kernel, multiples of 4 Gaussians
+        none_pg = [None] * ws.V
+        for c, g0 in enumerate(range(0, P, step)):
+            g1 = min(P, g0 + step)
+            backward_batched(ws, cams, means3D, shs, colors_precomp, opacities, scales, rotations, none_pg,
+                             pk.grads(), stats=(pk.views["grad_accum"], pk.views["denom"], pk.max_radii),
+                             phase=2, g_range=(g0, g1))
+            ev = self._events[c % len(self._events)]
+            ev.record(main)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                exchange(g0, g1)
+        main.wait_stream(side)
+
+    def capture_step(self, cams, means3D, shs, colors_precomp, opacities, scales, rotations, pixel_grads,
+                     head_only: bool = False):
         """Record one step (every launch of the view batch's forward + backward) into a CUDA graph and return it;
         ``graph.replay()`` then re-runs the step on the same buffers without per-launch host work.  The inputs
         must keep their addresses (parameters updated in place, cameras / pixel gradients written into the same
-        tensors); pixel_grads must be tensors, not callables."""
+        tensors); pixel_grads must be tensors, not callables.  head_only: record ``step_head`` (the part before
+        the chunked preprocess backward / exchange of a multi-GPU step)."""
         assert self.calibrated, "calibrate() first: the binning capacity is baked into the graph"
         assert not any(callable(pg) for pg in pixel_grads)
         args = (cams, means3D, shs, colors_precomp, opacities, scales, rotations, pixel_grads)
+        fn = self.step_head if head_only else self.step
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
-            self.step(*args)   # eager once on the side stream: one-time attribute / allocation work happens here
+            fn(*args)   # eager once on the side stream: one-time attribute / allocation work happens here
+            if head_only:   # leave the scratch clean (the eager head's records are consumed by a full tail)
+                backward_batched(self.ws[0], cams, means3D, shs, colors_precomp, opacities, scales, rotations,
+                                 [None] * self.ws[0].V, self.packed.grads(), phase=2)
         torch.cuda.current_stream(self.device).wait_stream(side)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            self.step(*args)
+            fn(*args)
         return graph
 
     def overflowed(self) -> bool:

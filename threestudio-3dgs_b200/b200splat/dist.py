@@ -26,6 +26,15 @@ def allreduce_packed(buffer: torch.Tensor, max_radii: torch.Tensor, group=None):
     dist.all_reduce(max_radii, op=dist.ReduceOp.MAX, group=group)
 
 
+def allreduce_packed_range(packed, g0: int, g1: int, group=None):
+    """NCCL/gloo version of the chunked exchange: the fields of the packed buffer and max_radii, Gaussians [g0, g1)."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    for name, off, w in packed.fields:
+        dist.all_reduce(packed.buffer[off + w * g0:off + w * g1], op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(packed.max_radii[g0:g1], op=dist.ReduceOp.MAX, group=group)
+
+
 class _RawCudaArray:
     """Zero-copy view of raw device memory for torch.as_tensor (CUDA array interface)."""
 
@@ -90,12 +99,20 @@ class P2PAllReduce:
         self.buffer = torch.as_tensor(_RawCudaArray(self._own[0], n_sum + n_max, "<f4"), device=self.device)
         dist.barrier(group=group)   # every rank has mapped every peer before the first exchange
 
-    def __call__(self):
-        """Stream-ordered on the current stream: on return of the kernel the buffer holds the reduced values."""
+    def __call__(self, segments=None):
+        """Stream-ordered on the current stream: when the kernel completes the listed (offset, count, op) float
+        ranges of the buffer (default: the whole SUM part and the MAX tail) hold the reduced values.  All ranks must
+        make the same sequence of calls."""
         C, _lib = self._C, self._lib
+        if segments is None:
+            segments = [(0, self.n_sum, 0)] + ([(self.n_sum, self.n_max, 1)] if self.n_max else [])
+        segments = [sg for sg in segments if sg[1] > 0]
+        assert 1 <= len(segments) <= 16
         self.epoch += 1
         a = _lib.P2PArgs()
-        a.rank, a.world, a.n_sum, a.n_max, a.epoch = self.rank, self.world, self.n_sum, self.n_max, self.epoch
+        a.rank, a.world, a.epoch, a.n_segments = self.rank, self.world, self.epoch, len(segments)
+        for i, (off, cnt, op) in enumerate(segments):
+            a.seg_offset[i], a.seg_count[i], a.seg_op[i] = int(off), int(cnt), int(op)
         for k in range(self.world):
             a.bufs[k], a.signals[k] = self._bufs[k], self._sigs[k]
         a.stream = torch.cuda.current_stream(self.device).cuda_stream

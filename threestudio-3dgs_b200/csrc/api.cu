@@ -335,12 +335,22 @@ int b200splat_p2p_allreduce(const b200splat_p2p_args* a) {
     if (!a) return fail(B200SPLAT_ERR_INVALID, "null args");
     if (a->world < 1 || a->world > P2P_MAX_RANKS || a->rank < 0 || a->rank >= a->world)
         return fail(B200SPLAT_ERR_INVALID, "rank %d / world %d out of range (max %d)", a->rank, a->world, P2P_MAX_RANKS);
-    if (a->n_sum < 0 || a->n_max < 0 || (a->n_sum & 3) || (a->n_max & 3))
-        return fail(B200SPLAT_ERR_INVALID, "n_sum and n_max must be non-negative multiples of 4");
+    if (a->n_segments < 1 || a->n_segments > P2P_MAX_SEG)
+        return fail(B200SPLAT_ERR_INVALID, "n_segments must be in [1, %d]", P2P_MAX_SEG);
     static_assert(P2P_SIGNAL_WORDS * 4 == B200SPLAT_P2P_SIGNAL_BYTES, "signal area size");
+    static_assert(P2P_MAX_SEG == B200SPLAT_P2P_MAX_SEGMENTS, "segment count");
     P2PTab t;
     t.rank = a->rank, t.world = a->world, t.epoch = a->epoch;
-    t.n_sum4 = a->n_sum / 4, t.n_max4 = a->n_max / 4;
+    t.n_seg = a->n_segments, t.seg_max_mask = 0u;
+    for (int i = 0; i < P2P_MAX_SEG; ++i) t.seg_first4[i] = t.seg_n4[i] = 0;
+    for (int i = 0; i < a->n_segments; ++i) {
+        if (a->seg_offset[i] < 0 || a->seg_count[i] < 0 || (a->seg_offset[i] & 3) || (a->seg_count[i] & 3))
+            return fail(B200SPLAT_ERR_INVALID, "segment %d: offset and count must be non-negative multiples of 4", i);
+        if (a->seg_op[i] != B200SPLAT_P2P_SUM && a->seg_op[i] != B200SPLAT_P2P_MAX)
+            return fail(B200SPLAT_ERR_INVALID, "segment %d: unknown op %d", i, a->seg_op[i]);
+        t.seg_first4[i] = a->seg_offset[i] / 4, t.seg_n4[i] = a->seg_count[i] / 4;
+        if (a->seg_op[i] == B200SPLAT_P2P_MAX) t.seg_max_mask |= 1u << i;
+    }
     for (int k = 0; k < P2P_MAX_RANKS; ++k) {
         t.bufs[k] = k < a->world ? reinterpret_cast<float*>(a->bufs[k]) : nullptr;
         t.signals[k] = k < a->world ? reinterpret_cast<uint32_t*>(a->signals[k]) : nullptr;
@@ -513,22 +523,25 @@ static int backward_run(BatchTab& tab, const float* means3D, const float* scales
                         const float* shs, const float* cov3D_precomp, float* dL_dmeans3D, float* dL_dshs,
                         float* dL_dcolors, float* dL_dopacity, float* dL_dscales, float* dL_drotations,
                         float* dL_dcov3D, float* sa, float* sd, float* sm, int accumulate, int debug, bool any_pairs,
-                        cudaStream_t st, bool scratch_clean = false) {
+                        cudaStream_t st, bool scratch_clean = false, int phase = 0, int g_begin = 0, int g_end = 0) {
     b200splat_camera dbg{};
     dbg.debug = debug;
     const int sel = sorted_sel_for(tab.grid_x * tab.grid_y);
-    {
+    tab.clean_scratch = scratch_clean ? 1 : 0;
+    if (phase != 2) {
         ProfScope ps(6, st);
-        tab.clean_scratch = scratch_clean ? 1 : 0;
         if (!scratch_clean)
             for (int v = 0; v < tab.V; ++v)
                 CU(cudaMemsetAsync(tab.v[v].grad2d, 0, (size_t)tab.P * GRAD2D_FLOATS * sizeof(float), st));
         if (any_pairs) CU(launch_render_backward(tab, sel, st));
     }
     DEBUG_SYNC(dbg, st, "render backward");
-    { ProfScope ps(7, st);
-    CU(launch_preprocess_backward(tab, means3D, scales, rotations, shs, cov3D_precomp, dL_dmeans3D, dL_dshs, dL_dcolors,
-                                  dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D, sa, sd, sm, accumulate, st)); }
+    if (phase != 1) {
+        ProfScope ps(7, st);
+        CU(launch_preprocess_backward(tab, means3D, scales, rotations, shs, cov3D_precomp, dL_dmeans3D, dL_dshs,
+                                      dL_dcolors, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D, sa, sd, sm,
+                                      accumulate, st, g_begin, g_end));
+    }
     DEBUG_SYNC(dbg, st, "preprocess backward");
     return B200SPLAT_OK;
 }
@@ -605,7 +618,8 @@ int b200splat_backward_batched(const b200splat_batch_backward_args* a) {
     }
     return backward_run(tab, a->means3D, a->scales, a->rotations, a->shs, nullptr, a->dL_dmeans3D, a->dL_dshs,
                         a->dL_dcolors, a->dL_dopacity, a->dL_dscales, a->dL_drotations, nullptr, a->stat_grad_accum,
-                        a->stat_denom, a->stat_max_radii, a->accumulate, a->cams[0].debug, true, st, a->scratch_clean != 0);
+                        a->stat_denom, a->stat_max_radii, a->accumulate, a->cams[0].debug, true, st, a->scratch_clean != 0,
+                        a->phase, a->g_begin, a->g_end);
 }
 
 int b200splat_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,

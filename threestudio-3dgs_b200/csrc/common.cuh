@@ -174,7 +174,7 @@ cudaError_t launch_preprocess_backward(const BatchTab& tab, const float* means3D
                                        float* dL_dmeans3D, float* dL_dshs, float* dL_dcolors, float* dL_dopacity,
                                        float* dL_dscales, float* dL_drotations, float* dL_dcov3D,
                                        float* stat_grad_accum, float* stat_denom, float* stat_max_radii,
-                                       int accumulate, cudaStream_t st);
+                                       int accumulate, cudaStream_t st, int g_begin = 0, int g_end = 0);
 
 size_t dist2_workspace_bytes(int P);
 cudaError_t launch_dist2(int P, const float* points, float* out, void* ws, cudaStream_t st);
@@ -183,13 +183,16 @@ void count_launch(int n = 1);
 
 // ---- all-reduce over NVLink peer memory (p2p.cu) -------------------------------------------------
 constexpr int P2P_MAX_RANKS = 8;
+constexpr int P2P_MAX_SEG = 16;
 constexpr int P2P_ERROR_WORD = 2 * P2P_MAX_RANKS;       // signal row layout: [ready x 8][done x 8][error][counter]
 constexpr int P2P_COUNTER_WORD = 2 * P2P_MAX_RANKS + 1;
 constexpr int P2P_SIGNAL_WORDS = 64;
 struct P2PTab {
     int rank, world;
     uint32_t epoch;
-    int64_t n_sum4, n_max4;            // float4 counts: [0, n_sum4) summed, [n_sum4, n_sum4 + n_max4) max-reduced
+    int n_seg;                         // disjoint float4 ranges reduced by this call
+    int64_t seg_first4[P2P_MAX_SEG], seg_n4[P2P_MAX_SEG];
+    uint32_t seg_max_mask;             // bit i: segment i is max-reduced (else summed)
     float* bufs[P2P_MAX_RANKS];        // every rank's buffer (own + IPC-mapped peers)
     uint32_t* signals[P2P_MAX_RANKS];  // every rank's signal words
 };

@@ -164,14 +164,17 @@ p2p_allreduce_kernel(const __grid_constant__ P2PTab t, int mode) {
     if (!wait_row(t, 0, tid)) s_flag = 0;
     __syncthreads();
     if (s_flag) {
-        const bool wide = mode == 0 && ((t.n_sum4 | t.n_max4) & 1) == 0 &&
-                          (reinterpret_cast<uintptr_t>(t.bufs[t.rank]) & 31) == 0;
-        if (wide) {
-            reduce_slice8<false, (U > 2 ? U / 2 : 1)>(t, 0, t.n_sum4 / 2);
-            reduce_slice8<true, (U > 2 ? U / 2 : 1)>(t, t.n_sum4 / 2, t.n_max4 / 2);
-        } else {
-            reduce_slice<false, U>(t, 0, t.n_sum4, mode);
-            reduce_slice<true, U>(t, t.n_sum4, t.n_max4, mode);
+        const bool aligned32 = (reinterpret_cast<uintptr_t>(t.bufs[t.rank]) & 31) == 0;
+        for (int sgm = 0; sgm < t.n_seg; ++sgm) {
+            const int64_t f4 = t.seg_first4[sgm], n4 = t.seg_n4[sgm];
+            const bool is_max = (t.seg_max_mask >> sgm) & 1u;
+            if (mode == 0 && aligned32 && ((f4 | n4) & 1) == 0) {
+                if (is_max) reduce_slice8<true, (U > 2 ? U / 2 : 1)>(t, f4 / 2, n4 / 2);
+                else reduce_slice8<false, (U > 2 ? U / 2 : 1)>(t, f4 / 2, n4 / 2);
+            } else {
+                if (is_max) reduce_slice<true, U>(t, f4, n4, mode);
+                else reduce_slice<false, U>(t, f4, n4, mode);
+            }
         }
     }
     // phase 1.  One system fence per CTA, by the thread that then counts the CTA as finished (the barrier makes
@@ -196,7 +199,7 @@ p2p_allreduce_kernel(const __grid_constant__ P2PTab t, int mode) {
 }
 
 cudaError_t launch_p2p_allreduce(const P2PTab& t, cudaStream_t st) {
-    static const int blocks = getenv("B200SPLAT_P2P_BLOCKS") ? atoi(getenv("B200SPLAT_P2P_BLOCKS")) : NUM_SMS * 4;
+    static const int blocks = getenv("B200SPLAT_P2P_BLOCKS") ? atoi(getenv("B200SPLAT_P2P_BLOCKS")) : NUM_SMS * 2;   // 2 per SM: same time as 4 or 8 (NVLink-bound), leaves room for the compute it overlaps
     static const int unroll = getenv("B200SPLAT_P2P_UNROLL") ? atoi(getenv("B200SPLAT_P2P_UNROLL")) : 4;
     static const int mode = getenv("B200SPLAT_P2P_MODE") ? atoi(getenv("B200SPLAT_P2P_MODE")) : 0;   // 1/2: timing experiments
     if (unroll == 8) p2p_allreduce_kernel<8><<<blocks, 256, 0, st>>>(t, mode);

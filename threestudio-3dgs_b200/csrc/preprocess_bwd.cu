@@ -165,7 +165,8 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
                            float* __restrict__ dL_dcolors, float* __restrict__ dL_dopacity,
                            float* __restrict__ dL_dscales, float* __restrict__ dL_drotations,
                            float* __restrict__ dL_dcov3D, float* __restrict__ stat_grad_accum,
-                           float* __restrict__ stat_denom, float* __restrict__ stat_max_radii) {
+                           float* __restrict__ stat_denom, float* __restrict__ stat_max_radii, int g_begin,
+                           int g_end) {
     __shared__ float sV[MAX_VIEWS][16], sP[MAX_VIEWS][16], sC[MAX_VIEWS][4];
     // dynamic shared memory: one 48-byte slot per (view, thread) -- first the landing zone of the view's gradient
     // record (cp.async), then the SH phase's per-view state -- and, on the vector path, the thread's SH row
@@ -180,8 +181,8 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
     }
     for (int i = threadIdx.x; i < V * 3; i += blockDim.x) sC[i / 3][i % 3] = tab.v[i / 3].campos[i % 3];
     __syncthreads();
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= tab.P) return;
+    const int idx = g_begin + blockIdx.x * blockDim.x + threadIdx.x;   // this launch covers [g_begin, g_end)
+    if (idx >= g_end) return;
     const int M = tab.M;
     constexpr int K = DEG < 0 ? 0 : (DEG + 1) * (DEG + 1);
     constexpr int NCH = (K + 3) / 4;          // live chunks of 4 coefficients
@@ -487,9 +488,12 @@ cudaError_t launch_preprocess_backward(const BatchTab& tab, const float* means3D
                                        float* dL_dmeans3D, float* dL_dshs, float* dL_dcolors, float* dL_dopacity,
                                        float* dL_dscales, float* dL_drotations, float* dL_dcov3D,
                                        float* stat_grad_accum, float* stat_denom, float* stat_max_radii,
-                                       int accumulate, cudaStream_t st) {
+                                       int accumulate, cudaStream_t st, int g_begin, int g_end) {
     if (tab.P <= 0) return cudaSuccess;
-    const int grid = (tab.P + 127) / 128;
+    if (g_end <= 0 || g_end > tab.P) g_end = tab.P;
+    if (g_begin < 0) g_begin = 0;
+    if (g_begin >= g_end) return cudaSuccess;
+    const int grid = (g_end - g_begin + 127) / 128;
     const bool vec = tab.sh_degree >= 0 && (tab.M & 3) == 0 && tab.M <= 16 &&
                      ((reinterpret_cast<uintptr_t>(shs) | reinterpret_cast<uintptr_t>(dL_dshs)) & 15) == 0;
     const size_t smem = ((size_t)tab.V * 128 * 3 + (vec ? 128 * SH_ROW_F4 : 0)) * sizeof(float4);
@@ -504,7 +508,7 @@ cudaError_t launch_preprocess_backward(const BatchTab& tab, const float* means3D
         }                                                                                                          \
         kfn<<<grid, 128, smem, st>>>(tab, means3D, scales, rotations, shs, cov3D_precomp, dL_dmeans3D, dL_dshs,     \
                                      dL_dcolors, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D,                \
-                                     stat_grad_accum, stat_denom, stat_max_radii);                                 \
+                                     stat_grad_accum, stat_denom, stat_max_radii, g_begin, g_end);                 \
     }
 #define DISPATCH_DEG(A, VC)                                                                                        \
     switch (tab.sh_degree) {                                                                                       \
