@@ -129,10 +129,12 @@ def test_forward_backward_parity(P, deg, H, W, seed):
     _check_grads(cu, orc)
 
 
-def test_intermediates_bit_exact():
+@pytest.mark.parametrize("P,H,W", [(16384, 128, 128),     # 64 tiles: one wide partition pass (tile id <= 10 bits)
+                                    (6000, 528, 528)])      # 1089 tiles: two 8-bit passes of the generic kernel
+def test_intermediates_bit_exact(P, H, W):
     """tiles_touched, point_offsets, depth bits, sorted keys, point list and tile ranges."""
     from b200splat import ops
-    sc, cam = _scene(16384, 0, 128, 128, 1235)
+    sc, cam = _scene(P, 0, H, W, 1235)
     s = oracle_settings(cam, 0)
     orc = _run_oracle(sc, s)
     camc = ops.make_cam(cuda_settings(s), "cuda")
@@ -495,8 +497,8 @@ def test_full_size_properties_headline_workload():
 
 
 def test_stress_shape_pair_mode_and_large_tile_count():
-    """Pair-sort fallback (index does not fit beside the key): 600K Gaussians at 1024x1024 (T = 4096, 45 key bits)
-    -- the stress config's tile count -- batched == per-view, sortedness."""
+    """600K Gaussians at 1024x1024 (T = 4096 tiles, the stress config's tile count: the pair words go through two
+    8-bit passes of the generic onesweep kernel instead of the single wide partition): batched == per-view, sortedness."""
     from b200splat import batched, ops
     P, H, W = 600_000, 1024, 1024
     sc = scenes.make_scene(P, 0, 0.5, seed=5)
