@@ -229,8 +229,13 @@ render_forward_kernel(const __grid_constant__ BatchTab tab, int sel) {
         // warp's private index list
         uint8_t* __restrict__ surv = s_surv[warp];
         int nsurv = 0;
+        // a warp whose 32 pixels have all stopped only helps staging from here on: no cull, no evaluation (the tile
+        // runs until its LAST pixel stops -- a silhouette pixel walks the whole list -- so most warps are in this state
+        // for most batches)
+        const bool warp_done = __all_sync(0xffffffffu, done);
 #pragma unroll
         for (int c = 0; c < FWD_BATCH / 32; ++c) {
+            if (warp_done) break;
             const int e = c * 32 + lane;
             bool keep = false;
             if (e < count) {
