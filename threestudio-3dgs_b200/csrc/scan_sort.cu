@@ -67,9 +67,29 @@ scan_lookback_kernel(int64_t n, const __grid_constant__ ScanTab tab) {
     const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
     uint32_t v[SCAN_ITEMS];
     const uint64_t* __restrict__ perm = tab.perm[view];
+    // gathered input: coalesced (striped) loads of the order words, dependent gathers, then a transpose through
+    // shared memory to the blocked arrangement the scan wants (index + index/32: conflict-free both ways).  The
+    // blocked loads (each lane 128 bytes apart) throttled the load/store unit: 32 requests per instruction.
+    __shared__ uint32_t s_x[SCAN_TILE + SCAN_TILE / 32];
+    const int64_t tile_base = (int64_t)tile * SCAN_TILE;
     if (perm != nullptr) {
+        uint32_t g[SCAN_ITEMS];
 #pragma unroll
-        for (int i = 0; i < SCAN_ITEMS; ++i) v[i] = (base + i < n) ? __ldg(in + (uint32_t)__ldg(perm + base + i)) : 0u;
+        for (int i = 0; i < SCAN_ITEMS; ++i) {
+            const int64_t e = tile_base + i * SCAN_THREADS + threadIdx.x;
+            g[i] = e < n ? (uint32_t)__ldg(perm + e) : 0xffffffffu;
+        }
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) {
+            const int idx = i * SCAN_THREADS + threadIdx.x;
+            s_x[idx + (idx >> 5)] = g[i] != 0xffffffffu ? __ldg(in + g[i]) : 0u;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) {
+            const int idx = threadIdx.x * SCAN_ITEMS + i;
+            v[i] = s_x[idx + (idx >> 5)];
+        }
     } else if (base + SCAN_ITEMS <= n) {
         const uint4* p = reinterpret_cast<const uint4*>(in + base);
 #pragma unroll
@@ -137,7 +157,19 @@ scan_lookback_kernel(int64_t n, const __grid_constant__ ScanTab tab) {
     }
     __syncthreads();
     const uint32_t off = s_excl + warp_off + (inc - tsum);
-    if (base + SCAN_ITEMS <= n) {
+    if (perm != nullptr) {   // back through shared memory: coalesced stores
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) {
+            const int idx = threadIdx.x * SCAN_ITEMS + i;
+            s_x[idx + (idx >> 5)] = v[i] + off;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) {
+            const int idx = i * SCAN_THREADS + threadIdx.x;
+            if (tile_base + idx < n) out[tile_base + idx] = s_x[idx + (idx >> 5)];
+        }
+    } else if (base + SCAN_ITEMS <= n) {
         uint4* p = reinterpret_cast<uint4*>(out + base);
 #pragma unroll
         for (int i = 0; i < SCAN_ITEMS / 4; ++i)
