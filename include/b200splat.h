@@ -27,12 +27,14 @@
 extern "C" {
 #endif
 
-#define B200SPLAT_ABI_VERSION 4
+#define B200SPLAT_ABI_VERSION 5
 
 #define B200SPLAT_OK 0
 #define B200SPLAT_ERR_INVALID -1   /* bad argument                                  */
 #define B200SPLAT_ERR_CUDA -2      /* a CUDA runtime call or kernel launch failed   */
 #define B200SPLAT_ERR_NOMEM -3     /* a caller-provided buffer is too small         */
+
+#define B200SPLAT_MAX_EXTRA 4      /* extra feature channels one raster pass can carry */
 
 typedef void* b200splat_stream; /* cudaStream_t */
 
@@ -61,7 +63,7 @@ typedef struct b200splat_camera {
 size_t b200splat_geom_bytes(int32_t P);                  /* per-Gaussian state kept for backward */
 size_t b200splat_image_bytes(int32_t H, int32_t W);      /* tile ranges + n_contrib + final T    */
 size_t b200splat_binning_bytes(int64_t num_rendered);    /* key/value ping-pong + sort scratch   */
-size_t b200splat_backward_scratch_bytes(int32_t P);      /* packed 2-D stage gradients           */
+size_t b200splat_backward_scratch_bytes(int32_t P);      /* packed 2-D stage gradients (+ extra channels) */
 
 /* ---- forward: replaces rasterize_gaussians (RasterizeGaussiansCUDA) ------------------------
  * Inputs (device): means3D (P,3); shs (P,M,3) or NULL; colors_precomp (P,3) or NULL; opacities
@@ -98,6 +100,13 @@ typedef struct b200splat_forward_args {
     b200splat_stream stream;
     int64_t* num_rendered_out;
     void** binning_out;
+    /* Optional extra feature channels rendered by the same pass (new, non-breaking): extra_features (P,n_extra)
+     * fp32, n_extra in 0..B200SPLAT_MAX_EXTRA; out_extra (n_extra,H,W) = sum_i e_i alpha_i T_i (no background
+     * term).  Replaces the reference's second rasterizer call with the per-Gaussian normals as colours
+     * (renderer/diff_gaussian_rasterizer_shading.py:177-187, ..._normal.py:175-185): same alphas, one pass. */
+    const float* extra_features;
+    int32_t n_extra;
+    float* out_extra;
 } b200splat_forward_args;
 
 int b200splat_forward(const b200splat_forward_args* args);
@@ -151,6 +160,13 @@ typedef struct b200splat_backward_args {
     float* stat_denom;
     float* stat_max_radii;
     b200splat_stream stream;
+    /* extra feature channels of the forward (same extra_features / n_extra): dL_dout_extra (n_extra,H,W) or NULL,
+     * dL_dextra (P,n_extra) written (added when accumulate != 0); the geometry gradients include the extra
+     * channels' contribution through alpha */
+    const float* extra_features;
+    int32_t n_extra;
+    const float* dL_dout_extra;
+    float* dL_dextra;
 } b200splat_backward_args;
 
 int b200splat_backward(const b200splat_backward_args* args);
@@ -191,6 +207,9 @@ typedef struct b200splat_batch_forward_args {
     int32_t sync;                 /* != 0: synchronise the stream and fill the two host arrays below */
     int64_t* num_rendered_out;    /* V */
     int32_t* overflow_out;        /* V */
+    const float* extra_features;  /* (P,n_extra) or NULL: see b200splat_forward_args */
+    int32_t n_extra;
+    float* const* out_extra;      /* V x (n_extra,H,W) */
 } b200splat_batch_forward_args;
 
 int b200splat_forward_batched(const b200splat_batch_forward_args* args);
@@ -239,6 +258,10 @@ typedef struct b200splat_batch_backward_args {
     float* stat_denom;
     float* stat_max_radii;
     b200splat_stream stream;
+    const float* extra_features;          /* see b200splat_backward_args */
+    int32_t n_extra;
+    const float* const* dL_dout_extra;    /* NULL or V entries, any may be NULL */
+    float* dL_dextra;                     /* (P,n_extra), summed over the views */
 } b200splat_batch_backward_args;
 
 int b200splat_backward_batched(const b200splat_batch_backward_args* args);

@@ -13,7 +13,7 @@ from pathlib import Path
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("B200SPLAT_LIB", _HERE / "libb200splat.so"))
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_VIEWS = 8
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
@@ -41,6 +41,7 @@ class ForwardArgs(C.Structure):
         ("binning_alloc", ALLOC_FN), ("alloc_user", C.c_void_p),
         ("stream", C.c_void_p),
         ("num_rendered_out", C.POINTER(C.c_int64)), ("binning_out", C.POINTER(C.c_void_p)),
+        ("extra_features", C.c_void_p), ("n_extra", C.c_int32), ("out_extra", C.c_void_p),
     ]
 
 
@@ -59,6 +60,8 @@ class BackwardArgs(C.Structure):
         ("accumulate", C.c_int32),
         ("stat_grad_accum", C.c_void_p), ("stat_denom", C.c_void_p), ("stat_max_radii", C.c_void_p),
         ("stream", C.c_void_p),
+        ("extra_features", C.c_void_p), ("n_extra", C.c_int32), ("dL_dout_extra", C.c_void_p),
+        ("dL_dextra", C.c_void_p),
     ]
 
 
@@ -81,6 +84,7 @@ class BatchForwardArgs(C.Structure):
         ("geom_buffer", PP), ("image_buffer", PP), ("binning_buffer", PP), ("binning_bytes", C.c_size_t),
         ("stream", C.c_void_p), ("sync", C.c_int32),
         ("num_rendered_out", C.POINTER(C.c_int64)), ("overflow_out", C.POINTER(C.c_int32)),
+        ("extra_features", C.c_void_p), ("n_extra", C.c_int32), ("out_extra", PP),
     ]
 
 
@@ -98,6 +102,7 @@ class BatchBackwardArgs(C.Structure):
         ("phase", C.c_int32), ("g_begin", C.c_int32), ("g_end", C.c_int32),
         ("stat_grad_accum", C.c_void_p), ("stat_denom", C.c_void_p), ("stat_max_radii", C.c_void_p),
         ("stream", C.c_void_p),
+        ("extra_features", C.c_void_p), ("n_extra", C.c_int32), ("dL_dout_extra", PP), ("dL_dextra", C.c_void_p),
     ]
 
 

@@ -124,8 +124,9 @@ class BatchWorkspace:
 
 
 def forward_batched(ws: BatchWorkspace, cams: Sequence[ops.Cam], means3D, shs, colors_precomp, opacities, scales,
-                    rotations, sync: bool = False):
-    """One launch set for all views.  With sync=True returns (num_rendered list, overflow list)."""
+                    rotations, sync: bool = False, extra_features=None, extra_out=None):
+    """One launch set for all views.  With sync=True returns (num_rendered list, overflow list).
+    extra_features (P,C') + extra_out (list of V (C',H,W) tensors): extra channels blended by the same pass."""
     V = len(cams)
     assert V == ws.V
     M = 0 if shs is None else int(shs.shape[1])
@@ -143,6 +144,10 @@ def forward_batched(ws: BatchWorkspace, cams: Sequence[ops.Cam], means3D, shs, c
     nr = (C.c_int64 * V)()
     ov = (C.c_int32 * V)()
     a.num_rendered_out, a.overflow_out = nr, ov
+    n_extra = ops._check_extra(extra_features, ws.P)
+    if n_extra:
+        eo = _parr([t.data_ptr() for t in extra_out])
+        a.extra_features, a.n_extra, a.out_extra = extra_features.data_ptr(), n_extra, eo
     with torch.cuda.device(ws.device):
         check(lib.b200splat_forward_batched(C.byref(a)), "b200splat_forward_batched")
     if sync:
@@ -154,8 +159,10 @@ def forward_batched(ws: BatchWorkspace, cams: Sequence[ops.Cam], means3D, shs, c
 def backward_batched(ws: BatchWorkspace, cams: Sequence[ops.Cam], means3D, shs, colors_precomp, opacities, scales,
                      rotations, pixel_grads, out: Dict[str, torch.Tensor], accumulate: bool = False,
                      stats=None, means2D_out: Optional[Sequence[Optional[torch.Tensor]]] = None,
-                     phase: int = 0, g_range: Optional[tuple] = None):
-    """phase 0: whole backward; 1: render backward only; 2: preprocess backward only, Gaussians g_range=(g0, g1)."""
+                     phase: int = 0, g_range: Optional[tuple] = None, extra_features=None, extra_grads=None):
+    """phase 0: whole backward; 1: render backward only; 2: preprocess backward only, Gaussians g_range=(g0, g1).
+    extra_features (P,C') + extra_grads (list of V (C',H,W) tensors or None): out["extra_features"] receives
+    dL/dextra_features summed over the views."""
     V = len(cams)
     M = 0 if shs is None else int(shs.shape[1])
     cam_arr = (_lib.Camera * V)(*[c.c_struct() for c in cams])
@@ -184,6 +191,11 @@ def backward_batched(ws: BatchWorkspace, cams: Sequence[ops.Cam], means3D, shs, 
     a.phase = int(phase)
     if g_range is not None:
         a.g_begin, a.g_end = int(g_range[0]), int(g_range[1])
+    n_extra = ops._check_extra(extra_features, ws.P)
+    if n_extra:
+        eg = _parr([ops._ptr(t) for t in (extra_grads or [None] * V)])
+        a.extra_features, a.n_extra = extra_features.data_ptr(), n_extra
+        a.dL_dout_extra, a.dL_dextra = eg, out["extra_features"].data_ptr()
     a.scratch_clean = 1   # ws.scratch is zero on entry; the library leaves it zero (it re-zeroes what it consumed)
     try:
         with torch.cuda.device(ws.device):
@@ -349,7 +361,8 @@ def render_views_fwd_bwd(cams: Sequence[ops.Cam], means3D, shs, colors_precomp, 
 # ------------------------------------------------------------------------------------------------------
 class _RasterizeViews(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, owner, cams, means3D, means2D, shs, colors_precomp, opacities, scales, rotations):
+    def forward(ctx, owner, cams, means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
+                extra_features=None):
         ws = owner.ws
         V, P, H, W = ws.V, ws.P, ws.H, ws.W
         dev = means3D.device
@@ -364,27 +377,33 @@ class _RasterizeViews(torch.autograd.Function):
         radii = torch.empty(V, P, dtype=torch.int32, device=dev)
         ws.color, ws.depth, ws.alpha = list(color.unbind(0)), list(depth.unbind(0)), list(alpha.unbind(0))
         ws.radii = list(radii.unbind(0))
+        n_extra = ops._check_extra(extra_features, P)
+        ex_ = f(extra_features, "extra_features") if n_extra else None
+        extra = torch.empty(V, n_extra, H, W, dtype=torch.float32, device=dev)
+        ekw = dict(extra_features=ex_, extra_out=list(extra.unbind(0))) if n_extra else {}
         if not owner.calibrated:
-            owner.calibrate(cams, m3, sh_, cp_, op_, sc_, ro_)
+            owner.calibrate(cams, m3, sh_, cp_, op_, sc_, ro_, **ekw)
         else:
-            forward_batched(ws, cams, m3, sh_, cp_, op_, sc_, ro_, sync=False)
+            forward_batched(ws, cams, m3, sh_, cp_, op_, sc_, ro_, sync=False, **ekw)
         owner.generation += 1
         ctx.owner, ctx.cams, ctx.generation = owner, cams, owner.generation
         ctx.has = (sh_ is not None, cp_ is not None)
         e = lambda t: t if t is not None else torch.empty(0, device=dev)
-        ctx.save_for_backward(m3, e(sh_), e(cp_), op_, sc_, ro_)
+        ctx.n_extra = n_extra
+        ctx.save_for_backward(m3, e(sh_), e(cp_), op_, sc_, ro_, e(ex_))
         ctx.mark_non_differentiable(radii)
-        return color, radii, depth, alpha
+        return color, radii, depth, alpha, extra
 
     @staticmethod
-    def backward(ctx, g_color, g_radii, g_depth, g_alpha):
+    def backward(ctx, g_color, g_radii, g_depth, g_alpha, g_extra):
         owner = ctx.owner
         if ctx.generation != owner.generation:
             raise RuntimeError("ViewBatchRasterizer: the workspace was reused by a later forward before this "
                                "backward ran; use one ViewBatchRasterizer per live graph")
         ws = owner.ws
-        m3, sh_, cp_, op_, sc_, ro_ = ctx.saved_tensors
+        m3, sh_, cp_, op_, sc_, ro_, ex_ = ctx.saved_tensors
         has_sh, has_cp = ctx.has
+        n_extra = ctx.n_extra
         sh_ = sh_ if has_sh else None
         cp_ = cp_ if has_cp else None
         V, P = ws.V, ws.P
@@ -400,16 +419,21 @@ class _RasterizeViews(torch.autograd.Function):
         gc, gd, ga = g(g_color), g(g_depth), g(g_alpha)
         pgs = [(None if gc is None else gc[v], None if gd is None else gd[v], None if ga is None else ga[v])
                for v in range(V)]
+        ekw = {}
+        if n_extra:
+            out["extra_features"] = new(P, n_extra)
+            ge = g(g_extra)
+            ekw = dict(extra_features=ex_, extra_grads=None if ge is None else list(ge.unbind(0)))
         backward_batched(ws, ctx.cams, m3, sh_, cp_, op_, sc_, ro_, pgs, out, accumulate=False,
-                         means2D_out=list(m2.unbind(0)))
+                         means2D_out=list(m2.unbind(0)), **ekw)
         return (None, None, out["means3D"], m2, out.get("shs"), out.get("colors_precomp"), out["opacities"],
-                out["scales"], out["rotations"])
+                out["scales"], out["rotations"], out.get("extra_features"))
 
 
 class ViewBatchRasterizer(torch.nn.Module):
     """Batched counterpart of ``GaussianRasterizer``: ``forward(raster_settings_list, means3D, means2D (V,P,3),
     opacities, shs=None, colors_precomp=None, scales=, rotations=)`` -> ``(color (V,3,H,W), radii (V,P) int32,
-    depth (V,1,H,W), alpha (V,1,H,W))`` with autograd; ``means2D.grad[v]`` is view v's NDC gradient, exactly what
+    depth (V,1,H,W), alpha (V,1,H,W))`` (+ ``extra (V,C',H,W)`` when ``extra_features (P,C')`` is given) with autograd; ``means2D.grad[v]`` is view v's NDC gradient, exactly what
     the per-view call would have produced (geometry/gaussian_base.py:815-819 reads it per view).  Holds the
     persistent device workspace of the batch; one instance per concurrently live autograd graph."""
 
@@ -420,10 +444,12 @@ class ViewBatchRasterizer(torch.nn.Module):
         self.calibrated = False
         self.generation = 0
 
-    def calibrate(self, cams, means3D, shs, colors_precomp, opacities, scales, rotations, headroom: float = 1.25):
+    def calibrate(self, cams, means3D, shs, colors_precomp, opacities, scales, rotations, headroom: float = 1.25,
+                  **extra):
         ws = self.ws
         while True:
-            nr, ov = forward_batched(ws, cams, means3D, shs, colors_precomp, opacities, scales, rotations, sync=True)
+            nr, ov = forward_batched(ws, cams, means3D, shs, colors_precomp, opacities, scales, rotations, sync=True,
+                                     **extra)
             need = int(max(nr) * headroom) + 4096
             if any(ov) or ws.capacity < need:
                 ws._alloc_binning(max(need, 2 * ws.capacity) if any(ov) else need)
@@ -441,7 +467,7 @@ class ViewBatchRasterizer(torch.nn.Module):
         return bad
 
     def forward(self, raster_settings, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None,
-                rotations=None):
+                rotations=None, extra_features=None):
         if (shs is None) == (colors_precomp is None):
             raise Exception("Please provide excatly one of either SHs or precomputed colors!")
         if scales is None or rotations is None:
@@ -450,4 +476,6 @@ class ViewBatchRasterizer(torch.nn.Module):
         if means3D.shape[0] != ws.P:
             raise RuntimeError("number of Gaussians changed (densify/prune): build a new ViewBatchRasterizer")
         cams = [ops.make_cam(rs, means3D.device) for rs in raster_settings]
-        return _RasterizeViews.apply(self, cams, means3D, means2D, shs, colors_precomp, opacities, scales, rotations)
+        out = _RasterizeViews.apply(self, cams, means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
+                                    extra_features)
+        return out if extra_features is not None else out[:4]

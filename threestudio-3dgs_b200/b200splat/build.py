@@ -25,6 +25,7 @@ SOURCES = {
     "preprocess.cu": ["-fmad=false"],
     "scan_sort.cu": [],
     "render.cu": [],
+    "extra.cu": [],
     "preprocess_bwd.cu": [],
     "knn.cu": [],
     "p2p.cu": [],

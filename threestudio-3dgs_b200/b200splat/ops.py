@@ -77,8 +77,22 @@ class ForwardState(NamedTuple):
     image: torch.Tensor
 
 
-def forward(cam: Cam, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp):
-    """Returns color (3,H,W), radii (P,) int32, depth (1,H,W), alpha (1,H,W), ForwardState."""
+MAX_EXTRA = 4
+
+
+def _check_extra(extra_features, P):
+    if extra_features is None:
+        return 0
+    if extra_features.dim() != 2 or extra_features.shape[0] != P or not 1 <= extra_features.shape[1] <= MAX_EXTRA:
+        raise ValueError(f"extra_features must be (P, 1..{MAX_EXTRA}); got {tuple(extra_features.shape)}")
+    return int(extra_features.shape[1])
+
+
+def forward(cam: Cam, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
+            extra_features=None):
+    """Returns color (3,H,W), radii (P,) int32, depth (1,H,W), alpha (1,H,W), ForwardState; with
+    ``extra_features`` (P,C'), C' <= 4, additionally the (C',H,W) image of those channels blended by the same
+    pass (inserted before the ForwardState)."""
     dev = means3D.device
     if not means3D.is_cuda:
         raise RuntimeError("b200splat.forward: tensors must be on a CUDA device (no CPU fallback)")
@@ -89,6 +103,8 @@ def forward(cam: Cam, means3D, shs, colors_precomp, opacities, scales, rotations
     depth = torch.empty(1, H, W, dtype=torch.float32, device=dev)
     alpha = torch.empty(1, H, W, dtype=torch.float32, device=dev)
     radii = torch.empty(P, dtype=torch.int32, device=dev)
+    n_extra = _check_extra(extra_features, P)
+    extra_img = torch.empty(n_extra, H, W, dtype=torch.float32, device=dev) if n_extra else None
     geom_bytes = lib.b200splat_geom_bytes(P)
     image_bytes = lib.b200splat_image_bytes(H, W)
     geom = torch.empty(geom_bytes, dtype=torch.uint8, device=dev)
@@ -117,14 +133,20 @@ def forward(cam: Cam, means3D, shs, colors_precomp, opacities, scales, rotations
     a.stream = _stream()
     a.num_rendered_out = C.pointer(nr)
     a.binning_out = C.pointer(bout)
+    if n_extra:
+        a.extra_features, a.n_extra, a.out_extra = extra_features.data_ptr(), n_extra, extra_img.data_ptr()
     with torch.cuda.device(dev):
         check(lib.b200splat_forward(C.byref(a)), "b200splat_forward")
     binning = held[0] if held else None
-    return color, radii, depth, alpha, ForwardState(P, M, int(nr.value), geom, binning, image)
+    st = ForwardState(P, M, int(nr.value), geom, binning, image)
+    if n_extra:
+        return color, radii, depth, alpha, extra_img, st
+    return color, radii, depth, alpha, st
 
 
 def backward(cam: Cam, st: ForwardState, means3D, shs, colors_precomp, opacities, scales, rotations,
-             cov3D_precomp, radii, out_alpha, g_color, g_depth, g_alpha, out=None, accumulate=False, stats=None):
+             cov3D_precomp, radii, out_alpha, g_color, g_depth, g_alpha, out=None, accumulate=False, stats=None,
+             extra_features=None, g_extra=None):
     """Returns dict of dense gradients (tensors allocated here unless ``out`` supplies them)."""
     dev = means3D.device
     P, M = st.P, st.M
@@ -142,6 +164,9 @@ def backward(cam: Cam, st: ForwardState, means3D, shs, colors_precomp, opacities
         out.setdefault("rotations", new(P, 4))
     if cov3D_precomp is not None:
         out.setdefault("cov3D_precomp", new(P, 6))
+    n_extra = _check_extra(extra_features, P)
+    if n_extra:
+        out.setdefault("extra_features", new(P, n_extra))
     scratch_bytes = lib.b200splat_backward_scratch_bytes(P)
     scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
     a = _lib.BackwardArgs()
@@ -161,6 +186,9 @@ def backward(cam: Cam, st: ForwardState, means3D, shs, colors_precomp, opacities
     if stats is not None:   # (grad_accum, denom, max_radii) each (P,) fp32, updated in place
         a.stat_grad_accum, a.stat_denom, a.stat_max_radii = (_ptr(t) for t in stats)
     a.stream = _stream()
+    if n_extra:
+        a.extra_features, a.n_extra = extra_features.data_ptr(), n_extra
+        a.dL_dout_extra, a.dL_dextra = _ptr(g_extra), out["extra_features"].data_ptr()
     with torch.cuda.device(dev):
         check(lib.b200splat_backward(C.byref(a)), "b200splat_backward")
     return out

@@ -70,6 +70,7 @@ size_t geom_layout(int P, void* base, GeomViews* v) {
     g.point_offsets = carve<uint32_t>(p, n);
     g.scan_ws_bytes = scan_workspace_bytes((int64_t)n);
     g.scan_ws = carve<char>(p, g.scan_ws_bytes);
+    g.ext4 = carve<float4>(p, n);
     if (v) *v = g;
     return (size_t)(p - p0);
 }
@@ -178,9 +179,10 @@ static int fill_camera(const b200splat_camera& c, const BatchTab& tab, ViewTab* 
     return B200SPLAT_OK;
 }
 
-static void fill_geom(int P, void* geom, ViewTab* vt) {
+static void fill_geom(int P, void* geom, ViewTab* vt, const float4** ext4 = nullptr) {
     GeomViews g;
     geom_layout(P, geom, &g);
+    if (ext4) *ext4 = g.ext4;
     vt->rec = g.rec, vt->depths = g.depths, vt->clamped = g.clamped;
     vt->tiles_touched = g.tiles_touched, vt->point_offsets = g.point_offsets;
     vt->rect = g.rect;
@@ -266,6 +268,14 @@ static PinnedSlot& pinned() {
 }  // namespace b200splat
 
 using namespace b200splat;
+
+static int check_extra(int n_extra, const void* features, bool has_out) {
+    if (n_extra < 0 || n_extra > EXT_FLOATS)
+        return fail(B200SPLAT_ERR_INVALID, "n_extra must be in [0, %d]", EXT_FLOATS);
+    if (n_extra > 0 && (!features || !has_out))
+        return fail(B200SPLAT_ERR_INVALID, "n_extra > 0 needs extra_features and the matching output");
+    return B200SPLAT_OK;
+}
 
 // binning + render part of the forward, common to the single-view and the batched entry points
 static int forward_tail(BatchTab& tab, int debug, cudaStream_t st, bool binning_cleared = false) {
@@ -375,8 +385,8 @@ size_t b200splat_geom_bytes(int32_t P) { return geom_layout(P, nullptr, nullptr)
 size_t b200splat_image_bytes(int32_t H, int32_t W) { return image_layout(H, W, nullptr, nullptr); }
 size_t b200splat_binning_bytes(int64_t R) { return binning_layout(R, nullptr, nullptr); }
 int64_t b200splat_binning_capacity(size_t bytes) { return capacity_for_bytes(bytes); }
-size_t b200splat_backward_scratch_bytes(int32_t P) {
-    return align_up((size_t)(P > 0 ? P : 1) * GRAD2D_FLOATS * sizeof(float), 256);
+size_t b200splat_backward_scratch_bytes(int32_t P) {   // grad2d records, then the extra-channel records
+    return grad2d_bytes(P) + align_up((size_t)(P > 0 ? P : 1) * EXT_FLOATS * sizeof(float), 256);
 }
 size_t b200splat_sort_workspace_bytes(int64_t n) { return sort_workspace_bytes(n); }
 size_t b200splat_scan_workspace_bytes(int64_t n) { return scan_workspace_bytes(n); }
@@ -407,6 +417,12 @@ int b200splat_forward(const b200splat_forward_args* a) {
     fill_image(tab.H, tab.W, a->image_buffer, &vt, &tab.tile_order);
     vt.out_color = a->out_color, vt.out_depth = a->out_depth, vt.out_alpha = a->out_alpha;
     vt.radii = a->radii;
+    rc = check_extra(a->n_extra, a->extra_features, a->out_extra != nullptr);
+    if (rc) return rc;
+    tab.n_extra = P > 0 ? a->n_extra : 0;
+    vt.out_extra = a->out_extra;
+    if (P <= 0 && a->n_extra > 0)
+        CU(cudaMemsetAsync(a->out_extra, 0, (size_t)a->n_extra * tab.H * tab.W * sizeof(float), st));
     if (a->num_rendered_out) *a->num_rendered_out = 0;
     if (a->binning_out) *a->binning_out = a->binning_buffer;
     if (P <= 0) CU(cudaMemsetAsync(vt.status, 0, STATUS_WORDS * sizeof(uint32_t), st));
@@ -416,11 +432,12 @@ int b200splat_forward(const b200splat_forward_args* a) {
         if (!a->means3D || !a->opacities || !a->radii) return fail(B200SPLAT_ERR_INVALID, "null per-Gaussian input");
         if (!a->geom_buffer || a->geom_bytes < geom_layout(P, nullptr, nullptr))
             return fail(B200SPLAT_ERR_NOMEM, "geom_buffer too small");
-        fill_geom(P, a->geom_buffer, &vt);
+        fill_geom(P, a->geom_buffer, &vt, &tab.ext4);
         { ProfScope ps(0, st);
         CU(launch_clear_batch(tab, /*with_binning=*/false, st));   // binning buffer: sized after the scan
         CU(launch_preprocess(tab, a->means3D, a->scales, a->rotations, a->opacities, a->shs, a->colors_precomp,
-                             a->cov3D_precomp, st)); }
+                             a->cov3D_precomp, st));
+        CU(launch_pad_extra(P, tab.n_extra, a->extra_features, const_cast<float4*>(tab.ext4), st)); }
         DEBUG_SYNC(a->cam, st, "preprocess");
         { ProfScope ps(3, st, /*counted=*/false);
         CU(launch_gaussian_sort(tab, st, /*cleared=*/true)); }
@@ -475,14 +492,18 @@ int b200splat_forward_batched(const b200splat_batch_forward_args* a) {
     const int64_t cap = capacity_for_bytes(a->binning_bytes);
     if (cap < 1) return fail(B200SPLAT_ERR_NOMEM, "binning_bytes too small");
     tab.capacity = (uint32_t)cap;
+    rc = check_extra(a->n_extra, a->extra_features, a->out_extra != nullptr);
+    if (rc) return rc;
+    tab.n_extra = a->n_extra;
     for (int v = 0; v < V; ++v) {
         ViewTab& vt = tab.v[v];
         rc = fill_camera(a->cams[v], tab, &vt);
         if (rc) return rc;
         if (!a->geom_buffer[v] || !a->image_buffer[v] || !a->binning_buffer[v] || !a->radii[v] || !a->out_color[v] ||
-            !a->out_depth[v] || !a->out_alpha[v])
+            !a->out_depth[v] || !a->out_alpha[v] || (tab.n_extra > 0 && !a->out_extra[v]))
             return fail(B200SPLAT_ERR_INVALID, "null buffer for view %d", v);
-        fill_geom(P, a->geom_buffer[v], &vt);
+        vt.out_extra = tab.n_extra > 0 ? a->out_extra[v] : nullptr;
+        fill_geom(P, a->geom_buffer[v], &vt, v == 0 ? &tab.ext4 : nullptr);
         fill_image(tab.H, tab.W, a->image_buffer[v], &vt, v == 0 ? &tab.tile_order : nullptr);
         fill_binning(cap, a->binning_buffer[v], &vt);
         vt.out_color = a->out_color[v], vt.out_depth = a->out_depth[v], vt.out_alpha = a->out_alpha[v];
@@ -491,7 +512,8 @@ int b200splat_forward_batched(const b200splat_batch_forward_args* a) {
     { ProfScope ps(0, st);
     CU(launch_clear_batch(tab, /*with_binning=*/true, st));
     CU(launch_preprocess(tab, a->means3D, a->scales, a->rotations, a->opacities, a->shs, a->colors_precomp, nullptr,
-                         st)); }
+                         st));
+    CU(launch_pad_extra(P, tab.n_extra, a->extra_features, const_cast<float4*>(tab.ext4), st)); }
     DEBUG_SYNC(a->cams[0], st, "preprocess");
     { ProfScope ps(3, st, /*counted=*/false);
     CU(launch_gaussian_sort(tab, st, /*cleared=*/true)); }
@@ -523,7 +545,8 @@ static int backward_run(BatchTab& tab, const float* means3D, const float* scales
                         const float* shs, const float* cov3D_precomp, float* dL_dmeans3D, float* dL_dshs,
                         float* dL_dcolors, float* dL_dopacity, float* dL_dscales, float* dL_drotations,
                         float* dL_dcov3D, float* sa, float* sd, float* sm, int accumulate, int debug, bool any_pairs,
-                        cudaStream_t st, bool scratch_clean = false, int phase = 0, int g_begin = 0, int g_end = 0) {
+                        cudaStream_t st, bool scratch_clean = false, int phase = 0, int g_begin = 0, int g_end = 0,
+                        float* dL_dextra = nullptr) {
     b200splat_camera dbg{};
     dbg.debug = debug;
     const int sel = sorted_sel_for(tab.grid_x * tab.grid_y);
@@ -531,8 +554,11 @@ static int backward_run(BatchTab& tab, const float* means3D, const float* scales
     if (phase != 2) {
         ProfScope ps(6, st);
         if (!scratch_clean)
-            for (int v = 0; v < tab.V; ++v)
+            for (int v = 0; v < tab.V; ++v) {
                 CU(cudaMemsetAsync(tab.v[v].grad2d, 0, (size_t)tab.P * GRAD2D_FLOATS * sizeof(float), st));
+                if (tab.n_extra > 0)
+                    CU(cudaMemsetAsync(tab.v[v].gradext, 0, (size_t)tab.P * EXT_FLOATS * sizeof(float), st));
+            }
         if (any_pairs) CU(launch_render_backward(tab, sel, st));
     }
     DEBUG_SYNC(dbg, st, "render backward");
@@ -541,6 +567,7 @@ static int backward_run(BatchTab& tab, const float* means3D, const float* scales
         CU(launch_preprocess_backward(tab, means3D, scales, rotations, shs, cov3D_precomp, dL_dmeans3D, dL_dshs,
                                       dL_dcolors, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D, sa, sd, sm,
                                       accumulate, st, g_begin, g_end));
+        CU(launch_extra_backward(tab, dL_dextra, accumulate, st, g_begin, g_end));
     }
     DEBUG_SYNC(dbg, st, "preprocess backward");
     return B200SPLAT_OK;
@@ -565,7 +592,10 @@ int b200splat_backward(const b200splat_backward_args* a) {
     if (!a->scratch || a->scratch_bytes < b200splat_backward_scratch_bytes(P))
         return fail(B200SPLAT_ERR_NOMEM, "scratch too small");
     if (!a->geom_buffer || !a->image_buffer || !a->radii) return fail(B200SPLAT_ERR_INVALID, "null saved buffer");
-    fill_geom(P, const_cast<void*>(a->geom_buffer), &vt);
+    rc = check_extra(a->n_extra, a->extra_features, a->dL_dextra != nullptr);
+    if (rc) return rc;
+    tab.n_extra = a->n_extra;
+    fill_geom(P, const_cast<void*>(a->geom_buffer), &vt, &tab.ext4);
     fill_image(tab.H, tab.W, const_cast<void*>(a->image_buffer), &vt, &tab.tile_order);
     vt.radii = const_cast<int32_t*>(a->radii);
     if (a->num_rendered > 0) {
@@ -575,10 +605,13 @@ int b200splat_backward(const b200splat_backward_args* a) {
     }
     vt.dL_dcolor = a->dL_dout_color, vt.dL_ddepth = a->dL_dout_depth, vt.dL_dalpha = a->dL_dout_alpha;
     vt.grad2d = reinterpret_cast<float*>(a->scratch);
+    vt.gradext = reinterpret_cast<float*>(reinterpret_cast<char*>(a->scratch) + grad2d_bytes(P));
+    vt.dL_dextra = a->dL_dout_extra;
     vt.dL_dmeans2D = a->dL_dmeans2D;
     return backward_run(tab, a->means3D, a->scales, a->rotations, a->shs, a->cov3D_precomp, a->dL_dmeans3D, a->dL_dshs,
                         a->dL_dcolors, a->dL_dopacity, a->dL_dscales, a->dL_drotations, a->dL_dcov3D, a->stat_grad_accum,
-                        a->stat_denom, a->stat_max_radii, a->accumulate, a->cam.debug, a->num_rendered > 0, st);
+                        a->stat_denom, a->stat_max_radii, a->accumulate, a->cam.debug, a->num_rendered > 0, st,
+                        /*scratch_clean=*/false, /*phase=*/0, 0, 0, a->dL_dextra);
 }
 
 int b200splat_backward_batched(const b200splat_batch_backward_args* a) {
@@ -600,13 +633,18 @@ int b200splat_backward_batched(const b200splat_batch_backward_args* a) {
     const int64_t cap = capacity_for_bytes(a->binning_bytes);
     if (cap < 1) return fail(B200SPLAT_ERR_NOMEM, "binning_bytes too small");
     tab.capacity = (uint32_t)cap;
+    rc = check_extra(a->n_extra, a->extra_features, a->dL_dextra != nullptr);
+    if (rc) return rc;
+    tab.n_extra = a->n_extra;
     for (int v = 0; v < V; ++v) {
         ViewTab& vt = tab.v[v];
         rc = fill_camera(a->cams[v], tab, &vt);
         if (rc) return rc;
         if (!a->geom_buffer[v] || !a->image_buffer[v] || !a->binning_buffer[v] || !a->radii[v] || !a->scratch[v])
             return fail(B200SPLAT_ERR_INVALID, "null buffer for view %d", v);
-        fill_geom(P, const_cast<void*>(a->geom_buffer[v]), &vt);
+        fill_geom(P, const_cast<void*>(a->geom_buffer[v]), &vt, v == 0 ? &tab.ext4 : nullptr);
+        vt.gradext = reinterpret_cast<float*>(reinterpret_cast<char*>(a->scratch[v]) + grad2d_bytes(P));
+        vt.dL_dextra = (tab.n_extra > 0 && a->dL_dout_extra) ? a->dL_dout_extra[v] : nullptr;
         fill_image(tab.H, tab.W, const_cast<void*>(a->image_buffer[v]), &vt, v == 0 ? &tab.tile_order : nullptr);
         fill_binning(cap, const_cast<void*>(a->binning_buffer[v]), &vt);
         vt.radii = const_cast<int32_t*>(a->radii[v]);
@@ -619,7 +657,7 @@ int b200splat_backward_batched(const b200splat_batch_backward_args* a) {
     return backward_run(tab, a->means3D, a->scales, a->rotations, a->shs, nullptr, a->dL_dmeans3D, a->dL_dshs,
                         a->dL_dcolors, a->dL_dopacity, a->dL_dscales, a->dL_drotations, nullptr, a->stat_grad_accum,
                         a->stat_denom, a->stat_max_radii, a->accumulate, a->cams[0].debug, true, st, a->scratch_clean != 0,
-                        a->phase, a->g_begin, a->g_end);
+                        a->phase, a->g_begin, a->g_end, a->dL_dextra);
 }
 
 int b200splat_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,

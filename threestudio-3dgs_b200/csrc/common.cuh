@@ -89,6 +89,10 @@ struct ViewTab {
     const float* dL_dalpha;
     float* grad2d;
     float* dL_dmeans2D;   // optional per-view output (P,3)
+    // extra feature channels blended by the same pass (normals, ...): BatchTab.n_extra > 0
+    float* out_extra;         // (n_extra, H, W): sum_i e_i alpha_i T_i, no background term
+    const float* dL_dextra;   // (n_extra, H, W) pixel gradients, or NULL
+    float* gradext;           // [P][4] per-Gaussian gradient of the padded extra record (atomics, behind grad2d)
 };
 
 struct BatchTab {
@@ -102,6 +106,8 @@ struct BatchTab {
     int digit_passes;          // 8-bit passes of the pair sort; 0 = one wide pass binned by the per-tile counts
     int idx_bits;              // index bits of a pair word (32)
     int clean_scratch;         // preprocess backward zeroes every grad2d record it has read (self-cleaning scratch)
+    int n_extra;               // 0..4 extra per-Gaussian feature channels rendered next to the colour
+    const float4* ext4;        // [P] the extra features padded to 16 B (view independent; lives in view 0's geometry)
     uint32_t* tile_order;      // [V * T] entries (view * T + tile), longest list first
     ViewTab v[MAX_VIEWS];
 };
@@ -118,6 +124,7 @@ struct GeomViews {
     uint32_t* point_offsets; // P
     void* scan_ws;
     size_t scan_ws_bytes;
+    float4* ext4;            // P   (extra feature channels padded to 16 B; only written when n_extra > 0)
 };
 struct BinningViews {
     uint64_t* keys[2];
@@ -175,6 +182,13 @@ cudaError_t launch_preprocess_backward(const BatchTab& tab, const float* means3D
                                        float* dL_dscales, float* dL_drotations, float* dL_dcov3D,
                                        float* stat_grad_accum, float* stat_denom, float* stat_max_radii,
                                        int accumulate, cudaStream_t st, int g_begin = 0, int g_end = 0);
+
+// extra feature channels (extra.cu): pad (P, n_extra) to float4 records; sum the views' per-Gaussian gradients
+constexpr int EXT_FLOATS = 4;
+cudaError_t launch_pad_extra(int P, int n_extra, const float* extra, float4* ext4, cudaStream_t st);
+cudaError_t launch_extra_backward(const BatchTab& tab, float* dL_dextra, int accumulate, cudaStream_t st,
+                                  int g_begin = 0, int g_end = 0);
+size_t grad2d_bytes(int P);   // offset of gradext inside the backward scratch
 
 size_t dist2_workspace_bytes(int P);
 cudaError_t launch_dist2(int P, const float* points, float* out, void* ws, cudaStream_t st);

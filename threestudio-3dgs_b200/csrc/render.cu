@@ -93,22 +93,26 @@ struct PointList {   // sorted list: packed words (key << idx_bits | idx) or a p
     }
 };
 
-// gather the record of list entry `pos` into buf[slot]; completion arrives on `bar`
-template <bool BULK>
+// gather the record of list entry `pos` into buf[slot] (and, EXT, its extra-feature record into extbuf[slot]);
+// completion arrives on `bar`
+template <bool BULK, bool EXT = false>
 __device__ __forceinline__ void stage_entry(float4* buf, uint32_t* ids, uint64_t* bar, const float* __restrict__ rec,
-                                            const PointList point_list, int slot, int64_t pos, bool valid) {
+                                            const PointList point_list, int slot, int64_t pos, bool valid,
+                                            float4* extbuf = nullptr, const float4* __restrict__ ext4 = nullptr) {
     if (valid) {
         const uint32_t id = point_list.at(pos);
         if (ids) ids[slot] = id;
         const float* src = rec + (size_t)id * REC_FLOATS;
         float4* dst = buf + 3 * slot;
         if (BULK) {
-            mbar_arrive_expect_tx(bar, REC_FLOATS * 4);
+            mbar_arrive_expect_tx(bar, REC_FLOATS * 4 + (EXT ? 16 : 0));
             bulk_g2s(dst, src, REC_FLOATS * 4, bar);
+            if (EXT) bulk_g2s(extbuf + slot, ext4 + id, 16, bar);
         } else {
             cp_async16(dst, src);
             cp_async16(dst + 1, src + 4);
             cp_async16(dst + 2, src + 8);
+            if (EXT) cp_async16(extbuf + slot, ext4 + id);
             cp_async_arrive_noinc(bar);
         }
     } else {
@@ -147,19 +151,23 @@ __device__ __forceinline__ void thread_pixel_cta(int& lx, int& ly) {
     lx = (warp & 1) * 8 + (lane & 7);
     ly = (warp >> 1) * 4 + (lane >> 3);
 }
-template <bool BULK>
+template <bool BULK, bool EXT>
 __device__ __forceinline__ void stage_batch_cta(float4* buf, uint32_t* ids, uint64_t* bar, const float* __restrict__ rec,
-                                                const PointList point_list, int64_t pos, bool valid) {
-    stage_entry<BULK>(buf, ids, bar, rec, point_list, (int)threadIdx.x, pos, valid);
+                                                const PointList point_list, int64_t pos, bool valid, float4* extbuf,
+                                                const float4* __restrict__ ext4) {
+    stage_entry<BULK, EXT>(buf, ids, bar, rec, point_list, (int)threadIdx.x, pos, valid, extbuf, ext4);
 }
 
 // ============================================================================================
 // K6 forward
 // ============================================================================================
-template <bool BULK>
+// EXT: up to 4 extra feature channels per Gaussian (one more 16-byte record per staged entry) are blended with the
+// same weights as the colour and written to out_extra (no background term)
+template <bool BULK, bool EXT>
 __global__ void __launch_bounds__(BLOCK_SIZE)
 render_forward_kernel(const __grid_constant__ BatchTab tab, int sel) {
     __shared__ __align__(16) float4 s_rec[FWD_STAGES][FWD_BATCH * 3];
+    __shared__ __align__(16) float4 s_ext[FWD_STAGES][EXT ? FWD_BATCH : 1];
     __shared__ __align__(8) uint64_t s_bar[FWD_STAGES];
     __shared__ __align__(16) uint8_t s_surv[BLOCK_SIZE / 32][FWD_BATCH + 16];
 
@@ -173,6 +181,7 @@ render_forward_kernel(const __grid_constant__ BatchTab tab, int sel) {
     const PointList point_list{tab.idx_bits ? vt.keys[sel] : nullptr, vt.vals[sel],
                                tab.idx_bits ? (uint32_t)((1ull << tab.idx_bits) - 1ull) : 0xffffffffu};
     const float* __restrict__ rec = vt.rec;
+    const float4* __restrict__ ext4 = tab.ext4;
     const float* __restrict__ bg = vt.bg;
     uint32_t* __restrict__ n_contrib = vt.n_contrib;
     uint32_t* __restrict__ n_visited = vt.n_visited;
@@ -202,12 +211,13 @@ render_forward_kernel(const __grid_constant__ BatchTab tab, int sel) {
 
     bool done = !inside;
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Wt = 0.f, D = 0.f;
+    float E0 = 0.f, E1 = 0.f, E2 = 0.f, E3 = 0.f;
     uint32_t last_contributor = 0, visited = 0;
     int traversed = 0;
 
     if (rounds > 0)
-        stage_batch_cta<BULK>(s_rec[0], nullptr, &s_bar[0], rec, point_list, (int64_t)r0 + threadIdx.x,
-                          (int)threadIdx.x < total);
+        stage_batch_cta<BULK, EXT>(s_rec[0], nullptr, &s_bar[0], rec, point_list, (int64_t)r0 + threadIdx.x,
+                                   (int)threadIdx.x < total, s_ext[0], ext4);
     for (int b = 0; b < rounds; ++b) {
         // also orders "everyone finished reading stage (b+1)&1" before it is refilled
         const int num_done = __syncthreads_count(done);
@@ -219,12 +229,14 @@ render_forward_kernel(const __grid_constant__ BatchTab tab, int sel) {
         }
         if (b + 1 < rounds) {
             const int nb = (b + 1) * FWD_BATCH + threadIdx.x;
-            stage_batch_cta<BULK>(s_rec[s ^ 1], nullptr, &s_bar[s ^ 1], rec, point_list, (int64_t)r0 + nb, nb < total);
+            stage_batch_cta<BULK, EXT>(s_rec[s ^ 1], nullptr, &s_bar[s ^ 1], rec, point_list, (int64_t)r0 + nb,
+                                       nb < total, s_ext[s ^ 1], ext4);
         }
         mbar_wait(&s_bar[s], (b >> 1) & 1);
         const int count = min(FWD_BATCH, total - b * FWD_BATCH);
         traversed = b * FWD_BATCH + count;
         const float4* __restrict__ buf = s_rec[s];
+        const float4* __restrict__ ebuf = s_ext[s];
         // batch-level cull: 8 independent tests per lane; survivors compacted (in list order) into the
         // warp's private index list
         uint8_t* __restrict__ surv = s_surv[warp];
@@ -255,6 +267,7 @@ render_forward_kernel(const __grid_constant__ BatchTab tab, int sel) {
             const uint32_t packed = *reinterpret_cast<const uint32_t*>(surv + i);
             int j[ILP];
             float alpha[ILP], cr[ILP], cg[ILP], cb[ILP], cd[ILP];
+            float4 ex[ILP];
             bool ok[ILP];
 #pragma unroll
             for (int k = 0; k < ILP; ++k) {
@@ -263,6 +276,7 @@ render_forward_kernel(const __grid_constant__ BatchTab tab, int sel) {
                 const float4 q0 = buf[3 * j[k]];
                 const float4 q1 = buf[3 * j[k] + 1];
                 const float2 q2 = *reinterpret_cast<const float2*>(buf + 3 * j[k] + 2);
+                if (EXT) ex[k] = ebuf[j[k]];
                 const float dx = q0.x - pixx, dy = q0.y - pixy;
                 const float power = -0.5f * (q0.z * dx * dx + q1.x * dy * dy) - q0.w * dx * dy;
                 alpha[k] = fminf(ALPHA_MAX, q1.y * __expf(power));
@@ -283,6 +297,7 @@ render_forward_kernel(const __grid_constant__ BatchTab tab, int sel) {
                     C2 += cb[k] * w;
                     Wt += w;
                     D += cd[k] * w;
+                    if (EXT) E0 += ex[k].x * w, E1 += ex[k].y * w, E2 += ex[k].z * w, E3 += ex[k].w * w;
                     T = test_T;
                     last_contributor = position;
                 }
@@ -304,6 +319,12 @@ render_forward_kernel(const __grid_constant__ BatchTab tab, int sel) {
         out_color[2 * HW + pix] = C2 + T * bg[2];
         out_depth[pix] = D;
         out_alpha[pix] = Wt;
+        if (EXT) {
+            const float E[EXT_FLOATS] = {E0, E1, E2, E3};
+#pragma unroll
+            for (int c = 0; c < EXT_FLOATS; ++c)
+                if (c < tab.n_extra) vt.out_extra[c * HW + pix] = E[c];
+        }
     }
 }
 
@@ -367,10 +388,39 @@ __device__ __forceinline__ int reduce_slot(int lane) {
     return k < 0 ? -1 : 5 * b4 + k;
 }
 
-template <bool BULK>
+// Sum 4 per-lane values over the warp with 6 shuffles; afterwards the lanes with (lane & 7) == 0 hold the total of
+// v[2 * bit4 + bit3] (reduce_slot4).
+__device__ __forceinline__ float warp_reduce4(const float v[4], int lane) {
+    const bool b4 = lane & 16, b3 = lane & 8;
+    float a0, a1;
+    {
+        float send = b4 ? v[0] : v[2];
+        float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+        a0 = (b4 ? v[2] : v[0]) + recv;
+        send = b4 ? v[1] : v[3];
+        recv = __shfl_xor_sync(0xffffffffu, send, 16);
+        a1 = (b4 ? v[3] : v[1]) + recv;
+    }
+    float c;
+    {
+        const float send = b3 ? a0 : a1;
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+        c = (b3 ? a1 : a0) + recv;
+    }
+    c += __shfl_xor_sync(0xffffffffu, c, 4);
+    c += __shfl_xor_sync(0xffffffffu, c, 2);
+    c += __shfl_xor_sync(0xffffffffu, c, 1);
+    return c;
+}
+__device__ __forceinline__ int reduce_slot4(int lane) {
+    return (lane & 7) ? -1 : 2 * ((lane >> 4) & 1) + ((lane >> 3) & 1);
+}
+
+template <bool BULK, bool EXT>
 __global__ void __launch_bounds__(32)
 render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
     __shared__ __align__(16) float4 s_rec[STAGES][BATCH * 3];
+    __shared__ __align__(16) float4 s_ext[STAGES][EXT ? BATCH : 1];
     __shared__ uint32_t s_ids[STAGES][BATCH];
     __shared__ __align__(8) uint64_t s_bar[STAGES];
     __shared__ __align__(16) uint8_t s_surv[BATCH + 16];
@@ -385,8 +435,10 @@ render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
     const PointList point_list{tab.idx_bits ? vt.keys[sel] : nullptr, vt.vals[sel],
                                tab.idx_bits ? (uint32_t)((1ull << tab.idx_bits) - 1ull) : 0xffffffffu};
     const float* __restrict__ rec = vt.rec;
+    const float4* __restrict__ ext4 = tab.ext4;
     const float* __restrict__ bg = vt.bg;
     float* __restrict__ grad2d = vt.grad2d;
+    float* __restrict__ gradext = vt.gradext;
     int lx, ly;
     thread_pixel(wblock, lx, ly);
     const int lane = threadIdx.x;
@@ -408,6 +460,7 @@ render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
     if (total == 0) return;
     const int rounds = (total + BATCH - 1) / BATCH;
     const int slot = reduce_slot(lane);
+    const int slot4 = reduce_slot4(lane);
 
     const float T_final = inside ? vt.final_T[pix] : 0.0f;
     float T = T_final;
@@ -416,6 +469,13 @@ render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
         if (vt.dL_dcolor) gC0 = vt.dL_dcolor[pix], gC1 = vt.dL_dcolor[HW + pix], gC2 = vt.dL_dcolor[2 * HW + pix];
         if (vt.dL_ddepth) gD = vt.dL_ddepth[pix];
         if (vt.dL_dalpha) gA = vt.dL_dalpha[pix];
+    }
+    float gE[EXT_FLOATS] = {0.f, 0.f, 0.f, 0.f}, accE[EXT_FLOATS] = {0.f, 0.f, 0.f, 0.f},
+          lE[EXT_FLOATS] = {0.f, 0.f, 0.f, 0.f};
+    if (EXT && inside && vt.dL_dextra) {
+#pragma unroll
+        for (int c = 0; c < EXT_FLOATS; ++c)
+            if (c < tab.n_extra) gE[c] = vt.dL_dextra[c * HW + pix];
     }
     const float bg_dot = bg[0] * gC0 + bg[1] * gC1 + bg[2] * gC2;
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accD = 0.f, accA = 0.f;
@@ -434,8 +494,8 @@ render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
         for (int u = 0; u < BATCH / 32; ++u) {
             const int sl = lane + 32 * u;
             const int p = b * BATCH + sl;
-            stage_entry<BULK>(s_rec[s], s_ids[s], &s_bar[s], rec, point_list, sl, (int64_t)r0 + (total - 1 - p),
-                              p < total);
+            stage_entry<BULK, EXT>(s_rec[s], s_ids[s], &s_bar[s], rec, point_list, sl, (int64_t)r0 + (total - 1 - p),
+                                   p < total, s_ext[s], ext4);
         }
     };
     stage(0);
@@ -470,6 +530,8 @@ render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
             bool hit[ILP];
             float G[ILP], alpha[ILP], inv1m[ILP], ddx[ILP], ddy[ILP], cA[ILP], cB[ILP], cC[ILP], op[ILP];
             float cr[ILP], cg[ILP], cb[ILP], cd[ILP];
+            float ve[ILP][EXT_FLOATS];
+            float4 ex[ILP];
 #pragma unroll
             for (int k = 0; k < ILP; ++k) {
                 const bool has = i + k < nsurv;
@@ -477,6 +539,7 @@ render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
                 const float4 q0 = buf[3 * j[k]];
                 const float4 q1 = buf[3 * j[k] + 1];
                 const float2 q2 = *reinterpret_cast<const float2*>(buf + 3 * j[k] + 2);
+                if (EXT) ex[k] = s_ext[s][j[k]];
                 const uint32_t q = (uint32_t)(total - 1 - (b * BATCH + j[k]));
                 ddx[k] = q0.x - pixx, ddy[k] = q0.y - pixy;
                 cA[k] = q0.z, cB[k] = q0.w, cC[k] = q1.x, op[k] = q1.y;
@@ -492,6 +555,10 @@ render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
             for (int k = 0; k < ILP; ++k) {
 #pragma unroll
                 for (int t = 0; t < 10; ++t) v[k][t] = 0.f;
+                if (EXT) {
+#pragma unroll
+                    for (int c = 0; c < EXT_FLOATS; ++c) ve[k][c] = 0.f;
+                }
                 if (hit[k]) {
                     const float a = alpha[k], dx = ddx[k], dy = ddy[k];
                     T = T * inv1m[k];
@@ -512,6 +579,16 @@ render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
                     dL_da += (cd[k] - accD) * gD;
                     accA = last_alpha + om * accA;
                     dL_da += (1.0f - accA) * gA;
+                    if (EXT) {
+                        const float e[EXT_FLOATS] = {ex[k].x, ex[k].y, ex[k].z, ex[k].w};
+#pragma unroll
+                        for (int c = 0; c < EXT_FLOATS; ++c) {
+                            accE[c] = last_alpha * lE[c] + om * accE[c];
+                            lE[c] = e[c];
+                            dL_da += (e[c] - accE[c]) * gE[c];
+                            ve[k][c] = w * gE[c];
+                        }
+                    }
                     dL_da *= T;
                     last_alpha = a;
                     dL_da += (-T_final * inv1m[k]) * bg_dot;
@@ -539,6 +616,15 @@ render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
                 for (int k = 0; k < ILP; ++k)
                     if (slot >= 0 && ((anyhit >> k) & 1u))
                         atomicAdd(grad2d + (size_t)s_ids[s][j[k]] * GRAD2D_FLOATS + slot, r[k]);
+                if (EXT) {
+                    float re[ILP];
+#pragma unroll
+                    for (int k = 0; k < ILP; ++k) re[k] = warp_reduce4(ve[k], lane);
+#pragma unroll
+                    for (int k = 0; k < ILP; ++k)
+                        if (slot4 >= 0 && slot4 < tab.n_extra && ((anyhit >> k) & 1u))
+                            atomicAdd(gradext + (size_t)s_ids[s][j[k]] * EXT_FLOATS + slot4, re[k]);
+                }
             }
         }
     }
@@ -555,20 +641,28 @@ static bool use_bulk_staging() {
 
 cudaError_t launch_render_forward(const BatchTab& tab, int sel, cudaStream_t st) {
     const unsigned grid = (unsigned)(tab.V * tab.grid_x * tab.grid_y);
-    if (use_bulk_staging())
-        render_forward_kernel<true><<<grid, BLOCK_SIZE, 0, st>>>(tab, sel);
-    else
-        render_forward_kernel<false><<<grid, BLOCK_SIZE, 0, st>>>(tab, sel);
+    const bool ext = tab.n_extra > 0;
+    if (use_bulk_staging()) {
+        if (ext) render_forward_kernel<true, true><<<grid, BLOCK_SIZE, 0, st>>>(tab, sel);
+        else render_forward_kernel<true, false><<<grid, BLOCK_SIZE, 0, st>>>(tab, sel);
+    } else {
+        if (ext) render_forward_kernel<false, true><<<grid, BLOCK_SIZE, 0, st>>>(tab, sel);
+        else render_forward_kernel<false, false><<<grid, BLOCK_SIZE, 0, st>>>(tab, sel);
+    }
     count_launch();
     return cudaGetLastError();
 }
 
 cudaError_t launch_render_backward(const BatchTab& tab, int sel, cudaStream_t st) {
     const unsigned grid = (unsigned)(tab.V * tab.grid_x * tab.grid_y * WARPS_PER_TILE);
-    if (use_bulk_staging())
-        render_backward_kernel<true><<<grid, 32, 0, st>>>(tab, sel);
-    else
-        render_backward_kernel<false><<<grid, 32, 0, st>>>(tab, sel);
+    const bool ext = tab.n_extra > 0;
+    if (use_bulk_staging()) {
+        if (ext) render_backward_kernel<true, true><<<grid, 32, 0, st>>>(tab, sel);
+        else render_backward_kernel<true, false><<<grid, 32, 0, st>>>(tab, sel);
+    } else {
+        if (ext) render_backward_kernel<false, true><<<grid, 32, 0, st>>>(tab, sel);
+        else render_backward_kernel<false, false><<<grid, 32, 0, st>>>(tab, sel);
+    }
     count_launch();
     return cudaGetLastError();
 }

@@ -18,6 +18,11 @@ allocated non-view tensors (callers write into them in place,
 renderer/diff_gaussian_rasterizer_shading.py:209-213) and only ``alpha`` of the outputs is kept
 for backward; backward can run twice on one forward (system/gaussian_splatting.py:129,137-138).
 
+One optional, non-breaking addition: ``extra_features=(P, C')`` (C' <= 4) renders C' more per-Gaussian channels
+with the SAME pass and alphas and appends their ``(C',H,W)`` image as a fifth output -- what the reference's
+normal / shading variants obtain from a second full rasterizer call with the normals as colours
+(renderer/diff_gaussian_rasterizer_shading.py:177-187).
+
 CUDA only: there is no CPU fallback; a missing extension raises at import.
 """
 from __future__ import annotations
@@ -50,15 +55,16 @@ def _opt(t):
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                        raster_settings):
-    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                                     cov3Ds_precomp, raster_settings)
+                        raster_settings, extra_features=None):
+    out = _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                    cov3Ds_precomp, raster_settings, extra_features)
+    return out if extra_features is not None else out[:4]
 
 
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                raster_settings):
+                raster_settings, extra_features=None):
         dev = means3D.device
         if not means3D.is_cuda:
             raise RuntimeError("diff_gaussian_rasterization (b200splat): inputs must be CUDA tensors; "
@@ -66,43 +72,51 @@ class _RasterizeGaussians(torch.autograd.Function):
         cam = _ops.make_cam(raster_settings, dev)
         P = means3D.shape[0]
         ctx.P = P
+        n_extra = _ops._check_extra(extra_features, P)
         if P == 0:
             H, W = cam.H, cam.W
             color = cam.bg.reshape(3, 1, 1).expand(3, H, W).contiguous()
-            z = lambda: torch.zeros(1, H, W, dtype=torch.float32, device=dev)
+            z = lambda c=1: torch.zeros(c, H, W, dtype=torch.float32, device=dev)
             radii = torch.zeros(0, dtype=torch.int32, device=dev)
             ctx.mark_non_differentiable(radii)
-            return color, radii, z(), z()
+            return color, radii, z(), z(), z(n_extra)
         f = _ops._f32c
         m3, sh_, cp_, op_ = f(means3D, "means3D"), f(_opt(sh), "shs"), f(_opt(colors_precomp), "colors_precomp"), \
             f(opacities, "opacities")
         sc_, ro_, c3_ = f(_opt(scales), "scales"), f(_opt(rotations), "rotations"), f(_opt(cov3Ds_precomp), "cov3D")
-        color, radii, depth, alpha, st = _ops.forward(cam, m3, sh_, cp_, op_, sc_, ro_, c3_)
+        ex_ = f(extra_features, "extra_features") if n_extra else None
+        res = _ops.forward(cam, m3, sh_, cp_, op_, sc_, ro_, c3_, ex_)
+        color, radii, depth, alpha = res[:4]
+        st = res[-1]
+        extra_img = res[4] if n_extra else torch.zeros(0, cam.H, cam.W, dtype=torch.float32, device=dev)
+        ctx.n_extra = n_extra
         ctx.cam = cam
         ctx.state = (st.P, st.M, st.num_rendered)
         ctx.present = (sh_ is not None, cp_ is not None, sc_ is not None, c3_ is not None)
         e = lambda t: t if t is not None else torch.empty(0, device=dev)
         ctx.save_for_backward(m3, e(sh_), e(cp_), op_, e(sc_), e(ro_), e(c3_), radii, alpha, st.geom,
-                              e(st.binning), st.image)
+                              e(st.binning), st.image, e(ex_))
         ctx.mark_non_differentiable(radii)
-        return color, radii, depth, alpha
+        return color, radii, depth, alpha, extra_img
 
     @staticmethod
-    def backward(ctx, g_color, g_radii, g_depth, g_alpha):
+    def backward(ctx, g_color, g_radii, g_depth, g_alpha, g_extra):
         if ctx.P == 0:
-            return (None,) * 9
-        m3, sh_, cp_, op_, sc_, ro_, c3_, radii, alpha, geom, binning, image = ctx.saved_tensors
+            return (None,) * 10
+        m3, sh_, cp_, op_, sc_, ro_, c3_, radii, alpha, geom, binning, image, ex_ = ctx.saved_tensors
         has_sh, has_cp, has_sr, has_c3 = ctx.present
         P, M, R = ctx.state
         st = _ops.ForwardState(P, M, R, geom, _opt(binning), image)
         gc = None if g_color is None else _ops._f32c(g_color, "grad_color")
         gd = None if g_depth is None else _ops._f32c(g_depth, "grad_depth")
         ga = None if g_alpha is None else _ops._f32c(g_alpha, "grad_alpha")
+        n_extra = ctx.n_extra
+        ge = None if (g_extra is None or not n_extra) else _ops._f32c(g_extra, "grad_extra")
         g = _ops.backward(ctx.cam, st, m3, sh_ if has_sh else None, cp_ if has_cp else None, op_,
                           sc_ if has_sr else None, ro_ if has_sr else None, c3_ if has_c3 else None,
-                          radii, alpha, gc, gd, ga)
+                          radii, alpha, gc, gd, ga, extra_features=ex_ if n_extra else None, g_extra=ge)
         return (g["means3D"], g["means2D"], g.get("shs"), g.get("colors_precomp"), g["opacities"],
-                g.get("scales"), g.get("rotations"), g.get("cov3D_precomp"), None)
+                g.get("scales"), g.get("rotations"), g.get("cov3D_precomp"), None, g.get("extra_features"))
 
 
 class GaussianRasterizer(nn.Module):
@@ -116,7 +130,7 @@ class GaussianRasterizer(nn.Module):
             return _ops.mark_visible(positions, rs.viewmatrix, rs.projmatrix)
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
-                cov3D_precomp=None):
+                cov3D_precomp=None, extra_features=None):
         if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
             raise Exception("Please provide excatly one of either SHs or precomputed colors!")
         if ((scales is None or rotations is None) and cov3D_precomp is None) or (
@@ -127,7 +141,8 @@ class GaussianRasterizer(nn.Module):
                                    colors_precomp if colors_precomp is not None else empty, opacities,
                                    scales if scales is not None else empty,
                                    rotations if rotations is not None else empty,
-                                   cov3D_precomp if cov3D_precomp is not None else empty, self.raster_settings)
+                                   cov3D_precomp if cov3D_precomp is not None else empty, self.raster_settings,
+                                   extra_features)
 
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians"]
