@@ -266,6 +266,62 @@ typedef struct b200splat_batch_backward_args {
 
 int b200splat_backward_batched(const b200splat_batch_backward_args* args);
 
+/* ---- fused per-pixel post-ops of the renderer variants (forward + backward), for V views at once -------------
+ * What the reference does in ~25 PyTorch kernels per view after the rasterizer call:
+ *   PLAIN       render = clamp(image, 0, 1)                          (renderer/diff_gaussian_rasterizer_advanced.py:139-146)
+ *   BACKGROUND  render = clamp(image + (1 - alpha) * bg)             (..._background.py:130-141)
+ *   NORMAL      + normal = normalize(Depth2Normal(rays_o + depth * rays_d)) * 0.5 * alpha + 0.5, with the
+ *               gradients of normal and depth cut where alpha <= 0.99 (..._normal.py:172-201)
+ *   SHADING     + point-light Lambert shading of albedo = image / (alpha + 1e-6) and the composite
+ *               fg * alpha + (1 - alpha) * bg (..._shading.py:174-213; material/gaussian_material.py:70-104);
+ *               pred_normal (the rendered per-Gaussian normals, used detached) replaces the depth normal
+ *               as the shading normal when given (..._shading.py:195-197).
+ * Layouts: image / pred_normal / render / normal / their gradients (V,3,H,W); depth, alpha (V,1,H,W);
+ * rays_o, rays_d, bg, d_bg (V,H,W,3); light (V,3); all device fp32, contiguous.  Backward recomputes the forward
+ * from the same inputs; g_* may be NULL (= zeros); d_bg may be NULL. */
+#define B200SPLAT_POST_PLAIN 0
+#define B200SPLAT_POST_BACKGROUND 1
+#define B200SPLAT_POST_NORMAL 2
+#define B200SPLAT_POST_SHADING 3
+#define B200SPLAT_SHADE_ALBEDO 0
+#define B200SPLAT_SHADE_TEXTURELESS 1
+#define B200SPLAT_SHADE_DIFFUSE 2
+typedef struct b200splat_postprocess_args {
+    int32_t V;
+    int32_t H;
+    int32_t W;
+    int32_t mode;    /* B200SPLAT_POST_*  */
+    int32_t shading; /* B200SPLAT_SHADE_* (mode SHADING) */
+    const float* image;
+    const float* depth;
+    const float* alpha;
+    const float* rays_o;
+    const float* rays_d;
+    const float* bg;
+    const float* light;
+    const float* pred_normal;
+    float ambient[3]; /* material ambient_light_color */
+    float diffuse[3]; /* material diffuse_light_color */
+    /* forward outputs */
+    float* render;
+    float* normal;    /* modes NORMAL, SHADING */
+    float* depth_out; /* optional copy of depth (the output whose gradient is masked) */
+    /* backward: upstream gradients in, gradients of the rasterizer outputs and of bg out */
+    const float* g_render;
+    const float* g_normal;
+    const float* g_depth;
+    float* d_image;
+    float* d_depth;
+    float* d_alpha;
+    float* d_bg;
+    void* scratch; /* modes NORMAL, SHADING: >= b200splat_postprocess_scratch_bytes(V,H,W) */
+    size_t scratch_bytes;
+    b200splat_stream stream;
+} b200splat_postprocess_args;
+size_t b200splat_postprocess_scratch_bytes(int32_t V, int32_t H, int32_t W);
+int b200splat_postprocess_forward(const b200splat_postprocess_args* args);
+int b200splat_postprocess_backward(const b200splat_postprocess_args* args);
+
 /* ---- mark_visible: replaces markVisible (GaussianRasterizer.markVisible) ------------------- */
 int b200splat_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
                            const float* projmatrix, uint8_t* present, b200splat_stream stream);

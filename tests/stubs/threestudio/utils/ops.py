@@ -30,3 +30,16 @@ def get_cam_info_gaussian(c2w, fovx, fovy, znear, zfar):
 
 def dot(x, y):
     return torch.sum(x * y, -1, keepdim=True)
+
+
+def get_activation(name):
+    """threestudio.utils.ops.get_activation restated for the names the reference's material uses
+    (material/gaussian_material.py:9, :115): only needed so the file imports."""
+    if name is None or str(name).lower() == "none":
+        return lambda x: x
+    name = str(name).lower()
+    table = {"sigmoid": torch.sigmoid, "tanh": torch.tanh, "exp": torch.exp, "relu": torch.relu,
+             "softplus": torch.nn.functional.softplus}
+    if name not in table:
+        raise ValueError(f"unknown activation {name}")
+    return table[name]

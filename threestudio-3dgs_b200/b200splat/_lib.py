@@ -106,6 +106,19 @@ class BatchBackwardArgs(C.Structure):
     ]
 
 
+class PostprocessArgs(C.Structure):
+    _fields_ = [
+        ("V", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("mode", C.c_int32), ("shading", C.c_int32),
+        ("image", C.c_void_p), ("depth", C.c_void_p), ("alpha", C.c_void_p), ("rays_o", C.c_void_p),
+        ("rays_d", C.c_void_p), ("bg", C.c_void_p), ("light", C.c_void_p), ("pred_normal", C.c_void_p),
+        ("ambient", C.c_float * 3), ("diffuse", C.c_float * 3),
+        ("render", C.c_void_p), ("normal", C.c_void_p), ("depth_out", C.c_void_p),
+        ("g_render", C.c_void_p), ("g_normal", C.c_void_p), ("g_depth", C.c_void_p),
+        ("d_image", C.c_void_p), ("d_depth", C.c_void_p), ("d_alpha", C.c_void_p), ("d_bg", C.c_void_p),
+        ("scratch", C.c_void_p), ("scratch_bytes", C.c_size_t), ("stream", C.c_void_p),
+    ]
+
+
 class P2PArgs(C.Structure):
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("bufs", C.c_void_p * 8), ("signals", C.c_void_p * 8),
                 ("n_segments", C.c_int32), ("seg_offset", C.c_int64 * 16), ("seg_count", C.c_int64 * 16),
@@ -134,6 +147,9 @@ SYMBOLS = {
     "b200splat_binning_capacity": (C.c_int64, [C.c_size_t]),
     "b200splat_forward_batched": (C.c_int, [C.POINTER(BatchForwardArgs)]),
     "b200splat_backward_batched": (C.c_int, [C.POINTER(BatchBackwardArgs)]),
+    "b200splat_postprocess_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "b200splat_postprocess_forward": (C.c_int, [C.POINTER(PostprocessArgs)]),
+    "b200splat_postprocess_backward": (C.c_int, [C.POINTER(PostprocessArgs)]),
     "b200splat_mark_visible": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200splat_dist2_workspace_bytes": (C.c_size_t, [C.c_int32]),
     "b200splat_dist2": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

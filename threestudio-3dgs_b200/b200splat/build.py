@@ -26,6 +26,7 @@ SOURCES = {
     "scan_sort.cu": [],
     "render.cu": [],
     "extra.cu": [],
+    "postops.cu": [],
     "preprocess_bwd.cu": [],
     "knn.cu": [],
     "p2p.cu": [],

@@ -269,6 +269,9 @@ static PinnedSlot& pinned() {
 
 using namespace b200splat;
 
+// error reporting for the other translation units that export C-ABI entry points (postops.cu, adam.cu)
+int b200splat_set_error(int code, const char* msg) { return fail(code, "%s", msg); }
+
 static int check_extra(int n_extra, const void* features, bool has_out) {
     if (n_extra < 0 || n_extra > EXT_FLOATS)
         return fail(B200SPLAT_ERR_INVALID, "n_extra must be in [0, %d]", EXT_FLOATS);
