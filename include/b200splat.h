@@ -317,6 +317,8 @@ typedef struct b200splat_postprocess_args {
     void* scratch; /* modes NORMAL, SHADING: >= b200splat_postprocess_scratch_bytes(V,H,W) */
     size_t scratch_bytes;
     b200splat_stream stream;
+    const int32_t* shading_per_view; /* HOST array of V B200SPLAT_SHADE_* (V <= 64) overriding `shading`, or NULL:
+                                        the reference's material draws the mode per view in training */
 } b200splat_postprocess_args;
 size_t b200splat_postprocess_scratch_bytes(int32_t V, int32_t H, int32_t W);
 int b200splat_postprocess_forward(const b200splat_postprocess_args* args);

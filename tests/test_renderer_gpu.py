@@ -1,0 +1,161 @@
+"""GPU: ``B200GaussianBatchRenderer.batch_forward`` (one batched raster call + one fused post-op launch) against the
+composition the reference runs per view -- the single-view operator (parity-checked against the oracle in
+test_parity_gpu.py) followed by the reference's post-ops (oracle/postops.py, pinned to the reference files) -- on the
+same ``batch`` dict, for every renderer variant it mirrors."""
+import random
+import types
+
+import pytest
+import torch
+
+from b200splat import scenes
+from oracle import postops as PO
+from util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+OUT_TOL, GRAD_TOL = 1e-4, 1e-3
+SH_C0 = 0.28209479177387814
+
+
+class _Geometry:
+    def __init__(self, sc, pred_normal, seed):
+        mk = lambda t: t.cuda().clone().requires_grad_(True)
+        self.get_xyz, self.get_opacity, self.get_scaling = mk(sc.means3D), mk(sc.opacities), mk(sc.scales)
+        self.get_rotation, self.get_features = mk(sc.rotations), mk(sc.shs)
+        g = torch.Generator().manual_seed(seed)
+        self.get_normal = mk(torch.nn.functional.normalize(torch.randn(sc.means3D.shape[0], 3, generator=g), dim=-1))
+        self.cfg = types.SimpleNamespace(pred_normal=pred_normal)
+        self.active_sh_degree = sc.sh_degree
+
+    def leaves(self):
+        return dict(xyz=self.get_xyz, opacity=self.get_opacity, scaling=self.get_scaling, rotation=self.get_rotation,
+                    features=self.get_features, normal=self.get_normal)
+
+
+def _batch(V, H, W, seed):
+    cams = scenes.sds_cameras(V, H, W, seed=seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    c2ws = []
+    for cam in cams:
+        c2w = torch.inverse(cam.viewmatrix.t())
+        c2w[:3, 1:3] *= -1
+        c2ws.append(c2w)
+    rays_d = torch.nn.functional.normalize(torch.randn(V, H, W, 3, generator=g) * 0.3 + torch.tensor([0.0, 1.0, 0.0]),
+                                           dim=-1)
+    rays_o = torch.stack([cam.campos for cam in cams])[:, None, None, :].expand(V, H, W, 3).contiguous()
+    batch = dict(c2w=torch.stack(c2ws).cuda(), fovy=torch.tensor([c.fovy for c in cams]).cuda(), height=H, width=W,
+                 rays_o=rays_o.cuda(), rays_d=rays_d.cuda(), light_positions=(torch.randn(V, 3, generator=g) * 2).cuda())
+    return batch, cams
+
+
+def _weights(V, H, W, seed):
+    g = torch.Generator().manual_seed(seed)
+    return {k: torch.randn(V, H, W, c, generator=g) / (H * W) for k, c in
+            (("comp_rgb", 3), ("comp_normal", 3), ("comp_pred_normal", 3), ("comp_depth", 1), ("comp_mask", 1))}
+
+
+def _loss(outputs, wts, dev):
+    return sum((outputs[k] * w.to(dev)).sum() for k, w in wts.items() if k in outputs)
+
+
+@pytest.mark.parametrize("variant,pred_normal,train", [("plain", False, False), ("advanced", False, True),
+                                                        ("background", False, True), ("normal", False, True),
+                                                        ("normal", True, True), ("shading", False, True),
+                                                        ("shading", True, False)])
+def test_batch_forward_matches_the_per_view_composition(variant, pred_normal, train):
+    from b200splat.renderer import B200GaussianBatchRenderer, _settings
+    from diff_gaussian_rasterization import GaussianRasterizer
+    P, H, W, V = 5000, 64, 80, 3
+    sc = scenes.make_scene(P, 1, 0.8, seed=201)
+    batch, cams = _batch(V, H, W, 202)
+    wts = _weights(V, H, W, 203)
+    bg_map = torch.rand(V, H, W, 3, generator=torch.Generator().manual_seed(204)).cuda().requires_grad_(True)
+    bgt = torch.tensor([1.0, 1.0, 1.0], device="cuda")
+
+    class Ren(B200GaussianBatchRenderer):
+        pass
+
+    ren = Ren()
+    ren.variant, ren.training, ren.background_tensor = variant, train, bgt
+    ren.geometry = _Geometry(sc, pred_normal, 205)
+    ren.background = lambda dirs: bg_map
+    mat = types.SimpleNamespace(ambient_light_color=torch.tensor([0.1, 0.1, 0.1]),
+                                diffuse_light_color=torch.tensor([0.9, 0.9, 0.9]), ambient_only=False, training=train,
+                                cfg=types.SimpleNamespace(diffuse_prob=0.75, textureless_prob=0.5, soft_shading=False))
+    ren.material = mat
+    random.seed(7)
+    out = ren.batch_forward(batch)
+    _loss(out, wts, "cuda").backward()
+    got_grads = {k: t.grad.clone() for k, t in ren.geometry.leaves().items() if t.grad is not None}
+    got_bg = None if bg_map.grad is None else bg_map.grad.clone()
+    bg_map.grad = None
+
+    # ---- expected: the reference's per-view loop (same random call sequence for the material) -----------------------
+    random.seed(7)
+    geo = _Geometry(sc, pred_normal, 205)
+    exp = {k: [] for k in ("comp_rgb", "comp_normal", "comp_pred_normal", "comp_depth", "comp_mask")}
+    m2_grads, radii_all = [], []
+    m2s = []
+    for v, cam in enumerate(cams):
+        # invert_bg_prob = 1: never inverted in training, always in eval (renderer/diff_gaussian_rasterizer.py:59-64)
+        raster_bg = (bgt if train else 1.0 - bgt) if variant in ("plain", "advanced", "normal") else bgt * 0
+        # the camera is rebuilt from batch["c2w"] / batch["fovy"] exactly as the reference's loop does
+        # (renderer/gaussian_batch_renderer.py:23-49 -> get_cam_info_gaussian)
+        rs = _settings(batch, v, raster_bg, 1, "cuda")
+        m2 = torch.zeros(P, 3, device="cuda", requires_grad=True)
+        m2s.append(m2)
+        kw = dict(means3D=geo.get_xyz, opacities=geo.get_opacity, scales=geo.get_scaling, rotations=geo.get_rotation,
+                  cov3D_precomp=None)
+        image, radii, depth, alpha = GaussianRasterizer(raster_settings=rs)(means2D=m2, shs=geo.get_features,
+                                                                            colors_precomp=None, **kw)
+        radii_all.append(radii)
+        pred = None
+        if pred_normal:
+            pred = GaussianRasterizer(raster_settings=rs)(means2D=torch.zeros_like(m2), shs=geo.get_normal.unsqueeze(1),
+                                                          colors_precomp=None, **kw)[0]
+        shading = "diffuse"
+        if variant == "shading":
+            if train:
+                shading = "albedo" if random.random() > 0.75 else ("textureless" if random.random() < 0.5 else "diffuse")
+        mode = {"plain": PO.MODE_PLAIN, "advanced": PO.MODE_PLAIN, "background": PO.MODE_BACKGROUND,
+                "normal": PO.MODE_NORMAL, "shading": PO.MODE_SHADING}[variant]
+        post = PO.postprocess_view(mode, image.cpu(), depth.cpu(), alpha.cpu(), batch["rays_o"][v].cpu(),
+                                   batch["rays_d"][v].cpu(), bg_map[v].cpu(), batch["light_positions"][v].cpu(),
+                                   mat.ambient_light_color, mat.diffuse_light_color, shading,
+                                   None if pred is None else pred.cpu())
+        exp["comp_rgb"].append(post["render"].permute(1, 2, 0))
+        if variant in ("normal", "shading"):
+            exp["comp_normal"].append(post["normal"].permute(1, 2, 0))
+            if pred is not None:
+                exp["comp_pred_normal"].append(pred.cpu().permute(1, 2, 0))
+        if variant not in ("plain", "background"):
+            exp["comp_depth"].append(post["depth"].permute(1, 2, 0))
+            exp["comp_mask"].append(alpha.cpu().permute(1, 2, 0))
+    exp = {k: torch.stack(v) for k, v in exp.items() if v}
+    _loss(exp, wts, "cpu").backward()
+
+    assert set(exp) <= set(out), (sorted(exp), sorted(out))
+    for k, ref in exp.items():
+        assert out[k].shape == ref.shape, (k, out[k].shape, ref.shape)
+        err = float((out[k].detach().cpu() - ref.detach()).abs().max())
+        assert err <= OUT_TOL, f"{variant}.{k}: {err}"
+    for k, t in geo.leaves().items():
+        if t.grad is None:
+            assert k not in got_grads or float(got_grads[k].abs().max()) == 0.0, k
+            continue
+        assert rel_err(got_grads[k], t.grad) <= GRAD_TOL, f"{variant} grad {k}: {rel_err(got_grads[k], t.grad)}"
+    if bg_map.grad is not None:
+        assert rel_err(got_bg, bg_map.grad) <= GRAD_TOL
+    for v in range(V):
+        assert torch.equal(out["radii"][v], radii_all[v])
+        assert torch.equal(out["visibility_filter"][v], radii_all[v] > 0)
+        if not pred_normal:
+            assert rel_err(out["viewspace_points"][v].grad, m2s[v].grad) <= GRAD_TOL
+    # the unchanged update_states statistics (geometry/gaussian_base.py:815-819, :845-851) run on the outputs
+    accum, denom = torch.zeros(P, 1, device="cuda"), torch.zeros(P, 1, device="cuda")
+    for v in range(V):
+        vis = out["visibility_filter"][v]
+        accum[vis] += torch.norm(out["viewspace_points"][v].grad[vis, :2], dim=-1, keepdim=True)
+        denom[vis] += 1
+    assert float(denom.sum()) == float(sum(int((r > 0).sum()) for r in radii_all))

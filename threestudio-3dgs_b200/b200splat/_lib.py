@@ -116,6 +116,7 @@ class PostprocessArgs(C.Structure):
         ("g_render", C.c_void_p), ("g_normal", C.c_void_p), ("g_depth", C.c_void_p),
         ("d_image", C.c_void_p), ("d_depth", C.c_void_p), ("d_alpha", C.c_void_p), ("d_bg", C.c_void_p),
         ("scratch", C.c_void_p), ("scratch_bytes", C.c_size_t), ("stream", C.c_void_p),
+        ("shading_per_view", C.POINTER(C.c_int32)),
     ]
 
 

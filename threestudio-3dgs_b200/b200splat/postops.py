@@ -29,6 +29,12 @@ SHADINGS = {"albedo": 0, "textureless": 1, "diffuse": 2}
 def _args(mode, shading, image, depth, alpha, rays_o, rays_d, bg, light, pred_normal, ambient, diffuse):
     V, _, H, W = image.shape
     a = _lib.PostprocessArgs()
+    if isinstance(shading, (list, tuple)):      # per-view modes
+        if len(shading) != V:
+            raise ValueError("one shading mode per view expected")
+        a._keep = (C.c_int32 * V)(*shading)
+        a.shading_per_view = a._keep
+        shading = shading[0]
     a.V, a.H, a.W, a.mode, a.shading = V, H, W, mode, shading
     a.image, a.depth, a.alpha = image.data_ptr(), depth.data_ptr(), alpha.data_ptr()
     a.rays_o, a.rays_d, a.bg = ops._ptr(rays_o), ops._ptr(rays_d), ops._ptr(bg)
@@ -93,9 +99,10 @@ def postprocess_views(mode: str, image, depth, alpha, *, bg=None, rays_o=None, r
                       pred_normal: Optional[torch.Tensor] = None, shading: str = "diffuse",
                       ambient: Sequence[float] = (0.1, 0.1, 0.1), diffuse: Sequence[float] = (0.9, 0.9, 0.9)):
     """image (V,3,H,W), depth / alpha (V,1,H,W) as returned by ``ViewBatchRasterizer``; bg / rays_o / rays_d
-    (V,H,W,3); light_positions (V,3); pred_normal (V,3,H,W) rendered per-Gaussian normals (used detached).
+    (V,H,W,3); light_positions (V,3); pred_normal (V,3,H,W) rendered per-Gaussian normals (used detached); shading: one mode or a list of V modes.
     Returns dict(render (V,3,H,W) clamped, normal (V,3,H,W) | None, depth (V,1,H,W))."""
-    m, s = MODES[mode], SHADINGS[shading]
+    m = MODES[mode]
+    s = [SHADINGS[x] for x in shading] if isinstance(shading, (list, tuple)) else SHADINGS[shading]
     if m in (1, 3) and bg is None:
         raise ValueError(f"mode {mode!r} needs bg")
     if m >= 2 and (rays_o is None or rays_d is None):

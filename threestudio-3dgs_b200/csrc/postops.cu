@@ -17,6 +17,7 @@
 
 namespace b200splat {
 
+constexpr int POST_MAX_PER_VIEW = 64;
 struct PostTab {
     int V, H, W, mode, shading;
     const float* image;   // (V,3,H,W)
@@ -28,6 +29,8 @@ struct PostTab {
     const float* light;   // (V,3)
     const float* pred;    // (V,3,H,W) or null
     float ambient[3], diffuse[3];
+    int per_view_shading;              // != 0: shading_v[view] instead of `shading`
+    uint8_t shading_v[POST_MAX_PER_VIEW];
     // forward outputs
     float* render;        // (V,3,H,W)
     float* normal;        // (V,3,H,W)
@@ -115,8 +118,9 @@ __device__ __forceinline__ void pixel_forward(const PostTab& t, int v, int y, in
         px.tl = v3(dl * t.diffuse[0] + t.ambient[0], dl * t.diffuse[1] + t.ambient[1], dl * t.diffuse[2] + t.ambient[2]);
         const V3 albc = v3(fminf(fmaxf(px.alb.x, 0.f), 1.f), fminf(fmaxf(px.alb.y, 0.f), 1.f),
                            fminf(fmaxf(px.alb.z, 0.f), 1.f));
-        if (t.shading == SHADE_ALBEDO) px.fg = px.alb;
-        else if (t.shading == SHADE_TEXTURELESS) px.fg = px.tl;
+        const int shading = t.per_view_shading ? (int)t.shading_v[v] : t.shading;
+        if (shading == SHADE_ALBEDO) px.fg = px.alb;
+        else if (shading == SHADE_TEXTURELESS) px.fg = px.tl;
         else px.fg = v3(albc.x * px.tl.x, albc.y * px.tl.y, albc.z * px.tl.z);
         const V3 bgv = ld3(t.bg + 3 * p);
         px.pre = px.fg * px.alpha + bgv * (1.0f - px.alpha);
@@ -175,9 +179,10 @@ __global__ void __launch_bounds__(256) postprocess_backward_local_kernel(const _
         d_al = dot3(g_pre, px.fg - bgv);
         d_bg = g_pre * (1.0f - al);
         V3 g_alb = v3(0.f, 0.f, 0.f), g_tl = v3(0.f, 0.f, 0.f);
-        if (t.shading == SHADE_ALBEDO) {
+        const int shading = t.per_view_shading ? (int)t.shading_v[v] : t.shading;
+        if (shading == SHADE_ALBEDO) {
             g_alb = g_fg;
-        } else if (t.shading == SHADE_TEXTURELESS) {
+        } else if (shading == SHADE_TEXTURELESS) {
             g_tl = g_fg;
         } else {
             const V3 albc = v3(fminf(fmaxf(px.alb.x, 0.f), 1.f), fminf(fmaxf(px.alb.y, 0.f), 1.f),
@@ -264,6 +269,16 @@ static int fill_tab(const b200splat_postprocess_args* a, PostTab* t) {
     t->image = a->image, t->depth = a->depth, t->alpha = a->alpha, t->rays_o = a->rays_o, t->rays_d = a->rays_d;
     t->bg = a->bg, t->light = a->light, t->pred = a->mode == POST_SHADING ? a->pred_normal : nullptr;
     for (int c = 0; c < 3; ++c) t->ambient[c] = a->ambient[c], t->diffuse[c] = a->diffuse[c];
+    if (a->shading_per_view && a->mode == POST_SHADING) {
+        if (a->V > POST_MAX_PER_VIEW)
+            return b200splat_set_error(B200SPLAT_ERR_INVALID, "shading_per_view supports at most 64 views per call");
+        t->per_view_shading = 1;
+        for (int v = 0; v < a->V; ++v) {
+            if (a->shading_per_view[v] < SHADE_ALBEDO || a->shading_per_view[v] > SHADE_DIFFUSE)
+                return b200splat_set_error(B200SPLAT_ERR_INVALID, "unknown per-view shading");
+            t->shading_v[v] = (uint8_t)a->shading_per_view[v];
+        }
+    }
     return B200SPLAT_OK;
 }
 
