@@ -324,6 +324,51 @@ size_t b200splat_postprocess_scratch_bytes(int32_t V, int32_t H, int32_t W);
 int b200splat_postprocess_forward(const b200splat_postprocess_args* args);
 int b200splat_postprocess_backward(const b200splat_postprocess_args* args);
 
+/* ---- fused activation-backward + Adam step on the rasterizer's gradient buffer --------------------------------
+ * The reference optimises RAW parameters with torch.optim.Adam(lr=0, eps=1e-15), one group per tensor
+ * (geometry/gaussian_base.py:470-525; per-step lr schedule :539-572), through the activations exp (scaling),
+ * sigmoid (opacity), F.normalize (rotation) and clip(-color_clip, color_clip) (features_dc)
+ * (geometry/gaussian_base.py:240-248, :371-400).  This entry point takes the gradients with respect to the
+ * ACTIVATED values -- the backward's outputs, i.e. the fields of the packed all-reduce buffer -- applies the
+ * activation Jacobians and one Adam step (amsgrad off, no weight decay) to the raw parameters and their
+ * exp_avg (m_*) / exp_avg_sq (v_*) states, in place.  lr order: xyz, f_dc, f_rest, opacity, scaling, rotation.
+ * step is the 1-based step count of this update.  rotation and g_rotations must be 16-byte aligned. */
+typedef struct b200splat_adam_args {
+    int32_t P;
+    int32_t M; /* SH coefficients per channel of g_shs: features_dc holds 1, features_rest M-1 */
+    float* xyz;           /* (P,3)     */
+    float* features_dc;   /* (P,1,3)   */
+    float* features_rest; /* (P,M-1,3), NULL when M == 1 */
+    float* opacity;       /* (P,1) raw */
+    float* scaling;       /* (P,3) raw */
+    float* rotation;      /* (P,4) raw */
+    float* m_xyz;
+    float* m_features_dc;
+    float* m_features_rest;
+    float* m_opacity;
+    float* m_scaling;
+    float* m_rotation;
+    float* v_xyz;
+    float* v_features_dc;
+    float* v_features_rest;
+    float* v_opacity;
+    float* v_scaling;
+    float* v_rotation;
+    const float* g_means3D;   /* (P,3)   */
+    const float* g_shs;       /* (P,M,3) */
+    const float* g_opacities; /* (P,1)   */
+    const float* g_scales;    /* (P,3)   */
+    const float* g_rotations; /* (P,4)   */
+    double lr[6]; /* doubles, like the Python floats torch.optim.Adam computes 1 - beta and lr / (1 - beta^t) from */
+    double beta1;
+    double beta2;
+    float eps;
+    float color_clip;
+    int32_t step;
+    b200splat_stream stream;
+} b200splat_adam_args;
+int b200splat_adam_step(const b200splat_adam_args* args);
+
 /* ---- mark_visible: replaces markVisible (GaussianRasterizer.markVisible) ------------------- */
 int b200splat_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
                            const float* projmatrix, uint8_t* present, b200splat_stream stream);

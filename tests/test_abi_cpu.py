@@ -35,7 +35,8 @@ def test_struct_layouts_match_header_field_order():
                        ("b200splat_batch_forward_args", _lib.BatchForwardArgs),
                        ("b200splat_batch_backward_args", _lib.BatchBackwardArgs),
                        ("b200splat_forward_views", _lib.ForwardViews),
-                       ("b200splat_postprocess_args", _lib.PostprocessArgs)):
+                       ("b200splat_postprocess_args", _lib.PostprocessArgs),
+                       ("b200splat_adam_args", _lib.AdamArgs)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), txt, flags=re.S).group(1)
         fields = [re.sub(r"\[.*\]", "", re.split(r"[\s\*]+", d.strip())[-1]) for d in body.split(";") if d.strip()]
         assert fields == [f[0] for f in cls._fields_], cname

@@ -120,6 +120,17 @@ class PostprocessArgs(C.Structure):
     ]
 
 
+_ADAM_TENSORS = ("xyz", "features_dc", "features_rest", "opacity", "scaling", "rotation")
+
+
+class AdamArgs(C.Structure):
+    _fields_ = ([("P", C.c_int32), ("M", C.c_int32)] + [(n, C.c_void_p) for n in _ADAM_TENSORS] +
+                [("m_" + n, C.c_void_p) for n in _ADAM_TENSORS] + [("v_" + n, C.c_void_p) for n in _ADAM_TENSORS] +
+                [(n, C.c_void_p) for n in ("g_means3D", "g_shs", "g_opacities", "g_scales", "g_rotations")] +
+                [("lr", C.c_double * 6), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_float),
+                 ("color_clip", C.c_float), ("step", C.c_int32), ("stream", C.c_void_p)])
+
+
 class P2PArgs(C.Structure):
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("bufs", C.c_void_p * 8), ("signals", C.c_void_p * 8),
                 ("n_segments", C.c_int32), ("seg_offset", C.c_int64 * 16), ("seg_count", C.c_int64 * 16),
@@ -151,6 +162,7 @@ SYMBOLS = {
     "b200splat_postprocess_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "b200splat_postprocess_forward": (C.c_int, [C.POINTER(PostprocessArgs)]),
     "b200splat_postprocess_backward": (C.c_int, [C.POINTER(PostprocessArgs)]),
+    "b200splat_adam_step": (C.c_int, [C.POINTER(AdamArgs)]),
     "b200splat_mark_visible": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200splat_dist2_workspace_bytes": (C.c_size_t, [C.c_int32]),
     "b200splat_dist2": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -27,6 +27,7 @@ SOURCES = {
     "render.cu": [],
     "extra.cu": [],
     "postops.cu": [],
+    "adam.cu": [],
     "preprocess_bwd.cu": [],
     "knn.cu": [],
     "p2p.cu": [],
