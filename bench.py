@@ -186,6 +186,95 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def aux_kernels(dev, P, M, H, W, V, cams, params, hbm_gbs):
+    """The kernels either side of the rasterizer, timed alone with CUDA events on the launch stream on
+    the bench workload's shapes: fused post-ops (shading mode, V views), fused activation-backward + Adam, and the
+    cost of 3 extra feature channels riding the raster pass.  Algorithmic bytes per launch as stated in DESIGN.md."""
+    import torch
+    from b200splat import batched
+    from b200splat.optim import FusedGaussianAdam
+    from b200splat.postops import postprocess_views
+    means3D, shs, opac, scales, rots = params
+
+    def timed(fn, iters=10):
+        for _ in range(3):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    def row(name, ms, nbytes, note):
+        ach = nbytes / (ms * 1e-3) / 1e9
+        return {"kernel": name, "bound": "hbm", "avg_ms": ms, "achieved": ach, "peak": hbm_gbs, "unit": "GB/s",
+                "frac": ach / hbm_gbs, "work_per_launch": nbytes, "note": note}
+
+    out = []
+    try:
+        g = torch.Generator(device="cpu").manual_seed(5)
+        rnd = lambda *s: torch.rand(*s, generator=g).to(dev)
+        img, dep, alp = rnd(V, 3, H, W).requires_grad_(True), (rnd(V, 1, H, W) * 3).requires_grad_(True), \
+            rnd(V, 1, H, W).requires_grad_(True)
+        rays_o, rays_d, bgm, light = rnd(V, H, W, 3), torch.nn.functional.normalize(rnd(V, H, W, 3), dim=-1), \
+            rnd(V, H, W, 3), rnd(V, 3) * 3
+        post = lambda: postprocess_views("shading", img, dep, alp, bg=bgm, rays_o=rays_o, rays_d=rays_d,
+                                         light_positions=light)
+        t_f = timed(post)
+        res = post()
+        gr, gn, gd = torch.randn_like(res["render"]), torch.randn_like(res["normal"]), torch.randn_like(res["depth"])
+
+        def fb():
+            r = post()
+            torch.autograd.backward([r["render"], r["normal"], r["depth"]], [gr, gn, gd])
+            img.grad = dep.grad = alp.grad = None
+        t_fb = timed(fb)
+        px = V * H * W
+        out.append(row("postprocess_fwd", t_f, 84 * px, f"shading mode, {V} views {H}x{W}: 14 floats in, 7 out per pixel"))
+        out.append(row("postprocess_bwd", max(t_fb - t_f, 1e-6), 116 * px,
+                       "two kernels (local + stencil gather); 21 floats in, 8 out per pixel; the 9-float scratch "
+                       "round trip is not counted as algorithmic; time = (fwd+bwd) - fwd through autograd"))
+        raw = dict(xyz=means3D.clone(), f_dc=shs[:, :1].contiguous(), f_rest=shs[:, 1:].contiguous(),
+                   opacity=torch.logit(opac.clamp(1e-4, 1 - 1e-4)), scaling=torch.log(scales), rotation=rots.clone())
+        opt = FusedGaussianAdam(raw, dict.fromkeys(("xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation"), 1e-4))
+        grads = dict(means3D=torch.randn_like(means3D), shs=torch.randn_like(shs), opacities=torch.randn_like(opac),
+                     scales=torch.randn_like(scales), rotations=torch.randn_like(rots))
+        t_a = timed(lambda: opt.step(grads))
+        out.append(row("adam_step", t_a, 7 * 4 * (11 + 3 * M) * P,
+                       "activation backward + Adam, 2 kernels: gradients read, parameter / exp_avg / exp_avg_sq read+written"))
+        del opt, raw, grads
+        # 3 extra feature channels in the same raster pass: step time with and without them
+        ws = batched.BatchWorkspace(V, P, H, W, dev)
+        extra = torch.rand(P, 3, generator=g).to(dev)
+        eo = [torch.empty(3, H, W, device=dev) for _ in range(V)]
+        pg = [(torch.randn(3, H, W, device=dev) / (H * W), None, None) for _ in range(V)]
+        eg = [torch.randn(3, H, W, device=dev) / (H * W) for _ in range(V)]
+        new = lambda *s: torch.empty(*s, device=dev)
+        outg = {"means3D": new(P, 3), "opacities": new(P, 1), "scales": new(P, 3), "rotations": new(P, 4),
+                "shs": new(P, M, 3), "extra_features": new(P, 3)}
+        nr, ov = batched.forward_batched(ws, cams, means3D, shs, None, opac, scales, rots, sync=True)
+        ws._alloc_binning(int(max(nr) * 1.25) + 4096)
+
+        def plain():
+            batched.forward_batched(ws, cams, means3D, shs, None, opac, scales, rots)
+            batched.backward_batched(ws, cams, means3D, shs, None, opac, scales, rots, pg, outg)
+
+        def with_extra():
+            batched.forward_batched(ws, cams, means3D, shs, None, opac, scales, rots, extra_features=extra, extra_out=eo)
+            batched.backward_batched(ws, cams, means3D, shs, None, opac, scales, rots, pg, outg, extra_features=extra,
+                                     extra_grads=eg)
+        t_p, t_e = timed(plain, 5), timed(with_extra, 5)
+        out.append({"kernel": "extra_channels_step", "avg_ms": t_e, "plain_step_ms": t_p, "overhead_frac": t_e / t_p - 1.0,
+                    "note": f"eager fwd+bwd of {V} views with 3 extra channels in the same pass vs without; the "
+                            "reference pays a second full rasterizer pass (+100 %) for them"})
+    except Exception as exc:   # reported in the JSON line, never hidden
+        out.append({"error": repr(exc)})
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
@@ -527,6 +616,10 @@ def main():
                                    f"{info['of_tiles']} tiles scaled x{info['of_tiles'] / info['tiles']:.1f}; "
                                    f"{info['cpu_seconds']:.1f} s of CPU work")}
 
+    aux = None
+    if rank == 0 and N == 1:
+        aux = aux_kernels(dev, P, M, H, W, V, cams, (means3D, shs, opac, scales, rots), peaks()["hbm_gbs"])
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": args.steps,
@@ -549,6 +642,7 @@ def main():
                                            "(the reference's unchanged loop), same host traffic"},
             "gpu_launches": launches,
             "roofline": roof, "kernels": kernels, "cpu_baseline": cpu_base,
+            "aux_kernels": aux,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -279,6 +279,10 @@ def forward_views(cam: Cam, st: ForwardState):
         return buf[off:off + nb].view(dtype).clone()
 
     R, P = st.num_rendered, st.P
+    if R and P:
+        # a batched view's state carries the binning CAPACITY as num_rendered: only the first point_offsets[P-1]
+        # pair words are live, the rest of the buffer is uninitialised
+        R = min(R, int(view(st.geom, v.point_offsets, P, torch.int32)[-1].item()))
     words = view(st.binning, v.keys_sorted, R, torch.int64) if R else torch.empty(0, dtype=torch.int64, device=dev)
     depths = view(st.geom, v.depths, P, torch.float32)
     # sorted pair words are (tile << 32 | gaussian); upstream's key = (tile << 32) | float_bits(depth[gaussian])
