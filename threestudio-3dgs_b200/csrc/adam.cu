@@ -7,8 +7,8 @@
 // Adam's foreach path runs ~12 more over 4 tensors per group.  Here one pass does both: each thread takes one
 // Gaussian's gradients with respect to the activated values -- exactly what preprocess-backward wrote into the packed
 // buffer (and what the all-reduce left there) -- applies the activation Jacobians in registers, and updates
-// exp_avg / exp_avg_sq / parameter in place.  A second, purely elementwise kernel handles the 3(M-1) higher-order SH
-// coefficients per Gaussian.  HBM-bound: 4 (13 + 3M) + 7 * 4 (11 + 3M) bytes per Gaussian.
+// exp_avg / exp_avg_sq / parameter in place.  Two launches: one elementwise kernel over every tensor whose activation is
+// elementwise, one quaternion kernel.  HBM-bound: 7 * 4 * (11 + 3M) bytes per Gaussian.
 //
 // Arithmetic mirrors torch.optim.Adam's single-tensor path (amsgrad off, weight decay 0, maximize off):
 //   exp_avg.lerp_(g, 1 - b1); exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2);
@@ -36,78 +36,72 @@ __device__ __forceinline__ void adam1(float& p, float& m, float& v, float g, flo
     p = p - step_size * (m / denom);
 }
 
-template <int N>
-__device__ __forceinline__ void adam_vec(float* p, float* m, float* v, const float (&g)[N], size_t base, float step_size,
-                                         const AdamTab& t) {
-#pragma unroll
-    for (int c = 0; c < N; ++c) {
-        float pp = p[base + c], mm = m[base + c], vv = v[base + c];
-        adam1(pp, mm, vv, g[c], step_size, t);
-        p[base + c] = pp, m[base + c] = mm, v[base + c] = vv;
+// Every parameter but the quaternion has an ELEMENTWISE activation (identity, clip, sigmoid, exp), so the (P,3) / (P,1)
+// / (P,K,3) tensors are walked as flat arrays, one element per thread, fully coalesced: a thread-per-Gaussian layout
+// reads and writes them with a 12-byte stride and measured 3x slower (194 vs ~65 us for 1 M Gaussians).
+//   element space: [xyz 3P | f_dc 3P | opacity P | scaling 3P | f_rest 3(M-1)P]
+__global__ void __launch_bounds__(256) adam_elementwise_kernel(const __grid_constant__ AdamTab t) {
+    const size_t P = (size_t)t.P;
+    const size_t n_xyz = 3 * P, n_dc = 3 * P, n_op = P, n_sc = 3 * P, per = 3 * (size_t)(t.M - 1), n_rest = per * P;
+    const size_t total = n_xyz + n_dc + n_op + n_sc + n_rest;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        float *p, *m, *v;
+        float g, step;
+        size_t k = e;
+        if (k < n_xyz) {                         // position: identity
+            p = t.xyz + k, m = t.m_xyz + k, v = t.v_xyz + k;
+            g = __ldg(t.g_means3D + k), step = t.step_size[0];
+        } else if ((k -= n_xyz) < n_dc) {        // SH DC: features_dc.clip(-c, c) passes the gradient where |raw| <= c
+            p = t.f_dc + k, m = t.m_f_dc + k, v = t.v_f_dc + k;
+            const size_t i = k / 3;
+            const float raw = *p;
+            g = (raw >= -t.color_clip && raw <= t.color_clip) ? __ldg(t.g_shs + i * 3 * t.M + (k - 3 * i)) : 0.f;
+            step = t.step_size[1];
+        } else if ((k -= n_dc) < n_op) {         // opacity = sigmoid(raw)
+            p = t.opacity + k, m = t.m_opacity + k, v = t.v_opacity + k;
+            const float o = 1.0f / (1.0f + expf(-*p));
+            g = __ldg(t.g_opacities + k) * o * (1.0f - o), step = t.step_size[3];
+        } else if ((k -= n_op) < n_sc) {         // scaling = exp(raw)
+            p = t.scaling + k, m = t.m_scaling + k, v = t.v_scaling + k;
+            g = __ldg(t.g_scales + k) * expf(*p), step = t.step_size[4];
+        } else {                                 // higher-order SH: features_rest (P, M-1, 3) <- g_shs (P, M, 3)[:, 1:, :]
+            k -= n_sc;
+            p = t.f_rest + k, m = t.m_f_rest + k, v = t.v_f_rest + k;
+            const size_t i = k / per;
+            g = __ldg(t.g_shs + i * 3 * t.M + 3 + (k - i * per)), step = t.step_size[2];
+        }
+        float pp = *p, mm = *m, vv = *v;
+        adam1(pp, mm, vv, g, step, t);
+        *p = pp, *m = mm, *v = vv;
     }
 }
 
-// one thread per Gaussian: xyz 3 | f_dc 3 | opacity 1 | scaling 3 | rotation 4
-__global__ void __launch_bounds__(256) adam_gaussian_kernel(const __grid_constant__ AdamTab t) {
+// rotation = q / max(|q|, 1e-12): one thread per quaternion, 16-byte accesses
+__global__ void __launch_bounds__(256) adam_rotation_kernel(const __grid_constant__ AdamTab t) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= t.P) return;
-    {   // position: identity activation
-        const float g[3] = {__ldg(t.g_means3D + 3 * (size_t)i), __ldg(t.g_means3D + 3 * (size_t)i + 1),
-                            __ldg(t.g_means3D + 3 * (size_t)i + 2)};
-        adam_vec<3>(t.xyz, t.m_xyz, t.v_xyz, g, 3 * (size_t)i, t.step_size[0], t);
+    float4* qp = reinterpret_cast<float4*>(t.rotation) + i;
+    float4* mp = reinterpret_cast<float4*>(t.m_rotation) + i;
+    float4* vp = reinterpret_cast<float4*>(t.v_rotation) + i;
+    const float4 q = *qp;
+    const float4 gq = __ldg(reinterpret_cast<const float4*>(t.g_rotations) + i);
+    const float n = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+    float g[4];
+    if (n >= 1e-12f) {
+        const float inv = 1.0f / n;
+        const float hx = q.x * inv, hy = q.y * inv, hz = q.z * inv, hw = q.w * inv;
+        const float d = hx * gq.x + hy * gq.y + hz * gq.z + hw * gq.w;
+        g[0] = (gq.x - hx * d) * inv, g[1] = (gq.y - hy * d) * inv, g[2] = (gq.z - hz * d) * inv,
+        g[3] = (gq.w - hw * d) * inv;
+    } else {
+        g[0] = gq.x * 1e12f, g[1] = gq.y * 1e12f, g[2] = gq.z * 1e12f, g[3] = gq.w * 1e12f;
     }
-    {   // SH DC: features_dc.clip(-c, c) -> the gradient passes where |raw| <= c
-        const float* gs = t.g_shs + (size_t)i * 3 * t.M;
-        float g[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float raw = t.f_dc[3 * (size_t)i + c];
-            g[c] = (raw >= -t.color_clip && raw <= t.color_clip) ? __ldg(gs + c) : 0.f;
-        }
-        adam_vec<3>(t.f_dc, t.m_f_dc, t.v_f_dc, g, 3 * (size_t)i, t.step_size[1], t);
-    }
-    {   // opacity = sigmoid(raw)
-        const float raw = t.opacity[i];
-        const float o = 1.0f / (1.0f + expf(-raw));
-        const float g[1] = {__ldg(t.g_opacities + i) * o * (1.0f - o)};
-        adam_vec<1>(t.opacity, t.m_opacity, t.v_opacity, g, (size_t)i, t.step_size[3], t);
-    }
-    {   // scaling = exp(raw)
-        float g[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) g[c] = __ldg(t.g_scales + 3 * (size_t)i + c) * expf(t.scaling[3 * (size_t)i + c]);
-        adam_vec<3>(t.scaling, t.m_scaling, t.v_scaling, g, 3 * (size_t)i, t.step_size[4], t);
-    }
-    {   // rotation = q / max(|q|, 1e-12)
-        const float4 q = *reinterpret_cast<const float4*>(t.rotation + 4 * (size_t)i);
-        const float4 gq = __ldg(reinterpret_cast<const float4*>(t.g_rotations + 4 * (size_t)i));
-        const float n = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
-        float g[4];
-        if (n >= 1e-12f) {
-            const float inv = 1.0f / n;
-            const float hx = q.x * inv, hy = q.y * inv, hz = q.z * inv, hw = q.w * inv;
-            const float d = hx * gq.x + hy * gq.y + hz * gq.z + hw * gq.w;
-            g[0] = (gq.x - hx * d) * inv, g[1] = (gq.y - hy * d) * inv, g[2] = (gq.z - hz * d) * inv,
-            g[3] = (gq.w - hw * d) * inv;
-        } else {
-            g[0] = gq.x * 1e12f, g[1] = gq.y * 1e12f, g[2] = gq.z * 1e12f, g[3] = gq.w * 1e12f;
-        }
-        adam_vec<4>(t.rotation, t.m_rotation, t.v_rotation, g, 4 * (size_t)i, t.step_size[5], t);
-    }
-}
-
-// higher-order SH coefficients: element e of features_rest (P, M-1, 3) <- g_shs (P, M, 3)[:, 1:, :]
-__global__ void __launch_bounds__(256) adam_sh_rest_kernel(const __grid_constant__ AdamTab t) {
-    const int per = 3 * (t.M - 1);
-    const size_t n = (size_t)t.P * per;
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
-        const size_t i = e / per;
-        const int j = (int)(e - i * per);
-        const float g = __ldg(t.g_shs + i * 3 * t.M + 3 + j);
-        float p = t.f_rest[e], m = t.m_f_rest[e], v = t.v_f_rest[e];
-        adam1(p, m, v, g, t.step_size[2], t);
-        t.f_rest[e] = p, t.m_f_rest[e] = m, t.v_f_rest[e] = v;
-    }
+    float4 pp = q, mm = *mp, vv = *vp;
+    adam1(pp.x, mm.x, vv.x, g[0], t.step_size[5], t);
+    adam1(pp.y, mm.y, vv.y, g[1], t.step_size[5], t);
+    adam1(pp.z, mm.z, vv.z, g[2], t.step_size[5], t);
+    adam1(pp.w, mm.w, vv.w, g[3], t.step_size[5], t);
+    *qp = pp, *mp = mm, *vp = vv;
 }
 
 }  // namespace b200splat
@@ -129,8 +123,9 @@ extern "C" int b200splat_adam_step(const b200splat_adam_args* a) {
         if (!p) return b200splat_set_error(B200SPLAT_ERR_INVALID, "null parameter / state / gradient pointer");
     if (rest && (!a->features_rest || !a->m_features_rest || !a->v_features_rest))
         return b200splat_set_error(B200SPLAT_ERR_INVALID, "M > 1 needs features_rest and its state");
-    if ((reinterpret_cast<uintptr_t>(a->rotation) | reinterpret_cast<uintptr_t>(a->g_rotations)) & 15)
-        return b200splat_set_error(B200SPLAT_ERR_INVALID, "rotation / g_rotations must be 16-byte aligned");
+    if ((reinterpret_cast<uintptr_t>(a->rotation) | reinterpret_cast<uintptr_t>(a->g_rotations) |
+         reinterpret_cast<uintptr_t>(a->m_rotation) | reinterpret_cast<uintptr_t>(a->v_rotation)) & 15)
+        return b200splat_set_error(B200SPLAT_ERR_INVALID, "rotation, its state and g_rotations must be 16-byte aligned");
     AdamTab t;
     t.P = a->P, t.M = a->M;
     t.xyz = a->xyz, t.f_dc = a->features_dc, t.f_rest = a->features_rest, t.opacity = a->opacity;
@@ -149,14 +144,11 @@ extern "C" int b200splat_adam_step(const b200splat_adam_args* a) {
     t.eps = a->eps, t.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
     t.color_clip = a->color_clip;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(a->stream);
-    adam_gaussian_kernel<<<(a->P + 255) / 256, 256, 0, st>>>(t);
-    count_launch();
-    if (rest) {
-        const size_t n = (size_t)a->P * 3 * (a->M - 1);
-        const unsigned blocks = (unsigned)((n + 255) / 256 < (size_t)NUM_SMS * 16 ? (n + 255) / 256 : (size_t)NUM_SMS * 16);
-        adam_sh_rest_kernel<<<blocks, 256, 0, st>>>(t);
-        count_launch();
-    }
+    const size_t total = (size_t)a->P * (10 + 3 * (size_t)(a->M - 1));
+    const size_t want = (total + 255) / 256, cap = (size_t)NUM_SMS * 32;
+    adam_elementwise_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(t);
+    adam_rotation_kernel<<<(a->P + 255) / 256, 256, 0, st>>>(t);
+    count_launch(2);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return b200splat_set_error(B200SPLAT_ERR_CUDA, cudaGetErrorString(e));
     return B200SPLAT_OK;

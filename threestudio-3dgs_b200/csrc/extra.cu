@@ -29,24 +29,25 @@ pad_extra_kernel(int P, int n_extra, const float* __restrict__ extra, float4* __
     ext4[i] = make_float4(e[0], e[1], e[2], e[3]);
 }
 
+// flat over the 4 P floats of the padded records: thread e sums element e of every view's record array (and zeroes it
+// again under the self-cleaning protocol); fully coalesced 4-byte accesses
 __global__ void __launch_bounds__(256)
 extra_backward_kernel(const __grid_constant__ BatchTab tab, float* __restrict__ dL_dextra, int accumulate, int g_begin,
                       int g_end) {
-    const int i = g_begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= g_end) return;
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    const size_t e0 = (size_t)g_begin * EXT_FLOATS, e1 = (size_t)g_end * EXT_FLOATS;
+    const size_t e = e0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= e1) return;
+    float s = 0.f;
     for (int v = 0; v < tab.V; ++v) {
-        if (tab.v[v].radii[i] <= 0) continue;   // never touched by render backward: still all-zero
-        float4* g = reinterpret_cast<float4*>(tab.v[v].gradext) + i;
-        const float4 x = *g;
-        s.x += x.x, s.y += x.y, s.z += x.z, s.w += x.w;
-        if (tab.clean_scratch) *g = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* g = tab.v[v].gradext + e;
+        s += *g;
+        if (tab.clean_scratch) *g = 0.f;
     }
-    const float e[EXT_FLOATS] = {s.x, s.y, s.z, s.w};
-    float* dst = dL_dextra + (size_t)i * tab.n_extra;
-#pragma unroll
-    for (int c = 0; c < EXT_FLOATS; ++c)
-        if (c < tab.n_extra) dst[c] = accumulate ? dst[c] + e[c] : e[c];
+    const int c = (int)(e & (EXT_FLOATS - 1));
+    if (c < tab.n_extra) {
+        float* dst = dL_dextra + (e >> 2) * tab.n_extra + c;
+        *dst = accumulate ? *dst + s : s;
+    }
 }
 
 cudaError_t launch_pad_extra(int P, int n_extra, const float* extra, float4* ext4, cudaStream_t st) {
@@ -62,7 +63,8 @@ cudaError_t launch_extra_backward(const BatchTab& tab, float* dL_dextra, int acc
     if (g_end <= 0 || g_end > tab.P) g_end = tab.P;
     if (g_begin < 0) g_begin = 0;
     if (g_begin >= g_end) return cudaSuccess;
-    extra_backward_kernel<<<(g_end - g_begin + 255) / 256, 256, 0, st>>>(tab, dL_dextra, accumulate, g_begin, g_end);
+    const size_t n = (size_t)(g_end - g_begin) * EXT_FLOATS;
+    extra_backward_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tab, dL_dextra, accumulate, g_begin, g_end);
     count_launch();
     return cudaGetLastError();
 }
