@@ -546,7 +546,7 @@ render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
                 const float power = -0.5f * (cA[k] * ddx[k] * ddx[k] + cC[k] * ddy[k] * ddy[k]) - cB[k] * ddx[k] * ddy[k];
                 G[k] = __expf(power);
                 alpha[k] = fminf(ALPHA_MAX, op[k] * G[k]);
-                inv1m[k] = 1.0f / (1.0f - alpha[k]);
+                inv1m[k] = __fdividef(1.0f, 1.0f - alpha[k]);   // MUFU.RCP + FMUL; 1 - alpha is in [0.01, 1]
                 hit[k] = has && (q < my_last) && (power <= 0.0f) && (alpha[k] >= ALPHA_MIN);
                 cr[k] = q1.w, cg[k] = q2.x, cb[k] = q2.y, cd[k] = q1.z;
             }
