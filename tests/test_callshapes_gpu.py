@@ -1,0 +1,126 @@
+"""GPU: the call shapes either side of the operator that the BASELINE configs name but the single-op parity tests do
+not exercise as a whole --
+
+  * the spacetime variant's call (renderer/diff_gaussian_rasterizer_st.py:135-150): NON-LEAF ``means3D`` (cubic
+    B-spline of control knots, translation basis of geometry/spline_utils.py:109-119), non-leaf ``rotations``
+    (normalize(q + dq[frame])), ``colors_precomp`` and ``shs=None`` -- gradients must reach the control knots;
+  * a whole training step: activations -> batched rasterizer -> loss -> backward -> fused Adam on the gradient
+    buffer, three steps, against the reference's sequence (per-view oracle rasterizer + autograd through the
+    activations + torch.optim.Adam with the reference's groups, oracle/optim.py).
+"""
+import pytest
+import torch
+
+from b200splat import scenes
+from oracle import torch_oracle as O
+from oracle.optim import GROUPS, OracleGaussianAdam
+from util import cuda_settings, oracle_settings, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _bspline_translation(knots: torch.Tensor, u: float) -> torch.Tensor:
+    """Uniform cubic B-spline of 4 control knots (P,4,3) at u in [0,1): coefficients of spline_utils.py:112-117."""
+    uu, uuu, oos = u * u, u * u * u, 1.0 / 6.0
+    c = [oos - 0.5 * u + 0.5 * uu - oos * uuu, 4.0 * oos - uu + 0.5 * uuu, oos + 0.5 * u + 0.5 * uu - 0.5 * uuu,
+         oos * uuu]
+    return sum(ci * knots[:, i] for i, ci in enumerate(c))
+
+
+def test_spacetime_call_shape_gradients_reach_the_control_knots():
+    from diff_gaussian_rasterization import GaussianRasterizer
+    P, H, W = 4000, 64, 64
+    sc = scenes.make_scene(P, 0, 0.8, seed=301)
+    cam = scenes.sds_cameras(1, H, W, seed=302)[0]
+    s = oracle_settings(cam, 0)
+    g = torch.Generator().manual_seed(303)
+    knots0 = sc.means3D[:, None, :] + 0.02 * torch.randn(P, 4, 3, generator=g)
+    dq0 = 0.05 * torch.randn(P, 4, generator=g)
+    rgb0 = torch.rand(P, 3, generator=g)
+    grads = scenes.pixel_grads(H, W, 304)
+
+    def run(dev, raster):
+        knots, dq, rgb, q = (t.to(dev).clone().requires_grad_(True) for t in (knots0, dq0, rgb0, sc.rotations))
+        means3D = _bspline_translation(knots, 0.37)
+        rots = torch.nn.functional.normalize(q + dq)
+        color, depth, alpha = raster(means3D, rots, rgb)
+        gc, gd, ga = (t.to(dev) for t in grads)
+        ((color * gc).sum() + (depth * gd).sum() + (alpha * ga).sum()).backward()
+        return dict(color=color.detach().cpu(), knots=knots.grad.cpu(), dq=dq.grad.cpu(), rgb=rgb.grad.cpu(),
+                    q=q.grad.cpu())
+
+    def cuda_raster(m3, rots, rgb):
+        m2 = torch.zeros_like(m3, requires_grad=True)
+        c, _, d, a = GaussianRasterizer(raster_settings=cuda_settings(s))(
+            means3D=m3, means2D=m2, shs=None, colors_precomp=rgb, opacities=sc.opacities.cuda(),
+            scales=sc.scales.cuda(), rotations=rots, cov3D_precomp=None)
+        return c, d, a
+
+    def oracle_raster(m3, rots, rgb):
+        from oracle.api import GaussianRasterizer as OR
+        c, _, d, a = OR(raster_settings=s)(means3D=m3, means2D=torch.zeros_like(m3), shs=None, colors_precomp=rgb,
+                                           opacities=sc.opacities, scales=sc.scales, rotations=rots,
+                                           cov3D_precomp=None)
+        return c, d, a
+
+    cu, orc = run("cuda", cuda_raster), run("cpu", oracle_raster)
+    assert float((cu["color"] - orc["color"]).abs().mean()) < 1e-5
+    for k in ("knots", "dq", "rgb", "q"):
+        assert rel_err(cu[k], orc[k]) <= 1e-3, f"{k}: {rel_err(cu[k], orc[k])}"
+    assert float(cu["knots"].abs().max()) > 0
+
+
+def test_three_training_steps_match_the_reference_sequence():
+    from b200splat.batched import ViewBatchRasterizer
+    from b200splat.optim import FusedGaussianAdam
+    P, deg, H, W, V = 3000, 1, 48, 48, 2
+    sc = scenes.make_scene(P, deg, 0.8, seed=311)
+    cams = scenes.sds_cameras(V, H, W, seed=312)
+    M = sc.shs.shape[1]
+    raw0 = dict(xyz=sc.means3D.clone(), f_dc=sc.shs[:, :1].clone(), f_rest=sc.shs[:, 1:].clone(),
+                opacity=torch.logit(sc.opacities.clamp(1e-4, 1 - 1e-4)), scaling=torch.log(sc.scales),
+                rotation=sc.rotations * 1.3)
+    lrs = dict(xyz=1.6e-4, f_dc=2.5e-3, f_rest=1.25e-4, opacity=5e-2, scaling=5e-3, rotation=1e-3)
+    target = [torch.rand(3, H, W, generator=torch.Generator().manual_seed(320 + v)) for v in range(V)]
+
+    # ---- product path: torch activations -> batched CUDA rasterizer -> autograd -> fused Adam on the gradients
+    dev = {k: v.clone().cuda() for k, v in raw0.items()}
+    opt = FusedGaussianAdam(dev, lrs)
+    rast = ViewBatchRasterizer(V, P, H, W)
+    settings = [cuda_settings(oracle_settings(c, deg)) for c in cams]
+    tgt = torch.stack(target).cuda()
+    for it in range(3):
+        act = dict(means3D=dev["xyz"].clone().requires_grad_(True),
+                   shs=torch.cat((dev["f_dc"], dev["f_rest"]), 1).requires_grad_(True),
+                   opacities=torch.sigmoid(dev["opacity"]).requires_grad_(True),
+                   scales=torch.exp(dev["scaling"]).requires_grad_(True),
+                   rotations=torch.nn.functional.normalize(dev["rotation"]).requires_grad_(True))
+        m2 = torch.zeros(V, P, 3, device="cuda", requires_grad=True)
+        color, radii, depth, alpha = rast(settings, act["means3D"], m2, act["opacities"], shs=act["shs"],
+                                          scales=act["scales"], rotations=act["rotations"])
+        loss = ((color - tgt) ** 2).mean() + 0.1 * alpha.mean()
+        loss.backward()
+        opt.step({k: v.grad.contiguous() for k, v in act.items()})
+    assert not rast.check_overflow()
+
+    # ---- reference sequence on the CPU oracle
+    from oracle.api import GaussianRasterizer as OR
+    orc = OracleGaussianAdam(raw0, lrs)
+    tgt_c = torch.stack(target)
+    for it in range(3):
+        orc.optimizer.zero_grad(set_to_none=True)
+        act = orc.activated()
+        cols, als = [], []
+        for v, c in enumerate(cams):
+            col, _, _, al = OR(raster_settings=oracle_settings(c, deg))(
+                means3D=act["means3D"], means2D=torch.zeros(P, 3), shs=act["shs"], colors_precomp=None,
+                opacities=act["opacities"], scales=act["scales"], rotations=act["rotations"], cov3D_precomp=None)
+            cols.append(col), als.append(al)
+        loss = ((torch.stack(cols) - tgt_c) ** 2).mean() + 0.1 * torch.stack(als).mean()
+        loss.backward()
+        orc.optimizer.step()
+    for k in GROUPS:
+        step = (orc.p[k].detach() - raw0[k]).abs().max()
+        err = (dev[k].cpu() - orc.p[k].detach()).abs().max()
+        # Adam normalises the step: the comparison is made relative to the distance the parameters moved
+        assert float(err) <= 2e-2 * float(step) + 1e-7, f"{k}: moved {float(step):.3e}, differs by {float(err):.3e}"

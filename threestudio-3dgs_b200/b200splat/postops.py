@@ -99,7 +99,8 @@ def postprocess_views(mode: str, image, depth, alpha, *, bg=None, rays_o=None, r
                       pred_normal: Optional[torch.Tensor] = None, shading: str = "diffuse",
                       ambient: Sequence[float] = (0.1, 0.1, 0.1), diffuse: Sequence[float] = (0.9, 0.9, 0.9)):
     """image (V,3,H,W), depth / alpha (V,1,H,W) as returned by ``ViewBatchRasterizer``; bg / rays_o / rays_d
-    (V,H,W,3); light_positions (V,3); pred_normal (V,3,H,W) rendered per-Gaussian normals (used detached); shading: one mode or a list of V modes.
+    (V,H,W,3); light_positions (V,3); pred_normal (V,3,H,W) rendered per-Gaussian normals (used detached);
+    shading: one mode or a list of V modes (the reference's material draws it per view in training).
     Returns dict(render (V,3,H,W) clamped, normal (V,3,H,W) | None, depth (V,1,H,W))."""
     m = MODES[mode]
     s = [SHADINGS[x] for x in shading] if isinstance(shading, (list, tuple)) else SHADINGS[shading]

@@ -4,10 +4,10 @@
 // Adam parameter groups (geometry/gaussian_base.py:470-525: torch.optim.Adam(l, lr=0.0, eps=1e-15), one lr per group,
 // scheduled per step :539-572) and feeds the rasterizer ACTIVATED values (exp, sigmoid, F.normalize, clip:
 // geometry/gaussian_base.py:240-248, :371-411).  After backward, autograd walks the activations back (~10 kernels) and
-// Adam's foreach path runs ~12 more over 4 tensors per group.  Here one pass does both: each thread takes one
-// Gaussian's gradients with respect to the activated values -- exactly what preprocess-backward wrote into the packed
-// buffer (and what the all-reduce left there) -- applies the activation Jacobians in registers, and updates
-// exp_avg / exp_avg_sq / parameter in place.  Two launches: one elementwise kernel over every tensor whose activation is
+// Adam's foreach path runs ~12 more over 4 tensors per group.  Here one pass does both: it takes the gradients with
+// respect to the activated values -- exactly what preprocess-backward wrote into the packed buffer (and what the
+// all-reduce left there) -- applies the activation Jacobians in registers, and updates exp_avg / exp_avg_sq /
+// parameter in place.  Two launches: one elementwise kernel over every tensor whose activation is
 // elementwise, one quaternion kernel.  HBM-bound: 7 * 4 * (11 + 3M) bytes per Gaussian.
 //
 // Arithmetic mirrors torch.optim.Adam's single-tensor path (amsgrad off, weight decay 0, maximize off):
