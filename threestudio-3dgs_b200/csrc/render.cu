@@ -417,7 +417,7 @@ __device__ __forceinline__ int reduce_slot4(int lane) {
 }
 
 template <bool BULK, bool EXT>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, EXT ? 16 : 1)   // EXT: cap at 128 registers (150 uncapped -> 13 warps per SM)
 render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
     __shared__ __align__(16) float4 s_rec[STAGES][BATCH * 3];
     __shared__ __align__(16) float4 s_ext[STAGES][EXT ? BATCH : 1];
