@@ -89,3 +89,70 @@ def test_product_path_refuses_cpu_tensors():
     import diff_gaussian_rasterization as dgr
     for mod in (ops, dgr):
         assert "oracle" not in inspect.getsource(mod), "product code must not reference the oracle"
+
+
+def test_new_entry_points_validate_arguments_before_launching():
+    from b200splat import _lib
+    lib = _lib.lib
+    assert lib.b200splat_postprocess_forward(None) == -1
+    p = _lib.PostprocessArgs()
+    assert lib.b200splat_postprocess_forward(C.byref(p)) == -1 and b"positive" in lib.b200splat_last_error()
+    p.V, p.H, p.W, p.mode = 1, 4, 4, 9
+    assert lib.b200splat_postprocess_forward(C.byref(p)) == -1 and b"mode" in lib.b200splat_last_error()
+    p.mode, p.image, p.depth, p.alpha = 3, 16, 16, 16            # shading mode without rays / bg / light
+    assert lib.b200splat_postprocess_backward(C.byref(p)) == -1 and b"rays" in lib.b200splat_last_error()
+    assert lib.b200splat_postprocess_scratch_bytes(4, 512, 512) == 4 * 512 * 512 * 36
+    a = _lib.AdamArgs()
+    a.P, a.M, a.step = 8, 1, 0
+    assert lib.b200splat_adam_step(C.byref(a)) == -1 and b"1-based" in lib.b200splat_last_error()
+    a.step = 1
+    assert lib.b200splat_adam_step(C.byref(a)) == -1 and b"null" in lib.b200splat_last_error()
+    a.P = 0
+    assert lib.b200splat_adam_step(C.byref(a)) == 0               # nothing to do, nothing launched
+    f = _lib.ForwardArgs()
+    f.P, f.M, f.shs, f.n_extra = 4, 1, 16, 7
+    f.scales = f.rotations = f.out_color = f.out_depth = f.out_alpha = f.image_buffer = 16
+    f.image_bytes = 1 << 30
+    f.cam.image_height = f.cam.image_width = 16
+    f.cam.bg = f.cam.viewmatrix = f.cam.projmatrix = f.cam.campos = 16
+    assert lib.b200splat_forward(C.byref(f)) == -1 and b"n_extra" in lib.b200splat_last_error()
+    assert _lib.launch_count() == 0
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/b200splat.h compiles as C99 (no C++ in the boundary) and a C program links the library and calls its
+    host-only entry points -- the binding a non-Python host would write."""
+    import shutil
+    import subprocess
+    from b200splat import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "b200splat.h"
+int main(void) {
+    b200splat_forward_args f;
+    b200splat_adam_args a;
+    b200splat_postprocess_args p;
+    memset(&f, 0, sizeof f); memset(&a, 0, sizeof a); memset(&p, 0, sizeof p);
+    if (b200splat_abi_version() != B200SPLAT_ABI_VERSION) return 1;
+    if (b200splat_geom_bytes(1000) == 0 || b200splat_backward_scratch_bytes(1000) < 64000) return 2;
+    if (b200splat_forward(&f) != B200SPLAT_ERR_INVALID || strlen(b200splat_last_error()) == 0) return 3;
+    if (b200splat_postprocess_forward(&p) != B200SPLAT_ERR_INVALID) return 4;
+    a.step = 1; a.M = 1;
+    if (b200splat_adam_step(&a) != B200SPLAT_OK) return 5;          /* P == 0: nothing to do */
+    if (b200splat_launch_count() != 0) return 6;
+    printf("abi %d ok\n", b200splat_abi_version());
+    return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    lib_dir = _lib.LIB_PATH.parent
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", f"-I{ROOT / 'include'}", str(src), "-o", str(exe),
+           f"-L{lib_dir}", "-l:libb200splat.so", f"-Wl,-rpath,{lib_dir}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
