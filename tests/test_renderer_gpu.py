@@ -159,3 +159,34 @@ def test_batch_forward_matches_the_per_view_composition(variant, pred_normal, tr
         accum[vis] += torch.norm(out["viewspace_points"][v].grad[vis, :2], dim=-1, keepdim=True)
         denom[vis] += 1
     assert float(denom.sum()) == float(sum(int((r > 0).sum()) for r in radii_all))
+
+
+def test_two_renders_before_backward_do_not_share_a_workspace():
+    """system/gaussian_zero123.py:212-235 renders twice per step and calls backward afterwards."""
+    from b200splat.renderer import B200GaussianBatchRenderer
+    P, H, W, V = 3000, 48, 48, 2
+    sc = scenes.make_scene(P, 0, 0.8, seed=221)
+    batch_a, _ = _batch(V, H, W, 222)
+    batch_b, _ = _batch(V, H, W, 223)
+
+    class Ren(B200GaussianBatchRenderer):
+        variant = "advanced"
+
+    ren = Ren()
+    ren.training, ren.background_tensor = True, torch.ones(3, device="cuda")
+    ren.geometry = _Geometry(sc, False, 224)
+    out_a = ren.batch_forward(batch_a)
+    out_b = ren.batch_forward(batch_b)               # same shape, first graph still alive
+    assert len(ren._b200_rasterizers[(V, P, H, W, "cuda:0")]) == 2
+    (out_a["comp_rgb"].sum() + out_b["comp_rgb"].sum()).backward()
+    g_two = ren.geometry.get_xyz.grad.clone()
+    # the same two renders one after the other
+    ren.geometry.get_xyz.grad = None
+    ren.batch_forward(batch_a)["comp_rgb"].sum().backward()
+    ren.batch_forward(batch_b)["comp_rgb"].sum().backward()
+    assert rel_err(g_two, ren.geometry.get_xyz.grad) <= 1e-4
+    assert all(not r.pending for r in ren._b200_rasterizers[(V, P, H, W, "cuda:0")])
+    with torch.no_grad():                             # inference never holds a workspace
+        for _ in range(6):
+            ren.batch_forward(batch_a)
+    assert len(ren._b200_rasterizers[(V, P, H, W, "cuda:0")]) == 2

@@ -426,6 +426,7 @@ class _RasterizeViews(torch.autograd.Function):
             ekw = dict(extra_features=ex_, extra_grads=None if ge is None else list(ge.unbind(0)))
         backward_batched(ws, ctx.cams, m3, sh_, cp_, op_, sc_, ro_, pgs, out, accumulate=False,
                          means2D_out=list(m2.unbind(0)), **ekw)
+        owner.pending = False
         return (None, None, out["means3D"], m2, out.get("shs"), out.get("colors_precomp"), out["opacities"],
                 out["scales"], out["rotations"], out.get("extra_features"))
 
@@ -443,6 +444,7 @@ class ViewBatchRasterizer(torch.nn.Module):
         self.ws = BatchWorkspace(views, P, H, W, torch.device(device))
         self.calibrated = False
         self.generation = 0
+        self.pending = False   # a forward with autograd enabled whose backward has not run yet owns the workspace
 
     def calibrate(self, cams, means3D, shs, colors_precomp, opacities, scales, rotations, headroom: float = 1.25,
                   **extra):
@@ -476,6 +478,9 @@ class ViewBatchRasterizer(torch.nn.Module):
         if means3D.shape[0] != ws.P:
             raise RuntimeError("number of Gaussians changed (densify/prune): build a new ViewBatchRasterizer")
         cams = [ops.make_cam(rs, means3D.device) for rs in raster_settings]
+        self.pending = torch.is_grad_enabled() and any(
+            t is not None and t.requires_grad for t in (means3D, means2D, opacities, shs, colors_precomp, scales,
+                                                        rotations, extra_features))
         out = _RasterizeViews.apply(self, cams, means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
                                     extra_features)
         return out if extra_features is not None else out[:4]

@@ -92,12 +92,22 @@ class B200GaussianBatchRenderer:
         return "albedo" if mat.ambient_only else "diffuse"
 
     def _rasterizer(self, V: int, P: int, H: int, W: int, device) -> ViewBatchRasterizer:
+        """A ViewBatchRasterizer (persistent workspace) for this shape whose last graph has been consumed.  Systems that
+        render twice before ``backward`` (system/gaussian_zero123.py:212-235: random-camera batch + reference view)
+        get a second instance instead of overwriting the first one's saved state."""
         key = (V, P, H, W, str(device))
         cache = self.__dict__.setdefault("_b200_rasterizers", {})
-        if key not in cache:
-            cache.clear()               # P changes at every densify / prune: keep one live workspace
-            cache[key] = ViewBatchRasterizer(V, P, H, W, device)
-        return cache[key]
+        for k in [k for k in cache if k[1] != P]:       # P changes at every densify / prune: drop stale workspaces
+            del cache[k]
+        pool = cache.setdefault(key, [])
+        for rast in pool:
+            if not rast.pending:
+                return rast
+        if len(pool) >= 4:
+            raise RuntimeError("B200GaussianBatchRenderer: 4 forward passes of the same shape are waiting for their "
+                               "backward; render under torch.no_grad() when no gradient is needed")
+        pool.append(ViewBatchRasterizer(V, P, H, W, device))
+        return pool[-1]
 
     def batch_forward(self, batch) -> Dict[str, Any]:
         pc = self.geometry
