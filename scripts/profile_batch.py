@@ -24,7 +24,11 @@ H, W = cams_h[0].image_height, cams_h[0].image_width
 pg = [tuple(to(g) for g in scenes.pixel_grads(H, W, 99 + v)) for v in range(V)]
 br = batched.BatchRenderer(m3.shape[0], sh.shape[1], H, W, dev, views=V)
 br.calibrate(cams, m3, sh, None, op, sc, ro)
-for _ in range(iters):
+for i in range(iters):
+    if i == iters - 1:          # ncu --profile-from-start off captures only the last step
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
     br.step(cams, m3, sh, None, op, sc, ro, pg)
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("ok", float(br.packed.buffer.abs().sum()), br.overflowed())

@@ -31,7 +31,10 @@ with open(f"{out_dir}/{tag}_ncu_launch_list.md", "w") as f:
 print("launch list:", len(tot), "kernels, total us", round(total))
 
 # ---- full capture: one row per kernel instance
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+# rep: an .ncu-rep, or the CSV of its raw page (`ncu -i rep --page raw --csv`, exported on the GPU box when the report
+# itself is too large to bring back)
+raw = open(rep).read() if rep.endswith(".csv") else \
+    subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rr = list(csv.reader(io.StringIO(raw))); hdr = rr[0]; units = rr[1]; idx = {h: i for i, h in enumerate(hdr)}
 keys = [("gpu__time_duration.sum", "us"), ("dram__bytes_read.sum", "dramR"), ("dram__bytes_write.sum", "dramW"),
         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"),
@@ -48,7 +51,7 @@ def to_bytes(v, u):
 traffic = {}
 with open(f"{out_dir}/{tag}_ncu_full_summary.md", "w") as f:
     f.write(f"# ncu --set full summary ({tag}), batched step of 4 views, headline workload (1M Gaussians, SH3, 512x512)\n\n"
-            "`ncu --set full --clock-control none --import-source on` on `scripts/profile_batch.py headline_1m_512_sh3 2 4`.\n"
+            "`ncu --set full --clock-control none --profile-from-start off` on `scripts/profile_batch.py headline_1m_512_sh3 3 4` (last step captured).\n"
             "One launch covers the 4 views of the step.  dram = dram__bytes_{read,write}.sum per launch.\n\n"
             "| kernel | us | DRAM read MB | DRAM write MB | DRAM % | SM % | issue % | warps % | regs | warp inst | top stalls |\n"
             "|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---|\n")
