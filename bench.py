@@ -50,8 +50,8 @@ def parse_args():
                          "3976/3927/3815/3640 renders/s -- the per-range handshakes and the SM slots the exchange "
                          "kernel takes from the compute cost more than the overlap returns)")
     ap.add_argument("--eager", action="store_true", help="launch the step from Python every time (no CUDA graph)")
-    ap.add_argument("--cpu-sample-tiles", type=int, default=0,
-                    help="tiles of the CPU-oracle sample (0: 512 for the cpu_baseline leg, 256 per reference-arm step)")
+    ap.add_argument("--no-configs", action="store_true",
+                    help="skip the short runs of the other BASELINE.json configurations (the `configs` array, N = 1 only)")
     return ap.parse_args()
 
 
@@ -113,10 +113,9 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_oracle_render_time(scene, cam, sample_tiles: int, threads: int):
-    """Seconds for ONE fwd+bwd render of the workload on the CPU oracle, measured on a bounded sample:
-    preprocess + key sort run on all P Gaussians; the per-tile blend (fwd + bwd) runs on an evenly spaced
-    subset of ``sample_tiles`` tiles and is scaled by (#tiles / #sampled)."""
+def cpu_oracle_render_time(scene, cam, threads: int):
+    """Wall-clock seconds of ONE complete fwd+bwd render of the workload on the CPU oracle: every Gaussian, every
+    tile, forward and backward -- nothing sampled, nothing scaled ("run once and say so")."""
     import torch
     from oracle import torch_oracle as O
     from b200splat import scenes
@@ -124,66 +123,104 @@ def cpu_oracle_render_time(scene, cam, sample_tiles: int, threads: int):
     s = O.Settings(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy, torch.ones(3), 1.0,
                    cam.viewmatrix, cam.projmatrix, scene.sh_degree, cam.campos, False, False)
     H, W = cam.image_height, cam.image_width
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        pre = O.preprocess(scene.means3D, scene.opacities, scene.scales, scene.rotations, None, scene.shs, None, s)
-        binned = O.bin_and_sort(pre, s)
-    t_front = time.perf_counter() - t0
-    d = O.derived_scalars(s)
-    T = d["grid_x"] * d["grid_y"]
-    n = max(1, min(sample_tiles, T))
-    tiles = [int(i * T / n) for i in range(n)]
     gc, gd, ga = scenes.pixel_grads(H, W, 7)
+    inputs = (scene.means3D, None, scene.shs, None, scene.opacities, scene.scales, scene.rotations, None)
     t0 = time.perf_counter()
-    with torch.no_grad():
-        out = O.render_forward(pre, binned, s, tiles=tiles)
+    out, pre, binned = O.rasterize_forward(*inputs, s)
     t_fwd = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    O.rasterize_backward((scene.means3D, None, scene.shs, None, scene.opacities, scene.scales, scene.rotations,
-                          None), s, pre, binned, out, gc, gd, ga, tiles=tiles)
-    t_bwd = time.perf_counter() - t0
-    # backward = per-tile part (scaled) + differentiable preprocess (not scaled); measured together, so
-    # scale only the tile share estimated from the forward ratio -- conservative: scale everything but
-    # t_front, which over-estimates CPU time slightly in the CPU's disfavour? No: keep it honest and
-    # scale only the tile loops; the preprocess-backward share is measured separately below.
-    t0 = time.perf_counter()
-    O.rasterize_backward((scene.means3D, None, scene.shs, None, scene.opacities, scene.scales, scene.rotations,
-                          None), s, pre, binned, out, gc, gd, ga, tiles=[])
-    t_bwd_pre = time.perf_counter() - t0
-    scale = T / n
-    total = t_front + t_fwd * scale + max(t_bwd - t_bwd_pre, 0.0) * scale + t_bwd_pre
-    return total, dict(t_front=t_front, t_fwd_sample=t_fwd, t_bwd_sample=t_bwd, t_bwd_pre=t_bwd_pre, tiles=n,
-                       of_tiles=T, cpu_seconds=t_front + t_fwd + t_bwd + t_bwd_pre)
+    O.rasterize_backward(inputs, s, pre, binned, out, gc, gd, ga)
+    total = time.perf_counter() - t0
+    return total, dict(t_fwd=t_fwd, t_bwd=total - t_fwd, tiles=int(binned["ranges"].shape[0]),
+                       num_rendered=int(binned["num_rendered"]))
 
 
 def run_reference(args):
     """Reference arm: the CPU oracle (kind "port" -- the reference's CUDA rasterizer is un-vendored and
-    cannot be built here) timed on the host cores, same workload/metric/unit."""
+    cannot be built here) on the host cores, same workload / metric / unit.  Each step is one COMPLETE
+    fwd+bwd render of one view (no tile sampling); `ms_per_step` is the measured mean wall-clock of the timed steps.
+    The run is bounded to about four minutes: if the first timed step shows that K steps would not fit, fewer steps
+    are timed and `steps` reports how many were."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
     from b200splat import scenes
     threads = os.cpu_count() or 1
+    t_start = time.perf_counter()
     scene, cams = scenes.make_workload(args.workload, views=1)
-    times = []
-    info = {}
-    for i in range(args.warmup + args.steps):
-        t, info = cpu_oracle_render_time(scene, cams[0], args.cpu_sample_tiles or 256, threads)
-        if i >= args.warmup:
-            times.append(t)
+    budget_s = 200.0
+    warm = min(args.warmup, 1)
+    for _ in range(warm):
+        cpu_oracle_render_time(scene, cams[0], threads)
+    times, info = [], {}
+    for i in range(args.steps):
+        t, info = cpu_oracle_render_time(scene, cams[0], threads)
+        times.append(t)
+        elapsed = time.perf_counter() - t_start
+        if i + 1 < args.steps and elapsed + t > budget_s:
+            break
     sec = sum(times) / len(times)
     val = 1.0 / sec
-    sample = (f"per step: preprocess+sort of all P, blend fwd+bwd on {info['tiles']} of {info['of_tiles']} tiles "
-              f"scaled x{info['of_tiles'] / info['tiles']:.1f}; {info['cpu_seconds']:.1f} s CPU work per step")
+    sample = (f"the whole workload per step: 1 view, all {scene.means3D.shape[0]} Gaussians, all {info['tiles']} tiles, "
+              f"forward + backward of the CPU oracle (no sampling, no scaling); {len(times)} timed steps after {warm} "
+              f"warm-up, {sum(times):.1f} s timed, {time.perf_counter() - t_start:.1f} s in total")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "steps": len(times), "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "views_per_step": 1, "device": "cpu"},
+            "config": {"workload": args.workload, "views_per_step": 1, "device": "cpu",
+                       "steps_requested": args.steps, "warmup_requested": args.warmup},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def measure_config(name, V, steps, warmup, dev):
+    """Short resident run of another BASELINE.json configuration on this GPU (the `configs` array of the bench line):
+    the same batched step, CUDA-graph replay, CUDA events on the launch stream."""
+    import torch
+    from b200splat import batched, ops, scenes
+    scene, cams_host = scenes.make_workload(name, views=V)
+    H, W = cams_host[0].image_height, cams_host[0].image_width
+    P, M = scene.means3D.shape[0], scene.shs.shape[1]
+    to = lambda t: t.to(dev).contiguous()
+    means3D, shs, opac, scales, rots = map(to, (scene.means3D, scene.shs, scene.opacities, scene.scales,
+                                                scene.rotations))
+    bg = torch.ones(3, device=dev)
+    cams = [ops.make_cam(_settings_like(c, bg, scene.sh_degree), dev) for c in cams_host]
+    pgrads = [tuple(to(g) for g in scenes.pixel_grads(H, W, 99 + v)) for v in range(V)]
+    renderer = batched.BatchRenderer(P, M, H, W, dev, views=V)
+    renderer.calibrate(cams, means3D, shs, None, opac, scales, rots)
+    graph = renderer.capture_step(cams, means3D, shs, None, opac, scales, rots, pgrads)
+    for _ in range(max(warmup, 3)):
+        graph.replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    ok = not renderer.overflowed()
+    nr = [int(x) for ws in renderer.ws for x in ws.num_rendered]
+    del graph, renderer
+    torch.cuda.empty_cache()
+    return {"workload": name, "value": V / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "views_per_step": V,
+            "steps": steps, "gaussians": P, "sh_degree": scene.sh_degree, "image": [H, W],
+            "pairs_per_view_at_calibration": int(sum(nr) / max(len(nr), 1)), "valid": ok}
+
+
+class _S:
+    pass
+
+
+def _settings_like(c, bg, sh_degree):
+    s = _S()
+    s.image_height, s.image_width, s.tanfovx, s.tanfovy = c.image_height, c.image_width, c.tanfovx, c.tanfovy
+    s.bg, s.scale_modifier, s.viewmatrix, s.projmatrix = bg, 1.0, c.viewmatrix, c.projmatrix
+    s.sh_degree, s.campos, s.prefiltered, s.debug = sh_degree, c.campos, False, False
+    return s
 
 
 def aux_kernels(dev, P, M, H, W, V, cams, params, hbm_gbs):
@@ -303,7 +340,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("B200SPLAT_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        # the caller's NCCL_DEBUG stands (the driver reads the communicator lines); NCCL's log goes to stderr so that
+        # stdout stays the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     N = world
     V = args.views_per_gpu
@@ -319,15 +358,8 @@ def main():
                                                 scene.rotations))
     bg = torch.ones(3, device=dev)
 
-    class S:  # settings-like
-        pass
-
     def dev_cam(c):
-        s = S()
-        s.image_height, s.image_width, s.tanfovx, s.tanfovy = c.image_height, c.image_width, c.tanfovx, c.tanfovy
-        s.bg, s.scale_modifier, s.viewmatrix, s.projmatrix = bg, 1.0, c.viewmatrix, c.projmatrix
-        s.sh_degree, s.campos, s.prefiltered, s.debug = scene.sh_degree, c.campos, False, False
-        return ops.make_cam(s, dev)
+        return ops.make_cam(_settings_like(c, bg, scene.sh_degree), dev)
 
     cams = [dev_cam(c) for c in cams_host]
     pgrads_host = [scenes.pixel_grads(H, W, 99 + rank * V + v) for v in range(V)]
@@ -336,9 +368,9 @@ def main():
     # place by one kernel per rank over NVLink peer memory (csrc/p2p.cu); --allreduce nccl uses NCCL instead
     p2p, allreduce_mode = None, ("none" if world == 1 else "nccl")
     use_p2p = args.allreduce == "p2p" or (args.allreduce == "auto" and world <= 4)
-    if world > 1 and use_p2p and P % 4 == 0:
+    if world > 1 and use_p2p:
         try:
-            p2p = bdist.P2PAllReduce(batched.PackedGrads.floats(P, M), P, dev)
+            p2p = bdist.P2PAllReduce(batched.PackedGrads.floats(P, M), batched.PackedGrads.padded(P), dev)
             allreduce_mode = "p2p_nvlink_kernel"
         except Exception as exc:
             print(f"bench: P2P all-reduce unavailable ({exc!r}); using NCCL", file=sys.stderr)
@@ -387,6 +419,37 @@ def main():
         else:
             bdist.allreduce_packed(packed.buffer, packed.max_radii)
 
+    def verify_exchange():
+        """After the timed region (N > 1): one more step WITHOUT the exchange, a copy of the local sums, then the
+        exchange as timed -- its result must be bit-identical on all ranks and equal to an independent NCCL SUM / MAX
+        of the copies (tolerance: the summation order over the ranks may differ, fp32)."""
+        if graph is not None and chunks == 1:
+            graph.replay()
+        else:
+            renderer.step(cams, means3D, shs, None, opac, scales, rots, pgrads)
+        torch.cuda.synchronize()
+        ref_sum, ref_max = packed.buffer.clone(), packed.max_radii.clone()
+        if p2p is not None:
+            p2p()
+        else:
+            bdist.allreduce_packed(packed.buffer, packed.max_radii)
+        dist.all_reduce(ref_sum, op=dist.ReduceOp.SUM)
+        dist.all_reduce(ref_max, op=dist.ReduceOp.MAX)
+        torch.cuda.synchronize()
+        scale = float(ref_sum.abs().max().clamp_min(1e-30))
+        err = float((packed.buffer - ref_sum).abs().max()) / scale
+        max_equal = bool(torch.equal(packed.max_radii, ref_max))
+        # bit-identical on every rank: compare two integer checksums of the raw words
+        words = packed.buffer.view(torch.int32).to(torch.int64)
+        chk = torch.stack([words.sum(), (words * (torch.arange(words.numel(), device=dev) % 8191 + 1)).sum(),
+                           packed.max_radii.view(torch.int32).to(torch.int64).sum()])
+        allchk = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(allchk, chk)
+        identical = all(bool(torch.equal(c, allchk[0])) for c in allchk)
+        nonzero = bool(ref_sum.abs().sum() > 0)
+        return {"ok": bool(err <= 2e-6 and max_equal and identical and nonzero), "max_rel_err_vs_nccl_sum": err,
+                "max_radii_equal": max_equal, "bit_identical_across_ranks": identical}
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -414,8 +477,10 @@ def main():
     if p2p is not None and p2p.failed():
         raise SystemExit("bench: the P2P all-reduce timed out waiting for a peer (invalid run)")
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    exchange_check = None
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        exchange_check = verify_exchange()
     total_ms = float(ms.item())
     ms_per_step = total_ms / args.steps
     value = N * V * args.steps / (total_ms / 1e3)
@@ -618,15 +683,28 @@ def main():
                 "avg_ms": dom["avg_ms"], "counters": cnt}
         if N == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            sec, info = cpu_oracle_render_time(scene, cams_host[0], args.cpu_sample_tiles or 512, threads)
+            t_cpu = [cpu_oracle_render_time(scene, cams_host[0], threads)[0] for _ in range(3)]
+            sec = statistics.median(t_cpu)
             cpu_base = {"value": 1.0 / sec, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": (f"1 view: preprocess+sort of all {P} Gaussians, blend fwd+bwd on {info['tiles']} of "
-                                   f"{info['of_tiles']} tiles scaled x{info['of_tiles'] / info['tiles']:.1f}; "
-                                   f"{info['cpu_seconds']:.1f} s of CPU work")}
+                        "sample": (f"3 complete fwd+bwd renders of one view of this workload on the CPU oracle (all {P} "
+                                   f"Gaussians, all tiles, nothing sampled or scaled), median; {sum(t_cpu):.1f} s of "
+                                   "CPU work")}
 
     aux = None
+    configs = None
     if rank == 0 and N == 1:
         aux = aux_kernels(dev, P, M, H, W, V, cams, (means3D, shs, opac, scales, rots), peaks()["hbm_gbs"])
+        if not args.no_configs and args.workload == DEFAULT_WORKLOAD:
+            # driver-run numbers for the other BASELINE.json configurations (short resident runs on this GPU)
+            del renderer, graph, vbr
+            torch.cuda.empty_cache()
+            configs = []
+            for name, v in (("config2_100k_512_sh0_b4", 4), ("config3_300k_512_sh0_b4", 4),
+                            ("config4_1m_256_sh3_b32", 32), ("stress_4m_1024_sh3_b64", 8)):
+                try:
+                    configs.append(measure_config(name, v, 3, 3, dev))
+                except Exception as exc:   # reported, never hidden
+                    configs.append({"workload": name, "error": repr(exc)})
 
     if rank == 0:
         line = {
@@ -650,8 +728,11 @@ def main():
                                            "(the reference's unchanged loop), same host traffic"},
             "gpu_launches": launches,
             "roofline": roof, "kernels": kernels, "cpu_baseline": cpu_base,
-            "aux_kernels": aux,
+            "aux_kernels": aux, "configs": configs,
         }
+        if exchange_check is not None:
+            line["exchange_verified"] = exchange_check["ok"]
+            line["exchange_check"] = exchange_check
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define B200SPLAT_ABI_VERSION 5
+#define B200SPLAT_ABI_VERSION 6
 
 #define B200SPLAT_OK 0
 #define B200SPLAT_ERR_INVALID -1   /* bad argument                                  */
@@ -210,6 +210,14 @@ typedef struct b200splat_batch_forward_args {
     const float* extra_features;  /* (P,n_extra) or NULL: see b200splat_forward_args */
     int32_t n_extra;
     float* const* out_extra;      /* V x (n_extra,H,W) */
+    /* Optional early overflow notice without a stream synchronisation: V 64-bit words of PINNED HOST memory
+     * (device-accessible by the same pointer: cudaHostAlloc / torch pin_memory).  The scan kernel -- the first
+     * point of the forward at which a view's pair count is known -- stores (notify_epoch << 32) | num_rendered of
+     * view v into pairs_notify[v] while the rest of the forward is still queued behind it; the host polls the word
+     * until it carries its epoch and compares the count with the capacity (count > capacity: the view's result is
+     * invalid, re-run with a larger buffer).  NULL: no notice. */
+    uint64_t* pairs_notify;
+    uint32_t notify_epoch;
 } b200splat_batch_forward_args;
 
 int b200splat_forward_batched(const b200splat_batch_forward_args* args);
@@ -462,6 +470,11 @@ int b200splat_p2p_allreduce(const b200splat_p2p_args* args);
 int b200splat_p2p_error(const void* own_signals, int32_t* flag_out);
 
 /* ---- misc ----------------------------------------------------------------------------------- */
+/* How the render kernels stage a tile's Gaussian records into shared memory: 0 = per-entry 16-byte cp.async
+ * (LDGSTS) arriving on the stage's mbarrier, 1 = cp.async.bulk (UBLKCP) with complete_tx on the mbarrier,
+ * -1 = the default (environment variable B200SPLAT_STAGING = "ldgsts" | "bulk", else the measured-faster one).
+ * Process-wide; takes effect at the next launch.  Returns the previous setting. */
+int b200splat_set_staging(int32_t mode);
 int b200splat_abi_version(void);
 const char* b200splat_last_error(void);
 /* Number of kernels this library launched since process start (all streams). */

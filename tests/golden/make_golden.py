@@ -18,7 +18,7 @@ ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "threestudio-3dgs_b200")); sys.path.insert(0, str(ROOT / "tests"))
 from b200splat import scenes  # noqa: E402
 from oracle import torch_oracle as O  # noqa: E402
-from util import oracle_settings  # noqa: E402
+from util import borderline_bounds, oracle_settings  # noqa: E402
 
 
 def digest(t: torch.Tensor) -> str:
@@ -35,7 +35,12 @@ def build():
                                            scene.rotations, None, s)
     g = O.rasterize_backward((scene.means3D, None, scene.shs, None, scene.opacities, scene.scales, scene.rotations,
                               None), s, pre, binned, out, *grads)
+    # pixels whose blend decisions sit on a hard cut-off, with the error a flipped decision may cause (tests/util.py):
+    # the CUDA path must stay within IMG_TOL + bound there and within IMG_TOL everywhere else
+    bb = borderline_bounds(pre, binned, s, out)
     return dict(
+        borderline_mask=bb["mask"].numpy(), bound_color=bb["color"].numpy(), bound_depth=bb["depth"].numpy(),
+        bound_alpha=bb["alpha"].numpy(),
         inputs_sha256=np.array(digest(torch.cat([scene.means3D.reshape(-1), scene.scales.reshape(-1),
                                                  scene.rotations.reshape(-1), scene.opacities.reshape(-1),
                                                  scene.shs.reshape(-1), cam.viewmatrix.reshape(-1),

@@ -31,7 +31,14 @@ def test_packed_layout():
     pk.views["denom"].fill_(2.0)
     assert float(pk.buffer.sum()) == 300 + 200
     pk2 = batched.PackedGrads(10, 0, "cpu", color_mode="colors_precomp")
-    assert pk2.buffer.numel() == 10 * (13 + 3)
+    # P is padded to a multiple of 4 per field so that every field starts on a 16-byte boundary for any P
+    assert pk2.P4 == 12 and pk2.buffer.numel() == 12 * (13 + 3) == batched.PackedGrads.floats(10, 0, "colors_precomp")
+    assert all(off % 4 == 0 for _, off, _ in pk2.fields)
+    assert pk2.views["rotations"].shape == (10, 4) and pk2.views["rotations"].is_contiguous()
+    segs = pk2.segments(4)                      # Gaussians [4, P): the tail range covers the (zero) padding
+    assert all(o % 4 == 0 and c % 4 == 0 for o, c, _ in segs) and segs[-1] == (pk2.buffer.numel() + 4, 8, 1)
+    pk2.views["means3D"].fill_(1.0)
+    assert float(pk2.buffer.sum()) == 30.0      # the padding Gaussians stay zero
 
 
 def _free_port():

@@ -9,7 +9,7 @@ import torch
 from b200splat import scenes
 from oracle import torch_oracle as O
 from oracle.knn import dist2_oracle
-from util import borderline_pixels, cuda_settings, oracle_settings, rel_err
+from util import borderline_bounds, check_images, cuda_settings, oracle_settings, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -57,15 +57,15 @@ def _run_oracle(sc, s, *, colors_precomp=None, cov3D=None, shs=None, grads=None)
 
 
 def _check_forward(cu, orc, s, allow_borderline=True):
+    """radii bit-exact; image / depth / alpha within IMG_TOL, except that a pixel with a blend decision on a hard
+    cut-off may deviate by what flipping that one decision moves (tests/util.py::borderline_bounds) -- and no more;
+    n_contrib (when the caller has it) equal outside those pixels."""
     out, pre, binned = orc["out"], orc["pre"], orc["binned"]
     assert torch.equal(cu["radii"].cpu(), pre["radii"]), "radii not bit-exact"
-    bad = borderline_pixels(pre, binned, s, out) if allow_borderline else torch.zeros_like(out["alpha"][0]).bool()
-    frac = float(bad.float().mean())
-    assert frac < 0.01, f"too many borderline pixels excluded: {frac}"
-    keep = ~bad
-    for name, ref in (("color", out["color"]), ("depth", out["depth"]), ("alpha", out["alpha"])):
-        err = ((cu[name].cpu() - ref).abs() * keep[None]).max().item()
-        assert err <= IMG_TOL, f"{name} max-abs {err} > {IMG_TOL}"
+    bounds = borderline_bounds(pre, binned, s, out)
+    if not allow_borderline:
+        bounds = {k: torch.zeros_like(v) for k, v in bounds.items()}
+    return check_images(cu, out, bounds, IMG_TOL)
 
 
 def _check_grads(cu, orc, tol=GRAD_TOL):
@@ -118,9 +118,20 @@ def test_inclusive_scan():
     (3000, 1, 50, 70, 8),
     (3000, 2, 64, 64, 9),
 ])
-def test_forward_backward_parity(P, deg, H, W, seed):
-    from b200splat import ops
+@pytest.mark.parametrize("staging", ["ldgsts", "bulk"])
+def test_forward_backward_parity(P, deg, H, W, seed, staging):
+    """Both staging variants of the render kernels: per-entry cp.async (LDGSTS) and cp.async.bulk (UBLKCP,
+    complete_tx on the stage's mbarrier)."""
+    from b200splat import _lib
     sc, cam = _scene(P, deg, H, W, seed)
+    _lib.set_staging(staging)
+    try:
+        _parity_case(sc, cam, deg, H, W, seed)
+    finally:
+        _lib.set_staging(None)
+
+
+def _parity_case(sc, cam, deg, H, W, seed):
     s = oracle_settings(cam, deg)
     grads = scenes.pixel_grads(H, W, seed + 1)
     orc = _run_oracle(sc, s, grads=grads)
@@ -158,8 +169,8 @@ def test_intermediates_bit_exact(P, H, W):
     assert torch.equal(v["keys_sorted"], binned["keys_sorted"])
     assert torch.equal(v["point_list"], binned["point_list"])
     assert torch.equal(v["ranges"], binned["ranges"])
-    nc = orc["out"]["n_contrib"]
-    assert (v["n_contrib"] == nc).float().mean() > 0.999
+    check_images(dict(color=color, depth=depth, alpha=alpha, n_contrib=v["n_contrib"]), orc["out"],
+                 borderline_bounds(pre, binned, s, orc["out"]), IMG_TOL)
 
 
 def test_colors_precomp_cov3d_precomp_and_bg():
@@ -268,9 +279,11 @@ def test_cuda_matches_committed_golden_vectors():
     assert sha(v["keys_sorted"]) == str(gold["keys_sorted_sha256"])
     assert sha(v["point_list"]) == str(gold["point_list_sha256"])
     assert np.array_equal(v["ranges"].numpy(), gold["ranges"])
-    for name, t in (("color", color), ("depth", depth), ("alpha", alpha)):
-        err = np.abs(t.cpu().numpy() - gold[name])
-        assert float((err > IMG_TOL).mean()) < 1e-3 and float(np.median(err)) < 1e-6, name
+    # the fixture carries the oracle's borderline pixels and the error a flipped blend decision may cause there
+    bounds = dict(mask=torch.from_numpy(gold["borderline_mask"]), color=torch.from_numpy(gold["bound_color"]),
+                  depth=torch.from_numpy(gold["bound_depth"]), alpha=torch.from_numpy(gold["bound_alpha"]))
+    ref = {k: torch.from_numpy(gold[k]) for k in ("color", "depth", "alpha", "n_contrib")}
+    check_images(dict(color=color, depth=depth, alpha=alpha, n_contrib=v["n_contrib"]), ref, bounds, IMG_TOL)
     gc, gd, ga = (g.cuda() for g in scenes.pixel_grads(cam.image_height, cam.image_width, 2024))
     g = ops.backward(camc, st, m3, sh, None, op, scl, rot, None, radii, alpha, gc, gd, ga)
     for k, gk in (("means3D", "g_means3D"), ("means2D", "g_means2D"), ("shs", "g_shs"), ("opacities", "g_opacities"),
@@ -521,3 +534,247 @@ def test_stress_shape_pair_mode_and_large_tile_count():
     assert torch.equal(br.ws[0].radii[0], radii) and float((br.ws[0].color[0] - color).abs().max()) < 1e-6
     for k in ("means3D", "shs", "opacities", "scales", "rotations"):
         assert rel_err(br.packed.views[k], pk.views[k]) < 1e-4, k
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Oracle parity AT THE BENCHMARKED SHAPES (BASELINE.json configs / the bench workloads): one view each, the whole
+# operator -- integer stages bit-exact, images 1e-4 (bounded on borderline pixels), n_contrib, gradients 1e-3.
+# The CPU oracle needs a few seconds per view at these sizes.
+# ----------------------------------------------------------------------------------------------------------------
+def _full_scale_parity(scene, cam, bg=(1.0, 1.0, 1.0), seed=5, colors_precomp=None):
+    from b200splat import ops
+    deg = scene.sh_degree
+    H, W = cam.image_height, cam.image_width
+    s = oracle_settings(cam, deg, bg=bg)
+    grads = scenes.pixel_grads(H, W, seed)
+    orc = _run_oracle(scene, s, grads=grads, colors_precomp=colors_precomp)
+    pre, binned, out = orc["pre"], orc["binned"], orc["out"]
+    camc = ops.make_cam(cuda_settings(s), "cuda")
+    d = lambda t: None if t is None else t.cuda().contiguous()
+    m3, op, scl, rot = map(d, (scene.means3D, scene.opacities, scene.scales, scene.rotations))
+    sh = None if colors_precomp is not None else d(scene.shs)
+    cp = d(colors_precomp)
+    color, radii, depth, alpha, st = ops.forward(camc, m3, sh, cp, op, scl, rot, None)
+    v = {k: t.cpu() for k, t in ops.forward_views(camc, st).items()}
+    assert st.num_rendered == binned["num_rendered"]
+    assert torch.equal(radii.cpu(), pre["radii"]), "radii"
+    assert torch.equal(v["tiles_touched"], pre["tiles_touched"]), "tiles_touched"
+    assert torch.equal(v["keys_sorted"], binned["keys_sorted"]), "sorted keys"
+    assert torch.equal(v["point_list"], binned["point_list"]), "point_list"
+    assert torch.equal(v["ranges"], binned["ranges"]), "ranges"
+    bounds = borderline_bounds(pre, binned, s, out)
+    frac, worst = check_images(dict(color=color, depth=depth, alpha=alpha, n_contrib=v["n_contrib"]), out, bounds,
+                               IMG_TOL)
+    g = ops.backward(camc, st, m3, sh, cp, op, scl, rot, None, radii, alpha, *(t.cuda() for t in grads))
+    errs = {}
+    for k, ref in orc["grads"].items():
+        if k == "stage" or ref is None:
+            continue
+        errs[k] = rel_err(g[k], ref)
+        assert errs[k] <= GRAD_TOL, f"grad {k}: rel err {errs[k]} > {GRAD_TOL}"
+    return dict(borderline_frac=frac, worst=worst, grad_err=errs, R=st.num_rendered)
+
+
+@pytest.mark.timeout(900)
+def test_headline_1m_512_sh3_parity():
+    """The bench workload (BASELINE.json metric: 1 M Gaussians, SH degree 3, 512 x 512)."""
+    scene, cams = scenes.make_workload("headline_1m_512_sh3", views=2)
+    for cam in cams:          # two of the rig's views (opposite azimuths)
+        _full_scale_parity(scene, cam)
+
+
+@pytest.mark.timeout(900)
+def test_config3_300k_512_raster_and_shading_postops_parity():
+    """BASELINE.json configs[2]: 300 K Gaussians, 512 x 512, the shading renderer -- the raster pass over a black
+    background (renderer/diff_gaussian_rasterizer_shading.py:94) against the oracle, then the fused post-ops at this
+    size against oracle/postops.py on the same raster images (forward 1e-4, pixel gradients 1e-3)."""
+    from b200splat import ops
+    from b200splat.postops import postprocess_views
+    from oracle import postops as PO
+    scene, cams = scenes.make_workload("config3_300k_512_sh0_b4", views=1)
+    cam = cams[0]
+    _full_scale_parity(scene, cam, bg=(0.0, 0.0, 0.0))
+    H, W = cam.image_height, cam.image_width
+    s = oracle_settings(cam, 0, bg=(0.0, 0.0, 0.0))
+    camc = ops.make_cam(cuda_settings(s), "cuda")
+    d = lambda t: t.cuda().contiguous()
+    color, radii, depth, alpha, st = ops.forward(camc, d(scene.means3D), d(scene.shs), None, d(scene.opacities),
+                                                 d(scene.scales), d(scene.rotations), None)
+    g = torch.Generator().manual_seed(77)
+    rays_d = torch.nn.functional.normalize(torch.randn(H, W, 3, generator=g) * 0.3 + torch.tensor([0.0, 1.0, 0.0]), dim=-1)
+    rays_o = cam.campos[None, None, :].expand(H, W, 3).contiguous()
+    bgm, light = torch.rand(H, W, 3, generator=g), torch.randn(3, generator=g) * 2
+    w = {k: torch.randn(c, H, W, generator=g) / (H * W) for k, c in (("render", 3), ("normal", 3), ("depth", 1))}
+    for shading in ("diffuse", "textureless", "albedo"):
+        lv = {k: t.detach().clone().requires_grad_(True) for k, t in (("image", color), ("depth", depth), ("alpha", alpha))}
+        bgc = bgm.cuda().requires_grad_(True)
+        post = postprocess_views("shading", lv["image"][None], lv["depth"][None], lv["alpha"][None], bg=bgc[None],
+                                 rays_o=rays_o.cuda()[None], rays_d=rays_d.cuda()[None],
+                                 light_positions=light.cuda()[None], shading=shading)
+        sum((post[k] * w[k].cuda()[None]).sum() for k in w).backward()
+        lo = {k: t.detach().cpu().clone().requires_grad_(True) for k, t in (("image", color), ("depth", depth), ("alpha", alpha))}
+        bgo = bgm.clone().requires_grad_(True)
+        ref = PO.postprocess_view(PO.MODE_SHADING, lo["image"], lo["depth"], lo["alpha"], rays_o, rays_d, bgo, light,
+                                  torch.tensor([0.1] * 3), torch.tensor([0.9] * 3), shading, None)
+        sum((ref[k] * w[k]).sum() for k in w).backward()
+        for k in w:
+            assert float((post[k][0].detach().cpu() - ref[k].detach()).abs().max()) <= IMG_TOL, (shading, k)
+        for k in lv:
+            if lo[k].grad is None:
+                assert lv[k].grad is None or float(lv[k].grad.abs().max()) == 0.0, (shading, k)
+            else:
+                assert rel_err(lv[k].grad, lo[k].grad) <= GRAD_TOL, (shading, k)
+        if bgo.grad is not None:
+            assert rel_err(bgc.grad, bgo.grad) <= GRAD_TOL, (shading, "bg")
+
+
+@pytest.mark.timeout(900)
+def test_config4_1m_256_sh3_parity():
+    """BASELINE.json configs[3]: 1 M Gaussians, SH degree 3, 256 x 256 (256 tiles), MVDream rig."""
+    scene, cams = scenes.make_workload("config4_1m_256_sh3_b32", views=5)
+    for cam in (cams[0], cams[4]):   # one view of each of two camera groups (different fovy / distance)
+        _full_scale_parity(scene, cam)
+
+
+@pytest.mark.timeout(900)
+def test_4096_tile_grid_sh3_parity():
+    """The stress configuration's image size (1024 x 1024: 4096 tiles, the pair words take the wide-grid path) with
+    250 K SH-degree-3 Gaussians."""
+    scene = scenes.make_scene(250_000, 3, 0.5, seed=4242)
+    cam = scenes.mvdream_cameras(1, 1024, 1024, seed=4243)[0]
+    _full_scale_parity(scene, cam)
+
+
+@pytest.mark.timeout(900)
+def test_spacetime_call_shape_parity_at_scale():
+    """BASELINE.json configs[4] call shape (renderer/diff_gaussian_rasterizer_st.py:135-150): precomputed colours
+    instead of SH, 200 K Gaussians at 512 x 512."""
+    scene = scenes.make_scene(200_000, 0, 0.5, seed=777)
+    cam = scenes.mvdream_cameras(1, 512, 512, seed=778)[0]
+    cp = torch.rand(200_000, 3, generator=torch.Generator().manual_seed(779))
+    _full_scale_parity(scene, cam, colors_precomp=cp)
+
+
+def test_binning_capacity_heals_itself():
+    """a view that outgrows the calibrated binning capacity must not come back as background.
+    The capacity is shrunk below what a closer, narrower camera needs; the forward notices (pair-count notice from
+    the scan kernel), regrows and renders again -- images, radii and gradients equal the per-view operator's."""
+    from b200splat.batched import ViewBatchRasterizer
+    from diff_gaussian_rasterization import GaussianRasterizer
+    P, deg, H, W, V = 20000, 1, 96, 96, 2
+    sc, _ = _scene(P, deg, H, W, 301)
+    far = scenes.sds_cameras(V, H, W, seed=302, camera_distance=4.0, fovy_deg=(69.0, 70.0))
+    near = scenes.sds_cameras(V, H, W, seed=302, camera_distance=1.6, fovy_deg=(30.0, 31.0))
+    dev = "cuda"
+    mk = lambda: [t.to(dev).clone().requires_grad_(True) for t in (sc.means3D, sc.shs, sc.opacities, sc.scales, sc.rotations)]
+    rast = ViewBatchRasterizer(V, P, H, W, dev)
+    m3, sh, op, scl, rot = mk()
+    rss = [cuda_settings(oracle_settings(c, deg), dev) for c in far]
+    rast(rss, means3D=m3, means2D=torch.zeros(V, P, 3, device=dev), opacities=op, shs=sh, scales=scl, rotations=rot)
+    small = max(rast.last_pairs) + 64
+    rast.ws._alloc_binning(small)                       # what a tight calibration on the far cameras would give
+    cap0, regrown0 = rast.ws.capacity, rast.regrown
+    rss = [cuda_settings(oracle_settings(c, deg), dev) for c in near]
+    pgs = [tuple(g.to(dev) for g in scenes.pixel_grads(H, W, 303 + i)) for i in range(V)]
+    m2 = torch.zeros(V, P, 3, device=dev, requires_grad=True)
+    C, R, D, A = rast(rss, means3D=m3, means2D=m2, opacities=op, shs=sh, scales=scl, rotations=rot)
+    assert max(rast.last_pairs) > cap0, "the near cameras were meant to overflow the shrunk capacity"
+    assert rast.regrown == regrown0 + 1 and rast.ws.capacity >= max(rast.last_pairs)
+    assert not rast.check_overflow()
+    sum((C[v] * pgs[v][0]).sum() + (D[v] * pgs[v][1]).sum() + (A[v] * pgs[v][2]).sum() for v in range(V)).backward()
+    n3, nsh, nop, nscl, nrot = mk()
+    loss = 0.0
+    for v in range(V):
+        n2 = torch.zeros(P, 3, device=dev, requires_grad=True)
+        c, r, d, a = GaussianRasterizer(raster_settings=rss[v])(means3D=n3, means2D=n2, shs=nsh, colors_precomp=None,
+                                                                opacities=nop, scales=nscl, rotations=nrot,
+                                                                cov3D_precomp=None)
+        assert torch.equal(R[v], r) and float((C[v] - c).abs().max()) < 1e-6 and float((A[v] - a).abs().max()) < 1e-6
+        assert float(a.max()) > 0.5, "the view must actually show the object"
+        loss = loss + (c * pgs[v][0]).sum() + (d * pgs[v][1]).sum() + (a * pgs[v][2]).sum()
+    loss.backward()
+    for got, want, name in zip((m3, sh, op, scl, rot), (n3, nsh, nop, nscl, nrot),
+                               ("means3D", "shs", "opacities", "scales", "rotations")):
+        assert rel_err(got.grad, want.grad) < 1e-4, name
+
+
+@pytest.mark.parametrize("P", [4999, 5001, 5002])
+def test_odd_gaussian_counts_through_the_packed_paths(P):
+    """P is arbitrary after densify / prune.  Every field of the packed gradient buffer stays
+    16-byte aligned (rotations are stored as float4), through BatchRenderer.step, the per-view loop into the packed
+    buffer, the step_head / step_tail split and FusedGaussianAdam's view of the same buffer."""
+    from b200splat import batched, ops
+    deg, H, W, V = 1, 64, 64, 2
+    sc, _ = _scene(P, deg, H, W, 311)
+    cams_h = scenes.sds_cameras(V, H, W, seed=312)
+    dev = "cuda"
+    d = lambda t: t.to(dev).contiguous()
+    m3, sh, op, scl, rot = map(d, (sc.means3D, sc.shs, sc.opacities, sc.scales, sc.rotations))
+    cams = [ops.make_cam(cuda_settings(oracle_settings(c, deg)), dev) for c in cams_h]
+    pgs = [tuple(d(g) for g in scenes.pixel_grads(H, W, 313 + i)) for i in range(V)]
+    pk_ref = batched.PackedGrads(P, sh.shape[1], dev)
+    assert all(off % 4 == 0 for _, off, _ in pk_ref.fields) and pk_ref.views["rotations"].data_ptr() % 16 == 0
+    batched.render_views_fwd_bwd(cams, m3, sh, None, op, scl, rot, pgs, pk_ref)
+    # independent reference: the drop-in operator + autograd
+    leaves = [t.clone().requires_grad_(True) for t in (m3, sh, op, scl, rot)]
+    from diff_gaussian_rasterization import GaussianRasterizer
+    loss = 0.0
+    for v in range(V):
+        rs = cuda_settings(oracle_settings(cams_h[v], deg), dev)
+        c, r, dd, a = GaussianRasterizer(raster_settings=rs)(means3D=leaves[0], means2D=torch.zeros(P, 3, device=dev),
+                                                             shs=leaves[1], colors_precomp=None, opacities=leaves[2],
+                                                             scales=leaves[3], rotations=leaves[4], cov3D_precomp=None)
+        loss = loss + (c * pgs[v][0]).sum() + (dd * pgs[v][1]).sum() + (a * pgs[v][2]).sum()
+    loss.backward()
+    for k, t in zip(("means3D", "shs", "opacities", "scales", "rotations"), leaves):
+        assert rel_err(pk_ref.views[k], t.grad) < 1e-4, k
+    br = batched.BatchRenderer(P, sh.shape[1], H, W, dev, views=V)
+    br.step(cams, m3, sh, None, op, scl, rot, pgs)
+    assert not br.overflowed()
+    for k in ("means3D", "shs", "opacities", "scales", "rotations", "grad_accum", "denom"):
+        assert rel_err(br.packed.views[k], pk_ref.views[k]) < 1e-4, k
+    first = br.packed.buffer.clone()
+    br.packed.buffer.zero_()
+    br.step_head(cams, m3, sh, None, op, scl, rot, pgs)
+    seen = []
+    br.step_tail(cams, m3, sh, None, op, scl, rot, lambda g0, g1: seen.append(br.packed.segments(g0, g1)), chunks=3)
+    torch.cuda.synchronize()
+    assert rel_err(br.packed.buffer, first) < 1e-5
+    assert all(o % 4 == 0 and c % 4 == 0 for segs in seen for o, c, _ in segs)
+    # the padding Gaussians of every field stay zero (they are summed by the exchange)
+    for name, off, w in br.packed.fields:
+        assert float(br.packed.buffer[off + w * P: off + w * br.packed.P4].abs().sum()) == 0.0, name
+
+
+def test_view_batch_rasterizer_survives_densify_and_prune():
+    """The number of Gaussians changes between steps (geometry/gaussian_base.py:853-869): the same
+    ViewBatchRasterizer keeps working (grow-only workspace), no rebuild, results equal the per-view operator's."""
+    from b200splat.batched import ViewBatchRasterizer
+    from diff_gaussian_rasterization import GaussianRasterizer
+    deg, H, W, V = 0, 64, 64, 2
+    dev = "cuda"
+    cams_h = scenes.sds_cameras(V, H, W, seed=322)
+    rss = [cuda_settings(oracle_settings(c, deg), dev) for c in cams_h]
+    rast = ViewBatchRasterizer(V, 3000, H, W, dev)
+    geoms = []
+    for P in (3000, 4501, 2000, 6000):
+        sc, _ = _scene(P, deg, H, W, 320 + P)
+        leaves = [t.to(dev).clone().requires_grad_(True) for t in (sc.means3D, sc.shs, sc.opacities, sc.scales, sc.rotations)]
+        m2 = torch.zeros(V, P, 3, device=dev, requires_grad=True)
+        C, R, D, A = rast(rss, means3D=leaves[0], means2D=m2, opacities=leaves[2], shs=leaves[1], scales=leaves[3],
+                          rotations=leaves[4])
+        (C.sum() + D.sum()).backward()
+        geoms.append(rast.ws.geom[0].data_ptr())
+        ref = [t.detach().clone().requires_grad_(True) for t in leaves]
+        loss = 0.0
+        for v in range(V):
+            n2 = torch.zeros(P, 3, device=dev, requires_grad=True)
+            c, r, dd, a = GaussianRasterizer(raster_settings=rss[v])(means3D=ref[0], means2D=n2, shs=ref[1],
+                                                                     colors_precomp=None, opacities=ref[2], scales=ref[3],
+                                                                     rotations=ref[4], cov3D_precomp=None)
+            assert torch.equal(R[v], r) and float((C[v] - c).abs().max()) < 1e-6
+            loss = loss + c.sum() + dd.sum()
+        loss.backward()
+        for a_, b_ in zip(leaves, ref):
+            assert rel_err(a_.grad, b_.grad) < 1e-4
+    assert geoms[1] == geoms[2], "shrinking P must not reallocate the workspace"

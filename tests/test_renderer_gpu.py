@@ -177,7 +177,7 @@ def test_two_renders_before_backward_do_not_share_a_workspace():
     ren.geometry = _Geometry(sc, False, 224)
     out_a = ren.batch_forward(batch_a)
     out_b = ren.batch_forward(batch_b)               # same shape, first graph still alive
-    assert len(ren._b200_rasterizers[(V, P, H, W, "cuda:0")]) == 2
+    assert len(ren._b200_rasterizers[(V, H, W, "cuda:0")]) == 2
     (out_a["comp_rgb"].sum() + out_b["comp_rgb"].sum()).backward()
     g_two = ren.geometry.get_xyz.grad.clone()
     # the same two renders one after the other
@@ -185,8 +185,8 @@ def test_two_renders_before_backward_do_not_share_a_workspace():
     ren.batch_forward(batch_a)["comp_rgb"].sum().backward()
     ren.batch_forward(batch_b)["comp_rgb"].sum().backward()
     assert rel_err(g_two, ren.geometry.get_xyz.grad) <= 1e-4
-    assert all(not r.pending for r in ren._b200_rasterizers[(V, P, H, W, "cuda:0")])
+    assert all(not r.pending for r in ren._b200_rasterizers[(V, H, W, "cuda:0")])
     with torch.no_grad():                             # inference never holds a workspace
         for _ in range(6):
             ren.batch_forward(batch_a)
-    assert len(ren._b200_rasterizers[(V, P, H, W, "cuda:0")]) == 2
+    assert len(ren._b200_rasterizers[(V, H, W, "cuda:0")]) == 2

@@ -13,7 +13,7 @@ from pathlib import Path
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("B200SPLAT_LIB", _HERE / "libb200splat.so"))
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_VIEWS = 8
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
@@ -85,6 +85,7 @@ class BatchForwardArgs(C.Structure):
         ("stream", C.c_void_p), ("sync", C.c_int32),
         ("num_rendered_out", C.POINTER(C.c_int64)), ("overflow_out", C.POINTER(C.c_int32)),
         ("extra_features", C.c_void_p), ("n_extra", C.c_int32), ("out_extra", PP),
+        ("pairs_notify", C.c_void_p), ("notify_epoch", C.c_uint32),
     ]
 
 
@@ -142,6 +143,7 @@ P2P_HANDLE_BYTES, P2P_SIGNAL_BYTES = 64, 256
 # every symbol include/b200splat.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "b200splat_abi_version": (C.c_int, []),
+    "b200splat_set_staging": (C.c_int, [C.c_int32]),
     "b200splat_last_error": (C.c_char_p, []),
     "b200splat_launch_count": (C.c_uint64, []),
     "b200splat_p2p_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
@@ -226,3 +228,11 @@ def profile_read():
 
 def launch_count() -> int:
     return int(lib.b200splat_launch_count())
+
+
+STAGING = {None: -1, "default": -1, "ldgsts": 0, "bulk": 1}
+
+
+def set_staging(mode) -> int:
+    """Select how the render kernels stage Gaussian records (None = default); returns the previous setting."""
+    return int(lib.b200splat_set_staging(STAGING[mode]))

@@ -15,6 +15,7 @@ only the accumulators are all-reduced, never means2D.grad itself.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -28,25 +29,36 @@ MAX_VIEWS = _lib.MAX_VIEWS
 class PackedGrads:
     """[dL/dmeans3D 3 | dL/dscales 3 | dL/drotations 4 | dL/dopacity 1 | dL/dshs 3M (or colours 3) |
     grad_accum 1 | denom 1] x P floats in ONE contiguous fp32 buffer (the all-reduce payload,
-    4*P*(13+3M) bytes), plus max_radii (P) reduced with MAX."""
+    4*P*(13+3M) bytes), plus max_radii (P) reduced with MAX.
+
+    Every field starts on a 16-byte boundary for ANY P (densify / prune make P arbitrary): a field of width w
+    occupies w * P4 floats, P4 = P rounded up to a multiple of 4; the up to 3 padding Gaussians stay zero.  The
+    kernels access rotations (and, when aligned, the SH rows) as float4, and the peer-memory all-reduce
+    exchanges whole float4s."""
+
+    @staticmethod
+    def padded(P: int) -> int:
+        return (P + 3) // 4 * 4
 
     @staticmethod
     def floats(P: int, M: int, color_mode: str = "shs") -> int:
-        """Floats of the SUM segment (the MAX segment, max_radii, is P more)."""
-        return (13 + (3 * M if color_mode == "shs" else 3)) * P
+        """Floats of the SUM segment (the MAX segment, max_radii, is padded(P) more)."""
+        return (13 + (3 * M if color_mode == "shs" else 3)) * PackedGrads.padded(P)
 
     def __init__(self, P: int, M: int, device, color_mode: str = "shs", storage: Optional[torch.Tensor] = None):
-        """``storage``: optional flat fp32 tensor of at least floats() + P elements that backs the buffer and
-        max_radii -- e.g. the exchange buffer of ``dist.P2PAllReduce``, so the all-reduce runs in place."""
+        """``storage``: optional flat fp32 tensor of at least floats() + padded(P) elements that backs the buffer
+        and max_radii -- e.g. the exchange buffer of ``dist.P2PAllReduce``, so the all-reduce runs in place."""
         self.P, self.M, self.color_mode = P, M, color_mode
+        P4 = self.P4 = self.padded(P)
         ncol = 3 * M if color_mode == "shs" else 3
         widths = [("means3D", 3), ("scales", 3), ("rotations", 4), ("opacities", 1),
                   (color_mode if color_mode == "shs" else "colors_precomp", ncol),
                   ("grad_accum", 1), ("denom", 1)]
-        total = sum(w for _, w in widths) * P
+        total = sum(w for _, w in widths) * P4
         if storage is not None:
-            assert storage.dtype == torch.float32 and storage.is_contiguous() and storage.numel() >= total + P
-            storage[:total + P].zero_()
+            assert storage.dtype == torch.float32 and storage.is_contiguous() and storage.numel() >= total + P4
+            assert storage.data_ptr() % 16 == 0
+            storage[:total + P4].zero_()
         self.buffer = storage[:total] if storage is not None else torch.zeros(total, dtype=torch.float32, device=device)
         self.views: Dict[str, torch.Tensor] = {}
         self.fields: List[tuple] = []   # (name, offset in floats, floats per Gaussian)
@@ -54,12 +66,13 @@ class PackedGrads:
         for name, w in widths:
             self.fields.append((name, off, w))
             self.views[name] = self.buffer[off:off + w * P].view(P, w) if w > 1 else self.buffer[off:off + P]
-            off += w * P
+            off += w * P4
         self.views["opacities"] = self.views["opacities"].view(P, 1)
         if color_mode == "shs":
             self.views["shs"] = self.views["shs"].view(P, M, 3)
-        self.max_radii = storage[total:total + P] if storage is not None else \
-            torch.zeros(P, dtype=torch.float32, device=device)
+        self._max_all = storage[total:total + P4] if storage is not None else \
+            torch.zeros(P4, dtype=torch.float32, device=device)
+        self.max_radii = self._max_all[:P]
         self.means2D_scratch = torch.empty(P, 3, dtype=torch.float32, device=device)
 
     @property
@@ -69,10 +82,13 @@ class PackedGrads:
     def segments(self, g0: int = 0, g1: Optional[int] = None):
         """(offset, count, op) float ranges of the exchange storage that hold Gaussians [g0, g1): one SUM range per
         field of the packed buffer plus the MAX range of max_radii (which sits right behind the buffer when the
-        storage is shared).  op: 0 = sum, 1 = max."""
+        storage is shared).  op: 0 = sum, 1 = max.  g0 must be a multiple of 4; a range that ends at P also covers
+        the field's (zero) padding, so offsets and counts are always multiples of 4 floats."""
         g1 = self.P if g1 is None else g1
-        segs = [(off + w * g0, w * (g1 - g0), 0) for _, off, w in self.fields]
-        segs.append((self.buffer.numel() + g0, g1 - g0, 1))
+        assert g0 % 4 == 0 and (g1 % 4 == 0 or g1 == self.P)
+        e1 = self.P4 if g1 == self.P else g1
+        segs = [(off + w * g0, w * (e1 - g0), 0) for _, off, w in self.fields]
+        segs.append((self.buffer.numel() + g0, e1 - g0, 1))
         return segs
 
     def zero_stats_(self):
@@ -91,31 +107,65 @@ def _parr(ptrs):
 class BatchWorkspace:
     """Persistent device buffers of a view batch (torch owns them): per view the geometry / image /
     binning buffers, the backward scratch and the output images.  The binning buffers have a capacity in
-    (tile, Gaussian) pairs; ``render`` grows them and re-runs when a view overflowed."""
+    (tile, Gaussian) pairs.  The per-Gaussian buffers are grow-only in P: densify / prune
+    (geometry/gaussian_base.py:853-869) change P every few hundred steps, ``resize`` keeps the allocation when the
+    new P fits (layouts are computed per call from P; the scratch is all-zero between steps whatever P was)."""
 
     def __init__(self, V: int, P: int, H: int, W: int, device, capacity_pairs: Optional[int] = None):
         assert 1 <= V <= MAX_VIEWS
-        self.V, self.P, self.H, self.W, self.device = V, P, H, W, device
+        self.V, self.H, self.W, self.device = V, H, W, torch.device(device)
         u8 = lambda n: torch.empty(int(n), dtype=torch.uint8, device=device)
         f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=device)
-        self.geom = [u8(lib.b200splat_geom_bytes(P)) for _ in range(V)]
         self.image = [u8(lib.b200splat_image_bytes(H, W)) for _ in range(V)]
-        # all-zero on entry to every backward and left all-zero by it (b200splat_batch_backward_args.scratch_clean)
-        self.scratch = [torch.zeros(int(lib.b200splat_backward_scratch_bytes(P)), dtype=torch.uint8, device=device)
-                        for _ in range(V)]
         self.color = [f32(3, H, W) for _ in range(V)]
         self.depth = [f32(1, H, W) for _ in range(V)]
         self.alpha = [f32(1, H, W) for _ in range(V)]
-        self.radii = [torch.empty(P, dtype=torch.int32, device=device) for _ in range(V)]
+        self.P = self.P_alloc = 0
+        self.resize(P)
         self.binning: List[torch.Tensor] = []
         self.binning_bytes = 0
         self.num_rendered = [0] * V
         self._alloc_binning(capacity_pairs or max(4 * P, 1 << 16))
+        # early notice of every view's pair count (b200splat_batch_forward_args.pairs_notify): pinned host words the
+        # scan kernel writes, polled by the host while the rest of the forward is still queued
+        self.notify = None
+        self.epoch = 0
+        if self.device.type == "cuda":
+            self.notify = torch.zeros(V, dtype=torch.int64).pin_memory()
+            self._notify_np = self.notify.numpy()
+
+    def resize(self, P: int):
+        if P > self.P_alloc:
+            alloc = P if self.P_alloc == 0 else max(P, int(self.P_alloc * 1.25))
+            dev = self.device
+            self.geom = [torch.empty(int(lib.b200splat_geom_bytes(alloc)), dtype=torch.uint8, device=dev)
+                         for _ in range(self.V)]
+            # all-zero on entry to every backward and left all-zero by it (b200splat_batch_backward_args.scratch_clean)
+            self.scratch = [torch.zeros(int(lib.b200splat_backward_scratch_bytes(alloc)), dtype=torch.uint8, device=dev)
+                            for _ in range(self.V)]
+            self._radii_all = [torch.empty(alloc, dtype=torch.int32, device=dev) for _ in range(self.V)]
+            self.P_alloc = alloc
+        self.P = P
+        self.radii = [r[:P] for r in self._radii_all]
 
     def _alloc_binning(self, pairs: int):
         self.binning_bytes = int(lib.b200splat_binning_bytes(int(pairs)))
         self.binning = [torch.empty(self.binning_bytes, dtype=torch.uint8, device=self.device) for _ in range(self.V)]
         self.capacity = int(lib.b200splat_binning_capacity(self.binning_bytes))
+
+    def wait_pair_counts(self, epoch: int, timeout_s: float = 60.0) -> List[int]:
+        """Spin until every view's notice of forward ``epoch`` has arrived; returns the V pair counts."""
+        import time
+        t0 = None
+        while True:
+            w = self._notify_np.copy()
+            if bool(((w >> 32) == epoch).all()):
+                return [int(x) for x in (w & 0xFFFFFFFF)]
+            if t0 is None:
+                t0 = time.perf_counter()
+            elif time.perf_counter() - t0 > timeout_s:
+                torch.cuda.synchronize(self.device)   # surfaces a sticky CUDA error, if that is why nothing arrived
+                raise RuntimeError("b200splat: the forward's pair-count notice never arrived")
 
     def states(self, M: int):
         """Per-view ops.ForwardState (for ops.forward_views / the single-view backward)."""
@@ -124,9 +174,11 @@ class BatchWorkspace:
 
 
 def forward_batched(ws: BatchWorkspace, cams: Sequence[ops.Cam], means3D, shs, colors_precomp, opacities, scales,
-                    rotations, sync: bool = False, extra_features=None, extra_out=None):
+                    rotations, sync: bool = False, extra_features=None, extra_out=None, notify: bool = False):
     """One launch set for all views.  With sync=True returns (num_rendered list, overflow list).
-    extra_features (P,C') + extra_out (list of V (C',H,W) tensors): extra channels blended by the same pass."""
+    extra_features (P,C') + extra_out (list of V (C',H,W) tensors): extra channels blended by the same pass.
+    notify=True: returns (epoch, None); ``ws.wait_pair_counts(epoch)`` then yields the views' pair counts as soon as
+    the scan kernel has run, without synchronising the stream."""
     V = len(cams)
     assert V == ws.V
     M = 0 if shs is None else int(shs.shape[1])
@@ -139,8 +191,11 @@ def forward_batched(ws: BatchWorkspace, cams: Sequence[ops.Cam], means3D, shs, c
                                                             ws.image, ws.binning)]
     a.out_color, a.out_depth, a.out_alpha, a.radii, a.geom_buffer, a.image_buffer, a.binning_buffer = keep
     a.binning_bytes = ws.binning_bytes
-    a.stream = ops._stream()
+    a.stream = ops._stream(ws.device)
     a.sync = int(sync)
+    if notify:
+        ws.epoch = (ws.epoch % 0x7FFFFFFF) + 1
+        a.pairs_notify, a.notify_epoch = ws.notify.data_ptr(), ws.epoch
     nr = (C.c_int64 * V)()
     ov = (C.c_int32 * V)()
     a.num_rendered_out, a.overflow_out = nr, ov
@@ -153,7 +208,7 @@ def forward_batched(ws: BatchWorkspace, cams: Sequence[ops.Cam], means3D, shs, c
     if sync:
         ws.num_rendered = [int(x) for x in nr]
         return ws.num_rendered, [int(x) for x in ov]
-    return None, None
+    return (ws.epoch if notify else None), None
 
 
 def backward_batched(ws: BatchWorkspace, cams: Sequence[ops.Cam], means3D, shs, colors_precomp, opacities, scales,
@@ -187,7 +242,7 @@ def backward_batched(ws: BatchWorkspace, cams: Sequence[ops.Cam], means3D, shs, 
     a.accumulate = int(bool(accumulate))
     if stats is not None:
         a.stat_grad_accum, a.stat_denom, a.stat_max_radii = (ops._ptr(t) for t in stats)
-    a.stream = ops._stream()
+    a.stream = ops._stream(ws.device)
     a.phase = int(phase)
     if g_range is not None:
         a.g_begin, a.g_end = int(g_range[0]), int(g_range[1])
@@ -381,10 +436,7 @@ class _RasterizeViews(torch.autograd.Function):
         ex_ = f(extra_features, "extra_features") if n_extra else None
         extra = torch.empty(V, n_extra, H, W, dtype=torch.float32, device=dev)
         ekw = dict(extra_features=ex_, extra_out=list(extra.unbind(0))) if n_extra else {}
-        if not owner.calibrated:
-            owner.calibrate(cams, m3, sh_, cp_, op_, sc_, ro_, **ekw)
-        else:
-            forward_batched(ws, cams, m3, sh_, cp_, op_, sc_, ro_, sync=False, **ekw)
+        owner.render_checked(cams, m3, sh_, cp_, op_, sc_, ro_, **ekw)
         owner.generation += 1
         ctx.owner, ctx.cams, ctx.generation = owner, cams, owner.generation
         ctx.has = (sh_ is not None, cp_ is not None)
@@ -392,6 +444,7 @@ class _RasterizeViews(torch.autograd.Function):
         ctx.n_extra = n_extra
         ctx.save_for_backward(m3, e(sh_), e(cp_), op_, sc_, ro_, e(ex_))
         ctx.mark_non_differentiable(radii)
+        owner._ctx = weakref.ref(ctx)   # the live graph (if any) that owns the workspace: see ViewBatchRasterizer.pending
         return color, radii, depth, alpha, extra
 
     @staticmethod
@@ -426,7 +479,6 @@ class _RasterizeViews(torch.autograd.Function):
             ekw = dict(extra_features=ex_, extra_grads=None if ge is None else list(ge.unbind(0)))
         backward_batched(ws, ctx.cams, m3, sh_, cp_, op_, sc_, ro_, pgs, out, accumulate=False,
                          means2D_out=list(m2.unbind(0)), **ekw)
-        owner.pending = False
         return (None, None, out["means3D"], m2, out.get("shs"), out.get("colors_precomp"), out["opacities"],
                 out["scales"], out["rotations"], out.get("extra_features"))
 
@@ -436,37 +488,69 @@ class ViewBatchRasterizer(torch.nn.Module):
     opacities, shs=None, colors_precomp=None, scales=, rotations=)`` -> ``(color (V,3,H,W), radii (V,P) int32,
     depth (V,1,H,W), alpha (V,1,H,W))`` (+ ``extra (V,C',H,W)`` when ``extra_features (P,C')`` is given) with autograd; ``means2D.grad[v]`` is view v's NDC gradient, exactly what
     the per-view call would have produced (geometry/gaussian_base.py:815-819 reads it per view).  Holds the
-    persistent device workspace of the batch; one instance per concurrently live autograd graph."""
+    persistent device workspace of the batch; one instance per concurrently live autograd graph.
+
+    The number of Gaussians may change between calls (densify / prune): the workspace grows when it has to.
+    The binning capacity heals itself: every forward learns its views' pair counts from the scan kernel through
+    pinned host memory (no stream synchronisation -- the rest of the forward is already queued behind the scan) and,
+    if a view outgrew the capacity (closer camera, narrower fov, grown scales), enlarges the buffers and renders
+    again before anything is returned; a view can never silently come back as background."""
+
+    HEADROOM = 1.5
 
     def __init__(self, views: int, P: int, H: int, W: int, device="cuda"):
         super().__init__()
         assert views <= MAX_VIEWS, f"at most {MAX_VIEWS} views per batch call"
         self.ws = BatchWorkspace(views, P, H, W, torch.device(device))
-        self.calibrated = False
         self.generation = 0
-        self.pending = False   # a forward with autograd enabled whose backward has not run yet owns the workspace
+        self.regrown = 0          # how many times a forward had to be repeated with larger binning buffers
+        self.last_pairs: List[int] = []
+        self._ctx = None
 
-    def calibrate(self, cams, means3D, shs, colors_precomp, opacities, scales, rotations, headroom: float = 1.25,
-                  **extra):
+    @property
+    def pending(self) -> bool:
+        """True while an autograd graph recorded by this rasterizer can still run its backward: the graph's node is
+        alive and its saved tensors have not been released (they are released by a backward without
+        ``retain_graph`` -- the reference runs two backward passes over one graph, system/gaussian_splatting.py:
+        129-138 -- or when the outputs are dropped)."""
+        ctx = self._ctx() if self._ctx is not None else None
+        if ctx is None:
+            return False
+        try:
+            ctx.saved_tensors
+        except RuntimeError:
+            return False
+        return True
+
+    def render_checked(self, cams, means3D, shs, colors_precomp, opacities, scales, rotations, **extra):
+        """The batch's forward with the capacity check described in the class docstring."""
         ws = self.ws
-        while True:
-            nr, ov = forward_batched(ws, cams, means3D, shs, colors_precomp, opacities, scales, rotations, sync=True,
-                                     **extra)
-            need = int(max(nr) * headroom) + 4096
-            if any(ov) or ws.capacity < need:
-                ws._alloc_binning(max(need, 2 * ws.capacity) if any(ov) else need)
-                continue
-            break
-        self.calibrated = True
+        for attempt in range(4):
+            epoch, _ = forward_batched(ws, cams, means3D, shs, colors_precomp, opacities, scales, rotations, sync=False,
+                                       notify=True, **extra)
+            pairs = ws.wait_pair_counts(epoch)
+            self.last_pairs = pairs
+            if max(pairs) <= ws.capacity:
+                return
+            self.regrown += 1
+            ws._alloc_binning(int(max(pairs) * self.HEADROOM) + 4096)
+        raise RuntimeError("ViewBatchRasterizer: the binning buffers still overflow after regrowing them")
+
+    def calibrate(self, cams, means3D, shs, colors_precomp, opacities, scales, rotations, headroom: float = 1.5,
+                  **extra):
+        """Optional: size the binning buffers ahead of the first step (a forward does it on demand)."""
+        ws = self.ws
+        nr, ov = forward_batched(ws, cams, means3D, shs, colors_precomp, opacities, scales, rotations, sync=True, **extra)
+        need = int(max(nr) * headroom) + 4096
+        if any(ov) or ws.capacity < need:
+            ws._alloc_binning(need)
 
     def check_overflow(self) -> bool:
-        """One small device read; True (and re-calibration scheduled) if a view outgrew its binning capacity."""
+        """One small device read of the views' status words; True if a view of the LAST forward exceeded the
+        capacity.  ``forward`` repairs that itself, so this is a cross-check (tests, bench)."""
         ws = self.ws
         flags = [ops.status_tensor(ws.H, ws.W, st) for st in ws.states(0)]
-        bad = bool(torch.stack(flags)[:, 0].any().item())
-        if bad:
-            self.calibrated = False
-        return bad
+        return bool(torch.stack(flags)[:, 0].any().item())
 
     def forward(self, raster_settings, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None,
                 rotations=None, extra_features=None):
@@ -476,11 +560,14 @@ class ViewBatchRasterizer(torch.nn.Module):
             raise Exception("The batched rasterizer needs the scale/rotation pair")
         ws = self.ws
         if means3D.shape[0] != ws.P:
-            raise RuntimeError("number of Gaussians changed (densify/prune): build a new ViewBatchRasterizer")
+            if self.pending:
+                raise RuntimeError("ViewBatchRasterizer: the number of Gaussians changed while a graph recorded with "
+                                   "the old one is still waiting for its backward")
+            ws.resize(int(means3D.shape[0]))
         cams = [ops.make_cam(rs, means3D.device) for rs in raster_settings]
-        self.pending = torch.is_grad_enabled() and any(
-            t is not None and t.requires_grad for t in (means3D, means2D, opacities, shs, colors_precomp, scales,
-                                                        rotations, extra_features))
         out = _RasterizeViews.apply(self, cams, means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
                                     extra_features)
+        if not (torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (
+                means3D, means2D, opacities, shs, colors_precomp, scales, rotations, extra_features))):
+            self._ctx = None
         return out if extra_features is not None else out[:4]

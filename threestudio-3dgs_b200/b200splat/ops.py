@@ -33,8 +33,9 @@ def _f32c(t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
     return t
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _stream(dev=None) -> int:
+    """Handle of torch's current stream ON THE TENSORS' DEVICE (not on whatever device is current)."""
+    return torch.cuda.current_stream(dev).cuda_stream
 
 
 class Cam(NamedTuple):
@@ -130,7 +131,7 @@ def forward(cam: Cam, means3D, shs, colors_precomp, opacities, scales, rotations
     a.image_buffer, a.image_bytes = image.data_ptr(), image_bytes
     a.binning_buffer, a.binning_bytes = None, 0
     a.binning_alloc, a.alloc_user = cb, None
-    a.stream = _stream()
+    a.stream = _stream(dev)
     a.num_rendered_out = C.pointer(nr)
     a.binning_out = C.pointer(bout)
     if n_extra:
@@ -185,7 +186,7 @@ def backward(cam: Cam, st: ForwardState, means3D, shs, colors_precomp, opacities
     a.accumulate = int(bool(accumulate))
     if stats is not None:   # (grad_accum, denom, max_radii) each (P,) fp32, updated in place
         a.stat_grad_accum, a.stat_denom, a.stat_max_radii = (_ptr(t) for t in stats)
-    a.stream = _stream()
+    a.stream = _stream(dev)
     if n_extra:
         a.extra_features, a.n_extra = extra_features.data_ptr(), n_extra
         a.dL_dout_extra, a.dL_dextra = _ptr(g_extra), out["extra_features"].data_ptr()
@@ -203,7 +204,7 @@ def mark_visible(positions: torch.Tensor, viewmatrix: torch.Tensor, projmatrix: 
         v, p = _f32c(viewmatrix, "viewmatrix"), _f32c(projmatrix, "projmatrix")
         with torch.cuda.device(dev):
             check(lib.b200splat_mark_visible(P, positions.data_ptr(), v.data_ptr(), p.data_ptr(),
-                                             present.data_ptr(), _stream()), "b200splat_mark_visible")
+                                             present.data_ptr(), _stream(dev)), "b200splat_mark_visible")
     return present.bool()
 
 
@@ -218,7 +219,7 @@ def dist2(points: torch.Tensor) -> torch.Tensor:
     nbytes = lib.b200splat_dist2_workspace_bytes(P)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=points.device)
     with torch.cuda.device(points.device):
-        check(lib.b200splat_dist2(P, pts.data_ptr(), out.data_ptr(), ws.data_ptr(), nbytes, _stream()),
+        check(lib.b200splat_dist2(P, pts.data_ptr(), out.data_ptr(), ws.data_ptr(), nbytes, _stream(points.device)),
               "b200splat_dist2")
     return out
 
@@ -236,7 +237,7 @@ def sort_pairs(keys: torch.Tensor, vals: torch.Tensor, end_bit: int = 64):
     sel = C.c_int32(0)
     with torch.cuda.device(keys.device):
         check(lib.b200splat_sort_pairs(n, end_bit, k0.data_ptr(), v0.data_ptr(), k1.data_ptr(), v1.data_ptr(),
-                                       ws.data_ptr(), nbytes, C.byref(sel), _stream()), "b200splat_sort_pairs")
+                                       ws.data_ptr(), nbytes, C.byref(sel), _stream(keys.device)), "b200splat_sort_pairs")
     return (k1, v1) if sel.value else (k0, v0)
 
 
@@ -249,7 +250,7 @@ def inclusive_scan_u32(x: torch.Tensor) -> torch.Tensor:
     nbytes = lib.b200splat_scan_workspace_bytes(n)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
     with torch.cuda.device(x.device):
-        check(lib.b200splat_inclusive_scan_u32(n, x.data_ptr(), out.data_ptr(), ws.data_ptr(), nbytes, _stream()),
+        check(lib.b200splat_inclusive_scan_u32(n, x.data_ptr(), out.data_ptr(), ws.data_ptr(), nbytes, _stream(x.device)),
               "b200splat_inclusive_scan_u32")
     return out
 

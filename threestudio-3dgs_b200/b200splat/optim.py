@@ -65,6 +65,6 @@ class FusedGaussianAdam:
         a.beta1, a.beta2, a.eps = float(self.betas[0]), float(self.betas[1]), float(self.eps)
         a.color_clip = float(min(self.color_clip, 3.0e38))
         a.step = self.steps
-        a.stream = ops._stream()
+        a.stream = ops._stream(self.params["xyz"].device)
         with torch.cuda.device(self.params["xyz"].device):
             check(lib.b200splat_adam_step(C.byref(a)), "b200splat_adam_step")

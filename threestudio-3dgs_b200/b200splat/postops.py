@@ -41,7 +41,7 @@ def _args(mode, shading, image, depth, alpha, rays_o, rays_d, bg, light, pred_no
     a.light, a.pred_normal = ops._ptr(light), ops._ptr(pred_normal)
     a.ambient = (C.c_float * 3)(*ambient)
     a.diffuse = (C.c_float * 3)(*diffuse)
-    a.stream = ops._stream()
+    a.stream = ops._stream(image.device)
     return a
 
 

@@ -95,17 +95,16 @@ class B200GaussianBatchRenderer:
         """A ViewBatchRasterizer (persistent workspace) for this shape whose last graph has been consumed.  Systems that
         render twice before ``backward`` (system/gaussian_zero123.py:212-235: random-camera batch + reference view)
         get a second instance instead of overwriting the first one's saved state."""
-        key = (V, P, H, W, str(device))
-        cache = self.__dict__.setdefault("_b200_rasterizers", {})
-        for k in [k for k in cache if k[1] != P]:       # P changes at every densify / prune: drop stale workspaces
-            del cache[k]
-        pool = cache.setdefault(key, [])
+        key = (V, H, W, str(device))   # not P: a workspace survives densify / prune (it grows when it has to)
+        pool = self.__dict__.setdefault("_b200_rasterizers", {}).setdefault(key, [])
         for rast in pool:
             if not rast.pending:
                 return rast
         if len(pool) >= 4:
-            raise RuntimeError("B200GaussianBatchRenderer: 4 forward passes of the same shape are waiting for their "
-                               "backward; render under torch.no_grad() when no gradient is needed")
+            # four live graphs of one shape: hand out the oldest workspace again; should its graph still run a
+            # backward, that backward raises (generation check) instead of reading another forward's state
+            pool.append(pool.pop(0))
+            return pool[-1]
         pool.append(ViewBatchRasterizer(V, P, H, W, device))
         return pool[-1]
 

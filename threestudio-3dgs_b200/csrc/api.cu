@@ -272,6 +272,13 @@ using namespace b200splat;
 // error reporting for the other translation units that export C-ABI entry points (postops.cu, adam.cu)
 int b200splat_set_error(int code, const char* msg) { return fail(code, "%s", msg); }
 
+// rotations and dL/drotations are accessed as float4 (one 16-byte access per Gaussian)
+static int check_align16(const void* p, const char* what) {
+    if (p && (reinterpret_cast<uintptr_t>(p) & 15))
+        return fail(B200SPLAT_ERR_INVALID, "%s must be 16-byte aligned (it is accessed as float4 per Gaussian)", what);
+    return B200SPLAT_OK;
+}
+
 static int check_extra(int n_extra, const void* features, bool has_out) {
     if (n_extra < 0 || n_extra > EXT_FLOATS)
         return fail(B200SPLAT_ERR_INVALID, "n_extra must be in [0, %d]", EXT_FLOATS);
@@ -311,6 +318,7 @@ static int forward_tail(BatchTab& tab, int debug, cudaStream_t st, bool binning_
 extern "C" {
 
 int b200splat_abi_version(void) { return B200SPLAT_ABI_VERSION; }
+int b200splat_set_staging(int32_t mode) { return set_staging_mode(mode); }
 
 // ---- all-reduce over NVLink peer memory ----------------------------------------------------------
 int b200splat_p2p_alloc(size_t bytes, void** ptr, void* handle_out) {
@@ -407,6 +415,7 @@ int b200splat_forward(const b200splat_forward_args* a) {
     if (has_sr == (a->cov3D_precomp != nullptr))
         return fail(B200SPLAT_ERR_INVALID, "provide exactly one of (scales, rotations) / cov3D_precomp");
     if (has_sh && a->M < 1) return fail(B200SPLAT_ERR_INVALID, "shs given but M < 1");
+    if (int rca = check_align16(a->rotations, "rotations")) return rca;
     if (!a->out_color || !a->out_depth || !a->out_alpha) return fail(B200SPLAT_ERR_INVALID, "null output image");
     BatchTab tab;
     int rc = init_table(a->cam, P, a->M, has_sh, &tab);
@@ -488,6 +497,7 @@ int b200splat_forward_batched(const b200splat_batch_forward_args* a) {
     if (!a->scales || !a->rotations || !a->means3D || !a->opacities)
         return fail(B200SPLAT_ERR_INVALID, "means3D, opacities, scales and rotations are required");
     if (has_sh && a->M < 1) return fail(B200SPLAT_ERR_INVALID, "shs given but M < 1");
+    if (int rca = check_align16(a->rotations, "rotations")) return rca;
     BatchTab tab;
     int rc = init_table(a->cams[0], P, a->M, has_sh, &tab);
     if (rc) return rc;
@@ -522,7 +532,7 @@ int b200splat_forward_batched(const b200splat_batch_forward_args* a) {
     CU(launch_gaussian_sort(tab, st, /*cleared=*/true)); }
     DEBUG_SYNC(a->cams[0], st, "depth sort");
     { ProfScope ps(1, st);
-    CU(launch_scan_batch(tab, st, /*cleared=*/true)); }
+    CU(launch_scan_batch(tab, st, /*cleared=*/true, a->pairs_notify, a->notify_epoch)); }
     DEBUG_SYNC(a->cams[0], st, "scan");
     rc = forward_tail(tab, a->cams[0].debug, st, /*binning_cleared=*/true);
     if (rc) return rc;
@@ -592,6 +602,8 @@ int b200splat_backward(const b200splat_backward_args* a) {
     if (!a->dL_dmeans3D || !a->dL_dmeans2D || !a->dL_dopacity)
         return fail(B200SPLAT_ERR_INVALID, "dL_dmeans3D / dL_dmeans2D / dL_dopacity must be given");
     if (has_sh && !a->dL_dshs) return fail(B200SPLAT_ERR_INVALID, "shs given but dL_dshs is NULL");
+    if (int rca = check_align16(a->rotations, "rotations")) return rca;
+    if (int rca = check_align16(a->dL_drotations, "dL_drotations")) return rca;
     if (!a->scratch || a->scratch_bytes < b200splat_backward_scratch_bytes(P))
         return fail(B200SPLAT_ERR_NOMEM, "scratch too small");
     if (!a->geom_buffer || !a->image_buffer || !a->radii) return fail(B200SPLAT_ERR_INVALID, "null saved buffer");
@@ -629,6 +641,8 @@ int b200splat_backward_batched(const b200splat_batch_backward_args* a) {
     if (!a->dL_dmeans3D || !a->dL_dopacity || !a->dL_dscales || !a->dL_drotations)
         return fail(B200SPLAT_ERR_INVALID, "dL_dmeans3D / dL_dopacity / dL_dscales / dL_drotations must be given");
     if (has_sh && !a->dL_dshs) return fail(B200SPLAT_ERR_INVALID, "shs given but dL_dshs is NULL");
+    if (int rca = check_align16(a->rotations, "rotations")) return rca;
+    if (int rca = check_align16(a->dL_drotations, "dL_drotations")) return rca;
     BatchTab tab;
     int rc = init_table(a->cams[0], P, a->M, has_sh, &tab);
     if (rc) return rc;

@@ -155,7 +155,9 @@ cudaError_t launch_mark_visible(int P, const float* means3D, const float* view, 
                                 uint8_t* present, cudaStream_t st);
 
 size_t scan_workspace_bytes(int64_t n);
-cudaError_t launch_scan_batch(const BatchTab& tab, cudaStream_t st, bool cleared = false);
+// notify / epoch: optional early notice of every view's pair count in host-mapped memory (see b200splat.h)
+cudaError_t launch_scan_batch(const BatchTab& tab, cudaStream_t st, bool cleared = false, uint64_t* notify = nullptr,
+                              uint32_t epoch = 0);
 // zero the small per-view work areas of a forward in one launch (with_binning: also the pair sort's and the tile counts)
 cudaError_t launch_clear_batch(const BatchTab& tab, bool with_binning, cudaStream_t st);   // tiles_touched (in depth order) -> point_offsets
 cudaError_t launch_gaussian_sort(const BatchTab& tab, cudaStream_t st, bool cleared = false);   // gwords[0] sorted by depth bits (stable)
@@ -194,6 +196,7 @@ size_t dist2_workspace_bytes(int P);
 cudaError_t launch_dist2(int P, const float* points, float* out, void* ws, cudaStream_t st);
 
 void count_launch(int n = 1);
+int set_staging_mode(int mode);   // render.cu; returns the previous mode
 
 // ---- all-reduce over NVLink peer memory (p2p.cu) -------------------------------------------------
 constexpr int P2P_MAX_RANKS = 8;

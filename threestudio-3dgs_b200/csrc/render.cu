@@ -28,6 +28,7 @@
 //    one 10-lane global atomic per (warp, Gaussian).
 #include "common.cuh"
 
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 
@@ -630,13 +631,17 @@ render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
     }
 }
 
+// staging mode: -1 = default (environment B200SPLAT_STAGING, else LDGSTS), 0 = LDGSTS, 1 = bulk (UBLKCP)
+static std::atomic<int> g_staging{-1};
+int set_staging_mode(int mode) { return g_staging.exchange(mode < 0 ? -1 : (mode ? 1 : 0)); }
 static bool use_bulk_staging() {
-    static int mode = -1;
-    if (mode < 0) {
+    const int m = g_staging.load(std::memory_order_relaxed);
+    if (m >= 0) return m == 1;
+    static const int env_mode = [] {
         const char* e = getenv("B200SPLAT_STAGING");
-        mode = (e && strcmp(e, "bulk") == 0) ? 1 : 0;
-    }
-    return mode == 1;
+        return (e && strcmp(e, "bulk") == 0) ? 1 : 0;
+    }();
+    return env_mode == 1;
 }
 
 cudaError_t launch_render_forward(const BatchTab& tab, int sel, cudaStream_t st) {

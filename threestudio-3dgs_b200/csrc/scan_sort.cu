@@ -50,6 +50,8 @@ struct ScanTab {
     uint32_t* out[MAX_VIEWS];
     uint32_t* ticket[MAX_VIEWS];
     uint64_t* desc[MAX_VIEWS];
+    uint64_t* notify;   // optional host-mapped words [V]: (epoch << 32 | total) of each view as soon as it is known
+    uint32_t epoch;
 };
 
 __global__ void __launch_bounds__(SCAN_THREADS)
@@ -154,6 +156,12 @@ scan_lookback_kernel(int64_t n, const __grid_constant__ ScanTab tab) {
             if (lane == 0) st_volatile_u64(desc + tile, FLAG_INC | (uint64_t)(excl + block_total));
         }
         if (lane == 0) s_excl = excl;
+        // the last tile knows the view's total (= num_rendered in the pipeline): tell the host right away
+        if (lane == 0 && tab.notify != nullptr && (int64_t)(tile + 1) * SCAN_TILE >= n)
+        {
+            st_volatile_u64(tab.notify + view, ((uint64_t)tab.epoch << 32) | (uint64_t)(excl + block_total));
+            __threadfence_system();
+        }
     }
     __syncthreads();
     const uint32_t off = s_excl + warp_off + (inc - tsum);
@@ -228,12 +236,13 @@ cudaError_t launch_clear_batch(const BatchTab& tab, bool with_binning, cudaStrea
     return cudaGetLastError();
 }
 
-cudaError_t launch_scan_batch(const BatchTab& tab, cudaStream_t st, bool cleared) {
+cudaError_t launch_scan_batch(const BatchTab& tab, cudaStream_t st, bool cleared, uint64_t* notify, uint32_t epoch) {
     const int64_t n = tab.P;
     if (n <= 0) return cudaSuccess;
     const int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     ScanTab s;
     s.V = tab.V;
+    s.notify = notify, s.epoch = epoch;
     for (int v = 0; v < tab.V; ++v) {
         s.perm[v] = tab.v[v].gwords[0];
         s.in[v] = tab.v[v].tiles_touched;
@@ -257,6 +266,7 @@ cudaError_t launch_inclusive_scan(int64_t n, const uint32_t* in, uint32_t* out, 
     if (e != cudaSuccess) return e;
     ScanTab s;
     s.V = 1;
+    s.notify = nullptr, s.epoch = 0;
     s.perm[0] = nullptr;
     s.in[0] = in;
     s.out[0] = out;
