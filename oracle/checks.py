@@ -119,3 +119,42 @@ def check_images(cu, out, bounds, tol, max_frac=0.01):
         neq = (nc != ref) & ~mask
         assert int(neq.sum()) == 0, f"n_contrib differs on {int(neq.sum())} non-borderline pixels"
     return frac, worst
+
+
+def cut_variants(tol=2e-5):
+    """(permissive, strict) cut-offs around the nominal ones: every blend decision that lies within ``tol``
+    (relative; 50 tol for the transmittance test, 1e-6 absolute for power <= 0 -- the windows of
+    ``borderline_bounds``) of a cut-off is taken one way by the first and the other way by the second."""
+    from . import spec
+    perm = O.Cuts(spec.ALPHA_MIN * (1 - tol), spec.T_MIN * (1 - 50 * tol), 1e-6)
+    strict = O.Cuts(spec.ALPHA_MIN * (1 + tol), spec.T_MIN * (1 + 50 * tol), -1e-6)
+    return perm, strict
+
+
+def check_grads_bounded(got, nominal, permissive, strict, tol):
+    """Gradient parity that knows about borderline blend decisions.  For every gradient element
+
+        |got - nominal| <= tol * ||nominal||_inf + |permissive - nominal| + |strict - nominal|
+
+    where the three oracle results differ only in how the decisions that sit on a hard cut-off were taken
+    (``cut_variants``).  An element no such decision touches has all three equal and gets the plain ``tol`` bar; an
+    element a flipped pair feeds may differ by what the flips move (each flagged decision is in exactly one of the
+    two differences, so any combination of flips stays inside the sum).  Returns {name: (plain rel err, number of
+    elements that needed the wider bar)}."""
+    rep = {}
+    for k, ref in nominal.items():
+        if k == "stage" or ref is None:
+            continue
+        g = got[k]
+        assert g is not None, f"missing grad {k}"
+        g = g.detach().cpu().double().reshape(ref.shape)
+        ref64 = ref.double()
+        scale = float(ref64.abs().max().clamp_min(1e-20))
+        slack = (permissive[k].double() - ref64).abs() + (strict[k].double() - ref64).abs()
+        err = (g - ref64).abs()
+        over = err - (tol * scale + slack)
+        assert float(over.max()) <= 0.0, (f"grad {k}: error {float(err.flatten()[over.argmax()]) / scale:.3e} (relative to "
+                                          f"the tensor's max) exceeds {tol} + the borderline slack "
+                                          f"{float(slack.flatten()[over.argmax()]) / scale:.3e}")
+        rep[k] = (float(err.max()) / scale, int((err > tol * scale).sum()))
+    return rep

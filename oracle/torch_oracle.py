@@ -312,7 +312,19 @@ def bin_and_sort(pre, s: Settings):
 # stage a8: renderCUDA forward (front-to-back alpha blending, early termination)
 # ----------------------------------------------------------------------------------------
 
-def _blend_tile(pixx, pixy, xy_x, xy_y, con_a, con_b, con_c, opac, rgb, depth, T0=None):
+class Cuts(NamedTuple):
+    """The three hard cut-offs of the blend loop.  The nominal values are upstream's; the parity tests also run the
+    backward with slightly more permissive / stricter values to learn which gradient elements depend on a decision
+    that a 1-ulp difference between exp() implementations can flip (tests/util.py::check_grads_bounded)."""
+    alpha_min: float = spec.ALPHA_MIN
+    t_min: float = spec.T_MIN
+    power_max: float = 0.0
+
+
+NOMINAL_CUTS = Cuts()
+
+
+def _blend_tile(pixx, pixy, xy_x, xy_y, con_a, con_b, con_c, opac, rgb, depth, T0=None, cuts: Cuts = NOMINAL_CUTS):
     """Blend the entries (already in list order) over the given pixels.
 
     pix*: (Np,) float pixel coordinates.  Per-entry tensors: (G,).  rgb: (G,3).
@@ -326,12 +338,12 @@ def _blend_tile(pixx, pixy, xy_x, xy_y, con_a, con_b, con_c, opac, rgb, depth, T
     G = torch.exp(power)
     raw = opac[None, :] * G
     alpha = raw + (torch.clamp_max(raw.detach(), spec.ALPHA_MAX) - raw.detach())
-    valid = (power.detach() <= 0) & (alpha.detach() >= spec.ALPHA_MIN)
+    valid = (power.detach() <= cuts.power_max) & (alpha.detach() >= cuts.alpha_min)
     a_eff = torch.where(valid, alpha.detach(), torch.zeros_like(alpha))
     first = torch.ones_like(a_eff[:, :1]) if T0 is None else T0[:, None].to(a_eff.dtype)
     # sequential product T_k = T_{k-1} (1 - alpha_k), carry-in first
     T_incl = torch.cumprod(torch.cat([first, 1.0 - a_eff], dim=1), dim=1)[:, 1:]
-    term = valid & (T_incl < spec.T_MIN)
+    term = valid & (T_incl < cuts.t_min)
     stopped = torch.cummax(term.to(torch.int8), dim=1).values.bool()
     blended = valid & ~stopped
     a_use = torch.where(blended, alpha, torch.zeros_like(alpha))
@@ -426,11 +438,14 @@ def rasterize_forward(means3D, means2D, shs, colors_precomp, opacities, scales, 
 # conventions; tile by tile so memory stays bounded.
 # ----------------------------------------------------------------------------------------
 
-def rasterize_backward(inputs, s: Settings, pre, binned, fwd, dL_dcolor, dL_ddepth, dL_dalpha, tiles=None):
+def rasterize_backward(inputs, s: Settings, pre, binned, fwd, dL_dcolor, dL_ddepth, dL_dalpha, tiles=None,
+                       cuts: Cuts = NOMINAL_CUTS):
     """Returns dict of gradients for means3D, means2D, shs, colors_precomp, opacities, scales,
     rotations, cov3D_precomp (None where the input was None).  Also returns the per-Gaussian
     2D-stage gradients (dL/dxy_pix, dL/dconic, dL/dopacity, dL/drgb, dL/ddepth) that the CUDA
-    render-backward kernel emits, for stage-level debugging."""
+    render-backward kernel emits, for stage-level debugging.
+    ``cuts``: non-nominal cut-offs re-decide every blend decision inside this call (the forward's n_contrib only
+    bounds how far each tile's list is read, with a margin)."""
     means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp = inputs
     d = derived_scalars(s)
     W, H, gx, gy = d["W"], d["H"], d["grid_x"], d["grid_y"]
@@ -463,6 +478,8 @@ def rasterize_backward(inputs, s: Settings, pre, binned, fwd, dL_dcolor, dL_ddep
             x0, y0 = tx * spec.BLOCK_X, ty * spec.BLOCK_Y
             x1, y1 = min(x0 + spec.BLOCK_X, W), min(y0 + spec.BLOCK_Y, H)
             nmax = int(ncontrib[y0:y1, x0:x1].max())
+            if cuts is not NOMINAL_CUTS:   # a later termination / an extra blended entry may lie behind n_contrib
+                nmax = min(int(ranges[ty * gx + tx, 1]) - r0, nmax + 64)
             if nmax == 0:
                 continue
             ids = row_of[pl[r0:r0 + nmax]]
@@ -473,7 +490,7 @@ def rasterize_backward(inputs, s: Settings, pre, binned, fwd, dL_dcolor, dL_ddep
             with torch.enable_grad():
                 rgb = torch.stack(loc[6:9], -1)
                 C, D, A, Tf, _, _, _ = _blend_tile(pixx, pixy, loc[0], loc[1], loc[2], loc[3], loc[4],
-                                                loc[5], rgb, loc[9])
+                                                loc[5], rgb, loc[9], cuts=cuts)
                 col = C + Tf[:, None] * bg[None, :]
                 gC = dL_dcolor[:, y0:y1, x0:x1].reshape(3, -1).t()
                 gD = dL_ddepth[0, y0:y1, x0:x1].reshape(-1)

@@ -9,7 +9,8 @@ import torch
 from b200splat import scenes
 from oracle import torch_oracle as O
 from oracle.knn import dist2_oracle
-from util import borderline_bounds, check_images, cuda_settings, oracle_settings, rel_err
+from util import (borderline_bounds, check_grads_bounded, check_images, cuda_settings, cut_variants, oracle_settings,
+                  rel_err)
 
 pytestmark = pytest.mark.gpu
 
@@ -51,8 +52,12 @@ def _run_oracle(sc, s, *, colors_precomp=None, cov3D=None, shs=None, grads=None)
     out, pre, binned = O.rasterize_forward(sc.means3D, None, shs, colors_precomp, sc.opacities, scl, rot, cov3D, s)
     res = dict(out=out, pre=pre, binned=binned)
     if grads is not None:
-        res["grads"] = O.rasterize_backward((sc.means3D, None, shs, colors_precomp, sc.opacities, scl, rot, cov3D),
-                                            s, pre, binned, out, *grads)
+        inputs = (sc.means3D, None, shs, colors_precomp, sc.opacities, scl, rot, cov3D)
+        res["grads"] = O.rasterize_backward(inputs, s, pre, binned, out, *grads)
+        # the same backward with every borderline blend decision taken the permissive / the strict way
+        perm, strict = cut_variants()
+        res["grads_perm"] = O.rasterize_backward(inputs, s, pre, binned, out, *grads, cuts=perm)
+        res["grads_strict"] = O.rasterize_backward(inputs, s, pre, binned, out, *grads, cuts=strict)
     return res
 
 
@@ -69,14 +74,9 @@ def _check_forward(cu, orc, s, allow_borderline=True):
 
 
 def _check_grads(cu, orc, tol=GRAD_TOL):
-    for k, ref in orc["grads"].items():
-        if k == "stage" or ref is None:
-            continue
-        got = cu["grads"][k]
-        assert got is not None, f"missing grad {k}"
-        assert got.shape == ref.shape, (k, got.shape, ref.shape)
-        e = rel_err(got, ref)
-        assert e <= tol, f"grad {k}: rel err {e} > {tol}"
+    """<= 1e-3 relative for every gradient element no borderline blend decision feeds; an element such a decision
+    feeds may differ by what flipping it moves (oracle/checks.py::check_grads_bounded)."""
+    return check_grads_bounded(cu["grads"], orc["grads"], orc["grads_perm"], orc["grads_strict"], tol)
 
 
 def _scene(P, deg, H, W, seed, r0=0.8, scale_mul=1.0):
@@ -566,12 +566,10 @@ def _full_scale_parity(scene, cam, bg=(1.0, 1.0, 1.0), seed=5, colors_precomp=No
     frac, worst = check_images(dict(color=color, depth=depth, alpha=alpha, n_contrib=v["n_contrib"]), out, bounds,
                                IMG_TOL)
     g = ops.backward(camc, st, m3, sh, cp, op, scl, rot, None, radii, alpha, *(t.cuda() for t in grads))
-    errs = {}
-    for k, ref in orc["grads"].items():
-        if k == "stage" or ref is None:
-            continue
-        errs[k] = rel_err(g[k], ref)
-        assert errs[k] <= GRAD_TOL, f"grad {k}: rel err {errs[k]} > {GRAD_TOL}"
+    errs = _check_grads(dict(grads=g), orc)
+    wide = sum(n for _, n in errs.values())
+    total = sum(t.numel() for k, t in orc["grads"].items() if k != "stage" and t is not None)
+    assert wide <= 1e-4 * total, f"{wide} of {total} gradient elements needed the borderline slack"
     return dict(borderline_frac=frac, worst=worst, grad_err=errs, R=st.num_rendered)
 
 

@@ -5,7 +5,8 @@ import torch
 
 from b200splat import scenes
 from oracle import torch_oracle as O
-from oracle.checks import borderline_bounds, borderline_pixels, check_images  # noqa: F401  (re-exported)
+from oracle.checks import (borderline_bounds, borderline_pixels, check_grads_bounded, check_images,  # noqa: F401
+                           cut_variants)
 
 
 def oracle_settings(cam: scenes.Camera, sh_degree: int, bg=(1.0, 1.0, 1.0), scale_modifier=1.0) -> O.Settings:
