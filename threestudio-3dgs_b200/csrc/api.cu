@@ -102,6 +102,8 @@ size_t image_layout(int H, int W, void* base, ImageViews* v) {
     im.tile_order = carve<uint32_t>(p, (size_t)gx * gy * MAX_VIEWS);
     im.status = carve<uint32_t>(p, STATUS_WORDS);
     im.tile_count = carve<uint32_t>(p, (size_t)gx * gy);
+    im.block_last = carve<uint32_t>(p, (size_t)gx * gy * (BLOCK_SIZE / 32));
+    im.block_order = carve<uint32_t>(p, 4 + (size_t)gx * gy * (BLOCK_SIZE / 32) * MAX_VIEWS);
     if (v) *v = im;
     return (size_t)(p - p0);
 }
@@ -192,13 +194,15 @@ static void fill_geom(int P, void* geom, ViewTab* vt, const float4** ext4 = null
     vt->scan_desc = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(g.scan_ws) + 16);
 }
 
-static void fill_image(int H, int W, void* image, ViewTab* vt, uint32_t** tile_order) {
+static void fill_image(int H, int W, void* image, ViewTab* vt, uint32_t** tile_order, uint32_t** block_order = nullptr) {
     ImageViews im;
     image_layout(H, W, image, &im);
     vt->ranges = im.ranges, vt->n_contrib = im.n_contrib, vt->n_visited = im.n_visited, vt->final_T = im.final_T;
     vt->status = im.status;
     vt->tile_count = im.tile_count;
+    vt->block_last = im.block_last;
     if (tile_order) *tile_order = im.tile_order;
+    if (block_order) *block_order = im.block_order;
 }
 
 static void fill_binning(int64_t capacity, void* binning, ViewTab* vt) {
@@ -426,7 +430,7 @@ int b200splat_forward(const b200splat_forward_args* a) {
     if (rc) return rc;
     if (!a->image_buffer || a->image_bytes < image_layout(tab.H, tab.W, nullptr, nullptr))
         return fail(B200SPLAT_ERR_NOMEM, "image_buffer too small");
-    fill_image(tab.H, tab.W, a->image_buffer, &vt, &tab.tile_order);
+    fill_image(tab.H, tab.W, a->image_buffer, &vt, &tab.tile_order, &tab.block_order);
     vt.out_color = a->out_color, vt.out_depth = a->out_depth, vt.out_alpha = a->out_alpha;
     vt.radii = a->radii;
     rc = check_extra(a->n_extra, a->extra_features, a->out_extra != nullptr);
@@ -517,7 +521,8 @@ int b200splat_forward_batched(const b200splat_batch_forward_args* a) {
             return fail(B200SPLAT_ERR_INVALID, "null buffer for view %d", v);
         vt.out_extra = tab.n_extra > 0 ? a->out_extra[v] : nullptr;
         fill_geom(P, a->geom_buffer[v], &vt, v == 0 ? &tab.ext4 : nullptr);
-        fill_image(tab.H, tab.W, a->image_buffer[v], &vt, v == 0 ? &tab.tile_order : nullptr);
+        fill_image(tab.H, tab.W, a->image_buffer[v], &vt, v == 0 ? &tab.tile_order : nullptr,
+                   v == 0 ? &tab.block_order : nullptr);
         fill_binning(cap, a->binning_buffer[v], &vt);
         vt.out_color = a->out_color[v], vt.out_depth = a->out_depth[v], vt.out_alpha = a->out_alpha[v];
         vt.radii = a->radii[v];
@@ -572,7 +577,10 @@ static int backward_run(BatchTab& tab, const float* means3D, const float* scales
                 if (tab.n_extra > 0)
                     CU(cudaMemsetAsync(tab.v[v].gradext, 0, (size_t)tab.P * EXT_FLOATS * sizeof(float), st));
             }
-        if (any_pairs) CU(launch_render_backward(tab, sel, st));
+        if (any_pairs) {
+            CU(launch_block_order(tab, st));
+            CU(launch_render_backward(tab, sel, st));
+        }
     }
     DEBUG_SYNC(dbg, st, "render backward");
     if (phase != 1) {
@@ -611,7 +619,7 @@ int b200splat_backward(const b200splat_backward_args* a) {
     if (rc) return rc;
     tab.n_extra = a->n_extra;
     fill_geom(P, const_cast<void*>(a->geom_buffer), &vt, &tab.ext4);
-    fill_image(tab.H, tab.W, const_cast<void*>(a->image_buffer), &vt, &tab.tile_order);
+    fill_image(tab.H, tab.W, const_cast<void*>(a->image_buffer), &vt, &tab.tile_order, &tab.block_order);
     vt.radii = const_cast<int32_t*>(a->radii);
     if (a->num_rendered > 0) {
         if (!a->binning_buffer) return fail(B200SPLAT_ERR_INVALID, "null binning buffer");
@@ -662,7 +670,8 @@ int b200splat_backward_batched(const b200splat_batch_backward_args* a) {
         fill_geom(P, const_cast<void*>(a->geom_buffer[v]), &vt, v == 0 ? &tab.ext4 : nullptr);
         vt.gradext = reinterpret_cast<float*>(reinterpret_cast<char*>(a->scratch[v]) + grad2d_bytes(P));
         vt.dL_dextra = (tab.n_extra > 0 && a->dL_dout_extra) ? a->dL_dout_extra[v] : nullptr;
-        fill_image(tab.H, tab.W, const_cast<void*>(a->image_buffer[v]), &vt, v == 0 ? &tab.tile_order : nullptr);
+        fill_image(tab.H, tab.W, const_cast<void*>(a->image_buffer[v]), &vt, v == 0 ? &tab.tile_order : nullptr,
+                   v == 0 ? &tab.block_order : nullptr);
         fill_binning(cap, const_cast<void*>(a->binning_buffer[v]), &vt);
         vt.radii = const_cast<int32_t*>(a->radii[v]);
         vt.dL_dcolor = a->dL_dout_color ? a->dL_dout_color[v] : nullptr;

@@ -34,7 +34,8 @@ constexpr float PW_EPS = 0.0000001f;
 //   cull_thr = 2 ln(255 opacity) + margin: the largest value of the conic quadratic at which alpha >= 1/255
 constexpr int REC_FLOATS = 12;
 // packed 2-D stage gradients accumulated by render-backward (48 B per Gaussian)
-//   g0 = (dx, dy, dconic_a, dconic_b)  g1 = (dconic_c, dopacity, dr, dg)  g2 = (db, ddepth, 0, 0)
+//   g0 = (dx, dy, 2 dconic_a, dconic_b)  g1 = (2 dconic_c, dopacity, dr, dg)  g2 = (db, ddepth, 0, 0)
+//   (the consumer applies the factor 1/2 of the two diagonal conic terms)
 constexpr int GRAD2D_FLOATS = 12;
 
 constexpr int RADIX_BITS = 8;
@@ -80,6 +81,7 @@ struct ViewTab {
     float* final_T;
     uint32_t* status;
     uint32_t* tile_count;  // [T] pairs per tile, accumulated by duplicateWithKeys (ranges = its exclusive scan)
+    uint32_t* block_last;  // [T * 8] largest n_contrib of every 8x4 pixel block (written by render forward)
     float* out_color;
     float* out_depth;
     float* out_alpha;
@@ -109,6 +111,8 @@ struct BatchTab {
     int n_extra;               // 0..4 extra per-Gaussian feature channels rendered next to the colour
     const float4* ext4;        // [P] the extra features padded to 16 B (view independent; lives in view 0's geometry)
     uint32_t* tile_order;      // [V * T] entries (view * T + tile), longest list first
+    uint32_t* block_order;     // [1 + V * T * 8]: count, then the batch's non-empty 8x4 blocks ((view * T + tile) * 8 + block),
+                               // most list entries to walk first: the work items of render backward
     ViewTab v[MAX_VIEWS];
 };
 
@@ -138,6 +142,8 @@ struct ImageViews {
     float* final_T;          // H * W  (transmittance after the last blended entry; 1 - alpha loses bits)
     uint32_t* n_visited;     // H * W  (list entries traversed by the pixel in forward)
     uint32_t* tile_order;    // MAX_VIEWS * T (a batch uses view 0's copy)
+    uint32_t* block_last;    // T * 8
+    uint32_t* block_order;   // 4 + MAX_VIEWS * T * 8 (a batch uses view 0's copy)
     uint32_t* status;        // STATUS_WORDS
     uint32_t* tile_count;    // T
 };
@@ -175,6 +181,7 @@ cudaError_t launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_
 // pipeline sort: histograms already accumulated by duplicateWithKeys, n read from the device per view
 cudaError_t launch_sort_batch(const BatchTab& tab, cudaStream_t st);
 cudaError_t launch_tile_ranges_batch(const BatchTab& tab, int sel, cudaStream_t st);   // + tile order
+cudaError_t launch_block_order(const BatchTab& tab, cudaStream_t st);   // work order of render backward (after forward)
 
 cudaError_t launch_render_forward(const BatchTab& tab, int sel, cudaStream_t st);
 cudaError_t launch_render_backward(const BatchTab& tab, int sel, cudaStream_t st);

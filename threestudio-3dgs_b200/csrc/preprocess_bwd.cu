@@ -301,7 +301,8 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
         const float* mP = sP[v];
         float4* slot = s_slots + ((size_t)v * 128 + threadIdx.x) * 3;
         const float4 g0 = slot[0], g1 = slot[1], g2 = slot[2];
-        const float g_px = g0.x, g_py = g0.y, g_ca = g0.z, g_cb = g0.w, g_cc = g1.x, g_op = g1.y;
+        // render backward leaves the two diagonal conic gradients without their factor 1/2 (render.cu K7)
+        const float g_px = g0.x, g_py = g0.y, g_ca = 0.5f * g0.z, g_cb = g0.w, g_cc = 0.5f * g1.x, g_op = g1.y;
         float g_rgb[3] = {g1.z, g1.w, g2.x};
         const float g_depth = g2.y;
 

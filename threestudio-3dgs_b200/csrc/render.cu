@@ -34,8 +34,6 @@
 
 namespace b200splat {
 
-constexpr int BATCH = 64;    // list entries per warp batch (2 per lane)
-constexpr int STAGES = 3;    // ring depth: two batches in flight while one is blended
 constexpr int WARPS_PER_TILE = BLOCK_SIZE / 32;
 constexpr int ILP = 4;   // survivors whose alpha is evaluated together (hides the LDS/MUFU latency chain)
 
@@ -309,6 +307,10 @@ render_forward_kernel(const __grid_constant__ BatchTab tab, int sel) {
             }
         }
     }
+    {   // the block's largest n_contrib: how far render backward has to walk the list for these 32 pixels
+        const uint32_t wl = __reduce_max_sync(0xffffffffu, inside ? last_contributor : 0u);
+        if (lane == 0) vt.block_last[tile * WARPS_PER_TILE + warp] = wl;
+    }
     if (inside) {
         const int pix = pyi * W + pxi;
         const size_t HW = (size_t)H * W;
@@ -332,109 +334,80 @@ render_forward_kernel(const __grid_constant__ BatchTab tab, int sel) {
 // ============================================================================================
 // K7 backward
 // ============================================================================================
+//
+// Per pixel, walking its tile's list back to front over the entries that were blended in the forward:
+//
+//     T_i   = T_{i+1} / (1 - alpha_i)                          transmittance in front of entry i
+//     dot_i = g_C . c_i + g_D z_i + g_A                        (+ g_E . e_i with extra channels)
+//     dL/dalpha_i = dot_i T_i - S_i / (1 - alpha_i),           S_i = sum_{j > i} dot_j alpha_j T_j + T_final (g_C . bg)
+//
+// i.e. ONE scalar suffix sum S instead of upstream's five normalised per-channel recurrences
+// (accum_rec = last_alpha last_c + (1 - last_alpha) accum_rec; (c - accum_rec) g T): the same derivative of
+// C = sum_j c_j alpha_j T_j + T_final bg, written with the pixel gradient contracted first.  It costs 5 dependent
+// operations per blended pair instead of ~25.
+//
+// The 10 (14 with extra channels) partial gradients of a Gaussian are summed over the warp's 32 pixels through shared
+// memory: every lane stores its partials of the ILP survivors of a group as rows of a [32 lanes][ILP * 12 (16)] matrix
+// (3 or 4 STS.128 per survivor), then lane (c, h) sums float4-column c over the 16 rows of half h (16 LDS.128), the two
+// halves are combined with 4 shuffles, and the lanes holding a column issue ONE 16-byte vector reduction
+// (red.global.add.v4.f32) each into the Gaussian's 48-byte gradient record.  Per survivor that is ~27 instructions
+// and 3 vector atomics; the 12-shuffle transposed butterfly it replaces cost 46 (12 SHFL + 22 SEL + 12 FADD) and 10
+// scalar atomics.
 
-// Sum 10 per-lane values over the 32 lanes with 12 shuffles (transposed butterfly): after the call the
-// lane whose slot (see reduce_slot) is k holds the warp total of v[k] in the return value.
-__device__ __forceinline__ float warp_reduce10(const float v[10], int lane) {
-    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
-    float a[5];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        const float send = b4 ? v[k] : v[k + 5];
-        const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
-        a[k] = (b4 ? v[k + 5] : v[k]) + recv;
-    }
-    float c[3];
-    {
-        // keep (a0,a1,a2) when b3 == 0, (a3,a4,-) when b3 == 1
-        float send = b3 ? a[0] : a[3];
-        float recv = __shfl_xor_sync(0xffffffffu, send, 8);
-        c[0] = (b3 ? a[3] : a[0]) + recv;
-        send = b3 ? a[1] : a[4];
-        recv = __shfl_xor_sync(0xffffffffu, send, 8);
-        c[1] = (b3 ? a[4] : a[1]) + recv;
-        send = b3 ? a[2] : 0.f;
-        recv = __shfl_xor_sync(0xffffffffu, send, 8);
-        c[2] = (b3 ? 0.f : a[2]) + recv;
-    }
-    float d[2];
-    {
-        // keep (c0,c1) when b2 == 0, (c2,-) when b2 == 1
-        float send = b2 ? c[0] : c[2];
-        float recv = __shfl_xor_sync(0xffffffffu, send, 4);
-        d[0] = (b2 ? c[2] : c[0]) + recv;
-        send = b2 ? c[1] : 0.f;
-        recv = __shfl_xor_sync(0xffffffffu, send, 4);
-        d[1] = (b2 ? 0.f : c[1]) + recv;
-    }
-    float e;
-    {
-        const float send = b1 ? d[0] : d[1];
-        const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
-        e = (b1 ? d[1] : d[0]) + recv;
-    }
-    e += __shfl_xor_sync(0xffffffffu, e, 1);
-    return e;
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
-// index k (0..9) of the value a lane ends up holding, or -1
-__device__ __forceinline__ int reduce_slot(int lane) {
-    if (lane & 1) return -1;
-    const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1, b1 = (lane >> 1) & 1;
-    int k;
-    if (!b3) {
-        if (!b2) k = b1; else k = b1 ? -1 : 2;
-    } else {
-        if (!b2) k = 3 + b1; else k = -1;
-    }
-    return k < 0 ? -1 : 5 * b4 + k;
+__device__ __forceinline__ void red_add_v4(float* addr, const float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
 }
 
-// Sum 4 per-lane values over the warp with 6 shuffles; afterwards the lanes with (lane & 7) == 0 hold the total of
-// v[2 * bit4 + bit3] (reduce_slot4).
-__device__ __forceinline__ float warp_reduce4(const float v[4], int lane) {
-    const bool b4 = lane & 16, b3 = lane & 8;
-    float a0, a1;
-    {
-        float send = b4 ? v[0] : v[2];
-        float recv = __shfl_xor_sync(0xffffffffu, send, 16);
-        a0 = (b4 ? v[2] : v[0]) + recv;
-        send = b4 ? v[1] : v[3];
-        recv = __shfl_xor_sync(0xffffffffu, send, 16);
-        a1 = (b4 ? v[3] : v[1]) + recv;
-    }
-    float c;
-    {
-        const float send = b3 ? a0 : a1;
-        const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
-        c = (b3 ? a1 : a0) + recv;
-    }
-    c += __shfl_xor_sync(0xffffffffu, c, 4);
-    c += __shfl_xor_sync(0xffffffffu, c, 2);
-    c += __shfl_xor_sync(0xffffffffu, c, 1);
-    return c;
+// packed fp32 pairs (Blackwell FADD2 / FMUL2 / FFMA2: two fp32 operations per issue slot)
+__device__ __forceinline__ float2 add2(const float2 a, const float2 b) {
+    float2 r;
+    asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
 }
-__device__ __forceinline__ int reduce_slot4(int lane) {
-    return (lane & 7) ? -1 : 2 * ((lane >> 4) & 1) + ((lane >> 3) & 1);
+__device__ __forceinline__ float2 mul2(const float2 a, const float2 b) {
+    float2 r;
+    asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
 }
 
-template <bool BULK, bool EXT>
-__global__ void __launch_bounds__(32, EXT ? 16 : 1)   // EXT: cap at 128 registers (150 uncapped -> 13 warps per SM)
+constexpr int BWD_BATCH = 64;   // list entries per warp batch (two per lane)
+// BWD_STAGES: ring depth (3: two batches in flight while one is processed; 2: one in flight, 3.4 KB less shared memory)
+template <bool BULK, bool EXT, int BWD_STAGES>
+__global__ void __launch_bounds__(32, EXT ? 12 : (BWD_STAGES == 2 ? 16 : 13))
 render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
-    __shared__ __align__(16) float4 s_rec[STAGES][BATCH * 3];
-    __shared__ __align__(16) float4 s_ext[STAGES][EXT ? BATCH : 1];
-    __shared__ uint32_t s_ids[STAGES][BATCH];
-    __shared__ __align__(8) uint64_t s_bar[STAGES];
-    __shared__ __align__(16) uint8_t s_surv[BATCH + 16];
+    constexpr int F4 = EXT ? 4 : 3;        // float4s of a survivor's reduced record: 10 gradients + 2 pad (+ 4 extra)
+    constexpr int NC4 = ILP * F4;          // float4 columns of a group's matrix
+    constexpr int RS = NC4 * 4 + 4;        // row stride in floats (52 / 68: STS.128 of 8 neighbouring lanes hit 8 bank groups)
+    constexpr int PER_LANE = BWD_BATCH / 32;
+    __shared__ __align__(16) float4 s_rec[BWD_STAGES][BWD_BATCH * 3];
+    __shared__ __align__(16) float4 s_ext[BWD_STAGES][EXT ? BWD_BATCH : 1];
+    __shared__ uint32_t s_ids[BWD_STAGES][BWD_BATCH];
+    __shared__ __align__(8) uint64_t s_bar[BWD_STAGES];
+    __shared__ __align__(16) float s_red[32 * RS];
 
     const int W = tab.W, H = tab.H, grid_x = tab.grid_x;
     const int n_tiles = grid_x * tab.grid_y;
-    const uint32_t entry = tab.tile_order[blockIdx.x / WARPS_PER_TILE];   // longest lists of the batch first (LPT)
-    const int wblock = blockIdx.x % WARPS_PER_TILE;
+    // work item: a non-empty 8x4 block of the batch, longest walk first (block_order_kernel); launched over all blocks
+    if (blockIdx.x >= tab.block_order[0]) return;
+    const uint32_t item = tab.block_order[4 + blockIdx.x];
+    const uint32_t entry = item / WARPS_PER_TILE;
+    const int wblock = (int)(item % WARPS_PER_TILE);
     const ViewTab& vt = tab.v[entry / n_tiles];
     const int tile = (int)(entry % n_tiles);
     const int tile_x = tile % grid_x, tile_y = tile / grid_x;
-    const PointList point_list{tab.idx_bits ? vt.keys[sel] : nullptr, vt.vals[sel],
-                               tab.idx_bits ? (uint32_t)((1ull << tab.idx_bits) - 1ull) : 0xffffffffu};
+    // the sorted list: low halves of the packed pair words (tile << 32 | gaussian), or a plain index array
+    const uint32_t* __restrict__ list = tab.idx_bits ? reinterpret_cast<const uint32_t*>(vt.keys[sel]) : vt.vals[sel];
+    const int list_stride = tab.idx_bits ? 2 : 1;
     const float* __restrict__ rec = vt.rec;
     const float4* __restrict__ ext4 = tab.ext4;
     const float* __restrict__ bg = vt.bg;
@@ -443,7 +416,6 @@ render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
     int lx, ly;
     thread_pixel(wblock, lx, ly);
     const int lane = threadIdx.x;
-    const uint32_t lt_mask = (1u << lane) - 1u;
     const int pxi = tile_x * BLOCK_X + lx, pyi = tile_y * BLOCK_Y + ly;
     const bool inside = pxi < W && pyi < H;
     const float pixx = (float)pxi, pixy = (float)pyi;
@@ -454,14 +426,57 @@ render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
     const uint32_t r0 = vt.ranges[2 * tile];
 
     const uint32_t my_last = inside ? vt.n_contrib[pix] : 0u;
-    uint32_t warp_last = my_last;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, o));
-    const int total = (int)warp_last;  // entries [0,total) of the tile's list can have contributed to this block
+    const int total = (int)__reduce_max_sync(0xffffffffu, my_last);  // entries [0,total) can have contributed to this block
     if (total == 0) return;
-    const int rounds = (total + BATCH - 1) / BATCH;
-    const int slot = reduce_slot(lane);
-    const int slot4 = reduce_slot4(lane);
+    const int rounds = (total + BWD_BATCH - 1) / BWD_BATCH;
+
+    // Batch b holds list positions total-1-(b*64+t), t = 0..63 (back to front), slot t = lane + 32 u.  The list word
+    // (-> Gaussian index) of a batch is loaded one iteration before its record is gathered and is not touched until
+    // then, so the gather's address is in a register when it is issued: the dependent chain word -> record is split
+    // over two iterations instead of stalling the warp in the middle of one.
+    auto load_ids = [&](int bb, uint32_t (&id)[PER_LANE]) {
+#pragma unroll
+        for (int u = 0; u < PER_LANE; ++u) {
+            const int p = bb * BWD_BATCH + lane + 32 * u;
+            id[u] = 0xffffffffu;
+            if (bb < rounds && p < total) id[u] = __ldg(list + (size_t)list_stride * ((size_t)r0 + (size_t)(total - 1 - p)));
+        }
+    };
+    auto stage = [&](int bb, const uint32_t (&id)[PER_LANE]) {
+        const int st = bb % BWD_STAGES;
+        uint64_t* bar = &s_bar[st];
+#pragma unroll
+        for (int u = 0; u < PER_LANE; ++u) {
+            const int sl = lane + 32 * u;
+            if (id[u] != 0xffffffffu) {
+                s_ids[st][sl] = id[u];
+                const float* src = rec + (size_t)id[u] * REC_FLOATS;
+                float4* dst = s_rec[st] + 3 * sl;
+                if (BULK) {
+                    mbar_arrive_expect_tx(bar, REC_FLOATS * 4 + (EXT ? 16 : 0));
+                    bulk_g2s(dst, src, REC_FLOATS * 4, bar);
+                    if (EXT) bulk_g2s(s_ext[st] + sl, ext4 + id[u], 16, bar);
+                } else {
+                    cp_async16(dst, src);
+                    cp_async16(dst + 1, src + 4);
+                    cp_async16(dst + 2, src + 8);
+                    if (EXT) cp_async16(s_ext[st] + sl, ext4 + id[u]);
+                    cp_async_arrive_noinc(bar);
+                }
+            } else {
+                mbar_arrive(bar);
+            }
+        }
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < BWD_STAGES; ++st) mbar_init(&s_bar[st], BWD_BATCH);
+        mbar_fence_init();
+    }
+    uint32_t id_a[PER_LANE], id_b[PER_LANE], id_next[PER_LANE];
+    load_ids(0, id_a);
+    load_ids(1, id_b);
+    if (BWD_STAGES == 3) load_ids(2, id_next);
 
     const float T_final = inside ? vt.final_T[pix] : 0.0f;
     float T = T_final;
@@ -471,47 +486,55 @@ render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
         if (vt.dL_ddepth) gD = vt.dL_ddepth[pix];
         if (vt.dL_dalpha) gA = vt.dL_dalpha[pix];
     }
-    float gE[EXT_FLOATS] = {0.f, 0.f, 0.f, 0.f}, accE[EXT_FLOATS] = {0.f, 0.f, 0.f, 0.f},
-          lE[EXT_FLOATS] = {0.f, 0.f, 0.f, 0.f};
+    float gE[EXT_FLOATS] = {0.f, 0.f, 0.f, 0.f};
     if (EXT && inside && vt.dL_dextra) {
 #pragma unroll
         for (int c = 0; c < EXT_FLOATS; ++c)
             if (c < tab.n_extra) gE[c] = vt.dL_dextra[c * HW + pix];
     }
-    const float bg_dot = bg[0] * gC0 + bg[1] * gC1 + bg[2] * gC2;
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accD = 0.f, accA = 0.f;
-    float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, lD = 0.f;
+    // suffix sum of dot_j alpha_j T_j over the entries behind the current one; the background is the last "entry"
+    float S = T_final * (bg[0] * gC0 + bg[1] * gC1 + bg[2] * gC2);
 
-    if (lane == 0) {
+    // reduction roles: lane (c4, half) sums float4-column c4 of s_red over rows [16 half, 16 half + 16).  Half 1 walks
+    // its rows starting 4 further down (rows 20..31, 16..19): row r of half 0 and row 16 + (r + 4) % 16 of half 1 are
+    // 16 banks apart, so the quarter-warp that mixes columns of both halves (lanes 8..15 without extra channels) is
+    // conflict free.
+    const int c4 = lane % NC4, half = lane / NC4;             // half >= 2: idle in the column sums (non-EXT lanes 24..31)
+    const bool red_active = half < 2;
+    const float4* red_src = reinterpret_cast<const float4*>(s_red + (red_active && half ? 20 : 0) * RS) + c4;   // steps 0..11
+    const float4* red_src2 = red_src + (half == 1 ? -4 : 12) * (RS / 4);                                         // steps 12..15
+    float4* my_row = reinterpret_cast<float4*>(s_red + lane * RS);
+    const int red_k = c4 / F4, red_part = c4 % F4;            // survivor of the group / float4 of its record this lane owns
+    // the two pad floats of every record are zero for the whole kernel (only .xy of its third float4 is ever stored)
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) mbar_init(&s_bar[s], BATCH);
-        mbar_fence_init();
-    }
+    for (int k = 0; k < ILP; ++k) my_row[k * F4 + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    // per-survivor results of phase 1 (registers reused from group to group)
+    float a_h[ILP], og_h[ILP], G_h[ILP], inv1m[ILP], ddx[ILP], ddy[ILP], cA[ILP], cB[ILP], cC[ILP], dot[ILP];
+    float4 ex[ILP];
+    uint32_t jpack = 0, anyhit = 0;   // slots of the group's survivors (one byte each); which of them hit some pixel
+
     __syncwarp();
-    // batch b holds list positions total-1-(b*64+t), t = 0..63 (back to front)
-    auto stage = [&](int b) {
-        const int s = b % STAGES;
+    constexpr int AHEAD = BWD_STAGES - 1;   // batches in flight
+    stage(0, id_a);
+    if (AHEAD == 2) {
+        if (rounds > 1) stage(1, id_b);
+    } else {
 #pragma unroll
-        for (int u = 0; u < BATCH / 32; ++u) {
-            const int sl = lane + 32 * u;
-            const int p = b * BATCH + sl;
-            stage_entry<BULK, EXT>(s_rec[s], s_ids[s], &s_bar[s], rec, point_list, sl, (int64_t)r0 + (total - 1 - p),
-                                   p < total, s_ext[s], ext4);
-        }
-    };
-    stage(0);
-    if (rounds > 1) stage(1);
+        for (int u = 0; u < PER_LANE; ++u) id_next[u] = id_b[u];
+    }
     for (int b = 0; b < rounds; ++b) {
         __syncwarp();   // every lane finished with the slot refilled below (batch b-1's)
-        if (b + 2 < rounds) stage(b + 2);
-        const int s = b % STAGES;
-        mbar_wait(&s_bar[s], (b / STAGES) & 1);
-        const int count = min(BATCH, total - b * BATCH);
-        const float4* __restrict__ buf = s_rec[s];
-        int nsurv = 0;
+        if (b + AHEAD < rounds) stage(b + AHEAD, id_next);
+        load_ids(b + AHEAD + 1, id_next);
+        const int st = b % BWD_STAGES;
+        mbar_wait(&s_bar[st], (b / BWD_STAGES) & 1);
+        const int count = min(BWD_BATCH, total - b * BWD_BATCH);
+        const float4* __restrict__ buf = s_rec[st];
+        unsigned long long surv = 0ull;   // survivors of the batch, bit = slot (list order = bit order)
 #pragma unroll
-        for (int c = 0; c < BATCH / 32; ++c) {
-            const int e = c * 32 + lane;
+        for (int u = 0; u < PER_LANE; ++u) {
+            const int e = lane + 32 * u;
             bool keep = false;
             if (e < count) {
                 const float4 q0 = buf[3 * e];
@@ -519,113 +542,102 @@ render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
                 const float thr = buf[3 * e + 2].z;
                 keep = cull_keep(q0, q1.x, thr, X0, X1, Y0, Y1);
             }
-            const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-            if (keep) s_surv[nsurv + __popc(bal & lt_mask)] = (uint8_t)e;
-            nsurv += __popc(bal);
+            surv |= (unsigned long long)__ballot_sync(0xffffffffu, keep) << (32 * u);
         }
-        __syncwarp();
-        for (int i = 0; i < nsurv; i += ILP) {
-            const uint32_t packed = *reinterpret_cast<const uint32_t*>(s_surv + i);
-            int j[ILP];
-            float v[ILP][10];
-            bool hit[ILP];
-            float G[ILP], alpha[ILP], inv1m[ILP], ddx[ILP], ddy[ILP], cA[ILP], cB[ILP], cC[ILP], op[ILP];
-            float cr[ILP], cg[ILP], cb[ILP], cd[ILP];
-            float ve[ILP][EXT_FLOATS];
-            float4 ex[ILP];
+        // ---- phase 1: ILP survivors evaluated independently (LDS / MUFU latencies overlap) -----------------------
+        auto eval_group = [&]() {
+            jpack = 0, anyhit = 0;
 #pragma unroll
             for (int k = 0; k < ILP; ++k) {
-                const bool has = i + k < nsurv;
-                j[k] = has ? (int)((packed >> (8 * k)) & 0xffu) : (int)(packed & 0xffu);
-                const float4 q0 = buf[3 * j[k]];
-                const float4 q1 = buf[3 * j[k] + 1];
-                const float2 q2 = *reinterpret_cast<const float2*>(buf + 3 * j[k] + 2);
-                if (EXT) ex[k] = s_ext[s][j[k]];
-                const uint32_t q = (uint32_t)(total - 1 - (b * BATCH + j[k]));
+                const bool has = surv != 0ull;
+                const int j = has ? __ffsll((long long)surv) - 1 : 0;
+                surv &= surv - 1ull;
+                jpack |= (uint32_t)j << (8 * k);
+                const float4 q0 = buf[3 * j];
+                const float4 q1 = buf[3 * j + 1];
+                const float2 q2 = *reinterpret_cast<const float2*>(buf + 3 * j + 2);
+                const uint32_t q = (uint32_t)(total - 1 - (b * BWD_BATCH + j));
                 ddx[k] = q0.x - pixx, ddy[k] = q0.y - pixy;
-                cA[k] = q0.z, cB[k] = q0.w, cC[k] = q1.x, op[k] = q1.y;
+                cA[k] = q0.z, cB[k] = q0.w, cC[k] = q1.x;
                 const float power = -0.5f * (cA[k] * ddx[k] * ddx[k] + cC[k] * ddy[k] * ddy[k]) - cB[k] * ddx[k] * ddy[k];
-                G[k] = __expf(power);
-                alpha[k] = fminf(ALPHA_MAX, op[k] * G[k]);
-                inv1m[k] = __fdividef(1.0f, 1.0f - alpha[k]);   // MUFU.RCP + FMUL; 1 - alpha is in [0.01, 1]
-                hit[k] = has && (q < my_last) && (power <= 0.0f) && (alpha[k] >= ALPHA_MIN);
-                cr[k] = q1.w, cg[k] = q2.x, cb[k] = q2.y, cd[k] = q1.z;
-            }
-            // sequential recurrences, predicated per lane
-#pragma unroll
-            for (int k = 0; k < ILP; ++k) {
-#pragma unroll
-                for (int t = 0; t < 10; ++t) v[k][t] = 0.f;
+                const float G = __expf(power);
+                const float og = q1.y * G;
+                const float alpha = fminf(ALPHA_MAX, og);
+                const bool hit = has && (q < my_last) && (power <= 0.0f) && (alpha >= ALPHA_MIN);
+                // a pair that was not blended leaves every state variable and every sum unchanged: alpha = 0, 1/(1-alpha) = 1
+                a_h[k] = hit ? alpha : 0.f;
+                og_h[k] = hit ? og : 0.f;
+                G_h[k] = hit ? G : 0.f;
+                inv1m[k] = hit ? rcp_approx(1.0f - alpha) : 1.0f;   // MUFU.RCP; 1 - alpha is in [0.01, 1]
+                float d = fmaf(gD, q1.z, gA);
+                d = fmaf(gC2, q2.y, d), d = fmaf(gC1, q2.x, d), d = fmaf(gC0, q1.w, d);
                 if (EXT) {
-#pragma unroll
-                    for (int c = 0; c < EXT_FLOATS; ++c) ve[k][c] = 0.f;
+                    ex[k] = s_ext[st][j];
+                    d = fmaf(gE[0], ex[k].x, d), d = fmaf(gE[1], ex[k].y, d);
+                    d = fmaf(gE[2], ex[k].z, d), d = fmaf(gE[3], ex[k].w, d);
                 }
-                if (hit[k]) {
-                    const float a = alpha[k], dx = ddx[k], dy = ddy[k];
-                    T = T * inv1m[k];
-                    const float w = a * T;
-                    const float om = 1.0f - last_alpha;
-                    float dL_da = 0.f;
-                    acc0 = last_alpha * lc0 + om * acc0;
-                    lc0 = cr[k];
-                    dL_da += (cr[k] - acc0) * gC0;
-                    acc1 = last_alpha * lc1 + om * acc1;
-                    lc1 = cg[k];
-                    dL_da += (cg[k] - acc1) * gC1;
-                    acc2 = last_alpha * lc2 + om * acc2;
-                    lc2 = cb[k];
-                    dL_da += (cb[k] - acc2) * gC2;
-                    accD = last_alpha * lD + om * accD;
-                    lD = cd[k];
-                    dL_da += (cd[k] - accD) * gD;
-                    accA = last_alpha + om * accA;
-                    dL_da += (1.0f - accA) * gA;
-                    if (EXT) {
-                        const float e[EXT_FLOATS] = {ex[k].x, ex[k].y, ex[k].z, ex[k].w};
+                dot[k] = d;
+                anyhit |= (__any_sync(0xffffffffu, hit) ? 1u : 0u) << k;
+            }
+        };
+        if (surv != 0ull) eval_group();
+        else anyhit = 0u;
+        bool more = true;
+        while (more) {
+            const uint32_t hit_g = anyhit, jpack_g = jpack;
+            if (hit_g) {
+                // ---- phase 2: the recurrence, in list order; each survivor's partial gradients go to this lane's row
 #pragma unroll
-                        for (int c = 0; c < EXT_FLOATS; ++c) {
-                            accE[c] = last_alpha * lE[c] + om * accE[c];
-                            lE[c] = e[c];
-                            dL_da += (e[c] - accE[c]) * gE[c];
-                            ve[k][c] = w * gE[c];
-                        }
+                for (int k = 0; k < ILP; ++k) {
+                    T *= inv1m[k];
+                    const float w = a_h[k] * T;
+                    const float dL_da = fmaf(dot[k], T, -(S * inv1m[k]));
+                    S = fmaf(dot[k], w, S);
+                    // alpha = o G (straight through the min), G = exp(power), power = -0.5 (A dx^2 + C dy^2) - B dx dy,
+                    // d = mean - pixel
+                    const float qq = -og_h[k] * dL_da;
+                    const float2 qxy = mul2(make_float2(qq, qq), make_float2(ddx[k], ddy[k]));
+                    const float2 dia = mul2(qxy, make_float2(ddx[k], ddy[k]));       // (2 d conic a, 2 d conic c)
+                    const float2 wc = mul2(make_float2(w, w), make_float2(gC0, gC1));
+                    const float2 wd = mul2(make_float2(w, w), make_float2(gC2, gD));
+                    float4* row = my_row + k * F4;
+                    // (d mean x, d mean y, 2 d conic a, d conic b) (2 d conic c, d opacity, d r, d g) (d b, d depth, 0, 0):
+                    // the factor 1/2 of the two diagonal conic terms is applied by the consumer (preprocess backward)
+                    row[0] = make_float4(fmaf(cA[k], qxy.x, cB[k] * qxy.y), fmaf(cC[k], qxy.y, cB[k] * qxy.x), dia.x,
+                                         qxy.x * ddy[k]);
+                    row[1] = make_float4(dia.y, G_h[k] * dL_da, wc.x, wc.y);
+                    *reinterpret_cast<float2*>(row + 2) = wd;
+                    if (EXT) row[3] = make_float4(w * gE[0], w * gE[1], w * gE[2], w * gE[3]);
+                }
+                __syncwarp();
+            }
+            // the next group's phase 1 is independent of this group's reduction: issued first, they overlap
+            more = surv != 0ull;
+            if (more) eval_group();
+            if (hit_g) {
+                // ---- phase 3: column sums over the 32 rows, one vector reduction per float4 of a record -----------
+                float2 s0 = make_float2(0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;   // (xy, zw) of the even / the odd rows
+                if (red_active) {
+#pragma unroll
+                    for (int r = 0; r < 16; r += 2) {
+                        const float4 t = r < 12 ? red_src[r * (RS / 4)] : red_src2[(r - 12) * (RS / 4)];
+                        const float4 u = r < 12 ? red_src[(r + 1) * (RS / 4)] : red_src2[(r - 11) * (RS / 4)];
+                        s0 = add2(s0, make_float2(t.x, t.y)), s1 = add2(s1, make_float2(t.z, t.w));
+                        s2 = add2(s2, make_float2(u.x, u.y)), s3 = add2(s3, make_float2(u.z, u.w));
                     }
-                    dL_da *= T;
-                    last_alpha = a;
-                    dL_da += (-T_final * inv1m[k]) * bg_dot;
-                    const float dL_dG = op[k] * dL_da;
-                    const float gdx = G[k] * dx, gdy = G[k] * dy;
-                    // power = -0.5 (A dx^2 + C dy^2) - B dx dy, d = mean - pixel
-                    v[k][0] = dL_dG * (-gdx * cA[k] - gdy * cB[k]);
-                    v[k][1] = dL_dG * (-gdy * cC[k] - gdx * cB[k]);
-                    v[k][2] = -0.5f * gdx * dx * dL_dG;
-                    v[k][3] = -gdx * dy * dL_dG;
-                    v[k][4] = -0.5f * gdy * dy * dL_dG;
-                    v[k][5] = G[k] * dL_da;
-                    v[k][6] = w * gC0, v[k][7] = w * gC1, v[k][8] = w * gC2, v[k][9] = w * gD;
                 }
-            }
-            // ILP independent warp reductions (interleaved by the scheduler), one 10-lane atomic each
-            uint32_t anyhit = 0;
-#pragma unroll
-            for (int k = 0; k < ILP; ++k) anyhit |= (__any_sync(0xffffffffu, hit[k]) ? 1u : 0u) << k;
-            if (anyhit) {
-                float r[ILP];
-#pragma unroll
-                for (int k = 0; k < ILP; ++k) r[k] = warp_reduce10(v[k], lane);
-#pragma unroll
-                for (int k = 0; k < ILP; ++k)
-                    if (slot >= 0 && ((anyhit >> k) & 1u))
-                        atomicAdd(grad2d + (size_t)s_ids[s][j[k]] * GRAD2D_FLOATS + slot, r[k]);
-                if (EXT) {
-                    float re[ILP];
-#pragma unroll
-                    for (int k = 0; k < ILP; ++k) re[k] = warp_reduce4(ve[k], lane);
-#pragma unroll
-                    for (int k = 0; k < ILP; ++k)
-                        if (slot4 >= 0 && slot4 < tab.n_extra && ((anyhit >> k) & 1u))
-                            atomicAdd(gradext + (size_t)s_ids[s][j[k]] * EXT_FLOATS + slot4, re[k]);
+                s0 = add2(s0, s2), s1 = add2(s1, s3);
+                float4 acc = make_float4(s0.x, s0.y, s1.x, s1.y);
+                acc.x += __shfl_down_sync(0xffffffffu, acc.x, NC4);
+                acc.y += __shfl_down_sync(0xffffffffu, acc.y, NC4);
+                acc.z += __shfl_down_sync(0xffffffffu, acc.z, NC4);
+                acc.w += __shfl_down_sync(0xffffffffu, acc.w, NC4);
+                if (lane < NC4 && ((hit_g >> red_k) & 1u)) {
+                    const size_t id = s_ids[st][(jpack_g >> (8 * red_k)) & 0xffu];
+                    if (!EXT || red_part < 3) red_add_v4(grad2d + id * GRAD2D_FLOATS + 4 * red_part, acc);
+                    else red_add_v4(gradext + id * EXT_FLOATS, acc);
                 }
+                __syncwarp();   // the rows are rewritten by the next group
             }
         }
     }
@@ -658,16 +670,27 @@ cudaError_t launch_render_forward(const BatchTab& tab, int sel, cudaStream_t st)
     return cudaGetLastError();
 }
 
+static int backward_stages() {
+    static const int n = [] {
+        const char* e = getenv("B200SPLAT_BWD_STAGES");
+        return (e && atoi(e) == 3) ? 3 : 2;   // measured on B200 (headline, 4 views): 2 stages 108.6, 3 stages 110.6 us/view
+    }();
+    return n;
+}
+
 cudaError_t launch_render_backward(const BatchTab& tab, int sel, cudaStream_t st) {
     const unsigned grid = (unsigned)(tab.V * tab.grid_x * tab.grid_y * WARPS_PER_TILE);
     const bool ext = tab.n_extra > 0;
-    if (use_bulk_staging()) {
-        if (ext) render_backward_kernel<true, true><<<grid, 32, 0, st>>>(tab, sel);
-        else render_backward_kernel<true, false><<<grid, 32, 0, st>>>(tab, sel);
+    const bool bulk = use_bulk_staging();
+#define LAUNCH_BWD(B, E, S) render_backward_kernel<B, E, S><<<grid, 32, 0, st>>>(tab, sel)
+    if (backward_stages() == 2) {
+        if (bulk) { if (ext) LAUNCH_BWD(true, true, 2); else LAUNCH_BWD(true, false, 2); }
+        else { if (ext) LAUNCH_BWD(false, true, 2); else LAUNCH_BWD(false, false, 2); }
     } else {
-        if (ext) render_backward_kernel<false, true><<<grid, 32, 0, st>>>(tab, sel);
-        else render_backward_kernel<false, false><<<grid, 32, 0, st>>>(tab, sel);
+        if (bulk) { if (ext) LAUNCH_BWD(true, true, 3); else LAUNCH_BWD(true, false, 3); }
+        else { if (ext) LAUNCH_BWD(false, true, 3); else LAUNCH_BWD(false, false, 3); }
     }
+#undef LAUNCH_BWD
     count_launch();
     return cudaGetLastError();
 }

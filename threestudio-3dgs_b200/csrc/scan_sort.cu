@@ -1137,6 +1137,75 @@ tile_ranges_from_counts_kernel(const __grid_constant__ BatchTab tab) {
     }
 }
 
+// Work order of render backward: the batch's 8x4 pixel blocks that have anything to walk (largest n_contrib of the
+// block > 0), most entries first (LPT over the SMs at the granularity the backward actually works at: a silhouette
+// block walks ten times more entries than its neighbours in the same tile).  block_order[0] = count, entries follow
+// at [4..).  One CTA; counting sort on the same monotone 11-bit key as the tile order.
+__global__ void __launch_bounds__(1024)
+block_order_kernel(const __grid_constant__ BatchTab tab, int n) {
+    __shared__ uint32_t s_cnt[ORDER_BUCKETS];
+    __shared__ uint32_t s_warp[32];
+    const int per_view = tab.grid_x * tab.grid_y * (BLOCK_SIZE / 32);
+    for (int i = threadIdx.x; i < ORDER_BUCKETS; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+    auto bucket_of = [&](int i) -> uint32_t {
+        const uint32_t len = tab.v[i / per_view].block_last[i % per_view];
+        if (len == 0u) return 0xffffffffu;
+        const uint32_t k = min((uint32_t)(ORDER_BUCKETS - 1), __float_as_uint((float)len) >> 20);
+        return (ORDER_BUCKETS - 1) - k;   // descending: the longest walks get the smallest bucket index
+    };
+    // 8 independent loads in flight per thread: a single CTA is latency-bound, not bandwidth-bound
+    constexpr int UN = 8;
+    for (int i0 = threadIdx.x; i0 < n; i0 += UN * blockDim.x) {
+        uint32_t b[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int i = i0 + u * blockDim.x;
+            b[u] = i < n ? bucket_of(i) : 0xffffffffu;
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u)
+            if (b[u] != 0xffffffffu) atomicAdd(&s_cnt[b[u]], 1u);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t c0 = s_cnt[2 * threadIdx.x], c1 = s_cnt[2 * threadIdx.x + 1];
+    uint32_t inc = c0 + c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w = 0; w < warp; ++w) woff += s_warp[w];
+    const uint32_t excl = woff + inc - (c0 + c1);
+    if (threadIdx.x == 1023) tab.block_order[0] = excl + c0 + c1;   // number of non-empty blocks
+    __syncthreads();
+    s_cnt[2 * threadIdx.x] = excl;
+    s_cnt[2 * threadIdx.x + 1] = excl + c0;
+    __syncthreads();
+    for (int i0 = threadIdx.x; i0 < n; i0 += UN * blockDim.x) {
+        uint32_t b[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int i = i0 + u * blockDim.x;
+            b[u] = i < n ? bucket_of(i) : 0xffffffffu;
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u)
+            if (b[u] != 0xffffffffu) tab.block_order[4 + atomicAdd(&s_cnt[b[u]], 1u)] = (uint32_t)(i0 + u * blockDim.x);
+    }
+}
+
+cudaError_t launch_block_order(const BatchTab& tab, cudaStream_t st) {
+    const int n = tab.V * tab.grid_x * tab.grid_y * (BLOCK_SIZE / 32);
+    block_order_kernel<<<1, 1024, 0, st>>>(tab, n);
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t launch_tile_ranges_batch(const BatchTab& tab, int sel, cudaStream_t st) {
     const int T = tab.grid_x * tab.grid_y;
     if (tab.P > 0 && tab.capacity > 0 && T <= 8192) {
