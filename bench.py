@@ -41,15 +41,24 @@ def parse_args():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--views-per-gpu", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--allreduce", default="auto", choices=["auto", "p2p", "nccl"],
-                    help="multi-GPU gradient exchange: own NVLink peer-memory kernel, NCCL, or auto = the faster one "
-                         "measured on this pool (p2p up to 4 GPUs, NCCL/NVLS at 8)")
+    ap.add_argument("--allreduce", default="auto", choices=["auto", "mc", "p2p", "nccl"],
+                    help="multi-GPU gradient exchange: mc = own kernel through NVSwitch multicast (multimem.ld_reduce / "
+                         "multimem.st, in-switch reduction), p2p = own kernel over NVLink peer memory, nccl; auto = p2p "
+                         "at 2 GPUs, mc at 3..8 (where the box supports multicast; else p2p up to 4 GPUs, NCCL above)")
     ap.add_argument("--exchange-chunks", type=int, default=1,
                     help="multi-GPU: Gaussian ranges of the preprocess backward whose exchange overlaps the next range "
-                         "(1 = one exchange after the step, the default: measured at 2 GPUs 1/2/4/8 ranges -> "
-                         "3976/3927/3815/3640 renders/s -- the per-range handshakes and the SM slots the exchange "
-                         "kernel takes from the compute cost more than the overlap returns)")
+                         "(1 = one exchange after the step, the default.  Measured with the whole step incl. the exchange "
+                         "kernels in ONE CUDA graph, 1/2/4 ranges: 2 GPUs p2p 4312/-/4167, multicast 3769/3719/3645; "
+                         "8 GPUs NCCL 13952/12587/12252 renders/s -- preprocess backward is HBM-bound and so is the "
+                         "exchange's local side: overlapped they slow each other down by more than the overlap returns)")
     ap.add_argument("--eager", action="store_true", help="launch the step from Python every time (no CUDA graph)")
+    ap.add_argument("--quick", action="store_true",
+                    help="only the resident timed region (no e2e, no per-kernel table, no aux / cpu / configs legs): "
+                         "for exchange experiments at N > 1")
+    ap.add_argument("--views-total", type=int, default=0,
+                    help="strong scaling: this many views per step in total, split evenly over the GPUs "
+                         "(BASELINE.json configs[3]: 32 views of config4_1m_256_sh3_b32); 0 = weak scaling with "
+                         "--views-per-gpu")
     ap.add_argument("--no-configs", action="store_true",
                     help="skip the short runs of the other BASELINE.json configurations (the `configs` array, N = 1 only)")
     return ap.parse_args()
@@ -346,6 +355,11 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     N = world
     V = args.views_per_gpu
+    scaling = "weak"
+    if args.views_total:
+        if args.views_total % N:
+            raise SystemExit("--views-total must be a multiple of the number of GPUs")
+        V, scaling = args.views_total // N, "strong"
 
     # ---- workload: replicated scene, per-rank views ------------------------------------------------
     scene, cams_all = scenes.make_workload(args.workload, views=V * N)
@@ -367,10 +381,20 @@ def main():
     # multi-GPU: the packed gradient buffer lives in CUDA-IPC memory mapped by all ranks and is all-reduced in
     # place by one kernel per rank over NVLink peer memory (csrc/p2p.cu); --allreduce nccl uses NCCL instead
     p2p, allreduce_mode = None, ("none" if world == 1 else "nccl")
-    use_p2p = args.allreduce == "p2p" or (args.allreduce == "auto" and world <= 4)
+    # auto (measured on this pool, profiles/r2_scaling.md): 2 GPUs -> peer-memory kernel (a rank's own half never
+    # crosses NVLink), 3..8 GPUs -> multicast kernel (in-switch reduction), NCCL only as the fall-back
+    if world > 1 and (args.allreduce == "mc" or (args.allreduce == "auto" and world > 2)):
+        try:
+            p2p = bdist.MulticastAllReduce(batched.PackedGrads.floats(P, M), batched.PackedGrads.padded(P), dev,
+                                           device_epoch=True)
+            allreduce_mode = "nvswitch_multicast_kernel"
+        except Exception as exc:
+            print(f"bench: multicast all-reduce unavailable ({exc!r})", file=sys.stderr)
+            p2p = None
+    use_p2p = p2p is None and (args.allreduce == "p2p" or (args.allreduce in ("auto", "mc") and world <= 4))
     if world > 1 and use_p2p:
         try:
-            p2p = bdist.P2PAllReduce(batched.PackedGrads.floats(P, M), batched.PackedGrads.padded(P), dev)
+            p2p = bdist.P2PAllReduce(batched.PackedGrads.floats(P, M), batched.PackedGrads.padded(P), dev, device_epoch=True)
             allreduce_mode = "p2p_nvlink_kernel"
         except Exception as exc:
             print(f"bench: P2P all-reduce unavailable ({exc!r}); using NCCL", file=sys.stderr)
@@ -380,27 +404,44 @@ def main():
     renderer.calibrate(cams, means3D, shs, None, opac, scales, rots)
 
     # the step's launches are recorded once into a CUDA graph (the C ABI never synchronises in the batched path);
-    # --eager launches them from Python every step instead
+    # --eager launches them from Python every step instead.  With an own exchange kernel (multicast / peer memory) the
+    # exchange is part of the graph: after the step, or range by range on a forked stream (--exchange-chunks).
     graph, launch_mode = None, "eager"
     chunks = args.exchange_chunks if world > 1 else 1
     l_a = _lib.launch_count()
     renderer.step(cams, means3D, shs, None, opac, scales, rots, pgrads)
     launches_per_step = _lib.launch_count() - l_a
-    if not args.eager:
-        try:
-            graph = renderer.capture_step(cams, means3D, shs, None, opac, scales, rots, pgrads, head_only=chunks > 1)
-            launch_mode = "cuda_graph"
-        except Exception as exc:   # report, do not hide: the run continues on the eager path
-            print(f"bench: CUDA graph capture failed ({exc!r}); eager launches", file=sys.stderr)
-            graph = None
 
     def exchange(g0, g1):
         if p2p is not None:
             p2p(packed.segments(g0, g1))
-        else:
-            bdist.allreduce_packed_range(packed, g0, g1)
+        else:   # one coalesced SUM launch per range; the (small) MAX of max_radii once, with the last range
+            bdist.allreduce_packed_range(packed, g0, g1, with_max=False)
+            if g1 == P:
+                dist.all_reduce(packed.max_radii, op=dist.ReduceOp.MAX)
+
+    graph_has_exchange = False
+    if not args.eager:
+        try:
+            if p2p is not None:
+                l_b = _lib.launch_count()
+                graph = renderer.capture_step(cams, means3D, shs, None, opac, scales, rots, pgrads, exchange=exchange,
+                                              chunks=chunks)
+                graph_has_exchange = True
+                launches_per_step = (_lib.launch_count() - l_b) // 2      # the eager pass + the captured pass
+            else:
+                graph = renderer.capture_step(cams, means3D, shs, None, opac, scales, rots, pgrads, head_only=chunks > 1)
+            launch_mode = "cuda_graph"
+        except Exception as exc:   # report, do not hide: the run continues on the eager path
+            print(f"bench: CUDA graph capture failed ({exc!r}); eager launches", file=sys.stderr)
+            graph, graph_has_exchange = None, False
+    if world > 1:
+        dist.barrier()
 
     def step():
+        if graph_has_exchange:
+            graph.replay()
+            return
         if chunks > 1:
             # multi-GPU: forward + render backward, then preprocess backward in Gaussian ranges whose gradients are
             # exchanged on a side stream while the next range is computed
@@ -423,7 +464,7 @@ def main():
         """After the timed region (N > 1): one more step WITHOUT the exchange, a copy of the local sums, then the
         exchange as timed -- its result must be bit-identical on all ranks and equal to an independent NCCL SUM / MAX
         of the copies (tolerance: the summation order over the ranks may differ, fp32)."""
-        if graph is not None and chunks == 1:
+        if graph is not None and chunks == 1 and not graph_has_exchange:
             graph.replay()
         else:
             renderer.step(cams, means3D, shs, None, opac, scales, rots, pgrads)
@@ -470,7 +511,9 @@ def main():
     e1.record()
     barrier()
     launches = _lib.launch_count() - l0          # launched from the host inside the timed region (incl. p2p kernels)
-    if graph is not None:                        # + the graph's nodes: the whole step, or the step minus the
+    if graph_has_exchange:                       # everything is a graph node: the step and its exchange kernels
+        launches += launches_per_step * args.steps
+    elif graph is not None:                      # + the graph's nodes: the whole step, or the step minus the
         launches += (launches_per_step - (1 if chunks > 1 else 0)) * args.steps   # chunked preprocess backward
     if renderer.overflowed():
         raise SystemExit("bench: a view exceeded its binning capacity during the timed region (invalid run)")
@@ -484,6 +527,19 @@ def main():
     total_ms = float(ms.item())
     ms_per_step = total_ms / args.steps
     value = N * V * args.steps / (total_ms / 1e3)
+
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": args.steps,
+                              "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+                              "scaling": scaling, "quick": True,
+                              "config": {"workload": args.workload, "views_per_gpu_per_step": V, "launch": launch_mode,
+                                         "allreduce": allreduce_mode, "exchange_chunks": chunks},
+                              "exchange_verified": None if exchange_check is None else exchange_check["ok"],
+                              "exchange_check": exchange_check, "gpu_launches": launches}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- e2e: public API (GaussianRasterizer + autograd), host buffers for the step's inputs ----------
     from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
@@ -709,7 +765,7 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "gaussians": P, "sh_degree": scene.sh_degree, "image": [H, W],
                        "views_per_gpu_per_step": V, "global_views_per_step": V * N,

@@ -442,7 +442,9 @@ int b200splat_profile_read(float* ms, int64_t* count);
  * (any host channel: torch.distributed all_gather_object), maps the peers' with b200splat_p2p_open, and then
  * calls b200splat_p2p_allreduce on its own stream: every listed segment of every rank's buffer becomes its sum (or
  * maximum) over the ranks, in place, bit-identical on all ranks.  Segment offsets / counts are multiples of 4 floats;
- * epoch must increase by 1 per call, equally on all ranks (calls of one group are stream-ordered on each rank).
+ * epoch must increase by 1 per call, equally on all ranks (calls of one group are stream-ordered on each rank);
+ * epoch = 0: the library keeps the call counter itself, in the rank's signal words -- no launch argument changes
+ * from call to call, so the exchange can be captured in a CUDA graph and replayed (do not mix the two modes).
  * Returns B200SPLAT_OK immediately (stream-ordered); b200splat_p2p_error reads the rank's error flag
  * (peer timeout) -- it synchronises nothing itself, call it after the stream is known to be idle. */
 #define B200SPLAT_P2P_MAX_RANKS 8
@@ -468,6 +470,28 @@ int b200splat_p2p_close(void* mapped_ptr);
 int b200splat_p2p_free(void* ptr);
 int b200splat_p2p_allreduce(const b200splat_p2p_args* args);
 int b200splat_p2p_error(const void* own_signals, int32_t* flag_out);
+
+/* ---- all-reduce through NVSwitch multicast (in-switch reduction) -----------------------------------------------
+ * Same contract as b200splat_p2p_allreduce (segments, ops, epoch, in place, bit-identical on all ranks), but the data
+ * plane is the switch: every rank's buffer is bound to ONE multicast object (CUDA VMM multicast; the shipped Python
+ * host side gets it from torch.distributed._symmetric_memory), rank r pulls its slice of every segment with
+ * multimem.ld_reduce (the switch adds / maxes the N copies on the way) and pushes the result to all ranks with
+ * multimem.st (the switch replicates it): N/N of the buffer per NVLink direction per GPU instead of 2 (N-1)/N.
+ * mc_buffer: the multicast address of the buffer; signals[k]: rank k's signal words, peer-mapped as for
+ * b200splat_p2p_allreduce (B200SPLAT_P2P_SIGNAL_BYTES each, zero before the first call).  MAX segments hold
+ * non-negative floats (radii): they are reduced as unsigned integers (same order), exactly. */
+typedef struct b200splat_mc_args {
+    int32_t rank, world;
+    void* mc_buffer;
+    void* signals[B200SPLAT_P2P_MAX_RANKS];
+    int32_t n_segments;
+    int64_t seg_offset[B200SPLAT_P2P_MAX_SEGMENTS]; /* in floats, multiple of 4 */
+    int64_t seg_count[B200SPLAT_P2P_MAX_SEGMENTS];  /* in floats, multiple of 4 */
+    int32_t seg_op[B200SPLAT_P2P_MAX_SEGMENTS];     /* B200SPLAT_P2P_SUM | B200SPLAT_P2P_MAX */
+    uint32_t epoch;
+    b200splat_stream stream;
+} b200splat_mc_args;
+int b200splat_mc_allreduce(const b200splat_mc_args* args);
 
 /* ---- misc ----------------------------------------------------------------------------------- */
 /* How the render kernels stage a tile's Gaussian records into shared memory: 0 = per-entry 16-byte cp.async

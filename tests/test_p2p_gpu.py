@@ -17,7 +17,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n_sum, n_max, rounds, out):
+def _worker(rank, world, port, n_sum, n_max, rounds, out, kind="p2p"):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, os.path.join(root, "threestudio-3dgs_b200"))
@@ -25,13 +25,25 @@ def _worker(rank, world, port, n_sum, n_max, rounds, out):
     from b200splat import dist as bdist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     torch.cuda.set_device(rank)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
     dev = torch.device("cuda", rank)
-    ar = bdist.P2PAllReduce(n_sum, n_max, dev)
+    if kind == "mc":
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        try:
+            ar = bdist.MulticastAllReduce(n_sum, n_max, dev)
+        except RuntimeError as exc:       # no NVSwitch multicast on this box: all ranks raise together
+            if rank == 0:
+                out.put(-1)
+            dist.destroy_process_group()
+            return
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        ar = bdist.P2PAllReduce(n_sum, n_max, dev)
     ok = True
     for r in range(rounds):
         gens = [torch.Generator().manual_seed(1000 * r + k) for k in range(world)]
         parts = [torch.randn(n_sum + n_max, generator=g) for g in gens]
+        for prt in parts:
+            prt[n_sum:] = prt[n_sum:].abs().round()      # the MAX segment holds radii: non-negative
         want_sum = parts[0][:n_sum].clone()
         for k in range(1, world):            # the kernel sums in rank order: bit-exact expectation
             want_sum += parts[k][:n_sum]
@@ -40,10 +52,18 @@ def _worker(rank, world, port, n_sum, n_max, rounds, out):
         ar()
         torch.cuda.synchronize(dev)
         got = ar.buffer.cpu()
-        ok = ok and torch.equal(got[:n_sum], want_sum) and torch.equal(got[n_sum:], want_max)
+        if kind == "mc":     # the switch's summation order is its own: tolerance on the sum, identical bits on all ranks
+            scale = float(want_sum.abs().max().clamp_min(1e-30))
+            ok = ok and float((got[:n_sum] - want_sum).abs().max()) <= 1e-6 * scale and torch.equal(got[n_sum:], want_max)
+            chk = ar.buffer.view(torch.int32).to(torch.int64).sum().reshape(1)
+            allchk = [torch.empty_like(chk) for _ in range(world)]
+            dist.all_gather(allchk, chk)
+            ok = ok and all(bool(torch.equal(c, allchk[0])) for c in allchk)
+        else:
+            ok = ok and torch.equal(got[:n_sum], want_sum) and torch.equal(got[n_sum:], want_max)
     ok = ok and not ar.failed()
     ar.close()
-    res = torch.tensor([1 if ok else 0])
+    res = torch.tensor([1 if ok else 0], device=dev if kind == "mc" else "cpu")
     dist.all_reduce(res, op=dist.ReduceOp.MIN)
     if rank == 0:
         out.put(int(res.item()))
@@ -60,3 +80,19 @@ def test_p2p_allreduce_matches_rank_ordered_sum(n_sum, n_max):
     q = ctx.SimpleQueue()
     mp.spawn(_worker, args=(world, _free_port(), n_sum, n_max, 3, q), nprocs=world, join=True)
     assert q.get() == 1
+
+
+@pytest.mark.parametrize("n_sum,n_max", [(61 * 4096, 4096), (1 << 20, 0), (8, 8)])
+def test_multicast_allreduce_matches_sum_and_max(n_sum, n_max):
+    """b200splat_mc_allreduce (multimem.ld_reduce / multimem.st through NVSwitch multicast)."""
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    mp.spawn(_worker, args=(world, _free_port(), n_sum, n_max, 3, q, "mc"), nprocs=world, join=True)
+    r = q.get()
+    if r == -1:
+        pytest.skip("no NVSwitch multicast support on this box")
+    assert r == 1

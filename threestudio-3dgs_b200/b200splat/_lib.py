@@ -138,6 +138,12 @@ class P2PArgs(C.Structure):
                 ("seg_op", C.c_int32 * 16), ("epoch", C.c_uint32), ("stream", C.c_void_p)]
 
 
+class MCArgs(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("mc_buffer", C.c_void_p), ("signals", C.c_void_p * 8),
+                ("n_segments", C.c_int32), ("seg_offset", C.c_int64 * 16), ("seg_count", C.c_int64 * 16),
+                ("seg_op", C.c_int32 * 16), ("epoch", C.c_uint32), ("stream", C.c_void_p)]
+
+
 P2P_HANDLE_BYTES, P2P_SIGNAL_BYTES = 64, 256
 
 # every symbol include/b200splat.h declares: name -> (restype, argtypes)
@@ -152,6 +158,7 @@ SYMBOLS = {
     "b200splat_p2p_free": (C.c_int, [C.c_void_p]),
     "b200splat_p2p_allreduce": (C.c_int, [C.POINTER(P2PArgs)]),
     "b200splat_p2p_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "b200splat_mc_allreduce": (C.c_int, [C.POINTER(MCArgs)]),
     "b200splat_geom_bytes": (C.c_size_t, [C.c_int32]),
     "b200splat_image_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "b200splat_binning_bytes": (C.c_size_t, [C.c_int64]),

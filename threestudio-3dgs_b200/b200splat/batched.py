@@ -351,27 +351,43 @@ class BatchRenderer:
         main.wait_stream(side)
 
     def capture_step(self, cams, means3D, shs, colors_precomp, opacities, scales, rotations, pixel_grads,
-                     head_only: bool = False):
+                     head_only: bool = False, exchange=None, chunks: int = 1):
         """Record one step (every launch of the view batch's forward + backward) into a CUDA graph and return it;
         ``graph.replay()`` then re-runs the step on the same buffers without per-launch host work.  The inputs
         must keep their addresses (parameters updated in place, cameras / pixel gradients written into the same
         tensors); pixel_grads must be tensors, not callables.  head_only: record ``step_head`` (the part before
-        the chunked preprocess backward / exchange of a multi-GPU step)."""
+        the chunked preprocess backward / exchange of a multi-GPU step).
+        exchange(g0, g1): the multi-GPU gradient exchange of Gaussians [g0, g1) -- recorded INTO the graph (own
+        kernels with a device-side call counter only: ``P2PAllReduce`` / ``MulticastAllReduce`` with
+        ``device_epoch=True``): after the whole step when ``chunks`` <= 1, else range by range on a forked stream while
+        the next range's preprocess backward runs (``step_tail``)."""
         assert self.calibrated, "calibrate() first: the binning capacity is baked into the graph"
         assert not any(callable(pg) for pg in pixel_grads)
         args = (cams, means3D, shs, colors_precomp, opacities, scales, rotations, pixel_grads)
-        fn = self.step_head if head_only else self.step
+        params = (cams, means3D, shs, colors_precomp, opacities, scales, rotations)
+
+        def fn():
+            if exchange is None:
+                (self.step_head if head_only else self.step)(*args)
+            elif chunks <= 1:
+                self.step(*args)
+                exchange(0, self.P)
+            else:
+                self.step_head(*args)
+                self.step_tail(*params, exchange, chunks=chunks)
+
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
-            fn(*args)   # eager once on the side stream: one-time attribute / allocation work happens here
-            if head_only:   # leave the scratch clean (the eager head's records are consumed by a full tail)
+            fn()   # eager once on the side stream: one-time attribute / allocation work happens here
+            if head_only and exchange is None:   # leave the scratch clean (the eager head's records are consumed by a full tail)
                 backward_batched(self.ws[0], cams, means3D, shs, colors_precomp, opacities, scales, rotations,
                                  [None] * self.ws[0].V, self.packed.grads(), phase=2)
         torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            fn(*args)
+            fn()
         return graph
 
     def overflowed(self) -> bool:

@@ -26,13 +26,25 @@ def allreduce_packed(buffer: torch.Tensor, max_radii: torch.Tensor, group=None):
     dist.all_reduce(max_radii, op=dist.ReduceOp.MAX, group=group)
 
 
-def allreduce_packed_range(packed, g0: int, g1: int, group=None):
-    """NCCL/gloo version of the chunked exchange: the fields of the packed buffer and max_radii, Gaussians [g0, g1)."""
+def allreduce_packed_range(packed, g0: int, g1: int, group=None, with_max: bool = True):
+    """NCCL/gloo version of the chunked exchange: the fields of the packed buffer (and max_radii), Gaussians [g0, g1).
+    The per-field SUM all-reduces of a range are coalesced into ONE collective launch (ncclGroupStart/End) -- seven
+    separate launches per range cost more than the overlap of a range's exchange with the next range's compute
+    returns."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
-    for name, off, w in packed.fields:
-        dist.all_reduce(packed.buffer[off + w * g0:off + w * g1], op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(packed.max_radii[g0:g1], op=dist.ReduceOp.MAX, group=group)
+    e1 = packed.P4 if g1 == packed.P else g1
+    slices = [packed.buffer[off + w * g0:off + w * e1] for _, off, w in packed.fields]
+    if dist.get_backend(group) == "nccl":   # gloo has no coalescing (and a failed attempt leaves its queue open)
+        from torch.distributed.distributed_c10d import _coalescing_manager
+        with _coalescing_manager(group=group, device=packed.buffer.device, async_ops=False):
+            for t in slices:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    else:
+        for t in slices:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    if with_max:
+        dist.all_reduce(packed.max_radii[g0:g1], op=dist.ReduceOp.MAX, group=group)
 
 
 class _RawCudaArray:
@@ -50,7 +62,9 @@ class P2PAllReduce:
     it (``PackedGrads(..., storage=ar.buffer)``) and call ``ar()`` after the backward.  One process per GPU of
     ONE box; the handles travel through ``torch.distributed`` (any backend)."""
 
-    def __init__(self, n_sum: int, n_max: int, device, group=None):
+    def __init__(self, n_sum: int, n_max: int, device, group=None, device_epoch: bool = False):
+        """device_epoch: the kernel keeps the call counter in the rank's signal words (epoch argument 0), so a call can
+        be captured in a CUDA graph and replayed; all ranks must choose the same mode."""
         import ctypes as C
         from . import _lib
         self._lib, self._C = _lib, C
@@ -58,6 +72,7 @@ class P2PAllReduce:
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         assert self.world <= 8, "one NVSwitch box: at most 8 ranks"
         self.n_sum, self.n_max, self.device, self.epoch = n_sum, n_max, torch.device(device), 0
+        self.device_epoch = device_epoch
         lib = _lib.lib
         # every step below is collective-safe: a rank that fails still takes part in the exchange of the status, so
         # all ranks raise together instead of some waiting in a collective for a peer that already gave up
@@ -110,7 +125,7 @@ class P2PAllReduce:
         assert 1 <= len(segments) <= 16
         self.epoch += 1
         a = _lib.P2PArgs()
-        a.rank, a.world, a.epoch, a.n_segments = self.rank, self.world, self.epoch, len(segments)
+        a.rank, a.world, a.epoch, a.n_segments = self.rank, self.world, 0 if self.device_epoch else self.epoch, len(segments)
         for i, (off, cnt, op) in enumerate(segments):
             a.seg_offset[i], a.seg_count[i], a.seg_op[i] = int(off), int(cnt), int(op)
         for k in range(self.world):
@@ -141,6 +156,82 @@ class P2PAllReduce:
         torch.cuda.synchronize(self.device)
         self.buffer = None
         self._release()
+
+
+class MulticastAllReduce:
+    """In-place SUM (+ MAX tail) all-reduce of one fp32 buffer per rank through NVSwitch multicast
+    (b200splat_mc_allreduce, csrc/p2p.cu: multimem.ld_reduce / multimem.st -- the switch adds the ranks' copies on the
+    way in and replicates the result on the way out, N/N of the buffer per NVLink direction instead of 2 (N-1)/N).
+    Same use as ``P2PAllReduce``: build the step's PackedGrads on ``buffer`` and call the object after the backward.
+    The symmetric allocation, the multicast binding and the peer-mapped signal pads are torch's
+    (``torch.distributed._symmetric_memory``: plumbing); the data path is this library's kernel.  Raises at
+    construction -- on all ranks together -- when the box has no multicast support."""
+
+    SIGNAL_OFFSET = 4096   # bytes into torch's signal pad (its own barrier uses the first words)
+
+    def __init__(self, n_sum: int, n_max: int, device, group=None, device_epoch: bool = False):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self._lib, self._C = _lib, C
+        assert n_sum % 4 == 0 and n_max % 4 == 0, "segment lengths must be multiples of 4 floats"
+        group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        assert self.world <= 8, "one NVSwitch box: at most 8 ranks"
+        self.n_sum, self.n_max, self.device, self.epoch = n_sum, n_max, torch.device(device), 0
+        self.device_epoch = device_epoch
+        err = None
+        try:
+            with torch.cuda.device(self.device):
+                self.buffer = symm_mem.empty(n_sum + n_max, dtype=torch.float32, device=self.device)
+                self._hdl = symm_mem.rendezvous(self.buffer, group)
+            self._mc = int(self._hdl.multicast_ptr)
+            if not self._mc:
+                raise RuntimeError("no multicast address (NVSwitch multicast unsupported here)")
+            if self._hdl.signal_pad_size < self.SIGNAL_OFFSET + _lib.P2P_SIGNAL_BYTES:
+                raise RuntimeError("signal pad too small")
+            self._sigs = [int(p) + self.SIGNAL_OFFSET for p in self._hdl.signal_pad_ptrs]
+            self.buffer.zero_()
+        except Exception as exc:
+            err = repr(exc)
+        status: list = [None] * self.world
+        dist.all_gather_object(status, err, group=group)
+        bad = [f"rank {k}: {e}" for k, e in enumerate(status) if e]
+        if bad:
+            self.buffer = None
+            raise RuntimeError("MulticastAllReduce setup failed (" + "; ".join(bad) + ")")
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=group)
+
+    def __call__(self, segments=None):
+        """Stream-ordered on the current stream; see ``P2PAllReduce.__call__``."""
+        C, _lib = self._C, self._lib
+        if segments is None:
+            segments = [(0, self.n_sum, 0)] + ([(self.n_sum, self.n_max, 1)] if self.n_max else [])
+        segments = [sg for sg in segments if sg[1] > 0]
+        assert 1 <= len(segments) <= 16
+        self.epoch += 1
+        a = _lib.MCArgs()
+        a.rank, a.world, a.epoch, a.n_segments = self.rank, self.world, 0 if self.device_epoch else self.epoch, len(segments)
+        a.mc_buffer = self._mc
+        for i, (off, cnt, op) in enumerate(segments):
+            a.seg_offset[i], a.seg_count[i], a.seg_op[i] = int(off), int(cnt), int(op)
+        for k in range(self.world):
+            a.signals[k] = self._sigs[k]
+        a.stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib.b200splat_mc_allreduce(C.byref(a)), "b200splat_mc_allreduce")
+
+    def failed(self) -> bool:
+        C = self._C
+        torch.cuda.synchronize(self.device)
+        flag = C.c_int32(0)
+        self._lib.check(self._lib.lib.b200splat_p2p_error(self._sigs[self.rank], C.byref(flag)), "b200splat_p2p_error")
+        return flag.value != 0
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        self.buffer, self._hdl = None, None
 
 
 def reference_update_states(xyz_gradient_accum, denom, max_radii2D, grad_accum_step, denom_step, max_radii_step):

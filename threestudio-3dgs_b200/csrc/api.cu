@@ -386,6 +386,35 @@ int b200splat_p2p_allreduce(const b200splat_p2p_args* a) {
     CU(launch_p2p_allreduce(t, reinterpret_cast<cudaStream_t>(a->stream)));
     return B200SPLAT_OK;
 }
+int b200splat_mc_allreduce(const b200splat_mc_args* a) {
+    if (!a) return fail(B200SPLAT_ERR_INVALID, "null args");
+    if (a->world < 1 || a->world > P2P_MAX_RANKS || a->rank < 0 || a->rank >= a->world)
+        return fail(B200SPLAT_ERR_INVALID, "rank %d / world %d out of range (max %d)", a->rank, a->world, P2P_MAX_RANKS);
+    if (a->n_segments < 1 || a->n_segments > P2P_MAX_SEG)
+        return fail(B200SPLAT_ERR_INVALID, "n_segments must be in [1, %d]", P2P_MAX_SEG);
+    if (!a->mc_buffer || (reinterpret_cast<uintptr_t>(a->mc_buffer) & 15))
+        return fail(B200SPLAT_ERR_INVALID, "multicast buffer pointer missing or misaligned");
+    P2PTab t;
+    t.rank = a->rank, t.world = a->world, t.epoch = a->epoch;
+    t.n_seg = a->n_segments, t.seg_max_mask = 0u;
+    for (int i = 0; i < P2P_MAX_SEG; ++i) t.seg_first4[i] = t.seg_n4[i] = 0;
+    for (int i = 0; i < a->n_segments; ++i) {
+        if (a->seg_offset[i] < 0 || a->seg_count[i] < 0 || (a->seg_offset[i] & 3) || (a->seg_count[i] & 3))
+            return fail(B200SPLAT_ERR_INVALID, "segment %d: offset and count must be non-negative multiples of 4", i);
+        if (a->seg_op[i] != B200SPLAT_P2P_SUM && a->seg_op[i] != B200SPLAT_P2P_MAX)
+            return fail(B200SPLAT_ERR_INVALID, "segment %d: unknown op %d", i, a->seg_op[i]);
+        t.seg_first4[i] = a->seg_offset[i] / 4, t.seg_n4[i] = a->seg_count[i] / 4;
+        if (a->seg_op[i] == B200SPLAT_P2P_MAX) t.seg_max_mask |= 1u << i;
+    }
+    for (int k = 0; k < P2P_MAX_RANKS; ++k) {
+        t.bufs[k] = nullptr;
+        t.signals[k] = k < a->world ? reinterpret_cast<uint32_t*>(a->signals[k]) : nullptr;
+        if (k < a->world && !t.signals[k]) return fail(B200SPLAT_ERR_INVALID, "signal pointer of rank %d missing", k);
+    }
+    if (a->world == 1) return B200SPLAT_OK;
+    CU(launch_mc_allreduce(t, reinterpret_cast<float*>(a->mc_buffer), reinterpret_cast<cudaStream_t>(a->stream)));
+    return B200SPLAT_OK;
+}
 int b200splat_p2p_error(const void* own_signals, int32_t* flag_out) {
     if (!own_signals || !flag_out) return fail(B200SPLAT_ERR_INVALID, "bad argument");
     uint32_t w = 0;

@@ -208,8 +208,9 @@ int set_staging_mode(int mode);   // render.cu; returns the previous mode
 // ---- all-reduce over NVLink peer memory (p2p.cu) -------------------------------------------------
 constexpr int P2P_MAX_RANKS = 8;
 constexpr int P2P_MAX_SEG = 16;
-constexpr int P2P_ERROR_WORD = 2 * P2P_MAX_RANKS;       // signal row layout: [ready x 8][done x 8][error][counter]
+constexpr int P2P_ERROR_WORD = 2 * P2P_MAX_RANKS;       // signal row layout: [ready x 8][done x 8][error][counter][epoch]
 constexpr int P2P_COUNTER_WORD = 2 * P2P_MAX_RANKS + 1;
+constexpr int P2P_EPOCH_WORD = 2 * P2P_MAX_RANKS + 2;     // the rank's call counter (epoch argument 0: see p2p.cu)
 constexpr int P2P_SIGNAL_WORDS = 64;
 struct P2PTab {
     int rank, world;
@@ -221,6 +222,8 @@ struct P2PTab {
     uint32_t* signals[P2P_MAX_RANKS];  // every rank's signal words
 };
 cudaError_t launch_p2p_allreduce(const P2PTab& t, cudaStream_t st);
+// the same through the NVSwitch multicast address `mc` of the buffers (t.bufs unused)
+cudaError_t launch_mc_allreduce(const P2PTab& t, float* mc, cudaStream_t st);
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // per-thread asynchronous 16-byte copies global -> shared (LDGSTS), groups committed / awaited by the same thread

@@ -58,13 +58,21 @@ __device__ __forceinline__ void st_cg8(float* p, const float8& r) {
 
 constexpr long long P2P_SPIN_LIMIT = 8000000000ll;   // SM clocks
 
+// The call's epoch.  t.epoch != 0: given by the host (must increase by 1 per call).  t.epoch == 0: the rank keeps its
+// own call counter in its signal row (word P2P_EPOCH_WORD), read here by every CTA and advanced by the last CTA of the
+// kernel -- nothing in the launch arguments changes from call to call, so the exchange can be captured in a CUDA graph
+// and replayed (launches of one rank are stream-ordered; every rank makes the same sequence of calls).
+__device__ __forceinline__ uint32_t call_epoch(const P2PTab& t) {
+    return t.epoch ? t.epoch : ld_acquire_sys(t.signals[t.rank] + P2P_EPOCH_WORD) + 1u;
+}
+
 // wait until every peer's word in my signal row `row` reached `epoch`; returns false on timeout
-__device__ __forceinline__ bool wait_row(const P2PTab& t, int row, int tid) {
+__device__ __forceinline__ bool wait_row(const P2PTab& t, int row, int tid, uint32_t epoch) {
     bool ok = true;
     if (tid < t.world) {
         const uint32_t* flag = t.signals[t.rank] + row * P2P_MAX_RANKS + tid;
         const long long t0 = clock64();
-        while ((int32_t)(ld_acquire_sys(flag) - t.epoch) < 0) {
+        while ((int32_t)(ld_acquire_sys(flag) - epoch) < 0) {
             if (clock64() - t0 > P2P_SPIN_LIMIT) {
                 ok = false;
                 break;
@@ -157,11 +165,12 @@ __global__ void __launch_bounds__(256)
 p2p_allreduce_kernel(const __grid_constant__ P2PTab t, int mode) {
     __shared__ int s_flag;
     const int tid = threadIdx.x;
+    const uint32_t epoch = call_epoch(t);
     // phase 0
-    if (blockIdx.x == 0 && tid < t.world) st_release_sys(t.signals[tid] + 0 * P2P_MAX_RANKS + t.rank, t.epoch);
+    if (blockIdx.x == 0 && tid < t.world) st_release_sys(t.signals[tid] + 0 * P2P_MAX_RANKS + t.rank, epoch);
     if (tid == 0) s_flag = 1;
     __syncthreads();
-    if (!wait_row(t, 0, tid)) s_flag = 0;
+    if (!wait_row(t, 0, tid, epoch)) s_flag = 0;
     __syncthreads();
     if (s_flag) {
         const bool aligned32 = (reinterpret_cast<uintptr_t>(t.bufs[t.rank]) & 31) == 0;
@@ -193,9 +202,107 @@ p2p_allreduce_kernel(const __grid_constant__ P2PTab t, int mode) {
     }
     __syncthreads();
     if (s_flag == 2) {
-        if (tid < t.world) st_release_sys(t.signals[tid] + 1 * P2P_MAX_RANKS + t.rank, t.epoch);
-        wait_row(t, 1, tid);
+        if (tid < t.world) st_release_sys(t.signals[tid] + 1 * P2P_MAX_RANKS + t.rank, epoch);
+        wait_row(t, 1, tid, epoch);
+        // every CTA of this launch has read the call counter (they all passed the count above): advance it
+        __syncthreads();
+        if (tid == 0 && t.epoch == 0u) st_release_sys(t.signals[t.rank] + P2P_EPOCH_WORD, epoch);
     }
+}
+
+// ---- the same exchange through the NVSwitch multicast address of the buffers ---------------------------------------
+// multimem.ld_reduce: one load whose value is the switch's reduction of the word at that offset in every bound buffer;
+// multimem.st: one store the switch replicates into every bound buffer.
+__device__ __forceinline__ float4 mc_ld_add4(const float* p) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ void mc_st4(float* p, const float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t mc_ld_max_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.max.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mc_st_u32(uint32_t* p, uint32_t v) {
+    asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int U>
+__global__ void __launch_bounds__(256)
+mc_allreduce_kernel(const __grid_constant__ P2PTab t, float* mc) {
+    __shared__ int s_flag;
+    const int tid = threadIdx.x;
+    const uint32_t epoch = call_epoch(t);
+    // phase 0: "my buffer is complete" to every peer; wait for theirs
+    if (blockIdx.x == 0 && tid < t.world) st_release_sys(t.signals[tid] + 0 * P2P_MAX_RANKS + t.rank, epoch);
+    if (tid == 0) s_flag = 1;
+    __syncthreads();
+    if (!wait_row(t, 0, tid, epoch)) s_flag = 0;
+    __syncthreads();
+    if (s_flag) {
+        const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+        for (int sgm = 0; sgm < t.n_seg; ++sgm) {
+            const int64_t first4 = t.seg_first4[sgm], n4 = t.seg_n4[sgm];
+            const int64_t lo = first4 + n4 * t.rank / t.world, hi = first4 + n4 * (t.rank + 1) / t.world;   // my slice
+            if ((t.seg_max_mask >> sgm) & 1u) {
+                uint32_t* w = reinterpret_cast<uint32_t*>(mc);
+                for (int64_t i = 4 * lo + (int64_t)blockIdx.x * blockDim.x + tid; i < 4 * hi; i += stride)
+                    mc_st_u32(w + i, mc_ld_max_u32(w + i));
+                continue;
+            }
+            for (int64_t i0 = lo + (int64_t)blockIdx.x * blockDim.x + tid; i0 < hi; i0 += U * stride) {
+                float4 v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int64_t i = i0 + u * stride;
+                    if (i < hi) v[u] = mc_ld_add4(mc + 4 * i);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int64_t i = i0 + u * stride;
+                    if (i < hi) mc_st4(mc + 4 * i, v[u]);
+                }
+            }
+        }
+    }
+    // phase 1: my replicated stores have landed everywhere -> tell every peer, wait for theirs (see p2p_allreduce_kernel)
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence_system();
+        uint32_t* counter = t.signals[t.rank] + P2P_COUNTER_WORD;
+        const uint32_t prev = atomicAdd(counter, 1u);
+        s_flag = (prev == gridDim.x - 1) ? 2 : 0;
+        if (s_flag == 2) {
+            *counter = 0u;
+            __threadfence_system();
+        }
+    }
+    __syncthreads();
+    if (s_flag == 2) {
+        if (tid < t.world) st_release_sys(t.signals[tid] + 1 * P2P_MAX_RANKS + t.rank, epoch);
+        wait_row(t, 1, tid, epoch);
+        // every CTA of this launch has read the call counter (they all passed the count above): advance it
+        __syncthreads();
+        if (tid == 0 && t.epoch == 0u) st_release_sys(t.signals[t.rank] + P2P_EPOCH_WORD, epoch);
+    }
+}
+
+cudaError_t launch_mc_allreduce(const P2PTab& t, float* mc, cudaStream_t st) {
+    static const int blocks = getenv("B200SPLAT_MC_BLOCKS") ? atoi(getenv("B200SPLAT_MC_BLOCKS")) : NUM_SMS;
+    static const int unroll = getenv("B200SPLAT_MC_UNROLL") ? atoi(getenv("B200SPLAT_MC_UNROLL")) : 4;
+    if (unroll == 8) mc_allreduce_kernel<8><<<blocks, 256, 0, st>>>(t, mc);
+    else if (unroll == 2) mc_allreduce_kernel<2><<<blocks, 256, 0, st>>>(t, mc);
+    else mc_allreduce_kernel<4><<<blocks, 256, 0, st>>>(t, mc);
+    count_launch();
+    return cudaGetLastError();
 }
 
 cudaError_t launch_p2p_allreduce(const P2PTab& t, cudaStream_t st) {
