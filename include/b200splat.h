@@ -57,6 +57,12 @@ typedef struct b200splat_camera {
     const float* viewmatrix;  /* device, 16 */
     const float* projmatrix;  /* device, 16 */
     const float* campos;      /* device, 3  */
+    /* Optional: the camera's derived scalars already on the device, 4 floats (focal_x = W / (2 tanfovx),
+     * focal_y = H / (2 tanfovy), limx = 1.3 tanfovx, limy = 1.3 tanfovy).  When set, tanfovx / tanfovy above are
+     * ignored: a caller whose field of view lives in a device tensor (the reference's batch["fovy"],
+     * renderer/diff_gaussian_rasterizer.py:80-81 reads it back with math.tan(tensor) -- one D2H sync per view) never
+     * has to bring it to the host.  NULL: computed from tanfovx / tanfovy on the host. */
+    const float* scalars_dev;
 } b200splat_camera;
 
 /* ---- buffer sizing (bytes) --------------------------------------------------------------- */
@@ -327,6 +333,9 @@ typedef struct b200splat_postprocess_args {
     b200splat_stream stream;
     const int32_t* shading_per_view; /* HOST array of V B200SPLAT_SHADE_* (V <= 64) overriding `shading`, or NULL:
                                         the reference's material draws the mode per view in training */
+    const float* lights_per_view;    /* HOST array (V,6) = (ambient rgb, diffuse rgb) per view (V <= 64) overriding
+                                        ambient / diffuse, or NULL: the material's soft_shading draws a new ambient
+                                        ratio per view in training (material/gaussian_material.py:58-63) */
 } b200splat_postprocess_args;
 size_t b200splat_postprocess_scratch_bytes(int32_t V, int32_t H, int32_t W);
 int b200splat_postprocess_forward(const b200splat_postprocess_args* args);

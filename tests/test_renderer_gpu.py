@@ -59,11 +59,11 @@ def _loss(outputs, wts, dev):
     return sum((outputs[k] * w.to(dev)).sum() for k, w in wts.items() if k in outputs)
 
 
-@pytest.mark.parametrize("variant,pred_normal,train", [("plain", False, False), ("advanced", False, True),
-                                                        ("background", False, True), ("normal", False, True),
-                                                        ("normal", True, True), ("shading", False, True),
-                                                        ("shading", True, False)])
-def test_batch_forward_matches_the_per_view_composition(variant, pred_normal, train):
+@pytest.mark.parametrize("variant,pred_normal,train,soft", [
+    ("plain", False, False, False), ("advanced", False, True, False), ("background", False, True, False),
+    ("normal", False, True, False), ("normal", True, True, False), ("shading", False, True, False),
+    ("shading", True, False, False), ("shading", False, True, True)])
+def test_batch_forward_matches_the_per_view_composition(variant, pred_normal, train, soft):
     from b200splat.renderer import B200GaussianBatchRenderer, _settings
     from diff_gaussian_rasterization import GaussianRasterizer
     P, H, W, V = 5000, 64, 80, 3
@@ -82,7 +82,7 @@ def test_batch_forward_matches_the_per_view_composition(variant, pred_normal, tr
     ren.background = lambda dirs: bg_map
     mat = types.SimpleNamespace(ambient_light_color=torch.tensor([0.1, 0.1, 0.1]),
                                 diffuse_light_color=torch.tensor([0.9, 0.9, 0.9]), ambient_only=False, training=train,
-                                cfg=types.SimpleNamespace(diffuse_prob=0.75, textureless_prob=0.5, soft_shading=False))
+                                cfg=types.SimpleNamespace(diffuse_prob=0.75, textureless_prob=0.5, soft_shading=soft))
     ren.material = mat
     random.seed(7)
     out = ren.batch_forward(batch)
@@ -115,14 +115,19 @@ def test_batch_forward_matches_the_per_view_composition(variant, pred_normal, tr
             pred = GaussianRasterizer(raster_settings=rs)(means2D=torch.zeros_like(m2), shs=geo.get_normal.unsqueeze(1),
                                                           colors_precomp=None, **kw)[0]
         shading = "diffuse"
+        ambient_c, diffuse_c = mat.ambient_light_color, mat.diffuse_light_color
         if variant == "shading":
+            if train and soft:   # material/gaussian_material.py:58-63: a new ambient ratio per view, drawn first
+                r = random.random()
+                diffuse_c = torch.full_like(mat.diffuse_light_color, r)
+                ambient_c = 1.0 - diffuse_c
             if train:
                 shading = "albedo" if random.random() > 0.75 else ("textureless" if random.random() < 0.5 else "diffuse")
         mode = {"plain": PO.MODE_PLAIN, "advanced": PO.MODE_PLAIN, "background": PO.MODE_BACKGROUND,
                 "normal": PO.MODE_NORMAL, "shading": PO.MODE_SHADING}[variant]
         post = PO.postprocess_view(mode, image.cpu(), depth.cpu(), alpha.cpu(), batch["rays_o"][v].cpu(),
                                    batch["rays_d"][v].cpu(), bg_map[v].cpu(), batch["light_positions"][v].cpu(),
-                                   mat.ambient_light_color, mat.diffuse_light_color, shading,
+                                   ambient_c, diffuse_c, shading,
                                    None if pred is None else pred.cpu())
         exp["comp_rgb"].append(post["render"].permute(1, 2, 0))
         if variant in ("normal", "shading"):
@@ -190,3 +195,47 @@ def test_two_renders_before_backward_do_not_share_a_workspace():
         for _ in range(6):
             ren.batch_forward(batch_a)
     assert len(ren._b200_rasterizers[(V, H, W, "cuda:0")]) == 2
+
+
+def test_device_cameras_match_the_reference_construction_and_batch_forward_never_synchronises():
+    """(1) ``_camera_batch`` (batched device ops) == get_cam_info_gaussian per view on the host (restated in
+    b200splat.scenes.cam_info_gaussian; call site renderer/gaussian_batch_renderer.py:23-49).  (2) After a warm-up
+    call, ``batch_forward`` + backward run with torch's synchronisation debug mode set to "error": no .item() / .cpu() /
+    float(tensor) anywhere on the path (the reference's loop has one D2H read of fovy per view,
+    renderer/diff_gaussian_rasterizer.py:80-81)."""
+    import math
+    from b200splat.renderer import B200GaussianBatchRenderer, _camera_batch
+    P, H, W, V = 4000, 64, 64, 4
+    sc = scenes.make_scene(P, 0, 0.8, seed=231)
+    batch, cams = _batch(V, H, W, 232)
+    wvt, full, centre, tan = _camera_batch(batch)
+    for v in range(V):
+        fovy = float(batch["fovy"][v])
+        rw, rf, rc = scenes.cam_info_gaussian(batch["c2w"][v].cpu(), fovy, fovy, 0.1, 100.0)
+        assert float((wvt[v].cpu() - rw).abs().max()) < 2e-6 and float((full[v].cpu() - rf).abs().max()) < 1e-5
+        assert float((centre[v].cpu() - rc).abs().max()) < 1e-5
+        assert float(tan[v]) == float(torch.tensor(math.tan(fovy * 0.5), dtype=torch.float32))
+
+    class Ren(B200GaussianBatchRenderer):
+        variant = "shading"
+
+    ren = Ren()
+    ren.training, ren.background_tensor = True, torch.ones(3, device="cuda")
+    ren.geometry = _Geometry(sc, True, 233)
+    bg_map = torch.rand(V, H, W, 3, device="cuda")
+    ren.background = lambda dirs: bg_map
+    ren.material = types.SimpleNamespace(ambient_light_color=torch.tensor([0.1, 0.1, 0.1], device="cuda"),
+                                         diffuse_light_color=torch.tensor([0.9, 0.9, 0.9], device="cuda"),
+                                         ambient_only=False, training=True,
+                                         cfg=types.SimpleNamespace(diffuse_prob=0.75, textureless_prob=0.5, soft_shading=True))
+    out = ren.batch_forward(batch)                   # warm-up: workspaces, pinned notice words, light-colour cache
+    (out["comp_rgb"].sum() + out["comp_depth"].sum()).backward()
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        out = ren.batch_forward(batch)
+        (out["comp_rgb"].sum() + out["comp_depth"].sum()).backward()
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    torch.cuda.synchronize()
+    assert torch.isfinite(out["comp_rgb"]).all()

@@ -25,6 +25,7 @@ class Camera(C.Structure):
         ("tanfovx", C.c_float), ("tanfovy", C.c_float), ("scale_modifier", C.c_float),
         ("sh_degree", C.c_int32), ("prefiltered", C.c_int32), ("debug", C.c_int32),
         ("bg", C.c_void_p), ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("campos", C.c_void_p),
+        ("scalars_dev", C.c_void_p),
     ]
 
 
@@ -117,7 +118,7 @@ class PostprocessArgs(C.Structure):
         ("g_render", C.c_void_p), ("g_normal", C.c_void_p), ("g_depth", C.c_void_p),
         ("d_image", C.c_void_p), ("d_depth", C.c_void_p), ("d_alpha", C.c_void_p), ("d_bg", C.c_void_p),
         ("scratch", C.c_void_p), ("scratch_bytes", C.c_size_t), ("stream", C.c_void_p),
-        ("shading_per_view", C.POINTER(C.c_int32)),
+        ("shading_per_view", C.POINTER(C.c_int32)), ("lights_per_view", C.POINTER(C.c_float)),
     ]
 
 

@@ -441,17 +441,20 @@ class _RasterizeViews(torch.autograd.Function):
         m3, sh_, cp_, op_ = f(means3D, "means3D"), f(shs, "shs"), f(colors_precomp, "colors_precomp"), \
             f(opacities, "opacities")
         sc_, ro_ = f(scales, "scales"), f(rotations, "rotations")
-        # fresh outputs every call (callers write into them in place); the workspace only lends scratch
-        color = torch.empty(V, 3, H, W, dtype=torch.float32, device=dev)
-        depth = torch.empty(V, 1, H, W, dtype=torch.float32, device=dev)
-        alpha = torch.empty(V, 1, H, W, dtype=torch.float32, device=dev)
-        radii = torch.empty(V, P, dtype=torch.int32, device=dev)
-        ws.color, ws.depth, ws.alpha = list(color.unbind(0)), list(depth.unbind(0)), list(alpha.unbind(0))
-        ws.radii = list(radii.unbind(0))
+        # fresh outputs every call (callers write into them in place); the workspace only lends scratch.
+        # owner.single: the one-view operator (GaussianRasterizer) -- outputs without the view dimension
+        lead = () if owner.single else (V,)
+        unb = (lambda t: [t]) if owner.single else (lambda t: list(t.unbind(0)))
+        color = torch.empty(*lead, 3, H, W, dtype=torch.float32, device=dev)
+        depth = torch.empty(*lead, 1, H, W, dtype=torch.float32, device=dev)
+        alpha = torch.empty(*lead, 1, H, W, dtype=torch.float32, device=dev)
+        radii = torch.empty(*lead, P, dtype=torch.int32, device=dev)
+        ws.color, ws.depth, ws.alpha = unb(color), unb(depth), unb(alpha)
+        ws.radii = unb(radii)
         n_extra = ops._check_extra(extra_features, P)
         ex_ = f(extra_features, "extra_features") if n_extra else None
-        extra = torch.empty(V, n_extra, H, W, dtype=torch.float32, device=dev)
-        ekw = dict(extra_features=ex_, extra_out=list(extra.unbind(0))) if n_extra else {}
+        extra = torch.empty(*lead, n_extra, H, W, dtype=torch.float32, device=dev)
+        ekw = dict(extra_features=ex_, extra_out=unb(extra)) if n_extra else {}
         owner.render_checked(cams, m3, sh_, cp_, op_, sc_, ro_, **ekw)
         owner.generation += 1
         ctx.owner, ctx.cams, ctx.generation = owner, cams, owner.generation
@@ -483,18 +486,20 @@ class _RasterizeViews(torch.autograd.Function):
             out["shs"] = new(P, sh_.shape[1], 3)
         if has_cp:
             out["colors_precomp"] = new(P, 3)
-        m2 = new(V, P, 3)
+        single = owner.single
+        m2 = new(P, 3) if single else new(V, P, 3)
         g = lambda t: None if t is None else ops._f32c(t, "grad")
         gc, gd, ga = g(g_color), g(g_depth), g(g_alpha)
-        pgs = [(None if gc is None else gc[v], None if gd is None else gd[v], None if ga is None else ga[v])
-               for v in range(V)]
+        pick = (lambda t, v: t) if single else (lambda t, v: t[v])
+        pgs = [(None if gc is None else pick(gc, v), None if gd is None else pick(gd, v),
+                None if ga is None else pick(ga, v)) for v in range(V)]
         ekw = {}
         if n_extra:
             out["extra_features"] = new(P, n_extra)
             ge = g(g_extra)
-            ekw = dict(extra_features=ex_, extra_grads=None if ge is None else list(ge.unbind(0)))
+            ekw = dict(extra_features=ex_, extra_grads=None if ge is None else ([ge] if single else list(ge.unbind(0))))
         backward_batched(ws, ctx.cams, m3, sh_, cp_, op_, sc_, ro_, pgs, out, accumulate=False,
-                         means2D_out=list(m2.unbind(0)), **ekw)
+                         means2D_out=[m2] if single else list(m2.unbind(0)), **ekw)
         return (None, None, out["means3D"], m2, out.get("shs"), out.get("colors_precomp"), out["opacities"],
                 out["scales"], out["rotations"], out.get("extra_features"))
 
@@ -514,9 +519,11 @@ class ViewBatchRasterizer(torch.nn.Module):
 
     HEADROOM = 1.5
 
-    def __init__(self, views: int, P: int, H: int, W: int, device="cuda"):
+    def __init__(self, views: int, P: int, H: int, W: int, device="cuda", single: bool = False):
         super().__init__()
         assert views <= MAX_VIEWS, f"at most {MAX_VIEWS} views per batch call"
+        assert not single or views == 1
+        self.single = single      # one-view operator: tensors without the leading view dimension (see one_view_forward)
         self.ws = BatchWorkspace(views, P, H, W, torch.device(device))
         self.generation = 0
         self.regrown = 0          # how many times a forward had to be repeated with larger binning buffers
@@ -587,3 +594,36 @@ class ViewBatchRasterizer(torch.nn.Module):
                 means3D, means2D, opacities, shs, colors_precomp, scales, rotations, extra_features))):
             self._ctx = None
         return out if extra_features is not None else out[:4]
+
+
+# ------------------------------------------------------------------------------------------------------
+# The one-view operator on pooled persistent workspaces: what ``diff_gaussian_rasterization.GaussianRasterizer``
+# (the reference's unchanged per-view loop, renderer/gaussian_batch_renderer.py:21-54) runs on.  Compared with the
+# allocate-per-call single-view entry point it has no host round trip in the middle of the forward (the pair count is
+# learnt from the scan kernel's notice while the rest of the forward is already queued), no per-call allocation of the
+# geometry / binning / scratch buffers and no 64 MB scratch memset per backward (self-cleaning scratch).
+# ------------------------------------------------------------------------------------------------------
+_ONE_VIEW_POOL: Dict[tuple, List["ViewBatchRasterizer"]] = {}
+ONE_VIEW_POOL_MAX = 16   # live graphs per (device, H, W): 4 views per step, two batches per step in the zero123 systems
+
+
+def one_view_rasterizer(P: int, H: int, W: int, device) -> Optional["ViewBatchRasterizer"]:
+    """A pooled one-view rasterizer whose last graph has been consumed, or None when ONE_VIEW_POOL_MAX graphs of this
+    shape are still alive (the caller then takes the allocating path)."""
+    pool = _ONE_VIEW_POOL.setdefault((str(device), H, W), [])
+    for rast in pool:
+        if not rast.pending:
+            return rast
+    if len(pool) >= ONE_VIEW_POOL_MAX:
+        return None
+    pool.append(ViewBatchRasterizer(1, P, H, W, device, single=True))
+    return pool[-1]
+
+
+def one_view_forward(rast: "ViewBatchRasterizer", cam: ops.Cam, means3D, means2D, shs, colors_precomp, opacities, scales,
+                     rotations, extra_features=None):
+    """-> (color (3,H,W), radii (P,), depth (1,H,W), alpha (1,H,W), extra (C',H,W)) with autograd."""
+    if means3D.shape[0] != rast.ws.P:
+        rast.ws.resize(int(means3D.shape[0]))
+    return _RasterizeViews.apply(rast, [cam], means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
+                                 extra_features)

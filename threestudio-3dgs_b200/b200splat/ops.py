@@ -52,21 +52,34 @@ class Cam(NamedTuple):
     viewmatrix: torch.Tensor
     projmatrix: torch.Tensor
     campos: torch.Tensor
+    scalars: Optional[torch.Tensor] = None   # device (focal_x, focal_y, limx, limy) when tanfov is a device tensor
 
     def c_struct(self) -> _lib.Camera:
         return _lib.Camera(self.H, self.W, float(self.tanfovx), float(self.tanfovy), float(self.scale_modifier),
                            int(self.sh_degree), int(bool(self.prefiltered)), int(bool(self.debug)),
                            self.bg.data_ptr(), self.viewmatrix.data_ptr(), self.projmatrix.data_ptr(),
-                           self.campos.data_ptr())
+                           self.campos.data_ptr(), None if self.scalars is None else self.scalars.data_ptr())
+
+
+def camera_scalars(tanfovx: torch.Tensor, tanfovy: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    """(..., 4) fp32 (focal_x, focal_y, limx, limy) from device tangents, in the operation order of the C side
+    (csrc/api.cu fill_camera): W / (2 tan), H / (2 tan), 1.3 tan -- one IEEE fp32 operation each, so the values equal
+    what the host computes from the same fp32 tangents bit for bit."""
+    tx, ty = tanfovx.float(), tanfovy.float()
+    return torch.stack([float(W) / (2.0 * tx), float(H) / (2.0 * ty), tx * 1.3, ty * 1.3], dim=-1).contiguous()
 
 
 def make_cam(settings, device) -> Cam:
     t = lambda x, n: _f32c(torch.as_tensor(x, device=device) if not torch.is_tensor(x) else x.to(device), n)
-    return Cam(int(settings.image_height), int(settings.image_width), float(settings.tanfovx),
-               float(settings.tanfovy), float(settings.scale_modifier), int(settings.sh_degree),
+    H, W = int(settings.image_height), int(settings.image_width)
+    tx, ty, scalars = settings.tanfovx, settings.tanfovy, None
+    if torch.is_tensor(tx) and tx.is_cuda:   # the field of view lives on the device: keep it there (no .item() sync)
+        scalars = camera_scalars(tx.reshape(()), (ty if torch.is_tensor(ty) else tx.new_tensor(ty)).reshape(()), H, W)
+        tx = ty = 0.0
+    return Cam(H, W, float(tx), float(ty), float(settings.scale_modifier), int(settings.sh_degree),
                bool(settings.prefiltered), bool(settings.debug), t(settings.bg, "bg").reshape(-1),
                t(settings.viewmatrix, "viewmatrix"), t(settings.projmatrix, "projmatrix"),
-               t(settings.campos, "campos").reshape(-1))
+               t(settings.campos, "campos").reshape(-1), scalars)
 
 
 class ForwardState(NamedTuple):

@@ -39,6 +39,13 @@ def _args(mode, shading, image, depth, alpha, rays_o, rays_d, bg, light, pred_no
     a.image, a.depth, a.alpha = image.data_ptr(), depth.data_ptr(), alpha.data_ptr()
     a.rays_o, a.rays_d, a.bg = ops._ptr(rays_o), ops._ptr(rays_d), ops._ptr(bg)
     a.light, a.pred_normal = ops._ptr(light), ops._ptr(pred_normal)
+    if ambient and isinstance(ambient[0], (list, tuple)):     # per-view light colours (soft_shading)
+        if len(ambient) != V or len(diffuse) != V:
+            raise ValueError("one (ambient, diffuse) pair per view expected")
+        flat = [float(x) for v in range(V) for x in (*ambient[v], *diffuse[v])]
+        a._keep_l = (C.c_float * (6 * V))(*flat)
+        a.lights_per_view = a._keep_l
+        ambient, diffuse = ambient[0], diffuse[0]
     a.ambient = (C.c_float * 3)(*ambient)
     a.diffuse = (C.c_float * 3)(*diffuse)
     a.stream = ops._stream(image.device)
@@ -66,7 +73,7 @@ class _Postprocess(torch.autograd.Function):
             check(lib.b200splat_postprocess_forward(C.byref(a)), "b200splat_postprocess_forward")
         e = lambda t: t if t is not None else torch.empty(0, device=dev)
         ctx.save_for_backward(image, depth, alpha, e(bg), e(rays_o), e(rays_d), e(light), e(pred_normal))
-        ctx.cfg = (mode, shading, tuple(ambient), tuple(diffuse), bg is not None and bg.requires_grad)
+        ctx.cfg = (mode, shading, ambient, diffuse, bg is not None and bg.requires_grad)
         return render, normal, depth_out
 
     @staticmethod
@@ -95,6 +102,13 @@ class _Postprocess(torch.autograd.Function):
         return (d_image, d_depth, d_alpha, d_bg) + (None,) * 8
 
 
+def _lights(c):
+    """(3,) colour or a list of V (3,) colours -> plain floats (tuples: they are kept on the autograd ctx)."""
+    if len(c) and isinstance(c[0], (list, tuple)):
+        return tuple(tuple(float(x) for x in v) for v in c)
+    return tuple(float(x) for x in c)
+
+
 def postprocess_views(mode: str, image, depth, alpha, *, bg=None, rays_o=None, rays_d=None, light_positions=None,
                       pred_normal: Optional[torch.Tensor] = None, shading: str = "diffuse",
                       ambient: Sequence[float] = (0.1, 0.1, 0.1), diffuse: Sequence[float] = (0.9, 0.9, 0.9)):
@@ -112,5 +126,5 @@ def postprocess_views(mode: str, image, depth, alpha, *, bg=None, rays_o=None, r
         raise ValueError("mode 'shading' needs light_positions")
     render, normal, depth_out = _Postprocess.apply(
         image, depth, alpha, bg, m, s, rays_o, rays_d, light_positions,
-        None if pred_normal is None else pred_normal.detach(), [float(x) for x in ambient], [float(x) for x in diffuse])
+        None if pred_normal is None else pred_normal.detach(), _lights(ambient), _lights(diffuse))
     return dict(render=render, normal=normal if m >= 2 else None, depth=depth_out)

@@ -13,7 +13,7 @@ Mix it into a renderer class that has what the reference's renderers have: ``sel
 ``GaussianBaseModel`` getters, geometry/gaussian_base.py:371-411), ``self.background_tensor``, ``self.training`` and,
 for the background / shading variants, ``self.background`` (called with ``dirs=(V,H,W,3)``) and ``self.material``
 (``ambient_light_color``, ``diffuse_light_color``, ``ambient_only``, ``cfg.diffuse_prob``,
-``cfg.textureless_prob``, ``cfg.soft_shading`` -- material/gaussian_material.py:13-104).  ``variant`` selects which of
+``cfg.textureless_prob``, ``cfg.soft_shading`` -- material/gaussian_material.py:13-104; all of them honoured).  ``variant`` selects which of
 the reference's renderer files is mirrored:
 
     "plain"       renderer/diff_gaussian_rasterizer.py            render only, background inverted in eval
@@ -45,15 +45,49 @@ from .postops import postprocess_views
 SH_C0 = 0.28209479177387814
 
 
-def _settings(batch, v: int, bg: torch.Tensor, sh_degree: int, device):
+def _camera_batch(batch, znear: float = 0.1, zfar: float = 100.0):
+    """All V cameras of ``batch`` at once, ON THE DEVICE: what the reference's loop builds per view with
+    ``get_cam_info_gaussian(c2w, fovx=fovy, fovy, znear=0.1, zfar=100)`` (renderer/gaussian_batch_renderer.py:23-49;
+    the same construction as geometry/sugar.py:891-896 + utils/sugar_utils.py:809-829) -- flip the y / z camera axes
+    of c2w, invert, transpose -> world_view_transform; times the transposed projection -> full_proj_transform; camera
+    centre = inverse(world_view_transform)[3, :3].  Nothing here reads a tensor back: the reference's
+    ``math.tan(FoVx * 0.5)`` on a 0-dim CUDA tensor (renderer/diff_gaussian_rasterizer.py:80-81) is one D2H
+    synchronisation per view; here tan(fovy / 2) stays a device tensor all the way into the kernels
+    (b200splat_camera.scalars_dev).  The tangent is taken in float64 and rounded to fp32, as Python's math.tan does.
+    Returns (world_view (V,4,4), full_proj (V,4,4), centre (V,3), tanfov (V,))."""
+    c2w = batch["c2w"].detach().to(torch.float32).clone()
+    V = c2w.shape[0]
+    if c2w.shape[-2] == 3:
+        last = torch.tensor([0.0, 0.0, 0.0, 1.0], device=c2w.device).expand(V, 1, 4)
+        c2w = torch.cat([c2w, last], dim=1)
+    c2w[:, :3, 1:3] *= -1
+    # inv_ex without the error check: linalg.inv reads its info tensor back (a synchronisation)
+    wvt = torch.linalg.inv_ex(c2w, check_errors=False).inverse.transpose(1, 2).contiguous()
+    fovy = batch["fovy"].detach().reshape(-1).to(c2w.device)
+    tan64 = torch.tan(fovy.double() * 0.5)
+    # utils/sugar_utils.py:809-829 with fovx = fovy: P[0,0] = P[1,1] = 2 znear / (2 tan znear), P[3,2] = 1,
+    # P[2,2] = zfar / (zfar - znear), P[2,3] = -zfar znear / (zfar - znear)
+    p00 = (2.0 * znear / (2.0 * (tan64 * znear))).float()
+    proj_t = torch.zeros(V, 4, 4, device=c2w.device)          # the TRANSPOSED projection
+    proj_t[:, 0, 0] = p00
+    proj_t[:, 1, 1] = p00
+    proj_t[:, 2, 2] = zfar / (zfar - znear)
+    proj_t[:, 3, 2] = -(zfar * znear) / (zfar - znear)
+    proj_t[:, 2, 3] = 1.0
+    full = torch.bmm(wvt, proj_t).contiguous()
+    centre = torch.linalg.inv_ex(wvt, check_errors=False).inverse[:, 3, :3].contiguous()
+    return wvt, full, centre, tan64.float()
+
+
+def _settings(batch, v: int, bg: torch.Tensor, sh_degree: int, device, cams=None):
+    """GaussianRasterizationSettings of view v; tanfovx / tanfovy are 0-dim DEVICE tensors (b200splat's operators take
+    them as such and never read them back)."""
     from diff_gaussian_rasterization import GaussianRasterizationSettings
-    fovy = float(batch["fovy"][v])
-    wvt, full, center = scenes.cam_info_gaussian(batch["c2w"][v].detach().float().cpu(), fovy, fovy, 0.1, 100.0)
-    t = math.tan(fovy * 0.5)
+    wvt, full, centre, tan = cams if cams is not None else _camera_batch(batch)
     return GaussianRasterizationSettings(
-        image_height=int(batch["height"]), image_width=int(batch["width"]), tanfovx=t, tanfovy=t, bg=bg,
-        scale_modifier=1.0, viewmatrix=wvt.to(device), projmatrix=full.to(device), sh_degree=sh_degree,
-        campos=center.to(device), prefiltered=False, debug=False)
+        image_height=int(batch["height"]), image_width=int(batch["width"]), tanfovx=tan[v], tanfovy=tan[v], bg=bg,
+        scale_modifier=1.0, viewmatrix=wvt[v], projmatrix=full[v], sh_degree=sh_degree, campos=centre[v],
+        prefiltered=False, debug=False)
 
 
 class _ViewspacePoints:
@@ -79,17 +113,31 @@ class B200GaussianBatchRenderer:
     invert_bg_prob: float = 1.0     # Config.invert_bg_prob of the plain / advanced / normal renderers
 
     # ---- what the reference's material.forward decides per call (material/gaussian_material.py:51-93) ----------
-    def _shading_mode(self) -> str:
+    def _light_and_shading(self):
+        """One view's (ambient rgb, diffuse rgb, shading mode), drawn with the same ``random.random()`` call sequence as
+        the reference's per-view ``material.forward``: first the ambient ratio of ``soft_shading`` (training only),
+        then the shading-mode draws.  The material's two colour buffers are read back once and cached."""
         mat = self.material
-        if self.training and getattr(mat.cfg, "soft_shading", False):
-            raise NotImplementedError("soft_shading draws new light colours per view; use the per-view operator")
+        cache = self.__dict__.setdefault("_b200_light_cache", {})
+        key = (id(mat.ambient_light_color), id(mat.diffuse_light_color))
+        if key not in cache:
+            cache.clear()
+            cache[key] = (tuple(float(x) for x in mat.ambient_light_color.tolist()),
+                          tuple(float(x) for x in mat.diffuse_light_color.tolist()))
+        ambient, diffuse = cache[key]
+        if mat.training and getattr(mat.cfg, "soft_shading", False):
+            r = random.random()
+            diffuse, ambient = (r, r, r), (1.0 - r, 1.0 - r, 1.0 - r)
         if mat.training:
             if mat.ambient_only or random.random() > mat.cfg.diffuse_prob:
-                return "albedo"
-            if random.random() < mat.cfg.textureless_prob:
-                return "textureless"
-            return "diffuse"
-        return "albedo" if mat.ambient_only else "diffuse"
+                mode = "albedo"
+            elif random.random() < mat.cfg.textureless_prob:
+                mode = "textureless"
+            else:
+                mode = "diffuse"
+        else:
+            mode = "albedo" if mat.ambient_only else "diffuse"
+        return ambient, diffuse, mode
 
     def _rasterizer(self, V: int, P: int, H: int, W: int, device) -> ViewBatchRasterizer:
         """A ViewBatchRasterizer (persistent workspace) for this shape whose last graph has been consumed.  Systems that
@@ -133,9 +181,10 @@ class B200GaussianBatchRenderer:
         opac, scales, rots = pc.get_opacity, pc.get_scaling, pc.get_rotation
         vsp = torch.zeros(bs, P, 3, dtype=means3D.dtype, device=dev, requires_grad=True)
         images, depths, alphas, radiis, extras = [], [], [], [], []
+        cams = _camera_batch(batch)     # all views' cameras with batched device ops: no per-view D2H / H2D round trips
         for v0 in range(0, bs, MAX_VIEWS):
             n = min(MAX_VIEWS, bs - v0)
-            settings = [_settings(batch, v, bgs[v], pc.active_sh_degree, dev) for v in range(v0, v0 + n)]
+            settings = [_settings(batch, v, bgs[v], pc.active_sh_degree, dev, cams) for v in range(v0, v0 + n)]
             rast = self._rasterizer(n, P, H, W, dev)
             with torch.autocast("cuda", enabled=False):
                 out = rast(settings, means3D, vsp[v0:v0 + n], opac, shs=shs, colors_precomp=override, scales=scales,
@@ -167,10 +216,9 @@ class B200GaussianBatchRenderer:
         if variant in ("normal", "shading"):
             kw.update(rays_o=batch["rays_o"], rays_d=batch["rays_d"])
         if variant == "shading":
-            modes = [self._shading_mode() for _ in range(bs)]
-            mat = self.material
-            kw.update(light_positions=batch["light_positions"], pred_normal=pred_map, shading=modes,
-                      ambient=mat.ambient_light_color.tolist(), diffuse=mat.diffuse_light_color.tolist())
+            lights = [self._light_and_shading() for _ in range(bs)]
+            kw.update(light_positions=batch["light_positions"], pred_normal=pred_map, shading=[m for _, _, m in lights],
+                      ambient=[a for a, _, _ in lights], diffuse=[d for _, d, _ in lights])
         mode = {"plain": "plain", "advanced": "plain"}.get(variant, variant)
         post = postprocess_views(mode, image, depth, alpha, **kw)
         outputs["comp_rgb"] = post["render"].permute(0, 2, 3, 1)

@@ -178,6 +178,7 @@ static int fill_camera(const b200splat_camera& c, const BatchTab& tab, ViewTab* 
     vt->focal_y = (float)tab.H / (2.0f * c.tanfovy);
     vt->limx = FOV_CLAMP * c.tanfovx;
     vt->limy = FOV_CLAMP * c.tanfovy;
+    vt->scalars = c.scalars_dev;
     return B200SPLAT_OK;
 }
 

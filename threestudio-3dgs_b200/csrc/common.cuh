@@ -53,6 +53,7 @@ struct ViewTab {
     const float* campos;
     const float* bg;
     float tanfovx, tanfovy, focal_x, focal_y, limx, limy;
+    const float* scalars;   // optional device copy of (focal_x, focal_y, limx, limy): overrides the four host values
     // per-Gaussian state of this view (geometry buffer)
     int32_t* radii;
     float* rec;

@@ -31,6 +31,8 @@ struct PostTab {
     float ambient[3], diffuse[3];
     int per_view_shading;              // != 0: shading_v[view] instead of `shading`
     uint8_t shading_v[POST_MAX_PER_VIEW];
+    int per_view_light;                // != 0: light_v[view] = (ambient rgb, diffuse rgb) instead of ambient / diffuse
+    float light_v[POST_MAX_PER_VIEW][6];
     // forward outputs
     float* render;        // (V,3,H,W)
     float* normal;        // (V,3,H,W)
@@ -115,7 +117,9 @@ __device__ __forceinline__ void pixel_forward(const PostTab& t, int v, int y, in
         }
         px.dotv = dot3(px.sn, px.ld);
         const float dl = fmaxf(px.dotv, 0.f);
-        px.tl = v3(dl * t.diffuse[0] + t.ambient[0], dl * t.diffuse[1] + t.ambient[1], dl * t.diffuse[2] + t.ambient[2]);
+        const float* amb = t.per_view_light ? t.light_v[v] : t.ambient;
+        const float* dif = t.per_view_light ? t.light_v[v] + 3 : t.diffuse;
+        px.tl = v3(dl * dif[0] + amb[0], dl * dif[1] + amb[1], dl * dif[2] + amb[2]);
         const V3 albc = v3(fminf(fmaxf(px.alb.x, 0.f), 1.f), fminf(fmaxf(px.alb.y, 0.f), 1.f),
                            fminf(fmaxf(px.alb.z, 0.f), 1.f));
         const int shading = t.per_view_shading ? (int)t.shading_v[v] : t.shading;
@@ -195,7 +199,8 @@ __global__ void __launch_bounds__(256) postprocess_backward_local_kernel(const _
         const float inv = 1.0f / (al + 1e-6f);
         d_img = g_alb * inv;                          // albedo = image / (alpha + 1e-6)
         d_al -= dot3(g_alb, px.alb) * inv;
-        const float g_dot = px.dotv >= 0.f ? g_tl.x * t.diffuse[0] + g_tl.y * t.diffuse[1] + g_tl.z * t.diffuse[2] : 0.f;
+        const float* dif = t.per_view_light ? t.light_v[v] + 3 : t.diffuse;
+        const float g_dot = px.dotv >= 0.f ? g_tl.x * dif[0] + g_tl.y * dif[1] + g_tl.z * dif[2] : 0.f;
         const V3 g_ld = px.sn * g_dot;
         if (!t.pred) g_nh = px.ld * g_dot;             // shading normal = the depth-derived normal
         g_xyz = normalize3_vjp(px.ld, px.vlen, g_ld) * -1.0f;   // light direction = normalize(light - xyz)
@@ -269,6 +274,13 @@ static int fill_tab(const b200splat_postprocess_args* a, PostTab* t) {
     t->image = a->image, t->depth = a->depth, t->alpha = a->alpha, t->rays_o = a->rays_o, t->rays_d = a->rays_d;
     t->bg = a->bg, t->light = a->light, t->pred = a->mode == POST_SHADING ? a->pred_normal : nullptr;
     for (int c = 0; c < 3; ++c) t->ambient[c] = a->ambient[c], t->diffuse[c] = a->diffuse[c];
+    if (a->lights_per_view && a->mode == POST_SHADING) {
+        if (a->V > POST_MAX_PER_VIEW)
+            return b200splat_set_error(B200SPLAT_ERR_INVALID, "lights_per_view supports at most 64 views per call");
+        t->per_view_light = 1;
+        for (int v = 0; v < a->V; ++v)
+            for (int c = 0; c < 6; ++c) t->light_v[v][c] = a->lights_per_view[6 * v + c];
+    }
     if (a->shading_per_view && a->mode == POST_SHADING) {
         if (a->V > POST_MAX_PER_VIEW)
             return b200splat_set_error(B200SPLAT_ERR_INVALID, "shading_per_view supports at most 64 views per call");

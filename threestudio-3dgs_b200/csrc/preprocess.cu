@@ -72,13 +72,19 @@ preprocess_kernel(const __grid_constant__ BatchTab tab, const float* __restrict_
                   const float* __restrict__ scales, const float* __restrict__ rotations,
                   const float* __restrict__ opacities, const float* __restrict__ shs,
                   const float* __restrict__ colors_precomp, const float* __restrict__ cov3D_precomp) {
-    __shared__ float sV[MAX_VIEWS][16], sP[MAX_VIEWS][16], sC[MAX_VIEWS][4];
+    __shared__ float sV[MAX_VIEWS][16], sP[MAX_VIEWS][16], sC[MAX_VIEWS][4], sS[MAX_VIEWS][4];
     const int V = tab.V;
     for (int i = threadIdx.x; i < V * 16; i += blockDim.x) {
         sV[i >> 4][i & 15] = tab.v[i >> 4].view[i & 15];
         sP[i >> 4][i & 15] = tab.v[i >> 4].proj[i & 15];
     }
     for (int i = threadIdx.x; i < V * 3; i += blockDim.x) sC[i / 3][i % 3] = tab.v[i / 3].campos[i % 3];
+    // (focal_x, focal_y, limx, limy): from the host, or from the device when the field of view never left it
+    for (int i = threadIdx.x; i < V * 4; i += blockDim.x) {
+        const ViewTab& t = tab.v[i >> 2];
+        const float host[4] = {t.focal_x, t.focal_y, t.limx, t.limy};
+        sS[i >> 2][i & 3] = t.scalars ? t.scalars[i & 3] : host[i & 3];
+    }
     __syncthreads();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= tab.P) return;
@@ -192,12 +198,13 @@ preprocess_kernel(const __grid_constant__ BatchTab tab, const float* __restrict_
             const float ndcx = hx * pw, ndcy = hy * pw;
             // EWA projection
             const float txtz = tvx / tvz, tytz = tvy / tvz;
-            const float tx = fminf(vt.limx, fmaxf(-vt.limx, txtz)) * tvz;
-            const float ty = fminf(vt.limy, fmaxf(-vt.limy, tytz)) * tvz;
-            const float J00 = vt.focal_x / tvz;
-            const float J02 = -(vt.focal_x * tx) / (tvz * tvz);
-            const float J11 = vt.focal_y / tvz;
-            const float J12 = -(vt.focal_y * ty) / (tvz * tvz);
+            const float focal_x = sS[v][0], focal_y = sS[v][1], limx = sS[v][2], limy = sS[v][3];
+            const float tx = fminf(limx, fmaxf(-limx, txtz)) * tvz;
+            const float ty = fminf(limy, fmaxf(-limy, tytz)) * tvz;
+            const float J00 = focal_x / tvz;
+            const float J02 = -(focal_x * tx) / (tvz * tvz);
+            const float J11 = focal_y / tvz;
+            const float J12 = -(focal_y * ty) / (tvz * tvz);
             const float M00 = J00 * mV[0] + J02 * mV[2];
             const float M01 = J00 * mV[4] + J02 * mV[6];
             const float M02 = J00 * mV[8] + J02 * mV[10];

@@ -167,7 +167,7 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
                            float* __restrict__ dL_dcov3D, float* __restrict__ stat_grad_accum,
                            float* __restrict__ stat_denom, float* __restrict__ stat_max_radii, int g_begin,
                            int g_end) {
-    __shared__ float sV[MAX_VIEWS][16], sP[MAX_VIEWS][16], sC[MAX_VIEWS][4];
+    __shared__ float sV[MAX_VIEWS][16], sP[MAX_VIEWS][16], sC[MAX_VIEWS][4], sS[MAX_VIEWS][4];
     // dynamic shared memory: one 48-byte slot per (view, thread) -- first the landing zone of the view's gradient
     // record (cp.async), then the SH phase's per-view state -- and, on the vector path, the thread's SH row
     // (row stride 13 float4: LDS.128 of neighbouring threads fall in different bank groups)
@@ -180,6 +180,11 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
         sP[i >> 4][i & 15] = tab.v[i >> 4].proj[i & 15];
     }
     for (int i = threadIdx.x; i < V * 3; i += blockDim.x) sC[i / 3][i % 3] = tab.v[i / 3].campos[i % 3];
+    for (int i = threadIdx.x; i < V * 4; i += blockDim.x) {   // (focal_x, focal_y, limx, limy), host or device copy
+        const ViewTab& t = tab.v[i >> 2];
+        const float host[4] = {t.focal_x, t.focal_y, t.limx, t.limy};
+        sS[i >> 2][i & 3] = t.scalars ? t.scalars[i & 3] : host[i & 3];
+    }
     __syncthreads();
     const int idx = g_begin + blockIdx.x * blockDim.x + threadIdx.x;   // this launch covers [g_begin, g_end)
     if (idx >= g_end) return;
@@ -311,13 +316,14 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
         const float tvy = mV[1] * x + mV[5] * y + mV[9] * z + mV[13];
         const float tvz = mV[2] * x + mV[6] * y + mV[10] * z + mV[14];
         const float txtz = tvx / tvz, tytz = tvy / tvz;
-        const float tx = fminf(vt.limx, fmaxf(-vt.limx, txtz)) * tvz;
-        const float ty = fminf(vt.limy, fmaxf(-vt.limy, tytz)) * tvz;
-        const float xmul = (txtz < -vt.limx || txtz > vt.limx) ? 0.f : 1.f;
-        const float ymul = (tytz < -vt.limy || tytz > vt.limy) ? 0.f : 1.f;
+        const float focal_x = sS[v][0], focal_y = sS[v][1], limx = sS[v][2], limy = sS[v][3];
+        const float tx = fminf(limx, fmaxf(-limx, txtz)) * tvz;
+        const float ty = fminf(limy, fmaxf(-limy, tytz)) * tvz;
+        const float xmul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
+        const float ymul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
         const float itz = 1.0f / tvz, itz2 = itz * itz, itz3 = itz2 * itz;
-        const float J00 = vt.focal_x * itz, J02 = -vt.focal_x * tx * itz2;
-        const float J11 = vt.focal_y * itz, J12 = -vt.focal_y * ty * itz2;
+        const float J00 = focal_x * itz, J02 = -focal_x * tx * itz2;
+        const float J11 = focal_y * itz, J12 = -focal_y * ty * itz2;
         const float M0[3] = {J00 * mV[0] + J02 * mV[2], J00 * mV[4] + J02 * mV[6], J00 * mV[8] + J02 * mV[10]};
         const float M1[3] = {J11 * mV[1] + J12 * mV[2], J11 * mV[5] + J12 * mV[6], J11 * mV[9] + J12 * mV[10]};
         const float S0[3] = {c0 * M0[0] + c1 * M0[1] + c2 * M0[2], c1 * M0[0] + c3 * M0[1] + c4 * M0[2],
@@ -349,10 +355,10 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
             const float dJ02 = dM0[0] * mV[2] + dM0[1] * mV[6] + dM0[2] * mV[10];
             const float dJ11 = dM1[0] * mV[1] + dM1[1] * mV[5] + dM1[2] * mV[9];
             const float dJ12 = dM1[0] * mV[2] + dM1[1] * mV[6] + dM1[2] * mV[10];
-            const float dtx = xmul * -vt.focal_x * itz2 * dJ02;
-            const float dty = ymul * -vt.focal_y * itz2 * dJ12;
-            const float dtz = -vt.focal_x * itz2 * dJ00 - vt.focal_y * itz2 * dJ11 +
-                              2.f * vt.focal_x * tx * itz3 * dJ02 + 2.f * vt.focal_y * ty * itz3 * dJ12;
+            const float dtx = xmul * -focal_x * itz2 * dJ02;
+            const float dty = ymul * -focal_y * itz2 * dJ12;
+            const float dtz = -focal_x * itz2 * dJ00 - focal_y * itz2 * dJ11 +
+                              2.f * focal_x * tx * itz3 * dJ02 + 2.f * focal_y * ty * itz3 * dJ12;
             dmx += mV[0] * dtx + mV[1] * dty + mV[2] * dtz;
             dmy += mV[4] * dtx + mV[5] * dty + mV[6] * dtz;
             dmz += mV[8] * dtx + mV[9] * dty + mV[10] * dtz;
