@@ -220,6 +220,72 @@ def measure_config(name, V, steps, warmup, dev):
             "pairs_per_view_at_calibration": int(sum(nr) / max(len(nr), 1)), "valid": ok}
 
 
+def measure_spacetime(name, V, steps, warmup, dev, world=1, rank=0):
+    """BASELINE.json configs[4] as written: the spacetime call shape (b200splat/spacetime.py; reference
+    renderer/diff_gaussian_rasterizer_st.py:135-150).  Every view has its own timestamp, hence its own non-leaf
+    ``means3D`` (cubic B-spline of 12 knots per Gaussian) and ``rotations``; the rasterizer is called once per view
+    through the drop-in ``GaussianRasterizer`` (as the reference's loop does) and autograd carries the gradients to the
+    knots.  A step = V views forward + one backward (+ an NCCL all-reduce of the parameter gradients at N > 1).  Timed
+    end to end on the device (CUDA events), parameters resident."""
+    import torch
+    import torch.distributed as dist
+    from b200splat import scenes, spacetime
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    scene, cams_all = scenes.make_workload(name, views=V * world)
+    cams_host = cams_all[rank * V:(rank + 1) * V]
+    H, W = cams_host[0].image_height, cams_host[0].image_width
+    P = scene.means3D.shape[0]
+    params = spacetime.SpacetimeParams(*[t.to(dev).contiguous().requires_grad_(True)
+                                         for t in spacetime.make_params(scene, seed=77)])
+    bg = torch.ones(3, device=dev)
+    rss = [GaussianRasterizationSettings(H, W, c.tanfovx, c.tanfovy, bg, 1.0, c.viewmatrix.to(dev), c.projmatrix.to(dev),
+                                         0, c.campos.to(dev), False, False) for c in cams_host]
+    pgs = [tuple(g.to(dev) for g in scenes.pixel_grads(H, W, 99 + rank * V + v)) for v in range(V)]
+    frames = params.omega.shape[0]
+    times = [((rank * V + v + 0.5) / (V * world), int((rank * V + v + 0.5) / (V * world) * frames)) for v in range(V)]
+
+    def step():
+        for t in params:
+            t.grad = None
+        loss = None
+        for v in range(V):
+            m3, scl, rot, opa, col = spacetime.timed_all(params, *times[v])
+            m2 = torch.zeros_like(m3, requires_grad=True)
+            c, r, d, a = GaussianRasterizer(raster_settings=rss[v])(means3D=m3, means2D=m2, shs=None, colors_precomp=col,
+                                                                    opacities=opa, scales=scl, rotations=rot,
+                                                                    cov3D_precomp=None)
+            l = (c * pgs[v][0]).sum() + (d * pgs[v][1]).sum() + (a * pgs[v][2]).sum()
+            loss = l if loss is None else loss + l
+        loss.backward()
+        if world > 1:
+            for t in params:
+                dist.all_reduce(t.grad)
+
+    from b200splat import _lib
+    for _ in range(max(warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    knots_grad = float(params.knots.grad.abs().max())
+    return {"workload": name, "value": V * world / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+            "views_per_step": V * world, "views_per_gpu_per_step": V, "steps": steps, "gaussians": P, "image": [H, W],
+            "call_shape": "spacetime: per-view spline means3D + normalize(q + dq[frame]) (non-leaf), colors_precomp; one "
+                          "GaussianRasterizer call per view, autograd to the 12 knots per Gaussian",
+            "gpu_launches": int(_lib.launch_count() - l0), "knots_grad_max": knots_grad, "valid": knots_grad > 0}
+
+
 class _S:
     pass
 
@@ -354,6 +420,18 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     N = world
+    if args.workload == "stress_4m_1024_st_b64":
+        # BASELINE.json configs[4] as written (spacetime call shape): its own short bench line
+        V = args.views_per_gpu if args.views_per_gpu != 4 else 8
+        res = measure_spacetime(args.workload, V, args.steps, args.warmup, dev, world, rank)
+        if rank == 0:
+            res.update({"metric": METRIC, "n_gpus": N, "warmup": max(args.warmup, 3), "higher_is_better": True,
+                        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                        "config": {"workload": args.workload, "views_per_gpu_per_step": V}})
+            print(json.dumps(res), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     V = args.views_per_gpu
     scaling = "weak"
     if args.views_total:
@@ -761,6 +839,11 @@ def main():
                     configs.append(measure_config(name, v, 3, 3, dev))
                 except Exception as exc:   # reported, never hidden
                     configs.append({"workload": name, "error": repr(exc)})
+            try:    # configs[4] as written: the spacetime call shape, one GPU's share (8 of the 64 views)
+                configs.append(measure_spacetime("stress_4m_1024_st_b64", 8, 3, 3, dev))
+            except Exception as exc:
+                configs.append({"workload": "stress_4m_1024_st_b64", "error": repr(exc)})
+            torch.cuda.empty_cache()
 
     if rank == 0:
         line = {

@@ -178,6 +178,8 @@ WORKLOADS = {
     "config4_1m_256_sh3_b32": (1_000_000, 3, 0.5, 256, 256, 32, "mvdream"),
     "headline_1m_512_sh3": (1_000_000, 3, 0.5, 512, 512, 1, "mvdream"),
     "stress_4m_1024_sh3_b64": (4_000_000, 3, 0.5, 1024, 1024, 64, "mvdream"),
+    # BASELINE.json configs[4] as written: the spacetime call shape (b200splat/spacetime.py) on the same scene size
+    "stress_4m_1024_st_b64": (4_000_000, 0, 0.5, 1024, 1024, 64, "mvdream"),
 }
 
 
