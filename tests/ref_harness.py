@@ -15,12 +15,18 @@ from pathlib import Path
 import torch
 from torch.overrides import TorchFunctionMode
 
-REFERENCE = Path("/root/reference")
 STUBS = Path(__file__).resolve().parent / "stubs"
+# The reference tree.  It does not exist on the GPU box; scripts/stage_reference_for_gpu.py copies the handful of
+# files the harness imports into tests/_refcopy/ (git-ignored, never committed; it travels with the gpurun snapshot
+# like the built .so), so that the GPU tests can run the reference's UNCHANGED files on the CUDA backend.
+_CANDIDATES = (Path("/root/reference"), Path(__file__).resolve().parent / "_refcopy")
+NEEDED = ("renderer/diff_gaussian_rasterizer.py", "renderer/gaussian_batch_renderer.py", "geometry/gaussian_base.py",
+          "geometry/gaussian_io.py", "geometry/mesh_utils.py")
+REFERENCE = next((p for p in _CANDIDATES if (p / "renderer" / "diff_gaussian_rasterizer.py").exists()), _CANDIDATES[0])
 
 
 def available() -> bool:
-    return (REFERENCE / "renderer" / "diff_gaussian_rasterizer.py").exists()
+    return all((REFERENCE / f).exists() for f in NEEDED)
 
 
 class CudaToCpu(TorchFunctionMode):
