@@ -217,9 +217,10 @@ typedef struct b200splat_batch_forward_args {
     int32_t n_extra;
     float* const* out_extra;      /* V x (n_extra,H,W) */
     /* Optional early overflow notice without a stream synchronisation: V 64-bit words of PINNED HOST memory
-     * (device-accessible by the same pointer: cudaHostAlloc / torch pin_memory).  The scan kernel -- the first
-     * point of the forward at which a view's pair count is known -- stores (notify_epoch << 32) | num_rendered of
-     * view v into pairs_notify[v] while the rest of the forward is still queued behind it; the host polls the word
+     * (device-accessible by the same pointer: cudaHostAlloc / torch pin_memory).  A small reduction right behind the
+     * preprocess kernel -- the first point of the forward at which a view's pair count is known -- stores
+     * (notify_epoch << 32) | num_rendered of view v into pairs_notify[v] while the depth sort, the scan, the key
+     * duplication, the tile partition and the render are still queued behind it; the host polls the word
      * until it carries its epoch and compares the count with the capacity (count > capacity: the view's result is
      * invalid, re-run with a larger buffer).  NULL: no notice. */
     uint64_t* pairs_notify;

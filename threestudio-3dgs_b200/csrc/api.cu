@@ -561,13 +561,16 @@ int b200splat_forward_batched(const b200splat_batch_forward_args* a) {
     CU(launch_clear_batch(tab, /*with_binning=*/true, st));
     CU(launch_preprocess(tab, a->means3D, a->scales, a->rotations, a->opacities, a->shs, a->colors_precomp, nullptr,
                          st));
-    CU(launch_pad_extra(P, tab.n_extra, a->extra_features, const_cast<float4*>(tab.ext4), st)); }
+    CU(launch_pad_extra(P, tab.n_extra, a->extra_features, const_cast<float4*>(tab.ext4), st));
+    // the views' pair counts for a host that waits for them (pairs_notify): known here, ~5 us of work, with the
+    // depth sort, the scan, the key duplication, the tile partition and the render still to be queued behind it
+    CU(launch_pair_count(tab, a->pairs_notify, a->notify_epoch, st)); }
     DEBUG_SYNC(a->cams[0], st, "preprocess");
     { ProfScope ps(3, st, /*counted=*/false);
     CU(launch_gaussian_sort(tab, st, /*cleared=*/true)); }
     DEBUG_SYNC(a->cams[0], st, "depth sort");
     { ProfScope ps(1, st);
-    CU(launch_scan_batch(tab, st, /*cleared=*/true, a->pairs_notify, a->notify_epoch)); }
+    CU(launch_scan_batch(tab, st, /*cleared=*/true)); }
     DEBUG_SYNC(a->cams[0], st, "scan");
     rc = forward_tail(tab, a->cams[0].debug, st, /*binning_cleared=*/true);
     if (rc) return rc;

@@ -44,7 +44,7 @@ constexpr int MAX_PASSES = 8;
 
 // status words of a view (in its image buffer)
 constexpr int STATUS_OVERFLOW = 0;   // != 0: num_rendered exceeded the binning capacity (results invalid)
-constexpr int STATUS_WORDS = 4;
+constexpr int STATUS_WORDS = 4;      // [1], [2]: pair-count sum / ticket of pair_count_kernel (scan_sort.cu)
 
 struct ViewTab {
     // camera (device pointers to the reference's transposed 4x4s) + host-derived fp32 scalars
@@ -204,6 +204,7 @@ size_t dist2_workspace_bytes(int P);
 cudaError_t launch_dist2(int P, const float* points, float* out, void* ws, cudaStream_t st);
 
 void count_launch(int n = 1);
+cudaError_t launch_pair_count(const BatchTab& tab, uint64_t* notify, uint32_t epoch, cudaStream_t st);   // scan_sort.cu
 int set_staging_mode(int mode);   // render.cu; returns the previous mode
 
 // ---- all-reduce over NVLink peer memory (p2p.cu) -------------------------------------------------

@@ -189,6 +189,46 @@ scan_lookback_kernel(int64_t n, const __grid_constant__ ScanTab tab) {
     }
 }
 
+// Early notice of every view's pair count (= sum of tiles_touched) for the host: run right after preprocess, long
+// before the scan produces the same number, so that a host waiting for it (b200splat_batch_forward_args.pairs_notify)
+// gets it while most of the forward is still queued.  Grid (blocks, V); the last CTA of a view writes the word.
+constexpr int STATUS_PAIR_SUM = 1, STATUS_PAIR_TICKET = 2;
+__global__ void __launch_bounds__(256)
+pair_count_kernel(const __grid_constant__ BatchTab tab, uint64_t* notify, uint32_t epoch) {
+    const ViewTab& vt = tab.v[blockIdx.y];
+    const uint4* __restrict__ t4 = reinterpret_cast<const uint4*>(vt.tiles_touched);
+    const int n4 = tab.P / 4;
+    uint32_t sum = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        const uint4 a = __ldg(t4 + i);
+        sum += a.x + a.y + a.z + a.w;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (tab.P & 3)) sum += vt.tiles_touched[4 * n4 + threadIdx.x];
+    sum = __reduce_add_sync(0xffffffffu, sum);
+    __shared__ uint32_t s_sum;
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && sum) atomicAdd(&s_sum, sum);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_sum) atomicAdd(vt.status + STATUS_PAIR_SUM, s_sum);
+        __threadfence();
+        if (atomicAdd(vt.status + STATUS_PAIR_TICKET, 1u) == gridDim.x - 1) {
+            __threadfence();
+            const uint32_t total = atomicAdd(vt.status + STATUS_PAIR_SUM, 0u);
+            st_volatile_u64(notify + blockIdx.y, ((uint64_t)epoch << 32) | (uint64_t)total);
+            __threadfence_system();
+        }
+    }
+}
+cudaError_t launch_pair_count(const BatchTab& tab, uint64_t* notify, uint32_t epoch, cudaStream_t st) {
+    if (tab.P <= 0 || notify == nullptr) return cudaSuccess;
+    const int blocks = min(NUM_SMS, (tab.P / 4 + 255) / 256 + 1);
+    pair_count_kernel<<<dim3(blocks, tab.V), 256, 0, st>>>(tab, notify, epoch);
+    count_launch();
+    return cudaGetLastError();
+}
+
 size_t scan_workspace_bytes(int64_t n) {
     int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     return align_up(16 + (size_t)tiles * 8, 256);
