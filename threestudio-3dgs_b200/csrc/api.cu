@@ -293,19 +293,22 @@ static int check_extra(int n_extra, const void* features, bool has_out) {
 }
 
 // binning + render part of the forward, common to the single-view and the batched entry points
-static int forward_tail(BatchTab& tab, int debug, cudaStream_t st, bool binning_cleared = false) {
+static int forward_tail(BatchTab& tab, int debug, cudaStream_t st, bool binning_cleared = false,
+                        bool duplicated = false) {
     const int T = tab.grid_x * tab.grid_y;
     const int sel = sorted_sel_for(T);
     b200splat_camera dbg{};
     dbg.debug = debug;
     if (tab.P > 0 && tab.capacity > 0) {
         tab.sort_tiles_cap = sort_tiles_for(tab.capacity);
-        { ProfScope ps(2, st);
-        for (int v = 0; v < tab.V && !binning_cleared; ++v) {
-            CU(cudaMemsetAsync(tab.v[v].hist, 0, pair_sort_zero_bytes(tab.capacity, tab.end_bit), st));
-            CU(cudaMemsetAsync(tab.v[v].tile_count, 0, (size_t)T * sizeof(uint32_t), st));
+        if (!duplicated) {
+            ProfScope ps(2, st);
+            for (int v = 0; v < tab.V && !binning_cleared; ++v) {
+                CU(cudaMemsetAsync(tab.v[v].hist, 0, pair_sort_zero_bytes(tab.capacity, tab.end_bit), st));
+                CU(cudaMemsetAsync(tab.v[v].tile_count, 0, (size_t)T * sizeof(uint32_t), st));
+            }
+            CU(launch_duplicate(tab, st));
         }
-        CU(launch_duplicate(tab, st)); }
         DEBUG_SYNC(dbg, st, "duplicateWithKeys");
         { ProfScope ps(3, st);
         CU(launch_sort_batch(tab, st)); }
@@ -569,10 +572,19 @@ int b200splat_forward_batched(const b200splat_batch_forward_args* a) {
     { ProfScope ps(3, st, /*counted=*/false);
     CU(launch_gaussian_sort(tab, st, /*cleared=*/true)); }
     DEBUG_SYNC(a->cams[0], st, "depth sort");
-    { ProfScope ps(1, st);
-    CU(launch_scan_batch(tab, st, /*cleared=*/true)); }
+    // scan of the pair counts in depth order + duplicateWithKeys: one fused kernel (family "duplicate" of the profile)
+    // when the tile histogram fits in shared memory, else the two stand-alone kernels
+    tab.sort_tiles_cap = sort_tiles_for(tab.capacity);
+    const bool fused = scan_duplicate_supported(tab);
+    if (fused) {
+        ProfScope ps(2, st);
+        CU(launch_scan_duplicate(tab, st));
+    } else {
+        ProfScope ps(1, st);
+        CU(launch_scan_batch(tab, st, /*cleared=*/true));
+    }
     DEBUG_SYNC(a->cams[0], st, "scan");
-    rc = forward_tail(tab, a->cams[0].debug, st, /*binning_cleared=*/true);
+    rc = forward_tail(tab, a->cams[0].debug, st, /*binning_cleared=*/true, /*duplicated=*/fused);
     if (rc) return rc;
     if (a->sync) {
         static thread_local uint32_t* host = nullptr;

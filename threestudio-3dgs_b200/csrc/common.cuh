@@ -158,6 +158,9 @@ cudaError_t launch_preprocess(const BatchTab& tab, const float* means3D, const f
                               const float* opacities, const float* shs, const float* colors_precomp,
                               const float* cov3D_precomp, cudaStream_t st);
 cudaError_t launch_duplicate(const BatchTab& tab, cudaStream_t st);
+// scan + duplicateWithKeys in one kernel (scan_sort.cu); needs the scan work area AND the binning work areas cleared
+bool scan_duplicate_supported(const BatchTab& tab);
+cudaError_t launch_scan_duplicate(const BatchTab& tab, cudaStream_t st);
 cudaError_t launch_mark_visible(int P, const float* means3D, const float* view, const float* proj,
                                 uint8_t* present, cudaStream_t st);
 

@@ -229,6 +229,188 @@ cudaError_t launch_pair_count(const BatchTab& tab, uint64_t* notify, uint32_t ep
     return cudaGetLastError();
 }
 
+// ============================================================================================
+// K2+K3 fused: inclusive scan of tiles_touched in depth order AND duplicateWithKeys in one kernel
+// ============================================================================================
+// The stand-alone scan gathered tiles_touched[order[i]], wrote point_offsets, and duplicateWithKeys then re-read the
+// order words and the offsets and gathered the tile rectangle of the same Gaussians.  Here a CTA takes 8192 consecutive
+// ranks of the depth order: order words (coalesced) -> ONE gather of the 8-byte rectangle (its area is the count) ->
+// CTA scan + decoupled look-back (the aggregate is published BEFORE the emission, so successors never wait for it) ->
+// every thread emits the pair words (tile << 32 | gaussian) of its 16 Gaussians at their scanned offsets, and the per-tile
+// pair counts (global bins of the tile partition, tile ranges) are accumulated in shared memory and flushed once per CTA.
+// Same outputs, bit for bit, as scan_lookback_kernel + duplicate_kernel: point_offsets, pair words, tile_count, hist.
+constexpr int SD_MAX_TILES = 8192;
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_duplicate_kernel(const __grid_constant__ BatchTab tab) {
+    extern __shared__ uint32_t s_dyn[];                 // [SCAN_TILE + SCAN_TILE/32] exchange | [passes*256] | [T]
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_warp[SCAN_THREADS / 32];
+    __shared__ uint32_t s_excl;
+    const ViewTab& vt = tab.v[blockIdx.y];
+    const int64_t n = tab.P;
+    const int T = tab.grid_x * tab.grid_y, gx = tab.grid_x;
+    const int passes = tab.digit_passes, end_bit = tab.end_bit;
+    uint32_t* s_x = s_dyn;
+    uint32_t* s_hist = s_dyn + SCAN_TILE + SCAN_TILE / 32;
+    uint32_t* s_cnt = s_hist + passes * 256;
+    for (int i = threadIdx.x; i < passes * 256 + T; i += SCAN_THREADS) s_hist[i] = 0;
+    if (threadIdx.x == 0) s_tile = atomicAdd(vt.scan_ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const int64_t tile_base = (int64_t)tile * SCAN_TILE;
+    const uint64_t* __restrict__ order = vt.gwords[0];
+    const ushort4* __restrict__ rect = vt.rect;
+    uint64_t* desc = vt.scan_desc;
+    // ---- striped loads: order word, then the rectangle of that Gaussian ---------------------------------
+    uint32_t g[SCAN_ITEMS];
+    ushort4 rc[SCAN_ITEMS];
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        const int64_t e = tile_base + i * SCAN_THREADS + threadIdx.x;
+        g[i] = e < n ? (uint32_t)__ldg(order + e) : 0xffffffffu;
+    }
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i)
+        rc[i] = g[i] != 0xffffffffu ? __ldg(rect + g[i]) : make_ushort4(0, 0, 0, 0);
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        const int idx = i * SCAN_THREADS + threadIdx.x;
+        s_x[idx + (idx >> 5)] = (uint32_t)((rc[i].z - rc[i].x) * (rc[i].w - rc[i].y));
+    }
+    __syncthreads();
+    // ---- blocked scan (as scan_lookback_kernel) --------------------------------------------------------------
+    uint32_t v[SCAN_ITEMS];
+    uint32_t tsum = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        const int idx = threadIdx.x * SCAN_ITEMS + i;
+        tsum += s_x[idx + (idx >> 5)];
+        v[i] = tsum;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t warp_off = 0, block_total = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+        const uint32_t t = s_warp[w];
+        if (w < warp) warp_off += t;
+        block_total += t;
+    }
+    if (warp == 0) {
+        uint32_t excl = 0;
+        if (tile == 0) {
+            if (lane == 0) st_volatile_u64(desc + 0, FLAG_INC | block_total);
+        } else {
+            if (lane == 0) st_volatile_u64(desc + tile, FLAG_AGG | block_total);
+            int64_t look = (int64_t)tile - 1;
+            while (true) {
+                const int64_t idx = look - lane;
+                uint64_t d = FLAG_INC;
+                if (idx >= 0) {
+                    do {
+                        d = ld_volatile_u64(desc + idx);
+                    } while ((d >> 32) == 0);
+                }
+                const uint32_t inc_mask = __ballot_sync(0xffffffffu, (d >> 32) == 2);
+                uint32_t val = (uint32_t)d;
+                if (inc_mask) {
+                    const int first = __ffs(inc_mask) - 1;
+                    if (lane > first) val = 0;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+                excl += val;
+                if (inc_mask) break;
+                look -= 32;
+            }
+            if (lane == 0) st_volatile_u64(desc + tile, FLAG_INC | (uint64_t)(excl + block_total));
+        }
+        if (lane == 0) s_excl = excl;
+    }
+    __syncthreads();
+    const uint32_t off = s_excl + warp_off + (inc - tsum);
+    // ---- inclusive offsets back to the striped arrangement: point_offsets (coalesced) and the emission ------
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        const int idx = threadIdx.x * SCAN_ITEMS + i;
+        s_x[idx + (idx >> 5)] = v[i] + off;
+    }
+    __syncthreads();
+    uint32_t* __restrict__ out = vt.point_offsets;
+    uint64_t* __restrict__ words = vt.keys[0];
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        const int idx = i * SCAN_THREADS + threadIdx.x;
+        const uint32_t incl = s_x[idx + (idx >> 5)];
+        if (tile_base + idx < n) out[tile_base + idx] = incl;
+        const int x0 = rc[i].x, y0 = rc[i].y, x1 = rc[i].z, y1 = rc[i].w;
+        const uint32_t ntiles = (uint32_t)((x1 - x0) * (y1 - y0));
+        if (ntiles == 0) continue;
+        if (incl > tab.capacity) {                       // pairs beyond the binning capacity are dropped and flagged
+            atomicOr(vt.status + STATUS_OVERFLOW, 1u);
+            continue;
+        }
+        uint32_t o = incl - ntiles;
+        for (int ty = y0; ty < y1; ++ty) {
+            for (int tx = x0; tx < x1; ++tx) {
+                const uint32_t t = (uint32_t)(ty * gx + tx);
+                words[o++] = ((uint64_t)t << 32) | (uint64_t)g[i];
+                atomicAdd(&s_cnt[t], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- flush: per-tile counts (and the digit histograms of the 8-bit passes, derived from them) -----------
+    for (int t = threadIdx.x; t < T; t += SCAN_THREADS) {
+        const uint32_t c = s_cnt[t];
+        if (c) {
+            atomicAdd(&vt.tile_count[t], c);
+            for (int p = 0; p < passes; ++p) {
+                const int bits = min(8, end_bit - 8 * p);
+                atomicAdd(&s_hist[p * 256 + (((uint32_t)t >> (8 * p)) & ((1u << bits) - 1u))], c);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * 256; i += SCAN_THREADS) {
+        const uint32_t c = s_hist[i];
+        if (c) atomicAdd(&vt.hist[i], c);
+    }
+}
+
+// true: the fused kernel covers this configuration (the tile histogram fits in shared memory)
+bool scan_duplicate_supported(const BatchTab& tab) {
+    static const bool on = [] {
+        const char* e = getenv("B200SPLAT_FUSED_SCAN_DUP");
+        return !(e && e[0] == '0');
+    }();
+    return on && tab.grid_x * tab.grid_y <= SD_MAX_TILES;
+}
+
+cudaError_t launch_scan_duplicate(const BatchTab& tab, cudaStream_t st) {
+    const int64_t n = tab.P;
+    if (n <= 0) return cudaSuccess;
+    const int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    const int T = tab.grid_x * tab.grid_y;
+    const size_t smem = ((size_t)SCAN_TILE + SCAN_TILE / 32 + (size_t)tab.digit_passes * 256 + T) * sizeof(uint32_t);
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(scan_duplicate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr = smem;
+    }
+    scan_duplicate_kernel<<<dim3((unsigned)tiles, tab.V), SCAN_THREADS, smem, st>>>(tab);
+    count_launch();
+    return cudaGetLastError();
+}
+
 size_t scan_workspace_bytes(int64_t n) {
     int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     return align_up(16 + (size_t)tiles * 8, 256);
@@ -1093,27 +1275,42 @@ constexpr int ORDER_BUCKETS = 2048;
 __global__ void __launch_bounds__(1024)
 tile_order_kernel(const __grid_constant__ BatchTab tab, int n) {
     __shared__ uint32_t s_cnt[ORDER_BUCKETS];
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_empty;      // cursor of the empty tiles (they all go to the end of the order)
     const int T = tab.grid_x * tab.grid_y;
     for (int i = threadIdx.x; i < ORDER_BUCKETS; i += blockDim.x) s_cnt[i] = 0;
+    if (threadIdx.x == 0) s_empty = 0;
     __syncthreads();
-    auto bucket_of = [&](int i) {
+    auto bucket_of = [&](int i) -> uint32_t {   // 0xffffffff: empty tile
         const uint32_t* r = tab.v[i / T].ranges + 2 * (i % T);
         const uint32_t len = r[1] - r[0];
+        if (len == 0u) return 0xffffffffu;
         // descending: longest lists get the smallest bucket index
-        const uint32_t k = len ? min((uint32_t)(ORDER_BUCKETS - 1), __float_as_uint((float)len) >> 20) : 0u;
-        return (ORDER_BUCKETS - 1) - k;
+        return (ORDER_BUCKETS - 1) - min((uint32_t)(ORDER_BUCKETS - 2), __float_as_uint((float)len) >> 20);
     };
-    // warp-aggregated shared atomics: most tiles of a sparse image are empty and share one bucket
+    // Most tiles of a sparse image are empty: they are counted per warp (one shared atomic per warp), the others
+    // with one plain shared atomic each (their buckets are spread).  4 independent loads in flight per thread: a
+    // single CTA is latency-bound.
+    constexpr int UN = 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_round = (n + 31) / 32 * 32;
-    for (int i = threadIdx.x; i < n_round; i += blockDim.x) {
-        const uint32_t b = i < n ? bucket_of(i) : 0xffffffffu;
-        const uint32_t peers = __match_any_sync(0xffffffffu, b);
-        if (i < n && lane == __ffs(peers) - 1) atomicAdd(&s_cnt[b], (uint32_t)__popc(peers));
+    const int n_round = (n + UN * 1024 - 1) / (UN * 1024) * (UN * 1024);   // whole warps take part in the votes
+    uint32_t empties = 0;
+    for (int i0 = threadIdx.x; i0 < n_round; i0 += UN * blockDim.x) {
+        uint32_t b[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int i = i0 + u * blockDim.x;
+            b[u] = i < n ? bucket_of(i) : 0xfffffffeu;   // 0xfffffffe: beyond the end
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            if (b[u] < ORDER_BUCKETS) atomicAdd(&s_cnt[b[u]], 1u);
+            empties += __popc(__ballot_sync(0xffffffffu, b[u] == 0xffffffffu));
+        }
     }
+    if (lane == 0 && empties) atomicAdd(&s_empty, empties);
     __syncthreads();
     // exclusive scan of the bucket counts (2 buckets per thread)
-    __shared__ uint32_t s_warp[32];
     const uint32_t c0 = s_cnt[2 * threadIdx.x], c1 = s_cnt[2 * threadIdx.x + 1];
     uint32_t inc = c0 + c1;
 #pragma unroll
@@ -1129,15 +1326,28 @@ tile_order_kernel(const __grid_constant__ BatchTab tab, int n) {
     __syncthreads();
     s_cnt[2 * threadIdx.x] = excl;
     s_cnt[2 * threadIdx.x + 1] = excl + c0;
+    if (threadIdx.x == 0) s_empty = (uint32_t)n - s_empty;   // the empty tiles start behind all the others
     __syncthreads();
-    for (int i = threadIdx.x; i < n_round; i += blockDim.x) {
-        const uint32_t b = i < n ? bucket_of(i) : 0xffffffffu;
-        const uint32_t peers = __match_any_sync(0xffffffffu, b);
-        const int leader = __ffs(peers) - 1;
-        uint32_t base = 0;
-        if (i < n && lane == leader) base = atomicAdd(&s_cnt[b], (uint32_t)__popc(peers));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (i < n) tab.tile_order[base + __popc(peers & ((1u << lane) - 1u))] = (uint32_t)i;
+    for (int i0 = threadIdx.x; i0 < n_round; i0 += UN * blockDim.x) {
+        uint32_t b[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int i = i0 + u * blockDim.x;
+            b[u] = i < n ? bucket_of(i) : 0xfffffffeu;
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (b[u] < ORDER_BUCKETS) tab.tile_order[atomicAdd(&s_cnt[b[u]], 1u)] = (uint32_t)i;
+            const uint32_t em = __ballot_sync(0xffffffffu, b[u] == 0xffffffffu);
+            if (em) {
+                uint32_t base = 0;
+                const int leader = __ffs(em) - 1;
+                if (lane == leader) base = atomicAdd(&s_empty, (uint32_t)__popc(em));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (b[u] == 0xffffffffu) tab.tile_order[base + __popc(em & ((1u << lane) - 1u))] = (uint32_t)i;
+            }
+        }
     }
 }
 
