@@ -158,12 +158,16 @@ def test_intermediates_bit_exact(P, H, W):
     assert torch.equal(radii.cpu(), pre["radii"])
     assert torch.equal(v["tiles_touched"], pre["tiles_touched"])
     vis = pre["visible"]
-    # the Gaussians are depth-sorted first (stable; culled ones last) and the offsets are the scan in THAT order
+    # the Gaussians are depth-sorted first (stable: ties keep index order) and the offsets are the scan in THAT order.
+    # Culled Gaussians emit nothing, so the sort is free to leave them anywhere (it sorts key - min on 24 bits when the
+    # depth range allows); the VISIBLE ones must come in exactly the oracle's (depth bits, index) order.
     dbits = pre["depth"].contiguous().view(torch.int32).long() & 0xFFFFFFFF
-    dbits = torch.where(vis, dbits, torch.full_like(dbits, 0xFFFFFFFF))
-    order = torch.sort(dbits, stable=True).indices
-    assert torch.equal(v["gaussian_order"] & 0xFFFFFFFF, order)
-    assert torch.equal(v["point_offsets"].long(), torch.cumsum(pre["tiles_touched"].long()[order], 0))
+    order_cuda = (v["gaussian_order"] & 0xFFFFFFFF).long()
+    assert torch.equal(torch.sort(order_cuda).values, torch.arange(P)), "the depth order must be a permutation"
+    vis_idx = vis.nonzero().reshape(-1)
+    want_vis = vis_idx[torch.sort(dbits[vis_idx], stable=True).indices]
+    assert torch.equal(order_cuda[vis[order_cuda]], want_vis)
+    assert torch.equal(v["point_offsets"].long(), torch.cumsum(pre["tiles_touched"].long()[order_cuda], 0))
     assert int(v["point_offsets"][-1]) == int(binned["point_offsets"][-1])
     assert torch.equal(v["depths"][vis].view(torch.int32), pre["depth"][vis].contiguous().view(torch.int32))
     assert torch.equal(v["keys_sorted"], binned["keys_sorted"])
