@@ -267,9 +267,13 @@ def test_cuda_matches_committed_golden_vectors():
     from pathlib import Path
     import numpy as np
     from b200splat import ops
-    gold = np.load(Path(__file__).parent / "golden" / "config1_oracle.npz")
-    scene, cams = scenes.make_workload("config1_16k_128_sh0", views=1)
-    cam = cams[0]
+    import importlib.util
+    gdir = Path(__file__).parent / "golden"
+    gold = np.load(gdir / "config1_oracle.npz")
+    spec_ = importlib.util.spec_from_file_location("make_golden", gdir / "make_golden.py")
+    mg = importlib.util.module_from_spec(spec_)
+    spec_.loader.exec_module(mg)
+    scene, cam, pix_grads = mg.load_inputs(gold)     # the fixture's own inputs: no host-dependent regeneration
     s = oracle_settings(cam, 0)
     camc = ops.make_cam(cuda_settings(s), "cuda")
     d = lambda t: t.cuda().contiguous()
@@ -288,7 +292,7 @@ def test_cuda_matches_committed_golden_vectors():
                   depth=torch.from_numpy(gold["bound_depth"]), alpha=torch.from_numpy(gold["bound_alpha"]))
     ref = {k: torch.from_numpy(gold[k]) for k in ("color", "depth", "alpha", "n_contrib")}
     check_images(dict(color=color, depth=depth, alpha=alpha, n_contrib=v["n_contrib"]), ref, bounds, IMG_TOL)
-    gc, gd, ga = (g.cuda() for g in scenes.pixel_grads(cam.image_height, cam.image_width, 2024))
+    gc, gd, ga = (g.cuda() for g in pix_grads)
     g = ops.backward(camc, st, m3, sh, None, op, scl, rot, None, radii, alpha, gc, gd, ga)
     for k, gk in (("means3D", "g_means3D"), ("means2D", "g_means2D"), ("shs", "g_shs"), ("opacities", "g_opacities"),
                   ("scales", "g_scales"), ("rotations", "g_rotations")):
