@@ -659,7 +659,9 @@ def main():
 
     from b200splat.batched import ViewBatchRasterizer
     vbr = ViewBatchRasterizer(V, P, H, W, dev)
-    copy_stream = torch.cuda.Stream(device=dev)
+    copy_stream = torch.cuda.Stream(device=dev)      # device -> host (images, loss)
+    upload_stream = torch.cuda.Stream(device=dev)    # host -> device: never waits for the main stream, so the pixel
+    #                                                  gradients of step k+1 cross PCIe while step k's backward runs
 
     # host side of the batched step: ONE pinned block per kind of input, so a step costs two uploads
     cam_block = pin(torch.stack([torch.cat([c.viewmatrix.reshape(-1), c.projmatrix.reshape(-1),
@@ -668,8 +670,8 @@ def main():
 
     def e2e_step_batched():
         """Public batched operator (ViewBatchRasterizer + autograd).  Host inputs of the step (cameras, bg,
-        upstream pixel gradients) come from pinned memory; the pixel-gradient upload runs on a copy stream
-        while the forward renders; images and the loss are read back."""
+        upstream pixel gradients) come from pinned memory; the pixel-gradient upload runs on its own stream
+        (under the previous step's backward and this step's forward); images and the loss are read back."""
         for p in params:
             p.grad = None
         main = torch.cuda.current_stream()
@@ -677,12 +679,12 @@ def main():
         rss = [GaussianRasterizationSettings(H, W, cams_host[v].tanfovx, cams_host[v].tanfovy, cb[v, 35:38], 1.0,
                                              cb[v, 0:16].view(4, 4), cb[v, 16:32].view(4, 4), scene.sh_degree,
                                              cb[v, 32:35], False, False) for v in range(V)]
-        with torch.cuda.stream(copy_stream):
+        with torch.cuda.stream(upload_stream):
             pgd = pg_block.to(dev, non_blocking=True)
         m2 = torch.zeros(V, P, 3, device=dev, requires_grad=True)
         C, R, D, A = vbr(rss, means3D=params[0], means2D=m2, opacities=params[2], shs=params[1], scales=params[3],
                          rotations=params[4])
-        main.wait_stream(copy_stream)
+        main.wait_stream(upload_stream)
         pgd.record_stream(main)
         loss = (C * pgd[:, 0:3]).sum() + (D * pgd[:, 3:4]).sum() + (A * pgd[:, 4:5]).sum()
         copy_stream.wait_stream(main)            # images leave over PCIe while the backward runs

@@ -104,6 +104,8 @@ size_t image_layout(int H, int W, void* base, ImageViews* v) {
     im.tile_count = carve<uint32_t>(p, (size_t)gx * gy);
     im.block_last = carve<uint32_t>(p, (size_t)gx * gy * (BLOCK_SIZE / 32));
     im.block_order = carve<uint32_t>(p, 4 + (size_t)gx * gy * (BLOCK_SIZE / 32) * MAX_VIEWS);
+    im.block_hist = carve<uint32_t>(p, ORDER_BUCKETS);
+    im.block_code = carve<uint32_t>(p, (size_t)gx * gy * (BLOCK_SIZE / 32) * MAX_VIEWS);
     if (v) *v = im;
     return (size_t)(p - p0);
 }
@@ -195,15 +197,17 @@ static void fill_geom(int P, void* geom, ViewTab* vt, const float4** ext4 = null
     vt->scan_desc = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(g.scan_ws) + 16);
 }
 
-static void fill_image(int H, int W, void* image, ViewTab* vt, uint32_t** tile_order, uint32_t** block_order = nullptr) {
+static void fill_image(int H, int W, void* image, ViewTab* vt, BatchTab* batch) {   // batch: takes the per-batch areas
     ImageViews im;
     image_layout(H, W, image, &im);
     vt->ranges = im.ranges, vt->n_contrib = im.n_contrib, vt->n_visited = im.n_visited, vt->final_T = im.final_T;
     vt->status = im.status;
     vt->tile_count = im.tile_count;
     vt->block_last = im.block_last;
-    if (tile_order) *tile_order = im.tile_order;
-    if (block_order) *block_order = im.block_order;
+    if (batch) {
+        batch->tile_order = im.tile_order, batch->block_order = im.block_order;
+        batch->block_hist = im.block_hist, batch->block_code = im.block_code;
+    }
 }
 
 static void fill_binning(int64_t capacity, void* binning, ViewTab* vt) {
@@ -256,6 +260,42 @@ struct ProfScope {
         g_prof.push_back(r);
     }
 };
+
+// A second stream + two events per (host thread, device): lets a forward put kernels that do not depend on each other
+// on parallel branches (fork: side waits for an event recorded on the caller's stream; join: the caller's stream waits
+// for an event recorded on side).  Works the same under stream capture (the branch becomes a parallel path of the graph).
+struct SideLane {
+    cudaStream_t s = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static SideLane* side_lane() {
+    static const bool enabled = [] {
+        const char* e = getenv("B200SPLAT_FORK");
+        return !(e && e[0] == '0');
+    }();
+    if (!enabled) return nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        if (g_prof_on) return nullptr;      // per-family event timing wants the families back to back on one stream
+    }
+    constexpr int MAX_DEV = 32;
+    static thread_local SideLane lanes[MAX_DEV];
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return nullptr;
+    SideLane& l = lanes[dev];
+    if (!l.s) {
+        cudaStream_t s = nullptr;
+        cudaEvent_t a = nullptr, b = nullptr;
+        if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&a, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&b, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        l.s = s, l.fork = a, l.join = b;
+    }
+    return &l;
+}
 
 struct PinnedSlot {
     int64_t* host = nullptr;
@@ -310,12 +350,28 @@ static int forward_tail(BatchTab& tab, int debug, cudaStream_t st, bool binning_
             CU(launch_duplicate(tab, st));
         }
         DEBUG_SYNC(dbg, st, "duplicateWithKeys");
+    }
+    // The tile ranges (exclusive scan of duplicateWithKeys' per-tile counts) and the tile order of the render do not
+    // depend on the sorted pair words: they run on a parallel branch next to the pair partition (12 us per step off
+    // the critical path).  Above 8192 tiles the ranges are read off the sorted words and the branch is not taken.
+    SideLane* lane = (tab.P > 0 && tab.capacity > 0 && T <= 8192 && !debug) ? side_lane() : nullptr;
+    if (lane) {
+        CU(cudaEventRecord(lane->fork, st));
+        CU(cudaStreamWaitEvent(lane->s, lane->fork, 0));
+        CU(launch_tile_ranges_batch(tab, sel, lane->s));
+        CU(cudaEventRecord(lane->join, lane->s));
+    }
+    if (tab.P > 0 && tab.capacity > 0) {
         { ProfScope ps(3, st);
         CU(launch_sort_batch(tab, st)); }
         DEBUG_SYNC(dbg, st, "sort");
     }
-    { ProfScope ps(4, st);
-    CU(launch_tile_ranges_batch(tab, sel, st)); }
+    if (lane) {
+        CU(cudaStreamWaitEvent(st, lane->join, 0));
+    } else {
+        ProfScope ps(4, st);
+        CU(launch_tile_ranges_batch(tab, sel, st));
+    }
     DEBUG_SYNC(dbg, st, "identifyTileRanges");
     { ProfScope ps(5, st);
     CU(launch_render_forward(tab, sel, st)); }
@@ -463,7 +519,7 @@ int b200splat_forward(const b200splat_forward_args* a) {
     if (rc) return rc;
     if (!a->image_buffer || a->image_bytes < image_layout(tab.H, tab.W, nullptr, nullptr))
         return fail(B200SPLAT_ERR_NOMEM, "image_buffer too small");
-    fill_image(tab.H, tab.W, a->image_buffer, &vt, &tab.tile_order, &tab.block_order);
+    fill_image(tab.H, tab.W, a->image_buffer, &vt, &tab);
     vt.out_color = a->out_color, vt.out_depth = a->out_depth, vt.out_alpha = a->out_alpha;
     vt.radii = a->radii;
     rc = check_extra(a->n_extra, a->extra_features, a->out_extra != nullptr);
@@ -554,8 +610,7 @@ int b200splat_forward_batched(const b200splat_batch_forward_args* a) {
             return fail(B200SPLAT_ERR_INVALID, "null buffer for view %d", v);
         vt.out_extra = tab.n_extra > 0 ? a->out_extra[v] : nullptr;
         fill_geom(P, a->geom_buffer[v], &vt, v == 0 ? &tab.ext4 : nullptr);
-        fill_image(tab.H, tab.W, a->image_buffer[v], &vt, v == 0 ? &tab.tile_order : nullptr,
-                   v == 0 ? &tab.block_order : nullptr);
+        fill_image(tab.H, tab.W, a->image_buffer[v], &vt, v == 0 ? &tab : nullptr);
         fill_binning(cap, a->binning_buffer[v], &vt);
         vt.out_color = a->out_color[v], vt.out_depth = a->out_depth[v], vt.out_alpha = a->out_alpha[v];
         vt.radii = a->radii[v];
@@ -664,7 +719,7 @@ int b200splat_backward(const b200splat_backward_args* a) {
     if (rc) return rc;
     tab.n_extra = a->n_extra;
     fill_geom(P, const_cast<void*>(a->geom_buffer), &vt, &tab.ext4);
-    fill_image(tab.H, tab.W, const_cast<void*>(a->image_buffer), &vt, &tab.tile_order, &tab.block_order);
+    fill_image(tab.H, tab.W, const_cast<void*>(a->image_buffer), &vt, &tab);
     vt.radii = const_cast<int32_t*>(a->radii);
     if (a->num_rendered > 0) {
         if (!a->binning_buffer) return fail(B200SPLAT_ERR_INVALID, "null binning buffer");
@@ -715,8 +770,7 @@ int b200splat_backward_batched(const b200splat_batch_backward_args* a) {
         fill_geom(P, const_cast<void*>(a->geom_buffer[v]), &vt, v == 0 ? &tab.ext4 : nullptr);
         vt.gradext = reinterpret_cast<float*>(reinterpret_cast<char*>(a->scratch[v]) + grad2d_bytes(P));
         vt.dL_dextra = (tab.n_extra > 0 && a->dL_dout_extra) ? a->dL_dout_extra[v] : nullptr;
-        fill_image(tab.H, tab.W, const_cast<void*>(a->image_buffer[v]), &vt, v == 0 ? &tab.tile_order : nullptr,
-                   v == 0 ? &tab.block_order : nullptr);
+        fill_image(tab.H, tab.W, const_cast<void*>(a->image_buffer[v]), &vt, v == 0 ? &tab : nullptr);
         fill_binning(cap, const_cast<void*>(a->binning_buffer[v]), &vt);
         vt.radii = const_cast<int32_t*>(a->radii[v]);
         vt.dL_dcolor = a->dL_dout_color ? a->dL_dout_color[v] : nullptr;

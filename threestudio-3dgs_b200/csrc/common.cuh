@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 namespace b200splat {
 
@@ -44,7 +45,22 @@ constexpr int MAX_PASSES = 8;
 
 // status words of a view (in its image buffer)
 constexpr int STATUS_OVERFLOW = 0;   // != 0: num_rendered exceeded the binning capacity (results invalid)
-constexpr int STATUS_WORDS = 4;      // [1], [2]: pair-count sum / ticket of pair_count_kernel (scan_sort.cu)
+constexpr int STATUS_WORDS = 4;
+// buckets of the longest-first work orders (tile order of render forward, block order of render backward): a monotone
+// 11-bit key of the list length (float exponent + 3 mantissa bits: 8 buckets per octave)
+constexpr int ORDER_BUCKETS = 2048;
+constexpr uint32_t BLOCK_CODE_NONE = 0xffffffffu;
+__host__ __device__ __forceinline__ uint32_t order_bucket(uint32_t len) {   // descending: longest -> smallest bucket index
+#ifdef __CUDA_ARCH__
+    const uint32_t k = __float_as_uint((float)len) >> 20;
+#else
+    const float f = (float)len;
+    uint32_t k;
+    memcpy(&k, &f, 4);
+    k >>= 20;
+#endif
+    return (uint32_t)(ORDER_BUCKETS - 1) - (k < (uint32_t)(ORDER_BUCKETS - 1) ? k : (uint32_t)(ORDER_BUCKETS - 1));
+}      // [1], [2]: pair-count sum / ticket of pair_count_kernel (scan_sort.cu)
 
 struct ViewTab {
     // camera (device pointers to the reference's transposed 4x4s) + host-derived fp32 scalars
@@ -112,8 +128,11 @@ struct BatchTab {
     int n_extra;               // 0..4 extra per-Gaussian feature channels rendered next to the colour
     const float4* ext4;        // [P] the extra features padded to 16 B (view independent; lives in view 0's geometry)
     uint32_t* tile_order;      // [V * T] entries (view * T + tile), longest list first
-    uint32_t* block_order;     // [1 + V * T * 8]: count, then the batch's non-empty 8x4 blocks ((view * T + tile) * 8 + block),
+    uint32_t* block_order;     // [4 + V * T * 8]: count, then the batch's non-empty 8x4 blocks ((view * T + tile) * 8 + block),
                                // most list entries to walk first: the work items of render backward
+    uint32_t* block_hist;      // [ORDER_BUCKETS] blocks per walk-length bucket: zeroed by tile_order_kernel, counted by
+                               // render forward (one atomic per warp, whose return value is the block's rank in its bucket)
+    uint32_t* block_code;      // [V * T * 8] bucket << 20 | rank of every block (0xffffffff: nothing to walk)
     ViewTab v[MAX_VIEWS];
 };
 
@@ -145,6 +164,8 @@ struct ImageViews {
     uint32_t* tile_order;    // MAX_VIEWS * T (a batch uses view 0's copy)
     uint32_t* block_last;    // T * 8
     uint32_t* block_order;   // 4 + MAX_VIEWS * T * 8 (a batch uses view 0's copy)
+    uint32_t* block_hist;    // ORDER_BUCKETS (view 0's copy)
+    uint32_t* block_code;    // MAX_VIEWS * T * 8 (view 0's copy)
     uint32_t* status;        // STATUS_WORDS
     uint32_t* tile_count;    // T
 };

@@ -95,7 +95,7 @@ __device__ __forceinline__ void sh_chunk_view(const float sv[12], float x, float
 template <int C, int K, bool ACC, bool VEC>
 __device__ __forceinline__ void sh_chunk_all_views(const float* __restrict__ sh, const float4* sh_row,
                                                    float* __restrict__ dst, int M, int V, uint32_t vis,
-                                                   float4* s_slots /* [V][128][3] */) {
+                                                   float4* s_slots /* [V][128][3] */, int col) {
     if (4 * C >= K) return;
     float sv[12];
     if (VEC) {
@@ -120,7 +120,7 @@ __device__ __forceinline__ void sh_chunk_all_views(const float* __restrict__ sh,
     for (int t = 0; t < 12; ++t) acc[t] = 0.f;
     for (int v = 0; v < V; ++v) {
         if (!((vis >> v) & 1u)) continue;
-        float4* r = s_slots + ((size_t)v * 128 + threadIdx.x) * 3;
+        float4* r = s_slots + ((size_t)v * 128 + col) * 3;
         const float4 ra = r[0], rb = r[1];
         float4 rc = r[2];
         const float g[3] = {ra.x, ra.y, ra.z};
@@ -155,6 +155,98 @@ __device__ __forceinline__ void put(float* p, float v) {
     if (ACC) *p += v; else *p = v;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Scan kernel: one thread per Gaussian, streaming, full occupancy.  Which views saw the Gaussian (radii > 0), and in
+// which of those did render backward leave a gradient at all?  Most pairs of a dense scene sit behind the saturation
+// point of their pixels: the Gaussian is visible, its 48-byte gradient record is all zeros, and every term it would
+// add to the parameter gradients is an exact zero.  Such a view is dropped here.  A Gaussian without any gradient
+// only gets its zero outputs and its statistics written -- no parameters, no SH row, no arithmetic; the others are
+// appended (index, live views, clamp bits) to the work list of preprocess_backward_kernel, whose warps are then full
+// of Gaussians that do have work.  (In the headline scene ~1/6 of the Gaussians of a 4-view step carry a gradient.)
+//   * zero outputs of EVERY Gaussian of the range are written here, warp-cooperatively for the SH block (the 32
+//     Gaussians of a warp own 32 x 12 M contiguous bytes: full-line stores); the worker overwrites its Gaussians;
+//   * densification statistics that need no gradient (visibility count, largest radius) are applied here.
+// ---------------------------------------------------------------------------------------------------------------
+template <bool ACC>
+__global__ void __launch_bounds__(256)
+preprocess_backward_scan_kernel(const __grid_constant__ BatchTab tab, float* __restrict__ dL_dmeans3D,
+                                float* __restrict__ dL_dshs, float* __restrict__ dL_dcolors,
+                                float* __restrict__ dL_dopacity, float* __restrict__ dL_dscales,
+                                float* __restrict__ dL_drotations, float* __restrict__ dL_dcov3D,
+                                float* __restrict__ stat_denom, float* __restrict__ stat_max_radii, int has_clamp,
+                                int sh_vec, uint2* __restrict__ live_list, uint32_t* __restrict__ live_count,
+                                int g_begin, int g_end) {
+    const int V = tab.V, M = tab.M;
+    const int lane = threadIdx.x & 31;
+    const int warp_first = g_begin + (int)(blockIdx.x * blockDim.x + (threadIdx.x & ~31u));
+    const int idx = warp_first + lane;
+    const bool in_range = idx < g_end;
+    uint32_t vis = 0, live = 0, clamp3 = 0;
+    if (in_range) {
+        int max_radius = 0;
+        int rad[MAX_VIEWS];
+#pragma unroll
+        for (int v = 0; v < MAX_VIEWS; ++v) rad[v] = v < V ? tab.v[v].radii[idx] : 0;
+#pragma unroll
+        for (int v = 0; v < MAX_VIEWS; ++v) {
+            if (rad[v] > 0) vis |= 1u << v;
+            max_radius = max(max_radius, rad[v]);
+        }
+        // all visible views' records in flight together
+        uint4 rec[MAX_VIEWS][3];
+#pragma unroll
+        for (int v = 0; v < MAX_VIEWS; ++v) {
+            if ((vis >> v) & 1u) {
+                const uint4* gp = reinterpret_cast<const uint4*>(tab.v[v].grad2d) + 3 * (size_t)idx;
+                rec[v][0] = gp[0], rec[v][1] = gp[1], rec[v][2] = gp[2];
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < MAX_VIEWS; ++v) {
+            if ((vis >> v) & 1u) {
+                const uint4 a = rec[v][0], b = rec[v][1], c = rec[v][2];
+                if (a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w | c.x | c.y) live |= 1u << v;
+            }
+        }
+        if (has_clamp)
+            for (int v = 0; v < V; ++v)
+                if ((live >> v) & 1u) clamp3 |= ((uint32_t)tab.v[v].clamped[idx] & 7u) << (3 * v);
+        if (stat_denom && vis) stat_denom[idx] += (float)__popc(vis);
+        if (stat_max_radii && vis) stat_max_radii[idx] = fmaxf(stat_max_radii[idx], (float)max_radius);
+        if (!ACC) {
+            for (int v = 0; v < V; ++v) {      // views without a gradient: dL/dmeans2D = 0
+                float* m2 = tab.v[v].dL_dmeans2D;
+                if (m2 && !((live >> v) & 1u)) m2[3 * idx] = m2[3 * idx + 1] = m2[3 * idx + 2] = 0.f;
+            }
+            if (live == 0) {
+                dL_dmeans3D[3 * idx] = dL_dmeans3D[3 * idx + 1] = dL_dmeans3D[3 * idx + 2] = 0.f;
+                dL_dopacity[idx] = 0.f;
+                if (dL_dshs && !sh_vec) for (int k = 0; k < 3 * M; ++k) dL_dshs[(size_t)idx * 3 * M + k] = 0.f;
+                if (dL_dcolors) dL_dcolors[3 * idx] = dL_dcolors[3 * idx + 1] = dL_dcolors[3 * idx + 2] = 0.f;
+                if (dL_dscales) dL_dscales[3 * idx] = dL_dscales[3 * idx + 1] = dL_dscales[3 * idx + 2] = 0.f;
+                if (dL_drotations) reinterpret_cast<float4*>(dL_drotations)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (dL_dcov3D) for (int k = 0; k < 6; ++k) dL_dcov3D[(size_t)idx * 6 + k] = 0.f;
+            }
+        }
+    }
+    // the SH gradients of the warp's Gaussians: one contiguous block, zeroed with full-width vector stores (the worker
+    // overwrites the rows of the Gaussians that have a gradient; it runs after this kernel)
+    if (!ACC && dL_dshs && sh_vec && warp_first < g_end) {
+        const int rows = min(32, g_end - warp_first);
+        float4* d4 = reinterpret_cast<float4*>(dL_dshs + (size_t)warp_first * 3 * M);
+        const int n4 = rows * (3 * M / 4);
+        for (int k = lane; k < n4; k += 32) d4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // append the Gaussians that have work (one atomic per warp)
+    const uint32_t m = __ballot_sync(0xffffffffu, live != 0);
+    if (m) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(live_count, (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (live) live_list[base + __popc(m & ((1u << lane) - 1u))] = make_uint2((uint32_t)idx, live | (clamp3 << 8));
+    }
+}
+
 // DEG = -1: colours precomputed
 template <int DEG, bool ACC, bool VEC>
 __global__ void __launch_bounds__(128)
@@ -165,13 +257,13 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
                            float* __restrict__ dL_dcolors, float* __restrict__ dL_dopacity,
                            float* __restrict__ dL_dscales, float* __restrict__ dL_drotations,
                            float* __restrict__ dL_dcov3D, float* __restrict__ stat_grad_accum,
-                           float* __restrict__ stat_denom, float* __restrict__ stat_max_radii, int g_begin,
-                           int g_end) {
+                           const uint2* __restrict__ live_list, const uint32_t* __restrict__ live_count) {
     __shared__ float sV[MAX_VIEWS][16], sP[MAX_VIEWS][16], sC[MAX_VIEWS][4], sS[MAX_VIEWS][4];
     // dynamic shared memory: one 48-byte slot per (view, thread) -- first the landing zone of the view's gradient
     // record (cp.async), then the SH phase's per-view state -- and, on the vector path, the thread's SH row
     // (row stride 13 float4: LDS.128 of neighbouring threads fall in different bank groups)
     extern __shared__ float4 s_dyn4[];
+    if (blockIdx.x * blockDim.x >= *live_count) return;   // launched over the whole range: most CTAs stop here
     float4* s_slots = s_dyn4;   // [V][128][3]
     const int V = tab.V;
     float4* sh_row = (VEC && DEG >= 0) ? s_dyn4 + (size_t)V * 128 * 3 + threadIdx.x * SH_ROW_F4 : nullptr;
@@ -186,57 +278,30 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
         sS[i >> 2][i & 3] = t.scalars ? t.scalars[i & 3] : host[i & 3];
     }
     __syncthreads();
-    const int idx = g_begin + blockIdx.x * blockDim.x + threadIdx.x;   // this launch covers [g_begin, g_end)
-    if (idx >= g_end) return;
     const int M = tab.M;
     constexpr int K = DEG < 0 ? 0 : (DEG + 1) * (DEG + 1);
     constexpr int NCH = (K + 3) / 4;          // live chunks of 4 coefficients
-
-    // every load whose address is known goes out first: radii, clamp bits and the parameters of the Gaussian
-    uint32_t vis = 0, clampbits = 0;
-    int max_radius = 0;
-    for (int v = 0; v < V; ++v) {
-        const int r = tab.v[v].radii[idx];
-        if (DEG >= 0) clampbits |= (uint32_t)tab.v[v].clamped[idx] << (4 * v);
-        if (r > 0) vis |= 1u << v;
-        max_radius = max(max_radius, r);
-    }
-    const float x = means3D[3 * idx], y = means3D[3 * idx + 1], z = means3D[3 * idx + 2];
-    const bool has_sr = (scales != nullptr) && (cov3D_precomp == nullptr);
-    float sc_in[3] = {0.f, 0.f, 0.f};
-    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (has_sr) {
-        sc_in[0] = scales[3 * idx], sc_in[1] = scales[3 * idx + 1], sc_in[2] = scales[3 * idx + 2];
-        q = reinterpret_cast<const float4*>(rotations)[idx];
-    }
-    if (vis == 0) {
-        if (!ACC) {
-            dL_dmeans3D[3 * idx] = dL_dmeans3D[3 * idx + 1] = dL_dmeans3D[3 * idx + 2] = 0.f;
-            dL_dopacity[idx] = 0.f;
-            if (dL_dshs) for (int k = 0; k < 3 * M; ++k) dL_dshs[(size_t)idx * 3 * M + k] = 0.f;
-            if (dL_dcolors) dL_dcolors[3 * idx] = dL_dcolors[3 * idx + 1] = dL_dcolors[3 * idx + 2] = 0.f;
-            if (dL_dscales) dL_dscales[3 * idx] = dL_dscales[3 * idx + 1] = dL_dscales[3 * idx + 2] = 0.f;
-            if (dL_drotations) reinterpret_cast<float4*>(dL_drotations)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (dL_dcov3D) for (int k = 0; k < 6; ++k) dL_dcov3D[(size_t)idx * 6 + k] = 0.f;
-            for (int v = 0; v < V; ++v) {
-                float* m2 = tab.v[v].dL_dmeans2D;
-                if (m2) m2[3 * idx] = m2[3 * idx + 1] = m2[3 * idx + 2] = 0.f;
-            }
-        }
-        return;
-    }
-    // asynchronous copies into the thread's own shared-memory slots: group 0 = the visible views' 48-byte
-    // gradient records, group 1 = the SH row.  They land while Sigma3 / the per-view chains run.
+    // work item: a Gaussian with a gradient in at least one view, from the list preprocess_backward_scan_kernel wrote
+    // (x = index, y = views with a gradient | clamp bits of view v << (8 + 3 v)); launched over the whole range
+    const uint32_t item_no = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item_no >= *live_count) return;
+    const uint2 item = live_list[item_no];
+    const int idx = (int)item.x;
+    const uint32_t vis = item.y & 0xffu;           // from here on "vis" = the views with a gradient
+    const uint32_t clamp3 = item.y >> 8;           // 3 clamp bits per view
+    const int src = threadIdx.x;                   // slot column of this thread
+    // asynchronous copies into the thread's own shared-memory slots: group 0 = the live views' 48-byte gradient
+    // records, group 1 = the SH row.  They land while Sigma3 / the per-view chains run.
     for (int v = 0; v < V; ++v) {
         if ((vis >> v) & 1u) {
             const float4* gp = reinterpret_cast<const float4*>(tab.v[v].grad2d) + 3 * (size_t)idx;
-            float4* slot = s_slots + ((size_t)v * 128 + threadIdx.x) * 3;
+            float4* slot = s_slots + ((size_t)v * 128 + src) * 3;
             cpa16(slot, gp), cpa16(slot + 1, gp + 1), cpa16(slot + 2, gp + 2);
         }
     }
     cpa_commit();
     const float* sh = DEG >= 0 ? shs + (size_t)idx * M * 3 : nullptr;
-    if (DEG >= 0) {
+    if (DEG >= 0) {   // the SH row goes out first (asynchronous, into the thread's own row), then the parameters
         if (VEC) {
             const float4* s4 = reinterpret_cast<const float4*>(sh);
 #pragma unroll
@@ -247,6 +312,14 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
         }
     }
     cpa_commit();
+    const float x = means3D[3 * idx], y = means3D[3 * idx + 1], z = means3D[3 * idx + 2];
+    const bool has_sr = (scales != nullptr) && (cov3D_precomp == nullptr);
+    float sc_in[3] = {0.f, 0.f, 0.f};
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has_sr) {
+        sc_in[0] = scales[3 * idx], sc_in[1] = scales[3 * idx + 1], sc_in[2] = scales[3 * idx + 2];
+        q = reinterpret_cast<const float4*>(rotations)[idx];
+    }
     // Sigma3 (view independent); R and s kept for its backward
     float c0, c1, c2, c3, c4, c5;
     float R[3][3], s[3];
@@ -283,11 +356,11 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
     float dmx = 0.f, dmy = 0.f, dmz = 0.f, dop = 0.f;
     float dS[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float dcol[3] = {0.f, 0.f, 0.f};
-    float st_norm = 0.f, st_cnt = 0.f;
+    float st_norm = 0.f;
 
     cpa_wait<1>();   // the gradient records have landed (each thread reads only what it copied itself)
     if (tab.clean_scratch) {   // self-cleaning scratch: the record is consumed, leave zeros for the next backward
-        for (int v = 0; v < V; ++v) {
+        for (int v = 0; v < V; ++v) {   // (the stores are issued after the loads have completed: DESIGN.md 4b)
             if ((vis >> v) & 1u) {
                 float4* gp = reinterpret_cast<float4*>(tab.v[v].grad2d) + 3 * (size_t)idx;
                 gp[0] = gp[1] = gp[2] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -296,15 +369,10 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
     }
     for (int v = 0; v < V; ++v) {
         const ViewTab& vt = tab.v[v];
-        if (!((vis >> v) & 1u)) {
-            if (!ACC && vt.dL_dmeans2D) {
-                vt.dL_dmeans2D[3 * idx] = vt.dL_dmeans2D[3 * idx + 1] = vt.dL_dmeans2D[3 * idx + 2] = 0.f;
-            }
-            continue;
-        }
+        if (!((vis >> v) & 1u)) continue;   // (its dL/dmeans2D was zeroed by the scan kernel)
         const float* mV = sV[v];
         const float* mP = sP[v];
-        float4* slot = s_slots + ((size_t)v * 128 + threadIdx.x) * 3;
+        float4* slot = s_slots + ((size_t)v * 128 + src) * 3;
         const float4 g0 = slot[0], g1 = slot[1], g2 = slot[2];
         // render backward leaves the two diagonal conic gradients without their factor 1/2 (render.cu K7)
         const float g_px = g0.x, g_py = g0.y, g_ca = 0.5f * g0.z, g_cb = g0.w, g_cc = 0.5f * g1.x, g_op = g1.y;
@@ -385,11 +453,10 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
         }
         // densification statistics of this view (geometry/gaussian_base.py:815-819)
         st_norm += sqrtf(gnx * gnx + gny * gny);
-        st_cnt += 1.0f;
         dop += g_op;
         // ---- colour -----------------------------------------------------------------------------
         if (DEG >= 0) {
-            const uint32_t bits = (clampbits >> (4 * v)) & 7u;
+            const uint32_t bits = (clamp3 >> (3 * v)) & 7u;
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch)
                 if (bits & (1u << ch)) g_rgb[ch] = 0.f;
@@ -408,10 +475,10 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
     if (DEG >= 0) {
         float* dst = dL_dshs + (size_t)idx * M * 3;
         cpa_wait<0>();   // the SH row has landed
-        sh_chunk_all_views<0, K, ACC, VEC>(sh, sh_row, dst, M, V, vis, s_slots);
-        sh_chunk_all_views<1, K, ACC, VEC>(sh, sh_row, dst, M, V, vis, s_slots);
-        sh_chunk_all_views<2, K, ACC, VEC>(sh, sh_row, dst, M, V, vis, s_slots);
-        sh_chunk_all_views<3, K, ACC, VEC>(sh, sh_row, dst, M, V, vis, s_slots);
+        sh_chunk_all_views<0, K, ACC, VEC>(sh, sh_row, dst, M, V, vis, s_slots, src);
+        sh_chunk_all_views<1, K, ACC, VEC>(sh, sh_row, dst, M, V, vis, s_slots, src);
+        sh_chunk_all_views<2, K, ACC, VEC>(sh, sh_row, dst, M, V, vis, s_slots, src);
+        sh_chunk_all_views<3, K, ACC, VEC>(sh, sh_row, dst, M, V, vis, s_slots, src);
         if (!ACC) {   // coefficients above the active degree get zero gradients
             if (VEC) {
                 float4* d4 = reinterpret_cast<float4*>(dst);
@@ -424,7 +491,7 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
         // through dir = d / |d|, per view
         for (int v = 0; v < V; ++v) {
             if (!((vis >> v) & 1u)) continue;
-            const float4* r = s_slots + ((size_t)v * 128 + threadIdx.x) * 3;
+            const float4* r = s_slots + ((size_t)v * 128 + src) * 3;
             const float4 ra = r[0], rb = r[1], rc = r[2];
             const float dx = ra.w, dy = rb.x, dz = rb.y, in = rb.z;
             const float ddx = rc.x, ddy = rc.y, ddz = rc.z;
@@ -485,9 +552,8 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
     put<ACC>(dL_dmeans3D + 3 * idx + 2, dmz);
     put<ACC>(dL_dopacity + idx, dop);
     // fused densification statistics (geometry/gaussian_base.py:815-819, 846-851)
+    // (denominator and largest radius: the scan kernel; a view without a gradient adds a zero norm)
     if (stat_grad_accum) stat_grad_accum[idx] += st_norm;
-    if (stat_denom) stat_denom[idx] += st_cnt;
-    if (stat_max_radii) stat_max_radii[idx] = fmaxf(stat_max_radii[idx], (float)max_radius);
 }
 
 cudaError_t launch_preprocess_backward(const BatchTab& tab, const float* means3D, const float* scales,
@@ -503,6 +569,29 @@ cudaError_t launch_preprocess_backward(const BatchTab& tab, const float* means3D
     const int grid = (g_end - g_begin + 127) / 128;
     const bool vec = tab.sh_degree >= 0 && (tab.M & 3) == 0 && tab.M <= 16 &&
                      ((reinterpret_cast<uintptr_t>(shs) | reinterpret_cast<uintptr_t>(dL_dshs)) & 15) == 0;
+    // work list of the Gaussians that carry a gradient: view 0's second depth-sort buffer (dead after the forward) and
+    // its sort tickets hold the list and its length
+    uint2* live_list = reinterpret_cast<uint2*>(tab.v[0].gwords[1]);
+    uint32_t* live_count = tab.v[0].gtickets;
+    cudaError_t e0 = cudaMemsetAsync(live_count, 0, sizeof(uint32_t), st);
+    if (e0 != cudaSuccess) return e0;
+    {
+        const int sgrid = (g_end - g_begin + 255) / 256;
+        // zero rows of dL_dshs are written warp-wide when a row is a whole number of float4s at a 16-byte aligned base
+        const int sh_vec = (dL_dshs != nullptr && ((3 * tab.M) & 3) == 0 &&
+                            (reinterpret_cast<uintptr_t>(dL_dshs) & 15) == 0) ? 1 : 0;
+        if (accumulate)
+            preprocess_backward_scan_kernel<true><<<sgrid, 256, 0, st>>>(
+                tab, dL_dmeans3D, dL_dshs, dL_dcolors, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D, stat_denom,
+                stat_max_radii, tab.sh_degree >= 0 ? 1 : 0, sh_vec, live_list, live_count, g_begin, g_end);
+        else
+            preprocess_backward_scan_kernel<false><<<sgrid, 256, 0, st>>>(
+                tab, dL_dmeans3D, dL_dshs, dL_dcolors, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D, stat_denom,
+                stat_max_radii, tab.sh_degree >= 0 ? 1 : 0, sh_vec, live_list, live_count, g_begin, g_end);
+        count_launch();
+        e0 = cudaGetLastError();
+        if (e0 != cudaSuccess) return e0;
+    }
     const size_t smem = ((size_t)tab.V * 128 * 3 + (vec ? 128 * SH_ROW_F4 : 0)) * sizeof(float4);
 #define LAUNCH_PB(D, A, VC)                                                                                        \
     {                                                                                                              \
@@ -515,7 +604,7 @@ cudaError_t launch_preprocess_backward(const BatchTab& tab, const float* means3D
         }                                                                                                          \
         kfn<<<grid, 128, smem, st>>>(tab, means3D, scales, rotations, shs, cov3D_precomp, dL_dmeans3D, dL_dshs,     \
                                      dL_dcolors, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D,                \
-                                     stat_grad_accum, stat_denom, stat_max_radii, g_begin, g_end);                 \
+                                     stat_grad_accum, live_list, live_count);                                      \
     }
 #define DISPATCH_DEG(A, VC)                                                                                        \
     switch (tab.sh_degree) {                                                                                       \

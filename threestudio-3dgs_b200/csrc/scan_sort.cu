@@ -540,38 +540,52 @@ struct HistTab {
     const uint64_t* keys[MAX_VIEWS];
     uint32_t* hist[MAX_VIEWS];
 };
+template <int PASSES>   // 0: run-time pass count (stand-alone sort); the pipeline's depth sort uses 4
 __global__ void __launch_bounds__(256)
-radix_histogram_kernel(int64_t n, int passes, int end_bit, int shift_base, const __grid_constant__ HistTab tab) {
+radix_histogram_kernel(int64_t n, int passes_rt, int end_bit, int shift_base, const __grid_constant__ HistTab tab) {
     __shared__ uint32_t s_hist[MAX_PASSES * RADIX];
+    const int passes = PASSES ? PASSES : passes_rt;
     const uint64_t* __restrict__ keys = tab.keys[blockIdx.y];
     uint32_t* __restrict__ hist = tab.hist[blockIdx.y];
     for (int i = threadIdx.x; i < passes * RADIX; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
-    const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t n_round = (n + 31) / 32 * 32;  // keep warps converged for the votes
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-        const bool ok = i < n;
-        const uint64_t k = ok ? __ldg(keys + i) : 0ull;
-        for (int p = 0; p < passes; ++p) {
-            const int shift = p * RADIX_BITS;
-            const int bits = min(RADIX_BITS, end_bit - shift);
-            const uint32_t d = (uint32_t)(k >> (shift + shift_base)) & ((1u << bits) - 1u);
-            if (p + 1 < passes) {   // low digits are spread: one plain shared-memory atomic per key
-                if (ok) atomicAdd(&s_hist[p * RADIX + d], 1u);
-                continue;
+    constexpr int UN = 4;                              // independent loads in flight per thread
+    // top digit (the exponent byte of depth): a view holds two or three distinct values, and 256 threads adding to the
+    // same two shared-memory words serialise -- every thread counts its two most recent values in registers instead
+    uint32_t da = 0xffffffffu, db = 0xffffffffu, ca = 0, cb = 0;
+    const int top_shift = (passes - 1) * RADIX_BITS;
+    const uint32_t top_mask = (1u << min(RADIX_BITS, end_bit - top_shift)) - 1u;
+    uint32_t* s_top = s_hist + (passes - 1) * RADIX;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += UN * stride) {
+        uint64_t kk[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) kk[u] = (i0 + u * stride < n) ? __ldg(keys + i0 + u * stride) : 0ull;
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            if (i0 + u * stride >= n) continue;
+            const uint64_t k = kk[u] >> shift_base;
+#pragma unroll
+            for (int p = 0; p < (PASSES ? PASSES - 1 : MAX_PASSES - 1); ++p) {   // low digits are spread: plain atomics
+                if (p + 1 < passes) {
+                    const int shift = p * RADIX_BITS;
+                    atomicAdd(&s_hist[p * RADIX + ((uint32_t)(k >> shift) & (RADIX - 1))], 1u);
+                }
             }
-            // top digit: often warp-uniform (the exponent byte of depth) -- one add for the warp
-            const uint32_t d0 = __shfl_sync(0xffffffffu, d, 0);
-            const uint32_t same = __ballot_sync(0xffffffffu, ok && d == d0);
-            const uint32_t okm = __ballot_sync(0xffffffffu, ok);
-            if (same == okm) {
-                if (lane == 0 && okm) atomicAdd(&s_hist[p * RADIX + d0], (uint32_t)__popc(okm));
-            } else if (ok) {
-                atomicAdd(&s_hist[p * RADIX + d], 1u);
+            const uint32_t d = (uint32_t)(k >> top_shift) & top_mask;
+            if (d == da) {
+                ++ca;
+            } else if (d == db) {
+                ++cb;
+            } else {                 // evict the older entry
+                if (cb) atomicAdd(&s_top[db], cb);
+                db = da, cb = ca;
+                da = d, ca = 1;
             }
         }
     }
+    if (ca) atomicAdd(&s_top[da], ca);
+    if (cb) atomicAdd(&s_top[db], cb);
     __syncthreads();
     for (int i = threadIdx.x; i < passes * RADIX; i += blockDim.x) {
         const uint32_t c = s_hist[i];
@@ -960,7 +974,8 @@ tile_partition_kernel(int n_bins, const __grid_constant__ SortTab tab) {
         }
     }
     __syncthreads();
-    // ---- P3: decoupled look-back of the thread's bins, interleaved ----------------------------------
+    // ---- P3: decoupled look-back of the thread's bins, interleaved; the loads of its first step are in flight while
+    // the keys are scattered into shared memory (the scatter needs the tile-local offsets only) ---------------
     {
         uint32_t excl[WIDE_DPT];
         bool found[WIDE_DPT];
@@ -969,8 +984,8 @@ tile_partition_kernel(int n_bins, const __grid_constant__ SortTab tab) {
         constexpr int LOOK = 4;
         int look = (int)tile - 1;
         const uint32_t* col = sv.desc + tid;
-        while (!(found[0] && found[1] && found[2] && found[3])) {
-            uint32_t v[WIDE_DPT][LOOK];
+        uint32_t v[WIDE_DPT][LOOK];
+        auto issue = [&]() {
 #pragma unroll
             for (int k = 0; k < WIDE_DPT; ++k)
 #pragma unroll
@@ -978,6 +993,14 @@ tile_partition_kernel(int n_bins, const __grid_constant__ SortTab tab) {
                     v[k][u] = (!found[k] && look - u >= 0)
                                   ? ld_volatile_u32(col + (size_t)(look - u) * WIDE_BINS + k * SORT_THREADS)
                                   : DESC_INC;
+        };
+        issue();
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const uint32_t d = (uint32_t)(key[i] >> 32) & mask;
+            S.keys[rank[i] + S.a[d] + S.warp_hist[warp][d]] = key[i];
+        }
+        while (true) {
 #pragma unroll
             for (int k = 0; k < WIDE_DPT; ++k)
 #pragma unroll
@@ -990,7 +1013,9 @@ tile_partition_kernel(int n_bins, const __grid_constant__ SortTab tab) {
                         found[k] = (x >> 30) == 2;
                     }
                 }
+            if (found[0] && found[1] && found[2] && found[3]) break;
             look -= LOOK;
+            issue();
         }
 #pragma unroll
         for (int k = 0; k < WIDE_DPT; ++k) {
@@ -1000,13 +1025,7 @@ tile_partition_kernel(int n_bins, const __grid_constant__ SortTab tab) {
         }
     }
     __syncthreads();
-    // ---- scatter through shared memory, coalesced write-out -----------------------------------------
-#pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-        const uint32_t d = (uint32_t)(key[i] >> 32) & mask;
-        S.keys[rank[i] + S.a[d] + S.warp_hist[warp][d]] = key[i];
-    }
-    __syncthreads();
+    // ---- coalesced write-out ------------------------------------------------------------------------------
     uint64_t* __restrict__ keys_out = sv.keys_out;
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
@@ -1106,7 +1125,7 @@ cudaError_t launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_
     HistTab ht;
     ht.keys[0] = keys[0];
     ht.hist[0] = hist;
-    radix_histogram_kernel<<<dim3(hgrid, 1), 256, 0, st>>>(n, passes, end_bit, 0, ht);
+    radix_histogram_kernel<0><<<dim3(hgrid, 1), 256, 0, st>>>(n, passes, end_bit, 0, ht);
     count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -1171,7 +1190,7 @@ cudaError_t launch_gaussian_sort(const BatchTab& tab, cudaStream_t st, bool clea
     }
     int64_t hg = (n + 255) / 256;
     const int hgrid = (int)(hg < (int64_t)NUM_SMS * 8 / tab.V ? hg : (int64_t)NUM_SMS * 8 / tab.V);
-    radix_histogram_kernel<<<dim3(hgrid > 0 ? hgrid : 1, tab.V), 256, 0, st>>>(n, 4, 32, 32, ht);
+    radix_histogram_kernel<4><<<dim3(hgrid > 0 ? hgrid : 1, tab.V), 256, 0, st>>>(n, 4, 32, 32, ht);
     count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -1270,15 +1289,15 @@ tile_ranges_kernel(const __grid_constant__ BatchTab tab, int sel) {
 
 // order[] = the batch's (view * T + tile) entries by decreasing Gaussian-list length (LPT scheduling of the
 // render CTAs).  One CTA, counting sort on a monotone 11-bit key of the length (float exponent + 3 mantissa
-// bits: 8 buckets per octave) -- the order inside a bucket is irrelevant for load balance.
-constexpr int ORDER_BUCKETS = 2048;
+// bits: 8 buckets per octave, common.cuh order_bucket) -- the order inside a bucket is irrelevant for load balance.
+// Also zeroes the walk-length histogram that render forward fills for the block order of render backward.
 __global__ void __launch_bounds__(1024)
 tile_order_kernel(const __grid_constant__ BatchTab tab, int n) {
     __shared__ uint32_t s_cnt[ORDER_BUCKETS];
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_empty;      // cursor of the empty tiles (they all go to the end of the order)
     const int T = tab.grid_x * tab.grid_y;
-    for (int i = threadIdx.x; i < ORDER_BUCKETS; i += blockDim.x) s_cnt[i] = 0;
+    for (int i = threadIdx.x; i < ORDER_BUCKETS; i += blockDim.x) s_cnt[i] = 0, tab.block_hist[i] = 0;
     if (threadIdx.x == 0) s_empty = 0;
     __syncthreads();
     auto bucket_of = [&](int i) -> uint32_t {   // 0xffffffff: empty tile
@@ -1390,36 +1409,19 @@ tile_ranges_from_counts_kernel(const __grid_constant__ BatchTab tab) {
 // Work order of render backward: the batch's 8x4 pixel blocks that have anything to walk (largest n_contrib of the
 // block > 0), most entries first (LPT over the SMs at the granularity the backward actually works at: a silhouette
 // block walks ten times more entries than its neighbours in the same tile).  block_order[0] = count, entries follow
-// at [4..).  One CTA; counting sort on the same monotone 11-bit key as the tile order.
+// at [4..).  A counting sort on the monotone 11-bit key of the walk length whose COUNTING half is done by render
+// forward itself: each of its warps adds its block to block_hist[bucket] with one global atomic and keeps the returned
+// rank (block_code = bucket << 20 | rank).  What is left is this scatter: every CTA scans the 2048 bucket counts and
+// places its 1024 blocks at bucket start + rank.  (The single-CTA kernel that did both halves took 33 us per step
+// between render forward and render backward; this one takes ~3.)
 __global__ void __launch_bounds__(1024)
-block_order_kernel(const __grid_constant__ BatchTab tab, int n) {
-    __shared__ uint32_t s_cnt[ORDER_BUCKETS];
+block_scatter_kernel(const __grid_constant__ BatchTab tab, int n) {
+    __shared__ uint32_t s_start[ORDER_BUCKETS];
     __shared__ uint32_t s_warp[32];
-    const int per_view = tab.grid_x * tab.grid_y * (BLOCK_SIZE / 32);
-    for (int i = threadIdx.x; i < ORDER_BUCKETS; i += blockDim.x) s_cnt[i] = 0;
-    __syncthreads();
-    auto bucket_of = [&](int i) -> uint32_t {
-        const uint32_t len = tab.v[i / per_view].block_last[i % per_view];
-        if (len == 0u) return 0xffffffffu;
-        const uint32_t k = min((uint32_t)(ORDER_BUCKETS - 1), __float_as_uint((float)len) >> 20);
-        return (ORDER_BUCKETS - 1) - k;   // descending: the longest walks get the smallest bucket index
-    };
-    // 8 independent loads in flight per thread: a single CTA is latency-bound, not bandwidth-bound
-    constexpr int UN = 8;
-    for (int i0 = threadIdx.x; i0 < n; i0 += UN * blockDim.x) {
-        uint32_t b[UN];
-#pragma unroll
-        for (int u = 0; u < UN; ++u) {
-            const int i = i0 + u * blockDim.x;
-            b[u] = i < n ? bucket_of(i) : 0xffffffffu;
-        }
-#pragma unroll
-        for (int u = 0; u < UN; ++u)
-            if (b[u] != 0xffffffffu) atomicAdd(&s_cnt[b[u]], 1u);
-    }
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t c0 = s_cnt[2 * threadIdx.x], c1 = s_cnt[2 * threadIdx.x + 1];
+    const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const uint32_t code = i < n ? tab.block_code[i] : BLOCK_CODE_NONE;     // in flight during the scan
+    const uint32_t c0 = tab.block_hist[2 * threadIdx.x], c1 = tab.block_hist[2 * threadIdx.x + 1];
     uint32_t inc = c0 + c1;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -1431,27 +1433,16 @@ block_order_kernel(const __grid_constant__ BatchTab tab, int n) {
     uint32_t woff = 0;
     for (int w = 0; w < warp; ++w) woff += s_warp[w];
     const uint32_t excl = woff + inc - (c0 + c1);
-    if (threadIdx.x == 1023) tab.block_order[0] = excl + c0 + c1;   // number of non-empty blocks
+    if (blockIdx.x == 0 && threadIdx.x == 1023) tab.block_order[0] = excl + c0 + c1;   // number of non-empty blocks
+    s_start[2 * threadIdx.x] = excl;
+    s_start[2 * threadIdx.x + 1] = excl + c0;
     __syncthreads();
-    s_cnt[2 * threadIdx.x] = excl;
-    s_cnt[2 * threadIdx.x + 1] = excl + c0;
-    __syncthreads();
-    for (int i0 = threadIdx.x; i0 < n; i0 += UN * blockDim.x) {
-        uint32_t b[UN];
-#pragma unroll
-        for (int u = 0; u < UN; ++u) {
-            const int i = i0 + u * blockDim.x;
-            b[u] = i < n ? bucket_of(i) : 0xffffffffu;
-        }
-#pragma unroll
-        for (int u = 0; u < UN; ++u)
-            if (b[u] != 0xffffffffu) tab.block_order[4 + atomicAdd(&s_cnt[b[u]], 1u)] = (uint32_t)(i0 + u * blockDim.x);
-    }
+    if (code != BLOCK_CODE_NONE) tab.block_order[4 + s_start[code >> 20] + (code & 0xfffffu)] = (uint32_t)i;
 }
 
 cudaError_t launch_block_order(const BatchTab& tab, cudaStream_t st) {
     const int n = tab.V * tab.grid_x * tab.grid_y * (BLOCK_SIZE / 32);
-    block_order_kernel<<<1, 1024, 0, st>>>(tab, n);
+    block_scatter_kernel<<<(n + 1023) / 1024, 1024, 0, st>>>(tab, n);
     count_launch();
     return cudaGetLastError();
 }
