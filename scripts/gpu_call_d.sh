@@ -1,0 +1,14 @@
+set -x
+cd $GRAFT_REPO_ROOT
+TAG=${1:-r2d}
+( time B200SPLAT_FWD=ring timeout 1200 python -m pytest tests/test_parity_gpu.py tests/test_extra_gpu.py tests/test_renderer_gpu.py -m gpu -x -q ) > gpurun_out/${TAG}_pytest_ring.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest_ring.log
+tail -3 gpurun_out/${TAG}_pytest_ring.log
+for envs in "B200SPLAT_FWD=sync" "B200SPLAT_FWD=ring"; do
+  echo "== $envs" >> gpurun_out/${TAG}_ab.log
+  env $envs timeout 300 python bench.py --quick --steps 30 --warmup 5 >> gpurun_out/${TAG}_ab.log 2>&1
+done
+cut -c1-200 gpurun_out/${TAG}_ab.log
+B200SPLAT_FWD=ring timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"preprocess_backward|render_forward|radix_histogram|tile_partition" -o gpurun_out/${TAG}_full -f \
+   python scripts/profile_batch.py headline_1m_512_sh3 3 4 > gpurun_out/${TAG}_ncu_full.log 2>&1
+echo "ncu rc=$?"

@@ -63,14 +63,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
     } while (!ok);
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                 : "=r"(ok)
-                 : "r"(smem_u32(bar)), "r"(parity)
-                 : "memory");
-    return ok != 0;
-}
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(smem_dst)),
@@ -339,217 +331,6 @@ render_forward_kernel(const __grid_constant__ BatchTab tab, int sel) {
         out_color[2 * HW + pix] = C2 + T * bg[2];
         out_depth[pix] = D;
         out_alpha[pix] = Wt;
-        if (EXT) {
-            const float E[EXT_FLOATS] = {E0, E1, E2, E3};
-#pragma unroll
-            for (int c = 0; c < EXT_FLOATS; ++c)
-                if (c < tab.n_extra) vt.out_extra[c * HW + pix] = E[c];
-        }
-    }
-}
-
-// ============================================================================================
-// K6 forward, ring variant (default): the 8 warps of a tile still SHARE the staged batches (each thread gathers one of
-// a batch's 256 records), but they no longer meet at a CTA barrier per batch.  The batches live in a ring of
-// RING_STAGES stages with a "full" mbarrier (256 arrivals: the copies have landed) and an "empty" mbarrier (8 arrivals:
-// every warp has finished reading) per stage; a thread refills a stage as soon as its previous batch is empty, so a
-// warp with few survivors in a batch runs up to RING_STAGES - 1 batches ahead of one with many.  The barrier of the
-// lock-step kernel (render_forward_kernel) was 37 % of its stall samples: a batch costs a warp between nothing (its
-// pixels have stopped) and 256 evaluations, and every batch waited for the slowest.  A tile ends when all 8 warps
-// have stopped (a shared counter), which waiting warps poll.  Results are identical to the lock-step kernel's.
-// ============================================================================================
-constexpr int RING_STAGES = 3;
-template <bool EXT>
-struct RingSmem {
-    float4 rec[RING_STAGES][FWD_BATCH * 3];
-    float4 ext[RING_STAGES][EXT ? FWD_BATCH : 1];
-    uint8_t surv[BLOCK_SIZE / 32][FWD_BATCH + 16];
-    uint64_t full[RING_STAGES], empty[RING_STAGES];
-    uint32_t done_warps;
-};
-
-template <bool EXT>
-__global__ void __launch_bounds__(BLOCK_SIZE)
-render_forward_ring_kernel(const __grid_constant__ BatchTab tab, int sel) {
-    extern __shared__ __align__(16) unsigned char ring_raw[];
-    RingSmem<EXT>& S = *reinterpret_cast<RingSmem<EXT>*>(ring_raw);
-
-    const int W = tab.W, H = tab.H, grid_x = tab.grid_x;
-    const int n_tiles = grid_x * tab.grid_y;
-    const uint32_t entry = tab.tile_order[blockIdx.x];   // longest lists of the whole view batch first (LPT)
-    const ViewTab& vt = tab.v[entry / n_tiles];
-    const int tile = (int)(entry % n_tiles);
-    const int tile_x = tile % grid_x, tile_y = tile / grid_x;
-    const PointList point_list{tab.idx_bits ? vt.keys[sel] : nullptr, vt.vals[sel],
-                               tab.idx_bits ? (uint32_t)((1ull << tab.idx_bits) - 1ull) : 0xffffffffu};
-    const float* __restrict__ rec = vt.rec;
-    const float4* __restrict__ ext4 = tab.ext4;
-    const float* __restrict__ bg = vt.bg;
-    int lx, ly;
-    thread_pixel_cta(lx, ly);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    const int pxi = tile_x * BLOCK_X + lx, pyi = tile_y * BLOCK_Y + ly;
-    const bool inside = pxi < W && pyi < H;
-    const float pixx = (float)pxi, pixy = (float)pyi;
-    const float X0 = (float)(tile_x * BLOCK_X + (warp & 1) * 8), X1 = X0 + 7.f;
-    const float Y0 = (float)(tile_y * BLOCK_Y + (warp >> 1) * 4), Y1 = Y0 + 3.f;
-    const uint32_t r0 = vt.ranges[2 * tile], r1 = vt.ranges[2 * tile + 1];
-    const int total = (int)(r1 - r0);
-    const int rounds = (total + FWD_BATCH - 1) / FWD_BATCH;
-
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int s = 0; s < RING_STAGES; ++s) {
-            mbar_init(&S.full[s], BLOCK_SIZE);
-            mbar_init(&S.empty[s], BLOCK_SIZE / 32);
-        }
-        S.done_warps = 0;
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    bool done = !inside;
-    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Wt = 0.f, D = 0.f;
-    float E0 = 0.f, E1 = 0.f, E2 = 0.f, E3 = 0.f;
-    uint32_t last_contributor = 0, visited = 0;
-    int traversed = 0;
-    volatile uint32_t* done_warps = &S.done_warps;
-    constexpr uint32_t ALL_WARPS = BLOCK_SIZE / 32;
-
-    auto stage = [&](int nb) {
-        const int st = nb % RING_STAGES;
-        const int e = nb * FWD_BATCH + (int)threadIdx.x;
-        stage_entry<false, EXT>(S.rec[st], nullptr, &S.full[st], rec, point_list, (int)threadIdx.x, (int64_t)r0 + e,
-                                e < total, S.ext[st], ext4);
-    };
-    // wait for a phase of an mbarrier, giving up when the tile has ended; the decision is taken by lane 0 for the warp
-    auto wait_or_quit = [&](uint64_t* bar, uint32_t parity) -> bool {   // false: the tile has ended
-        int st;
-        do {
-            st = 0;
-            if (lane == 0) st = mbar_try_wait(bar, parity) ? 1 : (*done_warps == ALL_WARPS ? 2 : 0);
-            st = __shfl_sync(0xffffffffu, st, 0);
-        } while (st == 0);
-        __syncwarp();
-        return st == 1;
-    };
-    for (int nb = 0; nb < RING_STAGES - 1 && nb < rounds; ++nb) stage(nb);
-    bool warp_done = __all_sync(0xffffffffu, done);
-    if (warp_done && lane == 0) atomicAdd(&S.done_warps, 1u);   // a warp wholly outside the image
-    for (int b = 0; b < rounds; ++b) {
-        if (__any_sync(0xffffffffu, *done_warps == ALL_WARPS)) break;
-        const int nb = b + RING_STAGES - 1;
-        if (nb < rounds) {
-            // stage nb % RING_STAGES held batch b - 1: every warp must have finished reading it
-            if (b >= 1 && !wait_or_quit(&S.empty[(b - 1) % RING_STAGES], (uint32_t)(((b - 1) / RING_STAGES) & 1))) break;
-            stage(nb);
-        }
-        const int s = b % RING_STAGES;
-        if (!wait_or_quit(&S.full[s], (uint32_t)((b / RING_STAGES) & 1))) break;
-        if (!warp_done) {
-            const int count = min(FWD_BATCH, total - b * FWD_BATCH);
-            traversed = b * FWD_BATCH + count;
-            const float4* __restrict__ buf = S.rec[s];
-            const float4* __restrict__ ebuf = S.ext[s];
-            // batch-level cull: 8 independent tests per lane; survivors compacted (in list order) into the warp's
-            // private index list
-            uint8_t* __restrict__ surv = S.surv[warp];
-            int nsurv = 0;
-#pragma unroll
-            for (int c = 0; c < FWD_BATCH / 32; ++c) {
-                const int e = c * 32 + lane;
-                bool keep = false;
-                if (e < count) {
-                    const float4 q0 = buf[3 * e];
-                    const float4 q1 = buf[3 * e + 1];
-                    const float thr = buf[3 * e + 2].z;
-                    keep = cull_keep(q0, q1.x, thr, X0, X1, Y0, Y1);
-                }
-                const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-                if (keep) surv[nsurv + __popc(bal & lt_mask)] = (uint8_t)e;
-                nsurv += __popc(bal);
-            }
-            __syncwarp();
-            for (int i = 0; i < nsurv; i += ILP) {
-                if (__all_sync(0xffffffffu, done)) break;
-                // ILP survivors: alpha evaluated independently, then blended in list order (predicated, branch free)
-                const uint32_t packed = *reinterpret_cast<const uint32_t*>(surv + i);
-                int j[ILP];
-                float alpha[ILP], cr[ILP], cg[ILP], cb[ILP], cd[ILP];
-                float4 ex[ILP];
-                bool ok[ILP];
-#pragma unroll
-                for (int k = 0; k < ILP; ++k) {
-                    const bool has = i + k < nsurv;
-                    j[k] = has ? (int)((packed >> (8 * k)) & 0xffu) : (int)(packed & 0xffu);
-                    const float4 q0 = buf[3 * j[k]];
-                    const float4 q1 = buf[3 * j[k] + 1];
-                    const float2 q2 = *reinterpret_cast<const float2*>(buf + 3 * j[k] + 2);
-                    if (EXT) ex[k] = ebuf[j[k]];
-                    const float dx = q0.x - pixx, dy = q0.y - pixy;
-                    const float power = -0.5f * (q0.z * dx * dx + q1.x * dy * dy) - q0.w * dx * dy;
-                    alpha[k] = fminf(ALPHA_MAX, q1.y * __expf(power));
-                    ok[k] = has && (power <= 0.0f) && (alpha[k] >= ALPHA_MIN);
-                    cr[k] = q1.w, cg[k] = q2.x, cb[k] = q2.y, cd[k] = q1.z;
-                }
-#pragma unroll
-                for (int k = 0; k < ILP; ++k) {
-                    const bool act = ok[k] && !done;
-                    const float test_T = T * (1.0f - alpha[k]);
-                    const bool stop = act && (test_T < T_MIN);
-                    const bool use = act && !stop;
-                    const uint32_t position = (uint32_t)(b * FWD_BATCH + j[k] + 1);
-                    if (use) {
-                        const float w = alpha[k] * T;
-                        C0 += cr[k] * w;
-                        C1 += cg[k] * w;
-                        C2 += cb[k] * w;
-                        Wt += w;
-                        D += cd[k] * w;
-                        if (EXT) E0 += ex[k].x * w, E1 += ex[k].y * w, E2 += ex[k].z * w, E3 += ex[k].w * w;
-                        T = test_T;
-                        last_contributor = position;
-                    }
-                    if (stop) {
-                        done = true;
-                        visited = position;
-                    }
-                }
-            }
-            __syncwarp();   // every lane has finished reading the stage
-        }
-        if (lane == 0) mbar_arrive(&S.empty[s]);
-        if (!warp_done && __all_sync(0xffffffffu, done)) {
-            warp_done = true;
-            if (lane == 0) atomicAdd(&S.done_warps, 1u);
-        }
-    }
-    asm volatile("cp.async.wait_all;" ::: "memory");   // this thread's copies must land before the CTA's smem is released
-    {   // the block's largest n_contrib: how far render backward has to walk the list for these 32 pixels; the block
-        // enters the counting sort of render backward's work order here (bucket of the walk length, rank in the bucket)
-        const uint32_t wl = __reduce_max_sync(0xffffffffu, inside ? last_contributor : 0u);
-        if (lane == 0) {
-            vt.block_last[tile * WARPS_PER_TILE + warp] = wl;
-            uint32_t code = BLOCK_CODE_NONE;
-            if (wl) {
-                const uint32_t bucket = order_bucket(wl);
-                code = bucket << 20 | atomicAdd(tab.block_hist + bucket, 1u);
-            }
-            tab.block_code[(size_t)entry * WARPS_PER_TILE + warp] = code;
-        }
-    }
-    if (inside) {
-        const int pix = pyi * W + pxi;
-        const size_t HW = (size_t)H * W;
-        vt.n_contrib[pix] = last_contributor;
-        vt.n_visited[pix] = visited ? visited : (uint32_t)traversed;
-        vt.final_T[pix] = T;
-        vt.out_color[pix] = C0 + T * bg[0];
-        vt.out_color[HW + pix] = C1 + T * bg[1];
-        vt.out_color[2 * HW + pix] = C2 + T * bg[2];
-        vt.out_depth[pix] = D;
-        vt.out_alpha[pix] = Wt;
         if (EXT) {
             const float E[EXT_FLOATS] = {E0, E1, E2, E3};
 #pragma unroll
@@ -884,33 +665,9 @@ static bool use_bulk_staging() {
     return env_mode == 1;
 }
 
-static bool forward_ring() {   // B200SPLAT_FWD=ring selects the ring kernel, =sync the lock-step kernel (A/B)
-    static const bool on = [] {
-        const char* e = getenv("B200SPLAT_FWD");
-        return e && strcmp(e, "ring") == 0;
-    }();
-    return on;
-}
-
 cudaError_t launch_render_forward(const BatchTab& tab, int sel, cudaStream_t st) {
     const unsigned grid = (unsigned)(tab.V * tab.grid_x * tab.grid_y);
     const bool ext = tab.n_extra > 0;
-    if (forward_ring() && !use_bulk_staging()) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(render_forward_ring_kernel<false>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RingSmem<false>));
-            if (e != cudaSuccess) return e;
-            e = cudaFuncSetAttribute(render_forward_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)sizeof(RingSmem<true>));
-            if (e != cudaSuccess) return e;
-            attr_set = true;
-        }
-        if (ext) render_forward_ring_kernel<true><<<grid, BLOCK_SIZE, sizeof(RingSmem<true>), st>>>(tab, sel);
-        else render_forward_ring_kernel<false><<<grid, BLOCK_SIZE, sizeof(RingSmem<false>), st>>>(tab, sel);
-        count_launch();
-        return cudaGetLastError();
-    }
     if (use_bulk_staging()) {
         if (ext) render_forward_kernel<true, true><<<grid, BLOCK_SIZE, 0, st>>>(tab, sel);
         else render_forward_kernel<true, false><<<grid, BLOCK_SIZE, 0, st>>>(tab, sel);
