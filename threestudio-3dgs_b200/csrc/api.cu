@@ -314,6 +314,12 @@ static PinnedSlot& pinned() {
 
 using namespace b200splat;
 
+// backward scratch of a view: grad2d records | extra-channel records | one byte per Gaussian that render backward sets
+// when it adds a gradient to the Gaussian's record (what preprocess backward's scan looks at instead of the records)
+static size_t touched_offset(int P) {
+    return grad2d_bytes(P) + align_up((size_t)(P > 0 ? P : 1) * EXT_FLOATS * sizeof(float), 256);
+}
+
 // error reporting for the other translation units that export C-ABI entry points (postops.cu, adam.cu)
 int b200splat_set_error(int code, const char* msg) { return fail(code, "%s", msg); }
 
@@ -490,7 +496,7 @@ size_t b200splat_image_bytes(int32_t H, int32_t W) { return image_layout(H, W, n
 size_t b200splat_binning_bytes(int64_t R) { return binning_layout(R, nullptr, nullptr); }
 int64_t b200splat_binning_capacity(size_t bytes) { return capacity_for_bytes(bytes); }
 size_t b200splat_backward_scratch_bytes(int32_t P) {   // grad2d records, then the extra-channel records
-    return grad2d_bytes(P) + align_up((size_t)(P > 0 ? P : 1) * EXT_FLOATS * sizeof(float), 256);
+    return touched_offset(P) + align_up((size_t)(P > 0 ? P : 1), 256);   // + one "has a gradient" byte per Gaussian
 }
 size_t b200splat_sort_workspace_bytes(int64_t n) { return sort_workspace_bytes(n); }
 size_t b200splat_scan_workspace_bytes(int64_t n) { return scan_workspace_bytes(n); }
@@ -674,6 +680,7 @@ static int backward_run(BatchTab& tab, const float* means3D, const float* scales
         if (!scratch_clean)
             for (int v = 0; v < tab.V; ++v) {
                 CU(cudaMemsetAsync(tab.v[v].grad2d, 0, (size_t)tab.P * GRAD2D_FLOATS * sizeof(float), st));
+                CU(cudaMemsetAsync(tab.v[v].touched, 0, (size_t)tab.P, st));
                 if (tab.n_extra > 0)
                     CU(cudaMemsetAsync(tab.v[v].gradext, 0, (size_t)tab.P * EXT_FLOATS * sizeof(float), st));
             }
@@ -729,6 +736,7 @@ int b200splat_backward(const b200splat_backward_args* a) {
     vt.dL_dcolor = a->dL_dout_color, vt.dL_ddepth = a->dL_dout_depth, vt.dL_dalpha = a->dL_dout_alpha;
     vt.grad2d = reinterpret_cast<float*>(a->scratch);
     vt.gradext = reinterpret_cast<float*>(reinterpret_cast<char*>(a->scratch) + grad2d_bytes(P));
+    vt.touched = reinterpret_cast<uint8_t*>(a->scratch) + touched_offset(P);
     vt.dL_dextra = a->dL_dout_extra;
     vt.dL_dmeans2D = a->dL_dmeans2D;
     return backward_run(tab, a->means3D, a->scales, a->rotations, a->shs, a->cov3D_precomp, a->dL_dmeans3D, a->dL_dshs,
@@ -769,6 +777,7 @@ int b200splat_backward_batched(const b200splat_batch_backward_args* a) {
             return fail(B200SPLAT_ERR_INVALID, "null buffer for view %d", v);
         fill_geom(P, const_cast<void*>(a->geom_buffer[v]), &vt, v == 0 ? &tab.ext4 : nullptr);
         vt.gradext = reinterpret_cast<float*>(reinterpret_cast<char*>(a->scratch[v]) + grad2d_bytes(P));
+        vt.touched = reinterpret_cast<uint8_t*>(a->scratch[v]) + touched_offset(P);
         vt.dL_dextra = (tab.n_extra > 0 && a->dL_dout_extra) ? a->dL_dout_extra[v] : nullptr;
         fill_image(tab.H, tab.W, const_cast<void*>(a->image_buffer[v]), &vt, v == 0 ? &tab : nullptr);
         fill_binning(cap, const_cast<void*>(a->binning_buffer[v]), &vt);

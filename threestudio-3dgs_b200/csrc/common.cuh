@@ -112,6 +112,7 @@ struct ViewTab {
     float* out_extra;         // (n_extra, H, W): sum_i e_i alpha_i T_i, no background term
     const float* dL_dextra;   // (n_extra, H, W) pixel gradients, or NULL
     float* gradext;           // [P][4] per-Gaussian gradient of the padded extra record (atomics, behind grad2d)
+    uint8_t* touched;         // [P] set to 1 by render backward when it adds to the Gaussian's record (behind gradext)
 };
 
 struct BatchTab {

@@ -157,9 +157,9 @@ __device__ __forceinline__ void put(float* p, float v) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // Scan kernel: one thread per Gaussian, streaming, full occupancy.  Which views saw the Gaussian (radii > 0), and in
-// which of those did render backward leave a gradient at all?  Most pairs of a dense scene sit behind the saturation
-// point of their pixels: the Gaussian is visible, its 48-byte gradient record is all zeros, and every term it would
-// add to the parameter gradients is an exact zero.  Such a view is dropped here.  A Gaussian without any gradient
+// which of those did render backward leave a gradient at all (its `touched` byte)?  Most pairs of a dense scene sit
+// behind the saturation point of their pixels: the Gaussian is visible, its 48-byte gradient record is all zeros, and
+// every term it would add to the parameter gradients is an exact zero.  Such a view is dropped here.  A Gaussian without any gradient
 // only gets its zero outputs and its statistics written -- no parameters, no SH row, no arithmetic; the others are
 // appended (index, live views, clamp bits) to the work list of preprocess_backward_kernel, whose warps are then full
 // of Gaussians that do have work.  (In the headline scene ~1/6 of the Gaussians of a 4-view step carry a gradient.)
@@ -192,20 +192,16 @@ preprocess_backward_scan_kernel(const __grid_constant__ BatchTab tab, float* __r
             if (rad[v] > 0) vis |= 1u << v;
             max_radius = max(max_radius, rad[v]);
         }
-        // all visible views' records in flight together
-        uint4 rec[MAX_VIEWS][3];
+        // which of the visible views left a gradient: render backward's byte per (view, Gaussian); consumed here (a set
+        // byte is cleared, after it has been read: self-cleaning like the records)
+        uint8_t tch[MAX_VIEWS];
+#pragma unroll
+        for (int v = 0; v < MAX_VIEWS; ++v) tch[v] = ((vis >> v) & 1u) ? tab.v[v].touched[idx] : (uint8_t)0;
 #pragma unroll
         for (int v = 0; v < MAX_VIEWS; ++v) {
-            if ((vis >> v) & 1u) {
-                const uint4* gp = reinterpret_cast<const uint4*>(tab.v[v].grad2d) + 3 * (size_t)idx;
-                rec[v][0] = gp[0], rec[v][1] = gp[1], rec[v][2] = gp[2];
-            }
-        }
-#pragma unroll
-        for (int v = 0; v < MAX_VIEWS; ++v) {
-            if ((vis >> v) & 1u) {
-                const uint4 a = rec[v][0], b = rec[v][1], c = rec[v][2];
-                if (a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w | c.x | c.y) live |= 1u << v;
+            if (tch[v]) {
+                live |= 1u << v;
+                tab.v[v].touched[idx] = 0;
             }
         }
         if (has_clamp)

@@ -162,8 +162,8 @@ __device__ __forceinline__ void stage_batch_cta(float4* buf, uint32_t* ids, uint
 // ============================================================================================
 // EXT: up to 4 extra feature channels per Gaussian (one more 16-byte record per staged entry) are blended with the
 // same weights as the colour and written to out_extra (no background term)
-template <bool BULK, bool EXT>
-__global__ void __launch_bounds__(BLOCK_SIZE)
+template <bool BULK, bool EXT, int MINB = 0>
+__global__ void __launch_bounds__(BLOCK_SIZE, MINB)
 render_forward_kernel(const __grid_constant__ BatchTab tab, int sel) {
     __shared__ __align__(16) float4 s_rec[FWD_STAGES][FWD_BATCH * 3];
     __shared__ __align__(16) float4 s_ext[FWD_STAGES][EXT ? FWD_BATCH : 1];
@@ -403,6 +403,7 @@ render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
     __shared__ uint32_t s_ids[BWD_STAGES][BWD_BATCH];
     __shared__ __align__(8) uint64_t s_bar[BWD_STAGES];
     __shared__ __align__(16) float s_red[32 * RS];
+    __shared__ __align__(4) uint8_t s_surv[BWD_BATCH + 4];
 
     const int W = tab.W, H = tab.H, grid_x = tab.grid_x;
     const int n_tiles = grid_x * tab.grid_y;
@@ -422,9 +423,11 @@ render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
     const float* __restrict__ bg = vt.bg;
     float* __restrict__ grad2d = vt.grad2d;
     float* __restrict__ gradext = vt.gradext;
+    uint8_t* __restrict__ touched = vt.touched;
     int lx, ly;
     thread_pixel(wblock, lx, ly);
     const int lane = threadIdx.x;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     const int pxi = tile_x * BLOCK_X + lx, pyi = tile_y * BLOCK_Y + ly;
     const bool inside = pxi < W && pyi < H;
     const float pixx = (float)pxi, pixy = (float)pyi;
@@ -540,7 +543,9 @@ render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
         mbar_wait(&s_bar[st], (b / BWD_STAGES) & 1);
         const int count = min(BWD_BATCH, total - b * BWD_BATCH);
         const float4* __restrict__ buf = s_rec[st];
-        unsigned long long surv = 0ull;   // survivors of the batch, bit = slot (list order = bit order)
+        // survivors of the batch, compacted in list order into the warp's byte list (one LDS.32 then hands a group its
+        // four slots; walking a 64-bit mask with ffs cost 14 % of the kernel's stall samples)
+        int nsurv = 0, gi = 0;
 #pragma unroll
         for (int u = 0; u < PER_LANE; ++u) {
             const int e = lane + 32 * u;
@@ -551,17 +556,18 @@ render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
                 const float thr = buf[3 * e + 2].z;
                 keep = cull_keep(q0, q1.x, thr, X0, X1, Y0, Y1);
             }
-            surv |= (unsigned long long)__ballot_sync(0xffffffffu, keep) << (32 * u);
+            const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+            if (keep) s_surv[nsurv + __popc(bal & lt_mask)] = (uint8_t)e;
+            nsurv += __popc(bal);
         }
+        __syncwarp();
         // ---- phase 1: ILP survivors evaluated independently (LDS / MUFU latencies overlap) -----------------------
         auto eval_group = [&]() {
-            jpack = 0, anyhit = 0;
+            jpack = *reinterpret_cast<const uint32_t*>(s_surv + gi), anyhit = 0;
 #pragma unroll
             for (int k = 0; k < ILP; ++k) {
-                const bool has = surv != 0ull;
-                const int j = has ? __ffsll((long long)surv) - 1 : 0;
-                surv &= surv - 1ull;
-                jpack |= (uint32_t)j << (8 * k);
+                const bool has = gi + k < nsurv;
+                const int j = has ? (int)((jpack >> (8 * k)) & 0xffu) : 0;
                 const float4 q0 = buf[3 * j];
                 const float4 q1 = buf[3 * j + 1];
                 const float2 q2 = *reinterpret_cast<const float2*>(buf + 3 * j + 2);
@@ -588,8 +594,9 @@ render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
                 dot[k] = d;
                 anyhit |= (__any_sync(0xffffffffu, hit) ? 1u : 0u) << k;
             }
+            gi += ILP;
         };
-        if (surv != 0ull) eval_group();
+        if (nsurv > 0) eval_group();
         else anyhit = 0u;
         bool more = true;
         while (more) {
@@ -621,7 +628,7 @@ render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
                 __syncwarp();
             }
             // the next group's phase 1 is independent of this group's reduction: issued first, they overlap
-            more = surv != 0ull;
+            more = gi < nsurv;
             if (more) eval_group();
             if (hit_g) {
                 // ---- phase 3: column sums over the 32 rows, one vector reduction per float4 of a record -----------
@@ -645,6 +652,9 @@ render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
                     const size_t id = s_ids[st][(jpack_g >> (8 * red_k)) & 0xffu];
                     if (!EXT || red_part < 3) red_add_v4(grad2d + id * GRAD2D_FLOATS + 4 * red_part, acc);
                     else red_add_v4(gradext + id * EXT_FLOATS, acc);
+                    // "this Gaussian has a gradient in this view": what preprocess backward's scan reads instead of
+                    // the 48-byte record (a plain byte store; every writer stores the same value)
+                    if (red_part == 0) touched[id] = 1;
                 }
                 __syncwarp();   // the rows are rewritten by the next group
             }
@@ -672,7 +682,13 @@ cudaError_t launch_render_forward(const BatchTab& tab, int sel, cudaStream_t st)
         if (ext) render_forward_kernel<true, true><<<grid, BLOCK_SIZE, 0, st>>>(tab, sel);
         else render_forward_kernel<true, false><<<grid, BLOCK_SIZE, 0, st>>>(tab, sel);
     } else {
+        static const int minb = [] {   // B200SPLAT_FWD_MINB=6: cap the registers for 6 CTAs per SM (A/B)
+            const char* e = getenv("B200SPLAT_FWD_MINB");
+            return e ? atoi(e) : 1;
+        }();
         if (ext) render_forward_kernel<false, true><<<grid, BLOCK_SIZE, 0, st>>>(tab, sel);
+        else if (minb == 6) render_forward_kernel<false, false, 6><<<grid, BLOCK_SIZE, 0, st>>>(tab, sel);
+        else if (minb == 7) render_forward_kernel<false, false, 7><<<grid, BLOCK_SIZE, 0, st>>>(tab, sel);
         else render_forward_kernel<false, false><<<grid, BLOCK_SIZE, 0, st>>>(tab, sel);
     }
     count_launch();
