@@ -510,11 +510,48 @@ def test_full_size_properties_headline_workload():
     br.step(cams, m3, sh, None, op, scl, rot, pgs)
     assert not br.overflowed()
     assert torch.equal(br.ws[0].radii[0], radii) and float((br.ws[0].color[0] - color).abs().max()) < 1e-6
+    # the batched pipeline (fused scan + duplicateWithKeys, look-back-free partition from the count matrix) produces the
+    # single-view pipeline's sorted list bit for bit
+    vb = ops.forward_views(cams[0], br.ws[0].states(sh.shape[1])[0])
+    assert int(vb["point_offsets"][-1]) == R
+    assert torch.equal(vb["keys_sorted"][:R], v["keys_sorted"]) and torch.equal(vb["point_list"][:R], v["point_list"])
+    assert torch.equal(vb["ranges"], v["ranges"]) and torch.equal(vb["n_contrib"], v["n_contrib"])
     _, radii_b, _, alpha_b, st_b = ops.forward(cams[1], m3, sh, None, op, scl, rot, None)
     gsum = {k: ga[k] + ops.backward(cams[1], st_b, m3, sh, None, op, scl, rot, None, radii_b, alpha_b, *pgs[1])[k]
             for k in ("means3D", "shs", "opacities", "scales", "rotations")}
     for k, t in gsum.items():
         assert rel_err(br.packed.views[k], t) < 1e-4, k
+
+
+@pytest.mark.parametrize("P,H,W,scale_mul", [(20000, 256, 256, 6.0),     # huge splats: > 8 partition tiles per CTA
+                                              (50000, 512, 512, 1.0),     # 1024 tiles: every bin of the wide pass
+                                              (700, 64, 48, 1.0)])        # less than one partition tile
+def test_batched_binning_matches_single_view_bit_for_bit(P, H, W, scale_mul):
+    """The batched forward's binning (depth sort -> fused scan + duplicateWithKeys with the per-(partition tile, image
+    tile) count matrix -> partition offsets -> look-back-free partition) against the single-view pipeline (stand-alone
+    scan, duplicateWithKeys, look-back partition), which the oracle tests pin: sorted words, list, ranges, n_contrib."""
+    from b200splat import batched, ops
+    sc, _ = _scene(P, 0, H, W, 905)
+    cams_h = scenes.sds_cameras(2, H, W, seed=906)
+    dev = "cuda"
+    d = lambda t: t.to(dev).contiguous()
+    m3, sh, op, rot = map(d, (sc.means3D, sc.shs, sc.opacities, sc.rotations))
+    scl = d(sc.scales * scale_mul)
+    cams = [ops.make_cam(cuda_settings(oracle_settings(c, 0)), dev) for c in cams_h]
+    pgs = [tuple(d(g) for g in scenes.pixel_grads(H, W, 910 + i)) for i in range(2)]
+    br = batched.BatchRenderer(P, sh.shape[1], H, W, dev, views=2)
+    br.step(cams, m3, sh, None, op, scl, rot, pgs)
+    assert not br.overflowed()
+    for i in range(2):
+        color, radii, depth, alpha, st = ops.forward(cams[i], m3, sh, None, op, scl, rot, None)
+        vs = ops.forward_views(cams[i], st)
+        vb = ops.forward_views(cams[i], br.ws[0].states(sh.shape[1])[i])
+        R = st.num_rendered
+        assert int(vb["point_offsets"][-1]) == R
+        assert torch.equal(vb["keys_sorted"][:R], vs["keys_sorted"]), "sorted pair words"
+        assert torch.equal(vb["point_list"][:R], vs["point_list"]), "point list"
+        assert torch.equal(vb["ranges"], vs["ranges"]) and torch.equal(vb["n_contrib"], vs["n_contrib"])
+        assert torch.equal(br.ws[0].color[i], color)
 
 
 def test_stress_shape_pair_mode_and_large_tile_count():

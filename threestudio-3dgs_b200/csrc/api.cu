@@ -360,6 +360,8 @@ static int forward_tail(BatchTab& tab, int debug, cudaStream_t st, bool binning_
     // The tile ranges (exclusive scan of duplicateWithKeys' per-tile counts) and the tile order of the render do not
     // depend on the sorted pair words: they run on a parallel branch next to the pair partition (12 us per step off
     // the critical path).  Above 8192 tiles the ranges are read off the sorted words and the branch is not taken.
+    { ProfScope ps(3, st, /*counted=*/false);
+    CU(launch_partition_offsets(tab, st)); }   // (look-back-free partition only) also writes the per-tile counts
     SideLane* lane = (tab.P > 0 && tab.capacity > 0 && T <= 8192 && !debug) ? side_lane() : nullptr;
     if (lane) {
         CU(cudaEventRecord(lane->fork, st));
@@ -637,6 +639,7 @@ int b200splat_forward_batched(const b200splat_batch_forward_args* a) {
     // when the tile histogram fits in shared memory, else the two stand-alone kernels
     tab.sort_tiles_cap = sort_tiles_for(tab.capacity);
     const bool fused = scan_duplicate_supported(tab);
+    tab.pt_words = fused ? partition_direct_words(tab) : 0;
     if (fused) {
         ProfScope ps(2, st);
         CU(launch_scan_duplicate(tab, st));

@@ -123,6 +123,8 @@ struct BatchTab {
     uint32_t capacity;         // pairs each view's key/value arrays can hold
     int end_bit;               // tile-id bits: pair words (tile << 32 | index) are sorted on bits [32, 32 + end_bit)
     int sort_tiles_cap;        // ceil(capacity / SORT_TILE)
+    int pt_words;              // > 0: scan + duplicateWithKeys also count the pairs per (partition tile of pt_words
+                               // words, image tile) for the look-back-free pair partition (scan_sort.cu K4d)
     int digit_passes;          // 8-bit passes of the pair sort; 0 = one wide pass binned by the per-tile counts
     int idx_bits;              // index bits of a pair word (32)
     int clean_scratch;         // preprocess backward zeroes every grad2d record it has read (self-cleaning scratch)
@@ -182,6 +184,7 @@ cudaError_t launch_preprocess(const BatchTab& tab, const float* means3D, const f
 cudaError_t launch_duplicate(const BatchTab& tab, cudaStream_t st);
 // scan + duplicateWithKeys in one kernel (scan_sort.cu); needs the scan work area AND the binning work areas cleared
 bool scan_duplicate_supported(const BatchTab& tab);
+int partition_direct_words(const BatchTab& tab);   // words per partition tile of the look-back-free partition, or 0
 cudaError_t launch_scan_duplicate(const BatchTab& tab, cudaStream_t st);
 cudaError_t launch_mark_visible(int P, const float* means3D, const float* view, const float* proj,
                                 uint8_t* present, cudaStream_t st);
@@ -205,6 +208,7 @@ int sort_tiles_for(int64_t n);
 cudaError_t launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_t* vals[2], void* ws, int* sel,
                               cudaStream_t st);
 // pipeline sort: histograms already accumulated by duplicateWithKeys, n read from the device per view
+cudaError_t launch_partition_offsets(const BatchTab& tab, cudaStream_t st);   // look-back-free partition: before ranges
 cudaError_t launch_sort_batch(const BatchTab& tab, cudaStream_t st);
 cudaError_t launch_tile_ranges_batch(const BatchTab& tab, int sel, cudaStream_t st);   // + tile order
 cudaError_t launch_block_order(const BatchTab& tab, cudaStream_t st);   // work order of render backward (after forward)
@@ -256,6 +260,11 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // per-thread asynchronous 16-byte copies global -> shared (LDGSTS), groups committed / awaited by the same thread
 __device__ __forceinline__ void cpa16(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void cpa4(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
                  "l"(gmem_src)
                  : "memory");
 }

@@ -183,32 +183,34 @@ preprocess_backward_scan_kernel(const __grid_constant__ BatchTab tab, float* __r
     const bool in_range = idx < g_end;
     uint32_t vis = 0, live = 0, clamp3 = 0;
     if (in_range) {
-        int max_radius = 0;
+        // every load of the thread goes out before anything is consumed (one round of memory latency instead of three:
+        // the kernel is a stream of independent 1-16 byte reads and zero stores).  The bytes of a view that did not
+        // see the Gaussian are zero, so they are read unconditionally.
         int rad[MAX_VIEWS];
+        uint8_t tch[MAX_VIEWS], clp[MAX_VIEWS];
 #pragma unroll
-        for (int v = 0; v < MAX_VIEWS; ++v) rad[v] = v < V ? tab.v[v].radii[idx] : 0;
+        for (int v = 0; v < MAX_VIEWS; ++v) {
+            rad[v] = v < V ? tab.v[v].radii[idx] : 0;
+            tch[v] = v < V ? tab.v[v].touched[idx] : (uint8_t)0;
+            clp[v] = (v < V && has_clamp) ? tab.v[v].clamped[idx] : (uint8_t)0;
+        }
+        const float sd = stat_denom ? stat_denom[idx] : 0.f;
+        const float sm = stat_max_radii ? stat_max_radii[idx] : 0.f;
+        int max_radius = 0;
 #pragma unroll
         for (int v = 0; v < MAX_VIEWS; ++v) {
             if (rad[v] > 0) vis |= 1u << v;
             max_radius = max(max_radius, rad[v]);
-        }
-        // which of the visible views left a gradient: render backward's byte per (view, Gaussian); consumed here (a set
-        // byte is cleared, after it has been read: self-cleaning like the records)
-        uint8_t tch[MAX_VIEWS];
-#pragma unroll
-        for (int v = 0; v < MAX_VIEWS; ++v) tch[v] = ((vis >> v) & 1u) ? tab.v[v].touched[idx] : (uint8_t)0;
-#pragma unroll
-        for (int v = 0; v < MAX_VIEWS; ++v) {
+            // which of the views left a gradient: render backward's byte per (view, Gaussian); consumed here (a set
+            // byte is cleared, after it has been read: self-cleaning like the records)
             if (tch[v]) {
                 live |= 1u << v;
+                clamp3 |= ((uint32_t)clp[v] & 7u) << (3 * v);
                 tab.v[v].touched[idx] = 0;
             }
         }
-        if (has_clamp)
-            for (int v = 0; v < V; ++v)
-                if ((live >> v) & 1u) clamp3 |= ((uint32_t)tab.v[v].clamped[idx] & 7u) << (3 * v);
-        if (stat_denom && vis) stat_denom[idx] += (float)__popc(vis);
-        if (stat_max_radii && vis) stat_max_radii[idx] = fmaxf(stat_max_radii[idx], (float)max_radius);
+        if (stat_denom && vis) stat_denom[idx] = sd + (float)__popc(vis);
+        if (stat_max_radii && vis) stat_max_radii[idx] = fmaxf(sm, (float)max_radius);
         if (!ACC) {
             for (int v = 0; v < V; ++v) {      // views without a gradient: dL/dmeans2D = 0
                 float* m2 = tab.v[v].dL_dmeans2D;
@@ -259,7 +261,7 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
     // record (cp.async), then the SH phase's per-view state -- and, on the vector path, the thread's SH row
     // (row stride 13 float4: LDS.128 of neighbouring threads fall in different bank groups)
     extern __shared__ float4 s_dyn4[];
-    if (blockIdx.x * blockDim.x >= *live_count) return;   // launched over the whole range: most CTAs stop here
+    if (blockIdx.x * blockDim.x >= *live_count) return;
     float4* s_slots = s_dyn4;   // [V][128][3]
     const int V = tab.V;
     float4* sh_row = (VEC && DEG >= 0) ? s_dyn4 + (size_t)V * 128 * 3 + threadIdx.x * SH_ROW_F4 : nullptr;
@@ -279,8 +281,9 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
     constexpr int NCH = (K + 3) / 4;          // live chunks of 4 coefficients
     // work item: a Gaussian with a gradient in at least one view, from the list preprocess_backward_scan_kernel wrote
     // (x = index, y = views with a gradient | clamp bits of view v << (8 + 3 v)); launched over the whole range
-    const uint32_t item_no = blockIdx.x * blockDim.x + threadIdx.x;
-    if (item_no >= *live_count) return;
+    // a resident grid (launch_preprocess_backward: a few CTAs per SM) walks the list
+    const uint32_t n_items = *live_count;
+    for (uint32_t item_no = blockIdx.x * blockDim.x + threadIdx.x; item_no < n_items; item_no += gridDim.x * blockDim.x) {
     const uint2 item = live_list[item_no];
     const int idx = (int)item.x;
     const uint32_t vis = item.y & 0xffu;           // from here on "vis" = the views with a gradient
@@ -550,6 +553,7 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
     // fused densification statistics (geometry/gaussian_base.py:815-819, 846-851)
     // (denominator and largest radius: the scan kernel; a view without a gradient adds a zero norm)
     if (stat_grad_accum) stat_grad_accum[idx] += st_norm;
+    }   // work-list loop
 }
 
 cudaError_t launch_preprocess_backward(const BatchTab& tab, const float* means3D, const float* scales,
@@ -598,7 +602,8 @@ cudaError_t launch_preprocess_backward(const BatchTab& tab, const float* means3D
             if (e != cudaSuccess) return e;                                                                        \
             attr = smem;                                                                                           \
         }                                                                                                          \
-        kfn<<<grid, 128, smem, st>>>(tab, means3D, scales, rotations, shs, cov3D_precomp, dL_dmeans3D, dL_dshs,     \
+        kfn<<<grid < NUM_SMS * 4 ? grid : NUM_SMS * 4, 128, smem, st>>>(                                           \
+            tab, means3D, scales, rotations, shs, cov3D_precomp, dL_dmeans3D, dL_dshs,                             \
                                      dL_dcolors, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D,                \
                                      stat_grad_accum, live_list, live_count);                                      \
     }

@@ -240,24 +240,35 @@ cudaError_t launch_pair_count(const BatchTab& tab, uint64_t* notify, uint32_t ep
 // pair counts (global bins of the tile partition, tile ranges) are accumulated in shared memory and flushed once per CTA.
 // Same outputs, bit for bit, as scan_lookback_kernel + duplicate_kernel: point_offsets, pair words, tile_count, hist.
 constexpr int SD_MAX_TILES = 8192;
-__global__ void __launch_bounds__(SCAN_THREADS)
+constexpr int PO_CHUNKS_WORDS = 32 * 1024;   // chunk bases of partition_offsets_kernel: [PO_CHUNKS][WIDE_BINS]
+constexpr int SD_NPT = 8;          // partition tiles of a CTA's pair range counted in shared memory (pt mode)
+constexpr int WIDE_BITS = 10;      // the single-pass pair partition handles tile ids of up to 10 bits (512 x 512 images)
+constexpr int WIDE_BINS = 1 << WIDE_BITS;
+template <int SD_T>   // threads per CTA (512: one CTA per SM; 256: two, whose phases overlap)
+__global__ void __launch_bounds__(SD_T, SD_T == 256 ? 2 : 1)
 scan_duplicate_kernel(const __grid_constant__ BatchTab tab) {
-    extern __shared__ uint32_t s_dyn[];                 // [SCAN_TILE + SCAN_TILE/32] exchange | [passes*256] | [T]
+    constexpr int SD_TILE = SD_T * SCAN_ITEMS;
+    extern __shared__ uint32_t s_dyn[];                 // [SD_TILE + SD_TILE/32] exchange | [passes*256] | [T]
     __shared__ uint32_t s_tile;
-    __shared__ uint32_t s_warp[SCAN_THREADS / 32];
+    __shared__ uint32_t s_warp[SD_T / 32];
     __shared__ uint32_t s_excl;
     const ViewTab& vt = tab.v[blockIdx.y];
     const int64_t n = tab.P;
     const int T = tab.grid_x * tab.grid_y, gx = tab.grid_x;
     const int passes = tab.digit_passes, end_bit = tab.end_bit;
     uint32_t* s_x = s_dyn;
-    uint32_t* s_hist = s_dyn + SCAN_TILE + SCAN_TILE / 32;
+    uint32_t* s_hist = s_dyn + SD_TILE + SD_TILE / 32;
     uint32_t* s_cnt = s_hist + passes * 256;
-    for (int i = threadIdx.x; i < passes * 256 + T; i += SCAN_THREADS) s_hist[i] = 0;
+    // pt mode (look-back-free pair partition, K4d): the pairs are counted per (partition tile of pt_words words of the
+    // pair stream, image tile) -- SD_NPT partition tiles of this CTA's part of the stream in shared memory, any further
+    // ones (huge splats) straight in global memory -- and flushed into the matrix vt.desc[partition tile][1024]
+    const uint32_t pt_words = (uint32_t)tab.pt_words;
+    const int cnt_words = pt_words ? SD_NPT * T : T;
+    for (int i = threadIdx.x; i < passes * 256 + cnt_words; i += SD_T) s_hist[i] = 0;
     if (threadIdx.x == 0) s_tile = atomicAdd(vt.scan_ticket, 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
-    const int64_t tile_base = (int64_t)tile * SCAN_TILE;
+    const int64_t tile_base = (int64_t)tile * SD_TILE;
     const uint64_t* __restrict__ order = vt.gwords[0];
     const ushort4* __restrict__ rect = vt.rect;
     uint64_t* desc = vt.scan_desc;
@@ -266,7 +277,7 @@ scan_duplicate_kernel(const __grid_constant__ BatchTab tab) {
     ushort4 rc[SCAN_ITEMS];
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) {
-        const int64_t e = tile_base + i * SCAN_THREADS + threadIdx.x;
+        const int64_t e = tile_base + i * SD_T + threadIdx.x;
         g[i] = e < n ? (uint32_t)__ldg(order + e) : 0xffffffffu;
     }
 #pragma unroll
@@ -274,7 +285,7 @@ scan_duplicate_kernel(const __grid_constant__ BatchTab tab) {
         rc[i] = g[i] != 0xffffffffu ? __ldg(rect + g[i]) : make_ushort4(0, 0, 0, 0);
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) {
-        const int idx = i * SCAN_THREADS + threadIdx.x;
+        const int idx = i * SD_T + threadIdx.x;
         s_x[idx + (idx >> 5)] = (uint32_t)((rc[i].z - rc[i].x) * (rc[i].w - rc[i].y));
     }
     __syncthreads();
@@ -298,7 +309,7 @@ scan_duplicate_kernel(const __grid_constant__ BatchTab tab) {
     __syncthreads();
     uint32_t warp_off = 0, block_total = 0;
 #pragma unroll
-    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+    for (int w = 0; w < SD_T / 32; ++w) {
         const uint32_t t = s_warp[w];
         if (w < warp) warp_off += t;
         block_total += t;
@@ -345,9 +356,11 @@ scan_duplicate_kernel(const __grid_constant__ BatchTab tab) {
     __syncthreads();
     uint32_t* __restrict__ out = vt.point_offsets;
     uint64_t* __restrict__ words = vt.keys[0];
+    const uint32_t pt_first = pt_words ? s_excl / pt_words : 0u;   // partition tile of this CTA's first pair
+    uint32_t* __restrict__ matrix = vt.desc;
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) {
-        const int idx = i * SCAN_THREADS + threadIdx.x;
+        const int idx = i * SD_T + threadIdx.x;
         const uint32_t incl = s_x[idx + (idx >> 5)];
         if (tile_base + idx < n) out[tile_base + idx] = incl;
         const int x0 = rc[i].x, y0 = rc[i].y, x1 = rc[i].z, y1 = rc[i].w;
@@ -358,17 +371,56 @@ scan_duplicate_kernel(const __grid_constant__ BatchTab tab) {
             continue;
         }
         uint32_t o = incl - ntiles;
-        for (int ty = y0; ty < y1; ++ty) {
-            for (int tx = x0; tx < x1; ++tx) {
-                const uint32_t t = (uint32_t)(ty * gx + tx);
-                words[o++] = ((uint64_t)t << 32) | (uint64_t)g[i];
-                atomicAdd(&s_cnt[t], 1u);
+        if (pt_words) {
+            uint32_t pt = o / pt_words;
+            uint32_t next = (pt + 1u) * pt_words;        // first pair of the next partition tile
+            pt -= pt_first;
+            if (incl <= next && pt < (uint32_t)SD_NPT) {   // all pairs of the Gaussian in one counted partition tile
+                uint32_t* __restrict__ row = s_cnt + pt * T;
+                for (int ty = y0; ty < y1; ++ty) {
+                    for (int tx = x0; tx < x1; ++tx) {
+                        const uint32_t t = (uint32_t)(ty * gx + tx);
+                        words[o++] = ((uint64_t)t << 32) | (uint64_t)g[i];
+                        atomicAdd(&row[t], 1u);
+                    }
+                }
+            } else {
+                for (int ty = y0; ty < y1; ++ty) {
+                    for (int tx = x0; tx < x1; ++tx) {
+                        const uint32_t t = (uint32_t)(ty * gx + tx);
+                        if (o == next) ++pt, next += pt_words;
+                        words[o++] = ((uint64_t)t << 32) | (uint64_t)g[i];
+                        if (pt < (uint32_t)SD_NPT) atomicAdd(&s_cnt[pt * T + t], 1u);
+                        else atomicAdd(&matrix[(size_t)(pt_first + pt) * WIDE_BINS + t], 1u);
+                    }
+                }
+            }
+        } else {
+            for (int ty = y0; ty < y1; ++ty) {
+                for (int tx = x0; tx < x1; ++tx) {
+                    const uint32_t t = (uint32_t)(ty * gx + tx);
+                    words[o++] = ((uint64_t)t << 32) | (uint64_t)g[i];
+                    atomicAdd(&s_cnt[t], 1u);
+                }
             }
         }
     }
     __syncthreads();
+    if (pt_words) {   // flush the CTA's part of the count matrix; the per-tile totals are summed by partition_offsets_kernel
+        // rows this CTA's pairs can have reached: from its first pair's partition tile to its last pair's
+        const uint32_t last_pair = s_excl + block_total;   // one past
+        const int rows = min(SD_NPT, (int)((last_pair + pt_words - 1) / pt_words - pt_first));
+        for (int r = 0; r < rows; ++r) {
+            uint32_t* __restrict__ dst = matrix + (size_t)(pt_first + (uint32_t)r) * WIDE_BINS;
+            for (int t = threadIdx.x; t < T; t += SD_T) {
+                const uint32_t c = s_cnt[r * T + t];
+                if (c) atomicAdd(&dst[t], c);
+            }
+        }
+        return;
+    }
     // ---- flush: per-tile counts (and the digit histograms of the 8-bit passes, derived from them) -----------
-    for (int t = threadIdx.x; t < T; t += SCAN_THREADS) {
+    for (int t = threadIdx.x; t < T; t += SD_T) {
         const uint32_t c = s_cnt[t];
         if (c) {
             atomicAdd(&vt.tile_count[t], c);
@@ -379,7 +431,7 @@ scan_duplicate_kernel(const __grid_constant__ BatchTab tab) {
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < passes * 256; i += SCAN_THREADS) {
+    for (int i = threadIdx.x; i < passes * 256; i += SD_T) {
         const uint32_t c = s_hist[i];
         if (c) atomicAdd(&vt.hist[i], c);
     }
@@ -394,25 +446,38 @@ bool scan_duplicate_supported(const BatchTab& tab) {
     return on && tab.grid_x * tab.grid_y <= SD_MAX_TILES;
 }
 
+static int sd_threads() {   // B200SPLAT_SD_THREADS = 256 | 512
+    static const int t = [] {
+        const char* e = getenv("B200SPLAT_SD_THREADS");
+        return (e && atoi(e) == 512) ? 512 : 256;   // measured (headline, 4 views): 256 -> 1.2187, 512 -> 1.2244 ms per step
+    }();
+    return t;
+}
 cudaError_t launch_scan_duplicate(const BatchTab& tab, cudaStream_t st) {
     const int64_t n = tab.P;
     if (n <= 0) return cudaSuccess;
-    const int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    const int threads = sd_threads();
+    const int64_t tile = (int64_t)threads * SCAN_ITEMS;
+    const int64_t tiles = (n + tile - 1) / tile;
     const int T = tab.grid_x * tab.grid_y;
-    const size_t smem = ((size_t)SCAN_TILE + SCAN_TILE / 32 + (size_t)tab.digit_passes * 256 + T) * sizeof(uint32_t);
+    const size_t smem = ((size_t)tile + tile / 32 + (size_t)tab.digit_passes * 256 +
+                         (size_t)(tab.pt_words ? SD_NPT * T : T)) * sizeof(uint32_t);
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(scan_duplicate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(scan_duplicate_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(scan_duplicate_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr = smem;
     }
-    scan_duplicate_kernel<<<dim3((unsigned)tiles, tab.V), SCAN_THREADS, smem, st>>>(tab);
+    if (threads == 256) scan_duplicate_kernel<256><<<dim3((unsigned)tiles, tab.V), 256, smem, st>>>(tab);
+    else scan_duplicate_kernel<512><<<dim3((unsigned)tiles, tab.V), 512, smem, st>>>(tab);
     count_launch();
     return cudaGetLastError();
 }
 
 size_t scan_workspace_bytes(int64_t n) {
-    int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    int64_t tiles = (n + SCAN_TILE / 2 - 1) / (SCAN_TILE / 2);   // (the fused kernel may run with half-size tiles)
     return align_up(16 + (size_t)tiles * 8, 256);
 }
 
@@ -533,6 +598,20 @@ int sort_tiles_for(int64_t n) {   // tiles of the pipeline's (keys-only or pair)
     return (int)((n + tile - 1) / tile);
 }
 static int sort_tiles_pairs(int64_t n) { return (int)((n + SORT_TILE - 1) / SORT_TILE); }
+
+// words per partition tile when the look-back-free partition (K4d) applies: one wide pass, the fused kernel, the
+// count matrix of a CTA in shared memory.  B200SPLAT_DIRECT_PARTITION=0 selects the look-back kernel (A/B).
+int partition_direct_words(const BatchTab& tab) {
+    static const bool on = [] {
+        const char* e = getenv("B200SPLAT_DIRECT_PARTITION");
+        return !(e && e[0] == '0');
+    }();
+    if (!on || tab.digit_passes != 0 || !scan_duplicate_supported(tab)) return 0;
+    if (tab.grid_x * tab.grid_y > WIDE_BINS) return 0;
+    const int items = sort_items();
+    return SORT_THREADS * (items == 8 || items == 16 ? items : 24);
+}
+
 
 // Histogram of every digit place in one read of the keys (stand-alone sort only; the pipeline gets its
 // histograms from duplicateWithKeys).  hist: [passes][256] u32 (zeroed).
@@ -857,8 +936,6 @@ onesweep_pass_kernel(int shift, int bits, const __grid_constant__ SortTab tab) {
 // thread owns WIDE_DPT bins (bin = tid + k * 256, so descriptor rows are read coalesced), whose look-backs run
 // interleaved.  The global histogram of the digit is duplicateWithKeys' per-tile count.
 // --------------------------------------------------------------------------------------------
-constexpr int WIDE_BITS = 10;
-constexpr int WIDE_BINS = 1 << WIDE_BITS;
 constexpr int WIDE_DPT = WIDE_BINS / SORT_THREADS;
 template <int ITEMS>
 struct WideSmemT {
@@ -1037,11 +1114,232 @@ tile_partition_kernel(int n_bins, const __grid_constant__ SortTab tab) {
     }
 }
 
+// --------------------------------------------------------------------------------------------
+// K4d: the same stable partition WITHOUT a look-back.  What a tile of the onesweep pass asks its predecessors -- how
+// many words of each bin lie in front of it -- does not depend on the partition at all: scan + duplicateWithKeys emit
+// the words and know where each one lands, so they count them per (partition tile, image tile) on the way
+// (scan_duplicate_kernel, pt mode: the count matrix M[partition tile][1024] in the look-back descriptors' memory).
+// partition_offsets_kernel turns M into exclusive prefixes along the partition tiles (PO_CHUNKS chunks of rows, the last
+// CTA of a view chains the chunk totals and adds the bins' global starts; the per-tile totals it meets are
+// duplicateWithKeys' tile_count), and a tile of tile_partition_direct_kernel reads its two rows of offsets and never
+// waits for anybody.  In the look-back kernel 41 % of the instructions and a third of the stall samples were the
+// look-back: with 296 tiles resident and 4 x 4 descriptors per thread and round trip, the first wave alone walks for
+// ~25 us (profiles/r2_ncu_full_summary.md).
+// --------------------------------------------------------------------------------------------
+constexpr int PO_CHUNKS = 32;
+struct OffsetsView {
+    const uint32_t* n_ptr;       // live pair count
+    const uint32_t* overflow;
+    uint32_t* matrix;            // [tiles][1024] counts -> exclusive prefix inside the row's chunk
+    uint32_t* chunk_base;        // [PO_CHUNKS][1024] chunk totals -> first destination of the chunk's words of a bin
+    uint32_t* tile_count;        // [T] out: pairs per image tile
+    uint32_t* ticket;
+};
+struct OffsetsTab {
+    uint32_t capacity;
+    uint32_t pt_words;
+    OffsetsView v[MAX_VIEWS];
+};
+__device__ __forceinline__ void partition_rows(uint32_t n, uint32_t pt_words, int& tiles, int& rows_per_chunk) {
+    tiles = (int)((n + pt_words - 1) / pt_words);
+    rows_per_chunk = (tiles + PO_CHUNKS - 1) / PO_CHUNKS;
+}
+__global__ void __launch_bounds__(WIDE_BINS)
+partition_offsets_kernel(int n_bins, const __grid_constant__ OffsetsTab tab) {
+    const OffsetsView& ov = tab.v[blockIdx.y];
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_last;
+    const int bin = threadIdx.x, lane = bin & 31, warp = bin >> 5;
+    const bool overflow = *ov.overflow != 0u;
+    const uint32_t n = overflow ? 0u : min(*ov.n_ptr, tab.capacity);
+    int tiles, rpc;
+    partition_rows(n, tab.pt_words, tiles, rpc);
+    const int r0 = (int)blockIdx.x * rpc, r1 = min(r0 + rpc, tiles);
+    uint32_t run = 0;
+    constexpr int UN = 8;
+    for (int r = r0; r < r1; r += UN) {
+        uint32_t x[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) x[u] = (r + u < r1) ? ov.matrix[(size_t)(r + u) * WIDE_BINS + bin] : 0u;
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            if (r + u < r1) ov.matrix[(size_t)(r + u) * WIDE_BINS + bin] = run;
+            run += x[u];
+        }
+    }
+    __stcg(ov.chunk_base + (size_t)blockIdx.x * WIDE_BINS + bin, run);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ov.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // last CTA of the view: chunk totals -> exclusive prefix over the chunks, plus the bin's global start
+    uint32_t tot[PO_CHUNKS];
+    uint32_t total = 0;
+#pragma unroll
+    for (int c = 0; c < PO_CHUNKS; ++c) {
+        tot[c] = __ldcg(ov.chunk_base + (size_t)c * WIDE_BINS + bin);
+        total += tot[c];
+    }
+    if (bin < n_bins) ov.tile_count[bin] = total;
+    uint32_t inc = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t start = inc - total;
+    for (int w = 0; w < warp; ++w) start += s_warp[w];
+#pragma unroll
+    for (int c = 0; c < PO_CHUNKS; ++c) {
+        ov.chunk_base[(size_t)c * WIDE_BINS + bin] = start;
+        start += tot[c];
+    }
+}
+
+template <int ITEMS>
+struct DirectSmemT {
+    uint64_t keys[SORT_THREADS * ITEMS];
+    uint32_t warp_hist[SORT_WARPS][WIDE_BINS + 1];
+    uint32_t a[WIDE_BINS];   // bin total of this tile -> exclusive offset of the bin inside the tile
+    uint32_t b[WIDE_BINS];   // destination of the tile's first word of the bin, minus a
+    uint32_t s_l[SORT_WARPS];
+};
+template <int ITEMS>
+__global__ void __launch_bounds__(SORT_THREADS, 2)
+tile_partition_direct_kernel(const __grid_constant__ SortTab tab) {
+    constexpr int TILE = SORT_THREADS * ITEMS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DirectSmemT<ITEMS>& S = *reinterpret_cast<DirectSmemT<ITEMS>*>(smem_raw);
+    const SortView& sv = tab.v[blockIdx.y];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (*sv.overflow != 0u) return;
+    const uint32_t n = min(*sv.n_ptr, tab.capacity);
+    const uint32_t tile = blockIdx.x;
+    if ((int64_t)tile * TILE >= (int64_t)n) return;
+    int tiles, rpc;
+    partition_rows(n, (uint32_t)TILE, tiles, rpc);
+    const int64_t tile_base = (int64_t)tile * TILE;
+    const int valid = (int)min((int64_t)TILE, (int64_t)n - tile_base);
+    constexpr uint32_t mask = WIDE_BINS - 1;
+    const uint64_t* __restrict__ keys_in = sv.keys_in;
+    uint64_t key[ITEMS];
+    uint32_t rank[ITEMS];
+    const int wbase = warp * (32 * ITEMS) + lane;
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const int li = wbase + i * 32;
+        key[i] = (li < valid) ? __ldg(keys_in + tile_base + li) : ~0ull;
+    }
+    // the tile's offsets: its row of the matrix + its chunk's row (sv.desc = matrix, sv.hist_pass = chunk bases),
+    // copied asynchronously into S.b / S.a by the thread that will combine them after the ranking
+#pragma unroll
+    for (int k = 0; k < WIDE_DPT; ++k) {
+        const int d = tid + k * SORT_THREADS;
+        cpa4(&S.b[d], sv.desc + (size_t)tile * WIDE_BINS + d);
+        cpa4(&S.a[d], sv.hist_pass + (size_t)(tile / (uint32_t)rpc) * WIDE_BINS + d);
+    }
+    cpa_commit();
+    for (int i = tid; i < SORT_WARPS * (WIDE_BINS + 1); i += SORT_THREADS) (&S.warp_hist[0][0])[i] = 0;
+    __syncthreads();
+    // ---- warp-level stable ranking (as tile_partition_kernel) ---------------------------------------
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    {
+        uint32_t info[ITEMS];
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) info[i] = ballot_match<WIDE_BITS>((uint32_t)(key[i] >> 32) & mask);
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const uint32_t d = (uint32_t)(key[i] >> 32) & mask;
+            const uint32_t peers = info[i];
+            const int leader = __ffs(peers) - 1;
+            uint32_t pre = 0;
+            if (lane == leader) {
+                pre = S.warp_hist[warp][d];
+                S.warp_hist[warp][d] = pre + (uint32_t)__popc(peers);
+            }
+            rank[i] = pre;
+            info[i] = (uint32_t)leader | ((uint32_t)__popc(peers & lt_mask) << 8);
+            __syncwarp();
+        }
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i)
+            rank[i] = __shfl_sync(0xffffffffu, rank[i], (int)(info[i] & 31u)) + (info[i] >> 8);
+    }
+    __syncthreads();
+    // ---- per bin: exclusive prefix over the warps, tile total --------------------------------------
+    cpa_wait<0>();   // this thread's offset copies (it reads only what it copied itself)
+#pragma unroll
+    for (int k = 0; k < WIDE_DPT; ++k) {
+        const int d = tid + k * SORT_THREADS;
+        uint32_t bin_total = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; ++w) {
+            const uint32_t t = S.warp_hist[w][d];
+            S.warp_hist[w][d] = bin_total;
+            bin_total += t;
+        }
+        S.b[d] += S.a[d];
+        S.a[d] = bin_total;
+    }
+    __syncthreads();
+    // ---- exclusive scan of the tile's bin totals (thread t scans bins 4t..4t+3) ---------------------
+    {
+        uint32_t la[WIDE_DPT], sa = 0;
+#pragma unroll
+        for (int k = 0; k < WIDE_DPT; ++k) {
+            la[k] = sa;
+            sa += S.a[tid * WIDE_DPT + k];
+        }
+        uint32_t ia = sa;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t1 = __shfl_up_sync(0xffffffffu, ia, o);
+            if (lane >= o) ia += t1;
+        }
+        if (lane == 31) S.s_l[warp] = ia;
+        __syncthreads();
+        uint32_t oa = ia - sa;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; ++w)
+            if (w < warp) oa += S.s_l[w];
+#pragma unroll
+        for (int k = 0; k < WIDE_DPT; ++k) {
+            const int d = tid * WIDE_DPT + k;
+            const uint32_t ex = oa + la[k];
+            S.a[d] = ex;
+            S.b[d] -= ex;     // destination of local position p of bin d: b[d] + p
+        }
+    }
+    __syncthreads();
+    // ---- scatter through shared memory, coalesced write-out -----------------------------------------
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const uint32_t d = (uint32_t)(key[i] >> 32) & mask;
+        S.keys[rank[i] + S.a[d] + S.warp_hist[warp][d]] = key[i];
+    }
+    __syncthreads();
+    uint64_t* __restrict__ keys_out = sv.keys_out;
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const int p = i * SORT_THREADS + tid;
+        if (p < valid) {
+            const uint64_t k = S.keys[p];
+            keys_out[S.b[(uint32_t)(k >> 32) & mask] + (uint32_t)p] = k;
+        }
+    }
+}
+
 // workspace: hist [MAX_PASSES][256] u32 | tickets [64] u32 | desc [passes][tiles][256] u32
 static int64_t sort_tiles_max(int64_t n) { return (n + 2047) / 2048; }
 size_t sort_workspace_bytes(int64_t n) {
     const int64_t tiles = sort_tiles_max(n < 1 ? 1 : n);
-    return align_up((size_t)MAX_PASSES * RADIX * 4 + 256 + (size_t)MAX_PASSES * tiles * RADIX * 4, 256);
+    // (+ the chunk bases of the look-back-free partition behind its count matrix, which lives in the descriptors)
+    return align_up((size_t)MAX_PASSES * RADIX * 4 + 256 + (size_t)MAX_PASSES * tiles * RADIX * 4 +
+                    (size_t)PO_CHUNKS_WORDS * 4, 256);
 }
 size_t sort_workspace_zero_bytes(int64_t capacity, int end_bit) {
     const int passes = (end_bit + RADIX_BITS - 1) / RADIX_BITS;
@@ -1100,6 +1398,15 @@ static cudaError_t ensure_sort_attr() {
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(tile_partition_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)sizeof(WideSmemT<24>));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(tile_partition_direct_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(DirectSmemT<8>));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(tile_partition_direct_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(DirectSmemT<16>));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(tile_partition_direct_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(DirectSmemT<24>));
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -1210,6 +1517,24 @@ cudaError_t launch_gaussian_sort(const BatchTab& tab, cudaStream_t st, bool clea
     return cudaSuccess;   // 4 passes: back in gwords[0]
 }
 
+// Look-back-free partition only (tab.pt_words > 0): the offsets of every partition tile and the per-tile pair counts
+// (tile_count: what the tile ranges are scanned from) out of the count matrix of scan + duplicateWithKeys.
+cudaError_t launch_partition_offsets(const BatchTab& tab, cudaStream_t st) {
+    if (tab.P <= 0 || tab.capacity == 0 || tab.pt_words <= 0) return cudaSuccess;
+    const int tiles = sort_tiles_for(tab.capacity);
+    OffsetsTab ot;
+    ot.capacity = tab.capacity;
+    ot.pt_words = (uint32_t)tab.pt_words;
+    for (int v = 0; v < tab.V; ++v) {
+        const ViewTab& vt = tab.v[v];
+        ot.v[v] = OffsetsView{vt.point_offsets + (tab.P - 1), vt.status + STATUS_OVERFLOW, vt.desc,
+                              vt.desc + (size_t)tiles * WIDE_BINS, vt.tile_count, vt.tickets + 1};
+    }
+    partition_offsets_kernel<<<dim3(PO_CHUNKS, tab.V), WIDE_BINS, 0, st>>>(tab.grid_x * tab.grid_y, ot);
+    count_launch();
+    return cudaGetLastError();
+}
+
 // Stable sort of every view's pair words (tile << 32 | index) on the tile bits [32, 32 + end_bit); histograms
 // come from duplicateWithKeys, the pair count from the device.  Result in keys[passes & 1].
 cudaError_t launch_sort_batch(const BatchTab& tab, cudaStream_t st) {
@@ -1219,6 +1544,29 @@ cudaError_t launch_sort_batch(const BatchTab& tab, cudaStream_t st) {
     const int tiles = sort_tiles_for(tab.capacity);
     cudaError_t e = ensure_sort_attr();
     if (e != cudaSuccess) return e;
+    if (passes == 0 && tab.pt_words > 0) {   // look-back-free partition (K4d): offsets from the count matrix
+        SortTab t;                           // (launch_partition_offsets has run: it also produces tile_count)
+        t.capacity = tab.capacity;
+        for (int v = 0; v < tab.V; ++v) {
+            const ViewTab& vt = tab.v[v];
+            uint32_t* chunk_base = vt.desc + (size_t)tiles * WIDE_BINS;
+            t.v[v] = SortView{vt.point_offsets + (tab.P - 1), 0u, vt.status + STATUS_OVERFLOW, vt.keys[0], nullptr,
+                              vt.keys[1], nullptr, chunk_base, vt.tickets, vt.desc};
+        }
+        const dim3 grid(tiles, tab.V);
+        switch (tab.pt_words / SORT_THREADS) {
+            case 8:
+                tile_partition_direct_kernel<8><<<grid, SORT_THREADS, sizeof(DirectSmemT<8>), st>>>(t);
+                break;
+            case 16:
+                tile_partition_direct_kernel<16><<<grid, SORT_THREADS, sizeof(DirectSmemT<16>), st>>>(t);
+                break;
+            default:
+                tile_partition_direct_kernel<24><<<grid, SORT_THREADS, sizeof(DirectSmemT<24>), st>>>(t);
+        }
+        count_launch();
+        return cudaGetLastError();
+    }
     if (passes == 0) {   // one wide pass: bins = tiles, global histogram = the per-tile counts
         SortTab t;
         t.capacity = tab.capacity;
