@@ -168,7 +168,9 @@ typedef struct b200splat_backward_args {
     b200splat_stream stream;
     /* extra feature channels of the forward (same extra_features / n_extra): dL_dout_extra (n_extra,H,W) or NULL,
      * dL_dextra (P,n_extra) written (added when accumulate != 0); the geometry gradients include the extra
-     * channels' contribution through alpha */
+     * channels' contribution through alpha -- except dL_dmeans2D and stat_grad_accum, which see the colour / depth /
+     * alpha terms only: the reference renders extra channels with a second rasterizer call whose means2D is a
+     * gradient-free zeros tensor (renderer/diff_gaussian_rasterizer_shading.py:177-187) */
     const float* extra_features;
     int32_t n_extra;
     const float* dL_dout_extra;

@@ -60,7 +60,10 @@ def _oracle_two_passes(sc, s, extra, grads, g_extra):
                                               None, s0)
     g2 = O.rasterize_backward((sc.means3D, None, None, ex3, sc.opacities, sc.scales, sc.rotations, None), s0, pre2,
                               binned2, out2, ge3, z1, z1)
-    total = {k: g1[k] + g2[k] for k in ("means3D", "means2D", "opacities", "scales", "rotations")}
+    total = {k: g1[k] + g2[k] for k in ("means3D", "opacities", "scales", "rotations")}
+    # the reference's second call gets a gradient-free zeros tensor as means2D
+    # (renderer/diff_gaussian_rasterizer_shading.py:177-187): viewspace gradients come from the colour pass alone
+    total["means2D"] = g1["means2D"]
     total["shs"] = g1["shs"]
     total["extra"] = g2["colors_precomp"][:, :C]
     return dict(out=out1, pre=pre, binned=binned, extra=out2["color"][:C], grads=total)

@@ -24,10 +24,11 @@ the reference's renderer files is mirrored:
 
 Differences a caller can observe, all deliberate: (1) ``viewspace_points[v]`` is a small stand-in whose ``.grad`` is
 view v's slice of ONE (V,P,3) gradient tensor -- enough for the unchanged ``GaussianBaseModel.update_states``
-(geometry/gaussian_base.py:815-819, :845-851), which only reads ``.grad[filter, :2]``; (2) with ``pred_normal`` the
-normals' gradient also reaches ``means2D`` (the reference feeds its second pass a gradient-free zeros tensor,
-renderer/diff_gaussian_rasterizer_shading.py:180); (3) the material's random shading mode is drawn per view with the
-same ``random.random()`` call sequence as the reference's per-view loop.
+(geometry/gaussian_base.py:815-819, :845-851), which only reads ``.grad[filter, :2]``; (2) the material's random
+shading mode is drawn per view with the same ``random.random()`` call sequence as the reference's per-view loop.
+With ``pred_normal`` the normals ride along as extra channels of the colour pass; as in the reference (whose second pass
+gets a gradient-free zeros tensor as means2D, renderer/diff_gaussian_rasterizer_shading.py:180) their gradient reaches
+``means3D`` but not ``viewspace_points`` / the densification statistic (the library keeps the two apart, render.cu K7).
 """
 from __future__ import annotations
 

@@ -432,6 +432,10 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
         }
         // ---- mean2D (NDC) and depth -------------------------------------------------------------
         const float gnx = g_px * 0.5f * (float)tab.W, gny = g_py * 0.5f * (float)tab.H;
+        // with extra channels the record's spare floats carry the mean gradient WITHOUT the extra channels' terms: that
+        // is what the reference's means2D sees (its second rasterizer call gets a gradient-free means2D)
+        const float gnx2 = tab.n_extra > 0 ? g2.z * 0.5f * (float)tab.W : gnx;
+        const float gny2 = tab.n_extra > 0 ? g2.w * 0.5f * (float)tab.H : gny;
         {
             const float hx = mP[0] * x + mP[4] * y + mP[8] * z + mP[12];
             const float hy = mP[1] * x + mP[5] * y + mP[9] * z + mP[13];
@@ -446,12 +450,12 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
             dmz += mV[10] * g_depth;
         }
         if (vt.dL_dmeans2D) {
-            put<ACC>(vt.dL_dmeans2D + 3 * idx, gnx);
-            put<ACC>(vt.dL_dmeans2D + 3 * idx + 1, gny);
+            put<ACC>(vt.dL_dmeans2D + 3 * idx, gnx2);
+            put<ACC>(vt.dL_dmeans2D + 3 * idx + 1, gny2);
             if (!ACC) vt.dL_dmeans2D[3 * idx + 2] = 0.f;
         }
         // densification statistics of this view (geometry/gaussian_base.py:815-819)
-        st_norm += sqrtf(gnx * gnx + gny * gny);
+        st_norm += sqrtf(gnx2 * gnx2 + gny2 * gny2);
         dop += g_op;
         // ---- colour -----------------------------------------------------------------------------
         if (DEG >= 0) {

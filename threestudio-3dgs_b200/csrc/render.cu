@@ -524,6 +524,8 @@ render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
     // per-survivor results of phase 1 (registers reused from group to group)
     float a_h[ILP], og_h[ILP], G_h[ILP], inv1m[ILP], ddx[ILP], ddy[ILP], cA[ILP], cB[ILP], cC[ILP], dot[ILP];
     float4 ex[ILP];
+    float dot0[ILP];          // EXT: dot without the extra channels' terms
+    float S0 = S;             // EXT: the suffix sum of dot0
     uint32_t jpack = 0, anyhit = 0;   // slots of the group's survivors (one byte each); which of them hit some pixel
 
     __syncwarp();
@@ -587,6 +589,7 @@ render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
                 float d = fmaf(gD, q1.z, gA);
                 d = fmaf(gC2, q2.y, d), d = fmaf(gC1, q2.x, d), d = fmaf(gC0, q1.w, d);
                 if (EXT) {
+                    dot0[k] = d;   // without the extra channels: what reaches dL/dmeans2D (see phase 2)
                     ex[k] = s_ext[st][j];
                     d = fmaf(gE[0], ex[k].x, d), d = fmaf(gE[1], ex[k].y, d);
                     d = fmaf(gE[2], ex[k].z, d), d = fmaf(gE[3], ex[k].w, d);
@@ -622,8 +625,20 @@ render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
                     row[0] = make_float4(fmaf(cA[k], qxy.x, cB[k] * qxy.y), fmaf(cC[k], qxy.y, cB[k] * qxy.x), dia.x,
                                          qxy.x * ddy[k]);
                     row[1] = make_float4(dia.y, G_h[k] * dL_da, wc.x, wc.y);
-                    *reinterpret_cast<float2*>(row + 2) = wd;
-                    if (EXT) row[3] = make_float4(w * gE[0], w * gE[1], w * gE[2], w * gE[3]);
+                    if (EXT) {
+                        // The reference renders the extra channels with a second rasterizer call whose means2D is a
+                        // gradient-free zeros tensor (renderer/diff_gaussian_rasterizer_shading.py:177-187): the extra
+                        // channels reach dL/dmeans3D but NOT dL/dmeans2D, the densification statistic
+                        // (geometry/gaussian_base.py:815-819).  The mean gradient without their terms rides in the
+                        // record's two spare floats; preprocess backward writes THAT to dL/dmeans2D / grad_accum.
+                        const float dL_da0 = fmaf(dot0[k], T, -(S0 * inv1m[k]));
+                        S0 = fmaf(dot0[k], w, S0);
+                        const float q0x = -og_h[k] * dL_da0 * ddx[k], q0y = -og_h[k] * dL_da0 * ddy[k];
+                        row[2] = make_float4(wd.x, wd.y, fmaf(cA[k], q0x, cB[k] * q0y), fmaf(cC[k], q0y, cB[k] * q0x));
+                        row[3] = make_float4(w * gE[0], w * gE[1], w * gE[2], w * gE[3]);
+                    } else {
+                        *reinterpret_cast<float2*>(row + 2) = wd;
+                    }
                 }
                 __syncwarp();
             }
