@@ -52,6 +52,9 @@ def parse_args():
                          "8 GPUs NCCL 13952/12587/12252 renders/s -- preprocess backward is HBM-bound and so is the "
                          "exchange's local side: overlapped they slow each other down by more than the overlap returns)")
     ap.add_argument("--eager", action="store_true", help="launch the step from Python every time (no CUDA graph)")
+    ap.add_argument("--dense-exchange", action="store_true",
+                    help="multi-GPU: exchange every row of the packed gradients (default: rows of the rotation / SH "
+                         "fields travel only when some rank has a gradient for the Gaussian)")
     ap.add_argument("--quick", action="store_true",
                     help="only the resident timed region (no e2e, no per-kernel table, no aux / cpu / configs legs): "
                          "for exchange experiments at N > 1")
@@ -459,12 +462,14 @@ def main():
     # multi-GPU: the packed gradient buffer lives in CUDA-IPC memory mapped by all ranks and is all-reduced in
     # place by one kernel per rank over NVLink peer memory (csrc/p2p.cu); --allreduce nccl uses NCCL instead
     p2p, allreduce_mode = None, ("none" if world == 1 else "nccl")
+    # row-sparse exchange (own kernels): room for the live map behind max_radii; --dense-exchange leaves it out
+    n_tail = 0 if args.dense_exchange else batched.PackedGrads.live_floats(P)
     # auto (measured on this pool, profiles/r2_scaling.md): 2 GPUs -> peer-memory kernel (a rank's own half never
     # crosses NVLink), 3..8 GPUs -> multicast kernel (in-switch reduction), NCCL only as the fall-back
     if world > 1 and (args.allreduce == "mc" or (args.allreduce == "auto" and world > 2)):
         try:
             p2p = bdist.MulticastAllReduce(batched.PackedGrads.floats(P, M), batched.PackedGrads.padded(P), dev,
-                                           device_epoch=True)
+                                           device_epoch=True, n_tail=n_tail)
             allreduce_mode = "nvswitch_multicast_kernel"
         except Exception as exc:
             print(f"bench: multicast all-reduce unavailable ({exc!r})", file=sys.stderr)
@@ -472,13 +477,17 @@ def main():
     use_p2p = p2p is None and (args.allreduce == "p2p" or (args.allreduce in ("auto", "mc") and world <= 4))
     if world > 1 and use_p2p:
         try:
-            p2p = bdist.P2PAllReduce(batched.PackedGrads.floats(P, M), batched.PackedGrads.padded(P), dev, device_epoch=True)
+            p2p = bdist.P2PAllReduce(batched.PackedGrads.floats(P, M), batched.PackedGrads.padded(P), dev, device_epoch=True,
+                                     n_tail=n_tail)
             allreduce_mode = "p2p_nvlink_kernel"
         except Exception as exc:
             print(f"bench: P2P all-reduce unavailable ({exc!r}); using NCCL", file=sys.stderr)
             p2p = None
     renderer = batched.BatchRenderer(P, M, H, W, dev, views=V, packed_storage=None if p2p is None else p2p.buffer)
     packed = renderer.packed
+    if p2p is not None and packed.live_map is not None:
+        p2p.live_offset = packed.live_offset_bytes
+        allreduce_mode += "+row_sparse"
     renderer.calibrate(cams, means3D, shs, None, opac, scales, rots)
 
     # the step's launches are recorded once into a CUDA graph (the C ABI never synchronises in the batched path);

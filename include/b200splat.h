@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define B200SPLAT_ABI_VERSION 6
+#define B200SPLAT_ABI_VERSION 7
 
 #define B200SPLAT_OK 0
 #define B200SPLAT_ERR_INVALID -1   /* bad argument                                  */
@@ -279,6 +279,10 @@ typedef struct b200splat_batch_backward_args {
     int32_t n_extra;
     const float* const* dL_dout_extra;    /* NULL or V entries, any may be NULL */
     float* dL_dextra;                     /* (P,n_extra), summed over the views */
+    /* optional (ABI 7): one byte per Gaussian of [g_begin, g_end), 1 if the Gaussian received a gradient in at least
+     * one view of this call (its parameter-gradient rows can be non-zero), else 0 (its rows are exactly zero) -- the
+     * live map of the row-sparse exchange, b200splat_p2p_args.seg_row_floats */
+    uint8_t* live_map;
 } b200splat_batch_backward_args;
 
 int b200splat_backward_batched(const b200splat_batch_backward_args* args);
@@ -475,6 +479,15 @@ typedef struct b200splat_p2p_args {
     int32_t seg_op[B200SPLAT_P2P_MAX_SEGMENTS];     /* B200SPLAT_P2P_SUM | B200SPLAT_P2P_MAX */
     uint32_t epoch;
     b200splat_stream stream;
+    /* Row-sparse SUM segments (ABI 7).  seg_row_floats[i] > 0 (a multiple of 4): segment i is an array of rows of that
+     * many floats, row j belongs to index seg_row0[i] + j (a Gaussian), and a row is exchanged only if the byte of its
+     * index in the LIVE MAP is non-zero on at least one rank; every other row must be all zeros on every rank (it is
+     * left alone).  The live map is one byte per index at byte offset live_offset of every rank's buffer (outside the
+     * exchanged segments); b200splat_backward_batched writes it (live_map).  seg_row0 is a multiple of 4.
+     * All zero: every segment is dense. */
+    int32_t seg_row_floats[B200SPLAT_P2P_MAX_SEGMENTS];
+    int64_t seg_row0[B200SPLAT_P2P_MAX_SEGMENTS];
+    int64_t live_offset;
 } b200splat_p2p_args;
 int b200splat_p2p_alloc(size_t bytes, void** ptr, void* handle_out);
 int b200splat_p2p_open(const void* handle, void** ptr);
@@ -502,6 +515,11 @@ typedef struct b200splat_mc_args {
     int32_t seg_op[B200SPLAT_P2P_MAX_SEGMENTS];     /* B200SPLAT_P2P_SUM | B200SPLAT_P2P_MAX */
     uint32_t epoch;
     b200splat_stream stream;
+    /* row-sparse SUM segments, as in b200splat_p2p_args (the union of the ranks' live maps is read through the
+     * multicast address: one multimem.ld_reduce.add.u32 sums four indices' bytes of all ranks) */
+    int32_t seg_row_floats[B200SPLAT_P2P_MAX_SEGMENTS];
+    int64_t seg_row0[B200SPLAT_P2P_MAX_SEGMENTS];
+    int64_t live_offset;
 } b200splat_mc_args;
 int b200splat_mc_allreduce(const b200splat_mc_args* args);
 

@@ -36,7 +36,16 @@ def test_packed_layout():
     assert all(off % 4 == 0 for _, off, _ in pk2.fields)
     assert pk2.views["rotations"].shape == (10, 4) and pk2.views["rotations"].is_contiguous()
     segs = pk2.segments(4)                      # Gaussians [4, P): the tail range covers the (zero) padding
-    assert all(o % 4 == 0 and c % 4 == 0 for o, c, _ in segs) and segs[-1] == (pk2.buffer.numel() + 4, 8, 1)
+    assert all(sg[0] % 4 == 0 and sg[1] % 4 == 0 for sg in segs) and segs[-1][:3] == (pk2.buffer.numel() + 4, 8, 1)
+    assert all(sg[3] == 0 for sg in segs)       # no live map (no shared exchange storage): every range is dense
+    # with exchange storage that has room for the live map, the float4-granular per-Gaussian fields become row-sparse
+    n = batched.PackedGrads.floats(10, 16) + 12 + batched.PackedGrads.live_floats(10)
+    pk3 = batched.PackedGrads(10, 16, "cpu", storage=torch.zeros(n))
+    assert pk3.live_map is not None and pk3.live_map.numel() == 12 and pk3.live_map.dtype == torch.uint8
+    assert pk3.live_offset_bytes == (batched.PackedGrads.floats(10, 16) + 12) * 4
+    sp = {name: sg for (name, _, _), sg in zip(pk3.fields, pk3.segments(4))}
+    assert sp["rotations"][3:] == (4, 4) and sp["shs"][3:] == (48, 4)
+    assert all(sp[k][3] == 0 for k in ("means3D", "scales", "opacities", "grad_accum", "denom"))
     pk2.views["means3D"].fill_(1.0)
     assert float(pk2.buffer.sum()) == 30.0      # the padding Gaussians stay zero
 

@@ -386,7 +386,7 @@ def test_batched_entry_points_match_per_view_path():
     assert ranges[0][0] == 0 and ranges[-1][1] == P and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
     assert rel_err(br.packed.buffer, first) < 1e-5
     segs = br.packed.segments(ranges[1][0], ranges[1][1])
-    assert len(segs) == len(br.packed.fields) + 1 and all(o % 4 == 0 and c % 4 == 0 for o, c, _ in segs)
+    assert len(segs) == len(br.packed.fields) + 1 and all(sg[0] % 4 == 0 and sg[1] % 4 == 0 for sg in segs)
     # sorted keys / ranges of a batched view are those of the single-view call
     st_b = ws.states(sh.shape[1])[1]
     vb = ops.forward_views(cams[1], st_b)
@@ -783,7 +783,7 @@ def test_odd_gaussian_counts_through_the_packed_paths(P):
     br.step_tail(cams, m3, sh, None, op, scl, rot, lambda g0, g1: seen.append(br.packed.segments(g0, g1)), chunks=3)
     torch.cuda.synchronize()
     assert rel_err(br.packed.buffer, first) < 1e-5
-    assert all(o % 4 == 0 and c % 4 == 0 for segs in seen for o, c, _ in segs)
+    assert all(sg[0] % 4 == 0 and sg[1] % 4 == 0 for segs in seen for sg in segs)
     # the padding Gaussians of every field stay zero (they are summed by the exchange)
     for name, off, w in br.packed.fields:
         assert float(br.packed.buffer[off + w * P: off + w * br.packed.P4].abs().sum()) == 0.0, name

@@ -13,7 +13,7 @@ from pathlib import Path
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("B200SPLAT_LIB", _HERE / "libb200splat.so"))
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_VIEWS = 8
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
@@ -105,6 +105,7 @@ class BatchBackwardArgs(C.Structure):
         ("stat_grad_accum", C.c_void_p), ("stat_denom", C.c_void_p), ("stat_max_radii", C.c_void_p),
         ("stream", C.c_void_p),
         ("extra_features", C.c_void_p), ("n_extra", C.c_int32), ("dL_dout_extra", PP), ("dL_dextra", C.c_void_p),
+        ("live_map", C.c_void_p),
     ]
 
 
@@ -136,13 +137,15 @@ class AdamArgs(C.Structure):
 class P2PArgs(C.Structure):
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("bufs", C.c_void_p * 8), ("signals", C.c_void_p * 8),
                 ("n_segments", C.c_int32), ("seg_offset", C.c_int64 * 16), ("seg_count", C.c_int64 * 16),
-                ("seg_op", C.c_int32 * 16), ("epoch", C.c_uint32), ("stream", C.c_void_p)]
+                ("seg_op", C.c_int32 * 16), ("epoch", C.c_uint32), ("stream", C.c_void_p),
+                ("seg_row_floats", C.c_int32 * 16), ("seg_row0", C.c_int64 * 16), ("live_offset", C.c_int64)]
 
 
 class MCArgs(C.Structure):
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("mc_buffer", C.c_void_p), ("signals", C.c_void_p * 8),
                 ("n_segments", C.c_int32), ("seg_offset", C.c_int64 * 16), ("seg_count", C.c_int64 * 16),
-                ("seg_op", C.c_int32 * 16), ("epoch", C.c_uint32), ("stream", C.c_void_p)]
+                ("seg_op", C.c_int32 * 16), ("epoch", C.c_uint32), ("stream", C.c_void_p),
+                ("seg_row_floats", C.c_int32 * 16), ("seg_row0", C.c_int64 * 16), ("live_offset", C.c_int64)]
 
 
 P2P_HANDLE_BYTES, P2P_SIGNAL_BYTES = 64, 256

@@ -41,6 +41,11 @@ class PackedGrads:
         return (P + 3) // 4 * 4
 
     @staticmethod
+    def live_floats(P: int) -> int:
+        """Floats behind max_radii that hold the live map of the row-sparse exchange (one byte per Gaussian)."""
+        return PackedGrads.padded(P) // 4
+
+    @staticmethod
     def floats(P: int, M: int, color_mode: str = "shs") -> int:
         """Floats of the SUM segment (the MAX segment, max_radii, is padded(P) more)."""
         return (13 + (3 * M if color_mode == "shs" else 3)) * PackedGrads.padded(P)
@@ -73,6 +78,15 @@ class PackedGrads:
         self._max_all = storage[total:total + P4] if storage is not None else \
             torch.zeros(P4, dtype=torch.float32, device=device)
         self.max_radii = self._max_all[:P]
+        # live map (shared exchange storage with room behind max_radii only): preprocess backward's scan writes one
+        # byte per Gaussian, 1 = it received a gradient on this rank; the exchange kernels move only the rows of the
+        # float4-granular per-Gaussian fields (rotations, SH) that are live on some rank (include/b200splat.h ABI 7)
+        self.live_map, self.live_offset_bytes = None, 0
+        if storage is not None and storage.numel() >= total + P4 + P4 // 4:
+            lm = storage[total + P4:total + P4 + P4 // 4]
+            lm.zero_()
+            self.live_map = lm.view(torch.uint8)
+            self.live_offset_bytes = (total + P4) * 4
         self.means2D_scratch = torch.empty(P, 3, dtype=torch.float32, device=device)
 
     @property
@@ -80,15 +94,18 @@ class PackedGrads:
         return self.buffer.numel() * 4
 
     def segments(self, g0: int = 0, g1: Optional[int] = None):
-        """(offset, count, op) float ranges of the exchange storage that hold Gaussians [g0, g1): one SUM range per
-        field of the packed buffer plus the MAX range of max_radii (which sits right behind the buffer when the
-        storage is shared).  op: 0 = sum, 1 = max.  g0 must be a multiple of 4; a range that ends at P also covers
+        """(offset, count, op, row_floats, row0) float ranges of the exchange storage that hold Gaussians [g0, g1): one
+        SUM range per field of the packed buffer plus the MAX range of max_radii (which sits right behind the buffer
+        when the storage is shared).  op: 0 = sum, 1 = max.  row_floats > 0: the range is row-sparse (rows of that many
+        floats, the first one is Gaussian row0; only rows live on some rank are exchanged).  g0 must be a multiple of 4; a range that ends at P also covers
         the field's (zero) padding, so offsets and counts are always multiples of 4 floats."""
         g1 = self.P if g1 is None else g1
         assert g0 % 4 == 0 and (g1 % 4 == 0 or g1 == self.P)
         e1 = self.P4 if g1 == self.P else g1
-        segs = [(off + w * g0, w * (e1 - g0), 0) for _, off, w in self.fields]
-        segs.append((self.buffer.numel() + g0, e1 - g0, 1))
+        sparse = lambda name, w: w if (self.live_map is not None and w % 4 == 0 and
+                                       name not in ("grad_accum", "denom")) else 0
+        segs = [(off + w * g0, w * (e1 - g0), 0, sparse(name, w), g0) for name, off, w in self.fields]
+        segs.append((self.buffer.numel() + g0, e1 - g0, 1, 0, 0))
         return segs
 
     def zero_stats_(self):
@@ -214,7 +231,8 @@ def forward_batched(ws: BatchWorkspace, cams: Sequence[ops.Cam], means3D, shs, c
 def backward_batched(ws: BatchWorkspace, cams: Sequence[ops.Cam], means3D, shs, colors_precomp, opacities, scales,
                      rotations, pixel_grads, out: Dict[str, torch.Tensor], accumulate: bool = False,
                      stats=None, means2D_out: Optional[Sequence[Optional[torch.Tensor]]] = None,
-                     phase: int = 0, g_range: Optional[tuple] = None, extra_features=None, extra_grads=None):
+                     phase: int = 0, g_range: Optional[tuple] = None, extra_features=None, extra_grads=None,
+                     live_map: Optional[torch.Tensor] = None):
     """phase 0: whole backward; 1: render backward only; 2: preprocess backward only, Gaussians g_range=(g0, g1).
     extra_features (P,C') + extra_grads (list of V (C',H,W) tensors or None): out["extra_features"] receives
     dL/dextra_features summed over the views."""
@@ -251,6 +269,8 @@ def backward_batched(ws: BatchWorkspace, cams: Sequence[ops.Cam], means3D, shs, 
         eg = _parr([ops._ptr(t) for t in (extra_grads or [None] * V)])
         a.extra_features, a.n_extra = extra_features.data_ptr(), n_extra
         a.dL_dout_extra, a.dL_dextra = eg, out["extra_features"].data_ptr()
+    if live_map is not None:
+        a.live_map = live_map.data_ptr()
     a.scratch_clean = 1   # ws.scratch is zero on entry; the library leaves it zero (it re-zeroes what it consumed)
     try:
         with torch.cuda.device(ws.device):
@@ -308,7 +328,7 @@ class BatchRenderer:
                 pg = pixel_grads[i + v]
                 pgs.append(pg(ws.color[v], ws.depth[v], ws.alpha[v]) if callable(pg) else pg)
             backward_batched(ws, cs, means3D, shs, colors_precomp, opacities, scales, rotations, pgs, out,
-                             accumulate=ci > 0, stats=stats)
+                             accumulate=ci > 0, stats=stats, live_map=pk.live_map)
             i += n
 
     def step_head(self, cams, means3D, shs, colors_precomp, opacities, scales, rotations, pixel_grads):
@@ -342,7 +362,7 @@ class BatchRenderer:
             g1 = min(P, g0 + step)
             backward_batched(ws, cams, means3D, shs, colors_precomp, opacities, scales, rotations, none_pg,
                              pk.grads(), stats=(pk.views["grad_accum"], pk.views["denom"], pk.max_radii),
-                             phase=2, g_range=(g0, g1))
+                             phase=2, g_range=(g0, g1), live_map=pk.live_map)
             ev = self._events[c % len(self._events)]
             ev.record(main)
             side.wait_event(ev)

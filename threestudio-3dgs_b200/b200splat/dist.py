@@ -62,9 +62,11 @@ class P2PAllReduce:
     it (``PackedGrads(..., storage=ar.buffer)``) and call ``ar()`` after the backward.  One process per GPU of
     ONE box; the handles travel through ``torch.distributed`` (any backend)."""
 
-    def __init__(self, n_sum: int, n_max: int, device, group=None, device_epoch: bool = False):
+    def __init__(self, n_sum: int, n_max: int, device, group=None, device_epoch: bool = False, n_tail: int = 0):
         """device_epoch: the kernel keeps the call counter in the rank's signal words (epoch argument 0), so a call can
-        be captured in a CUDA graph and replayed; all ranks must choose the same mode."""
+        be captured in a CUDA graph and replayed; all ranks must choose the same mode.  n_tail: floats allocated behind
+        the MAX part that are never exchanged (``PackedGrads`` keeps the row-sparse exchange's live map there;
+        ``live_offset`` then tells the kernel where it is)."""
         import ctypes as C
         from . import _lib
         self._lib, self._C = _lib, C
@@ -73,6 +75,7 @@ class P2PAllReduce:
         assert self.world <= 8, "one NVSwitch box: at most 8 ranks"
         self.n_sum, self.n_max, self.device, self.epoch = n_sum, n_max, torch.device(device), 0
         self.device_epoch = device_epoch
+        self.n_tail, self.live_offset = int(n_tail), 0
         lib = _lib.lib
         # every step below is collective-safe: a rank that fails still takes part in the exchange of the status, so
         # all ranks raise together instead of some waiting in a collective for a peer that already gave up
@@ -83,7 +86,7 @@ class P2PAllReduce:
             buf, sig = C.c_void_p(), C.c_void_p()
             hb, hs = C.create_string_buffer(_lib.P2P_HANDLE_BYTES), C.create_string_buffer(_lib.P2P_HANDLE_BYTES)
             try:
-                _lib.check(lib.b200splat_p2p_alloc((n_sum + n_max) * 4, C.byref(buf), hb), "b200splat_p2p_alloc")
+                _lib.check(lib.b200splat_p2p_alloc((n_sum + n_max + n_tail) * 4, C.byref(buf), hb), "b200splat_p2p_alloc")
                 _lib.check(lib.b200splat_p2p_alloc(_lib.P2P_SIGNAL_BYTES, C.byref(sig), hs), "b200splat_p2p_alloc")
                 self._own = (buf.value, sig.value)
             except Exception as exc:
@@ -111,7 +114,7 @@ class P2PAllReduce:
             self.buffer = None
             self._release()
             raise RuntimeError("P2PAllReduce setup failed (" + "; ".join(bad) + ")")
-        self.buffer = torch.as_tensor(_RawCudaArray(self._own[0], n_sum + n_max, "<f4"), device=self.device)
+        self.buffer = torch.as_tensor(_RawCudaArray(self._own[0], n_sum + n_max + n_tail, "<f4"), device=self.device)
         dist.barrier(group=group)   # every rank has mapped every peer before the first exchange
 
     def __call__(self, segments=None):
@@ -126,8 +129,11 @@ class P2PAllReduce:
         self.epoch += 1
         a = _lib.P2PArgs()
         a.rank, a.world, a.epoch, a.n_segments = self.rank, self.world, 0 if self.device_epoch else self.epoch, len(segments)
-        for i, (off, cnt, op) in enumerate(segments):
-            a.seg_offset[i], a.seg_count[i], a.seg_op[i] = int(off), int(cnt), int(op)
+        for i, sg in enumerate(segments):
+            a.seg_offset[i], a.seg_count[i], a.seg_op[i] = int(sg[0]), int(sg[1]), int(sg[2])
+            if len(sg) > 3 and sg[3] and self.live_offset:    # row-sparse range (PackedGrads.segments)
+                a.seg_row_floats[i], a.seg_row0[i] = int(sg[3]), int(sg[4])
+        a.live_offset = int(self.live_offset)
         for k in range(self.world):
             a.bufs[k], a.signals[k] = self._bufs[k], self._sigs[k]
         a.stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -169,7 +175,7 @@ class MulticastAllReduce:
 
     SIGNAL_OFFSET = 4096   # bytes into torch's signal pad (its own barrier uses the first words)
 
-    def __init__(self, n_sum: int, n_max: int, device, group=None, device_epoch: bool = False):
+    def __init__(self, n_sum: int, n_max: int, device, group=None, device_epoch: bool = False, n_tail: int = 0):
         import ctypes as C
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
@@ -180,10 +186,11 @@ class MulticastAllReduce:
         assert self.world <= 8, "one NVSwitch box: at most 8 ranks"
         self.n_sum, self.n_max, self.device, self.epoch = n_sum, n_max, torch.device(device), 0
         self.device_epoch = device_epoch
+        self.n_tail, self.live_offset = int(n_tail), 0
         err = None
         try:
             with torch.cuda.device(self.device):
-                self.buffer = symm_mem.empty(n_sum + n_max, dtype=torch.float32, device=self.device)
+                self.buffer = symm_mem.empty(n_sum + n_max + n_tail, dtype=torch.float32, device=self.device)
                 self._hdl = symm_mem.rendezvous(self.buffer, group)
             self._mc = int(self._hdl.multicast_ptr)
             if not self._mc:
@@ -214,8 +221,11 @@ class MulticastAllReduce:
         a = _lib.MCArgs()
         a.rank, a.world, a.epoch, a.n_segments = self.rank, self.world, 0 if self.device_epoch else self.epoch, len(segments)
         a.mc_buffer = self._mc
-        for i, (off, cnt, op) in enumerate(segments):
-            a.seg_offset[i], a.seg_count[i], a.seg_op[i] = int(off), int(cnt), int(op)
+        for i, sg in enumerate(segments):
+            a.seg_offset[i], a.seg_count[i], a.seg_op[i] = int(sg[0]), int(sg[1]), int(sg[2])
+            if len(sg) > 3 and sg[3] and self.live_offset:    # row-sparse range (PackedGrads.segments)
+                a.seg_row_floats[i], a.seg_row0[i] = int(sg[3]), int(sg[4])
+        a.live_offset = int(self.live_offset)
         for k in range(self.world):
             a.signals[k] = self._sigs[k]
         a.stream = torch.cuda.current_stream(self.device).cuda_stream

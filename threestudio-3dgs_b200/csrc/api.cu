@@ -435,7 +435,7 @@ int b200splat_p2p_allreduce(const b200splat_p2p_args* a) {
     P2PTab t;
     t.rank = a->rank, t.world = a->world, t.epoch = a->epoch;
     t.n_seg = a->n_segments, t.seg_max_mask = 0u;
-    for (int i = 0; i < P2P_MAX_SEG; ++i) t.seg_first4[i] = t.seg_n4[i] = 0;
+    for (int i = 0; i < P2P_MAX_SEG; ++i) t.seg_first4[i] = t.seg_n4[i] = 0, t.seg_row4[i] = 0, t.seg_row0[i] = 0;
     for (int i = 0; i < a->n_segments; ++i) {
         if (a->seg_offset[i] < 0 || a->seg_count[i] < 0 || (a->seg_offset[i] & 3) || (a->seg_count[i] & 3))
             return fail(B200SPLAT_ERR_INVALID, "segment %d: offset and count must be non-negative multiples of 4", i);
@@ -443,7 +443,15 @@ int b200splat_p2p_allreduce(const b200splat_p2p_args* a) {
             return fail(B200SPLAT_ERR_INVALID, "segment %d: unknown op %d", i, a->seg_op[i]);
         t.seg_first4[i] = a->seg_offset[i] / 4, t.seg_n4[i] = a->seg_count[i] / 4;
         if (a->seg_op[i] == B200SPLAT_P2P_MAX) t.seg_max_mask |= 1u << i;
+        const int rf = a->seg_row_floats[i];
+        if (rf != 0) {
+            if (rf < 0 || (rf & 3) || a->seg_op[i] != B200SPLAT_P2P_SUM || (a->seg_count[i] % rf) != 0 ||
+                a->seg_row0[i] < 0 || (a->seg_row0[i] & 3) || a->live_offset < 0 || (a->live_offset & 3))
+                return fail(B200SPLAT_ERR_INVALID, "segment %d: bad row-sparse description", i);
+            t.seg_row4[i] = rf / 4, t.seg_row0[i] = a->seg_row0[i];
+        }
     }
+    t.live_off = a->live_offset;
     for (int k = 0; k < P2P_MAX_RANKS; ++k) {
         t.bufs[k] = k < a->world ? reinterpret_cast<float*>(a->bufs[k]) : nullptr;
         t.signals[k] = k < a->world ? reinterpret_cast<uint32_t*>(a->signals[k]) : nullptr;
@@ -465,7 +473,7 @@ int b200splat_mc_allreduce(const b200splat_mc_args* a) {
     P2PTab t;
     t.rank = a->rank, t.world = a->world, t.epoch = a->epoch;
     t.n_seg = a->n_segments, t.seg_max_mask = 0u;
-    for (int i = 0; i < P2P_MAX_SEG; ++i) t.seg_first4[i] = t.seg_n4[i] = 0;
+    for (int i = 0; i < P2P_MAX_SEG; ++i) t.seg_first4[i] = t.seg_n4[i] = 0, t.seg_row4[i] = 0, t.seg_row0[i] = 0;
     for (int i = 0; i < a->n_segments; ++i) {
         if (a->seg_offset[i] < 0 || a->seg_count[i] < 0 || (a->seg_offset[i] & 3) || (a->seg_count[i] & 3))
             return fail(B200SPLAT_ERR_INVALID, "segment %d: offset and count must be non-negative multiples of 4", i);
@@ -473,7 +481,15 @@ int b200splat_mc_allreduce(const b200splat_mc_args* a) {
             return fail(B200SPLAT_ERR_INVALID, "segment %d: unknown op %d", i, a->seg_op[i]);
         t.seg_first4[i] = a->seg_offset[i] / 4, t.seg_n4[i] = a->seg_count[i] / 4;
         if (a->seg_op[i] == B200SPLAT_P2P_MAX) t.seg_max_mask |= 1u << i;
+        const int rf = a->seg_row_floats[i];
+        if (rf != 0) {
+            if (rf < 0 || (rf & 3) || a->seg_op[i] != B200SPLAT_P2P_SUM || (a->seg_count[i] % rf) != 0 ||
+                a->seg_row0[i] < 0 || (a->seg_row0[i] & 3) || a->live_offset < 0 || (a->live_offset & 3))
+                return fail(B200SPLAT_ERR_INVALID, "segment %d: bad row-sparse description", i);
+            t.seg_row4[i] = rf / 4, t.seg_row0[i] = a->seg_row0[i];
+        }
     }
+    t.live_off = a->live_offset;
     for (int k = 0; k < P2P_MAX_RANKS; ++k) {
         t.bufs[k] = nullptr;
         t.signals[k] = k < a->world ? reinterpret_cast<uint32_t*>(a->signals[k]) : nullptr;
@@ -791,6 +807,7 @@ int b200splat_backward_batched(const b200splat_batch_backward_args* a) {
         vt.grad2d = reinterpret_cast<float*>(a->scratch[v]);
         vt.dL_dmeans2D = a->dL_dmeans2D ? a->dL_dmeans2D[v] : nullptr;
     }
+    tab.live_map = a->live_map;
     return backward_run(tab, a->means3D, a->scales, a->rotations, a->shs, nullptr, a->dL_dmeans3D, a->dL_dshs,
                         a->dL_dcolors, a->dL_dopacity, a->dL_dscales, a->dL_drotations, nullptr, a->stat_grad_accum,
                         a->stat_denom, a->stat_max_radii, a->accumulate, a->cams[0].debug, true, st, a->scratch_clean != 0,

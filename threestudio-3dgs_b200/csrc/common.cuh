@@ -130,6 +130,7 @@ struct BatchTab {
     int clean_scratch;         // preprocess backward zeroes every grad2d record it has read (self-cleaning scratch)
     int n_extra;               // 0..4 extra per-Gaussian feature channels rendered next to the colour
     const float4* ext4;        // [P] the extra features padded to 16 B (view independent; lives in view 0's geometry)
+    uint8_t* live_map;         // optional [P]: preprocess backward's scan writes 1 for a Gaussian with a gradient, else 0
     uint32_t* tile_order;      // [V * T] entries (view * T + tile), longest list first
     uint32_t* block_order;     // [4 + V * T * 8]: count, then the batch's non-empty 8x4 blocks ((view * T + tile) * 8 + block),
                                // most list entries to walk first: the work items of render backward
@@ -249,6 +250,9 @@ struct P2PTab {
     int n_seg;                         // disjoint float4 ranges reduced by this call
     int64_t seg_first4[P2P_MAX_SEG], seg_n4[P2P_MAX_SEG];
     uint32_t seg_max_mask;             // bit i: segment i is max-reduced (else summed)
+    int seg_row4[P2P_MAX_SEG];         // > 0: row-sparse SUM segment, float4s per row
+    int64_t seg_row0[P2P_MAX_SEG];     // live-map index of the segment's first row
+    int64_t live_off;                  // byte offset of the live map (one byte per index) in every rank's buffer
     float* bufs[P2P_MAX_RANKS];        // every rank's buffer (own + IPC-mapped peers)
     uint32_t* signals[P2P_MAX_RANKS];  // every rank's signal words
 };

@@ -160,10 +160,128 @@ __device__ __forceinline__ void reduce_slice8(const P2PTab& t, int64_t first8, i
     }
 }
 
+// ---- the same exchange through the NVSwitch multicast address of the buffers ---------------------------------------
+// multimem.ld_reduce: one load whose value is the switch's reduction of the word at that offset in every bound buffer;
+// multimem.st: one store the switch replicates into every bound buffer.
+__device__ __forceinline__ float4 mc_ld_add4(const float* p) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ void mc_st4(float* p, const float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t mc_ld_max_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.max.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mc_st_u32(uint32_t* p, uint32_t v) {
+    asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ uint32_t mc_ld_add_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// Row-sparse SUM segment: rows of `row4` float4s, row j = live-map index row0 + j.  Most Gaussians of a dense scene
+// carry no gradient on any rank (preprocess backward's scan knows, and writes one byte per Gaussian into the live map
+// next to the packed buffer): their rows are zero everywhere and stay untouched.  Rank r owns the r-th slice of the
+// ROWS; a CTA takes a contiguous run of them in pieces of SP_ROWS rows: (1) union of the ranks' live bytes (16-byte
+// loads: 16 rows each), compacted into a shared-memory list; (2) the float4s of the listed rows are loaded from all
+// ranks in rank order, summed and stored to all ranks, as in reduce_slice.  MC: the union is ONE
+// multimem.ld_reduce.add.u32 per four rows (the switch adds the ranks' bytes; at most 8 ranks, no carry).
+constexpr int SP_ROWS = 2048;
+template <bool MC>
+__device__ __forceinline__ void reduce_rows(const P2PTab& t, float* mc, int64_t first4, int64_t n4, int row4,
+                                            int64_t row0, uint16_t* s_list, uint32_t* s_count) {
+    const int64_t rows = n4 / row4;
+    const int64_t lo = rows * t.rank / t.world / 16 * 16;                              // slices on 16-row boundaries
+    const int64_t hi = t.rank + 1 == t.world ? rows : rows * (t.rank + 1) / t.world / 16 * 16;
+    const int64_t per_cta = ((hi - lo + gridDim.x - 1) / gridDim.x + 15) / 16 * 16;
+    const int64_t c0 = lo + (int64_t)blockIdx.x * per_cta, c1 = min(hi, c0 + per_cta);
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int64_t p0 = c0; p0 < c1; p0 += SP_ROWS) {
+        const int n_rows = (int)min((int64_t)SP_ROWS, c1 - p0);
+        if (tid == 0) *s_count = 0;
+        __syncthreads();
+        // (1) union of the live bytes, 4 rows per thread and step
+        for (int qb = (tid & ~31) * 4; qb < n_rows; qb += blockDim.x * 4) {   // warp-uniform bound (shuffles below)
+            const int q = qb + lane * 4;
+            const int64_t idx = row0 + p0 + q;     // multiple of 4 (row0, lo, per_cta, SP_ROWS, q all are)
+            uint32_t u = 0;
+            if (q < n_rows) {
+                if (MC) {
+                    u = mc_ld_add_u32(reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(mc) + t.live_off + idx));
+                } else {
+                    for (int k = 0; k < t.world; ++k)
+                        u |= ld_cg_u32(reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(t.bufs[k]) + t.live_off + idx));
+                }
+            }
+            // rows q .. q+3 (beyond n_rows only in the segment's last piece: their bytes are padding zeros or belong
+            // to rows of another piece -- mask them off)
+            uint32_t m = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (((u >> (8 * b)) & 0xffu) && q + b < n_rows) m |= 1u << b;
+            const int cnt = __popc(m);
+            // warp-aggregated append
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int x = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += x;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            uint32_t base = 0;
+            if (lane == 31 && total) base = atomicAdd(s_count, (uint32_t)total);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            uint32_t pos = base + (uint32_t)(incl - cnt);
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if ((m >> b) & 1u) s_list[pos++] = (uint16_t)(q + b);
+        }
+        __syncthreads();
+        // (2) the listed rows.  (The list is in no particular order: every element is handled independently.)
+        const int64_t work = (int64_t)(*s_count) * row4;
+        for (int64_t j = tid; j < work; j += blockDim.x) {
+            const int r = (int)(j / row4), part = (int)(j % row4);
+            const int64_t i = first4 + (p0 + s_list[r]) * row4 + part;
+            float4 acc;
+            if (MC) {
+                acc = mc_ld_add4(mc + 4 * i);
+                mc_st4(mc + 4 * i, acc);
+            } else {
+                acc = ld_cg4(reinterpret_cast<const float4*>(t.bufs[0]) + i);
+                for (int k = 1; k < t.world; ++k) {
+                    const float4 v = ld_cg4(reinterpret_cast<const float4*>(t.bufs[k]) + i);
+                    acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+                }
+                for (int k = 0; k < t.world; ++k) st_cg4(reinterpret_cast<float4*>(t.bufs[k]) + i, acc);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 template <int U>
 __global__ void __launch_bounds__(256)
 p2p_allreduce_kernel(const __grid_constant__ P2PTab t, int mode) {
     __shared__ int s_flag;
+    __shared__ uint16_t s_list[SP_ROWS];
+    __shared__ uint32_t s_count;
     const int tid = threadIdx.x;
     const uint32_t epoch = call_epoch(t);
     // phase 0
@@ -177,6 +295,10 @@ p2p_allreduce_kernel(const __grid_constant__ P2PTab t, int mode) {
         for (int sgm = 0; sgm < t.n_seg; ++sgm) {
             const int64_t f4 = t.seg_first4[sgm], n4 = t.seg_n4[sgm];
             const bool is_max = (t.seg_max_mask >> sgm) & 1u;
+            if (t.seg_row4[sgm] > 0 && mode == 0) {
+                reduce_rows<false>(t, nullptr, f4, n4, t.seg_row4[sgm], t.seg_row0[sgm], s_list, &s_count);
+                continue;
+            }
             if (mode == 0 && aligned32 && ((f4 | n4) & 1) == 0) {
                 if (is_max) reduce_slice8<true, (U > 2 ? U / 2 : 1)>(t, f4 / 2, n4 / 2);
                 else reduce_slice8<false, (U > 2 ? U / 2 : 1)>(t, f4 / 2, n4 / 2);
@@ -210,35 +332,12 @@ p2p_allreduce_kernel(const __grid_constant__ P2PTab t, int mode) {
     }
 }
 
-// ---- the same exchange through the NVSwitch multicast address of the buffers ---------------------------------------
-// multimem.ld_reduce: one load whose value is the switch's reduction of the word at that offset in every bound buffer;
-// multimem.st: one store the switch replicates into every bound buffer.
-__device__ __forceinline__ float4 mc_ld_add4(const float* p) {
-    float4 v;
-    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                 : "l"(p)
-                 : "memory");
-    return v;
-}
-__device__ __forceinline__ void mc_st4(float* p, const float4 v) {
-    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
-                 "f"(v.w)
-                 : "memory");
-}
-__device__ __forceinline__ uint32_t mc_ld_max_u32(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("multimem.ld_reduce.relaxed.sys.global.max.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void mc_st_u32(uint32_t* p, uint32_t v) {
-    asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
 template <int U>
 __global__ void __launch_bounds__(256)
 mc_allreduce_kernel(const __grid_constant__ P2PTab t, float* mc) {
     __shared__ int s_flag;
+    __shared__ uint16_t s_list[SP_ROWS];
+    __shared__ uint32_t s_count;
     const int tid = threadIdx.x;
     const uint32_t epoch = call_epoch(t);
     // phase 0: "my buffer is complete" to every peer; wait for theirs
@@ -251,6 +350,10 @@ mc_allreduce_kernel(const __grid_constant__ P2PTab t, float* mc) {
         const int64_t stride = (int64_t)gridDim.x * blockDim.x;
         for (int sgm = 0; sgm < t.n_seg; ++sgm) {
             const int64_t first4 = t.seg_first4[sgm], n4 = t.seg_n4[sgm];
+            if (t.seg_row4[sgm] > 0) {
+                reduce_rows<true>(t, mc, first4, n4, t.seg_row4[sgm], t.seg_row0[sgm], s_list, &s_count);
+                continue;
+            }
             const int64_t lo = first4 + n4 * t.rank / t.world, hi = first4 + n4 * (t.rank + 1) / t.world;   // my slice
             if ((t.seg_max_mask >> sgm) & 1u) {
                 uint32_t* w = reinterpret_cast<uint32_t*>(mc);

@@ -209,6 +209,8 @@ preprocess_backward_scan_kernel(const __grid_constant__ BatchTab tab, float* __r
                 tab.v[v].touched[idx] = 0;
             }
         }
+        // the row-sparse exchange's live map; an accumulating call (a later view group of the same step) only adds
+        if (tab.live_map && (!ACC || live)) tab.live_map[idx] = live ? (uint8_t)1 : (uint8_t)0;
         if (stat_denom && vis) stat_denom[idx] = sd + (float)__popc(vis);
         if (stat_max_radii && vis) stat_max_radii[idx] = fmaxf(sm, (float)max_radius);
         if (!ACC) {
