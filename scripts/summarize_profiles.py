@@ -71,11 +71,12 @@ with open(f"{out_dir}/{tag}_ncu_full_summary.md", "w") as f:
                 f"{g('smsp__inst_executed.sum') / 1e6:.1f} M | {', '.join(f'{a} {b:.1f}' for a, b in st[:3])} |\n")
         traffic.setdefault(name, []).append(rd + wr)
 # family traffic per launch group (one step of the view batch): all kernels of the family summed
-fam_of = [("preprocess_backward_kernel", "preprocess_bwd"), ("preprocess_kernel", "preprocess"),
-          ("scan_lookback_kernel", "scan"), ("duplicate_kernel", "duplicate"), ("radix_histogram_kernel", "sort"),
-          ("onesweep_pass_kernel", "sort"), ("tile_partition_kernel", "sort"), ("tile_ranges", "ranges"),
+fam_of = [("preprocess_backward", "preprocess_bwd"), ("preprocess_kernel", "preprocess"), ("pair_count_kernel", "preprocess"),
+          ("scan_lookback_kernel", "scan"), ("scan_duplicate_kernel", "duplicate"), ("duplicate_kernel", "duplicate"),
+          ("radix_histogram_kernel", "sort"), ("onesweep_pass_kernel", "sort"), ("tile_partition", "sort"),
+          ("partition_offsets_kernel", "sort"), ("tile_ranges", "ranges"),
           ("tile_order_kernel", "ranges"), ("render_forward_kernel", "render_fwd"),
-          ("render_backward_kernel", "render_bwd")]
+          ("block_scatter_kernel", "render_bwd"), ("render_backward_kernel", "render_bwd")]
 steps_captured = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 tj = {}
 for k, v in traffic.items():
