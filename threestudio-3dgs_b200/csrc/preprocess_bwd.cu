@@ -237,13 +237,24 @@ preprocess_backward_scan_kernel(const __grid_constant__ BatchTab tab, float* __r
         const int n4 = rows * (3 * M / 4);
         for (int k = lane; k < n4; k += 32) d4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    // append the Gaussians that have work (one atomic per warp)
+    // append the Gaussians that have work: ONE atomic per CTA (one per warp -- 31 K returning atomics on one address per
+    // launch -- was half of this kernel's stall samples)
+    __shared__ uint32_t s_wcnt[8], s_base;
+    const int warp = threadIdx.x >> 5;
     const uint32_t m = __ballot_sync(0xffffffffu, live != 0);
-    if (m) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(live_count, (uint32_t)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (live) live_list[base + __popc(m & ((1u << lane) - 1u))] = make_uint2((uint32_t)idx, live | (clamp3 << 8));
+    if (lane == 0) s_wcnt[warp] = (uint32_t)__popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) total += s_wcnt[w];
+        s_base = total ? atomicAdd(live_count, total) : 0u;
+    }
+    __syncthreads();
+    if (live) {
+        uint32_t base = s_base;
+        for (int w = 0; w < warp; ++w) base += s_wcnt[w];
+        live_list[base + __popc(m & ((1u << lane) - 1u))] = make_uint2((uint32_t)idx, live | (clamp3 << 8));
     }
 }
 
@@ -291,6 +302,9 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
     const uint32_t vis = item.y & 0xffu;           // from here on "vis" = the views with a gradient
     const uint32_t clamp3 = item.y >> 8;           // 3 clamp bits per view
     const int src = threadIdx.x;                   // slot column of this thread
+    // the running statistic is read now and written at the end (a read-modify-write at the end of the chain stalled
+    // every thread for a DRAM round trip: 14 % of the kernel's attributed stall samples)
+    const float ga_prev = stat_grad_accum ? stat_grad_accum[idx] : 0.f;
     // asynchronous copies into the thread's own shared-memory slots: group 0 = the live views' 48-byte gradient
     // records, group 1 = the SH row.  They land while Sigma3 / the per-view chains run.
     for (int v = 0; v < V; ++v) {
@@ -558,7 +572,7 @@ preprocess_backward_kernel(const __grid_constant__ BatchTab tab, const float* __
     put<ACC>(dL_dopacity + idx, dop);
     // fused densification statistics (geometry/gaussian_base.py:815-819, 846-851)
     // (denominator and largest radius: the scan kernel; a view without a gradient adds a zero norm)
-    if (stat_grad_accum) stat_grad_accum[idx] += st_norm;
+    if (stat_grad_accum) stat_grad_accum[idx] = ga_prev + st_norm;
     }   // work-list loop
 }
 
