@@ -608,6 +608,9 @@ render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
                 // ---- phase 2: the recurrence, in list order; each survivor's partial gradients go to this lane's row
 #pragma unroll
                 for (int k = 0; k < ILP; ++k) {
+                    // a survivor that hit no pixel of the block (warp-uniform: anyhit is a vote) leaves T and S as they
+                    // are and contributes nothing: its row is not written and its column is neither summed nor sent
+                    if (!((hit_g >> k) & 1u)) continue;
                     T *= inv1m[k];
                     const float w = a_h[k] * T;
                     const float dL_da = fmaf(dot[k], T, -(S * inv1m[k]));
@@ -648,7 +651,7 @@ render_backward_kernel(const __grid_constant__ BatchTab tab, int sel) {
             if (hit_g) {
                 // ---- phase 3: column sums over the 32 rows, one vector reduction per float4 of a record -----------
                 float2 s0 = make_float2(0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;   // (xy, zw) of the even / the odd rows
-                if (red_active) {
+                if (red_active && ((hit_g >> red_k) & 1u)) {
 #pragma unroll
                     for (int r = 0; r < 16; r += 2) {
                         const float4 t = r < 12 ? red_src[r * (RS / 4)] : red_src2[(r - 12) * (RS / 4)];
