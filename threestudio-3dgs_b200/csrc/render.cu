@@ -13,19 +13,20 @@
 //    warp kept its registers until the slowest one was done.  Independent warps stop as soon as their own
 //    32 pixels are saturated (forward) / start at their own last contributor (backward), and the SM back-
 //    fills with the next work item;
-//  * a warp consumes its tile's Gaussian list in batches of 64 entries through a 3-stage shared-memory
+//  * a backward warp consumes its tile's Gaussian list in batches of 64 entries through a 2-stage shared-memory
 //    ring behind mbarriers: each lane gathers two 48-byte records per batch (common.cuh REC layout) either
-//    with bulk async copies (cp.async.bulk -> UBLKCP, complete_tx on the mbarrier) or with 16-byte
-//    cp.async (LDGSTS) whose completion arrives on the same mbarrier, two batches ahead of the blend;
+//    with 16-byte cp.async (LDGSTS, default) whose completion arrives on the stage's mbarrier, or with bulk async
+//    copies (cp.async.bulk -> UBLKCP, complete_tx on the mbarrier; measured 20 % slower for 48-byte granules);
 //  * warp-cooperative culling: for every 32 staged entries, lane l bounds entry l's best-case alpha
 //    over the warp's 8x4 pixel rectangle (exact minimum of the conic quadratic over the rectangle
 //    edges); only entries that can reach alpha >= 1/255 somewhere in the rectangle are evaluated by
 //    the 32 pixels.  Culling is conservative, so the set of blended (pixel, Gaussian) pairs -- and
 //    therefore the image, n_contrib and the gradients -- are exactly those of the unculled loop;
-//  * forward terminates a tile as soon as every pixel is saturated (T' < 1e-4);
-//  * backward walks back to front starting at the tile's largest n_contrib, and reduces the 10
-//    per-Gaussian partial gradients across the warp with a 12-shuffle transposed butterfly before
-//    one 10-lane global atomic per (warp, Gaussian).
+//  * forward terminates a tile as soon as every pixel is saturated (T' < 1e-4), and enters each of its 8x4 blocks
+//    into the counting sort of the backward's work order (longest walk first);
+//  * backward walks back to front starting at the block's largest n_contrib, with ONE scalar suffix-sum recurrence
+//    per pixel, and reduces the 10 per-Gaussian partial gradients across the warp through a shared-memory
+//    transpose (see K7 below) before three 16-byte vector atomics per (warp, Gaussian).
 #include "common.cuh"
 
 #include <atomic>

@@ -1,5 +1,6 @@
-// K2 inclusive scan (decoupled look-back), K4 onesweep LSD radix sort of (u64 key, u32 value) pairs,
-// K5 identifyTileRanges + longest-list-first tile order.  Hand-written; no CUB.
+// K2 inclusive scan (decoupled look-back), K2+K3 fused scan + duplicateWithKeys, K4 onesweep LSD radix sort of (u64 key,
+// u32 value) pairs, K4d look-back-free pair partition (count matrix -> offsets -> partition), K5 identifyTileRanges +
+// longest-list-first tile order, block order of render backward.  Hand-written; no CUB.
 //
 // Replaces cub::DeviceScan::InclusiveSum, cub::DeviceRadixSort::SortPairs and
 // rasterizer_impl.cu identifyTileRanges as called by upstream CudaRasterizer::Rasterizer::forward
