@@ -525,7 +525,8 @@ def test_full_size_properties_headline_workload():
 
 @pytest.mark.parametrize("P,H,W,scale_mul", [(20000, 256, 256, 6.0),     # huge splats: > 8 partition tiles per CTA
                                               (50000, 512, 512, 1.0),     # 1024 tiles: every bin of the wide pass
-                                              (700, 64, 48, 1.0)])        # less than one partition tile
+                                              (700, 64, 48, 1.0),         # less than one partition tile
+                                              (60000, 1024, 1024, 1.5)])  # 4096 tiles: fused kernel + two 8-bit passes
 def test_batched_binning_matches_single_view_bit_for_bit(P, H, W, scale_mul):
     """The batched forward's binning (depth sort -> fused scan + duplicateWithKeys with the per-(partition tile, image
     tile) count matrix -> partition offsets -> look-back-free partition) against the single-view pipeline (stand-alone
